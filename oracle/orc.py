@@ -1,0 +1,331 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes bindings of the CPU oracle (oracle/liborc.so, restated reference arithmetic) and of the
+reference's own FAST sources compiled into oracle/_ref/libfast_ref.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module. The product package (svo_pro_universal_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_LEVELS = 8
+MAX_CAMS = 4
+
+u8p = C.POINTER(C.c_uint8)
+f64p = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int)
+i16p = C.POINTER(C.c_short)
+
+
+class Corner(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("level", C.c_int), ("score", C.c_float), ("angle", C.c_float)]
+
+
+class Frame(C.Structure):
+    _fields_ = [
+        ("level_data", u8p * MAX_LEVELS),
+        ("level_cols", C.c_int * MAX_LEVELS),
+        ("level_rows", C.c_int * MAX_LEVELS),
+        ("level_step", C.c_int * MAX_LEVELS),
+        ("n_levels", C.c_int),
+        ("cam", C.c_double * 8),
+        ("width", C.c_int),
+        ("height", C.c_int),
+        ("distortion", C.c_int),
+        ("T_cam_imu", C.c_double * 7),
+        ("T_imu_world", C.c_double * 7),
+        ("n_features", C.c_int),
+        ("px", f64p),
+        ("f", f64p),
+        ("depth", f64p),
+        ("eligible", u8p),
+    ]
+
+
+class AlignOptions(C.Structure):
+    _fields_ = [
+        ("max_level", C.c_int), ("min_level", C.c_int),
+        ("estimate_illumination_gain", C.c_int), ("estimate_illumination_offset", C.c_int),
+        ("use_distortion_jacobian", C.c_int), ("robustification", C.c_int),
+        ("weight_scale", C.c_double),
+        ("max_iter", C.c_int),
+        ("eps", C.c_double),
+        ("alpha_init", C.c_double), ("beta_init", C.c_double),
+        ("have_prior", C.c_int),
+        ("prior_T", C.c_double * 7),
+        ("prior_alpha", C.c_double), ("prior_beta", C.c_double),
+        ("lambda_rot", C.c_double), ("lambda_trans", C.c_double),
+        ("lambda_alpha", C.c_double), ("lambda_beta", C.c_double),
+    ]
+
+
+class AlignResult(C.Structure):
+    _fields_ = [
+        ("n_tracked", C.c_int),
+        ("T_icur_iref", C.c_double * 7),
+        ("alpha", C.c_double), ("beta", C.c_double), ("chi2", C.c_double),
+        ("H", C.c_double * 64),
+        ("iters", C.c_int * MAX_LEVELS),
+        ("T_f_w", (C.c_double * 7) * MAX_CAMS),
+        ("stop", C.c_int),
+    ]
+
+
+class Feature(C.Structure):
+    _fields_ = [("type", C.c_int), ("px", C.c_double * 2), ("f", C.c_double * 3), ("grad", C.c_double * 2),
+                ("level", C.c_int)]
+
+
+class MatcherOptions(C.Structure):
+    _fields_ = [
+        ("align_1d", C.c_int), ("align_max_iter", C.c_int),
+        ("max_epi_search_steps", C.c_int),
+        ("subpix_refinement", C.c_int), ("epi_search_edgelet_filtering", C.c_int), ("scan_on_unit_sphere", C.c_int),
+        ("epi_search_edgelet_max_angle", C.c_double),
+        ("affine_est_offset", C.c_int), ("affine_est_gain", C.c_int),
+        ("max_patch_diff_ratio", C.c_double),
+    ]
+
+
+class MatchOut(C.Structure):
+    _fields_ = [
+        ("result", C.c_int),
+        ("px_cur", C.c_double * 2),
+        ("f_cur", C.c_double * 3),
+        ("search_level", C.c_int),
+        ("A_cur_ref", C.c_double * 4),
+        ("h_inv", C.c_double),
+        ("epi_length_pyramid", C.c_double),
+        ("reject", C.c_int),
+        ("depth", C.c_double),
+        ("patch_with_border", C.c_uint8 * 100),
+    ]
+
+
+def default_align_options(**kw):
+    """SparseImgAlignOptions defaults (sparse_img_align_base.h:37-46) + getDefaultSolverOptions (…base.cpp:35-42)."""
+    o = AlignOptions()
+    o.max_level, o.min_level = 4, 1
+    o.weight_scale = 10.0
+    o.max_iter = 10
+    o.eps = 0.0005
+    for k, v in kw.items():
+        if k == "prior_T":
+            o.prior_T[:] = list(v)
+        else:
+            setattr(o, k, v)
+    return o
+
+
+def default_matcher_options(**kw):
+    """Matcher::Options defaults (src/svo_direct/include/svo/direct/matcher.h:39-54)."""
+    o = MatcherOptions()
+    o.align_1d = 0
+    o.align_max_iter = 10
+    o.max_epi_search_steps = 100
+    o.subpix_refinement = 1
+    o.epi_search_edgelet_filtering = 1
+    o.scan_on_unit_sphere = 1
+    o.epi_search_edgelet_max_angle = 0.7
+    o.affine_est_offset = 1
+    o.affine_est_gain = 0
+    o.max_patch_diff_ratio = 2.0
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def build(force=False):
+    """Compile liborc.so (and _ref/libfast_ref.so when /root/reference is present)."""
+    so = os.path.join(_HERE, "liborc.so")
+    if force or not os.path.exists(so) or os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True)
+    return so
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(_HERE, "liborc.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_create_img_pyramid.restype = C.c_size_t
+        L.orc_compute_tau.restype = C.c_double
+        L.orc_px_error_angle.restype = C.c_double
+        L.orc_compute_tau.argtypes = [f64p, f64p, C.c_double, C.c_double]
+        L.orc_px_error_angle.argtypes = [C.POINTER(Frame), C.c_double]
+        L.orc_update_filter_vogiatzis.argtypes = [C.c_double, C.c_double, C.c_double, f64p]
+        L.orc_update_filter_gaussian.argtypes = [C.c_double, C.c_double, f64p]
+        L.orc_fast_detect_features.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                               C.c_int, C.c_int, u8p, C.c_int, f64p, f64p, i32p]
+        L.orc_find_match_direct.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f64p, C.POINTER(Feature), C.c_double,
+                                            f64p, C.POINTER(MatcherOptions), C.POINTER(MatchOut)]
+        L.orc_find_epipolar_match_direct.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f64p, C.POINTER(Feature),
+                                                     C.c_double, C.c_double, C.c_double, C.POINTER(MatcherOptions),
+                                                     C.POINTER(MatchOut)]
+        L.orc_get_warp_matrix_affine.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f64p, f64p, C.c_double, f64p,
+                                                 C.c_int, f64p]
+        L.orc_update_seeds.argtypes = [C.POINTER(Frame), C.c_int, C.POINTER(Frame), f64p, C.c_int, C.POINTER(Feature),
+                                       u8p, f64p, C.c_double, C.POINTER(MatcherOptions), C.c_double, C.c_double,
+                                       C.c_int, C.c_int, C.c_int, i32p, u8p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own FAST code (None if it was never built)."""
+    global _ref
+    if _ref is None:
+        so = os.path.join(_HERE, "_ref", "libfast_ref.so")
+        if not os.path.exists(so):
+            return None
+        _ref = C.CDLL(so)
+    return _ref
+
+
+def _u8(a):
+    return a.ctypes.data_as(u8p)
+
+
+def _f64(a):
+    return a.ctypes.data_as(f64p)
+
+
+def _i32(a):
+    return a.ctypes.data_as(i32p)
+
+
+def pyramid_level_sizes(cols, rows, n_levels):
+    out = [(cols, rows)]
+    for _ in range(1, n_levels):
+        cols, rows = cols // 2, rows // 2
+        out.append((cols, rows))
+    return out
+
+
+def create_img_pyramid(img0, n_levels, mode=-1):
+    """frame_utils::createImgPyramid -> list of tight uint8 arrays (level 0 is the input)."""
+    img0 = np.ascontiguousarray(img0, dtype=np.uint8)
+    rows, cols = img0.shape
+    sizes = pyramid_level_sizes(cols, rows, n_levels)
+    total = sum(c * r for c, r in sizes[1:])
+    buf = np.zeros(max(total, 1), np.uint8)
+    lib().orc_create_img_pyramid(_u8(img0), cols, rows, n_levels, _u8(buf), mode)
+    out, off = [img0], 0
+    for c, r in sizes[1:]:
+        out.append(buf[off:off + c * r].reshape(r, c).copy())
+        off += c * r
+    return out
+
+
+def fast_detect(img, barrier, arc=10, which="orc"):
+    """Returns (xy[n,2] int16) of the segment test. which: 'orc' restatement, 'ref_sse2', 'ref_plain10', 'ref_plain9'."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = w * h
+    xy = np.zeros((cap, 2), np.int16)
+    p = xy.ctypes.data_as(i16p)
+    if which == "orc":
+        n = lib().orc_fast_detect(_u8(img), w, h, w, barrier, arc, p, cap)
+    else:
+        sel = {"ref_sse2": 0, "ref_plain10": 1, "ref_plain9": 2}[which]
+        n = ref_lib().ref_fast_detect(_u8(img), w, h, w, barrier, sel, p, cap)
+    return xy[:n].copy()
+
+
+def fast_score10(img, xy, threshold, which="orc"):
+    img = np.ascontiguousarray(img, np.uint8)
+    xy = np.ascontiguousarray(xy, np.int16)
+    n = len(xy)
+    s = np.zeros(max(n, 1), np.int32)
+    fn = lib().orc_fast_score10 if which == "orc" else ref_lib().ref_fast_score10
+    fn(_u8(img), img.shape[1], xy.ctypes.data_as(i16p), n, threshold, _i32(s))
+    return s[:n]
+
+
+def fast_nonmax3x3(xy, scores, which="orc"):
+    xy = np.ascontiguousarray(xy, np.int16)
+    scores = np.ascontiguousarray(scores, np.int32)
+    n = len(xy)
+    idx = np.zeros(max(n, 1), np.int32)
+    fn = lib().orc_fast_nonmax3x3 if which == "orc" else ref_lib().ref_fast_nonmax3x3
+    m = fn(xy.ctypes.data_as(i16p), _i32(scores), n, _i32(idx))
+    return idx[:m].copy()
+
+
+def fast_detector(img0, n_levels=5, pyr_mode=-1, threshold=10, border=8, min_level=0, max_level=2, cell_size=30,
+                  occupancy=None):
+    """feature_detection_utils::fastDetector on a fresh pyramid -> structured array of per-cell Corners."""
+    img0 = np.ascontiguousarray(img0, np.uint8)
+    rows, cols = img0.shape
+    n_cols = -(-cols // cell_size)
+    n_rows = -(-rows // cell_size)
+    corners = (Corner * (n_cols * n_rows))()
+    occ = None if occupancy is None else _u8(np.ascontiguousarray(occupancy, np.uint8))
+    lib().orc_fast_detector(_u8(img0), cols, rows, n_levels, pyr_mode, threshold, border, min_level, max_level, cell_size,
+                            occ, corners)
+    dt = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4"), ("angle", "<f4")])
+    return np.frombuffer(corners, dtype=dt).copy()
+
+
+def make_frame(pyr, cam, T_cam_imu=None, T_imu_world=None, px=None, f=None, depth=None, eligible=None, keep=None):
+    """Build an orc Frame struct over numpy level arrays. `cam` = dict(fx,fy,cx,cy,k1,k2,p1,p2,width,height,distortion).
+    `keep` is a list that receives references keeping the numpy buffers alive."""
+    fr = Frame()
+    fr.n_levels = len(pyr)
+    for i, lv in enumerate(pyr):
+        assert lv.dtype == np.uint8 and lv.flags["C_CONTIGUOUS"]
+        fr.level_data[i] = _u8(lv)
+        fr.level_cols[i] = lv.shape[1]
+        fr.level_rows[i] = lv.shape[0]
+        fr.level_step[i] = lv.strides[0]
+    fr.cam[:] = [cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam.get("k1", 0.0), cam.get("k2", 0.0), cam.get("p1", 0.0),
+                 cam.get("p2", 0.0)]
+    fr.width, fr.height, fr.distortion = cam["width"], cam["height"], cam.get("distortion", 0)
+    ident = [1.0, 0, 0, 0, 0, 0, 0]
+    fr.T_cam_imu[:] = list(T_cam_imu) if T_cam_imu is not None else ident
+    fr.T_imu_world[:] = list(T_imu_world) if T_imu_world is not None else ident
+    bufs = [pyr]
+    if px is not None:
+        px = np.ascontiguousarray(px, np.float64)
+        f = np.ascontiguousarray(f, np.float64)
+        depth = np.ascontiguousarray(depth, np.float64)
+        n = len(depth)
+        eligible = np.ones(n, np.uint8) if eligible is None else np.ascontiguousarray(eligible, np.uint8)
+        fr.n_features = n
+        fr.px, fr.f, fr.depth, fr.eligible = _f64(px), _f64(f), _f64(depth), _u8(eligible)
+        bufs += [px, f, depth, eligible]
+    if keep is not None:
+        keep.append(bufs)
+    else:
+        fr._keep = bufs
+    return fr
+
+
+def sparse_align(ref_frames, cur_frames, opt):
+    """SparseImgAlign::run on one bundle (lists of Frame structs)."""
+    n = len(ref_frames)
+    R = (Frame * n)(*ref_frames)
+    Cc = (Frame * n)(*cur_frames)
+    res = AlignResult()
+    lib().orc_sparse_align(n, R, Cc, C.byref(opt), C.byref(res))
+    return res
+
+
+def sparse_align_batch(ref_frames, cur_frames, n_cams, opt, n_threads=1):
+    B = len(ref_frames) // n_cams
+    R = (Frame * len(ref_frames))(*ref_frames)
+    Cc = (Frame * len(cur_frames))(*cur_frames)
+    res = (AlignResult * B)()
+    lib().orc_sparse_align_batch(B, n_cams, R, Cc, C.byref(opt), res, n_threads)
+    return res

@@ -1,0 +1,156 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY.
+ * C interface of the CPU oracle (liborc.so), loaded by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs through ctypes. The product never links it.
+ * All pointers are host pointers. Transformations are 7 doubles (qw qx qy qz tx ty tz).
+ */
+#ifndef ORC_CAPI_H_
+#define ORC_CAPI_H_
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_LEVELS 8
+#define ORC_MAX_CAMS 4
+
+typedef struct {
+  int x, y, level;
+  float score, angle;
+} orc_corner;
+
+/* One camera frame: image pyramid (tight or strided), camera model, poses and (for ref frames of
+ * sparse alignment) the feature SoA run() reads. */
+typedef struct {
+  const uint8_t* level_data[ORC_MAX_LEVELS];
+  int level_cols[ORC_MAX_LEVELS];
+  int level_rows[ORC_MAX_LEVELS];
+  int level_step[ORC_MAX_LEVELS];
+  int n_levels;
+  double cam[8]; /* fx fy cx cy k1 k2 p1 p2 */
+  int width, height, distortion; /* distortion: 0 none, 1 radtan */
+  double T_cam_imu[7];
+  double T_imu_world[7];
+  int n_features;
+  const double* px;        /* [n][2] */
+  const double* f;         /* [n][3] */
+  const double* depth;     /* [n]    */
+  const uint8_t* eligible; /* [n]    */
+} orc_frame;
+
+typedef struct {
+  int max_level, min_level;
+  int estimate_illumination_gain, estimate_illumination_offset;
+  int use_distortion_jacobian, robustification;
+  double weight_scale;
+  int max_iter;
+  double eps;
+  double alpha_init, beta_init;
+  int have_prior;
+  double prior_T[7];
+  double prior_alpha, prior_beta;
+  double lambda_rot, lambda_trans, lambda_alpha, lambda_beta;
+} orc_align_options;
+
+typedef struct {
+  int n_tracked;
+  double T_icur_iref[7];
+  double alpha, beta, chi2;
+  double H[64];
+  int iters[ORC_MAX_LEVELS]; /* evaluateError calls per level, from max_level down */
+  double T_f_w[ORC_MAX_CAMS][7];
+  int stop;
+} orc_align_result;
+
+typedef struct {
+  int type; /* svo::FeatureType value */
+  double px[2];
+  double f[3];
+  double grad[2];
+  int level;
+} orc_feature;
+
+typedef struct {
+  int align_1d, align_max_iter;
+  int max_epi_search_steps;
+  int subpix_refinement, epi_search_edgelet_filtering, scan_on_unit_sphere;
+  double epi_search_edgelet_max_angle;
+  int affine_est_offset, affine_est_gain;
+  double max_patch_diff_ratio;
+} orc_matcher_options;
+
+typedef struct {
+  int result; /* Matcher::MatchResult */
+  double px_cur[2];
+  double f_cur[3];
+  int search_level;
+  double A_cur_ref[4]; /* row-major 2x2 */
+  double h_inv;
+  double epi_length_pyramid;
+  int reject;
+  double depth;
+  uint8_t patch_with_border[100];
+} orc_match_out;
+
+/* a1 */
+void orc_half_sample(const uint8_t* in, int cols, int rows, int stride, uint8_t* out, int out_stride, int mode);
+size_t orc_create_img_pyramid(const uint8_t* img0, int cols, int rows, int n_levels, uint8_t* out_levels_1_up, int mode);
+/* a2-a4 (restated) */
+int orc_fast_detect(const uint8_t* img, int w, int h, int stride, int barrier, int arc, short* xy, int cap);
+void orc_fast_score10(const uint8_t* img, int stride, const short* xy, int n, int threshold, int* scores);
+int orc_fast_nonmax3x3(const short* xy, const int* scores, int n, int* idx_out);
+/* a5: corners_out has n_cols*n_rows entries, initialised inside to (0,0,score=threshold,0,0). */
+void orc_fast_detector(const uint8_t* img0, int cols, int rows, int n_levels, int pyr_mode, int threshold, int border,
+                       int min_level, int max_level, int cell_size, const uint8_t* occupancy, orc_corner* corners_out);
+/* a5+a6: FastDetector::detect; returns the number of features written (<= max_n). occupancy may be NULL. */
+int orc_fast_detect_features(const uint8_t* img0, int cols, int rows, int n_levels, int pyr_mode, double threshold, int border,
+                             int min_level, int max_level, int cell_size, const uint8_t* occupancy, int max_n,
+                             double* px_out, double* score_out, int* level_out);
+/* b */
+int orc_sparse_align(int n_cams, const orc_frame* ref, const orc_frame* cur, const orc_align_options* opt, orc_align_result* res);
+/* B independent problems: ref/cur hold B*n_cams frames; n_threads worker threads (one problem per task). */
+int orc_sparse_align_batch(int B, int n_cams, const orc_frame* ref, const orc_frame* cur, const orc_align_options* opt,
+                           orc_align_result* res, int n_threads);
+/* c */
+int orc_warp_affine(const double A_cur_ref[4], const uint8_t* img, int cols, int rows, int step, const double px_ref[2],
+                    int level_ref, int search_level, int halfpatch_size, uint8_t* patch);
+void orc_get_warp_matrix_affine(const orc_frame* ref, const orc_frame* cur, const double px_ref[2], const double f_ref[3],
+                                double depth_ref, const double T_cur_ref[7], int level_ref, double A_out[4]);
+int orc_get_best_search_level(const double A[4], int max_level);
+int orc_zmssd(const uint8_t* ref_patch64, const uint8_t* cur, int stride);
+int orc_align2d(const uint8_t* img, int cols, int rows, int step, const uint8_t* patch_with_border, int n_iter,
+                int est_offset, int est_gain, double px[2]);
+int orc_align1d(const uint8_t* img, int cols, int rows, int step, const double dir[2], const uint8_t* patch_with_border,
+                int n_iter, int est_offset, int est_gain, double px[2], double* h_inv);
+int orc_find_match_direct(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], const orc_feature* ftr,
+                          double ref_depth, const double px_cur_in[2], const orc_matcher_options* opt, orc_match_out* out);
+int orc_find_epipolar_match_direct(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], const orc_feature* ftr,
+                                   double d_estimate_inv, double d_min_inv, double d_max_inv, const orc_matcher_options* opt,
+                                   orc_match_out* out);
+/* M features sharing (ref, cur, T_cur_ref); threaded. */
+int orc_find_match_direct_batch(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], int M,
+                                const orc_feature* ftrs, const double* ref_depth, const double* px_cur_in,
+                                const orc_matcher_options* opt, orc_match_out* out, int n_threads);
+int orc_find_epipolar_match_direct_batch(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], int M,
+                                         const orc_feature* ftrs, const double* d_inv3 /* [M][3] est,min,max */,
+                                         const orc_matcher_options* opt, orc_match_out* out, int n_threads);
+/* d */
+int orc_update_filter_vogiatzis(double z, double tau2, double mu_range, double state[4]);
+int orc_update_filter_gaussian(double z, double tau2, double state[4]);
+void orc_update_filter_vogiatzis_batch(int n, const double* z, const double* tau2, const double* mu_range, double* state,
+                                       uint8_t* ok, int n_threads);
+double orc_compute_tau(const double T_ref_cur[7], const double f[3], double z, double px_error_angle);
+double orc_px_error_angle(const orc_frame* frame, double px_noise);
+/* S seeds of one ref frame observed, in order, by n_obs cur frames. types/states are in/out.
+ * match_results (optional) is [n_obs][S]; success (optional) is [n_obs][S]. */
+int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frames, const double* T_cur_ref /* [n_obs][7] */,
+                     int S, const orc_feature* ftrs, uint8_t* types, double* states /* [S][4] */, double seed_mu_range,
+                     const orc_matcher_options* opt, double sigma2_convergence_threshold, double px_error_angle,
+                     int check_visibility, int check_convergence, int use_vogiatzis, int* match_results, uint8_t* success,
+                     int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
