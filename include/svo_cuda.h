@@ -1,0 +1,278 @@
+/* svo_cuda.h — C ABI of the B200-native direct front-end hot path of SVO Pro.
+ *
+ * Drop-in boundary: the reference has no FFI; its front-end modules are C++ classes
+ * new-ed inside FrameHandlerBase (src/svo/src/frame_handler_base.cpp:125,135,145). The C++ facades in
+ * svo_pro_universal_b200/host/ keep those class names and signatures and call the entry points below.
+ * Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every call returns an svo_status (0 = ok, negative = error; nothing throws across the ABI);
+ *   - one svo_cuda_ctx is bound to one GPU and one CUDA stream; calls on a ctx are serialised on that
+ *     stream, different contexts are independent (one ctx per GPU per host thread);
+ *   - `mem` says where the I/O arrays of a batched call live: SVO_MEM_HOST pointers are staged through the
+ *     context (async copies on its stream) and the call returns after the outputs have landed;
+ *     SVO_MEM_DEVICE pointers are used in place and the call returns without synchronising;
+ *   - transformations are 7 doubles (qw qx qy qz tx ty tz), T_a_b maps b-coordinates into a;
+ *   - images are 8-bit, pyramids live in device memory inside an svo_cuda_pyr (a batch of frames).
+ * There is no CPU fallback: without a CUDA device svo_cuda_ctx_create fails.
+ */
+#ifndef SVO_CUDA_H_
+#define SVO_CUDA_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_MAX_LEVELS 8
+#define SVO_MAX_CAMS 4
+
+typedef enum {
+  SVO_OK = 0,
+  SVO_ERR_INVALID_ARG = -1,
+  SVO_ERR_CUDA = -2,
+  SVO_ERR_NO_DEVICE = -3,
+  SVO_ERR_OUT_OF_MEMORY = -4,
+  SVO_ERR_TOO_MANY_FEATURES = -5,
+  SVO_ERR_UNSUPPORTED = -6
+} svo_status;
+
+typedef enum { SVO_MEM_HOST = 0, SVO_MEM_DEVICE = 1 } svo_mem;
+
+typedef struct svo_cuda_ctx svo_cuda_ctx;
+typedef struct svo_cuda_pyr svo_cuda_pyr;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int svo_cuda_ctx_create(int device, svo_cuda_ctx** out);
+int svo_cuda_ctx_destroy(svo_cuda_ctx* ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream. */
+int svo_cuda_ctx_set_stream(svo_cuda_ctx* ctx, void* cuda_stream);
+int svo_cuda_ctx_synchronize(svo_cuda_ctx* ctx);
+/* Human-readable description of the last error on this context (never NULL). */
+const char* svo_cuda_last_error(const svo_cuda_ctx* ctx);
+/* Number of kernels this library has launched on the context since creation (bench bookkeeping). */
+long long svo_cuda_launch_count(const svo_cuda_ctx* ctx);
+int svo_cuda_device_count(void);
+/* sizeof() of a POD struct of this header by name (e.g. "svo_align_result"), -1 if unknown: lets bindings verify their layout. */
+int svo_cuda_sizeof(const char* struct_name);
+
+/* ---- camera model -------------------------------------------------------------------------- */
+/* Pinhole with optional radial-tangential distortion:
+ * vk::cameras::PinholeProjection<NoDistortion|RadialTangentialDistortion>
+ * (src/vikit/vikit_cameras/include/vikit/cameras/implementation/pinhole_projection.hpp:30-76,
+ *  radial_tangential_distortion.h:34-95). */
+typedef struct {
+  double fx, fy, cx, cy;
+  double k1, k2, p1, p2;
+  int width, height;
+  int distortion; /* 0 = none, 1 = radial-tangential */
+  int _pad;
+} svo_camera;
+
+/* ---- (a1) image pyramid: svo::Frame::img_pyr_ built by frame_utils::createImgPyramid
+ *      (src/svo_common/src/frame.cpp:372-386) with vk::halfSample (src/vikit/vikit_common/src/vision.cpp:19-111).
+ * halfsample_mode: -1 = the reference's x86 rule per level (SSE2 rounding formula when cols % 16 == 0, truncating
+ * mean otherwise), 0 = always the truncating mean (non-SSE build). */
+int svo_cuda_pyr_create(svo_cuda_ctx* ctx, int n_frames, int width, int height, int n_levels, int halfsample_mode,
+                        svo_cuda_pyr** out);
+int svo_cuda_pyr_destroy(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr);
+/* Copy `count` level-0 images into frames [first, first+count). src rows are src_pitch bytes apart, frames
+ * src_frame_stride bytes apart. `mem` tells whether src is host or device memory. Asynchronous on the ctx stream
+ * (host memory should be pinned for the copy to overlap). */
+int svo_cuda_pyr_upload(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count, const uint8_t* src, size_t src_pitch,
+                        size_t src_frame_stride, svo_mem mem);
+/* Build levels 1..n-1 of frames [first, first+count) from their level 0 (one fused launch for up to 5 levels). */
+int svo_cuda_pyr_build(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count);
+/* Copy one level of one frame out (tight dst_pitch >= cols). Synchronises when dst is host memory. */
+int svo_cuda_pyr_download(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, uint8_t* dst, size_t dst_pitch,
+                          svo_mem mem);
+/* Geometry + device address of a level (frame 0); frames of one level are frame_stride bytes apart. */
+int svo_cuda_pyr_level_info(const svo_cuda_pyr* pyr, int level, int* cols, int* rows, size_t* pitch, size_t* frame_stride,
+                            void** device_ptr);
+
+/* ---- (a2-a5) pyramidal FAST detector with grid-cell non-max suppression:
+ *      svo::feature_detection_utils::fastDetector (src/svo_direct/src/feature_detection_utils.cpp:145-194),
+ *      fast::fast_corner_detect_10[_sse2] / fast_corner_score_10 / fast_nonmax_3x3
+ *      (src/fast_neon/include/fast/fast.h:20-41), OccupandyGrid2D::getCellIndex
+ *      (src/svo_common/include/svo/common/occupancy_grid_2d.h:82-95). */
+typedef struct { /* svo::Corner, src/svo_direct/include/svo/direct/feature_detection_types.h:17-29 */
+  int x, y, level;
+  float score, angle;
+} svo_corner;
+
+typedef struct { /* svo::DetectorOptions subset, feature_detection_types.h:49-84 */
+  int threshold;   /* threshold_primary (FAST barrier), default 10 */
+  int border;      /* default 8 */
+  int min_level;   /* default 0 */
+  int max_level;   /* default 2 */
+  int cell_size;   /* default 30 */
+  int arc_length;  /* 10 = what the reference front-end runs on x86; 9 = the ARM/NEON variant */
+} svo_detector_options;
+
+/* Number of grid cells per frame for a w x h image: ceil(w/cell) * ceil(h/cell). */
+int svo_cuda_grid_cells(int width, int height, int cell_size, int* n_cols, int* n_rows);
+
+/* For frames [first, first+count) (pyramid already built): per-cell best corner after per-level FAST detection,
+ * scoring, 3x3 non-max, border test and occupancy skip. corners_out: [count][n_cells]; cells without a corner hold
+ * (0,0,level 0,score=threshold,angle 0), exactly what fastDetector leaves in its pre-filled `corners`.
+ * occupancy_in: [count][n_cells] bytes (non-zero = cell already holds a feature) or NULL. */
+int svo_cuda_fast_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
+                         const uint8_t* occupancy_in, svo_corner* corners_out, svo_mem mem);
+/* Fused variant: builds the pyramid of the frames and detects in one pass over level 0 (a1 + a2-a5). */
+int svo_cuda_pyramid_fast_detect(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
+                                 const uint8_t* occupancy_in, svo_corner* corners_out, svo_mem mem);
+/* Raw per-level stages, for parity tests against fast::* (a2, a3, a4): dense maps for one level of one frame.
+ * score_map[rows][cols] int16: 0 where the pixel is not a corner at `threshold`, else fast_corner_score_10;
+ * nonmax_map[rows][cols] uint8: 1 where the corner survives fast_nonmax_3x3. Either may be NULL. */
+int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int threshold, int arc_length,
+                             int16_t* score_map, uint8_t* nonmax_map, svo_mem mem);
+
+/* ---- (b) svo::SparseImgAlign (src/svo_img_align/include/svo/img_align/sparse_img_align.h:30-77,
+ *      sparse_img_align_base.h:37-163; run(): src/svo_img_align/src/sparse_img_align.cpp:34-113) ---------- */
+typedef struct {
+  /* SparseImgAlignOptions (sparse_img_align_base.h:37-46) */
+  int max_level, min_level;
+  int estimate_illumination_gain, estimate_illumination_offset;
+  int use_distortion_jacobian, robustification;
+  double weight_scale;
+  /* vk::solver::MiniLeastSquaresSolverOptions (GaussNewton; sparse_img_align_base.cpp:35-42) */
+  int max_iter;
+  int _pad;
+  double eps;
+  /* setAlphaInitialValue / setBetaInitialValue */
+  double alpha_init, beta_init;
+  /* setWeightedPrior lambdas (used when a prior array is passed) */
+  double lambda_rot, lambda_trans, lambda_alpha, lambda_beta;
+} svo_sparse_align_options;
+
+typedef struct { /* setWeightedPrior(T_cur_ref_prior, alpha_prior, beta_prior, ...) per pair */
+  double T[7];
+  double alpha, beta;
+} svo_align_prior;
+
+typedef struct {
+  double T_icur_iref[7];           /* optimised state */
+  double T_f_w[SVO_MAX_CAMS][7];   /* cur frames' T_f_w_ = T_cam_imu * T_icur_iref * T_iref_world */
+  double alpha, beta;
+  double chi2;                     /* getError() */
+  double H[64];                    /* getHessian(), row-major 8x8, last evaluated */
+  int n_tracked;                   /* run() return value */
+  int iters[SVO_MAX_LEVELS];       /* evaluateError calls per level, from max_level down */
+  int stop;                        /* solver stop_ flag (NaN in dx) */
+} svo_align_result;
+
+/* B independent frame-bundle pairs, each with n_cams cameras (1 = mono, 2 = stereo).
+ *   ref_pyr/cur_pyr[c]      : pyramid batches of camera c; pair i uses frame ref_frame_idx[i*n_cams+c]
+ *                             (NULL index array = frame i).
+ *   cams[c], T_cam_imu[c*7] : camera model and extrinsics of camera c (shared by all pairs).
+ *   T_imu_world_ref/cur     : [B][7]; cur is the initial guess (frame_handler_base.cpp:346-358).
+ *   n_features[i*n_cams+c]  : features of ref frame c of pair i, stored at [(i*n_cams+c)*max_features + k] in
+ *   px [..][2], f [..][3] (unit bearing, Frame::f_vec_), depth [..] (distance landmark/seed -> ref camera centre),
+ *   eligible [..] (1 = has landmark or seed reference and is not a MapPoint type, sparse_img_align.cpp:242-248).
+ *   priors                  : NULL or [B].
+ * All arrays follow `mem`. */
+int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cuda_pyr* const* ref_pyr, const svo_cuda_pyr* const* cur_pyr,
+                          const int* ref_frame_idx, const int* cur_frame_idx, const svo_camera* cams, const double* T_cam_imu,
+                          int B, const double* T_imu_world_ref, const double* T_imu_world_cur, const int* n_features,
+                          int max_features, const double* px, const double* f, const double* depth, const uint8_t* eligible,
+                          const svo_sparse_align_options* opt, const svo_align_prior* priors, svo_align_result* results,
+                          svo_mem mem);
+
+/* ---- (c) svo::feature_alignment + svo::Matcher ------------------------------------------------------------ */
+typedef struct { /* svo::Matcher::Options, src/svo_direct/include/svo/direct/matcher.h:39-54 */
+  int align_1d, align_max_iter;
+  int max_epi_search_steps;
+  int subpix_refinement, epi_search_edgelet_filtering, scan_on_unit_sphere;
+  double epi_search_edgelet_max_angle;
+  int affine_est_offset, affine_est_gain;
+  double max_patch_diff_ratio;
+} svo_matcher_options;
+
+typedef struct { /* the parts of svo::FeatureWrapper the matcher reads (feature_wrapper.h:34-45) */
+  double px[2];
+  double f[3];
+  double grad[2];
+  int type;  /* svo::FeatureType */
+  int level;
+} svo_feature;
+
+typedef struct { /* Matcher public members read back by callers (matcher.h:70-79) + MatchResult */
+  double px_cur[2];
+  double f_cur[3];
+  double A_cur_ref[4];
+  double h_inv;
+  double epi_length_pyramid;
+  double depth;
+  int result; /* svo::Matcher::MatchResult */
+  int search_level;
+  int reject;
+  int _pad;
+} svo_match_out;
+
+/* feature_alignment::align2D (src/svo_direct/include/svo/direct/feature_alignment.h:34-43; .cpp:212-391).
+ * M patches against level `level` of frame frame_idx[i] of `pyr`: patch_with_border [M][100] u8, px [M][2] in/out
+ * (level coordinates), converged [M] u8. */
+int svo_cuda_align2d(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const int* frame_idx, const int* level, int M,
+                     const uint8_t* patch_with_border, int n_iter, int affine_est_offset, int affine_est_gain, double* px,
+                     uint8_t* converged, svo_mem mem);
+/* feature_alignment::align1D (feature_alignment.h:23-32; .cpp:31-209): dir [M][2]; h_inv [M] out (may be NULL). */
+int svo_cuda_align1d(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const int* frame_idx, const int* level, int M,
+                     const double* dir, const uint8_t* patch_with_border, int n_iter, int affine_est_offset,
+                     int affine_est_gain, double* px, double* h_inv, uint8_t* converged, svo_mem mem);
+/* warp::getWarpMatrixAffine + getBestSearchLevel + warpAffine (src/svo_direct/src/patch_warp.cpp:20-60,97-156) followed by
+ * the 10x10 -> 8x8 crop; outputs A [M][4], search_level [M], patch_with_border [M][100], ok [M]. Mostly for parity tests. */
+int svo_cuda_warp_affine(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const int* ref_frame_idx, const svo_camera* cam_ref,
+                         const svo_camera* cam_cur, const double* T_cur_ref, const int* T_idx, int M, const svo_feature* ftrs,
+                         const double* depth, double* A_out, int* search_level_out, uint8_t* patch_with_border_out,
+                         uint8_t* ok_out, svo_mem mem);
+/* Matcher::findMatchDirect (matcher.h:84-89; matcher.cpp:31-141) for M features. Feature i lives in ref frame
+ * ref_frame_idx[i], is searched in cur frame cur_frame_idx[i] with T_cur_ref[T_idx[i]] ([..][7]);
+ * px_cur_guess [M][2] is the caller's estimate (level-0 px). */
+int svo_cuda_find_match_direct(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const svo_cuda_pyr* cur_pyr,
+                               const int* ref_frame_idx, const int* cur_frame_idx, const svo_camera* cam_ref,
+                               const svo_camera* cam_cur, const double* T_cur_ref, const int* T_idx, int M,
+                               const svo_feature* ftrs, const double* ref_depth, const double* px_cur_guess,
+                               const svo_matcher_options* opt, svo_match_out* out, svo_mem mem);
+/* Matcher::findEpipolarMatchDirect (matcher.h:100-108; matcher.cpp:157-241): d_inv [M][3] = (estimate, min, max)
+ * inverse depths in the order the reference passes them (d_estimate_inv, d_min_inv, d_max_inv). */
+int svo_cuda_find_epipolar_match_direct(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const svo_cuda_pyr* cur_pyr,
+                                        const int* ref_frame_idx, const int* cur_frame_idx, const svo_camera* cam_ref,
+                                        const svo_camera* cam_cur, const double* T_cur_ref, const int* T_idx, int M,
+                                        const svo_feature* ftrs, const double* d_inv, const svo_matcher_options* opt,
+                                        svo_match_out* out, svo_mem mem);
+
+/* ---- (d) svo::DepthFilter seed update ---------------------------------------------------------------------- */
+/* depth_filter_utils::updateFilterVogiatzis (src/svo_direct/include/svo/direct/depth_filter.h:201-205;
+ * src/svo_direct/src/depth_filter.cpp:501-552): n independent updates; state [n][4] = (mu, sigma2, a, b) in/out;
+ * ok [n] (0 = the reference returns false). */
+int svo_cuda_update_filter_vogiatzis(svo_cuda_ctx* ctx, int n, const double* z, const double* tau2, const double* mu_range,
+                                     double* state, uint8_t* ok, svo_mem mem);
+/* depth_filter_utils::computeTau (depth_filter.cpp:580-596): T_ref_cur [n][7], f [n][3], z [n] -> tau [n]. */
+int svo_cuda_compute_tau(svo_cuda_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z,
+                         double px_error_angle, double* tau, svo_mem mem);
+
+typedef struct {
+  double seed_convergence_sigma2_thresh;      /* DepthFilterOptions, depth_filter.h:33 (200) */
+  double mappoint_convergence_sigma2_thresh;  /* depth_filter.h:37 (500) */
+  double px_error_angle;  /* cam.getAngleError(1.0): the function-static of depth_filter.cpp:383-384; <= 0 = derive from cam_cur */
+  int check_visibility, check_convergence, use_vogiatzis_update;
+  int _pad;
+} svo_depth_filter_options;
+
+/* DepthFilter::updateSeeds / depth_filter_utils::updateSeed (depth_filter.h:118-120,190-199; depth_filter.cpp:200-249,
+ * 367-499): S seeds, seed s lives in ref frame ref_frame_idx[s] of ref_pyr with mu range seed_mu_range[s];
+ * it is observed, in order, by n_obs frames: observation o of seed s uses cur frame obs_frame_idx[o*S+s] and
+ * T_cur_ref[obs_T_idx[o*S+s]]; a negative obs_frame_idx skips that observation (e.g. cur == ref frame).
+ * types [S] (uint8 FeatureType) and state [S][4] are updated in place; n_success[0] counts successful updates;
+ * match_results (optional) [n_obs][S] receives each Matcher::MatchResult (-1 = no match attempted). */
+int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const svo_cuda_pyr* cur_pyr, const svo_camera* cam_ref,
+                          const svo_camera* cam_cur, int S, const int* ref_frame_idx, const svo_feature* ftrs, uint8_t* types,
+                          double* state, const double* seed_mu_range, int n_obs, const int* obs_frame_idx,
+                          const int* obs_T_idx, const double* T_cur_ref, const svo_matcher_options* mopt,
+                          const svo_depth_filter_options* dopt, int* n_success, int* match_results, svo_mem mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_CUDA_H_ */

@@ -176,7 +176,7 @@ def lib():
         L.orc_get_warp_matrix_affine.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f64p, f64p, C.c_double, f64p,
                                                  C.c_int, f64p]
         L.orc_update_seeds.argtypes = [C.POINTER(Frame), C.c_int, C.POINTER(Frame), f64p, C.c_int, C.POINTER(Feature),
-                                       u8p, f64p, C.c_double, C.POINTER(MatcherOptions), C.c_double, C.c_double,
+                                       u8p, f64p, C.c_double, C.POINTER(MatcherOptions), C.c_double, C.c_double, C.c_double,
                                        C.c_int, C.c_int, C.c_int, i32p, u8p, C.c_int]
         _lib = L
     return _lib
@@ -329,3 +329,57 @@ def sparse_align_batch(ref_frames, cur_frames, n_cams, opt, n_threads=1):
     res = (AlignResult * B)()
     lib().orc_sparse_align_batch(B, n_cams, R, Cc, C.byref(opt), res, n_threads)
     return res
+
+
+def make_features(px, f, grad, ftype, level):
+    """Array of orc Feature structs from SoA numpy inputs."""
+    n = len(px)
+    arr = (Feature * n)()
+    for i in range(n):
+        arr[i].type = int(ftype[i])
+        arr[i].px[:] = [float(px[i][0]), float(px[i][1])]
+        arr[i].f[:] = [float(f[i][0]), float(f[i][1]), float(f[i][2])]
+        arr[i].grad[:] = [float(grad[i][0]), float(grad[i][1])]
+        arr[i].level = int(level[i])
+    return arr
+
+
+MATCH_OUT_NP = np.dtype([("result", "<i4"), ("px_cur", "<f8", 2), ("f_cur", "<f8", 3), ("search_level", "<i4"),
+                         ("A_cur_ref", "<f8", 4), ("h_inv", "<f8"), ("epi_length_pyramid", "<f8"), ("reject", "<i4"),
+                         ("depth", "<f8"), ("patch_with_border", "u1", 100)], align=True)
+
+
+def find_match_direct_batch(ref, cur, T_cur_ref, ftrs, ref_depth, px_guess, opt, n_threads=1):
+    M = len(ftrs)
+    out = (MatchOut * M)()
+    T = np.ascontiguousarray(T_cur_ref, np.float64)
+    dep = np.ascontiguousarray(ref_depth, np.float64)
+    pg = np.ascontiguousarray(px_guess, np.float64)
+    lib().orc_find_match_direct_batch(C.byref(ref), C.byref(cur), _f64(T), M, ftrs, _f64(dep), _f64(pg), C.byref(opt), out, n_threads)
+    assert C.sizeof(MatchOut) == MATCH_OUT_NP.itemsize
+    return np.frombuffer(out, dtype=MATCH_OUT_NP).copy()
+
+
+def find_epipolar_match_direct_batch(ref, cur, T_cur_ref, ftrs, d_inv3, opt, n_threads=1):
+    M = len(ftrs)
+    out = (MatchOut * M)()
+    T = np.ascontiguousarray(T_cur_ref, np.float64)
+    d3 = np.ascontiguousarray(d_inv3, np.float64)
+    lib().orc_find_epipolar_match_direct_batch(C.byref(ref), C.byref(cur), _f64(T), M, ftrs, _f64(d3), C.byref(opt), out, n_threads)
+    return np.frombuffer(out, dtype=MATCH_OUT_NP).copy()
+
+
+def update_seeds(ref, cur_frames, T_cur_ref, ftrs, types, states, mu_range, opt, sigma2_thresh=200.0, mappoint_thresh=500.0,
+                 px_error_angle=None, check_visibility=1, check_convergence=0, use_vogiatzis=1, n_threads=1):
+    """depth_filter_utils::updateSeed for S seeds x n_obs ordered observations. types/states are modified in place."""
+    n_obs, S = len(cur_frames), len(ftrs)
+    Cf = (Frame * n_obs)(*cur_frames)
+    T = np.ascontiguousarray(T_cur_ref, np.float64)
+    mr = np.full((n_obs, S), -1, np.int32)
+    ok = np.zeros((n_obs, S), np.uint8)
+    if px_error_angle is None:
+        px_error_angle = lib().orc_px_error_angle(C.byref(cur_frames[0]), 1.0)
+    n = lib().orc_update_seeds(C.byref(ref), n_obs, Cf, _f64(T), S, ftrs, _u8(types), _f64(states), mu_range, C.byref(opt),
+                               sigma2_thresh, mappoint_thresh, px_error_angle, check_visibility, check_convergence, use_vogiatzis,
+                               _i32(mr), _u8(ok), n_threads)
+    return n, mr, ok

@@ -340,7 +340,8 @@ double orc_px_error_angle(const orc_frame* frame, double px_noise) { return camO
 
 int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frames, const double* T_cur_ref, int S,
                      const orc_feature* ftrs, uint8_t* types, double* states, double seed_mu_range,
-                     const orc_matcher_options* opt, double sigma2_convergence_threshold, double px_error_angle,
+                     const orc_matcher_options* opt, double sigma2_convergence_threshold,
+                     double mappoint_sigma2_convergence_threshold, double px_error_angle,
                      int check_visibility, int check_convergence, int use_vogiatzis, int* match_results, uint8_t* success,
                      int n_threads) {
   const MatchFrame rf = matchFrameOf(ref);
@@ -355,8 +356,11 @@ int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
     FeatureType type = static_cast<FeatureType>(types[s]);
     for (int o = 0; o < n_obs; ++o) {
       int mr = -1;
+      // DepthFilter::updateSeeds picks the threshold by seed type (src/svo_direct/src/depth_filter.cpp:214-221)
+      const double cur_thresh = (type == FeatureType::kMapPointSeed || type == FeatureType::kMapPointSeedConverged)
+                                    ? mappoint_sigma2_convergence_threshold : sigma2_convergence_threshold;
       const bool ok = updateSeed(cfs[o], rf, Ts[o], featureOf(&ftrs[s]), type, states + 4 * size_t(s), seed_mu_range, m,
-                                 sigma2_convergence_threshold, px_error_angle, check_visibility != 0, check_convergence != 0,
+                                 cur_thresh, px_error_angle, check_visibility != 0, check_convergence != 0,
                                  use_vogiatzis != 0, &mr);
       if (match_results) match_results[size_t(o) * S + s] = mr;
       if (success) success[size_t(o) * S + s] = ok;

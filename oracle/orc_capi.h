@@ -146,7 +146,8 @@ double orc_px_error_angle(const orc_frame* frame, double px_noise);
  * match_results (optional) is [n_obs][S]; success (optional) is [n_obs][S]. */
 int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frames, const double* T_cur_ref /* [n_obs][7] */,
                      int S, const orc_feature* ftrs, uint8_t* types, double* states /* [S][4] */, double seed_mu_range,
-                     const orc_matcher_options* opt, double sigma2_convergence_threshold, double px_error_angle,
+                     const orc_matcher_options* opt, double sigma2_convergence_threshold,
+                     double mappoint_sigma2_convergence_threshold, double px_error_angle,
                      int check_visibility, int check_convergence, int use_vogiatzis, int* match_results, uint8_t* success,
                      int n_threads);
 

@@ -1,0 +1,434 @@
+"""ctypes binding of libsvo_cuda.so (include/svo_cuda.h) — the C ABI of the B200-native front-end hot path.
+
+This is plumbing for tests, bench.py and Python users; the product is the CUDA library behind the C ABI and the C++
+facades in svo_pro_universal_b200/host/. There is NO CPU fallback: if the shared library is missing or no CUDA device is
+visible, loading / context creation raises.
+
+Array arguments may be numpy arrays (host memory, SVO_MEM_HOST) or torch CUDA tensors (SVO_MEM_DEVICE); one call must not
+mix the two.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvo_cuda.so")
+
+MAX_LEVELS = 8
+MAX_CAMS = 4
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class SvoCudaError(RuntimeError):
+    pass
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
+                ("width", C.c_int), ("height", C.c_int), ("distortion", C.c_int), ("_pad", C.c_int)]
+
+    @classmethod
+    def from_dict(cls, d):
+        return cls(d["fx"], d["fy"], d["cx"], d["cy"], d.get("k1", 0.0), d.get("k2", 0.0), d.get("p1", 0.0),
+                   d.get("p2", 0.0), d["width"], d["height"], d.get("distortion", 0), 0)
+
+
+class DetectorOptions(C.Structure):
+    _fields_ = [("threshold", C.c_int), ("border", C.c_int), ("min_level", C.c_int), ("max_level", C.c_int),
+                ("cell_size", C.c_int), ("arc_length", C.c_int)]
+
+
+def detector_options(threshold=10, border=8, min_level=0, max_level=2, cell_size=30, arc_length=10):
+    """svo::DetectorOptions defaults (feature_detection_types.h:49-84)."""
+    return DetectorOptions(threshold, border, min_level, max_level, cell_size, arc_length)
+
+
+class SparseAlignOptions(C.Structure):
+    _fields_ = [("max_level", C.c_int), ("min_level", C.c_int),
+                ("estimate_illumination_gain", C.c_int), ("estimate_illumination_offset", C.c_int),
+                ("use_distortion_jacobian", C.c_int), ("robustification", C.c_int),
+                ("weight_scale", C.c_double),
+                ("max_iter", C.c_int), ("_pad", C.c_int),
+                ("eps", C.c_double),
+                ("alpha_init", C.c_double), ("beta_init", C.c_double),
+                ("lambda_rot", C.c_double), ("lambda_trans", C.c_double),
+                ("lambda_alpha", C.c_double), ("lambda_beta", C.c_double)]
+
+
+def sparse_align_options(**kw):
+    """SparseImgAlignOptions defaults (sparse_img_align_base.h:37-46) + getDefaultSolverOptions (…base.cpp:35-42)."""
+    o = SparseAlignOptions()
+    o.max_level, o.min_level = 4, 1
+    o.weight_scale = 10.0
+    o.max_iter = 10
+    o.eps = 0.0005
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+ALIGN_PRIOR_DTYPE = np.dtype([("T", "<f8", 7), ("alpha", "<f8"), ("beta", "<f8")])
+ALIGN_RESULT_DTYPE = np.dtype([("T_icur_iref", "<f8", 7), ("T_f_w", "<f8", (MAX_CAMS, 7)), ("alpha", "<f8"), ("beta", "<f8"),
+                               ("chi2", "<f8"), ("H", "<f8", 64), ("n_tracked", "<i4"), ("iters", "<i4", MAX_LEVELS),
+                               ("stop", "<i4")], align=True)
+CORNER_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4"), ("angle", "<f4")])
+FEATURE_DTYPE = np.dtype([("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("type", "<i4"), ("level", "<i4")])
+MATCH_OUT_DTYPE = np.dtype([("px_cur", "<f8", 2), ("f_cur", "<f8", 3), ("A_cur_ref", "<f8", 4), ("h_inv", "<f8"),
+                            ("epi_length_pyramid", "<f8"), ("depth", "<f8"), ("result", "<i4"), ("search_level", "<i4"),
+                            ("reject", "<i4"), ("_pad", "<i4")])
+
+
+class MatcherOptions(C.Structure):
+    _fields_ = [("align_1d", C.c_int), ("align_max_iter", C.c_int),
+                ("max_epi_search_steps", C.c_int),
+                ("subpix_refinement", C.c_int), ("epi_search_edgelet_filtering", C.c_int), ("scan_on_unit_sphere", C.c_int),
+                ("epi_search_edgelet_max_angle", C.c_double),
+                ("affine_est_offset", C.c_int), ("affine_est_gain", C.c_int),
+                ("max_patch_diff_ratio", C.c_double)]
+
+
+def matcher_options(**kw):
+    """svo::Matcher::Options defaults (matcher.h:39-54)."""
+    o = MatcherOptions(0, 10, 100, 1, 1, 1, 0.7, 1, 0, 2.0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class DepthFilterOptions(C.Structure):
+    _fields_ = [("seed_convergence_sigma2_thresh", C.c_double), ("mappoint_convergence_sigma2_thresh", C.c_double),
+                ("px_error_angle", C.c_double),
+                ("check_visibility", C.c_int), ("check_convergence", C.c_int), ("use_vogiatzis_update", C.c_int),
+                ("_pad", C.c_int)]
+
+
+def depth_filter_options(**kw):
+    """DepthFilterOptions defaults (depth_filter.h:27-60) and updateSeed's call-site flags (depth_filter.cpp:225-226)."""
+    o = DepthFilterOptions(200.0, 500.0, 0.0, 1, 0, 1, 0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+_lib = None
+
+
+def lib():
+    """Load libsvo_cuda.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SvoCudaError("libsvo_cuda.so is missing: build it with `make -C svo_pro_universal_b200/csrc` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.svo_cuda_last_error.restype = C.c_char_p
+        L.svo_cuda_last_error.argtypes = [C.c_void_p]
+        L.svo_cuda_launch_count.restype = C.c_longlong
+        L.svo_cuda_launch_count.argtypes = [C.c_void_p]
+        vp, ci, cd, sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+        L.svo_cuda_sizeof.argtypes = [C.c_char_p]
+        L.svo_cuda_ctx_create.argtypes = [ci, C.POINTER(vp)]
+        L.svo_cuda_ctx_destroy.argtypes = [vp]
+        L.svo_cuda_ctx_set_stream.argtypes = [vp, vp]
+        L.svo_cuda_ctx_synchronize.argtypes = [vp]
+        L.svo_cuda_grid_cells.argtypes = [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
+        L.svo_cuda_pyr_create.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(vp)]
+        L.svo_cuda_pyr_destroy.argtypes = [vp, vp]
+        L.svo_cuda_pyr_upload.argtypes = [vp, vp, ci, ci, vp, sz, sz, ci]
+        L.svo_cuda_pyr_build.argtypes = [vp, vp, ci, ci]
+        L.svo_cuda_pyr_download.argtypes = [vp, vp, ci, ci, vp, sz, ci]
+        L.svo_cuda_pyr_level_info.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(sz), C.POINTER(sz), C.POINTER(vp)]
+        L.svo_cuda_fast_detect.argtypes = [vp, vp, ci, ci, C.POINTER(DetectorOptions), vp, vp, ci]
+        L.svo_cuda_pyramid_fast_detect.argtypes = [vp, vp, ci, ci, C.POINTER(DetectorOptions), vp, vp, ci]
+        L.svo_cuda_fast_level_maps.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, ci]
+        L.svo_cuda_sparse_align.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(vp), vp, vp, C.POINTER(Camera), vp, ci, vp, vp,
+                                            vp, ci, vp, vp, vp, vp, C.POINTER(SparseAlignOptions), vp, vp, ci]
+        L.svo_cuda_align2d.argtypes = [vp, vp, vp, vp, ci, vp, ci, ci, ci, vp, vp, ci]
+        L.svo_cuda_align1d.argtypes = [vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, vp, vp, vp, ci]
+        L.svo_cuda_warp_affine.argtypes = [vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), vp, vp, ci, vp, vp, vp, vp, vp, vp, ci]
+        L.svo_cuda_find_match_direct.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), vp, vp, ci, vp, vp,
+                                                 vp, C.POINTER(MatcherOptions), vp, ci]
+        L.svo_cuda_find_epipolar_match_direct.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), vp, vp, ci,
+                                                          vp, vp, C.POINTER(MatcherOptions), vp, ci]
+        L.svo_cuda_update_filter_vogiatzis.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci]
+        L.svo_cuda_compute_tau.argtypes = [vp, ci, vp, vp, vp, cd, vp, ci]
+        L.svo_cuda_update_seeds.argtypes = [vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), ci, vp, vp, vp, vp, vp, ci, vp, vp,
+                                            vp, C.POINTER(MatcherOptions), C.POINTER(DepthFilterOptions), vp, vp, ci]
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "svo_cuda_ctx_create", "svo_cuda_ctx_destroy", "svo_cuda_ctx_set_stream", "svo_cuda_ctx_synchronize", "svo_cuda_last_error",
+    "svo_cuda_launch_count", "svo_cuda_device_count", "svo_cuda_sizeof", "svo_cuda_pyr_create", "svo_cuda_pyr_destroy", "svo_cuda_pyr_upload",
+    "svo_cuda_pyr_build", "svo_cuda_pyr_download", "svo_cuda_pyr_level_info", "svo_cuda_grid_cells", "svo_cuda_fast_detect",
+    "svo_cuda_pyramid_fast_detect", "svo_cuda_fast_level_maps", "svo_cuda_sparse_align", "svo_cuda_align2d", "svo_cuda_align1d",
+    "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
+    "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds",
+]
+
+
+def _is_torch(a):
+    return hasattr(a, "data_ptr")
+
+
+def _ptr(a):
+    """(void*, mem kind) of a numpy array, torch tensor or None."""
+    if a is None:
+        return None, None
+    if _is_torch(a):
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr()), (MEM_DEVICE if a.is_cuda else MEM_HOST)
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"], "arrays must be C-contiguous numpy arrays or torch tensors"
+    return C.c_void_p(a.ctypes.data), MEM_HOST
+
+
+def _ptrs(*arrs):
+    ps, kinds = [], set()
+    for a in arrs:
+        p, k = _ptr(a)
+        ps.append(p)
+        if k is not None:
+            kinds.add(k)
+    assert len(kinds) <= 1, "one call must not mix host and device arrays"
+    return ps, (kinds.pop() if kinds else MEM_HOST)
+
+
+class Context:
+    """svo_cuda_ctx: one GPU + one stream."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().svo_cuda_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            raise SvoCudaError(f"svo_cuda_ctx_create(device={device}) failed with status {rc} "
+                               "(no CUDA device? this library has no CPU fallback)")
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise SvoCudaError(f"status {rc}: {lib().svo_cuda_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(lib().svo_cuda_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self.check(lib().svo_cuda_ctx_synchronize(self._h))
+
+    @property
+    def launches(self):
+        return int(lib().svo_cuda_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().svo_cuda_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pyramid:
+    """svo_cuda_pyr: a device-resident batch of image pyramids (svo::Frame::img_pyr_ for n_frames frames)."""
+
+    def __init__(self, ctx, n_frames, width, height, n_levels, halfsample_mode=-1):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx.check(lib().svo_cuda_pyr_create(ctx._h, n_frames, width, height, n_levels, halfsample_mode, C.byref(self._h)))
+        self.n_frames, self.width, self.height, self.n_levels = n_frames, width, height, n_levels
+
+    def upload(self, images, first=0):
+        """images: [count, H, W] uint8 numpy (host) or torch cuda tensor."""
+        if not _is_torch(images):
+            images = np.ascontiguousarray(images, dtype=np.uint8)
+        if images.ndim == 2:
+            images = images.reshape((1,) + tuple(images.shape))
+        count, h, w = images.shape
+        assert (h, w) == (self.height, self.width)
+        p, kind = _ptr(images)
+        self.ctx.check(lib().svo_cuda_pyr_upload(self.ctx._h, self._h, first, count, p, w, w * h, kind))
+        if kind == MEM_HOST and not _is_torch(images):
+            self.ctx.synchronize()  # pageable numpy buffer: do not let it be freed under the copy
+
+    def build(self, first=0, count=None):
+        self.ctx.check(lib().svo_cuda_pyr_build(self.ctx._h, self._h, first, self.n_frames - first if count is None else count))
+
+    def level_info(self, level):
+        c, r, p, s, d = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t(), C.c_void_p()
+        self.ctx.check(lib().svo_cuda_pyr_level_info(self._h, level, C.byref(c), C.byref(r), C.byref(p), C.byref(s), C.byref(d)))
+        return dict(cols=c.value, rows=r.value, pitch=p.value, frame_stride=s.value, device_ptr=d.value)
+
+    def download(self, frame, level):
+        info = self.level_info(level)
+        out = np.empty((info["rows"], info["cols"]), np.uint8)
+        self.ctx.check(lib().svo_cuda_pyr_download(self.ctx._h, self._h, frame, level, C.c_void_p(out.ctypes.data), info["cols"], MEM_HOST))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().svo_cuda_pyr_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def grid_cells(width, height, cell_size):
+    nc, nr = C.c_int(), C.c_int()
+    n = lib().svo_cuda_grid_cells(width, height, cell_size, C.byref(nc), C.byref(nr))
+    return n, nc.value, nr.value
+
+
+def fast_detect(ctx, pyr, opt, first=0, count=None, occupancy=None, corners_out=None, fused_pyramid=False):
+    """fastDetector for frames [first, first+count): returns corners [count, n_cells] (CORNER_DTYPE)."""
+    count = pyr.n_frames - first if count is None else count
+    n_cells, _, _ = grid_cells(pyr.width, pyr.height, opt.cell_size)
+    if corners_out is None:
+        corners_out = np.zeros((count, n_cells), CORNER_DTYPE)
+    (po, pc), kind = _ptrs(occupancy, corners_out)
+    fn = lib().svo_cuda_pyramid_fast_detect if fused_pyramid else lib().svo_cuda_fast_detect
+    ctx.check(fn(ctx._h, pyr._h, first, count, C.byref(opt), po, pc, kind))
+    return corners_out
+
+
+def fast_level_maps(ctx, pyr, frame, level, threshold=10, arc_length=10):
+    info = pyr.level_info(level)
+    score = np.zeros((info["rows"], info["cols"]), np.int16)
+    nonmax = np.zeros((info["rows"], info["cols"]), np.uint8)
+    ctx.check(lib().svo_cuda_fast_level_maps(ctx._h, pyr._h, frame, level, threshold, arc_length,
+                                             C.c_void_p(score.ctypes.data), C.c_void_p(nonmax.ctypes.data), MEM_HOST))
+    return score, nonmax
+
+
+def sparse_align(ctx, ref_pyrs, cur_pyrs, cams, T_cam_imu, T_imu_world_ref, T_imu_world_cur, n_features, px, f, depth, eligible,
+                 opt, priors=None, ref_frame_idx=None, cur_frame_idx=None, results=None):
+    """svo_cuda_sparse_align. ref_pyrs/cur_pyrs: lists (one Pyramid per camera). Feature arrays are
+    [B, n_cams, max_features, ...]. Returns results (ALIGN_RESULT_DTYPE numpy, or the torch uint8 tensor passed in)."""
+    n_cams = len(ref_pyrs)
+    B = T_imu_world_ref.shape[0]
+    max_features = px.shape[-2]
+    cam_arr = (Camera * n_cams)(*cams)
+    rp = (C.c_void_p * n_cams)(*[p._h for p in ref_pyrs])
+    cp = (C.c_void_p * n_cams)(*[p._h for p in cur_pyrs])
+    T_cam_imu = np.ascontiguousarray(T_cam_imu, np.float64).reshape(n_cams, 7)
+    if results is None:
+        results = np.zeros(B, ALIGN_RESULT_DTYPE)
+    ps, kind = _ptrs(ref_frame_idx, cur_frame_idx, T_imu_world_ref, T_imu_world_cur, n_features, px, f, depth, eligible, priors, results)
+    ctx.check(lib().svo_cuda_sparse_align(ctx._h, n_cams, rp, cp, ps[0], ps[1], cam_arr, C.c_void_p(T_cam_imu.ctypes.data), B,
+                                          ps[2], ps[3], ps[4], max_features, ps[5], ps[6], ps[7], ps[8], C.byref(opt), ps[9],
+                                          ps[10], kind))
+    return results
+
+
+def align2d(ctx, pyr, frame_idx, level, patch_with_border, px, n_iter=10, est_offset=True, est_gain=False):
+    M = len(px)
+    px = np.ascontiguousarray(px, np.float64).copy()
+    conv = np.zeros(M, np.uint8)
+    ps, kind = _ptrs(np.ascontiguousarray(frame_idx, np.int32), np.ascontiguousarray(level, np.int32),
+                     np.ascontiguousarray(patch_with_border, np.uint8), px, conv)
+    ctx.check(lib().svo_cuda_align2d(ctx._h, pyr._h, ps[0], ps[1], M, ps[2], n_iter, int(est_offset), int(est_gain), ps[3], ps[4], kind))
+    return px, conv
+
+
+def align1d(ctx, pyr, frame_idx, level, direction, patch_with_border, px, n_iter=10, est_offset=True, est_gain=False):
+    M = len(px)
+    px = np.ascontiguousarray(px, np.float64).copy()
+    conv = np.zeros(M, np.uint8)
+    hinv = np.zeros(M, np.float64)
+    ps, kind = _ptrs(np.ascontiguousarray(frame_idx, np.int32), np.ascontiguousarray(level, np.int32),
+                     np.ascontiguousarray(direction, np.float64), np.ascontiguousarray(patch_with_border, np.uint8), px, hinv, conv)
+    ctx.check(lib().svo_cuda_align1d(ctx._h, pyr._h, ps[0], ps[1], M, ps[2], ps[3], n_iter, int(est_offset), int(est_gain),
+                                     ps[4], ps[5], ps[6], kind))
+    return px, conv, hinv
+
+
+def make_features(px, f, grad, ftype, level):
+    n = len(px)
+    a = np.zeros(n, FEATURE_DTYPE)
+    a["px"], a["f"], a["grad"], a["type"], a["level"] = px, f, grad, ftype, level
+    return a
+
+
+def warp_affine(ctx, ref_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, depth, ref_frame_idx=None, T_idx=None):
+    M = len(ftrs)
+    A = np.zeros((M, 4))
+    sl = np.zeros(M, np.int32)
+    pwb = np.zeros((M, 100), np.uint8)
+    ok = np.zeros(M, np.uint8)
+    T = np.ascontiguousarray(T_cur_ref, np.float64).reshape(-1, 7)
+    ps, kind = _ptrs(ref_frame_idx, T, T_idx, ftrs, np.ascontiguousarray(depth, np.float64), A, sl, pwb, ok)
+    ctx.check(lib().svo_cuda_warp_affine(ctx._h, ref_pyr._h, ps[0], C.byref(cam_ref), C.byref(cam_cur), ps[1], ps[2], M, ps[3], ps[4],
+                                         ps[5], ps[6], ps[7], ps[8], kind))
+    return A, sl, pwb, ok
+
+
+def find_match_direct(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, ref_depth, px_guess, opt, ref_frame_idx=None,
+                      cur_frame_idx=None, T_idx=None, out=None):
+    M = len(ftrs)
+    if out is None:
+        out = np.zeros(M, MATCH_OUT_DTYPE)
+    if not _is_torch(T_cur_ref):
+        T_cur_ref = np.ascontiguousarray(T_cur_ref, np.float64).reshape(-1, 7)
+    ps, kind = _ptrs(ref_frame_idx, cur_frame_idx, T_cur_ref, T_idx, ftrs, ref_depth, px_guess, out)
+    ctx.check(lib().svo_cuda_find_match_direct(ctx._h, ref_pyr._h, cur_pyr._h, ps[0], ps[1], C.byref(cam_ref), C.byref(cam_cur), ps[2],
+                                               ps[3], M, ps[4], ps[5], ps[6], C.byref(opt), ps[7], kind))
+    return out
+
+
+def find_epipolar_match_direct(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, d_inv, opt, ref_frame_idx=None,
+                               cur_frame_idx=None, T_idx=None, out=None):
+    M = len(ftrs)
+    if out is None:
+        out = np.zeros(M, MATCH_OUT_DTYPE)
+    if not _is_torch(T_cur_ref):
+        T_cur_ref = np.ascontiguousarray(T_cur_ref, np.float64).reshape(-1, 7)
+    ps, kind = _ptrs(ref_frame_idx, cur_frame_idx, T_cur_ref, T_idx, ftrs, d_inv, out)
+    ctx.check(lib().svo_cuda_find_epipolar_match_direct(ctx._h, ref_pyr._h, cur_pyr._h, ps[0], ps[1], C.byref(cam_ref), C.byref(cam_cur),
+                                                        ps[2], ps[3], M, ps[4], ps[5], C.byref(opt), ps[6], kind))
+    return out
+
+
+def update_filter_vogiatzis(ctx, z, tau2, mu_range, state, ok=None):
+    """In-place on `state` [n,4]. Returns ok [n] uint8."""
+    n = state.shape[0]
+    if ok is None and not _is_torch(state):
+        ok = np.zeros(n, np.uint8)
+    ps, kind = _ptrs(z, tau2, mu_range, state, ok)
+    ctx.check(lib().svo_cuda_update_filter_vogiatzis(ctx._h, n, ps[0], ps[1], ps[2], ps[3], ps[4], kind))
+    return ok
+
+
+def compute_tau(ctx, T_ref_cur, f, z, px_error_angle):
+    n = len(z)
+    tau = np.zeros(n)
+    ps, kind = _ptrs(np.ascontiguousarray(T_ref_cur, np.float64), np.ascontiguousarray(f, np.float64),
+                     np.ascontiguousarray(z, np.float64), tau)
+    ctx.check(lib().svo_cuda_compute_tau(ctx._h, n, ps[0], ps[1], ps[2], px_error_angle, ps[3], kind))
+    return tau
+
+
+def update_seeds(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, ftrs, types, state, seed_mu_range, obs_frame_idx, obs_T_idx, T_cur_ref,
+                 mopt, dopt, ref_frame_idx=None, want_match_results=True):
+    """svo_cuda_update_seeds; types/state updated in place. Returns (n_success, match_results [n_obs,S] or None)."""
+    S = len(ftrs)
+    n_obs = obs_frame_idx.shape[0]
+    dev = _is_torch(state)
+    if dev:
+        import torch
+        n_success = torch.zeros(1, dtype=torch.int32, device=state.device)
+        mr = torch.full((n_obs, S), -1, dtype=torch.int32, device=state.device) if want_match_results else None
+    else:
+        n_success = np.zeros(1, np.int32)
+        mr = np.full((n_obs, S), -1, np.int32) if want_match_results else None
+    ps, kind = _ptrs(ref_frame_idx, ftrs, types, state, seed_mu_range, obs_frame_idx, obs_T_idx, T_cur_ref, n_success, mr)
+    ctx.check(lib().svo_cuda_update_seeds(ctx._h, ref_pyr._h, cur_pyr._h, C.byref(cam_ref), C.byref(cam_cur), S, ps[0], ps[1], ps[2],
+                                          ps[3], ps[4], n_obs, ps[5], ps[6], ps[7], C.byref(mopt), C.byref(dopt), ps[8], ps[9], kind))
+    return n_success, mr

@@ -1,0 +1,536 @@
+// Device functions of the patch matcher, shared by the (c) kernels in matcher.cu and the (d) seed-update kernel in
+// depth_filter.cu. One 8-lane group works on one feature: lane r owns row r of the 8x8 patch, group-wide sums use
+// __shfl_xor_sync with the group's own mask so the four groups of a warp may diverge (different iteration counts,
+// different epipolar scan lengths).
+//
+// ref: src/svo_direct/src/patch_warp.cpp:20-60 (getWarpMatrixAffine), :97-110 (getBestSearchLevel), :112-156 (warpAffine)
+//      src/svo_direct/include/svo/direct/patch_utils.h:18-30, patch_score.h:43-109,264-283 (ZMSSD)
+//      src/svo_direct/src/feature_alignment.cpp:31-209 (align1D), :212-391 (align2D)
+//      src/svo_direct/src/matcher.cpp:31-141 (findMatchDirect), :157-241 (findEpipolarMatchDirect), :262-338,
+//      :340-413 (scanEpipolarUnitPlane), :415-488 (scanEpipolarUnitSphere), :492-505 (depthFromTriangulation)
+#pragma once
+#include "common.cuh"
+
+namespace svo_dev {
+
+constexpr int kGroup = 8;            // lanes per feature
+constexpr int kPwbPitch = 112;       // bytes of shared memory per group for the 10x10 patch (100 rounded up)
+
+enum MatchResult {  // svo::Matcher::MatchResult, matcher.h:56-68
+  kSuccess = 0, kFailScore, kFailTriangulation, kFailVisibility, kFailWarp, kFailAlignment, kFailRange, kFailAngle,
+  kFailCloseView, kFailLock, kFailTooFar
+};
+enum FeatureType {  // svo::FeatureType, src/svo_common/include/svo/common/types.h:60-73
+  kEdgeletSeed = 0, kCornerSeed = 1, kMapPointSeed = 2, kEdgeletSeedConverged = 3, kCornerSeedConverged = 4,
+  kMapPointSeedConverged = 5, kEdgelet = 6, kCorner = 7, kMapPoint = 8, kFixedLandmark = 9, kOutlier = 10
+};
+SVO_HD bool isEdgeletType(int t) { return t == kEdgelet || t == kEdgeletSeed || t == kEdgeletSeedConverged; }
+
+struct Group {
+  unsigned mask;  // the 8 lanes of this group
+  int r;          // lane within the group = patch row
+};
+SVO_D Group makeGroup() {
+  const int lane = threadIdx.x & 31;
+  Group g;
+  g.r = lane & (kGroup - 1);
+  g.mask = 0xFFu << (lane & ~(kGroup - 1));
+  return g;
+}
+template <class T>
+SVO_D T groupSum(const Group& g, T v) {
+  v += __shfl_xor_sync(g.mask, v, 1);
+  v += __shfl_xor_sync(g.mask, v, 2);
+  v += __shfl_xor_sync(g.mask, v, 4);
+  return v;
+}
+SVO_D bool groupAny(const Group& g, bool p) { return (__ballot_sync(g.mask, p) & g.mask) != 0u; }
+
+struct ImgView {
+  const uint8_t* data;
+  int cols, rows, pitch;
+};
+SVO_D ImgView levelView(const PyrView& p, int frame, int level) {
+  return ImgView{p.level(frame, level), p.cols[level], p.rows[level], p.pitch[level]};
+}
+
+// ---- c1 ------------------------------------------------------------------------------------------------------
+SVO_D void getWarpMatrixAffine(const svo_camera& cam_ref, const svo_camera& cam_cur, double pxr_x, double pxr_y, const V3d& f_ref,
+                               double depth_ref, const SE3d& T_cur_ref, int level_ref, double A[2][2]) {
+  const int kHalf = 5;
+  const V3d xyz_ref = f_ref * depth_ref;
+  V3d du = camBackProject3(cam_ref, pxr_x + double(kHalf) * (1 << level_ref), pxr_y);
+  V3d dv = camBackProject3(cam_ref, pxr_x, pxr_y + double(kHalf) * (1 << level_ref));
+  du = du * xyz_ref.z;
+  dv = dv * xyz_ref.z;
+  const V2d pc = camProject3(cam_cur, se3Apply(T_cur_ref, xyz_ref));
+  const V2d pdu = camProject3(cam_cur, se3Apply(T_cur_ref, du));
+  const V2d pdv = camProject3(cam_cur, se3Apply(T_cur_ref, dv));
+  A[0][0] = (pdu.x - pc.x) / kHalf; A[1][0] = (pdu.y - pc.y) / kHalf;
+  A[0][1] = (pdv.x - pc.x) / kHalf; A[1][1] = (pdv.y - pc.y) / kHalf;
+}
+SVO_D int getBestSearchLevel(const double A[2][2], int max_level) {
+  int sl = 0;
+  double D = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+  while (D > 3.0 && sl < max_level) { sl += 1; D *= 0.25; }
+  return sl;
+}
+// warpAffine with halfpatch_size = 5: the group fills pwb[100]; float arithmetic is spelled with round-to-nearest
+// intrinsics so no FMA is formed and the truncated u8 values equal the reference's.
+SVO_D bool warpAffine10(const Group& g, const double A[2][2], const ImgView& img, double pxr_x, double pxr_y, int level_ref,
+                        int search_level, uint8_t* pwb) {
+  const double det = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+  const double invdet = 1.0 / det;
+  const float sl = (float)(1 << search_level);
+  const float a00 = __fmul_rn((float)(A[1][1] * invdet), sl), a01 = __fmul_rn((float)(-A[0][1] * invdet), sl);
+  const float a10 = __fmul_rn((float)(-A[1][0] * invdet), sl), a11 = __fmul_rn((float)(A[0][0] * invdet), sl);
+  if (a00 != a00) return false;
+  const float lr = (float)(1 << level_ref);
+  const float p0 = __fdiv_rn((float)pxr_x, lr), p1 = __fdiv_rn((float)pxr_y, lr);
+  bool bad = false;
+  __syncwarp(g.mask);  // every lane is done reading the previous patch in pwb
+  for (int i = g.r; i < 100; i += kGroup) {
+    const int yy = i / 10, xx = i - yy * 10;
+    const float x = (float)(xx - 5), y = (float)(yy - 5);
+    const float px0 = __fadd_rn(__fadd_rn(__fmul_rn(a00, x), __fmul_rn(a01, y)), p0);
+    const float px1 = __fadd_rn(__fadd_rn(__fmul_rn(a10, x), __fmul_rn(a11, y)), p1);
+    const int xi = (int)floorf(px0), yi = (int)floorf(px1);
+    if (xi < 0 || yi < 0 || xi + 1 >= img.cols || yi + 1 >= img.rows || !(px0 == px0) || !(px1 == px1)) {
+      bad = true;
+      continue;
+    }
+    const float sx = __fsub_rn(px0, (float)xi), sy = __fsub_rn(px1, (float)yi);
+    const float w00 = __fmul_rn(__fsub_rn(1.0f, sx), __fsub_rn(1.0f, sy));
+    const float w01 = __fmul_rn(__fsub_rn(1.0f, sx), sy);
+    const float w10 = __fmul_rn(sx, __fsub_rn(1.0f, sy));
+    const float w11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, w00), w01), w10);
+    const uint8_t* p = img.data + (size_t)yi * img.pitch + xi;
+    const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, (float)p[0]), __fmul_rn(w01, (float)p[img.pitch])),
+                                        __fmul_rn(w10, (float)p[1])), __fmul_rn(w11, (float)p[img.pitch + 1]));
+    pwb[i] = (uint8_t)__float2int_rz(v);
+  }
+  __syncwarp(g.mask);
+  return !groupAny(g, bad);
+}
+
+// ---- small float inverses (Eigen cofactor forms) -------------------------------------------------------------
+SVO_D void inverse3f(const float m[3][3], float r[3][3]) {
+#define COF3(i, j) (m[(i + 1) % 3][(j + 1) % 3] * m[(i + 2) % 3][(j + 2) % 3] - m[(i + 1) % 3][(j + 2) % 3] * m[(i + 2) % 3][(j + 1) % 3])
+  const float c00 = COF3(0, 0), c10 = COF3(1, 0), c20 = COF3(2, 0);
+  const float det = c00 * m[0][0] + c10 * m[1][0] + c20 * m[2][0];
+  const float invdet = 1.0f / det;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[i][j] = COF3(j, i) * invdet;
+#undef COF3
+}
+SVO_D float det3f(const float m[4][4], int r0, int r1, int r2, int c0, int c1, int c2) {
+  return m[r0][c0] * (m[r1][c1] * m[r2][c2] - m[r1][c2] * m[r2][c1]) - m[r0][c1] * (m[r1][c0] * m[r2][c2] - m[r1][c2] * m[r2][c0]) +
+         m[r0][c2] * (m[r1][c0] * m[r2][c1] - m[r1][c1] * m[r2][c0]);
+}
+SVO_D void inverse4f(const float m[4][4], float r[4][4]) {
+  float cof[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r0 = (i == 0) ? 1 : 0, r1 = (i <= 1) ? 2 : 1, r2 = (i <= 2) ? 3 : 2;
+      const int c0 = (j == 0) ? 1 : 0, c1 = (j <= 1) ? 2 : 1, c2 = (j <= 2) ? 3 : 2;
+      const float d = det3f(m, r0, r1, r2, c0, c1, c2);
+      cof[i][j] = ((i + j) & 1) ? -d : d;
+    }
+  const float det = m[0][0] * cof[0][0] + m[0][1] * cof[0][1] + m[0][2] * cof[0][2] + m[0][3] * cof[0][3];
+  const float invdet = 1.0f / det;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[i][j] = cof[j][i] * invdet;
+}
+
+// 9 bytes x0..x0+8 of a 4-byte-aligned row: bytes 0..7 in (a,b), byte 8 returned in c's low byte.
+SVO_D void loadRow9(const uint8_t* row, int x0, unsigned& a, unsigned& b, unsigned& c) {
+  const unsigned* w = reinterpret_cast<const unsigned*>(row + (x0 & ~3));
+  const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+  const unsigned sh = (x0 & 3) * 8;
+  a = __funnelshift_r(w0, w1, sh);
+  b = __funnelshift_r(w1, w2, sh);
+  c = __funnelshift_r(w2, w3, sh) & 0xffu;
+}
+SVO_D unsigned byte9(unsigned a, unsigned b, unsigned c, int i) { return i < 4 ? byteOf(a, i) : (i < 8 ? byteOf(b, i - 4) : c); }
+
+// ---- c3: align2D ---------------------------------------------------------------------------------------------
+// pwb: the group's 10x10 patch in shared memory. u,v in/out (level px). Returns converged.
+SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n_iter, bool est_offset, bool est_gain,
+                   double& px_x, double& px_y) {
+  const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
+  float rdx[8], rdy[8], rref[8];
+  float h[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    const float J0 = 0.5f * (float)((int)it[x + 1] - (int)it[x - 1]);
+    const float J1 = 0.5f * (float)((int)it[x + 10] - (int)it[x - 10]);
+    const float J2 = est_offset ? 1.0f : 0.0f;
+    const float J3 = est_gain ? -1.0f * (float)it[x] : 0.0f;
+    rdx[x] = J0; rdy[x] = J1; rref[x] = (float)it[x];
+    h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J0 * J3;
+    h[4] += J1 * J1; h[5] += J1 * J2; h[6] += J1 * J3; h[7] += J2 * J2; h[8] += J2 * J3; h[9] += J3 * J3;
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) h[k] = groupSum(g, h[k]);
+  float H[4][4] = {{h[0], h[1], h[2], h[3]}, {h[1], h[4], h[5], h[6]}, {h[2], h[5], h[7], h[8]}, {h[3], h[6], h[8], h[9]}};
+  if (!est_offset) H[2][2] = 1.0f;
+  if (!est_gain) H[3][3] = 1.0f;
+  float Hinv[4][4];
+  inverse4f(H, Hinv);
+  float mean_diff = 0.f, alpha = 1.0f;
+  float u = (float)px_x, v = (float)px_y;
+  const float min_update_squared = (float)(0.03 * 0.03);
+  bool converged = false;
+  for (int iter = 0; iter < n_iter; ++iter) {
+    const int u_r = (int)floorf(u), v_r = (int)floorf(v);
+    if (u_r < 4 || v_r < 4 || u_r >= img.cols - 4 || v_r >= img.rows - 4) break;
+    if (u != u || v != v) return false;
+    const float sx = u - u_r, sy = v - v_r;
+    const float wTL = (float)((1.0 - sx) * (1.0 - sy)), wTR = (float)(sx * (1.0 - sy));
+    const float wBL = (float)((1.0 - sx) * sy), wBR = sx * sy;
+    const uint8_t* row = img.data + (size_t)(v_r + g.r - 4) * img.pitch;
+    unsigned a0, b0, c0, a1, b1, c1;
+    loadRow9(row, u_r - 4, a0, b0, c0);
+    loadRow9(row + img.pitch, u_r - 4, a1, b1, c1);
+    float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const float sp = wTL * (float)byte9(a0, b0, c0, x) + wTR * (float)byte9(a0, b0, c0, x + 1) +
+                       wBL * (float)byte9(a1, b1, c1, x) + wBR * (float)byte9(a1, b1, c1, x + 1);
+      const float res = sp - alpha * rref[x] + mean_diff;
+      j0 -= res * rdx[x];
+      j1 -= res * rdy[x];
+      j2 -= res;
+      j3 -= (-1.0f) * res * rref[x];
+    }
+    j0 = groupSum(g, j0); j1 = groupSum(g, j1); j2 = groupSum(g, j2); j3 = groupSum(g, j3);
+    if (!est_offset) j2 = 0.f;
+    if (!est_gain) j3 = 0.f;
+    const float up0 = Hinv[0][0] * j0 + Hinv[0][1] * j1 + Hinv[0][2] * j2 + Hinv[0][3] * j3;
+    const float up1 = Hinv[1][0] * j0 + Hinv[1][1] * j1 + Hinv[1][2] * j2 + Hinv[1][3] * j3;
+    const float up2 = Hinv[2][0] * j0 + Hinv[2][1] * j1 + Hinv[2][2] * j2 + Hinv[2][3] * j3;
+    const float up3 = Hinv[3][0] * j0 + Hinv[3][1] * j1 + Hinv[3][2] * j2 + Hinv[3][3] * j3;
+    u += up0; v += up1; mean_diff += up2; alpha += up3;
+    if (up0 * up0 + up1 * up1 < min_update_squared) { converged = true; break; }
+  }
+  px_x = u; px_y = v;
+  return converged;
+}
+
+// ---- c4: align1D ---------------------------------------------------------------------------------------------
+SVO_D bool align1D(const Group& g, const ImgView& img, double dir_x, double dir_y, const uint8_t* pwb, int n_iter, bool est_offset,
+                   bool est_gain, double& px_x, double& px_y, double* h_inv) {
+  const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
+  float rdv[8], rref[8];
+  float h[6] = {0, 0, 0, 0, 0, 0};  // 00 01 02 11 12 22
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    const float dx = (float)it[x + 1] - (float)it[x - 1];
+    const float dy = (float)it[x + 10] - (float)it[x - 10];
+    const float J0 = (float)(0.5f * (dir_x * dx + dir_y * dy));
+    const float J1 = est_offset ? 1.0f : 0.0f;
+    const float J2 = est_gain ? -1.0f * (float)it[x] : 0.0f;
+    rdv[x] = J0; rref[x] = (float)it[x];
+    h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J1 * J1; h[4] += J1 * J2; h[5] += J2 * J2;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) h[k] = groupSum(g, h[k]);
+  float H[3][3] = {{h[0], h[1], h[2]}, {h[1], h[3], h[4]}, {h[2], h[4], h[5]}};
+  if (!est_offset) H[1][1] = 1.0f;
+  if (!est_gain) H[2][2] = 1.0f;
+  if (h_inv) *h_inv = 1.0 / H[0][0] * 8 * 8;
+  float Hinv[3][3];
+  inverse3f(H, Hinv);
+  float mean_diff = 0.f, alpha = 1.0f;
+  float u = (float)px_x, v = (float)px_y;
+  const float min_update_squared = (float)(0.03 * 0.03);
+  bool converged = false;
+  for (int iter = 0; iter < n_iter; ++iter) {
+    const int u_r = (int)floorf(u), v_r = (int)floorf(v);
+    if (u_r < 4 || v_r < 4 || u_r >= img.cols - 4 || v_r >= img.rows - 4) break;
+    if (u != u || v != v) return false;
+    const float sx = u - u_r, sy = v - v_r;
+    const float wTL = (float)((1.0 - sx) * (1.0 - sy)), wTR = (float)(sx * (1.0 - sy));
+    const float wBL = (float)((1.0 - sx) * sy), wBR = sx * sy;
+    const uint8_t* row = img.data + (size_t)(v_r + g.r - 4) * img.pitch;
+    unsigned a0, b0, c0, a1, b1, c1;
+    loadRow9(row, u_r - 4, a0, b0, c0);
+    loadRow9(row + img.pitch, u_r - 4, a1, b1, c1);
+    float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const float ci = wTL * (float)byte9(a0, b0, c0, x) + wTR * (float)byte9(a0, b0, c0, x + 1) +
+                       wBL * (float)byte9(a1, b1, c1, x) + wBR * (float)byte9(a1, b1, c1, x + 1);
+      const float res = ci - alpha * rref[x] + mean_diff;
+      j0 -= res * rdv[x];
+      j1 -= res;
+      j2 -= (-1.0f) * res * rref[x];
+    }
+    j0 = groupSum(g, j0); j1 = groupSum(g, j1); j2 = groupSum(g, j2);
+    if (!est_offset) j1 = 0.f;
+    if (!est_gain) j2 = 0.f;
+    const float up0 = Hinv[0][0] * j0 + Hinv[0][1] * j1 + Hinv[0][2] * j2;
+    const float up1 = Hinv[1][0] * j0 + Hinv[1][1] * j1 + Hinv[1][2] * j2;
+    const float up2 = Hinv[2][0] * j0 + Hinv[2][1] * j1 + Hinv[2][2] * j2;
+    u = (float)(u + up0 * dir_x);
+    v = (float)(v + up0 * dir_y);
+    mean_diff += up1;
+    alpha += up2;
+    if (up0 * up0 < min_update_squared) { converged = true; break; }
+  }
+  px_x = u; px_y = v;
+  return converged;
+}
+
+// ---- matcher state -------------------------------------------------------------------------------------------
+struct MatchState {  // the public Matcher members (matcher.h:70-79)
+  double A[2][2];
+  double epi_x, epi_y;
+  double epi_length_pyramid;
+  double h_inv;
+  double px_x, px_y;
+  V3d f_cur;
+  int search_level;
+  int reject;
+};
+SVO_D void initMatchState(MatchState& m) {
+  m.A[0][0] = m.A[0][1] = m.A[1][0] = m.A[1][1] = 0.0;
+  m.epi_x = m.epi_y = m.epi_length_pyramid = m.h_inv = m.px_x = m.px_y = 0.0;
+  m.f_cur = V3d{0, 0, 0};
+  m.search_level = 0;
+  m.reject = 0;
+}
+
+// c6. Matcher::findMatchDirect (matcher.cpp:31-141)
+SVO_D int findMatchDirect(const Group& g, const PyrView& ref_pyr, int ref_frame, const PyrView& cur_pyr, int cur_frame,
+                          const svo_camera& cam_ref, const svo_camera& cam_cur, const SE3d& T_cur_ref, const svo_feature& ft,
+                          double ref_depth, double guess_x, double guess_y, const svo_matcher_options& opt, uint8_t* pwb,
+                          MatchState& m) {
+  const int pxi0 = (int)ft.px[0] / (1 << ft.level), pxi1 = (int)ft.px[1] / (1 << ft.level);
+  const int boundary = 4 + 2;
+  if (pxi0 < boundary || pxi1 < boundary || pxi0 >= cam_ref.width / (1 << ft.level) - boundary ||
+      pxi1 >= cam_ref.height / (1 << ft.level) - boundary)
+    return kFailVisibility;
+  const V3d f_ref{ft.f[0], ft.f[1], ft.f[2]};
+  getWarpMatrixAffine(cam_ref, cam_cur, ft.px[0], ft.px[1], f_ref, ref_depth, T_cur_ref, ft.level, m.A);
+  m.search_level = getBestSearchLevel(m.A, ref_pyr.n_levels - 1);
+  if (!warpAffine10(g, m.A, levelView(ref_pyr, ref_frame, ft.level), ft.px[0], ft.px[1], ft.level, m.search_level, pwb))
+    return kFailWarp;
+  const double sc = (double)(1 << m.search_level);
+  double ps_x = guess_x / sc, ps_y = guess_y / sc;
+  const double start_x = ps_x, start_y = ps_y;
+  const ImgView cur = levelView(cur_pyr, cur_frame, m.search_level);
+  bool ok;
+  if (isEdgeletType(ft.type)) {
+    V2d d{m.A[0][0] * ft.grad[0] + m.A[0][1] * ft.grad[1], m.A[1][0] * ft.grad[0] + m.A[1][1] * ft.grad[1]};
+    d = normalized2(d);
+    ok = align1D(g, cur, d.x, d.y, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y, &m.h_inv);
+  } else {
+    ok = align2D(g, cur, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y);
+  }
+  if (!ok) return kFailAlignment;
+  const double ddx = ps_x - start_x, ddy = ps_y - start_y;
+  if (sqrt(ddx * ddx + ddy * ddy) > opt.max_patch_diff_ratio * 8) return kFailTooFar;
+  m.px_x = ps_x * sc; m.px_y = ps_y * sc;
+  m.f_cur = normalized3(camBackProject3(cam_cur, m.px_x, m.px_y));
+  return kSuccess;
+}
+
+// findLocalMatch (matcher.cpp:262-289)
+SVO_D int findLocalMatch(const Group& g, const PyrView& cur_pyr, int cur_frame, double dir_x, double dir_y, int patch_level,
+                         const svo_matcher_options& opt, bool align_1d, const uint8_t* pwb, MatchState& m) {
+  const double sc = (double)(1 << patch_level);
+  double ps_x = m.px_x / sc, ps_y = m.px_y / sc;
+  const ImgView cur = levelView(cur_pyr, cur_frame, patch_level);
+  bool res;
+  if (align_1d) res = align1D(g, cur, dir_x, dir_y, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y, &m.h_inv);
+  else res = align2D(g, cur, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y);
+  if (!res) return kFailAlignment;
+  m.px_x = ps_x * sc; m.px_y = ps_y * sc;
+  return kSuccess;
+}
+
+// ZMSSD<4> against the strided 8x8 window whose top-left is (x0, y0): lane r scores row r (patch_score.h:264-283)
+struct ZmssdRef {
+  unsigned ref_lo, ref_hi;  // this lane's row of the reference patch (8 bytes)
+  int sumA, sumAA;
+};
+SVO_D ZmssdRef makeZmssdRef(const Group& g, const uint8_t* pwb) {
+  const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
+  ZmssdRef z;
+  z.ref_lo = it[0] | (it[1] << 8) | (it[2] << 16) | (it[3] << 24);
+  z.ref_hi = it[4] | (it[5] << 8) | (it[6] << 16) | (it[7] << 24);
+  int sA = 0, sAA = 0;
+#pragma unroll
+  for (int x = 0; x < 8; ++x) { const int n = it[x]; sA += n; sAA += n * n; }
+  z.sumA = groupSum(g, sA);
+  z.sumAA = groupSum(g, sAA);
+  return z;
+}
+SVO_D int zmssdScore(const Group& g, const ZmssdRef& z, const ImgView& img, int x0, int y0) {
+  unsigned a, b;
+  loadRow8(img.data + (size_t)(y0 + g.r) * img.pitch, x0, a, b);
+  int sB = 0, sBB = 0, sAB = 0;
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    const int c = x < 4 ? byteOf(a, x) : byteOf(b, x - 4);
+    const int rf = x < 4 ? byteOf(z.ref_lo, x) : byteOf(z.ref_hi, x - 4);
+    sB += c; sBB += c * c; sAB += c * rf;
+  }
+  sB = groupSum(g, sB); sBB = groupSum(g, sBB); sAB = groupSum(g, sAB);
+  return z.sumAA - 2 * sAB + sBB - (z.sumA * z.sumA - 2 * z.sumA * sB + sB * sB) / 64;
+}
+SVO_D bool isPatchWithinImage(const svo_camera& cam, int px, int py, int patch_level) {  // matcher.cpp:314-322
+  return !(px < 8 || py < 8 || px >= (cam.width / (1 << patch_level) - 8) || py >= (cam.height / (1 << patch_level) - 8));
+}
+
+SVO_D V3d angleAxisRotate(const V3d& axis, double angle, const V3d& v) {  // Eigen::AngleAxisd::toRotationMatrix() * v
+  double s, c;
+  sincos(angle, &s, &c);
+  const V3d sin_axis = axis * s;
+  const V3d cos1_axis = axis * (1.0 - c);
+  M3d R;
+  double tmp;
+  tmp = cos1_axis.x * axis.y; R.m[0][1] = tmp - sin_axis.z; R.m[1][0] = tmp + sin_axis.z;
+  tmp = cos1_axis.x * axis.z; R.m[0][2] = tmp + sin_axis.y; R.m[2][0] = tmp - sin_axis.y;
+  tmp = cos1_axis.y * axis.z; R.m[1][2] = tmp - sin_axis.x; R.m[2][1] = tmp + sin_axis.x;
+  R.m[0][0] = cos1_axis.x * axis.x + c;
+  R.m[1][1] = cos1_axis.y * axis.y + c;
+  R.m[2][2] = cos1_axis.z * axis.z + c;
+  return R * v;
+}
+
+// matcher_utils::depthFromTriangulation (matcher.cpp:492-505)
+SVO_D int depthFromTriangulation(const SE3d& T_search_ref, const V3d& f_ref, const V3d& f_cur, double* depth) {
+  const V3d a0 = quatRotate(T_search_ref.q, f_ref);
+  const V3d a1 = f_cur;
+  const double m00 = dot3(a0, a0), m01 = dot3(a0, a1), m10 = dot3(a1, a0), m11 = dot3(a1, a1);
+  const double det = m00 * m11 - m10 * m01;
+  if (det < 0.000001) return kFailTriangulation;
+  const double invdet = 1.0 / det;
+  const V3d row0 = a0 * (-(m11 * invdet)) + a1 * (-(-m01 * invdet));
+  *depth = fabs(dot3(row0, T_search_ref.t));
+  return kSuccess;
+}
+
+// c7. Matcher::findEpipolarMatchDirect (matcher.cpp:157-241)
+SVO_D int findEpipolarMatchDirect(const Group& g, const PyrView& ref_pyr, int ref_frame, const PyrView& cur_pyr, int cur_frame,
+                                  const svo_camera& cam_ref, const svo_camera& cam_cur, const SE3d& T_cur_ref, const svo_feature& ft,
+                                  double d_estimate_inv, double d_min_inv, double d_max_inv, const svo_matcher_options& opt,
+                                  bool align_1d, uint8_t* pwb, MatchState& m, double* depth) {
+  int zmssd_best = 2000 * 64;
+  const V3d f_ref{ft.f[0], ft.f[1], ft.f[2]};
+  const V3d Rf = quatRotate(T_cur_ref.q, f_ref);
+  const V3d A = Rf + T_cur_ref.t * d_min_inv;
+  const V3d B = Rf + T_cur_ref.t * d_max_inv;
+  const V2d px_A = camProject3(cam_cur, A), px_B = camProject3(cam_cur, B);
+  m.epi_x = px_A.x - px_B.x; m.epi_y = px_A.y - px_B.y;
+  getWarpMatrixAffine(cam_ref, cam_cur, ft.px[0], ft.px[1], f_ref, 1.0 / fmax(0.000001, d_estimate_inv), T_cur_ref, ft.level, m.A);
+  m.reject = 0;
+  if (isEdgeletType(ft.type) && opt.epi_search_edgelet_filtering) {
+    const V2d gc = normalized2(V2d{m.A[0][0] * ft.grad[0] + m.A[0][1] * ft.grad[1], m.A[1][0] * ft.grad[0] + m.A[1][1] * ft.grad[1]});
+    const V2d en = normalized2(V2d{m.epi_x, m.epi_y});
+    const double cosangle = fabs(gc.x * en.x + gc.y * en.y);
+    if (cosangle < opt.epi_search_edgelet_max_angle) { m.reject = 1; return kFailAngle; }
+  }
+  m.search_level = getBestSearchLevel(m.A, ref_pyr.n_levels - 1);
+  m.epi_length_pyramid = sqrt(m.epi_x * m.epi_x + m.epi_y * m.epi_y) / (1 << m.search_level);
+  const V2d epi_dir = normalized2(V2d{m.epi_x, m.epi_y});
+  if (!warpAffine10(g, m.A, levelView(ref_pyr, ref_frame, ft.level), ft.px[0], ft.px[1], ft.level, m.search_level, pwb))
+    return kFailWarp;
+
+  if (m.epi_length_pyramid < 2.0) {
+    m.px_x = (px_A.x + px_B.x) / 2.0; m.px_y = (px_A.y + px_B.y) / 2.0;
+    const int res = findLocalMatch(g, cur_pyr, cur_frame, epi_dir.x, epi_dir.y, m.search_level, opt, align_1d, pwb, m);
+    if (res != kSuccess) return res;
+    m.f_cur = normalized3(camBackProject3(cam_cur, m.px_x, m.px_y));
+    return depthFromTriangulation(T_cur_ref, f_ref, m.f_cur, depth);
+  }
+
+  const ZmssdRef zref = makeZmssdRef(g, pwb);
+  const V3d C = Rf + T_cur_ref.t * d_estimate_inv;
+  const int pl = m.search_level;
+  const ImgView cur = levelView(cur_pyr, cur_frame, pl);
+  const double plscale = (double)(1 << pl);
+  if (opt.scan_on_unit_sphere) {  // matcher.cpp:415-488
+    size_t n_steps = (size_t)(m.epi_length_pyramid / 0.7);
+    n_steps = n_steps > (size_t)opt.max_epi_search_steps ? (size_t)opt.max_epi_search_steps : n_steps;
+    const size_t half_steps = n_steps / 2;
+    const V3d f_A = normalized3(A), f_B = normalized3(B);
+    const double step = acos(dot3(f_A, f_B)) / n_steps;
+    const V3d axis = normalized3(cross3(f_B, f_A));
+    const V3d f_C = normalized3(C);
+    V3d f_best = f_C;
+    int last_x = 0, last_y = 0;
+    for (size_t i = 0; i < n_steps; i++) {
+      double angle;
+      if (i < half_steps) angle = i * step;
+      else angle = (i - half_steps) * (-step);
+      const V3d f = angleAxisRotate(axis, angle, f_C);
+      const V2d px = camProject3(cam_cur, f);
+      const int pxi0 = (int)(px.x / plscale + 0.5), pxi1 = (int)(px.y / plscale + 0.5);
+      if (pxi0 == last_x && pxi1 == last_y) continue;
+      last_x = pxi0; last_y = pxi1;
+      if (!isPatchWithinImage(cam_cur, pxi0, pxi1, pl)) {
+        if (i < half_steps) { i = half_steps; continue; }
+        else break;
+      }
+      const int z = zmssdScore(g, zref, cur, pxi0 - 4, pxi1 - 4);
+      if (z < zmssd_best) { zmssd_best = z; f_best = f; }
+    }
+    const V2d pb = camProject3(cam_cur, f_best);
+    m.px_x = pb.x; m.px_y = pb.y;
+  } else {  // matcher.cpp:340-413
+    size_t n_steps = (size_t)(m.epi_length_pyramid / 0.7);
+    double step_x = (A.x / A.z - B.x / B.z) / n_steps, step_y = (A.y / A.z - B.y / B.z) / n_steps;
+    if (n_steps > (size_t)opt.max_epi_search_steps) n_steps = (size_t)opt.max_epi_search_steps;
+    const double uvC_x = C.x / C.z, uvC_y = C.y / C.z;
+    double uv_x = uvC_x, uv_y = uvC_y, best_x = uv_x, best_y = uv_y;
+    bool forward = true;
+    int last_x = 0, last_y = 0;
+    for (size_t i = 0; i < n_steps; ++i, uv_x += step_x, uv_y += step_y) {
+      const V2d px = camProject3(cam_cur, V3d{uv_x, uv_y, 1.0});
+      const int pxi0 = (int)(px.x / plscale + 0.5), pxi1 = (int)(px.y / plscale + 0.5);
+      if (pxi0 == last_x && pxi1 == last_y) continue;
+      last_x = pxi0; last_y = pxi1;
+      if (!isPatchWithinImage(cam_cur, pxi0, pxi1, pl)) {
+        if (forward) {
+          i = (size_t)(n_steps * 0.5);
+          step_x = -step_x; step_y = -step_y;
+          uv_x = uvC_x; uv_y = uvC_y;
+          forward = false;
+          continue;
+        } else {
+          break;
+        }
+      }
+      const int z = zmssdScore(g, zref, cur, pxi0 - 4, pxi1 - 4);
+      if (z < zmssd_best) { zmssd_best = z; best_x = uv_x; best_y = uv_y; }
+      if (forward && (double)i > n_steps * 0.5) {
+        step_x = -step_x; step_y = -step_y;
+        uv_x = uvC_x; uv_y = uvC_y;
+        forward = false;
+      }
+    }
+    const V2d pb = camProject3(cam_cur, V3d{best_x, best_y, 1.0});
+    m.px_x = pb.x; m.px_y = pb.y;
+  }
+
+  if (zmssd_best < 2000 * 64) {
+    if (opt.subpix_refinement) {
+      const int res = findLocalMatch(g, cur_pyr, cur_frame, epi_dir.x, epi_dir.y, m.search_level, opt, align_1d, pwb, m);
+      if (res != kSuccess) return res;
+    }
+    m.f_cur = normalized3(camBackProject3(cam_cur, m.px_x, m.px_y));
+    return depthFromTriangulation(T_cur_ref, f_ref, m.f_cur, depth);
+  }
+  return kFailScore;
+}
+
+}  // namespace svo_dev

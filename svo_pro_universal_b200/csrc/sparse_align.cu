@@ -1,0 +1,558 @@
+// (b) svo::SparseImgAlign::run — inverse-compositional sparse image alignment, whole run() in ONE launch.
+//
+// ref: src/svo_img_align/src/sparse_img_align.cpp:34-156 (run / evaluateError), :209-541 (utils)
+//      src/svo_img_align/src/sparse_img_align_base.cpp:35-107 (defaults, update, applyPrior)
+//      src/vikit/vikit_solver/include/vikit/solver/implementation/mini_least_squares_solver.hpp:42-107 (Gauss-Newton),
+//      :253-262 (H.ldlt().solve(g)); src/vikit/vikit_solver/src/robust_cost.cpp:48-60 (Tukey)
+//      src/svo_common/include/svo/common/frame.h:342-357, src/svo_common/src/frame.cpp:274-290 (projection Jacobians)
+//
+// Mapping: one CTA per frame-bundle pair; the CTA walks all pyramid levels and all Gauss-Newton iterations on the
+// device (no host round trips). One thread per feature patch:
+//   setup      feature subset (b2) + base caches xyz_ref / 2x6 projection Jacobian (b3) -> shared memory (k-major, no
+//              bank conflicts), once per run;
+//   per level  6x6 bilinear reference patch (b4) -> 32 doubles per feature in shared memory (centre + the 4-neighbour
+//              values the central differences need);
+//   per iter   project, visibility test, 5x5 cur-image taps via two aligned 32-bit loads per row, 16 residuals (b5);
+//              the per-pixel Jacobian factorises as J = [ (dx*Jp0 + dy*Jp1)*scale ; a6 ; a7 ], so H and g of a patch
+//              are a rank-2 expansion of 5 (+7 with illumination) weighted sums — 16x fewer outer products than the
+//              reference's per-pixel loop, identical in exact arithmetic (b6);
+//              warp-shuffle + cross-warp reduction of the 21+6+2 (or 36+8+2) accumulators, then thread 0 runs the
+//              LDLT solve, prior, SE3/illumination update and the convergence test (b7, b8).
+// All arithmetic is FP64 like the reference (FloatType = double, src/svo_common/include/svo/common/types.h:16);
+// Tukey weights and the alpha/beta handed to the residual are float, as in the reference signatures.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kWarps = kThreads / 32;
+constexpr int kNVmax = 36 + 8 + 2;
+constexpr int kPerSlotDoubles = 3 + 12 + 2 + 32;  // xyz, Jp0|Jp1, uv, patch
+
+struct AlignParams {
+  int n_cams, B, max_features, slots;
+  PyrView ref_pyr[SVO_MAX_CAMS], cur_pyr[SVO_MAX_CAMS];
+  const int* ref_frame_idx;
+  const int* cur_frame_idx;
+  svo_camera cams[SVO_MAX_CAMS];
+  double T_cam_imu[SVO_MAX_CAMS][7];
+  const double* T_imu_world_ref;
+  const double* T_imu_world_cur;
+  const int* n_features;
+  const double* px;
+  const double* f;
+  const double* depth;
+  const uint8_t* eligible;
+  svo_sparse_align_options opt;
+  const svo_align_prior* priors;
+  svo_align_result* results;
+};
+
+struct Ctl {
+  SE3d T, T_old;
+  double alpha, beta, alpha_old, beta_old;
+  SE3d T_cam_imu[SVO_MAX_CAMS], T_imu_cam[SVO_MAX_CAMS];
+  double Rt[SVO_MAX_CAMS][12];  // T_cur_ref of camera c: R row-major (9) + t (3)
+  double H[64];
+  double g[8];
+  double I_prior[8];  // diagonal of I_prior_
+  double tot[kNVmax];
+  double chi2;
+  float alpha_f, beta_f;
+  int stop, brk, n_total;
+  int warp_cnt[kWarps];
+  int iters[SVO_MAX_LEVELS];
+};
+
+SVO_D double warpSum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ref: src/vikit/vikit_solver/src/robust_cost.cpp:48-60 with b = 4.6851f (robust_cost.h:70)
+SVO_D float tukeyWeight(float error) {
+  const float b_square = 4.6851f * 4.6851f;
+  const float x_square = error * error;
+  if (x_square <= b_square) {
+    const float tmp = 1.0f - x_square / b_square;
+    return tmp * tmp;
+  }
+  return 0.0f;
+}
+
+// Symmetric solve H dx = g (lower triangle of H read), LDL^T without pivoting; a zero pivot (an all-zero row/column of
+// the PSD normal matrix: illumination parameters switched off) yields dx_k = 0, which is what Eigen's pivoted
+// LDLT::solve returns for those rows (mini_least_squares_solver.hpp:258).
+__device__ __noinline__ void ldltSolve8(const double* H, const double* g, double* dx) {
+  double a[8][8];
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j <= i; ++j) a[i][j] = H[i * 8 + j];
+  const double tol = 2.2250738585072014e-308;
+  for (int k = 0; k < 8; ++k) {
+    double d = a[k][k];
+    for (int j = 0; j < k; ++j) d -= a[k][j] * a[k][j] * a[j][j];
+    a[k][k] = d;
+    const bool ok = fabs(d) > 0.0;
+    for (int i = k + 1; i < 8; ++i) {
+      double s = a[i][k];
+      for (int j = 0; j < k; ++j) s -= a[i][j] * a[k][j] * a[j][j];
+      a[i][k] = ok ? s / d : s;
+    }
+  }
+  double x[8];
+  for (int i = 0; i < 8; ++i) {
+    double s = g[i];
+    for (int j = 0; j < i; ++j) s -= a[i][j] * x[j];
+    x[i] = s;
+  }
+  for (int i = 0; i < 8; ++i) x[i] = (fabs(a[i][i]) > tol) ? x[i] / a[i][i] : 0.0;
+  for (int i = 7; i >= 0; --i) {
+    double s = x[i];
+    for (int j = i + 1; j < 8; ++j) s -= a[j][i] * x[j];
+    x[i] = s;
+  }
+  for (int i = 0; i < 8; ++i) dx[i] = x[i];
+}
+
+SVO_D void storeRt(const SE3d& T, double* Rt) {
+  const M3d R = quatToMatrix(T.q);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = R.m[r][c];
+  Rt[9] = T.t.x; Rt[10] = T.t.y; Rt[11] = T.t.z;
+}
+
+// thread 0: T_cur_ref of every camera for the current state (sparse_img_align.cpp:140-142)
+SVO_D void refreshCams(Ctl& c, int n_cams) {
+  for (int k = 0; k < n_cams; ++k) storeRt(se3Mul(se3Mul(c.T_cam_imu[k], c.T), c.T_imu_cam[k]), c.Rt[k]);
+  c.alpha_f = (float)c.alpha;
+  c.beta_f = (float)c.beta;
+}
+
+template <bool ILLUM>
+__global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParams P) {
+  constexpr int D = ILLUM ? 8 : 6;
+  constexpr int NH = D * (D + 1) / 2;
+  constexpr int NV = NH + D + 2;
+  extern __shared__ __align__(16) double smem[];
+  const int slots = P.slots;
+  double* s_xyz = smem;                  // [3][slots]
+  double* s_jp = s_xyz + 3 * slots;      // [12][slots]
+  double* s_uv = s_jp + 12 * slots;      // [2][slots]
+  double* s_patch = s_uv + 2 * slots;    // [32][slots]
+  double* s_red = s_patch + 32 * slots;  // [kWarps][kNVmax]
+  Ctl& ctl = *reinterpret_cast<Ctl*>(s_red + kWarps * kNVmax);
+  uint8_t* s_cam = reinterpret_cast<uint8_t*>(&ctl + 1);  // [slots]
+
+  const int pair = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_cams = P.n_cams;
+  const svo_sparse_align_options& opt = P.opt;
+
+  // ---- setup -----------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int c = 0; c < n_cams; ++c) {
+      ctl.T_cam_imu[c] = se3Load(P.T_cam_imu[c]);
+      ctl.T_imu_cam[c] = se3Inv(ctl.T_cam_imu[c]);
+    }
+    const SE3d T_iref_world = se3Load(P.T_imu_world_ref + 7 * (size_t)pair);
+    const SE3d T_icur_world = se3Load(P.T_imu_world_cur + 7 * (size_t)pair);
+    ctl.T = se3Mul(T_icur_world, se3Inv(T_iref_world));  // sparse_img_align.cpp:74-75
+    ctl.alpha = opt.alpha_init;
+    ctl.beta = opt.beta_init;
+    ctl.stop = 0;
+    ctl.chi2 = 1e10;  // reset(): mini_least_squares_solver.hpp:243
+    ctl.n_total = 0;
+    for (int i = 0; i < SVO_MAX_LEVELS; ++i) ctl.iters[i] = 0;
+    for (int i = 0; i < 64; ++i) ctl.H[i] = 0.0;
+    for (int i = 0; i < 8; ++i) ctl.I_prior[i] = 0.0;
+  }
+  __syncthreads();
+
+  // b2 + b3: ordered compaction of the eligible, in-bounds features of every ref camera, base caches
+  int n_total = 0;
+  for (int c = 0; c < n_cams; ++c) {
+    const size_t fbase = ((size_t)pair * n_cams + c) * P.max_features;
+    const int n = min(P.n_features[(size_t)pair * n_cams + c], P.max_features);
+    const PyrView& rp = P.ref_pyr[c];
+    const int ml = opt.max_level;
+    const double scale_max = 1.0f / (1 << ml);
+    const int rows_m2 = rp.rows[ml] - 2, cols_m2 = rp.cols[ml] - 2;
+    const svo_camera& cam = P.cams[c];
+    for (int base = 0; base < n; base += kThreads) {
+      const int i = base + tid;
+      bool ok = false;
+      double pu = 0, pv = 0;
+      if (i < n && P.eligible[fbase + i]) {
+        pu = P.px[2 * (fbase + i)];
+        pv = P.px[2 * (fbase + i) + 1];
+        // sparse_img_align.cpp:249-257 with patch_size_wb = 6, patch_center_wb = 2.5
+        const int u_tl_i = (int)floor(pu * scale_max - 2.5);
+        const int v_tl_i = (int)floor(pv * scale_max - 2.5);
+        ok = !(u_tl_i < 0 || v_tl_i < 0 || u_tl_i + 6 >= cols_m2 || v_tl_i + 6 >= rows_m2);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) ctl.warp_cnt[warp] = __popc(bal);
+      __syncthreads();
+      int off = n_total, chunk = 0;
+      for (int w = 0; w < kWarps; ++w) {
+        if (w < warp) off += ctl.warp_cnt[w];
+        chunk += ctl.warp_cnt[w];
+      }
+      if (ok) {
+        const int s = off + __popc(bal & ((1u << lane) - 1u));
+        if (s < slots) {
+          // sparse_img_align.cpp:262-317
+          const double depth = P.depth[fbase + i];
+          const V3d fv{P.f[3 * (fbase + i)], P.f[3 * (fbase + i) + 1], P.f[3 * (fbase + i) + 2]};
+          const V3d xyz_ref = fv * depth;
+          const V3d p_imu = se3Apply(ctl.T_imu_cam[c], xyz_ref);
+          const SE3d& Tci = ctl.T_cam_imu[c];
+          const V3d pc = se3Apply(Tci, p_imu);
+          const M3d R = quatToMatrix(Tci.q);
+          double Jp[2][3];
+          double mult;
+          if (!opt.use_distortion_jacobian) {  // Frame::jacobian_xyz2uv_imu, frame.h:342-357, times focal length
+            const double s = -1.0 / pc.z;
+            Jp[0][0] = s; Jp[0][1] = 0.0; Jp[0][2] = s * (-pc.x / pc.z);
+            Jp[1][0] = 0.0; Jp[1][1] = s; Jp[1][2] = s * (-pc.y / pc.z);
+            mult = fabs(cam.fx);
+          } else {  // Frame::jacobian_xyz2image_imu, frame.cpp:274-290, times -1
+            camProject3Jac(cam, pc, Jp);
+            mult = -1.0;
+          }
+          double Bm[2][3];
+          for (int r = 0; r < 2; ++r)
+            for (int k = 0; k < 3; ++k) Bm[r][k] = Jp[r][0] * R.m[0][k] + Jp[r][1] * R.m[1][k] + Jp[r][2] * R.m[2][k];
+          // G = [I | -skew(p_imu)]
+          const double G[3][6] = {{1, 0, 0, 0, p_imu.z, -p_imu.y}, {0, 1, 0, -p_imu.z, 0, p_imu.x}, {0, 0, 1, p_imu.y, -p_imu.x, 0}};
+          for (int r = 0; r < 2; ++r)
+            for (int k = 0; k < 6; ++k)
+              s_jp[(r * 6 + k) * slots + s] = (Bm[r][0] * G[0][k] + Bm[r][1] * G[1][k] + Bm[r][2] * G[2][k]) * mult;
+          s_xyz[0 * slots + s] = xyz_ref.x; s_xyz[1 * slots + s] = xyz_ref.y; s_xyz[2 * slots + s] = xyz_ref.z;
+          s_uv[0 * slots + s] = pu; s_uv[1 * slots + s] = pv;
+          s_cam[s] = (uint8_t)c;
+        }
+      }
+      n_total += chunk;
+      __syncthreads();
+    }
+  }
+  n_total = min(n_total, slots);
+  const size_t ref_f0 = 0;
+  (void)ref_f0;
+
+  if (n_total > 0) {
+    if (tid == 0) {
+      ctl.n_total = n_total;
+      refreshCams(ctl, n_cams);
+      ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
+    }
+    const bool est_gain = ILLUM && opt.estimate_illumination_gain;
+    const bool est_off = ILLUM && opt.estimate_illumination_offset;
+    const float wscale_f = (float)opt.weight_scale;
+    const int n_round = ((n_total + kThreads - 1) / kThreads) * kThreads;
+    int level_slot = 0;
+
+    for (int level = opt.max_level; level >= opt.min_level; --level, ++level_slot) {
+      const double scale = 1.0f / (1 << level);
+      // ---- b4: reference patches of this level (sparse_img_align.cpp:319-403) ----
+      for (int s = tid; s < n_total; s += kThreads) {
+        const int c = s_cam[s];
+        const PyrView& rp = P.ref_pyr[c];
+        const int rf = P.ref_frame_idx ? P.ref_frame_idx[(size_t)pair * n_cams + c] : pair;
+        const uint8_t* img = rp.level(rf, level);
+        const int pitch = rp.pitch[level];
+        const double u_tl = s_uv[s] * scale - 2.5, v_tl = s_uv[slots + s] * scale - 2.5;
+        const int ui = (int)floor(u_tl), vi = (int)floor(v_tl);
+        const double su = u_tl - ui, sv = v_tl - vi;
+        const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
+        unsigned ra, rb;
+        loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
+#pragma unroll
+        for (int y = 0; y < 6; ++y) {
+          unsigned na, nb;
+          loadRow8(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
+#pragma unroll
+          for (int x = 0; x < 6; ++x) {
+            const bool used = (y >= 1 && y <= 4) || (x >= 1 && x <= 4);
+            if (!used) continue;
+            const unsigned t0 = x < 4 ? byteOf(ra, x) : byteOf(rb, x - 4);
+            const unsigned t1 = (x + 1) < 4 ? byteOf(ra, x + 1) : byteOf(rb, x + 1 - 4);
+            const unsigned b0 = x < 4 ? byteOf(na, x) : byteOf(nb, x - 4);
+            const unsigned b1 = (x + 1) < 4 ? byteOf(na, x + 1) : byteOf(nb, x + 1 - 4);
+            const double val = wtl * t0 + wtr * t1 + wbl * b0 + wbr * b1;
+            const int k = (y == 0) ? (x - 1) : (y == 5) ? (28 + x - 1) : (4 + (y - 1) * 6 + x);
+            s_patch[k * slots + s] = val;
+          }
+          ra = na; rb = nb;
+        }
+      }
+      __syncthreads();
+
+      // ---- Gauss-Newton iterations of this level (mini_least_squares_solver.hpp:42-107) ----
+      const int max_iter = opt.max_iter;
+      for (int iter = 0; iter < max_iter; ++iter) {
+        // zero per-warp partials
+        for (int k = lane; k < NV; k += 32) s_red[warp * kNVmax + k] = 0.0;
+        __syncwarp();
+        const float alpha_f = ctl.alpha_f, beta_f = ctl.beta_f;
+        for (int s = tid; s < n_round; s += kThreads) {
+          bool vis = false;
+          double sxx = 0, sxy = 0, syy = 0, gx = 0, gy = 0, chi = 0;
+          double sx6 = 0, sy6 = 0, sx7 = 0, sy7 = 0, s66 = 0, s67 = 0, s77 = 0, g6 = 0, g7 = 0;
+          if (s < n_total) {
+            const int c = s_cam[s];
+            const double* Rt = ctl.Rt[c];
+            const double X = s_xyz[s], Y = s_xyz[slots + s], Z = s_xyz[2 * slots + s];
+            const V3d pc{Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9], Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10],
+                         Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11]};
+            if (!(pc.z < 0.0)) {  // sparse_img_align.cpp:432-438
+              const V2d uvc = camProject3(P.cams[c], pc);
+              const PyrView& cp = P.cur_pyr[c];
+              const double u_tl = uvc.x * scale - 1.5, v_tl = uvc.y * scale - 1.5;
+              // sparse_img_align.cpp:449-456 (NaN coordinates fall through as "visible" in the reference; they cannot
+              // be sampled, so they are dropped here)
+              if (!(u_tl < 0.0 || v_tl < 0.0 || u_tl + 4 + 2.0 >= cp.cols[level] || v_tl + 4 + 2.0 >= cp.rows[level]) &&
+                  u_tl == u_tl && v_tl == v_tl) {
+                vis = true;
+                const int cf = P.cur_frame_idx ? P.cur_frame_idx[(size_t)pair * n_cams + c] : pair;
+                const uint8_t* img = cp.level(cf, level);
+                const int pitch = cp.pitch[level];
+                const int ui = (int)floor(u_tl), vi = (int)floor(v_tl);
+                const double su = u_tl - ui, sv = v_tl - vi;
+                const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
+                const double gain = 1.0 + alpha_f;
+                unsigned ra, rb;
+                loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                  unsigned na, nb;
+                  loadRow8(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
+#pragma unroll
+                  for (int x = 0; x < 4; ++x) {
+                    const unsigned t0 = byteOf(ra, x);
+                    const unsigned t1 = x < 3 ? byteOf(ra, x + 1) : byteOf(rb, 0);
+                    const unsigned b0 = byteOf(na, x);
+                    const unsigned b1 = x < 3 ? byteOf(na, x + 1) : byteOf(nb, 0);
+                    const double I = wtl * t0 + wtr * t1 + wbl * b0 + wbr * b1;
+                    // 6x6 patch (Y=y+1, X=x+1): centre, left/right, up/down
+                    const int kc = 4 + y * 6 + (x + 1);
+                    const int ku = (y == 0) ? x : (4 + (y - 1) * 6 + (x + 1));
+                    const int kd = (y == 3) ? (28 + x) : (4 + (y + 1) * 6 + (x + 1));
+                    const double ref = s_patch[kc * slots + s];
+                    const double dx = 0.5 * (s_patch[(kc + 1) * slots + s] - s_patch[(kc - 1) * slots + s]);
+                    const double dy = 0.5 * (s_patch[kd * slots + s] - s_patch[ku * slots + s]);
+                    const double res = (I * gain + beta_f) - ref;  // sparse_img_align.cpp:488-489
+                    double w = 1.0;
+                    if (opt.robustification) w = (double)tukeyWeight((float)(res / wscale_f));
+                    const double wdx = w * dx, wdy = w * dy;
+                    sxx += wdx * dx; sxy += wdx * dy; syy += wdy * dy;
+                    gx += wdx * res; gy += wdy * res;
+                    chi += res * res * w;
+                    if (ILLUM) {
+                      const double a6 = est_gain ? -ref : 0.0, a7 = est_off ? -1.0 : 0.0;
+                      sx6 += wdx * a6; sy6 += wdy * a6; sx7 += wdx * a7; sy7 += wdy * a7;
+                      s66 += w * a6 * a6; s67 += w * a6 * a7; s77 += w * a7 * a7;
+                      g6 += w * a6 * res; g7 += w * a7 * res;
+                    }
+                  }
+                  ra = na; rb = nb;
+                }
+              }
+            }
+          }
+          if (__ballot_sync(0xffffffffu, vis) == 0u) continue;
+          // rank-2 expansion + warp reduction, one accumulator at a time
+          double jp0[6], jp1[6], ua[6], va[6];
+          const int sl = (s < n_total) ? s : 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            jp0[k] = s_jp[k * slots + sl] * scale;
+            jp1[k] = s_jp[(6 + k) * slots + sl] * scale;
+            ua[k] = sxx * jp0[k] + sxy * jp1[k];
+            va[k] = sxy * jp0[k] + syy * jp1[k];
+          }
+          double* red = s_red + warp * kNVmax;
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+#pragma unroll
+            for (int b = a; b < D; ++b) {
+              double v;
+              if (b < 6) v = ua[a] * jp0[b] + va[a] * jp1[b];
+              else if (a < 6) v = (b == 6) ? (jp0[a] * sx6 + jp1[a] * sy6) : (jp0[a] * sx7 + jp1[a] * sy7);
+              else v = (a == 6 && b == 6) ? s66 : (a == 6 ? s67 : s77);
+              v = warpSum(v);
+              if (lane == 0) red[idx] += v;
+              ++idx;
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            double v;
+            if (a < 6) v = -(jp0[a] * gx + jp1[a] * gy);
+            else v = (a == 6) ? -g6 : -g7;
+            v = warpSum(v);
+            if (lane == 0) red[NH + a] += v;
+          }
+          {
+            double v = warpSum(chi);
+            if (lane == 0) red[NH + D] += v;
+            v = warpSum(vis ? 16.0 : 0.0);
+            if (lane == 0) red[NH + D + 1] += v;
+          }
+        }
+        __syncthreads();
+        if (tid < NV) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) t += s_red[w * kNVmax + tid];
+          ctl.tot[tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          ctl.iters[level_slot] = iter + 1;
+          double H[64], g[8], dx[8];
+          for (int i = 0; i < 64; ++i) H[i] = 0.0;
+          for (int i = 0; i < 8; ++i) g[i] = 0.0;
+          int idx = 0;
+          for (int a = 0; a < D; ++a)
+            for (int b = a; b < D; ++b) { H[a * 8 + b] = ctl.tot[idx]; H[b * 8 + a] = ctl.tot[idx]; ++idx; }
+          for (int a = 0; a < D; ++a) g[a] = ctl.tot[NH + a];
+          const double new_chi2 = (double)(float)(ctl.tot[NH + D] / ctl.tot[NH + D + 1]);  // float chi2 / n_meas (:540)
+          if (P.priors) {  // applyPrior, sparse_img_align_base.cpp:77-107
+            const svo_align_prior& pr = P.priors[pair];
+            if (iter == 0) {
+              double mt = 0, mr = 0;
+              for (int j = 0; j < 3; ++j) mt = fmax(mt, fabs(H[j * 8 + j]));
+              for (int j = 3; j < 6; ++j) mr = fmax(mr, fabs(H[j * 8 + j]));
+              for (int j = 0; j < 3; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_trans * mt;
+              for (int j = 3; j < 6; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_rot * mr;
+              ctl.I_prior[6] = opt.lambda_alpha * H[6 * 8 + 6];
+              ctl.I_prior[7] = opt.lambda_beta * H[7 * 8 + 7];
+            }
+            for (int j = 0; j < 8; ++j) H[j * 8 + j] += ctl.I_prior[j];
+            const SE3d Tp = se3Load(pr.T);
+            const SE3d E = se3Mul(se3Inv(Tp), ctl.T);
+            const V3d lr = quatLog(E.q);
+            const double l[6] = {E.t.x, E.t.y, E.t.z, lr.x, lr.y, lr.z};
+            for (int j = 0; j < 6; ++j) g[j] += ctl.I_prior[j] * l[j];
+            g[6] += ctl.I_prior[6] * (pr.alpha - ctl.alpha);
+            g[7] += ctl.I_prior[7] * (pr.beta - ctl.beta);
+          }
+          for (int i = 0; i < 64; ++i) ctl.H[i] = H[i];
+          ldltSolve8(H, g, dx);
+          if (dx[0] != dx[0]) ctl.stop = 1;  // solveDefaultImpl: isnan(dx[0]) -> stop_
+          int brk = 0;
+          if (ctl.stop) {
+            ctl.T = ctl.T_old; ctl.alpha = ctl.alpha_old; ctl.beta = ctl.beta_old;  // rollback (:76-84)
+            brk = 1;
+          } else {
+            // update, sparse_img_align_base.cpp:64-75
+            SE3d inc;
+            inc.q = quatExp(V3d{-dx[3], -dx[4], -dx[5]});
+            inc.t = V3d{-dx[0], -dx[1], -dx[2]};
+            SE3d Tn = se3Mul(ctl.T, inc);
+            const double an = (ctl.alpha - dx[6]) / (1.0 + dx[6]);
+            const double bn = (ctl.beta - dx[7]) / (1.0 + dx[6]);
+            quatNormalize(Tn.q);
+            ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
+            ctl.T = Tn; ctl.alpha = an; ctl.beta = bn;
+            ctl.chi2 = new_chi2;
+            double x_norm = -1.0;
+            for (int i = 0; i < 8; ++i) { const double a = fabs(dx[i]); if (a > x_norm) x_norm = a; }
+            if (x_norm < opt.eps) brk = 1;
+          }
+          refreshCams(ctl, n_cams);
+          ctl.brk = brk;
+        }
+        __syncthreads();
+        if (ctl.brk) break;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- outputs (sparse_img_align.cpp:102-112) ----
+  if (tid == 0) {
+    svo_align_result& r = P.results[pair];
+    const SE3d T_iref_world = se3Load(P.T_imu_world_ref + 7 * (size_t)pair);
+    se3Store(ctl.T, r.T_icur_iref);
+    for (int c = 0; c < SVO_MAX_CAMS; ++c) {
+      if (c < n_cams) se3Store(se3Mul(se3Mul(ctl.T_cam_imu[c], ctl.T), T_iref_world), r.T_f_w[c]);
+      else for (int k = 0; k < 7; ++k) r.T_f_w[c][k] = 0.0;
+    }
+    r.alpha = ctl.alpha;
+    r.beta = ctl.beta;
+    r.chi2 = ctl.chi2;
+    for (int i = 0; i < 64; ++i) r.H[i] = ctl.H[i];
+    r.n_tracked = n_total;
+    for (int i = 0; i < SVO_MAX_LEVELS; ++i) r.iters[i] = ctl.iters[i];
+    r.stop = ctl.stop;
+  }
+}
+
+}  // namespace
+
+extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cuda_pyr* const* ref_pyr,
+                                     const svo_cuda_pyr* const* cur_pyr, const int* ref_frame_idx, const int* cur_frame_idx,
+                                     const svo_camera* cams, const double* T_cam_imu, int B, const double* T_imu_world_ref,
+                                     const double* T_imu_world_cur, const int* n_features, int max_features, const double* px,
+                                     const double* f, const double* depth, const uint8_t* eligible,
+                                     const svo_sparse_align_options* opt, const svo_align_prior* priors,
+                                     svo_align_result* results, svo_mem mem) {
+  if (!ctx || n_cams < 1 || n_cams > SVO_MAX_CAMS || !ref_pyr || !cur_pyr || !cams || !T_cam_imu || B < 0 || !T_imu_world_ref ||
+      !T_imu_world_cur || !n_features || max_features < 1 || !px || !f || !depth || !eligible || !opt || !results)
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_sparse_align: bad arguments");
+  if (opt->min_level < 0 || opt->max_level < opt->min_level || opt->max_iter < 0 || opt->max_level - opt->min_level >= SVO_MAX_LEVELS)
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_sparse_align: bad level range / max_iter");
+  for (int c = 0; c < n_cams; ++c) {
+    if (!ref_pyr[c] || !cur_pyr[c] || opt->max_level >= ref_pyr[c]->n_levels || opt->max_level >= cur_pyr[c]->n_levels)
+      return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_sparse_align: pyramid has fewer levels than max_level+1");
+    if (!ref_frame_idx && ref_pyr[c]->n_frames < B) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_sparse_align: ref batch < B");
+    if (!cur_frame_idx && cur_pyr[c]->n_frames < B) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_sparse_align: cur batch < B");
+  }
+  if (B == 0) return SVO_OK;
+  cudaSetDevice(ctx->device);
+
+  AlignParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_cams = n_cams; P.B = B; P.max_features = max_features;
+  const int slots = ((n_cams * max_features + 7) / 8) * 8;
+  P.slots = slots;
+  const size_t smem = (size_t)slots * kPerSlotDoubles * 8 + (size_t)kWarps * kNVmax * 8 + sizeof(Ctl) + slots + 16;
+  if (smem > 227 * 1024) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: n_cams*max_features exceeds the shared-memory capacity (~590 features per bundle)");
+  for (int c = 0; c < n_cams; ++c) {
+    P.ref_pyr[c] = makeView(ref_pyr[c]);
+    P.cur_pyr[c] = makeView(cur_pyr[c]);
+    P.cams[c] = cams[c];
+    for (int k = 0; k < 7; ++k) P.T_cam_imu[c][k] = T_cam_imu[7 * c + k];
+  }
+  P.opt = *opt;
+  Stager st(ctx, mem);
+  const size_t nf = (size_t)B * n_cams * max_features;
+  P.ref_frame_idx = st.in(ref_frame_idx, (size_t)B * n_cams);
+  P.cur_frame_idx = st.in(cur_frame_idx, (size_t)B * n_cams);
+  P.T_imu_world_ref = st.in(T_imu_world_ref, (size_t)B * 7);
+  P.T_imu_world_cur = st.in(T_imu_world_cur, (size_t)B * 7);
+  P.n_features = st.in(n_features, (size_t)B * n_cams);
+  P.px = st.in(px, nf * 2);
+  P.f = st.in(f, nf * 3);
+  P.depth = st.in(depth, nf);
+  P.eligible = st.in(eligible, nf);
+  P.priors = st.in(priors, (size_t)B);
+  P.results = st.out(results, (size_t)B);
+  if (st.failed()) return st.finish();
+
+  const bool illum = opt->estimate_illumination_gain || opt->estimate_illumination_offset;
+  if (illum) {
+    SVO_CUDA_TRY(ctx, cudaFuncSetAttribute(sparse_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparse_align_kernel<true><<<B, kThreads, smem, ctx->stream>>>(P);
+  } else {
+    SVO_CUDA_TRY(ctx, cudaFuncSetAttribute(sparse_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparse_align_kernel<false><<<B, kThreads, smem, ctx->stream>>>(P);
+  }
+  SVO_LAUNCH_CHECK(ctx);
+  return st.finish();
+}

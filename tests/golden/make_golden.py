@@ -1,0 +1,91 @@
+"""Generates the committed golden fixtures under tests/golden/ (run in the build container, where /root/reference exists).
+
+fast_ref_golden.npz   outputs of the REFERENCE's own FAST code (oracle/_ref/libfast_ref.so, compiled from
+                      /root/reference/src/fast_neon/src) on seeded synthetic images: segment test (SSE2 + plain), score and
+                      3x3 non-max, per pyramid level. These pin the oracle's rows a2-a4 and the CUDA kernels on boxes where
+                      /root/reference does not exist.
+oracle_golden.npz     outputs of the CPU oracle (restated reference arithmetic) for pyramid / sparse alignment / matcher /
+                      depth filter on seeded inputs: regression pins for the oracle itself ("parity unpinned" rows).
+Usage: python tests/golden/make_golden.py
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import orc  # noqa: E402
+from svo_pro_universal_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def fast_golden():
+    assert orc.ref_lib() is not None, "oracle/_ref/libfast_ref.so missing: run make -C oracle"
+    out = {}
+    cases = [(0, 752, 480, 10), (1, 752, 480, 20), (2, 160, 120, 5), (3, 47, 30, 7), (4, 21, 13, 10), (5, 22, 9, 10)]
+    out["cases"] = np.array(cases, np.int32)
+    for seed, w, h, thr in cases:
+        img0 = synth.make_image(seed, w, h, n_rect=max(8, w * h // 400))
+        pyr = orc.create_img_pyramid(img0, 3 if min(w, h) >= 28 else 1)
+        out[f"img_sha_{seed}"] = np.array(sha(img0))
+        for l, im in enumerate(pyr):
+            xy = orc.fast_detect(im, thr, 10, "ref_sse2")
+            xy_plain = orc.fast_detect(im, thr, 10, "ref_plain10")
+            assert np.array_equal(xy, xy_plain)
+            sc = orc.fast_score10(im, xy, thr, "ref")
+            nm = orc.fast_nonmax3x3(xy, sc, "ref")
+            xy9 = orc.fast_detect(im, thr, 9, "ref_plain9")
+            out[f"xy_{seed}_{l}"] = xy
+            out[f"score_{seed}_{l}"] = sc.astype(np.int16)
+            out[f"nonmax_{seed}_{l}"] = nm
+            out[f"xy9_{seed}_{l}"] = xy9
+    np.savez_compressed(os.path.join(HERE, "fast_ref_golden.npz"), **out)
+    print("fast_ref_golden.npz", os.path.getsize(os.path.join(HERE, "fast_ref_golden.npz")))
+
+
+def oracle_golden():
+    out = {}
+    # pyramid checksums
+    img = synth.make_image(11)
+    for mode in (-1, 0):
+        pyr = orc.create_img_pyramid(img, 5, mode)
+        out[f"pyr_sha_mode{mode}"] = np.array([sha(p) for p in pyr])
+    # fastDetector per-cell corners
+    for seed in (0, 5):
+        c = orc.fast_detector(synth.make_image(seed))
+        out[f"corners_{seed}"] = c
+    # sparse alignment
+    for seed in (1, 2, 3):
+        d = synth.make_align_pair(seed)
+        keep = []
+        rp = orc.create_img_pyramid(d["ref_img"], 5)
+        cp = orc.create_img_pyramid(d["cur_img"], 5)
+        rf = orc.make_frame(rp, d["cam"], d["T_cam_imu"], d["T_imu_world_ref"], d["px"], d["f"], d["depth"], d["eligible"], keep=keep)
+        cf = orc.make_frame(cp, d["cam"], d["T_cam_imu"], d["T_imu_world_cur_init"], keep=keep)
+        for name, kw in (("default", {}), ("illum_robust", dict(estimate_illumination_gain=1, estimate_illumination_offset=1, robustification=1))):
+            r = orc.sparse_align([rf], [cf], orc.default_align_options(**kw))
+            out[f"align_{name}_{seed}_T"] = np.array(r.T_icur_iref)
+            out[f"align_{name}_{seed}_ab"] = np.array([r.alpha, r.beta, r.chi2])
+            out[f"align_{name}_{seed}_iters"] = np.array(list(r.iters), np.int32)
+            out[f"align_{name}_{seed}_n"] = np.array(r.n_tracked)
+    # Vogiatzis filter known-answer rows
+    st = np.array([0.25, 0.0123, 10.0, 10.0])
+    rows = []
+    for z, tau2 in ((0.26, 1e-4), (0.24, 4e-4), (0.9, 1e-4), (0.255, 2e-5)):
+        ok = orc.lib().orc_update_filter_vogiatzis(z, tau2, 1.0 / 1.5, st.ctypes.data_as(orc.f64p))
+        rows.append(np.concatenate([[z, tau2, ok], st]))
+    out["vogiatzis_rows"] = np.array(rows)
+    np.savez_compressed(os.path.join(HERE, "oracle_golden.npz"), **out)
+    print("oracle_golden.npz", os.path.getsize(os.path.join(HERE, "oracle_golden.npz")))
+
+
+if __name__ == "__main__":
+    fast_golden()
+    oracle_golden()
