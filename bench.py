@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Headline benchmark: aligned frame-pairs/s (752x480, 4-level SparseImgAlign, ~180 features) and p50 single-pair latency.
+
+    python bench.py --gpus N --steps K --warmup W                 # our CUDA path (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference CPU path (oracle port) on the host cores
+
+One STEP = one pass of the hot path over one batch of B synthetic frame pairs per GPU:
+    build the pyramid of every NEW (cur) frame from its level-0 image  ->  SparseImgAlign::run for every pair
+(the ref frame's pyramid already exists: it was the previous step's new frame — src/svo/src/frame_handler_base.cpp:184-186
+builds it at frame creation, :634 aligns against the last frame).
+`value`  : whole-job pairs/s with every input resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`    : the same metric through the C ABI with HOST buffers: per step the new frames' level-0 images and the feature
+           arrays go host(pinned)->device and the per-pair results come back, all inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, N_LEVELS, N_FEATURES = 752, 480, 5, 180
+# per frame pair, mono, levels 4->1: ref L1-L4 + cur L1-L4 (2 x 119,850 B) + 180 x 40 B features + 2 x 72 B state
+ALGO_BYTES_PER_PAIR = 247044
+METRIC = "aligned frame-pairs/sec (752x480, 4-level SparseImgAlign, ~180 features)"
+
+
+def make_unique_pairs(n_unique, seed0):
+    from svo_pro_universal_b200 import synth
+    return [synth.make_align_pair(seed0 + s, n_features=N_FEATURES) for s in range(n_unique)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def orc_frames(orc, pairs, keep):
+    """Oracle frames (ref with prebuilt pyramid + features, cur template) for a list of synthetic pairs."""
+    refs, curs, l0 = [], [], []
+    for d in pairs:
+        rp = orc.create_img_pyramid(d["ref_img"], N_LEVELS)
+        refs.append(orc.make_frame(rp, d["cam"], d["T_cam_imu"], d["T_imu_world_ref"], d["px"], d["f"], d["depth"], d["eligible"], keep=keep))
+        curs.append(orc.make_frame([d["cur_img"]], d["cam"], d["T_cam_imu"], d["T_imu_world_cur_init"], keep=keep))
+        l0.append(d["cur_img"])
+    return refs, curs, l0
+
+
+def cpu_step_fn(n_pairs_per_step, n_threads, seed0=1000, n_unique=16):
+    """Returns (fn, sample description); fn() runs one bounded CPU step (pyramid + SparseImgAlign::run per pair) on all threads."""
+    from oracle import orc
+    uniq = make_unique_pairs(n_unique, seed0)
+    keep = []
+    refs, curs, l0 = orc_frames(orc, uniq, keep)
+    idx = [i % n_unique for i in range(n_pairs_per_step)]
+    R, Cc, L = [refs[i] for i in idx], [curs[i] for i in idx], [l0[i] for i in idx]
+    opt = orc.default_align_options()
+
+    def fn():
+        return orc.pyramid_align_batch(L, R, Cc, opt, N_LEVELS, n_threads)
+
+    fn._keep = (keep, uniq)
+    return fn, f"{n_pairs_per_step} pairs/step ({n_unique} unique synthetic pairs tiled), oracle port of the reference CPU path, {n_threads} threads"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    n_threads = os.cpu_count() or 1
+    per_step = max(64, 16 * n_threads)
+    fn, sample = cpu_step_fn(per_step, n_threads)
+    for _ in range(max(1, min(args.warmup, 3))):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    lat_fn, _ = cpu_step_fn(1, 1)
+    lats = []
+    for _ in range(50):
+        t = time.perf_counter(); lat_fn(); lats.append(time.perf_counter() - t)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "SparseImgAlign batch: pyramid of the new frame + run() per pair, 752x480, levels 4->1, 180 features, 4x4 patches",
+                   "pairs_per_step": per_step, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": n_threads, "kind": "port", "sample": sample,
+                         "latency_ms_p50_single_thread": 1e3 * float(np.median(lats))},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from svo_pro_universal_b200 import capi, batch, shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)  # our kernels and torch's events share one stream
+
+    B = args.batch  # pairs per GPU per step (weak scaling: per-GPU work is fixed)
+    uniq = make_unique_pairs(args.unique, 5000 + 1000 * rank)
+    pk = batch.tile_batch(batch.pack_align_batch(uniq, max_features=N_FEATURES), B)
+    cam = capi.Camera.from_dict(uniq[0]["cam"])
+    gopt = capi.sparse_align_options()
+
+    ref = capi.Pyramid(ctx, B, W, H, N_LEVELS)
+    cur = capi.Pyramid(ctx, B, W, H, N_LEVELS)
+    # pinned host copies (the e2e leg reads these every step)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_cur = pin(pk["cur_imgs"])
+    h = {k: pin(pk[k]) for k in ("T_imu_world_ref", "T_imu_world_cur", "n_features", "px", "f", "depth", "eligible")}
+    h_res = torch.zeros(B * capi.ALIGN_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    # device-resident copies (the `value` leg)
+    d = {k: v.to(dev) for k, v in h.items()}
+    d_cur0 = h_cur.to(dev)
+    d_res = torch.zeros(B * capi.ALIGN_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    ref.upload(torch.from_numpy(pk["ref_imgs"]).to(dev))
+    ref.build()
+    torch.cuda.synchronize()
+
+    def step_device(ev=None):
+        cur.upload(d_cur0)              # new frames arrive (device-to-device: inputs are already in HBM)
+        cur.build()
+        if ev:
+            ev[0].record(stream)
+        capi.sparse_align(ctx, [ref], [cur], [cam], pk["T_cam_imu"], d["T_imu_world_ref"], d["T_imu_world_cur"], d["n_features"],
+                          d["px"], d["f"], d["depth"], d["eligible"], gopt, results=d_res)
+        if ev:
+            ev[1].record(stream)
+
+    def step_e2e():
+        cur.upload(h_cur)               # H2D of the new frames' level-0 images from pinned memory
+        cur.build()
+        capi.sparse_align(ctx, [ref], [cur], [cam], pk["T_cam_imu"], h["T_imu_world_ref"], h["T_imu_world_cur"], h["n_features"],
+                          h["px"], h["f"], h["depth"], h["eligible"], gopt, results=h_res)  # stages H2D, copies results D2H, syncs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: device-resident ----
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0.record(stream)
+    for s in range(args.steps):
+        step_device(kev[s])
+    e1.record(stream)
+    barrier()
+    launches = ctx.launches - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    align_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI ----
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+    e2e_wall = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * B * args.steps / (max(e2e_ms, e2e_wall) * 1e-3)
+    h2d = int(h_cur.numel() + sum(v.numel() * v.element_size() for v in h.values()))
+    d2h = int(h_res.numel())
+
+    # sanity: the timed device path produced converged poses (guards against timing a no-op)
+    res = d_res.cpu().numpy().view(capi.ALIGN_RESULT_DTYPE)
+    assert (res["n_tracked"] > 100).all() and np.isfinite(res["T_icur_iref"]).all()
+
+    if world > 1:  # the only collective of the job: a final gather of the per-pair results
+        lo, hi = shard.partition(world * B, world, rank)
+        gathered = shard.gather_to_rank0(res, world * B)
+        assert rank != 0 or gathered.shape[0] == world * B
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- single-pair latency (B = 1 through the host-buffer path) ----
+    ref1 = capi.Pyramid(ctx, 1, W, H, N_LEVELS); cur1 = capi.Pyramid(ctx, 1, W, H, N_LEVELS)
+    ref1.upload(torch.from_numpy(pk["ref_imgs"][:1]).to(dev)); ref1.build()
+    h1 = {k: pin(pk[k][:1]) for k in h}
+    h1_img = pin(pk["cur_imgs"][:1]); h1_res = torch.zeros(capi.ALIGN_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    lat, lat_align = [], []
+    for i in range(120):
+        t = time.perf_counter()
+        cur1.upload(h1_img); cur1.build()
+        ctx.synchronize()
+        t_mid = time.perf_counter()
+        capi.sparse_align(ctx, [ref1], [cur1], [cam], pk["T_cam_imu"], h1["T_imu_world_ref"], h1["T_imu_world_cur"], h1["n_features"],
+                          h1["px"], h1["f"], h1["depth"], h1["eligible"], gopt, results=h1_res)
+        t_end = time.perf_counter()
+        if i >= 20:
+            lat.append(t_end - t); lat_align.append(t_end - t_mid)
+
+    # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----
+    n_threads = os.cpu_count() or 1
+    per_step = max(64, 16 * n_threads)
+    fn, sample = cpu_step_fn(per_step, n_threads)
+    fn()
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 10.0:
+        fn(); reps += 1
+    cpu_value = per_step * reps / (time.perf_counter() - t0)
+    lat_fn, _ = cpu_step_fn(1, 1)
+    cl = []
+    for _ in range(40):
+        t = time.perf_counter(); lat_fn(); cl.append(time.perf_counter() - t)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ALGO_BYTES_PER_PAIR * B / (align_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "SparseImgAlign batch: pyramid of the new frame + run() per pair, 752x480, levels 4->1, 180 features, 4x4 patches "
+                               "(BASELINE configs[0] batched)",
+                   "pairs_per_gpu_per_step": B, "unique_pairs": args.unique, "parallelism": f"frame-pair sharding x{world}, no collective in the hot path",
+                   "l2": "inputs larger than L2: %.1f GB of frame data per step per GPU vs 126 MB L2" % ((h_cur.numel() + B * 2 * 119850) / 1e9)},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "new frames' level-0 images + feature arrays H2D from pinned memory, results D2H, every step"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "sparse_align_kernel<false>", "kernel_ms": align_ms,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                     "note": "algorithmic bytes 247,044 B/pair; the kernel is FP64-issue/latency bound, not HBM bound (DESIGN.md)"},
+        "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": n_threads, "kind": "port", "sample": sample + ", ~10 s",
+                         "latency_ms_p50_single_thread": 1e3 * float(np.median(cl))},
+        "latency": {"p50_ms_pair_e2e": 1e3 * float(np.median(lat)), "p95_ms_pair_e2e": 1e3 * float(np.percentile(lat, 95)),
+                    "p50_ms_align_call": 1e3 * float(np.median(lat_align)),
+                    "note": "B=1 through the host-buffer C ABI: image H2D + pyramid + align + result D2H"},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="frame pairs per GPU per step")
+    ap.add_argument("--unique", type=int, default=32, help="unique synthetic pairs generated per rank (tiled to --batch)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

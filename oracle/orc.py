@@ -383,3 +383,15 @@ def update_seeds(ref, cur_frames, T_cur_ref, ftrs, types, states, mu_range, opt,
                                sigma2_thresh, mappoint_thresh, px_error_angle, check_visibility, check_convergence, use_vogiatzis,
                                _i32(mr), _u8(ok), n_threads)
     return n, mr, ok
+
+
+def pyramid_align_batch(cur_l0_list, ref_frames, cur_frames, opt, n_levels=5, n_threads=1, pyr_mode=-1):
+    """Threaded CPU 'frame pair step': pyramid of the new frame + SparseImgAlign::run (bench cpu_baseline / reference arm)."""
+    B = len(cur_l0_list)
+    rows, cols = cur_l0_list[0].shape
+    ptrs = (u8p * B)(*[_u8(a) for a in cur_l0_list])
+    R = (Frame * B)(*ref_frames)
+    Cc = (Frame * B)(*cur_frames)
+    res = (AlignResult * B)()
+    lib().orc_pyramid_align_batch(B, n_levels, ptrs, cols, rows, pyr_mode, R, Cc, C.byref(opt), res, n_threads)
+    return res

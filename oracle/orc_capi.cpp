@@ -372,3 +372,25 @@ int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
 }
 
 }  // extern "C"
+
+// One "frame pair step" of the hot path as the bench defines it: build the pyramid of the NEW (cur) frame from its level-0
+// image (frame_utils::createImgPyramid), then SparseImgAlign::run against the already-built ref frame. B independent pairs,
+// n_threads workers. cur[i] supplies camera/poses; its level pointers are ignored and rebuilt from cur_l0[i].
+extern "C" int orc_pyramid_align_batch(int B, int n_levels, const uint8_t* const* cur_l0, int cols, int rows, int pyr_mode,
+                                       const orc_frame* ref, const orc_frame* cur, const orc_align_options* opt,
+                                       orc_align_result* res, int n_threads) {
+  parallelFor(B, n_threads, [&](int i) {
+    Pyramid pyr;
+    createImgPyramid(cur_l0[i], cols, rows, cols, n_levels, pyr, pyr_mode);
+    orc_frame cf = cur[i];
+    cf.n_levels = n_levels;
+    for (int l = 0; l < n_levels; ++l) {
+      cf.level_data[l] = pyr.lv[l].data;
+      cf.level_cols[l] = pyr.lv[l].cols;
+      cf.level_rows[l] = pyr.lv[l].rows;
+      cf.level_step[l] = pyr.lv[l].step;
+    }
+    orc_sparse_align(1, ref + i, &cf, opt, res + i);
+  });
+  return 0;
+}

@@ -131,10 +131,12 @@ def test_frame_index_indirection_and_device_resident_io(ctx, orc):
     dev = torch.device("cuda:0")
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     out = torch.zeros(3 * capi.ALIGN_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    capi.sparse_align(ctx, [ref], [cur], [capi.Camera.from_dict(pairs[0]["cam"])], pk["T_cam_imu"], t(pk["T_imu_world_ref"][perm]),
-                      t(pk["T_imu_world_cur"][perm]), t(pk["n_features"][perm]), t(pk["px"][perm]), t(pk["f"][perm]),
-                      t(pk["depth"][perm]), t(pk["eligible"][perm]), gopt, ref_frame_idx=t(perm.reshape(3, 1)),
-                      cur_frame_idx=t(perm.reshape(3, 1)), results=out)
+    a = {k: t(pk[k][perm]) for k in ("T_imu_world_ref", "T_imu_world_cur", "n_features", "px", "f", "depth", "eligible")}
+    idx = t(perm.reshape(3, 1))
+    torch.cuda.synchronize()  # the context runs on its own non-blocking stream: make torch's uploads visible first
+    capi.sparse_align(ctx, [ref], [cur], [capi.Camera.from_dict(pairs[0]["cam"])], pk["T_cam_imu"], a["T_imu_world_ref"],
+                      a["T_imu_world_cur"], a["n_features"], a["px"], a["f"], a["depth"], a["eligible"], gopt, ref_frame_idx=idx,
+                      cur_frame_idx=idx, results=out)
     ctx.synchronize()
     res_dev = out.cpu().numpy().view(capi.ALIGN_RESULT_DTYPE)
     for k, i in enumerate(perm):
