@@ -39,7 +39,10 @@ SVO_D int fastMargin(const uint8_t* p, int pitch) {
   int mn4[16], mx4[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-  int best = -256;
+  // bright = max over arcs of the arc minimum, dark = min over arcs of the arc maximum; margin = max(bright, -dark) - 1.
+  // NB: nvcc 12.9 / sm_100a folds a negated operand into VIMNMX3 incorrectly (max(a, max(b, -c)) returns wrong values,
+  // see tools/mm_test.cu), so the negation is kept out of every min/max chain and hidden behind an asm barrier.
+  int bright = -256, dark = 256;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const int mn8 = min(mn4[k], mn4[(k + 4) & 15]);
@@ -47,9 +50,12 @@ SVO_D int fastMargin(const uint8_t* p, int pitch) {
     int mn, mx;
     if (ARC == 10) { mn = min(mn8, mn2[(k + 8) & 15]); mx = max(mx8, mx2[(k + 8) & 15]); }
     else           { mn = min(mn8, d[(k + 8) & 15]);   mx = max(mx8, d[(k + 8) & 15]); }
-    best = max(best, max(mn, -mx));
+    bright = max(bright, mn);
+    dark = min(dark, mx);
   }
-  return best - 1;
+  int ndark = -dark;
+  asm volatile("" : "+r"(ndark));
+  return max(bright, ndark) - 1;
 }
 
 struct FastParams {

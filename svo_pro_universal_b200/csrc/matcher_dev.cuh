@@ -159,25 +159,41 @@ SVO_D void loadRow9(const uint8_t* row, int x0, unsigned& a, unsigned& b, unsign
 }
 SVO_D unsigned byte9(unsigned a, unsigned b, unsigned c, int i) { return i < 4 ? byteOf(a, i) : (i < 8 ? byteOf(b, i - 4) : c); }
 
-// ---- c3: align2D ---------------------------------------------------------------------------------------------
-// pwb: the group's 10x10 patch in shared memory. u,v in/out (level px). Returns converged.
+// ---- c3/c4: align2D / align1D --------------------------------------------------------------------------------
+// Bit-exactness: the reference accumulates H and Jres in FLOAT, pixel by pixel in raster order. Lane r computes the
+// interpolated intensities / residuals of its patch row in parallel, then the running sums are carried through the
+// rows in order (owner lane adds its 8 pixels, result is broadcast with a shuffle), so every float operation happens in
+// the reference's order. The translation unit is compiled with -fmad=false so no multiply-add is contracted.
+template <int NK>
+SVO_D void bcastFrom(const Group& g, float (&acc)[NK], int owner) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) acc[k] = __shfl_sync(g.mask, acc[k], owner, kGroup);
+}
+
+// pwb: the group's 10x10 patch in shared memory. px in/out (level px). Returns converged.
 SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n_iter, bool est_offset, bool est_gain,
                    double& px_x, double& px_y) {
   const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
   float rdx[8], rdy[8], rref[8];
-  float h[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
 #pragma unroll
   for (int x = 0; x < 8; ++x) {
-    const float J0 = 0.5f * (float)((int)it[x + 1] - (int)it[x - 1]);
-    const float J1 = 0.5f * (float)((int)it[x + 10] - (int)it[x - 10]);
-    const float J2 = est_offset ? 1.0f : 0.0f;
-    const float J3 = est_gain ? -1.0f * (float)it[x] : 0.0f;
-    rdx[x] = J0; rdy[x] = J1; rref[x] = (float)it[x];
-    h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J0 * J3;
-    h[4] += J1 * J1; h[5] += J1 * J2; h[6] += J1 * J3; h[7] += J2 * J2; h[8] += J2 * J3; h[9] += J3 * J3;
+    rdx[x] = (float)(0.5 * ((int)it[x + 1] - (int)it[x - 1]));    // feature_alignment.cpp:252-253
+    rdy[x] = (float)(0.5 * ((int)it[x + 10] - (int)it[x - 10]));
+    rref[x] = (float)it[x];
   }
+  const float J2 = est_offset ? 1.0f : 0.0f;
+  float h[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33, H += J*J^T in raster order (:261)
+  for (int r = 0; r < kGroup; ++r) {
+    if (g.r == r) {
 #pragma unroll
-  for (int k = 0; k < 10; ++k) h[k] = groupSum(g, h[k]);
+      for (int x = 0; x < 8; ++x) {
+        const float J0 = rdx[x], J1 = rdy[x], J3 = est_gain ? -1.0f * rref[x] : 0.0f;
+        h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J0 * J3;
+        h[4] += J1 * J1; h[5] += J1 * J2; h[6] += J1 * J3; h[7] += J2 * J2; h[8] += J2 * J3; h[9] += J3 * J3;
+      }
+    }
+    bcastFrom(g, h, r);
+  }
   float H[4][4] = {{h[0], h[1], h[2], h[3]}, {h[1], h[4], h[5], h[6]}, {h[2], h[5], h[7], h[8]}, {h[3], h[6], h[8], h[9]}};
   if (!est_offset) H[2][2] = 1.0f;
   if (!est_gain) H[3][3] = 1.0f;
@@ -198,24 +214,32 @@ SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n
     unsigned a0, b0, c0, a1, b1, c1;
     loadRow9(row, u_r - 4, a0, b0, c0);
     loadRow9(row + img.pitch, u_r - 4, a1, b1, c1);
-    float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
+    float res[8];
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
       const float sp = wTL * (float)byte9(a0, b0, c0, x) + wTR * (float)byte9(a0, b0, c0, x + 1) +
                        wBL * (float)byte9(a1, b1, c1, x) + wBR * (float)byte9(a1, b1, c1, x + 1);
-      const float res = sp - alpha * rref[x] + mean_diff;
-      j0 -= res * rdx[x];
-      j1 -= res * rdy[x];
-      j2 -= res;
-      j3 -= (-1.0f) * res * rref[x];
+      res[x] = sp - alpha * rref[x] + mean_diff;  // :322-323
     }
-    j0 = groupSum(g, j0); j1 = groupSum(g, j1); j2 = groupSum(g, j2); j3 = groupSum(g, j3);
-    if (!est_offset) j2 = 0.f;
-    if (!est_gain) j3 = 0.f;
-    const float up0 = Hinv[0][0] * j0 + Hinv[0][1] * j1 + Hinv[0][2] * j2 + Hinv[0][3] * j3;
-    const float up1 = Hinv[1][0] * j0 + Hinv[1][1] * j1 + Hinv[1][2] * j2 + Hinv[1][3] * j3;
-    const float up2 = Hinv[2][0] * j0 + Hinv[2][1] * j1 + Hinv[2][2] * j2 + Hinv[2][3] * j3;
-    const float up3 = Hinv[3][0] * j0 + Hinv[3][1] * j1 + Hinv[3][2] * j2 + Hinv[3][3] * j3;
+    float j[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < kGroup; ++r) {
+      if (g.r == r) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          j[0] -= res[x] * rdx[x];
+          j[1] -= res[x] * rdy[x];
+          if (est_offset) j[2] -= res[x];
+          if (est_gain) j[3] -= (-1.0f * res[x]) * rref[x];
+        }
+      }
+      bcastFrom(g, j, r);
+    }
+    if (!est_offset) j[2] = 0.f;
+    if (!est_gain) j[3] = 0.f;
+    const float up0 = Hinv[0][0] * j[0] + Hinv[0][1] * j[1] + Hinv[0][2] * j[2] + Hinv[0][3] * j[3];
+    const float up1 = Hinv[1][0] * j[0] + Hinv[1][1] * j[1] + Hinv[1][2] * j[2] + Hinv[1][3] * j[3];
+    const float up2 = Hinv[2][0] * j[0] + Hinv[2][1] * j[1] + Hinv[2][2] * j[2] + Hinv[2][3] * j[3];
+    const float up3 = Hinv[3][0] * j[0] + Hinv[3][1] * j[1] + Hinv[3][2] * j[2] + Hinv[3][3] * j[3];
     u += up0; v += up1; mean_diff += up2; alpha += up3;
     if (up0 * up0 + up1 * up1 < min_update_squared) { converged = true; break; }
   }
@@ -223,24 +247,29 @@ SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n
   return converged;
 }
 
-// ---- c4: align1D ---------------------------------------------------------------------------------------------
 SVO_D bool align1D(const Group& g, const ImgView& img, double dir_x, double dir_y, const uint8_t* pwb, int n_iter, bool est_offset,
                    bool est_gain, double& px_x, double& px_y, double* h_inv) {
   const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
   float rdv[8], rref[8];
-  float h[6] = {0, 0, 0, 0, 0, 0};  // 00 01 02 11 12 22
 #pragma unroll
   for (int x = 0; x < 8; ++x) {
-    const float dx = (float)it[x + 1] - (float)it[x - 1];
+    const float dx = (float)it[x + 1] - (float)it[x - 1];         // feature_alignment.cpp:63-65
     const float dy = (float)it[x + 10] - (float)it[x - 10];
-    const float J0 = (float)(0.5f * (dir_x * dx + dir_y * dy));
-    const float J1 = est_offset ? 1.0f : 0.0f;
-    const float J2 = est_gain ? -1.0f * (float)it[x] : 0.0f;
-    rdv[x] = J0; rref[x] = (float)it[x];
-    h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J1 * J1; h[4] += J1 * J2; h[5] += J2 * J2;
+    rdv[x] = (float)(0.5f * (dir_x * dx + dir_y * dy));
+    rref[x] = (float)it[x];
   }
+  const float J1 = est_offset ? 1.0f : 0.0f;
+  float h[6] = {0, 0, 0, 0, 0, 0};  // 00 01 02 11 12 22
+  for (int r = 0; r < kGroup; ++r) {
+    if (g.r == r) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) h[k] = groupSum(g, h[k]);
+      for (int x = 0; x < 8; ++x) {
+        const float J0 = rdv[x], J2 = est_gain ? -1.0f * rref[x] : 0.0f;
+        h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J1 * J1; h[4] += J1 * J2; h[5] += J2 * J2;
+      }
+    }
+    bcastFrom(g, h, r);
+  }
   float H[3][3] = {{h[0], h[1], h[2]}, {h[1], h[3], h[4]}, {h[2], h[4], h[5]}};
   if (!est_offset) H[1][1] = 1.0f;
   if (!est_gain) H[2][2] = 1.0f;
@@ -262,22 +291,30 @@ SVO_D bool align1D(const Group& g, const ImgView& img, double dir_x, double dir_
     unsigned a0, b0, c0, a1, b1, c1;
     loadRow9(row, u_r - 4, a0, b0, c0);
     loadRow9(row + img.pitch, u_r - 4, a1, b1, c1);
-    float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+    float res[8];
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
       const float ci = wTL * (float)byte9(a0, b0, c0, x) + wTR * (float)byte9(a0, b0, c0, x + 1) +
                        wBL * (float)byte9(a1, b1, c1, x) + wBR * (float)byte9(a1, b1, c1, x + 1);
-      const float res = ci - alpha * rref[x] + mean_diff;
-      j0 -= res * rdv[x];
-      j1 -= res;
-      j2 -= (-1.0f) * res * rref[x];
+      res[x] = ci - alpha * rref[x] + mean_diff;  // :137-139
     }
-    j0 = groupSum(g, j0); j1 = groupSum(g, j1); j2 = groupSum(g, j2);
-    if (!est_offset) j1 = 0.f;
-    if (!est_gain) j2 = 0.f;
-    const float up0 = Hinv[0][0] * j0 + Hinv[0][1] * j1 + Hinv[0][2] * j2;
-    const float up1 = Hinv[1][0] * j0 + Hinv[1][1] * j1 + Hinv[1][2] * j2;
-    const float up2 = Hinv[2][0] * j0 + Hinv[2][1] * j1 + Hinv[2][2] * j2;
+    float j[3] = {0.f, 0.f, 0.f};
+    for (int r = 0; r < kGroup; ++r) {
+      if (g.r == r) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          j[0] -= res[x] * rdv[x];
+          if (est_offset) j[1] -= res[x];
+          if (est_gain) j[2] -= (-1.0f * res[x]) * rref[x];
+        }
+      }
+      bcastFrom(g, j, r);
+    }
+    if (!est_offset) j[1] = 0.f;
+    if (!est_gain) j[2] = 0.f;
+    const float up0 = Hinv[0][0] * j[0] + Hinv[0][1] * j[1] + Hinv[0][2] * j[2];
+    const float up1 = Hinv[1][0] * j[0] + Hinv[1][1] * j[1] + Hinv[1][2] * j[2];
+    const float up2 = Hinv[2][0] * j[0] + Hinv[2][1] * j[1] + Hinv[2][2] * j[2];
     u = (float)(u + up0 * dir_x);
     v = (float)(v + up0 * dir_y);
     mean_diff += up1;
