@@ -84,35 +84,47 @@ SVO_D float tukeyWeight(float error) {
 // Symmetric solve H dx = g (lower triangle of H read), LDL^T without pivoting; a zero pivot (an all-zero row/column of
 // the PSD normal matrix: illumination parameters switched off) yields dx_k = 0, which is what Eigen's pivoted
 // LDLT::solve returns for those rows (mini_least_squares_solver.hpp:258).
-__device__ __noinline__ void ldltSolve8(const double* H, const double* g, double* dx) {
-  double a[8][8];
-  for (int i = 0; i < 8; ++i)
-    for (int j = 0; j <= i; ++j) a[i][j] = H[i * 8 + j];
-  const double tol = 2.2250738585072014e-308;
-  for (int k = 0; k < 8; ++k) {
-    double d = a[k][k];
-    for (int j = 0; j < k; ++j) d -= a[k][j] * a[k][j] * a[j][j];
-    a[k][k] = d;
-    const bool ok = fabs(d) > 0.0;
-    for (int i = k + 1; i < 8; ++i) {
-      double s = a[i][k];
-      for (int j = 0; j < k; ++j) s -= a[i][j] * a[k][j] * a[j][j];
-      a[i][k] = ok ? s / d : s;
+// `tri` holds the upper triangle row-major ((0,0),(0,1)..(0,D-1),(1,1)..) plus `diag_add` on the diagonal. Everything is
+// unrolled at compile time so the factor lives in registers; one reciprocal per pivot.
+template <int D>
+SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double* g, double* dx) {
+  double L[D][D], dd[D], rd[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    double w[D];
+    double d = tri[k * D - (k * (k - 1)) / 2] + diag_add[k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) { w[j] = L[k][j] * dd[j]; d -= L[k][j] * w[j]; }
+    dd[k] = d;
+    const bool ok = fabs(d) > 2.2250738585072014e-308;
+    rd[k] = ok ? 1.0 / d : 0.0;
+#pragma unroll
+    for (int i = k + 1; i < D; ++i) {
+      double s = tri[k * D - (k * (k - 1)) / 2 + (i - k)];
+#pragma unroll
+      for (int j = 0; j < k; ++j) s -= L[i][j] * w[j];
+      L[i][k] = ok ? s * rd[k] : s;
     }
   }
-  double x[8];
-  for (int i = 0; i < 8; ++i) {
+  double x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
     double s = g[i];
-    for (int j = 0; j < i; ++j) s -= a[i][j] * x[j];
+#pragma unroll
+    for (int j = 0; j < i; ++j) s -= L[i][j] * x[j];
     x[i] = s;
   }
-  for (int i = 0; i < 8; ++i) x[i] = (fabs(a[i][i]) > tol) ? x[i] / a[i][i] : 0.0;
-  for (int i = 7; i >= 0; --i) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] *= rd[i];  // zero pivot -> 0, as Eigen's LDLT::solve
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
     double s = x[i];
-    for (int j = i + 1; j < 8; ++j) s -= a[j][i] * x[j];
+#pragma unroll
+    for (int j = i + 1; j < D; ++j) s -= L[j][i] * x[j];
     x[i] = s;
   }
-  for (int i = 0; i < 8; ++i) dx[i] = x[i];
+#pragma unroll
+  for (int i = 0; i < D; ++i) dx[i] = x[i];
 }
 
 SVO_D void storeRt(const SE3d& T, double* Rt) {
@@ -404,68 +416,76 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
           }
         }
         __syncthreads();
-        if (tid < NV) {
-          double t = 0.0;
+        if (warp == 0) {
+          // cross-warp totals: lane k owns accumulator k (NV <= 46 -> two per lane at most)
+          for (int k = lane; k < NV; k += 32) {
+            double t = 0.0;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) t += s_red[w * kNVmax + tid];
-          ctl.tot[tid] = t;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          ctl.iters[level_slot] = iter + 1;
-          double H[64], g[8], dx[8];
-          for (int i = 0; i < 64; ++i) H[i] = 0.0;
-          for (int i = 0; i < 8; ++i) g[i] = 0.0;
-          int idx = 0;
-          for (int a = 0; a < D; ++a)
-            for (int b = a; b < D; ++b) { H[a * 8 + b] = ctl.tot[idx]; H[b * 8 + a] = ctl.tot[idx]; ++idx; }
-          for (int a = 0; a < D; ++a) g[a] = ctl.tot[NH + a];
-          const double new_chi2 = (double)(float)(ctl.tot[NH + D] / ctl.tot[NH + D + 1]);  // float chi2 / n_meas (:540)
-          if (P.priors) {  // applyPrior, sparse_img_align_base.cpp:77-107
-            const svo_align_prior& pr = P.priors[pair];
-            if (iter == 0) {
-              double mt = 0, mr = 0;
-              for (int j = 0; j < 3; ++j) mt = fmax(mt, fabs(H[j * 8 + j]));
-              for (int j = 3; j < 6; ++j) mr = fmax(mr, fabs(H[j * 8 + j]));
-              for (int j = 0; j < 3; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_trans * mt;
-              for (int j = 3; j < 6; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_rot * mr;
-              ctl.I_prior[6] = opt.lambda_alpha * H[6 * 8 + 6];
-              ctl.I_prior[7] = opt.lambda_beta * H[7 * 8 + 7];
+            for (int w = 0; w < kWarps; ++w) t += s_red[w * kNVmax + k];
+            ctl.tot[k] = t;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            ctl.iters[level_slot] = iter + 1;
+            double g[D], dx[8], padd[D];
+#pragma unroll
+            for (int a = 0; a < D; ++a) { g[a] = ctl.tot[NH + a]; padd[a] = 0.0; }
+            const double new_chi2 = (double)(float)(ctl.tot[NH + D] / ctl.tot[NH + D + 1]);  // float chi2 / n_meas (:540)
+            if (P.priors) {  // applyPrior, sparse_img_align_base.cpp:77-107
+              const svo_align_prior& pr = P.priors[pair];
+              if (iter == 0) {
+                double mt = 0, mr = 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) mt = fmax(mt, fabs(ctl.tot[j * D - (j * (j - 1)) / 2]));
+#pragma unroll
+                for (int j = 3; j < 6; ++j) mr = fmax(mr, fabs(ctl.tot[j * D - (j * (j - 1)) / 2]));
+                for (int j = 0; j < 3; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_trans * mt;
+                for (int j = 3; j < 6; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_rot * mr;
+                ctl.I_prior[6] = (D == 8) ? opt.lambda_alpha * ctl.tot[6 * D - 15] : 0.0;
+                ctl.I_prior[7] = (D == 8) ? opt.lambda_beta * ctl.tot[7 * D - 21] : 0.0;
+              }
+              const SE3d Tp = se3Load(pr.T);
+              const SE3d E = se3Mul(se3Inv(Tp), ctl.T);
+              const V3d lr = quatLog(E.q);
+              const double l[6] = {E.t.x, E.t.y, E.t.z, lr.x, lr.y, lr.z};
+#pragma unroll
+              for (int j = 0; j < 6; ++j) { padd[j] = ctl.I_prior[j]; g[j] += ctl.I_prior[j] * l[j]; }
+              if (D == 8) {
+                padd[D - 2] = ctl.I_prior[6]; padd[D - 1] = ctl.I_prior[7];
+                g[D - 2] += ctl.I_prior[6] * (pr.alpha - ctl.alpha);
+                g[D - 1] += ctl.I_prior[7] * (pr.beta - ctl.beta);
+              }
             }
-            for (int j = 0; j < 8; ++j) H[j * 8 + j] += ctl.I_prior[j];
-            const SE3d Tp = se3Load(pr.T);
-            const SE3d E = se3Mul(se3Inv(Tp), ctl.T);
-            const V3d lr = quatLog(E.q);
-            const double l[6] = {E.t.x, E.t.y, E.t.z, lr.x, lr.y, lr.z};
-            for (int j = 0; j < 6; ++j) g[j] += ctl.I_prior[j] * l[j];
-            g[6] += ctl.I_prior[6] * (pr.alpha - ctl.alpha);
-            g[7] += ctl.I_prior[7] * (pr.beta - ctl.beta);
+            dx[6] = 0.0; dx[7] = 0.0;
+            ldltSolveTri<D>(ctl.tot, padd, g, dx);
+            if (dx[0] != dx[0]) ctl.stop = 1;  // solveDefaultImpl: isnan(dx[0]) -> stop_
+            int brk = 0;
+            if (ctl.stop) {
+              ctl.T = ctl.T_old; ctl.alpha = ctl.alpha_old; ctl.beta = ctl.beta_old;  // rollback (:76-84)
+              brk = 1;
+            } else {
+              // update, sparse_img_align_base.cpp:64-75
+              SE3d inc;
+              inc.q = quatExp(V3d{-dx[3], -dx[4], -dx[5]});
+              inc.t = V3d{-dx[0], -dx[1], -dx[2]};
+              SE3d Tn = se3Mul(ctl.T, inc);
+              const double an = (ctl.alpha - dx[6]) / (1.0 + dx[6]);
+              const double bn = (ctl.beta - dx[7]) / (1.0 + dx[6]);
+              quatNormalize(Tn.q);
+              ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
+              ctl.T = Tn; ctl.alpha = an; ctl.beta = bn;
+              ctl.chi2 = new_chi2;
+              double x_norm = -1.0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const double a = fabs(dx[i]); if (a > x_norm) x_norm = a; }
+              if (x_norm < opt.eps) brk = 1;
+            }
+            ctl.alpha_f = (float)ctl.alpha;
+            ctl.beta_f = (float)ctl.beta;
+            ctl.brk = brk;
           }
-          for (int i = 0; i < 64; ++i) ctl.H[i] = H[i];
-          ldltSolve8(H, g, dx);
-          if (dx[0] != dx[0]) ctl.stop = 1;  // solveDefaultImpl: isnan(dx[0]) -> stop_
-          int brk = 0;
-          if (ctl.stop) {
-            ctl.T = ctl.T_old; ctl.alpha = ctl.alpha_old; ctl.beta = ctl.beta_old;  // rollback (:76-84)
-            brk = 1;
-          } else {
-            // update, sparse_img_align_base.cpp:64-75
-            SE3d inc;
-            inc.q = quatExp(V3d{-dx[3], -dx[4], -dx[5]});
-            inc.t = V3d{-dx[0], -dx[1], -dx[2]};
-            SE3d Tn = se3Mul(ctl.T, inc);
-            const double an = (ctl.alpha - dx[6]) / (1.0 + dx[6]);
-            const double bn = (ctl.beta - dx[7]) / (1.0 + dx[6]);
-            quatNormalize(Tn.q);
-            ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
-            ctl.T = Tn; ctl.alpha = an; ctl.beta = bn;
-            ctl.chi2 = new_chi2;
-            double x_norm = -1.0;
-            for (int i = 0; i < 8; ++i) { const double a = fabs(dx[i]); if (a > x_norm) x_norm = a; }
-            if (x_norm < opt.eps) brk = 1;
-          }
-          refreshCams(ctl, n_cams);
-          ctl.brk = brk;
+          __syncwarp();
+          if (lane < n_cams) storeRt(se3Mul(se3Mul(ctl.T_cam_imu[lane], ctl.T), ctl.T_imu_cam[lane]), ctl.Rt[lane]);
         }
         __syncthreads();
         if (ctl.brk) break;
@@ -486,7 +506,14 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
     r.alpha = ctl.alpha;
     r.beta = ctl.beta;
     r.chi2 = ctl.chi2;
-    for (int i = 0; i < 64; ++i) r.H[i] = ctl.H[i];
+    // getHessian(): the last evaluated H_ (incl. the prior information) rebuilt from the reduced upper triangle
+    for (int i = 0; i < 64; ++i) r.H[i] = 0.0;
+    if (n_total > 0) {
+      int idx = 0;
+      for (int a = 0; a < D; ++a)
+        for (int b = a; b < D; ++b) { r.H[a * 8 + b] = ctl.tot[idx]; r.H[b * 8 + a] = ctl.tot[idx]; ++idx; }
+      if (P.priors) for (int j = 0; j < 8; ++j) r.H[j * 8 + j] += ctl.I_prior[j];
+    }
     r.n_tracked = n_total;
     for (int i = 0; i < SVO_MAX_LEVELS; ++i) r.iters[i] = ctl.iters[i];
     r.stop = ctl.stop;
