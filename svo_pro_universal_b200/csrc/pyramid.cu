@@ -31,44 +31,77 @@ struct PyrW {  // writable view
   uint8_t* data[SVO_MAX_LEVELS];
 };
 
-constexpr int kTileW = 256, kTileH = 16;
+constexpr int kTileW = 256, kTileH = 32;
 
+SVO_D uint4 ldStream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// One CTA halves a 256x32 tile of level l0 up to four times. Stage 1 works straight from registers: thread (row pair rp,
+// 16-px chunk ch) loads two 128-bit rows and produces 8 pixels of level l0+1; later stages read the previous level's tile
+// from shared memory. All index arithmetic is shifts; every level is written once with 64/32-bit stores.
 __global__ void __launch_bounds__(256) pyr_down_fused_kernel(PyrW v, int first, int l0, int nh, unsigned round_mask) {
-  __shared__ __align__(16) uint8_t tile[kTileW * kTileH + kTileW * kTileH / 4 + kTileW * kTileH / 16 + kTileW * kTileH / 64 + kTileW * kTileH / 256];
+  __shared__ __align__(16) uint8_t t1[128 * 16];
+  __shared__ __align__(16) uint8_t t2[64 * 8];
+  __shared__ __align__(16) uint8_t t3[32 * 4];
   const int frame = first + blockIdx.z;
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  {
-    const uint8_t* src = v.data[l0] + v.frame_stride[l0] * (unsigned long long)frame;
-    const int r = tid >> 4, c = tid & 15;
-    const int gx = x0 + c * 16, gy = y0 + r;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (gy < v.rows[l0] && gx < v.pitch[l0]) val = __ldg(reinterpret_cast<const uint4*>(src + (size_t)gy * v.pitch[l0] + gx));
-    *reinterpret_cast<uint4*>(&tile[r * kTileW + c * 16]) = val;
-  }
-  __syncthreads();
-  int in_off = 0, win = kTileW;
-  for (int k = 1; k <= nh; ++k) {
-    const int wout = kTileW >> k, hout = kTileH >> k;
-    const int out_off = in_off + win * (kTileH >> (k - 1));
-    const int per_row = wout >> 2;
-    const int items = hout * per_row;
-    const int L = l0 + k;
-    if (tid < items) {
-      const int oy = tid / per_row, ox4 = (tid - oy * per_row) * 4;
-      const uint2 top = *reinterpret_cast<const uint2*>(&tile[in_off + (2 * oy) * win + 2 * ox4]);
-      const uint2 bot = *reinterpret_cast<const uint2*>(&tile[in_off + (2 * oy + 1) * win + 2 * ox4]);
-      const unsigned o = down4(top.x, top.y, bot.x, bot.y, (round_mask >> (L - 1)) & 1u);
-      *reinterpret_cast<unsigned*>(&tile[out_off + oy * wout + ox4]) = o;
-      const int gx = (x0 >> k) + ox4, gy = (y0 >> k) + oy;
-      if (gy < v.rows[L] && gx < v.cols[L]) {
-        uint8_t* dst = v.data[L] + v.frame_stride[L] * (unsigned long long)frame;
-        *reinterpret_cast<unsigned*>(dst + (size_t)gy * v.pitch[L] + gx) = o;
-      }
+  const unsigned long long f = (unsigned long long)frame;
+  {  // stage 1: l0 -> l0+1
+    const int rp = tid >> 4, ch = tid & 15;
+    const int gx = x0 + ch * 16, gy = y0 + 2 * rp;
+    uint4 top = make_uint4(0, 0, 0, 0), bot = make_uint4(0, 0, 0, 0);
+    if (gy + 1 < v.rows[l0] && gx < v.pitch[l0]) {
+      const uint8_t* src = v.data[l0] + v.frame_stride[l0] * f + (size_t)gy * v.pitch[l0] + gx;
+      top = ldStream(reinterpret_cast<const uint4*>(src));
+      bot = ldStream(reinterpret_cast<const uint4*>(src + v.pitch[l0]));
     }
-    __syncthreads();
-    in_off = out_off;
-    win = wout;
+    const bool rnd = (round_mask >> l0) & 1u;
+    uint2 o;
+    o.x = down4(top.x, top.y, bot.x, bot.y, rnd);
+    o.y = down4(top.z, top.w, bot.z, bot.w, rnd);
+    *reinterpret_cast<uint2*>(&t1[rp * 128 + ch * 8]) = o;
+    const int L = l0 + 1;
+    const int ox = (x0 >> 1) + ch * 8, oy = (y0 >> 1) + rp;
+    if (oy < v.rows[L] && ox < v.cols[L]) *reinterpret_cast<uint2*>(v.data[L] + v.frame_stride[L] * f + (size_t)oy * v.pitch[L] + ox) = o;
+  }
+  if (nh < 2) return;
+  __syncthreads();
+  if (tid < 128) {  // stage 2: 128x16 -> 64x8, 4 px per thread
+    const int r = tid >> 4, c4 = (tid & 15) * 4;
+    const uint2 top = *reinterpret_cast<const uint2*>(&t1[(2 * r) * 128 + 2 * c4]);
+    const uint2 bot = *reinterpret_cast<const uint2*>(&t1[(2 * r + 1) * 128 + 2 * c4]);
+    const unsigned o = down4(top.x, top.y, bot.x, bot.y, (round_mask >> (l0 + 1)) & 1u);
+    *reinterpret_cast<unsigned*>(&t2[r * 64 + c4]) = o;
+    const int L = l0 + 2;
+    const int ox = (x0 >> 2) + c4, oy = (y0 >> 2) + r;
+    if (oy < v.rows[L] && ox < v.cols[L]) *reinterpret_cast<unsigned*>(v.data[L] + v.frame_stride[L] * f + (size_t)oy * v.pitch[L] + ox) = o;
+  }
+  if (nh < 3) return;
+  __syncthreads();
+  if (tid < 32) {  // stage 3: 64x8 -> 32x4
+    const int r = tid >> 3, c4 = (tid & 7) * 4;
+    const uint2 top = *reinterpret_cast<const uint2*>(&t2[(2 * r) * 64 + 2 * c4]);
+    const uint2 bot = *reinterpret_cast<const uint2*>(&t2[(2 * r + 1) * 64 + 2 * c4]);
+    const unsigned o = down4(top.x, top.y, bot.x, bot.y, (round_mask >> (l0 + 2)) & 1u);
+    *reinterpret_cast<unsigned*>(&t3[r * 32 + c4]) = o;
+    const int L = l0 + 3;
+    const int ox = (x0 >> 3) + c4, oy = (y0 >> 3) + r;
+    if (oy < v.rows[L] && ox < v.cols[L]) *reinterpret_cast<unsigned*>(v.data[L] + v.frame_stride[L] * f + (size_t)oy * v.pitch[L] + ox) = o;
+  }
+  if (nh < 4) return;
+  __syncwarp();
+  if (tid < 8) {  // stage 4: 32x4 -> 16x2 (same warp as stage 3)
+    const int r = tid >> 2, c4 = (tid & 3) * 4;
+    const uint2 top = *reinterpret_cast<const uint2*>(&t3[(2 * r) * 32 + 2 * c4]);
+    const uint2 bot = *reinterpret_cast<const uint2*>(&t3[(2 * r + 1) * 32 + 2 * c4]);
+    const unsigned o = down4(top.x, top.y, bot.x, bot.y, (round_mask >> (l0 + 3)) & 1u);
+    const int L = l0 + 4;
+    const int ox = (x0 >> 4) + c4, oy = (y0 >> 4) + r;
+    if (oy < v.rows[L] && ox < v.cols[L]) *reinterpret_cast<unsigned*>(v.data[L] + v.frame_stride[L] * f + (size_t)oy * v.pitch[L] + ox) = o;
   }
 }
 
