@@ -12,12 +12,14 @@
 //              bank conflicts), once per run;
 //   per level  6x6 bilinear reference patch (b4) -> 32 doubles per feature in shared memory (centre + the 4-neighbour
 //              values the central differences need);
-//   per iter   project, visibility test, 5x5 cur-image taps via two aligned 32-bit loads per row, 16 residuals (b5);
-//              the per-pixel Jacobian factorises as J = [ (dx*Jp0 + dy*Jp1)*scale ; a6 ; a7 ], so H and g of a patch
-//              are a rank-2 expansion of 5 (+7 with illumination) weighted sums — 16x fewer outer products than the
-//              reference's per-pixel loop, identical in exact arithmetic (b6);
-//              warp-shuffle + cross-warp reduction of the 21+6+2 (or 36+8+2) accumulators, then thread 0 runs the
-//              LDLT solve, prior, SE3/illumination update and the convergence test (b7, b8).
+//   per iter   project, visibility test, 5x5 cur-image taps via aligned 32-bit loads, 16 residuals (b5);
+//              the per-pixel Jacobian factorises as J = [ (dx*Jp0 + dy*Jp1)*scale ; a6 ; a7 ], so H and g of a patch are
+//              a rank-2 expansion of a few weighted sums — 16x fewer outer products than the reference's per-pixel
+//              loop, identical in exact arithmetic (b6). Without robust weights H depends only on WHICH patches are
+//              visible, so it is reduced once per level and again only when the visibility pattern changes; every
+//              iteration reduces just g, chi2, the measurement count and a "visibility changed" flag;
+//              warp-shuffle + cross-warp reduction, then warp 0 runs the register-resident LDLT solve, prior,
+//              SE3/illumination update and the convergence test (b7, b8) — two block barriers per iteration.
 // All arithmetic is FP64 like the reference (FloatType = double, src/svo_common/include/svo/common/types.h:16);
 // Tukey weights and the alpha/beta handed to the residual are float, as in the reference signatures.
 #include "common.cuh"
@@ -26,8 +28,9 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kWarps = kThreads / 32;
-constexpr int kNVmax = 36 + 8 + 2;
-constexpr int kPerSlotDoubles = 3 + 12 + 2 + 32;  // xyz, Jp0|Jp1, uv, patch
+constexpr int kNVmax = 36 + 8 + 3;                // H upper triangle + g + chi2 + n_meas + changed
+constexpr int kPerSlotBytes = (3 + 12 + 32) * 8 + 4 + 1;  // xyz, Jp0|Jp1, patch (doubles) + source index + camera
+constexpr int kFixedSlots = 184;                  // compile-time stride for the common <= 184-feature case
 
 struct AlignParams {
   int n_cams, B, max_features, slots;
@@ -53,13 +56,11 @@ struct Ctl {
   double alpha, beta, alpha_old, beta_old;
   SE3d T_cam_imu[SVO_MAX_CAMS], T_imu_cam[SVO_MAX_CAMS];
   double Rt[SVO_MAX_CAMS][12];  // T_cur_ref of camera c: R row-major (9) + t (3)
-  double H[64];
-  double g[8];
-  double I_prior[8];  // diagonal of I_prior_
+  double I_prior[8];            // diagonal of I_prior_
   double tot[kNVmax];
   double chi2;
   float alpha_f, beta_f;
-  int stop, brk, n_total;
+  int stop, brk;
   int warp_cnt[kWarps];
   int iters[SVO_MAX_LEVELS];
 };
@@ -81,11 +82,11 @@ SVO_D float tukeyWeight(float error) {
   return 0.0f;
 }
 
-// Symmetric solve H dx = g (lower triangle of H read), LDL^T without pivoting; a zero pivot (an all-zero row/column of
-// the PSD normal matrix: illumination parameters switched off) yields dx_k = 0, which is what Eigen's pivoted
-// LDLT::solve returns for those rows (mini_least_squares_solver.hpp:258).
-// `tri` holds the upper triangle row-major ((0,0),(0,1)..(0,D-1),(1,1)..) plus `diag_add` on the diagonal. Everything is
-// unrolled at compile time so the factor lives in registers; one reciprocal per pivot.
+// Symmetric solve H dx = g, LDL^T without pivoting; a zero pivot (an all-zero row/column of the PSD normal matrix:
+// illumination parameters switched off) yields dx_k = 0, which is what Eigen's pivoted LDLT::solve returns for those
+// rows (mini_least_squares_solver.hpp:258). `tri` holds the upper triangle row-major ((0,0),(0,1)..(0,D-1),(1,1)..),
+// `diag_add` is added on the diagonal. Everything unrolls at compile time so the factor lives in registers; one
+// reciprocal per pivot.
 template <int D>
 SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double* g, double* dx) {
   double L[D][D], dd[D], rd[D];
@@ -134,27 +135,75 @@ SVO_D void storeRt(const SE3d& T, double* Rt) {
   Rt[9] = T.t.x; Rt[10] = T.t.y; Rt[11] = T.t.z;
 }
 
-// thread 0: T_cur_ref of every camera for the current state (sparse_img_align.cpp:140-142)
-SVO_D void refreshCams(Ctl& c, int n_cams) {
-  for (int k = 0; k < n_cams; ++k) storeRt(se3Mul(se3Mul(c.T_cam_imu[k], c.T), c.T_imu_cam[k]), c.Rt[k]);
-  c.alpha_f = (float)c.alpha;
-  c.beta_f = (float)c.beta;
+// index of patch element (X, Y) of the 6x6 interpolated reference patch among the 32 stored values
+// (rows 0 and 5 keep only X = 1..4: the corners are never read)
+SVO_HD constexpr int patchIdx(int X, int Y) { return Y == 0 ? X - 1 : (Y == 5 ? 28 + X - 1 : 4 + (Y - 1) * 6 + X); }
+
+struct PatchSums {  // weighted sums over the 16 pixels of one patch
+  double sxx, sxy, syy;                         // H pose block
+  double sx6, sy6, sx7, sy7, s66, s67, s77;     // H illumination blocks
+};
+
+// Sums that form H when every weight is 1: they depend on the reference patch only.
+template <bool ILLUM>
+SVO_D PatchSums unitWeightSums(const double* patch, int stride, bool est_gain, bool est_off) {
+  PatchSums p = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const double ref = patch[patchIdx(x + 1, y + 1) * stride];
+      const double dx = 0.5 * (patch[patchIdx(x + 2, y + 1) * stride] - patch[patchIdx(x, y + 1) * stride]);
+      const double dy = 0.5 * (patch[patchIdx(x + 1, y + 2) * stride] - patch[patchIdx(x + 1, y) * stride]);
+      p.sxx += dx * dx; p.sxy += dx * dy; p.syy += dy * dy;
+      if (ILLUM) {
+        const double a6 = est_gain ? -ref : 0.0, a7 = est_off ? -1.0 : 0.0;
+        p.sx6 += dx * a6; p.sy6 += dy * a6; p.sx7 += dx * a7; p.sy7 += dy * a7;
+        p.s66 += a6 * a6; p.s67 += a6 * a7; p.s77 += a7 * a7;
+      }
+    }
+  return p;
 }
 
-template <bool ILLUM>
-__global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParams P) {
+// Rank-2 expansion of one patch's sums into the D(D+1)/2 upper-triangle entries of H, warp-reduced into red[0..NH).
+template <int D>
+SVO_D void reduceH(const PatchSums& p, const double* jp0, const double* jp1, double* red, int lane) {
+  double ua[6], va[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    ua[k] = p.sxx * jp0[k] + p.sxy * jp1[k];
+    va[k] = p.sxy * jp0[k] + p.syy * jp1[k];
+  }
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+#pragma unroll
+    for (int b = a; b < D; ++b) {
+      double v;
+      if (b < 6) v = ua[a] * jp0[b] + va[a] * jp1[b];
+      else if (a < 6) v = (b == 6) ? (jp0[a] * p.sx6 + jp1[a] * p.sy6) : (jp0[a] * p.sx7 + jp1[a] * p.sy7);
+      else v = (a == 6 && b == 6) ? p.s66 : (a == 6 ? p.s67 : p.s77);
+      v = warpSum(v);
+      if (lane == 0) red[idx] += v;
+      ++idx;
+    }
+  }
+}
+
+template <bool ILLUM, bool ROBUST, int SLOTS>
+__global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(const AlignParams P) {
   constexpr int D = ILLUM ? 8 : 6;
   constexpr int NH = D * (D + 1) / 2;
-  constexpr int NV = NH + D + 2;
+  constexpr int NV = NH + D + 3;  // H | g | chi2 | n_meas | changed
   extern __shared__ __align__(16) double smem[];
-  const int slots = P.slots;
-  double* s_xyz = smem;                  // [3][slots]
-  double* s_jp = s_xyz + 3 * slots;      // [12][slots]
-  double* s_uv = s_jp + 12 * slots;      // [2][slots]
-  double* s_patch = s_uv + 2 * slots;    // [32][slots]
-  double* s_red = s_patch + 32 * slots;  // [kWarps][kNVmax]
+  const int stride = SLOTS ? SLOTS : P.slots;
+  double* s_xyz = smem;                   // [3][stride]
+  double* s_jp = s_xyz + 3 * stride;      // [12][stride]
+  double* s_patch = s_jp + 12 * stride;   // [32][stride]
+  double* s_red = s_patch + 32 * stride;  // [kWarps][kNVmax]
   Ctl& ctl = *reinterpret_cast<Ctl*>(s_red + kWarps * kNVmax);
-  uint8_t* s_cam = reinterpret_cast<uint8_t*>(&ctl + 1);  // [slots]
+  int* s_src = reinterpret_cast<int*>(&ctl + 1);                // [stride] feature index inside its camera's array
+  uint8_t* s_cam = reinterpret_cast<uint8_t*>(s_src + stride);  // [stride]
 
   const int pair = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -174,10 +223,9 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
     ctl.beta = opt.beta_init;
     ctl.stop = 0;
     ctl.chi2 = 1e10;  // reset(): mini_least_squares_solver.hpp:243
-    ctl.n_total = 0;
     for (int i = 0; i < SVO_MAX_LEVELS; ++i) ctl.iters[i] = 0;
-    for (int i = 0; i < 64; ++i) ctl.H[i] = 0.0;
     for (int i = 0; i < 8; ++i) ctl.I_prior[i] = 0.0;
+    for (int i = 0; i < kNVmax; ++i) ctl.tot[i] = 0.0;
   }
   __syncthreads();
 
@@ -194,10 +242,8 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
     for (int base = 0; base < n; base += kThreads) {
       const int i = base + tid;
       bool ok = false;
-      double pu = 0, pv = 0;
       if (i < n && P.eligible[fbase + i]) {
-        pu = P.px[2 * (fbase + i)];
-        pv = P.px[2 * (fbase + i) + 1];
+        const double pu = P.px[2 * (fbase + i)], pv = P.px[2 * (fbase + i) + 1];
         // sparse_img_align.cpp:249-257 with patch_size_wb = 6, patch_center_wb = 2.5
         const int u_tl_i = (int)floor(pu * scale_max - 2.5);
         const int v_tl_i = (int)floor(pv * scale_max - 2.5);
@@ -213,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
       }
       if (ok) {
         const int s = off + __popc(bal & ((1u << lane) - 1u));
-        if (s < slots) {
+        if (s < stride) {
           // sparse_img_align.cpp:262-317
           const double depth = P.depth[fbase + i];
           const V3d fv{P.f[3 * (fbase + i)], P.f[3 * (fbase + i) + 1], P.f[3 * (fbase + i) + 2]};
@@ -225,9 +271,9 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
           double Jp[2][3];
           double mult;
           if (!opt.use_distortion_jacobian) {  // Frame::jacobian_xyz2uv_imu, frame.h:342-357, times focal length
-            const double s = -1.0 / pc.z;
-            Jp[0][0] = s; Jp[0][1] = 0.0; Jp[0][2] = s * (-pc.x / pc.z);
-            Jp[1][0] = 0.0; Jp[1][1] = s; Jp[1][2] = s * (-pc.y / pc.z);
+            const double sI = -1.0 / pc.z;
+            Jp[0][0] = sI; Jp[0][1] = 0.0; Jp[0][2] = sI * (-pc.x / pc.z);
+            Jp[1][0] = 0.0; Jp[1][1] = sI; Jp[1][2] = sI * (-pc.y / pc.z);
             mult = fabs(cam.fx);
           } else {  // Frame::jacobian_xyz2image_imu, frame.cpp:274-290, times -1
             camProject3Jac(cam, pc, Jp);
@@ -240,9 +286,9 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
           const double G[3][6] = {{1, 0, 0, 0, p_imu.z, -p_imu.y}, {0, 1, 0, -p_imu.z, 0, p_imu.x}, {0, 0, 1, p_imu.y, -p_imu.x, 0}};
           for (int r = 0; r < 2; ++r)
             for (int k = 0; k < 6; ++k)
-              s_jp[(r * 6 + k) * slots + s] = (Bm[r][0] * G[0][k] + Bm[r][1] * G[1][k] + Bm[r][2] * G[2][k]) * mult;
-          s_xyz[0 * slots + s] = xyz_ref.x; s_xyz[1 * slots + s] = xyz_ref.y; s_xyz[2 * slots + s] = xyz_ref.z;
-          s_uv[0 * slots + s] = pu; s_uv[1 * slots + s] = pv;
+              s_jp[(r * 6 + k) * stride + s] = (Bm[r][0] * G[0][k] + Bm[r][1] * G[1][k] + Bm[r][2] * G[2][k]) * mult;
+          s_xyz[0 * stride + s] = xyz_ref.x; s_xyz[1 * stride + s] = xyz_ref.y; s_xyz[2 * stride + s] = xyz_ref.z;
+          s_src[s] = i;
           s_cam[s] = (uint8_t)c;
         }
       }
@@ -250,14 +296,13 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
       __syncthreads();
     }
   }
-  n_total = min(n_total, slots);
-  const size_t ref_f0 = 0;
-  (void)ref_f0;
+  n_total = min(n_total, stride);
 
   if (n_total > 0) {
     if (tid == 0) {
-      ctl.n_total = n_total;
-      refreshCams(ctl, n_cams);
+      for (int k = 0; k < n_cams; ++k) storeRt(se3Mul(se3Mul(ctl.T_cam_imu[k], ctl.T), ctl.T_imu_cam[k]), ctl.Rt[k]);
+      ctl.alpha_f = (float)ctl.alpha;
+      ctl.beta_f = (float)ctl.beta;
       ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
     }
     const bool est_gain = ILLUM && opt.estimate_illumination_gain;
@@ -275,7 +320,8 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
         const int rf = P.ref_frame_idx ? P.ref_frame_idx[(size_t)pair * n_cams + c] : pair;
         const uint8_t* img = rp.level(rf, level);
         const int pitch = rp.pitch[level];
-        const double u_tl = s_uv[s] * scale - 2.5, v_tl = s_uv[slots + s] * scale - 2.5;
+        const size_t fi = ((size_t)pair * n_cams + c) * P.max_features + s_src[s];
+        const double u_tl = P.px[2 * fi] * scale - 2.5, v_tl = P.px[2 * fi + 1] * scale - 2.5;
         const int ui = (int)floor(u_tl), vi = (int)floor(v_tl);
         const double su = u_tl - ui, sv = v_tl - vi;
         const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
@@ -293,9 +339,7 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
             const unsigned t1 = (x + 1) < 4 ? byteOf(ra, x + 1) : byteOf(rb, x + 1 - 4);
             const unsigned b0 = x < 4 ? byteOf(na, x) : byteOf(nb, x - 4);
             const unsigned b1 = (x + 1) < 4 ? byteOf(na, x + 1) : byteOf(nb, x + 1 - 4);
-            const double val = wtl * t0 + wtr * t1 + wbl * b0 + wbr * b1;
-            const int k = (y == 0) ? (x - 1) : (y == 5) ? (28 + x - 1) : (4 + (y - 1) * 6 + x);
-            s_patch[k * slots + s] = val;
+            s_patch[patchIdx(x, y) * stride + s] = wtl * t0 + wtr * t1 + wbl * b0 + wbr * b1;
           }
           ra = na; rb = nb;
         }
@@ -303,20 +347,23 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
       __syncthreads();
 
       // ---- Gauss-Newton iterations of this level (mini_least_squares_solver.hpp:42-107) ----
+      unsigned vis_prev = 0u;  // bit j: was slot tid + j*kThreads visible in the previous iteration of this level
       const int max_iter = opt.max_iter;
       for (int iter = 0; iter < max_iter; ++iter) {
-        // zero per-warp partials
         for (int k = lane; k < NV; k += 32) s_red[warp * kNVmax + k] = 0.0;
         __syncwarp();
+        double* red = s_red + warp * kNVmax;
         const float alpha_f = ctl.alpha_f, beta_f = ctl.beta_f;
-        for (int s = tid; s < n_round; s += kThreads) {
+        unsigned vis_now = 0u;
+        int chunk_j = 0;
+        for (int s = tid; s < n_round; s += kThreads, ++chunk_j) {
           bool vis = false;
-          double sxx = 0, sxy = 0, syy = 0, gx = 0, gy = 0, chi = 0;
-          double sx6 = 0, sy6 = 0, sx7 = 0, sy7 = 0, s66 = 0, s67 = 0, s77 = 0, g6 = 0, g7 = 0;
+          double gx = 0, gy = 0, chi = 0, g6 = 0, g7 = 0;
+          PatchSums ps = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
           if (s < n_total) {
             const int c = s_cam[s];
             const double* Rt = ctl.Rt[c];
-            const double X = s_xyz[s], Y = s_xyz[slots + s], Z = s_xyz[2 * slots + s];
+            const double X = s_xyz[s], Y = s_xyz[stride + s], Z = s_xyz[2 * stride + s];
             const V3d pc{Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9], Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10],
                          Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11]};
             if (!(pc.z < 0.0)) {  // sparse_img_align.cpp:432-438
@@ -335,6 +382,7 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
                 const double su = u_tl - ui, sv = v_tl - vi;
                 const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
                 const double gain = 1.0 + alpha_f;
+                const double* patch = s_patch + s;
                 unsigned ra, rb;
                 loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
 #pragma unroll
@@ -348,58 +396,53 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
                     const unsigned b0 = byteOf(na, x);
                     const unsigned b1 = x < 3 ? byteOf(na, x + 1) : byteOf(nb, 0);
                     const double I = wtl * t0 + wtr * t1 + wbl * b0 + wbr * b1;
-                    // 6x6 patch (Y=y+1, X=x+1): centre, left/right, up/down
-                    const int kc = 4 + y * 6 + (x + 1);
-                    const int ku = (y == 0) ? x : (4 + (y - 1) * 6 + (x + 1));
-                    const int kd = (y == 3) ? (28 + x) : (4 + (y + 1) * 6 + (x + 1));
-                    const double ref = s_patch[kc * slots + s];
-                    const double dx = 0.5 * (s_patch[(kc + 1) * slots + s] - s_patch[(kc - 1) * slots + s]);
-                    const double dy = 0.5 * (s_patch[kd * slots + s] - s_patch[ku * slots + s]);
+                    const double ref = patch[patchIdx(x + 1, y + 1) * stride];
+                    // twice the central differences; the exact factor 0.5 is applied to the sums afterwards
+                    const double dx2 = patch[patchIdx(x + 2, y + 1) * stride] - patch[patchIdx(x, y + 1) * stride];
+                    const double dy2 = patch[patchIdx(x + 1, y + 2) * stride] - patch[patchIdx(x + 1, y) * stride];
                     const double res = (I * gain + beta_f) - ref;  // sparse_img_align.cpp:488-489
-                    double w = 1.0;
-                    if (opt.robustification) w = (double)tukeyWeight((float)(res / wscale_f));
-                    const double wdx = w * dx, wdy = w * dy;
-                    sxx += wdx * dx; sxy += wdx * dy; syy += wdy * dy;
-                    gx += wdx * res; gy += wdy * res;
-                    chi += res * res * w;
-                    if (ILLUM) {
-                      const double a6 = est_gain ? -ref : 0.0, a7 = est_off ? -1.0 : 0.0;
-                      sx6 += wdx * a6; sy6 += wdy * a6; sx7 += wdx * a7; sy7 += wdy * a7;
-                      s66 += w * a6 * a6; s67 += w * a6 * a7; s77 += w * a7 * a7;
-                      g6 += w * a6 * res; g7 += w * a7 * res;
+                    if (ROBUST) {
+                      const double w = (double)tukeyWeight((float)(res / wscale_f));
+                      const double wdx = w * dx2, wdy = w * dy2;
+                      ps.sxx += wdx * dx2; ps.sxy += wdx * dy2; ps.syy += wdy * dy2;
+                      gx += wdx * res; gy += wdy * res;
+                      chi += res * res * w;
+                      if (ILLUM) {
+                        const double a6 = est_gain ? -ref : 0.0, a7 = est_off ? -1.0 : 0.0;
+                        ps.sx6 += wdx * a6; ps.sy6 += wdy * a6; ps.sx7 += wdx * a7; ps.sy7 += wdy * a7;
+                        ps.s66 += w * a6 * a6; ps.s67 += w * a6 * a7; ps.s77 += w * a7 * a7;
+                        g6 += w * a6 * res; g7 += w * a7 * res;
+                      }
+                    } else {
+                      gx += dx2 * res; gy += dy2 * res;
+                      chi += res * res;
+                      if (ILLUM) {
+                        if (est_gain) g6 -= ref * res;
+                        if (est_off) g7 -= res;
+                      }
                     }
                   }
                   ra = na; rb = nb;
                 }
+                gx *= 0.5; gy *= 0.5;
+                if (ROBUST) {
+                  ps.sxx *= 0.25; ps.sxy *= 0.25; ps.syy *= 0.25;
+                  ps.sx6 *= 0.5; ps.sy6 *= 0.5; ps.sx7 *= 0.5; ps.sy7 *= 0.5;
+                }
               }
             }
           }
-          if (__ballot_sync(0xffffffffu, vis) == 0u) continue;
-          // rank-2 expansion + warp reduction, one accumulator at a time
-          double jp0[6], jp1[6], ua[6], va[6];
+          if (vis) vis_now |= (1u << chunk_j);
+          const bool changed = (iter == 0) || (vis != (((vis_prev >> chunk_j) & 1u) != 0u));
+          if (__ballot_sync(0xffffffffu, vis || changed) == 0u) continue;
           const int sl = (s < n_total) ? s : 0;
+          double jp0[6], jp1[6];
 #pragma unroll
           for (int k = 0; k < 6; ++k) {
-            jp0[k] = s_jp[k * slots + sl] * scale;
-            jp1[k] = s_jp[(6 + k) * slots + sl] * scale;
-            ua[k] = sxx * jp0[k] + sxy * jp1[k];
-            va[k] = sxy * jp0[k] + syy * jp1[k];
+            jp0[k] = s_jp[k * stride + sl] * scale;
+            jp1[k] = s_jp[(6 + k) * stride + sl] * scale;
           }
-          double* red = s_red + warp * kNVmax;
-          int idx = 0;
-#pragma unroll
-          for (int a = 0; a < D; ++a) {
-#pragma unroll
-            for (int b = a; b < D; ++b) {
-              double v;
-              if (b < 6) v = ua[a] * jp0[b] + va[a] * jp1[b];
-              else if (a < 6) v = (b == 6) ? (jp0[a] * sx6 + jp1[a] * sy6) : (jp0[a] * sx7 + jp1[a] * sy7);
-              else v = (a == 6 && b == 6) ? s66 : (a == 6 ? s67 : s77);
-              v = warpSum(v);
-              if (lane == 0) red[idx] += v;
-              ++idx;
-            }
-          }
+          if (ROBUST) reduceH<D>(ps, jp0, jp1, red, lane);
 #pragma unroll
           for (int a = 0; a < D; ++a) {
             double v;
@@ -413,12 +456,42 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
             if (lane == 0) red[NH + D] += v;
             v = warpSum(vis ? 16.0 : 0.0);
             if (lane == 0) red[NH + D + 1] += v;
+            const unsigned ch = __ballot_sync(0xffffffffu, changed);
+            if (lane == 0 && ch) red[NH + D + 2] += 1.0;
           }
         }
+        vis_prev = vis_now;
         __syncthreads();
+        bool h_fresh = ROBUST;
+        if (!ROBUST) {
+          // H depends only on the visible set: rebuild it when some patch entered or left the image
+          double any = 0.0;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) any += s_red[w * kNVmax + NH + D + 2];
+          h_fresh = (any != 0.0);
+          if (h_fresh) {
+            int cj = 0;
+            for (int s = tid; s < n_round; s += kThreads, ++cj) {
+              const bool vis = (vis_now >> cj) & 1u;
+              if (__ballot_sync(0xffffffffu, vis) == 0u) continue;
+              const int sl = (s < n_total) ? s : 0;
+              PatchSums ps = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+              if (vis) ps = unitWeightSums<ILLUM>(s_patch + sl, stride, est_gain, est_off);
+              double jp0[6], jp1[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) {
+                jp0[k] = s_jp[k * stride + sl] * scale;
+                jp1[k] = s_jp[(6 + k) * stride + sl] * scale;
+              }
+              reduceH<D>(ps, jp0, jp1, red, lane);
+            }
+            __syncthreads();
+          }
+        }
         if (warp == 0) {
-          // cross-warp totals: lane k owns accumulator k (NV <= 46 -> two per lane at most)
-          for (int k = lane; k < NV; k += 32) {
+          // cross-warp totals: lane k owns accumulator k; the H part is refreshed only when it was re-reduced
+          for (int k = lane; k < NH + D + 2; k += 32) {
+            if (k < NH && !h_fresh) continue;
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) t += s_red[w * kNVmax + k];
@@ -520,6 +593,14 @@ __global__ void __launch_bounds__(kThreads) sparse_align_kernel(const AlignParam
   }
 }
 
+template <bool ILLUM, bool ROBUST, int SLOTS>
+cudaError_t launchAlign(const AlignParams& P, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<ILLUM, ROBUST, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  sparse_align_kernel<ILLUM, ROBUST, SLOTS><<<P.B, kThreads, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cuda_pyr* const* ref_pyr,
@@ -546,9 +627,12 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   AlignParams P;
   memset(&P, 0, sizeof(P));
   P.n_cams = n_cams; P.B = B; P.max_features = max_features;
-  const int slots = ((n_cams * max_features + 7) / 8) * 8;
+  const int need = n_cams * max_features;
+  const bool fixed = need <= kFixedSlots;
+  const int slots = fixed ? kFixedSlots : ((need + 7) / 8) * 8;
+  if (slots > 32 * kThreads) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: too many features per bundle");
   P.slots = slots;
-  const size_t smem = (size_t)slots * kPerSlotDoubles * 8 + (size_t)kWarps * kNVmax * 8 + sizeof(Ctl) + slots + 16;
+  const size_t smem = (size_t)slots * kPerSlotBytes + (size_t)kWarps * kNVmax * 8 + sizeof(Ctl) + 32;
   if (smem > 227 * 1024) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: n_cams*max_features exceeds the shared-memory capacity (~590 features per bundle)");
   for (int c = 0; c < n_cams; ++c) {
     P.ref_pyr[c] = makeView(ref_pyr[c]);
@@ -573,13 +657,16 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   if (st.failed()) return st.finish();
 
   const bool illum = opt->estimate_illumination_gain || opt->estimate_illumination_offset;
-  if (illum) {
-    SVO_CUDA_TRY(ctx, cudaFuncSetAttribute(sparse_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sparse_align_kernel<true><<<B, kThreads, smem, ctx->stream>>>(P);
+  const bool robust = opt->robustification != 0;
+  cudaError_t e;
+  if (fixed) {
+    if (illum) e = robust ? launchAlign<true, true, kFixedSlots>(P, smem, ctx->stream) : launchAlign<true, false, kFixedSlots>(P, smem, ctx->stream);
+    else e = robust ? launchAlign<false, true, kFixedSlots>(P, smem, ctx->stream) : launchAlign<false, false, kFixedSlots>(P, smem, ctx->stream);
   } else {
-    SVO_CUDA_TRY(ctx, cudaFuncSetAttribute(sparse_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sparse_align_kernel<false><<<B, kThreads, smem, ctx->stream>>>(P);
+    if (illum) e = robust ? launchAlign<true, true, 0>(P, smem, ctx->stream) : launchAlign<true, false, 0>(P, smem, ctx->stream);
+    else e = robust ? launchAlign<false, true, 0>(P, smem, ctx->stream) : launchAlign<false, false, 0>(P, smem, ctx->stream);
   }
-  SVO_LAUNCH_CHECK(ctx);
+  ctx->launches++;
+  SVO_CUDA_TRY(ctx, e);
   return st.finish();
 }
