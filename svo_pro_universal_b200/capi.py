@@ -350,6 +350,13 @@ def align1d(ctx, pyr, frame_idx, level, direction, patch_with_border, px, n_iter
     return px, conv, hinv
 
 
+def _n_features(ftrs):
+    """Number of svo_feature records in a FEATURE_DTYPE numpy array or a torch byte tensor holding the same bytes."""
+    if _is_torch(ftrs):
+        return ftrs.numel() * ftrs.element_size() // FEATURE_DTYPE.itemsize
+    return len(ftrs)
+
+
 def make_features(px, f, grad, ftype, level):
     n = len(px)
     a = np.zeros(n, FEATURE_DTYPE)
@@ -358,7 +365,7 @@ def make_features(px, f, grad, ftype, level):
 
 
 def warp_affine(ctx, ref_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, depth, ref_frame_idx=None, T_idx=None):
-    M = len(ftrs)
+    M = _n_features(ftrs)
     A = np.zeros((M, 4))
     sl = np.zeros(M, np.int32)
     pwb = np.zeros((M, 100), np.uint8)
@@ -372,7 +379,7 @@ def warp_affine(ctx, ref_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, depth, ref_fram
 
 def find_match_direct(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, ref_depth, px_guess, opt, ref_frame_idx=None,
                       cur_frame_idx=None, T_idx=None, out=None):
-    M = len(ftrs)
+    M = _n_features(ftrs)
     if out is None:
         out = np.zeros(M, MATCH_OUT_DTYPE)
     if not _is_torch(T_cur_ref):
@@ -385,7 +392,7 @@ def find_match_direct(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, 
 
 def find_epipolar_match_direct(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, T_cur_ref, ftrs, d_inv, opt, ref_frame_idx=None,
                                cur_frame_idx=None, T_idx=None, out=None):
-    M = len(ftrs)
+    M = _n_features(ftrs)
     if out is None:
         out = np.zeros(M, MATCH_OUT_DTYPE)
     if not _is_torch(T_cur_ref):
@@ -418,7 +425,7 @@ def compute_tau(ctx, T_ref_cur, f, z, px_error_angle):
 def update_seeds(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, ftrs, types, state, seed_mu_range, obs_frame_idx, obs_T_idx, T_cur_ref,
                  mopt, dopt, ref_frame_idx=None, want_match_results=True):
     """svo_cuda_update_seeds; types/state updated in place. Returns (n_success, match_results [n_obs,S] or None)."""
-    S = len(ftrs)
+    S = _n_features(ftrs)
     n_obs = obs_frame_idx.shape[0]
     dev = _is_torch(state)
     if dev:

@@ -1,0 +1,434 @@
+// Host facades over the C ABI (see svo_b200.h). Every method packs its arguments into the POD batches of
+// include/svo_cuda.h, calls ONE entry point with host buffers (SVO_MEM_HOST) and unpacks the results; nothing here
+// computes the hot path on the CPU.
+#include "svo_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace svo {
+
+// ---- Transformation (kindr::minimal::QuatTransformation semantics; host-side glue only) --------------------------------
+static std::array<double, 3> rotate(const std::array<double, 4>& q, const std::array<double, 3>& v) {
+  // Eigen QuaternionBase::_transformVector
+  const double qx = q[1], qy = q[2], qz = q[3], w = q[0];
+  double ux = qy * v[2] - qz * v[1], uy = qz * v[0] - qx * v[2], uz = qx * v[1] - qy * v[0];
+  ux += ux; uy += uy; uz += uz;
+  return {v[0] + w * ux + (qy * uz - qz * uy), v[1] + w * uy + (qz * ux - qx * uz), v[2] + w * uz + (qx * uy - qy * ux)};
+}
+Transformation Transformation::inverse() const {  // quat-transformation-inl.h:209-213
+  Transformation r;
+  r.q = {q[0], -q[1], -q[2], -q[3]};
+  const auto v = rotate(r.q, t);
+  r.t = {-v[0], -v[1], -v[2]};
+  return r;
+}
+Transformation Transformation::operator*(const Transformation& b) const {  // quat-transformation-inl.h:150-156
+  Transformation r;
+  const auto& a = q;
+  r.q = {a[0] * b.q[0] - a[1] * b.q[1] - a[2] * b.q[2] - a[3] * b.q[3], a[0] * b.q[1] + a[1] * b.q[0] + a[2] * b.q[3] - a[3] * b.q[2],
+         a[0] * b.q[2] + a[2] * b.q[0] + a[3] * b.q[1] - a[1] * b.q[3], a[0] * b.q[3] + a[3] * b.q[0] + a[1] * b.q[2] - a[2] * b.q[1]};
+  const double n2 = r.q[0] * r.q[0] + r.q[1] * r.q[1] + r.q[2] * r.q[2] + r.q[3] * r.q[3];
+  if (std::abs(n2 - 1.0) > 1e-4) { const double n = std::sqrt(n2); for (double& c : r.q) c /= n; }
+  const auto v = rotate(q, b.t);
+  r.t = {t[0] + v[0], t[1] + v[1], t[2] + v[2]};
+  return r;
+}
+
+void Frame::clearFeatureStorage() {
+  px_vec_.clear(); f_vec_.clear(); grad_vec_.clear(); score_vec_.clear(); level_vec_.clear(); type_vec_.clear();
+  depth_vec_.clear(); invmu_sigma2_a_b_vec_.clear();
+  num_features_ = 0;
+}
+
+// ---- device plumbing -----------------------------------------------------------------------------------------------------
+namespace b200 {
+static void check(int rc, const char* what) {
+  if (rc != SVO_OK) throw Error(std::string(what) + " failed with status " + std::to_string(rc) + ": " + svo_cuda_last_error(context()));
+}
+svo_cuda_ctx* context() {
+  static thread_local svo_cuda_ctx* ctx = nullptr;
+  if (!ctx) {
+    const int rc = svo_cuda_ctx_create(0, &ctx);
+    if (rc != SVO_OK) throw Error("svo_cuda_ctx_create failed (no CUDA device? this front-end has no CPU fallback), status " + std::to_string(rc));
+  }
+  return ctx;
+}
+GpuPyramid::GpuPyramid(int width, int height, int n_levels) : width_(width), height_(height), n_levels_(n_levels) {
+  check(svo_cuda_pyr_create(context(), 1, width, height, n_levels, -1, &pyr_), "svo_cuda_pyr_create");
+}
+GpuPyramid::~GpuPyramid() {
+  if (pyr_) svo_cuda_pyr_destroy(context(), pyr_);
+}
+const GpuPyramid& ensureGpu(const Frame& frame) {
+  if (!frame.gpu_) {
+    if (frame.img_pyr_.empty() || frame.img_pyr_[0].empty()) throw Error("frame has no image");
+    const Image& l0 = frame.img_pyr_[0];
+    auto g = std::make_shared<GpuPyramid>(l0.cols, l0.rows, int(frame.img_pyr_.size()));
+    check(svo_cuda_pyr_upload(context(), g->handle(), 0, 1, l0.data, l0.step, l0.step * l0.rows, SVO_MEM_HOST), "svo_cuda_pyr_upload");
+    check(svo_cuda_pyr_build(context(), g->handle(), 0, 1), "svo_cuda_pyr_build");
+    frame.gpu_ = g;
+  }
+  return *frame.gpu_;
+}
+}  // namespace b200
+
+namespace frame_utils {
+void createImgPyramid(const Image& img_level_0, int n_levels, ImgPyr& pyr, std::shared_ptr<b200::GpuPyramid>* gpu) {
+  if (img_level_0.empty() || img_level_0.rows <= 0 || img_level_0.cols <= 0 || n_levels <= 0)
+    throw b200::Error("createImgPyramid: invalid image or level count");  // CHECKs of frame.cpp:374-377
+  auto g = std::make_shared<b200::GpuPyramid>(img_level_0.cols, img_level_0.rows, n_levels);
+  svo_cuda_ctx* ctx = b200::context();
+  b200::check(svo_cuda_pyr_upload(ctx, g->handle(), 0, 1, img_level_0.data, img_level_0.step, img_level_0.step * img_level_0.rows, SVO_MEM_HOST),
+              "svo_cuda_pyr_upload");
+  b200::check(svo_cuda_pyr_build(ctx, g->handle(), 0, 1), "svo_cuda_pyr_build");
+  pyr.resize(n_levels);
+  pyr[0] = img_level_0;
+  if (!pyr[0].storage.empty()) pyr[0].data = pyr[0].storage.data();
+  for (int l = 1; l < n_levels; ++l) {
+    int cols, rows;
+    svo_cuda_pyr_level_info(g->handle(), l, &cols, &rows, nullptr, nullptr, nullptr);
+    pyr[l] = Image(rows, cols);
+    b200::check(svo_cuda_pyr_download(ctx, g->handle(), 0, l, pyr[l].data, pyr[l].step, SVO_MEM_HOST), "svo_cuda_pyr_download");
+  }
+  if (gpu) *gpu = g;
+}
+}  // namespace frame_utils
+
+// ---- SparseImgAlign ---------------------------------------------------------------------------------------------------------
+SparseImgAlignBase::SolverOptions SparseImgAlignBase::getDefaultSolverOptions() {
+  SolverOptions options;
+  options.max_iter = 10;
+  options.eps = 0.0005;
+  return options;
+}
+void SparseImgAlignBase::setWeightedPrior(const Transformation& T_cur_ref_prior, double alpha_prior, double beta_prior, double lambda_rot,
+                                          double lambda_trans, double lambda_alpha, double lambda_beta) {
+  prior_lambda_rot_ = lambda_rot; prior_lambda_trans_ = lambda_trans; prior_lambda_alpha_ = lambda_alpha; prior_lambda_beta_ = lambda_beta;
+  T_cur_ref_prior.toArray(prior_.T);
+  prior_.alpha = alpha_prior; prior_.beta = beta_prior;
+  have_prior_ = true;
+}
+void SparseImgAlignBase::reset() {
+  have_prior_ = false;
+  chi2_ = 1e10;
+}
+
+size_t SparseImgAlign::run(const FrameBundle::Ptr& ref_frames, const FrameBundle::Ptr& cur_frames) {
+  if (!ref_frames || !cur_frames || ref_frames->empty() || ref_frames->size() != cur_frames->size() || ref_frames->size() > SVO_MAX_CAMS)
+    throw b200::Error("SparseImgAlign::run: invalid frame bundles");  // CHECKs of sparse_img_align.cpp:38-39
+  const int n_cams = int(ref_frames->size());
+  size_t max_f = 1;
+  for (const auto& f : ref_frames->frames_) max_f = std::max(max_f, f->num_features_);
+  std::vector<const svo_cuda_pyr*> rp(n_cams), cp(n_cams);
+  std::vector<svo_camera> cams(n_cams);
+  std::vector<double> T_cam_imu(7 * n_cams), px(2 * max_f * n_cams), fv(3 * max_f * n_cams), depth(max_f * n_cams, 1.0);
+  std::vector<uint8_t> eligible(max_f * n_cams, 0);
+  std::vector<int> n_features(n_cams);
+  for (int c = 0; c < n_cams; ++c) {
+    const Frame& rf = *ref_frames->at(c);
+    const Frame& cf = *cur_frames->at(c);
+    rp[c] = b200::ensureGpu(rf).handle();
+    cp[c] = b200::ensureGpu(cf).handle();
+    cams[c] = rf.cam_->model;
+    rf.T_cam_imu_.toArray(&T_cam_imu[7 * c]);
+    n_features[c] = int(rf.num_features_);
+    for (size_t i = 0; i < rf.num_features_; ++i) {
+      const size_t k = c * max_f + i;
+      px[2 * k] = rf.px_vec_[i][0]; px[2 * k + 1] = rf.px_vec_[i][1];
+      fv[3 * k] = rf.f_vec_[i][0]; fv[3 * k + 1] = rf.f_vec_[i][1]; fv[3 * k + 2] = rf.f_vec_[i][2];
+      const bool has_depth = i < rf.depth_vec_.size() && rf.depth_vec_[i] > 0.0;
+      depth[k] = has_depth ? rf.depth_vec_[i] : 1.0;
+      // sparse_img_align.cpp:242-248: needs a landmark or seed reference, and must not be a MapPoint type
+      eligible[k] = has_depth && !isMapPoint(rf.type_vec_[i]);
+    }
+  }
+  double T_ref[7], T_cur[7];
+  ref_frames->at(0)->T_imu_world().toArray(T_ref);
+  cur_frames->at(0)->T_imu_world().toArray(T_cur);
+  svo_sparse_align_options o{};
+  o.max_level = options_.max_level; o.min_level = options_.min_level;
+  o.estimate_illumination_gain = options_.estimate_illumination_gain;
+  o.estimate_illumination_offset = options_.estimate_illumination_offset;
+  o.use_distortion_jacobian = options_.use_distortion_jacobian;
+  o.robustification = options_.robustification;
+  o.weight_scale = options_.weight_scale;
+  o.max_iter = int(solver_options_.max_iter);
+  o.eps = solver_options_.eps;
+  o.alpha_init = alpha_init_; o.beta_init = beta_init_;
+  o.lambda_rot = prior_lambda_rot_; o.lambda_trans = prior_lambda_trans_; o.lambda_alpha = prior_lambda_alpha_; o.lambda_beta = prior_lambda_beta_;
+  svo_align_result res{};
+  const int zero = 0;
+  std::vector<int> idx(n_cams, zero);
+  b200::check(svo_cuda_sparse_align(b200::context(), n_cams, rp.data(), cp.data(), idx.data(), idx.data(), cams.data(), T_cam_imu.data(), 1,
+                                    T_ref, T_cur, n_features.data(), int(max_f), px.data(), fv.data(), depth.data(), eligible.data(), &o,
+                                    have_prior_ ? &prior_ : nullptr, &res, SVO_MEM_HOST),
+              "svo_cuda_sparse_align");
+  if (res.n_tracked == 0) return 0;  // "SparseImgAlign: no features to track!" — poses are left untouched (:53-57)
+  for (int c = 0; c < n_cams; ++c) cur_frames->at(c)->T_f_w_ = Transformation::fromArray(res.T_f_w[c]);  // :103-106
+  chi2_ = res.chi2;
+  std::copy(res.H, res.H + 64, H_.begin());
+  alpha_init_ = 0.0;  // :108-110
+  beta_init_ = 0.0;
+  return size_t(res.n_tracked);
+}
+
+// ---- feature alignment ------------------------------------------------------------------------------------------------------
+namespace {
+struct OneLevel {  // a single host image as a 1-frame, 1-level device pyramid
+  b200::GpuPyramid g;
+  explicit OneLevel(const Image& img) : g(img.cols, img.rows, 1) {
+    b200::check(svo_cuda_pyr_upload(b200::context(), g.handle(), 0, 1, img.data, img.step, img.step * img.rows, SVO_MEM_HOST), "svo_cuda_pyr_upload");
+  }
+};
+}  // namespace
+namespace feature_alignment {
+bool align1D(const Image& cur_img, const GradientVector& dir, uint8_t* ref_patch_with_border, uint8_t* /*ref_patch*/, const int n_iter,
+             const bool affine_est_offset, const bool affine_est_gain, Keypoint* cur_px_estimate, double* h_inv) {
+  if (!cur_px_estimate) throw b200::Error("align1D: cur_px_estimate is null");  // CHECK_NOTNULL (:42)
+  OneLevel lv(cur_img);
+  const int zero = 0;
+  uint8_t conv = 0;
+  double h = 0.0;
+  b200::check(svo_cuda_align1d(b200::context(), lv.g.handle(), &zero, &zero, 1, dir.data(), ref_patch_with_border, n_iter, affine_est_offset,
+                               affine_est_gain, cur_px_estimate->data(), &h, &conv, SVO_MEM_HOST), "svo_cuda_align1d");
+  if (h_inv) *h_inv = h;
+  return conv != 0;
+}
+bool align2D(const Image& cur_img, uint8_t* ref_patch_with_border, uint8_t* /*ref_patch*/, const int n_iter, const bool affine_est_offset,
+             const bool affine_est_gain, Keypoint& cur_px_estimate, bool /*no_simd*/) {
+  OneLevel lv(cur_img);
+  const int zero = 0;
+  uint8_t conv = 0;
+  b200::check(svo_cuda_align2d(b200::context(), lv.g.handle(), &zero, &zero, 1, ref_patch_with_border, n_iter, affine_est_offset, affine_est_gain,
+                               cur_px_estimate.data(), &conv, SVO_MEM_HOST), "svo_cuda_align2d");
+  return conv != 0;
+}
+}  // namespace feature_alignment
+
+// ---- Matcher -----------------------------------------------------------------------------------------------------------------
+svo_matcher_options Matcher::cOptions() const {
+  svo_matcher_options o{};
+  o.align_1d = options_.align_1d; o.align_max_iter = options_.align_max_iter;
+  o.max_epi_search_steps = int(options_.max_epi_search_steps);
+  o.subpix_refinement = options_.subpix_refinement;
+  o.epi_search_edgelet_filtering = options_.epi_search_edgelet_filtering;
+  o.scan_on_unit_sphere = options_.scan_on_unit_sphere;
+  o.epi_search_edgelet_max_angle = options_.epi_search_edgelet_max_angle;
+  o.affine_est_offset = options_.affine_est_offset_; o.affine_est_gain = options_.affine_est_gain_;
+  o.max_patch_diff_ratio = options_.max_patch_diff_ratio;
+  return o;
+}
+static svo_feature cFeature(const FeatureWrapper& f) {
+  svo_feature c{};
+  c.px[0] = f.px[0]; c.px[1] = f.px[1];
+  c.f[0] = f.f[0]; c.f[1] = f.f[1]; c.f[2] = f.f[2];
+  c.grad[0] = f.grad[0]; c.grad[1] = f.grad[1];
+  c.type = int(f.type);
+  c.level = f.level;
+  return c;
+}
+static void unpack(Matcher& m, const svo_match_out& o) {
+  std::copy(o.A_cur_ref, o.A_cur_ref + 4, m.A_cur_ref_.begin());
+  m.epi_length_pyramid_ = o.epi_length_pyramid;
+  m.h_inv_ = o.h_inv;
+  m.search_level_ = o.search_level;
+  m.reject_ = o.reject != 0;
+  m.px_cur_ = {o.px_cur[0], o.px_cur[1]};
+  m.f_cur_ = {o.f_cur[0], o.f_cur[1], o.f_cur[2]};
+}
+Matcher::MatchResult Matcher::findMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const FeatureWrapper& ref_ftr,
+                                              const FloatType& ref_depth, Keypoint& px_cur) {
+  const svo_feature ft = cFeature(ref_ftr);
+  const svo_matcher_options o = cOptions();
+  double T[7];
+  (cur_frame.T_f_w_ * ref_frame.T_f_w_.inverse()).toArray(T);  // cur.T_cam_world() * ref.T_world_cam() (matcher.cpp:49)
+  svo_match_out out{};
+  const int zero = 0;
+  const double d = ref_depth;
+  b200::check(svo_cuda_find_match_direct(b200::context(), b200::ensureGpu(ref_frame).handle(), b200::ensureGpu(cur_frame).handle(), &zero, &zero,
+                                         &ref_frame.cam_->model, &cur_frame.cam_->model, T, &zero, 1, &ft, &d, px_cur.data(), &o, &out, SVO_MEM_HOST),
+              "svo_cuda_find_match_direct");
+  unpack(*this, out);
+  if (out.result == 0) px_cur = px_cur_;
+  return static_cast<MatchResult>(out.result);
+}
+Matcher::MatchResult Matcher::findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const FeatureWrapper& ref_ftr,
+                                                      const double d_estimate_inv, const double d_min_inv, const double d_max_inv, double& depth) {
+  return findEpipolarMatchDirect(ref_frame, cur_frame, cur_frame.T_f_w_ * ref_frame.T_f_w_.inverse(), ref_ftr, d_estimate_inv, d_min_inv,
+                                 d_max_inv, depth);  // matcher.cpp:143-155
+}
+Matcher::MatchResult Matcher::findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const Transformation& T_cur_ref,
+                                                      const FeatureWrapper& ref_ftr, const double d_estimate_inv, const double d_min_inv,
+                                                      const double d_max_inv, double& depth) {
+  const svo_feature ft = cFeature(ref_ftr);
+  const svo_matcher_options o = cOptions();
+  double T[7];
+  T_cur_ref.toArray(T);
+  const double d3[3] = {d_estimate_inv, d_min_inv, d_max_inv};
+  svo_match_out out{};
+  const int zero = 0;
+  b200::check(svo_cuda_find_epipolar_match_direct(b200::context(), b200::ensureGpu(ref_frame).handle(), b200::ensureGpu(cur_frame).handle(), &zero,
+                                                  &zero, &ref_frame.cam_->model, &cur_frame.cam_->model, T, &zero, 1, &ft, d3, &o, &out, SVO_MEM_HOST),
+              "svo_cuda_find_epipolar_match_direct");
+  unpack(*this, out);
+  if (out.result == 0) depth = out.depth;
+  return static_cast<MatchResult>(out.result);
+}
+std::string Matcher::getResultString(const MatchResult& result) {  // matcher.cpp:243-260
+  switch (result) {
+    case MatchResult::kSuccess: return "success";
+    case MatchResult::kFailScore: return "fail score";
+    case MatchResult::kFailTriangulation: return "fail triangulation";
+    case MatchResult::kFailVisibility: return "fail visibility";
+    case MatchResult::kFailWarp: return "fail warp";
+    case MatchResult::kFailAlignment: return "fail alignment";
+    case MatchResult::kFailRange: return "fail range";
+    case MatchResult::kFailAngle: return "fail angle";
+    case MatchResult::kFailCloseView: return "fail close view";
+    case MatchResult::kFailLock: return "fail lock";
+    default: return "unknown";
+  }
+}
+
+// ---- DepthFilter ---------------------------------------------------------------------------------------------------------------
+namespace depth_filter_utils {
+static svo_depth_filter_options cDepthOptions(double seed_thresh, double map_thresh, bool check_visibility, bool check_convergence, bool vogiatzis) {
+  svo_depth_filter_options d{};
+  d.seed_convergence_sigma2_thresh = seed_thresh;
+  d.mappoint_convergence_sigma2_thresh = map_thresh;
+  d.px_error_angle = 0.0;  // derived from the cur camera: getAngleError(1.0), depth_filter.cpp:383-384
+  d.check_visibility = check_visibility; d.check_convergence = check_convergence; d.use_vogiatzis_update = vogiatzis;
+  return d;
+}
+// Seeds `indices` of ref_frame against cur_frame in one launch; writes states/types back. Returns #successes.
+static size_t updateSeedsOfFrame(const Frame& cur_frame, Frame& ref_frame, const std::vector<size_t>& indices, Matcher& matcher,
+                                 const svo_depth_filter_options& dopt) {
+  if (cur_frame.id_ == ref_frame.id_ || indices.empty()) return 0;  // "update seed with ref frame" (depth_filter.cpp:377-381)
+  const int S = int(indices.size());
+  std::vector<svo_feature> ft(S);
+  std::vector<uint8_t> types(S);
+  std::vector<double> state(4 * S), mu_range(S, ref_frame.seed_mu_range_);
+  std::vector<int> zeros(S, 0);
+  for (int k = 0; k < S; ++k) {
+    const size_t i = indices[k];
+    ft[k] = cFeature(FeatureWrapper{ref_frame.type_vec_[i], ref_frame.px_vec_[i], ref_frame.f_vec_[i], ref_frame.grad_vec_[i], ref_frame.level_vec_[i]});
+    types[k] = uint8_t(ref_frame.type_vec_[i]);
+    std::copy(ref_frame.invmu_sigma2_a_b_vec_[i].begin(), ref_frame.invmu_sigma2_a_b_vec_[i].end(), &state[4 * k]);
+  }
+  double T[7];
+  (cur_frame.T_f_w_ * ref_frame.T_f_w_.inverse()).toArray(T);  // depth_filter.cpp:406
+  const svo_matcher_options mo = matcher.cOptions();
+  int n_success = 0;
+  b200::check(svo_cuda_update_seeds(b200::context(), b200::ensureGpu(ref_frame).handle(), b200::ensureGpu(cur_frame).handle(), &ref_frame.cam_->model,
+                                    &cur_frame.cam_->model, S, zeros.data(), ft.data(), types.data(), state.data(), mu_range.data(), 1, zeros.data(),
+                                    zeros.data(), T, &mo, &dopt, &n_success, nullptr, SVO_MEM_HOST),
+              "svo_cuda_update_seeds");
+  for (int k = 0; k < S; ++k) {
+    const size_t i = indices[k];
+    ref_frame.type_vec_[i] = FeatureType(types[k]);
+    std::copy(&state[4 * k], &state[4 * k] + 4, ref_frame.invmu_sigma2_a_b_vec_[i].begin());
+  }
+  return size_t(n_success);
+}
+bool updateSeed(const Frame& cur_frame, Frame& ref_frame, const size_t& seed_index, Matcher& matcher, const FloatType sigma2_convergence_threshold,
+                const bool check_visibility, const bool check_convergence, const bool use_vogiatzis_update) {
+  const svo_depth_filter_options d =
+      cDepthOptions(sigma2_convergence_threshold, sigma2_convergence_threshold, check_visibility, check_convergence, use_vogiatzis_update);
+  return updateSeedsOfFrame(cur_frame, ref_frame, {seed_index}, matcher, d) == 1;
+}
+bool updateFilterVogiatzis(const FloatType z, const FloatType tau2, const FloatType z_range, SeedState& seed) {
+  uint8_t ok = 0;
+  b200::check(svo_cuda_update_filter_vogiatzis(b200::context(), 1, &z, &tau2, &z_range, seed.data(), &ok, SVO_MEM_HOST), "svo_cuda_update_filter_vogiatzis");
+  return ok != 0;
+}
+double computeTau(const Transformation& T_ref_cur, const BearingVector& f, const FloatType z, const FloatType px_error_angle) {
+  double T[7], tau = 0.0;
+  T_ref_cur.toArray(T);
+  b200::check(svo_cuda_compute_tau(b200::context(), 1, T, f.data(), &z, px_error_angle, &tau, SVO_MEM_HOST), "svo_cuda_compute_tau");
+  return tau;
+}
+}  // namespace depth_filter_utils
+
+DepthFilter::DepthFilter(const DepthFilterOptions& options) : options_(options) {
+  matcher_.options_.scan_on_unit_sphere = options.scan_epi_unit_sphere;  // depth_filter.cpp:35-41
+  matcher_.options_.affine_est_offset_ = options.affine_est_offset;
+  matcher_.options_.affine_est_gain_ = options.affine_est_gain;
+}
+size_t DepthFilter::updateSeeds(const std::vector<FramePtr>& ref_frames_with_seeds, const FramePtr& cur_frame) {
+  size_t n_success = 0;
+  const svo_depth_filter_options d = depth_filter_utils::cDepthOptions(options_.seed_convergence_sigma2_thresh,
+                                                                       options_.mappoint_convergence_sigma2_thresh, true, false, true);
+  for (const FramePtr& ref_frame : ref_frames_with_seeds) {
+    std::vector<size_t> seeds;
+    for (size_t i = 0; i < ref_frame->num_features_; ++i)
+      if (isSeed(ref_frame->type_vec_[i])) seeds.push_back(i);
+    n_success += depth_filter_utils::updateSeedsOfFrame(*cur_frame, *ref_frame, seeds, matcher_, d);
+  }
+  return n_success;
+}
+
+// ---- FAST detector ----------------------------------------------------------------------------------------------------------------
+namespace feature_detection_utils {
+void fastDetector(const b200::GpuPyramid& gpu, const int threshold, const int border, const size_t min_level, const size_t max_level,
+                  Corners& corners, OccupandyGrid2D& grid) {
+  if (corners.size() != grid.occupancy_.size() || int(max_level) > gpu.n_levels() - 1)
+    throw b200::Error("fastDetector: corners/grid size mismatch or max_level beyond the pyramid");  // CHECKs of :154-155
+  svo_detector_options o{threshold, border, int(min_level), int(max_level), grid.cell_size, 10};
+  std::vector<svo_corner> out(corners.size());
+  b200::check(svo_cuda_fast_detect(b200::context(), gpu.handle(), 0, 1, &o, grid.occupancy_.data(), out.data(), SVO_MEM_HOST), "svo_cuda_fast_detect");
+  for (size_t k = 0; k < out.size(); ++k)
+    if (out[k].score > corners[k].score) corners[k] = Corner(out[k].x, out[k].y, out[k].score, out[k].level, out[k].angle);
+}
+}  // namespace feature_detection_utils
+
+FastDetector::FastDetector(const DetectorOptions& options, const CameraPtr& cam)
+    : options_(options),
+      grid_(int(options.cell_size), int(std::ceil(double(cam->imageWidth()) / options.cell_size)),
+            int(std::ceil(double(cam->imageHeight()) / options.cell_size))) {}
+
+void FastDetector::detect(const FramePtr& frame) {
+  // FastDetector::detect (feature_detection.cpp:53-74) + fillFeatures (feature_detection_utils.cpp:72-142)
+  Corners corners(size_t(grid_.n_cols) * grid_.n_rows, Corner(0, 0, float(options_.threshold_primary), 0, 0.0f));
+  feature_detection_utils::fastDetector(b200::ensureGpu(*frame), int(options_.threshold_primary), options_.border, options_.min_level,
+                                        options_.max_level, corners, grid_);
+  std::vector<size_t> idx;
+  for (size_t k = 0; k < corners.size(); ++k)
+    if (corners[k].score > options_.threshold_primary) {
+      idx.push_back(k);
+      grid_.occupancy_[grid_.getCellIndex(corners[k].x, corners[k].y)] = 1;
+    }
+  std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return corners[a].score > corners[b].score; });
+  const svo_camera& cm = frame->cam_->model;
+  for (size_t k : idx) {
+    const Corner& c = corners[k];
+    frame->px_vec_.push_back({double(c.x), double(c.y)});
+    frame->grad_vec_.push_back({std::cos(c.angle), std::sin(c.angle)});
+    frame->score_vec_.push_back(c.score);
+    frame->level_vec_.push_back(c.level);
+    frame->type_vec_.push_back(FeatureType::kCorner);
+    frame->depth_vec_.push_back(-1.0);
+    frame->invmu_sigma2_a_b_vec_.push_back({0, 0, 0, 0});
+    // frame_utils::computeNormalizedBearingVectors (frame.cpp:427-439): f = normalize(backProject3(px)); <= n_cells keypoints
+    // per keyframe, host glue (pinhole_projection.hpp:30-41, radial_tangential_distortion.h:80-95)
+    double x = (c.x - cm.cx) * (1.0 / cm.fx), y = (c.y - cm.cy) * (1.0 / cm.fy);
+    if (cm.distortion) {
+      const double x0 = x, y0 = y;
+      for (int it = 0; it < 5; ++it) {
+        const double xx = x * x, yy = y * y, xy = x * y, xy2 = 2 * xy, r2 = xx + yy;
+        const double icdist = 1.0 / (1.0 + (cm.k1 + cm.k2 * r2) * r2);
+        const double ddx = cm.p1 * xy2 + cm.p2 * (r2 + 2.0 * xx), ddy = cm.p2 * xy2 + cm.p1 * (r2 + 2.0 * yy);
+        x = (x0 - ddx) * icdist;
+        y = (y0 - ddy) * icdist;
+      }
+    }
+    const double n = std::sqrt(x * x + y * y + 1.0);
+    frame->f_vec_.push_back({x / n, y / n, 1.0 / n});
+  }
+  frame->num_features_ = frame->px_vec_.size();
+  resetGrid();
+}
+
+}  // namespace svo

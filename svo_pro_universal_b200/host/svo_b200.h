@@ -1,0 +1,324 @@
+// svo_b200.h — C++ host facades of the B200 front-end hot path, mirroring the reference's class surface.
+//
+// The reference wires these classes behind src/svo/include/svo/svo_factory.h by new-ing them in FrameHandlerBase
+// (src/svo/src/frame_handler_base.cpp:125,135,145). The facades keep the reference's names, method signatures, public data
+// members and error behaviour for the hot path and forward the work to the C ABI of include/svo_cuda.h — there is no CPU
+// implementation behind them. In the reference tree the argument types are Eigen / OpenCV / minkindr types; neither library
+// is installed in this build environment, so this header carries minimal stand-ins with the SAME member names the facades
+// touch (Frame::img_pyr_, px_vec_, f_vec_, T_f_w_, invmu_sigma2_a_b_vec_, ...). INTEGRATION.md lists the one-line adapters from
+// the real types (cv::Mat -> Image, Eigen::Matrix<double,2,Dynamic> -> Keypoints, kindr::minimal::QuatTransformation ->
+// Transformation).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/svo_cuda.h"
+
+namespace svo {
+
+using FloatType = double;  // src/svo_common/include/svo/common/types.h:16
+
+// ---- stand-ins for the container types (see header comment) ------------------------------------------------------------
+struct Image {  // cv::Mat as used on this path: 8-bit, data / cols / rows / step
+  std::vector<uint8_t> storage;
+  uint8_t* data = nullptr;
+  int cols = 0, rows = 0;
+  size_t step = 0;
+  Image() = default;
+  Image(int rows_, int cols_) : storage(size_t(rows_) * cols_), data(storage.data()), cols(cols_), rows(rows_), step(cols_) {}
+  bool empty() const { return data == nullptr; }
+};
+using ImgPyr = std::vector<Image>;
+
+struct Transformation {  // kindr::minimal::QuatTransformation: rotation quaternion (w,x,y,z) + position
+  std::array<double, 4> q{{1, 0, 0, 0}};
+  std::array<double, 3> t{{0, 0, 0}};
+  void toArray(double* a) const { for (int i = 0; i < 4; ++i) a[i] = q[i]; for (int i = 0; i < 3; ++i) a[4 + i] = t[i]; }
+  static Transformation fromArray(const double* a) { Transformation T; for (int i = 0; i < 4; ++i) T.q[i] = a[i]; for (int i = 0; i < 3; ++i) T.t[i] = a[4 + i]; return T; }
+  Transformation inverse() const;
+  Transformation operator*(const Transformation& rhs) const;
+};
+
+using Keypoint = std::array<double, 2>;
+using BearingVector = std::array<double, 3>;
+using GradientVector = std::array<double, 2>;
+using SeedState = std::array<double, 4>;  // inv-mu, sigma2, a, b (src/svo_common/include/svo/common/seed.h)
+
+enum class FeatureType : uint8_t {  // src/svo_common/include/svo/common/types.h:60-73
+  kEdgeletSeed = 0, kCornerSeed = 1, kMapPointSeed = 2, kEdgeletSeedConverged = 3, kCornerSeedConverged = 4,
+  kMapPointSeedConverged = 5, kEdgelet = 6, kCorner = 7, kMapPoint = 8, kFixedLandmark = 9, kOutlier = 10
+};
+inline bool isSeed(FeatureType t) { return static_cast<uint8_t>(t) < 6; }
+inline bool isMapPoint(FeatureType t) { return t == FeatureType::kMapPoint || t == FeatureType::kMapPointSeed || t == FeatureType::kMapPointSeedConverged; }
+
+struct Camera {  // vk::cameras::CameraGeometry<PinholeProjection<...>>
+  svo_camera model{};
+  int imageWidth() const { return model.width; }
+  int imageHeight() const { return model.height; }
+};
+using CameraPtr = std::shared_ptr<Camera>;
+
+namespace b200 { class GpuPyramid; }
+
+// svo::Frame reduced to the members the hot path reads / writes (src/svo_common/include/svo/common/frame.h:30-424)
+struct Frame {
+  using Ptr = std::shared_ptr<Frame>;
+  int id_ = 0;
+  CameraPtr cam_;
+  ImgPyr img_pyr_;
+  Transformation T_f_w_;     // frame (camera) from world
+  Transformation T_cam_imu_; // T_cam_imu(); T_imu_cam() is its inverse
+  size_t num_features_ = 0;
+  std::vector<Keypoint> px_vec_;
+  std::vector<BearingVector> f_vec_;
+  std::vector<GradientVector> grad_vec_;
+  std::vector<double> score_vec_;
+  std::vector<int> level_vec_;
+  std::vector<FeatureType> type_vec_;
+  // Distance of the feature's landmark / seed from this camera's centre, < 0 when the feature has neither
+  // (replaces the landmark_vec_ / seed_ref_vec_ pointer walk of sparse_img_align.cpp:282-293, done by the adapter).
+  std::vector<double> depth_vec_;
+  std::vector<SeedState> invmu_sigma2_a_b_vec_;
+  double seed_mu_range_ = 0.0;
+  mutable std::shared_ptr<b200::GpuPyramid> gpu_;  // device-resident copy of img_pyr_ (the analogue of the reference's FrameGpu)
+
+  const CameraPtr& cam() const { return cam_; }
+  Transformation T_imu_world() const { return T_cam_imu_.inverse() * T_f_w_; }
+  const Transformation& T_cam_imu() const { return T_cam_imu_; }
+  void clearFeatureStorage();
+};
+using FramePtr = std::shared_ptr<Frame>;
+
+struct FrameBundle {  // frame.h:426-543
+  using Ptr = std::shared_ptr<FrameBundle>;
+  std::vector<FramePtr> frames_;
+  size_t size() const { return frames_.size(); }
+  bool empty() const { return frames_.empty(); }
+  const FramePtr& at(size_t i) const { return frames_.at(i); }
+};
+
+namespace frame_utils {
+// src/svo_common/src/frame.cpp:372-386 — builds the pyramid on the GPU (svo_cuda_pyr_build), keeps it resident in *gpu and
+// mirrors the levels into `pyr` for host code that still reads them.
+void createImgPyramid(const Image& img_level_0, int n_levels, ImgPyr& pyr, std::shared_ptr<b200::GpuPyramid>* gpu = nullptr);
+}  // namespace frame_utils
+
+// ---- (b) SparseImgAlign ------------------------------------------------------------------------------------------------
+struct SparseImgAlignOptions {  // src/svo_img_align/include/svo/img_align/sparse_img_align_base.h:37-46
+  int max_level = 4;
+  int min_level = 1;
+  bool estimate_illumination_gain = false;
+  bool estimate_illumination_offset = false;
+  bool use_distortion_jacobian = false;
+  bool robustification = false;
+  double weight_scale = 10;
+};
+namespace solver {
+struct MiniLeastSquaresSolverOptions {  // src/vikit/vikit_solver/include/vikit/solver/mini_least_squares_solver.h:20-47
+  size_t max_iter = 15;
+  double eps = 0.0000000001;
+  bool verbose = false;
+};
+}  // namespace solver
+
+class SparseImgAlignBase {
+ public:
+  using Ptr = std::shared_ptr<SparseImgAlignBase>;
+  using SolverOptions = solver::MiniLeastSquaresSolverOptions;
+  SolverOptions solver_options_;
+  SparseImgAlignBase(SolverOptions optimization_options, SparseImgAlignOptions options)
+      : solver_options_(optimization_options), options_(options) {}
+  virtual ~SparseImgAlignBase() = default;
+  virtual size_t run(const FrameBundle::Ptr& ref_frames, const FrameBundle::Ptr& cur_frames) = 0;
+  static SolverOptions getDefaultSolverOptions();  // sparse_img_align_base.cpp:35-42
+  void setWeightedPrior(const Transformation& T_cur_ref_prior, double alpha_prior, double beta_prior, double lambda_rot,
+                        double lambda_trans, double lambda_alpha, double lambda_beta);
+  void reset();  // MiniLeastSquaresSolver::reset (mini_least_squares_solver.hpp:240-250)
+  inline void setMaxNumFeaturesToAlign(int num) { max_num_features_ = num; }
+  inline void setAlphaInitialValue(double alpha_init) { alpha_init_ = alpha_init; }
+  inline void setBetaInitialValue(double beta_init) { beta_init_ = beta_init; }
+  inline void setCompensation(const bool do_compensation) {
+    options_.estimate_illumination_gain = do_compensation;
+    options_.estimate_illumination_offset = do_compensation;
+  }
+  double getError() const { return chi2_; }
+  const std::array<double, 64>& getHessian() const { return H_; }  // row-major 8x8
+
+ protected:
+  SparseImgAlignOptions options_;
+  bool have_prior_ = false;
+  svo_align_prior prior_{};
+  double prior_lambda_rot_ = 0, prior_lambda_trans_ = 0, prior_lambda_alpha_ = 0, prior_lambda_beta_ = 0;
+  int max_num_features_ = -1;  // stored but unused by the CPU reference as well (sparse_img_align_base.h:102-105)
+  double alpha_init_ = 0.0, beta_init_ = 0.0;
+  double chi2_ = 0.0;
+  std::array<double, 64> H_{};
+};
+
+class SparseImgAlign : public SparseImgAlignBase {  // src/svo_img_align/include/svo/img_align/sparse_img_align.h:30-77
+ public:
+  using Ptr = std::shared_ptr<SparseImgAlign>;
+  SparseImgAlign(SolverOptions optimization_options, SparseImgAlignOptions options)
+      : SparseImgAlignBase(optimization_options, options) {}
+  // Returns the number of tracked features; writes T_f_w_ of every cur frame (sparse_img_align.cpp:34-113).
+  size_t run(const FrameBundle::Ptr& ref_frames, const FrameBundle::Ptr& cur_frames) override;
+};
+
+// ---- (c) feature alignment + Matcher ------------------------------------------------------------------------------------
+namespace feature_alignment {  // src/svo_direct/include/svo/direct/feature_alignment.h:23-43
+bool align1D(const Image& cur_img, const GradientVector& dir, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter,
+             const bool affine_est_offset, const bool affine_est_gain, Keypoint* cur_px_estimate, double* h_inv = nullptr);
+bool align2D(const Image& cur_img, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter,
+             const bool affine_est_offset, const bool affine_est_gain, Keypoint& cur_px_estimate, bool no_simd = false);
+}  // namespace feature_alignment
+
+struct FeatureWrapper {  // src/svo_common/include/svo/common/feature_wrapper.h:34-45 (the fields the matcher reads)
+  FeatureType type;
+  Keypoint px;
+  BearingVector f;
+  GradientVector grad;
+  int level;
+};
+
+class Matcher {  // src/svo_direct/include/svo/direct/matcher.h:28-140
+ public:
+  static const int kHalfPatchSize = 4;
+  static const int kPatchSize = 8;
+  struct Options {
+    bool align_1d = false;
+    int align_max_iter = 10;
+    double max_epi_length_optim = 2.0;
+    size_t max_epi_search_steps = 100;
+    bool subpix_refinement = true;
+    bool epi_search_edgelet_filtering = true;
+    bool scan_on_unit_sphere = true;
+    double epi_search_edgelet_max_angle = 0.7;
+    bool verbose = false;
+    bool use_affine_warp_ = true;
+    bool affine_est_offset_ = true;
+    bool affine_est_gain_ = false;
+    double max_patch_diff_ratio = 2.0;
+  } options_;
+  enum class MatchResult { kSuccess, kFailScore, kFailTriangulation, kFailVisibility, kFailWarp, kFailAlignment, kFailRange,
+                           kFailAngle, kFailCloseView, kFailLock, kFailTooFar };
+  std::array<double, 4> A_cur_ref_{};  // row-major 2x2
+  double epi_length_pyramid_ = 0;
+  double h_inv_ = 0;
+  int search_level_ = 0;
+  bool reject_ = false;
+  Keypoint px_cur_{};
+  BearingVector f_cur_{};
+
+  MatchResult findMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const FeatureWrapper& ref_ftr, const FloatType& ref_depth,
+                              Keypoint& px_cur);
+  MatchResult findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const FeatureWrapper& ref_ftr,
+                                      const double d_estimate_inv, const double d_min_inv, const double d_max_inv, double& depth);
+  MatchResult findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const Transformation& T_cur_ref,
+                                      const FeatureWrapper& ref_ftr, const double d_estimate_inv, const double d_min_inv,
+                                      const double d_max_inv, double& depth);
+  static std::string getResultString(const MatchResult& result);
+  svo_matcher_options cOptions() const;
+};
+
+// ---- (d) DepthFilter -----------------------------------------------------------------------------------------------------
+struct DepthFilterOptions {  // src/svo_direct/include/svo/direct/depth_filter.h:27-60
+  double seed_convergence_sigma2_thresh = 200.0;
+  double mappoint_convergence_sigma2_thresh = 500.0;
+  bool scan_epi_unit_sphere = false;
+  bool affine_est_offset = true;
+  bool affine_est_gain = false;
+};
+
+namespace depth_filter_utils {  // depth_filter.h:179-236
+bool updateSeed(const Frame& cur_frame, Frame& ref_frame, const size_t& seed_index, Matcher& matcher,
+                const FloatType sigma2_convergence_threshold, const bool check_visibility = true, const bool check_convergence = false,
+                const bool use_vogiatzis_update = true);
+bool updateFilterVogiatzis(const FloatType z, const FloatType tau2, const FloatType z_range, SeedState& seed);
+double computeTau(const Transformation& T_ref_cur, const BearingVector& f, const FloatType z, const FloatType px_error_angle);
+}  // namespace depth_filter_utils
+
+class DepthFilter {
+ public:
+  DepthFilterOptions options_;
+  explicit DepthFilter(const DepthFilterOptions& options);
+  // DepthFilter::updateSeeds (depth_filter.cpp:200-249, non-threaded branch): every seed of every ref frame against cur_frame,
+  // one batched launch; returns the number of successful updates.
+  size_t updateSeeds(const std::vector<FramePtr>& ref_frames_with_seeds, const FramePtr& cur_frame);
+  Matcher& getMatcher() { return matcher_; }
+
+ private:
+  Matcher matcher_;
+};
+
+// ---- (a) FAST detector -----------------------------------------------------------------------------------------------------
+struct Corner {  // src/svo_direct/include/svo/direct/feature_detection_types.h:17-29
+  int x, y, level;
+  float score, angle;
+  Corner(int _x, int _y, float _score, int _level, float _angle) : x(_x), y(_y), level(_level), score(_score), angle(_angle) {}
+};
+using Corners = std::vector<Corner>;
+
+struct DetectorOptions {  // feature_detection_types.h:49-84 (FAST-relevant subset)
+  size_t cell_size = 30;
+  int max_level = 2;
+  int min_level = 0;
+  int border = 8;
+  double threshold_primary = 10.0;
+};
+
+class OccupandyGrid2D {  // src/svo_common/include/svo/common/occupancy_grid_2d.h:10-110
+ public:
+  const int cell_size, n_cols, n_rows;
+  std::vector<uint8_t> occupancy_;
+  OccupandyGrid2D(int cell_size_, int n_cols_, int n_rows_)
+      : cell_size(cell_size_), n_cols(n_cols_), n_rows(n_rows_), occupancy_(size_t(n_cols_) * n_rows_, 0) {}
+  void reset() { std::fill(occupancy_.begin(), occupancy_.end(), 0); }
+  size_t size() const { return occupancy_.size(); }
+  size_t getCellIndex(int x, int y, int scale = 1) const { return size_t((scale * y) / cell_size) * n_cols + size_t((scale * x) / cell_size); }
+};
+
+namespace feature_detection_utils {
+// src/svo_direct/include/svo/direct/feature_detection_utils.h:43-50; `gpu` is the frame's device pyramid.
+void fastDetector(const b200::GpuPyramid& gpu, const int threshold, const int border, const size_t min_level, const size_t max_level,
+                  Corners& corners, OccupandyGrid2D& grid);
+}  // namespace feature_detection_utils
+
+class FastDetector {  // src/svo_direct/include/svo/direct/feature_detection.h:20-81
+ public:
+  DetectorOptions options_;
+  OccupandyGrid2D grid_;
+  FastDetector(const DetectorOptions& options, const CameraPtr& cam);
+  // AbstractDetector::detect(const FramePtr&) (feature_detection.cpp:40-50): appends corners to the frame's SoA arrays,
+  // computes unit bearing vectors, resets the grid.
+  void detect(const FramePtr& frame);
+  void resetGrid() { grid_.reset(); }
+};
+
+// ---- device plumbing --------------------------------------------------------------------------------------------------------
+namespace b200 {
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+// The calling thread's context on the current device (created on first use; throws b200::Error when no GPU is present).
+svo_cuda_ctx* context();
+class GpuPyramid {  // RAII owner of a one-frame svo_cuda_pyr
+ public:
+  GpuPyramid(int width, int height, int n_levels);
+  ~GpuPyramid();
+  GpuPyramid(const GpuPyramid&) = delete;
+  GpuPyramid& operator=(const GpuPyramid&) = delete;
+  svo_cuda_pyr* handle() const { return pyr_; }
+  int n_levels() const { return n_levels_; }
+  int width() const { return width_; }
+  int height() const { return height_; }
+ private:
+  svo_cuda_pyr* pyr_ = nullptr;
+  int width_, height_, n_levels_;
+};
+// Device pyramid of a frame: reuses frame.gpu_ or uploads frame.img_pyr_[0] and builds the levels.
+const GpuPyramid& ensureGpu(const Frame& frame);
+}  // namespace b200
+
+}  // namespace svo

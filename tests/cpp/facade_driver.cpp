@@ -1,0 +1,126 @@
+// Test driver for the C++ facades (svo_pro_universal_b200/host/svo_b200.h): reads one synthetic frame pair written by
+// tests/test_gpu_host_facade.py, runs the reference-shaped calls (createImgPyramid, FastDetector::detect,
+// SparseImgAlign::run, Matcher::findMatchDirect / findEpipolarMatchDirect, DepthFilter::updateSeeds) and writes the results
+// back as raw doubles. The Python test compares them with the oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "../../svo_pro_universal_b200/host/svo_b200.h"
+
+using namespace svo;
+
+template <class T>
+static std::vector<T> rd(std::ifstream& f, size_t n) {
+  std::vector<T> v(n);
+  f.read(reinterpret_cast<char*>(v.data()), sizeof(T) * n);
+  return v;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) { std::fprintf(stderr, "usage: facade_driver in.bin out.bin\n"); return 2; }
+  try {
+    std::ifstream in(argv[1], std::ios::binary);
+    const auto hdr = rd<int32_t>(in, 4);
+    const int W = hdr[0], H = hdr[1], n_levels = hdr[2], N = hdr[3];
+    Image ref0(H, W), cur0(H, W);
+    in.read(reinterpret_cast<char*>(ref0.data), size_t(W) * H);
+    in.read(reinterpret_cast<char*>(cur0.data), size_t(W) * H);
+    const auto camv = rd<double>(in, 8);
+    const auto cami = rd<int32_t>(in, 3);
+    const auto T_cam_imu = rd<double>(in, 7), T_ref = rd<double>(in, 7), T_cur_init = rd<double>(in, 7), T_cur_true = rd<double>(in, 7);
+    const auto px = rd<double>(in, 2 * N), fv = rd<double>(in, 3 * N), depth = rd<double>(in, N), grad = rd<double>(in, 2 * N),
+               guess = rd<double>(in, 2 * N);
+    const auto type = rd<int32_t>(in, N), level = rd<int32_t>(in, N);
+
+    auto cam = std::make_shared<Camera>();
+    cam->model = svo_camera{camv[0], camv[1], camv[2], camv[3], camv[4], camv[5], camv[6], camv[7], cami[0], cami[1], cami[2], 0};
+    auto mk = [&](const Image& img, const std::vector<double>& T_f_w, int id) {
+      auto f = std::make_shared<Frame>();
+      f->id_ = id;
+      f->cam_ = cam;
+      frame_utils::createImgPyramid(img, n_levels, f->img_pyr_, &f->gpu_);
+      f->T_f_w_ = Transformation::fromArray(T_f_w.data());
+      f->T_cam_imu_ = Transformation::fromArray(T_cam_imu.data());
+      return f;
+    };
+    FramePtr ref = mk(ref0, T_ref, 1), cur = mk(cur0, T_cur_init, 2);
+    std::vector<double> out;
+
+    // (a) FastDetector::detect on the ref frame
+    {
+      FastDetector det(DetectorOptions(), cam);
+      det.detect(ref);
+      out.push_back(double(ref->num_features_));
+      for (size_t i = 0; i < ref->num_features_; ++i) {
+        out.push_back(ref->px_vec_[i][0]); out.push_back(ref->px_vec_[i][1]); out.push_back(ref->score_vec_[i]); out.push_back(ref->level_vec_[i]);
+      }
+      double cs = 0;  // checksum of the pyramid mirrored back to the host
+      for (const Image& im : ref->img_pyr_) for (int y = 0; y < im.rows; ++y) for (int x = 0; x < im.cols; ++x) cs += im.data[y * im.step + x] * double((x + 3 * y) % 7 + 1);
+      out.push_back(cs);
+      ref->clearFeatureStorage();
+    }
+    // features of the test set
+    for (int i = 0; i < N; ++i) {
+      ref->px_vec_.push_back({px[2 * i], px[2 * i + 1]});
+      ref->f_vec_.push_back({fv[3 * i], fv[3 * i + 1], fv[3 * i + 2]});
+      ref->grad_vec_.push_back({grad[2 * i], grad[2 * i + 1]});
+      ref->score_vec_.push_back(0);
+      ref->level_vec_.push_back(level[i]);
+      ref->type_vec_.push_back(FeatureType(type[i]));
+      ref->depth_vec_.push_back(depth[i]);
+      ref->invmu_sigma2_a_b_vec_.push_back({0.25, (1 / 1.5) * (1 / 1.5) / 36.0, 10.0, 10.0});
+    }
+    ref->num_features_ = N;
+    ref->seed_mu_range_ = 1 / 1.5;
+
+    // (b) SparseImgAlign::run
+    {
+      SparseImgAlign align(SparseImgAlign::getDefaultSolverOptions(), SparseImgAlignOptions());
+      auto rb = std::make_shared<FrameBundle>(), cb = std::make_shared<FrameBundle>();
+      rb->frames_ = {ref}; cb->frames_ = {cur};
+      align.reset();
+      const size_t n = align.run(rb, cb);
+      out.push_back(double(n));
+      double T[7]; cur->T_f_w_.toArray(T);
+      for (double v : T) out.push_back(v);
+      out.push_back(align.getError());
+    }
+    // (c) Matcher with the true relative pose
+    cur->T_f_w_ = Transformation::fromArray(T_cur_true.data());
+    {
+      Matcher m;
+      for (int i = 0; i < N; ++i) {
+        FeatureWrapper fw{FeatureType(type[i]), ref->px_vec_[i], ref->f_vec_[i], ref->grad_vec_[i], level[i]};
+        Keypoint pc{guess[2 * i], guess[2 * i + 1]};
+        const auto r = m.findMatchDirect(*ref, *cur, fw, depth[i], pc);
+        out.push_back(double(int(r))); out.push_back(pc[0]); out.push_back(pc[1]);
+        double d = 0;
+        const auto r2 = m.findEpipolarMatchDirect(*ref, *cur, fw, 1.0 / depth[i], 1.3 / depth[i], 0.7 / depth[i], d);
+        out.push_back(double(int(r2))); out.push_back(d); out.push_back(m.px_cur_[0]); out.push_back(m.px_cur_[1]);
+      }
+    }
+    // (d) DepthFilter::updateSeeds: every feature becomes a seed of its kind
+    {
+      for (int i = 0; i < N; ++i) ref->type_vec_[i] = (FeatureType(type[i]) == FeatureType::kEdgelet) ? FeatureType::kEdgeletSeed : FeatureType::kCornerSeed;
+      DepthFilterOptions o;
+      o.scan_epi_unit_sphere = true;
+      DepthFilter df(o);
+      const size_t n = df.updateSeeds({ref}, cur);
+      out.push_back(double(n));
+      for (int i = 0; i < N; ++i) {
+        for (double v : ref->invmu_sigma2_a_b_vec_[i]) out.push_back(v);
+        out.push_back(double(int(ref->type_vec_[i])));
+      }
+    }
+    std::ofstream o(argv[2], std::ios::binary);
+    o.write(reinterpret_cast<const char*>(out.data()), sizeof(double) * out.size());
+    std::printf("facade_driver ok: %zu doubles\n", out.size());
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "facade_driver: %s\n", e.what());
+    return 1;
+  }
+}

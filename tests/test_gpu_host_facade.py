@@ -1,0 +1,103 @@
+"""GPU test of the C++ host facades (svo_pro_universal_b200/host/svo_b200.h): the reference-shaped classes
+svo::SparseImgAlign, svo::Matcher, svo::DepthFilter, svo::FastDetector and frame_utils::createImgPyramid, driven by
+tests/cpp/facade_driver.cpp, give the oracle's results on a synthetic frame pair."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import oracle_align, pose_diff
+from svo_pro_universal_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _T_f_w(T_cam_imu, T_imu_world):
+    return synth.se3_mul(T_cam_imu, T_imu_world)
+
+
+def test_cpp_facades_match_oracle(orc, tmp_path):
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "svo_pro_universal_b200", "host")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    d = synth.make_align_pair(3, n_features=120)
+    N = len(d["px"])
+    rng = np.random.default_rng(9)
+    level = rng.integers(0, 3, N).astype(np.int32)
+    ftype = np.where(rng.uniform(size=N) < 0.25, synth.K_EDGELET, synth.K_CORNER).astype(np.int32)
+    grad = rng.normal(size=(N, 2)); grad /= np.linalg.norm(grad, axis=1)[:, None]
+    X = d["f"] * d["depth"][:, None]
+    R, t = synth.se3_to_Rt(d["T_cur_ref_gt"])
+    guess = synth.cam_project(d["cam"], X @ R.T + t) + rng.uniform(-1.5, 1.5, (N, 2))
+    T_ref = _T_f_w(d["T_cam_imu"], d["T_imu_world_ref"])
+    T_cur_init = _T_f_w(d["T_cam_imu"], d["T_imu_world_cur_init"])
+    T_cur_true = synth.se3_mul(d["T_cur_ref_gt"], T_ref)
+    cam = d["cam"]
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        np.array([752, 480, 5, N], np.int32).tofile(f)
+        d["ref_img"].tofile(f); d["cur_img"].tofile(f)
+        np.array([cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")], np.float64).tofile(f)
+        np.array([cam["width"], cam["height"], cam["distortion"]], np.int32).tofile(f)
+        for T in (d["T_cam_imu"], T_ref, T_cur_init, T_cur_true):
+            np.asarray(T, np.float64).tofile(f)
+        for a in (d["px"], d["f"], d["depth"], grad, guess):
+            np.ascontiguousarray(a, np.float64).tofile(f)
+        ftype.tofile(f); level.tofile(f)
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "facade_driver"), str(fin), str(fout)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(fout, np.float64)
+    p = 0
+
+    # (a) FastDetector::detect == oracle FastDetector::detect (sets compared: std::sort is unstable on ties)
+    n_det = int(out[p]); p += 1
+    det = out[p:p + 4 * n_det].reshape(n_det, 4); p += 4 * n_det
+    cs = out[p]; p += 1
+    px_o, sc_o, lv_o = np.zeros((416, 2)), np.zeros(416), np.zeros(416, np.int32)
+    n_o = orc.lib().orc_fast_detect_features(d["ref_img"].ctypes.data_as(orc.u8p), 752, 480, 5, -1, 10.0, 8, 0, 2, 30, None, 416,
+                                             px_o.ctypes.data_as(orc.f64p), sc_o.ctypes.data_as(orc.f64p), lv_o.ctypes.data_as(orc.i32p))
+    assert n_det == n_o > 100
+    exp = sorted(zip(px_o[:n_o, 0], px_o[:n_o, 1], sc_o[:n_o], lv_o[:n_o]))
+    assert sorted(map(tuple, det)) == [tuple(map(float, e)) for e in exp]
+    assert (np.diff(det[:, 2]) <= 0).all()  # sorted by score, best first
+    pyr = orc.create_img_pyramid(d["ref_img"], 5)
+    cs_o = sum(float((im.astype(np.float64) * ((np.arange(im.shape[1])[None, :] + 3 * np.arange(im.shape[0])[:, None]) % 7 + 1)).sum()) for im in pyr)
+    assert cs == cs_o  # host mirror of the GPU pyramid is bit-exact
+
+    # (b) SparseImgAlign::run writes cur->T_f_w_
+    n_tracked = int(out[p]); p += 1
+    T_f_w = out[p:p + 7]; p += 7
+    chi2 = out[p]; p += 1
+    o = oracle_align(orc, d, orc.default_align_options())
+    assert n_tracked == o.n_tracked
+    dq, dt = pose_diff(T_f_w, o.T_f_w[0])
+    assert dq < 1e-4 and dt < 1e-4
+    np.testing.assert_allclose(chi2, o.chi2, rtol=1e-4)
+
+    # (c) Matcher::findMatchDirect / findEpipolarMatchDirect per feature
+    m = out[p:p + 7 * N].reshape(N, 7); p += 7 * N
+    keep = []
+    rf = orc.make_frame(pyr, cam, keep=keep)
+    cf = orc.make_frame(orc.create_img_pyramid(d["cur_img"], 5), cam, keep=keep)
+    oft = orc.make_features(d["px"], d["f"], grad, ftype, level)
+    e1 = orc.find_match_direct_batch(rf, cf, d["T_cur_ref_gt"], oft, d["depth"], guess, orc.default_matcher_options())
+    inv = 1.0 / d["depth"]
+    e2 = orc.find_epipolar_match_direct_batch(rf, cf, d["T_cur_ref_gt"], oft, np.stack([inv, 1.3 * inv, 0.7 * inv], 1), orc.default_matcher_options())
+    assert np.array_equal(m[:, 0].astype(int), e1["result"]) and np.array_equal(m[:, 3].astype(int), e2["result"])
+    ok1, ok2 = e1["result"] == 0, e2["result"] == 0
+    assert ok1.sum() > N // 2 and ok2.sum() > N // 4
+    assert np.abs(m[ok1, 1:3] - e1["px_cur"][ok1]).max() < 1e-3
+    assert np.abs(m[ok2, 5:7] - e2["px_cur"][ok2]).max() < 1e-3
+    np.testing.assert_allclose(m[ok2, 4], e2["depth"][ok2], rtol=1e-4)
+
+    # (d) DepthFilter::updateSeeds
+    n_succ = int(out[p]); p += 1
+    sd = out[p:p + 5 * N].reshape(N, 5); p += 5 * N
+    assert p == len(out)
+    types = np.where(ftype == synth.K_EDGELET, synth.K_EDGELET_SEED, synth.K_CORNER_SEED).astype(np.uint8)
+    st = np.tile(np.array([0.25, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (N, 1))
+    n_o, _, _ = orc.update_seeds(rf, [cf], d["T_cur_ref_gt"][None], oft, types, st, 1 / 1.5, orc.default_matcher_options())
+    assert n_succ == n_o > N // 4
+    np.testing.assert_allclose(sd[:, :4], st, rtol=1e-4)
+    assert np.array_equal(sd[:, 4].astype(np.uint8), types)

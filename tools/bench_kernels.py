@@ -1,0 +1,188 @@
+"""Per-path measurements for SURVEY §8 rows (a), (c), (d): CUDA-event timings, algorithmic-byte rooflines and the oracle's
+CPU throughput on the same host, one JSON line per path (-> profiles/). The headline metric lives in bench.py."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from svo_pro_universal_b200 import capi, synth  # noqa: E402
+from oracle import orc  # noqa: E402
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+NT = os.cpu_count() or 1
+
+
+def timed(fn, stream, warmup=3, reps=10):
+    for _ in range(warmup):
+        fn()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record(stream); fn(); b.record(stream)
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in ev]))
+
+
+def main():
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = capi.Context(0)
+    ctx.set_stream(stream.cuda_stream)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = []
+
+    # ---- (a) BASELINE configs[1]: FAST pyramid detection + grid NMS on 1024 frames ----
+    B = 1024
+    uniq = np.stack([synth.make_image(200 + s) for s in range(16)])
+    imgs = t(uniq[np.arange(B) % 16])
+    pyr = capi.Pyramid(ctx, B, 752, 480, 5)
+    pyr.upload(imgs)
+    opt = capi.detector_options()
+    corners = torch.zeros(B * 416 * 20, dtype=torch.uint8, device=dev)
+    ms_pyr = timed(lambda: pyr.build(), stream)
+    ms_det = timed(lambda: capi.fast_detect(ctx, pyr, opt, corners_out=corners), stream)
+    ms_all = timed(lambda: capi.fast_detect(ctx, pyr, opt, corners_out=corners, fused_pyramid=True), stream)
+    t0 = time.perf_counter(); n_cpu = 0
+    while time.perf_counter() - t0 < 5.0:
+        orc.fast_detector(uniq[n_cpu % 16]); n_cpu += 1
+    cpu_fps_1t = n_cpu / (time.perf_counter() - t0)
+    bytes_frame = 487466
+    out.append({"path": "a: pyramid + FAST-10 + 3x3 nonmax + grid argmax", "config": "1024 synthetic 752x480 frames, thr 10, border 8, cell 30, levels 0-2",
+                "frames_per_s": B / (ms_all * 1e-3), "ms": {"pyramid": ms_pyr, "detect": ms_det, "pyramid+detect": ms_all},
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": bytes_frame, "achieved_GBs": bytes_frame * B / (ms_all * 1e-3) / 1e9,
+                             "peak_GBs": PEAK, "frac": bytes_frame * B / (ms_all * 1e-3) / 1e9 / PEAK,
+                             "pyramid_only_frac": (360960 + 119850) * B / (ms_pyr * 1e-3) / 1e9 / PEAK},
+                "cpu_baseline": {"frames_per_s_single_thread": cpu_fps_1t, "kind": "port (oracle; FAST rows pinned to the reference's own code)"}})
+    del pyr, imgs, corners
+
+    # ---- (c) BASELINE configs[2]: align2D / align1D via findMatchDirect, 2000 features x 256 pairs; epipolar search ----
+    NP, NF, NU = 256, 2000, 8
+    sets = [synth.make_match_set(300 + s, n_features=NF) for s in range(NU)]
+    ref = capi.Pyramid(ctx, NU, 752, 480, 5); cur = capi.Pyramid(ctx, NU, 752, 480, 5)
+    ref.upload(np.stack([m["ref_img"] for m in sets])); cur.upload(np.stack([m["cur_img"] for m in sets]))
+    ref.build(); cur.build()
+    cam = capi.Camera.from_dict(sets[0]["cam"])
+    pid = np.arange(NP) % NU
+    cat = lambda k: np.concatenate([sets[i][k] for i in pid])
+    ft = capi.make_features(cat("px"), cat("f"), cat("grad"), cat("type"), cat("level"))
+    M = len(ft)
+    fidx = np.concatenate([np.full(len(sets[i]["px"]), i, np.int32) for i in pid])
+    T = np.stack([m["T_cur_ref"] for m in sets])
+    d_ft = torch.from_numpy(ft.view(np.uint8)).to(dev)
+    d_idx, d_T, d_depth, d_guess = t(fidx), t(T), t(cat("depth")), t(cat("px_guess"))
+    d_out = torch.zeros(M * capi.MATCH_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    mopt = capi.matcher_options()
+    ms_fmd = timed(lambda: capi.find_match_direct(ctx, ref, cur, cam, cam, d_T, d_ft, d_depth, d_guess, mopt, ref_frame_idx=d_idx,
+                                                  cur_frame_idx=d_idx, T_idx=d_idx, out=d_out), stream)
+    res = d_out.cpu().numpy().view(capi.MATCH_OUT_DTYPE)
+    rng = np.random.default_rng(1)
+    inv = 1.0 / cat("depth")
+    est = inv * rng.uniform(0.7, 1.4, M)
+    spread = rng.uniform(0.1, 0.8, M) * inv
+    d_dinv = t(np.stack([est, est + spread, np.maximum(est - spread, 1e-8)], 1))
+    ms_epi = timed(lambda: capi.find_epipolar_match_direct(ctx, ref, cur, cam, cam, d_T, d_ft, d_dinv, mopt, ref_frame_idx=d_idx,
+                                                           cur_frame_idx=d_idx, T_idx=d_idx, out=d_out), stream, reps=5)
+    res_e = d_out.cpu().numpy().view(capi.MATCH_OUT_DTYPE)
+    keep = []
+    m0 = sets[0]
+    rf = orc.make_frame(orc.create_img_pyramid(m0["ref_img"], 5), m0["cam"], keep=keep)
+    cf = orc.make_frame(orc.create_img_pyramid(m0["cur_img"], 5), m0["cam"], keep=keep)
+    oft = orc.make_features(m0["px"], m0["f"], m0["grad"], m0["type"], m0["level"])
+    n0 = len(m0["px"])
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 4.0:
+        orc.find_match_direct_batch(rf, cf, m0["T_cur_ref"], oft, m0["depth"], m0["px_guess"], orc.default_matcher_options(), n_threads=NT); reps += 1
+    cpu_fmd = n0 * reps / (time.perf_counter() - t0)
+    d3 = np.stack([est[:n0], est[:n0] + spread[:n0], np.maximum(est[:n0] - spread[:n0], 1e-8)], 1)
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 4.0:
+        orc.find_epipolar_match_direct_batch(rf, cf, m0["T_cur_ref"], oft, d3, orc.default_matcher_options(), n_threads=NT); reps += 1
+    cpu_epi = n0 * reps / (time.perf_counter() - t0)
+    out.append({"path": "c: findMatchDirect (affine warp + align2D / align1D)", "config": f"{M} features = {NP} pairs x ~{NF} ({NU} unique pairs tiled)",
+                "features_per_s": M / (ms_fmd * 1e-3), "ms": ms_fmd, "success_frac": float((res["result"] == 0).mean()),
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_feature": 333, "achieved_GBs": 333 * M / (ms_fmd * 1e-3) / 1e9, "peak_GBs": PEAK,
+                             "frac": 333 * M / (ms_fmd * 1e-3) / 1e9 / PEAK, "note": "gather/latency bound: L1/L2 re-reads dominate, see DESIGN.md"},
+                "cpu_baseline": {"features_per_s": cpu_fmd, "cores": NT, "kind": "port"}})
+    out.append({"path": "c: findEpipolarMatchDirect (ZMSSD scan + subpixel + triangulation)", "config": f"{M} features, inverse-depth spread 10-80 %",
+                "features_per_s": M / (ms_epi * 1e-3), "ms": ms_epi, "success_frac": float((res_e["result"] == 0).mean()),
+                "mean_epi_length_px": float(res_e["epi_length_pyramid"].mean()),
+                "cpu_baseline": {"features_per_s": cpu_epi, "cores": NT, "kind": "port"}})
+    del ref, cur
+
+    # ---- (d) BASELINE configs[3]: 50k seeds x 64 observations ----
+    S, O = 50000, 64
+    rng = np.random.default_rng(2)
+    state0 = np.tile(np.array([0.25, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (S, 1))
+    z = 0.25 + rng.normal(size=S) * 0.01
+    d_state, d_z, d_tau2, d_mu = t(state0), t(z), t(np.full(S, 1e-4)), t(np.full(S, 1 / 1.5))
+    d_ok = torch.zeros(S, dtype=torch.uint8, device=dev)
+
+    def vog64():
+        for _ in range(O):
+            capi.update_filter_vogiatzis(ctx, d_z, d_tau2, d_mu, d_state, d_ok)
+    ms_v = timed(vog64, stream, warmup=1, reps=5)
+    st = state0.copy(); tau2 = np.full(S, 1e-4); mu = np.full(S, 1 / 1.5)
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 3.0:
+        orc.lib().orc_update_filter_vogiatzis_batch(S, z.ctypes.data_as(orc.f64p), tau2.ctypes.data_as(orc.f64p), mu.ctypes.data_as(orc.f64p),
+                                                    st.ctypes.data_as(orc.f64p), None, NT); reps += 1
+    cpu_v = S * reps / (time.perf_counter() - t0)
+    out.append({"path": "d: updateFilterVogiatzis (pure filter update)", "config": f"{S} seeds x {O} ordered updates ({O} launches)",
+                "updates_per_s": S * O / (ms_v * 1e-3), "ms": ms_v,
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_update": 80, "achieved_GBs": 80 * S * O / (ms_v * 1e-3) / 1e9, "peak_GBs": PEAK,
+                             "frac": 80 * S * O / (ms_v * 1e-3) / 1e9 / PEAK, "note": "4 MB working set stays in L2; launch-latency bound at this size"},
+                "cpu_baseline": {"updates_per_s": cpu_v, "cores": NT, "kind": "port"}})
+    # full updateSeed chain: seeds spread over 125 reference keyframes x 400 seeds, 64 observation frames each (16 unique sequences)
+    NSEQ_U, NOBS_U = 4, 16
+    seqs = [synth.make_seed_sequence(400 + s, n_seeds=400, n_obs=NOBS_U) for s in range(NSEQ_U)]
+    per = min(len(q["px"]) for q in seqs)
+    NSEQ = S // per
+    ref = capi.Pyramid(ctx, NSEQ_U, 752, 480, 5); cur = capi.Pyramid(ctx, NSEQ_U * NOBS_U, 752, 480, 5)
+    ref.upload(np.stack([q["ref_img"] for q in seqs])); cur.upload(np.stack([im for q in seqs for im in q["cur_imgs"]]))
+    ref.build(); cur.build()
+    sid = np.arange(NSEQ) % NSEQ_U
+    catq = lambda k: np.concatenate([seqs[i][k][:per] for i in sid])
+    ftq = capi.make_features(catq("px"), catq("f"), catq("grad"), catq("type").astype(np.int32), catq("level"))
+    Sq = len(ftq)
+    ref_idx = np.repeat(sid, per).astype(np.int32)
+    obs = np.arange(O) % NOBS_U
+    obs_frame = (ref_idx[None, :] * NOBS_U + obs[:, None]).astype(np.int32)
+    Tq = np.concatenate([q["T_cur_ref"] for q in seqs])
+    types0 = catq("type").astype(np.uint8); stq0 = catq("state")
+    d_ftq = torch.from_numpy(ftq.view(np.uint8)).to(dev)
+    d_types, d_st = t(types0), t(stq0)
+    d_mu2, d_ref_idx, d_obs, d_Tq = t(np.full(Sq, seqs[0]["mu_range"])), t(ref_idx), t(obs_frame), t(Tq)
+    dopt = capi.depth_filter_options()
+
+    def seeds():
+        d_types.copy_(t(types0)); d_st.copy_(t(stq0))
+        return capi.update_seeds(ctx, ref, cur, cam, cam, d_ftq, d_types, d_st, d_mu2, d_obs, d_obs, d_Tq, mopt, dopt, ref_frame_idx=d_ref_idx,
+                                 want_match_results=False)
+    ms_s = timed(seeds, stream, warmup=1, reps=3)
+    n_succ, _ = seeds(); torch.cuda.synchronize()
+    q0 = seqs[0]
+    keep2 = []
+    rf = orc.make_frame(orc.create_img_pyramid(q0["ref_img"], 5), q0["cam"], keep=keep2)
+    cfs = [orc.make_frame(orc.create_img_pyramid(im, 5), q0["cam"], keep=keep2) for im in q0["cur_imgs"]]
+    oft = orc.make_features(q0["px"][:per], q0["f"][:per], q0["grad"][:per], q0["type"][:per].astype(np.int32), q0["level"][:per])
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 5.0:
+        ty = q0["type"][:per].copy(); stt = q0["state"][:per].copy()
+        orc.update_seeds(rf, cfs, q0["T_cur_ref"], oft, ty, stt, q0["mu_range"], orc.default_matcher_options(), n_threads=NT); reps += 1
+    cpu_s = per * NOBS_U * reps / (time.perf_counter() - t0)
+    out.append({"path": "d: updateSeed chain (visibility gate + epipolar match + tau + Vogiatzis + convergence)",
+                "config": f"{Sq} seeds x {O} ordered observations in ONE launch ({NSEQ_U} unique keyframes x {NOBS_U} unique observation frames, tiled)",
+                "seed_observations_per_s": Sq * O / (ms_s * 1e-3), "ms": ms_s, "success_frac": float(n_succ.item()) / (Sq * O),
+                "cpu_baseline": {"seed_observations_per_s": cpu_s, "cores": NT, "kind": "port"}})
+    for o in out:
+        print(json.dumps(o))
+
+
+if __name__ == "__main__":
+    main()
