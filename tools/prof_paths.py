@@ -1,0 +1,75 @@
+"""Small driver for ncu captures: every hot-path kernel launched 3 times at one-wave-or-more sizes (no CPU oracle work).
+    ncu --set full -k regex:<kernel> -s 1 -c 1 ... python tools/prof_paths.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from svo_pro_universal_b200 import capi, synth, batch  # noqa: E402
+
+REPS = 3
+ctx = capi.Context(0)
+
+# (a)+(b): B pairs, pyramid + FAST + sparse alignment
+B = int(os.environ.get("PROF_PAIRS", "1184"))
+uniq = [synth.make_align_pair(5000 + s) for s in range(8)]
+pk = batch.tile_batch(batch.pack_align_batch(uniq, max_features=180), B)
+ref = capi.Pyramid(ctx, B, 752, 480, 5); cur = capi.Pyramid(ctx, B, 752, 480, 5)
+ref.upload(pk["ref_imgs"]); cur.upload(pk["cur_imgs"]); ref.build()
+cam = capi.Camera.from_dict(uniq[0]["cam"])
+for _ in range(REPS):
+    cur.build()
+    res = capi.sparse_align(ctx, [ref], [cur], [cam], pk["T_cam_imu"], pk["T_imu_world_ref"], pk["T_imu_world_cur"], pk["n_features"],
+                            pk["px"], pk["f"], pk["depth"], pk["eligible"], capi.sparse_align_options())
+for _ in range(REPS):
+    capi.fast_detect(ctx, cur, capi.detector_options())
+for _ in range(REPS):
+    capi.fast_detect(ctx, cur, capi.detector_options(), fused_pyramid=True)
+print("align iters", res["iters"][:2].tolist(), "n", res["n_tracked"][:2])
+del ref, cur
+
+# (c): matcher paths
+NP, NF, NU = 64, 2000, 4
+sets = [synth.make_match_set(300 + s, n_features=NF) for s in range(NU)]
+ref = capi.Pyramid(ctx, NU, 752, 480, 5); cur = capi.Pyramid(ctx, NU, 752, 480, 5)
+ref.upload(np.stack([m["ref_img"] for m in sets])); cur.upload(np.stack([m["cur_img"] for m in sets]))
+ref.build(); cur.build()
+pid = np.arange(NP) % NU
+cat = lambda k: np.concatenate([sets[i][k] for i in pid])
+ft = capi.make_features(cat("px"), cat("f"), cat("grad"), cat("type"), cat("level"))
+fidx = np.concatenate([np.full(len(sets[i]["px"]), i, np.int32) for i in pid])
+T = np.stack([m["T_cur_ref"] for m in sets])
+mopt = capi.matcher_options()
+for _ in range(REPS):
+    r = capi.find_match_direct(ctx, ref, cur, cam, cam, T, ft, cat("depth"), cat("px_guess"), mopt, ref_frame_idx=fidx, cur_frame_idx=fidx, T_idx=fidx)
+print("findMatchDirect success", float((r["result"] == 0).mean()))
+rng = np.random.default_rng(1)
+inv = 1.0 / cat("depth"); est = inv * rng.uniform(0.7, 1.4, len(ft)); spread = rng.uniform(0.1, 0.8, len(ft)) * inv
+dinv = np.stack([est, est + spread, np.maximum(est - spread, 1e-8)], 1)
+for _ in range(REPS):
+    r = capi.find_epipolar_match_direct(ctx, ref, cur, cam, cam, T, ft, dinv, mopt, ref_frame_idx=fidx, cur_frame_idx=fidx, T_idx=fidx)
+print("epipolar success", float((r["result"] == 0).mean()))
+del ref, cur
+
+# (d): depth filter
+S = 50000
+state = np.tile(np.array([0.25, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (S, 1))
+z = 0.25 + rng.normal(size=S) * 0.01
+for _ in range(REPS):
+    capi.update_filter_vogiatzis(ctx, z, np.full(S, 1e-4), np.full(S, 1 / 1.5), state)
+q = synth.make_seed_sequence(400, n_seeds=400, n_obs=8)
+n = len(q["px"])
+ref = capi.Pyramid(ctx, 1, 752, 480, 5); cur = capi.Pyramid(ctx, 8, 752, 480, 5)
+ref.upload(q["ref_img"][None]); cur.upload(np.stack(q["cur_imgs"])); ref.build(); cur.build()
+rep = 32
+ftq = capi.make_features(*(np.concatenate([q[k]] * rep) for k in ("px", "f", "grad")), np.concatenate([q["type"].astype(np.int32)] * rep),
+                         np.concatenate([q["level"]] * rep))
+obs = np.tile(np.arange(8, dtype=np.int32)[:, None], (1, n * rep))
+for _ in range(REPS):
+    ty = np.concatenate([q["type"].astype(np.uint8)] * rep); st = np.concatenate([q["state"]] * rep)
+    ns, _ = capi.update_seeds(ctx, ref, cur, cam, cam, ftq, ty, st, np.full(n * rep, q["mu_range"]), obs, obs, q["T_cur_ref"], mopt,
+                              capi.depth_filter_options(), want_match_results=False)
+print("update_seeds successes", ns)
