@@ -10,56 +10,86 @@
 //   margin = max over the 16 arcs of ARC contiguous pixels of max(min_arc d_i, -max_arc d_i) - 1
 // the pixel is a corner at barrier b iff margin >= b, and fast_corner_score_10 = max(b, margin).
 //
-// Kernel layout: a CTA owns a 64x16 interior tile; the u8 tile with a 4-pixel halo is staged in shared memory
-// with aligned 32-bit loads; phase A writes scores for the interior + 1 ring; phase B does the 3x3 non-max,
-// border / occupancy tests and a 64-bit atomicMax per grid cell whose key reproduces the reference's visiting
-// order (score desc, then level asc, y asc, x asc — `score > corners[k].score` is strict).
+// Kernel layout (one launch for all levels of all frames): a CTA owns a 128x16 interior tile of one level; the u8 tile
+// with a 4-pixel halo is staged in shared memory with one 128-bit load per thread. Three compacting stages keep every
+// lane busy on the rare pixels that need work:
+//   1. compass quick-reject on ALL pixels, 4 pixels per thread in 16x2 packed SIMD (VIMNMX.S16x2 / VIADD.16x2): an arc
+//      of >= 9 circle pixels always contains two adjacent compass points, i.e. one of {N,S} and one of {E,W};
+//      survivors are pushed on a shared-memory candidate list;
+//   2. exact margin on the candidates only: bright (I_i - p) and dark (p - I_i) margins ride in the two 16-bit halves
+//      of one register, so the 16 arc minima and their maximum cost 56 packed min/max (VIMNMX3.U16x2);
+//      corners (margin >= threshold) write their score into a tile score map and go on a corner list;
+//   3. 3x3 non-max on the corner list (neighbours outside the tile are scored on demand from the halo), border /
+//      occupancy tests and a 64-bit atomicMax per grid cell whose key reproduces the reference's visiting order
+//      (score desc, then level asc, y asc, x asc — `score > corners[k].score` is strict).
 #include "common.cuh"
 
 namespace {
 
-constexpr int kTW = 64, kTH = 16, kHalo = 4;
-constexpr int kSW = kTW + 2 * kHalo;          // 72 staged columns
-constexpr int kSH = kTH + 2 * kHalo;          // 24 staged rows
-constexpr int kScW = kTW + 2, kScH = kTH + 2; // score region (interior + 1 ring)
-constexpr int kScPitch = kScW + 2;            // 68
+constexpr int kTW = 128, kTH = 16, kHalo = 4;
+constexpr int kPadL = 16;                      // staged columns start at x0 - 16 so every 128-bit load is aligned
+constexpr int kSPitch = kTW + 2 * kPadL;       // 160 staged bytes per row
+constexpr int kSRows = kTH + 2 * kHalo;        // 24 staged rows
+constexpr int kThreadsFast = 256;
 
+// Circle offsets in the order of fast_10_score.cpp:3158-3175 (pixel[0] = (0,3), clockwise through (3,0), (0,-3), (-3,0)).
+#define SVO_FAST_CIRCLE(p, pitch, X)                                                                               \
+  X(0, (p)[3 * (pitch)])       X(1, (p)[3 * (pitch) + 1])   X(2, (p)[2 * (pitch) + 2])   X(3, (p)[(pitch) + 3])     \
+  X(4, (p)[3])                 X(5, (p)[-(pitch) + 3])      X(6, (p)[-2 * (pitch) + 2])  X(7, (p)[-3 * (pitch) + 1]) \
+  X(8, (p)[-3 * (pitch)])      X(9, (p)[-3 * (pitch) - 1])  X(10, (p)[-2 * (pitch) - 2]) X(11, (p)[-(pitch) - 3])   \
+  X(12, (p)[-3])               X(13, (p)[(pitch) - 3])      X(14, (p)[2 * (pitch) - 2])  X(15, (p)[3 * (pitch) - 1])
+
+// margin = max over the 16 arcs of ARC contiguous circle pixels of max(min_arc(I_i - p), min_arc(p - I_i)) - 1.
+// Packed: v_i = (I_i - p + 256) | (p - I_i + 256) << 16 — one IMAD per circle pixel (I_i * 0xFFFF0001 + K; both halves
+// stay in [1, 511], so no borrow crosses the halves) — then unsigned 16x2 min over each arc and max over the arcs.
 template <int ARC>
 SVO_D int fastMargin(const uint8_t* p, int pitch) {
-  const int c = p[0];
-  int d[16];
-  d[0] = p[3 * pitch] - c;       d[1] = p[3 * pitch + 1] - c;   d[2] = p[2 * pitch + 2] - c;   d[3] = p[pitch + 3] - c;
-  d[4] = p[3] - c;               d[5] = p[-pitch + 3] - c;      d[6] = p[-2 * pitch + 2] - c;  d[7] = p[-3 * pitch + 1] - c;
-  d[8] = p[-3 * pitch] - c;      d[9] = p[-3 * pitch - 1] - c;  d[10] = p[-2 * pitch - 2] - c; d[11] = p[-pitch - 3] - c;
-  d[12] = p[-3] - c;             d[13] = p[pitch - 3] - c;      d[14] = p[2 * pitch - 2] - c;  d[15] = p[3 * pitch - 1] - c;
-  // sliding min / max over ARC contiguous entries, log-step
-  int mn2[16], mx2[16];
+  const unsigned c = p[0];
+  const unsigned K = (256u - c) | ((c + 256u) << 16);
+  unsigned v[16];
+#define SVO_X(i, e) v[i] = (unsigned)(e) * 0xFFFF0001u + K;
+  SVO_FAST_CIRCLE(p, pitch, SVO_X)
+#undef SVO_X
+  unsigned arc[16];
+  if (ARC == 10) {
+    unsigned m2[16], m4[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
-  int mn4[16], mx4[16];
+    for (int k = 0; k < 16; ++k) m2[k] = __vminu2(v[k], v[(k + 1) & 15]);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-  // bright = max over arcs of the arc minimum, dark = min over arcs of the arc maximum; margin = max(bright, -dark) - 1.
-  // NB: nvcc 12.9 / sm_100a folds a negated operand into VIMNMX3 incorrectly (max(a, max(b, -c)) returns wrong values,
-  // see tools/mm_test.cu), so the negation is kept out of every min/max chain and hidden behind an asm barrier.
-  int bright = -256, dark = 256;
+    for (int k = 0; k < 16; ++k) m4[k] = __vminu2(m2[k], m2[(k + 2) & 15]);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int mn8 = min(mn4[k], mn4[(k + 4) & 15]);
-    const int mx8 = max(mx4[k], mx4[(k + 4) & 15]);
-    int mn, mx;
-    if (ARC == 10) { mn = min(mn8, mn2[(k + 8) & 15]); mx = max(mx8, mx2[(k + 8) & 15]); }
-    else           { mn = min(mn8, d[(k + 8) & 15]);   mx = max(mx8, d[(k + 8) & 15]); }
-    bright = max(bright, mn);
-    dark = min(dark, mx);
+    for (int k = 0; k < 16; ++k) arc[k] = __vimin3_u16x2(m4[k], m4[(k + 4) & 15], m2[(k + 8) & 15]);
+  } else {
+    unsigned m3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(v[k], v[(k + 1) & 15], v[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) arc[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
   }
-  int ndark = -dark;
-  asm volatile("" : "+r"(ndark));
-  return max(bright, ndark) - 1;
+  unsigned b0 = __vimax3_u16x2(arc[0], arc[1], arc[2]), b1 = __vimax3_u16x2(arc[3], arc[4], arc[5]);
+  unsigned b2 = __vimax3_u16x2(arc[6], arc[7], arc[8]), b3 = __vimax3_u16x2(arc[9], arc[10], arc[11]);
+  unsigned b4 = __vimax3_u16x2(arc[12], arc[13], arc[14]);
+  b0 = __vimax3_u16x2(b0, b1, b2);
+  b3 = __vimax3_u16x2(b3, b4, arc[15]);
+  b0 = __vmaxu2(b0, b3);
+  return (int)max(b0 & 0xFFFFu, b0 >> 16) - 257;
 }
 
+// Quick reject for two horizontally adjacent pixels held as 16x2 halves: non-zero half <=> that pixel may be a corner.
+// bright needs (N > p+t or S > p+t) and (E > p+t or W > p+t)  <=>  min(max(N,S), max(E,W)) > p + t; dark is the mirror image.
+SVO_D unsigned quickPair(unsigned C, unsigned N, unsigned S, unsigned E, unsigned W, unsigned T, unsigned nT) {
+  const unsigned qb = __vmins2(__vmaxs2(N, S), __vmaxs2(E, W));
+  const unsigned qd = __vmaxs2(__vmins2(N, S), __vmins2(E, W));
+  const unsigned hi = __vadd2(C, T), lo = __vadd2(C, nT);
+  return (__vmaxs2(qb, hi) ^ hi) | (__vmins2(qd, lo) ^ lo);
+}
+SVO_D unsigned lo16x2(unsigned w) { return __byte_perm(w, 0u, 0x4140); }  // bytes 0,1 -> 16-bit halves
+SVO_D unsigned hi16x2(unsigned w) { return __byte_perm(w, 0u, 0x4342); }  // bytes 2,3 -> 16-bit halves
+
 struct FastParams {
-  int level, threshold, border, cell_size, n_cols, n_cells, first;
+  int min_level, max_level, threshold, border, cell_size, n_cols, n_cells, first;
+  int tile_base[SVO_MAX_LEVELS + 1];  // first tile index of every level inside blockIdx.x
+  int tiles_x[SVO_MAX_LEVELS];
   unsigned long long* keys;        // [count][n_cells] or nullptr
   const uint8_t* occupancy;        // [count][n_cells] or nullptr
   short* score_map;                // dense debug maps for one frame (level coords) or nullptr
@@ -67,66 +97,122 @@ struct FastParams {
 };
 
 template <int ARC>
-__global__ void __launch_bounds__(256) fast_level_kernel(PyrView v, FastParams P) {
-  __shared__ __align__(16) uint8_t s_img[kSH * kSW];
-  __shared__ short s_score[kScH * kScPitch];
-  const int L = P.level;
-  const int cols = v.cols[L], rows = v.rows[L], pitch = v.pitch[L];
-  const int frame_local = blockIdx.z;
-  const uint8_t* img = v.level(P.first + frame_local, L);
-  const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+__global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, FastParams P) {
+  __shared__ __align__(16) uint8_t s_img[kSRows * kSPitch];
+  __shared__ __align__(16) short s_score[kTH * kTW];
+  __shared__ unsigned short s_cand[kTH * kTW];
+  __shared__ unsigned short s_corner[kTH * kTW];
+  __shared__ int s_ncand, s_ncorner;
   const int tid = threadIdx.x;
+  int L = P.min_level;
+  while (L < P.max_level && (int)blockIdx.x >= P.tile_base[L + 1]) ++L;
+  const int tile = blockIdx.x - P.tile_base[L];
+  const int ty = tile / P.tiles_x[L], tx = tile - ty * P.tiles_x[L];
+  const int cols = v.cols[L], rows = v.rows[L], pitch = v.pitch[L];
+  const int frame_local = blockIdx.y;
+  const uint8_t* img = v.level(P.first + frame_local, L);
+  const int x0 = tx * kTW, y0 = ty * kTH;
+  const int thr = P.threshold;
 
-  // stage tile + halo: words of 4 px, aligned because x0 - 4 is a multiple of 4 and rows are 16-B aligned
-  for (int i = tid; i < kSH * (kSW / 4); i += 256) {
-    const int r = i / (kSW / 4), cw = i - r * (kSW / 4);
-    const int gy = y0 - kHalo + r, gx = x0 - kHalo + cw * 4;
-    unsigned w = 0;
-    if (gy >= 0 && gy < rows && gx >= 0 && gx < pitch) w = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)gy * pitch + gx));
-    *reinterpret_cast<unsigned*>(&s_img[r * kSW + cw * 4]) = w;
+  // stage tile + halo: one aligned 128-bit load per thread (x0 - 16 and the row pitch are multiples of 16)
+  if (tid < kSRows * (kSPitch / 16)) {
+    const int r = tid / (kSPitch / 16), q = tid - r * (kSPitch / 16);
+    const int gy = y0 - kHalo + r, gx = x0 - kPadL + q * 16;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (gy >= 0 && gy < rows && gx >= 0 && gx < pitch) w = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx));
+    *reinterpret_cast<uint4*>(&s_img[r * kSPitch + q * 16]) = w;
   }
+  reinterpret_cast<uint4*>(s_score)[tid] = make_uint4(0, 0, 0, 0);  // 256 threads x 16 B = the whole score tile
+  if (tid == 0) { s_ncand = 0; s_ncorner = 0; }
   __syncthreads();
 
-  // phase A: scores on interior + 1 ring
-  for (int i = tid; i < kScH * kScW; i += 256) {
-    const int r = i / kScW, c = i - r * kScW;
-    const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-    short sc = 0;
-    if (gx >= 3 && gy >= 3 && gx < cols - 3 && gy < rows - 3) {
-      const uint8_t* p = &s_img[(r + kHalo - 1) * kSW + (c + kHalo - 1)];
-      // cheap necessary condition: an arc of >= 9 contiguous circle pixels contains 2 adjacent compass points
-      const int cpx = p[0];
-      const int hi = cpx + P.threshold, lo = cpx - P.threshold;
-      const int n = p[-3 * kSW], s = p[3 * kSW], e = p[3], w = p[-3];
-      const bool bright = ((n > hi) + (e > hi) + (s > hi) + (w > hi)) >= 2;
-      const bool dark = ((n < lo) + (e < lo) + (s < lo) + (w < lo)) >= 2;
-      if (bright || dark) {
-        const int m = fastMargin<ARC>(p, kSW);
-        if (m >= P.threshold) sc = (short)m;  // score = max(threshold, margin) = margin; threshold >= 1 so 0 means "no corner"
+  // stage 1: quick reject, one warp per tile row, 4 pixels per lane
+  {
+    const unsigned T = (unsigned)thr * 0x10001u, nT = ((unsigned)(-thr) & 0xFFFFu) * 0x10001u;
+    const int g = tid & 31;
+    const int gx0 = x0 + 4 * g;
+    const int jlo = max(3 - gx0, 0), jhi = min(cols - 3 - gx0, 4);
+    const unsigned colmask = jhi > jlo ? (((1u << jhi) - 1u) & ~((1u << jlo) - 1u)) : 0u;
+#pragma unroll
+    for (int rr = 0; rr < kTH / 8; ++rr) {
+      const int r = (tid >> 5) + rr * 8;
+      const int gy = y0 + r;
+      const uint8_t* base = s_img + (r + kHalo) * kSPitch + kPadL + 4 * g;
+      const unsigned wc = *reinterpret_cast<const unsigned*>(base);
+      const unsigned wm = *reinterpret_cast<const unsigned*>(base - 4), wp = *reinterpret_cast<const unsigned*>(base + 4);
+      const unsigned wn = *reinterpret_cast<const unsigned*>(base - 3 * kSPitch), ws = *reinterpret_cast<const unsigned*>(base + 3 * kSPitch);
+      const unsigned we = __funnelshift_r(wc, wp, 24);  // pixels x+3 .. x+6
+      const unsigned ww = __funnelshift_r(wm, wc, 8);   // pixels x-3 .. x
+      const unsigned e01 = quickPair(lo16x2(wc), lo16x2(wn), lo16x2(ws), lo16x2(we), lo16x2(ww), T, nT);
+      const unsigned e23 = quickPair(hi16x2(wc), hi16x2(wn), hi16x2(ws), hi16x2(we), hi16x2(ww), T, nT);
+      unsigned f = ((e01 & 0xFFFFu) ? 1u : 0u) | ((e01 >> 16) ? 2u : 0u) | ((e23 & 0xFFFFu) ? 4u : 0u) | ((e23 >> 16) ? 8u : 0u);
+      f &= (gy >= 3 && gy < rows - 3) ? colmask : 0u;
+      if (f) {
+        int at = atomicAdd(&s_ncand, __popc(f));
+        while (f) {
+          const int j = __ffs(f) - 1;
+          f &= f - 1;
+          s_cand[at++] = (unsigned short)((r << 7) | (4 * g + j));
+        }
       }
     }
-    s_score[r * kScPitch + c] = sc;
   }
   __syncthreads();
 
-  // phase B: non-max, border, cell arg-max
-  const int scale = 1 << L;
-  for (int i = tid; i < kTH * kTW; i += 256) {
-    const int r = i / kTW, c = i - r * kTW;
-    const int gy = y0 + r, gx = x0 + c;
-    if (gx >= cols || gy >= rows) continue;
-    const short* sp = &s_score[(r + 1) * kScPitch + (c + 1)];
-    const int sc = sp[0];
-    if (P.score_map) P.score_map[(size_t)gy * cols + gx] = (short)sc;
-    bool keep = sc > 0;
-    if (keep) {
-      keep = !(sp[-kScPitch - 1] >= sc || sp[-kScPitch] >= sc || sp[-kScPitch + 1] >= sc || sp[-1] >= sc || sp[1] >= sc ||
-               sp[kScPitch - 1] >= sc || sp[kScPitch] >= sc || sp[kScPitch + 1] >= sc);
+  // stage 2: exact margin on the candidates
+  const int ncand = s_ncand;
+  for (int i = tid; i < ncand; i += kThreadsFast) {
+    const int idx = s_cand[i];
+    const int r = idx >> 7, c = idx & 127;
+    const int m = fastMargin<ARC>(&s_img[(r + kHalo) * kSPitch + kPadL + c], kSPitch);
+    if (m >= thr) {  // score = max(threshold, margin) = margin; threshold >= 1 so 0 means "no corner"
+      s_score[idx] = (short)m;
+      s_corner[atomicAdd(&s_ncorner, 1)] = (unsigned short)idx;
     }
-    if (P.nonmax_map) P.nonmax_map[(size_t)gy * cols + gx] = keep ? 1 : 0;
-    if (!keep || !P.keys) continue;
+  }
+  __syncthreads();
+
+  if (P.score_map || P.nonmax_map) {  // dense debug maps of this tile (parity tests of the raw stages)
+    for (int i = tid; i < kTH * kTW; i += kThreadsFast) {
+      const int gy = y0 + (i >> 7), gx = x0 + (i & 127);
+      if (gx >= cols || gy >= rows) continue;
+      if (P.score_map) P.score_map[(size_t)gy * cols + gx] = s_score[i];
+      if (P.nonmax_map) P.nonmax_map[(size_t)gy * cols + gx] = 0;
+    }
+    __syncthreads();
+  }
+
+  // stage 3: 3x3 non-max on the corners, border, cell arg-max
+  const int ncorner = s_ncorner;
+  for (int i = tid; i < ncorner; i += kThreadsFast) {
+    const int idx = s_corner[i];
+    const int r = idx >> 7, c = idx & 127;
+    const int gy = y0 + r, gx = x0 + c;
+    const int sc = s_score[idx];
+    bool keep = true;
+#pragma unroll 1
+    for (int n = 0; n < 9 && keep; ++n) {
+      if (n == 4) continue;
+      const int dr = n / 3 - 1, dc = n - (n / 3) * 3 - 1;
+      const int rr = r + dr, cc = c + dc;
+      int nsc;
+      if ((unsigned)rr < (unsigned)kTH && (unsigned)cc < (unsigned)kTW) {
+        nsc = s_score[rr * kTW + cc];
+      } else {  // neighbour belongs to another tile: score it from the halo
+        const int ny = gy + dr, nx = gx + dc;
+        nsc = 0;
+        if (nx >= 3 && ny >= 3 && nx < cols - 3 && ny < rows - 3) {
+          const int m = fastMargin<ARC>(&s_img[(rr + kHalo) * kSPitch + kPadL + cc], kSPitch);
+          if (m >= thr) nsc = m;
+        }
+      }
+      if (nsc >= sc) keep = false;
+    }
+    if (!keep) continue;
+    if (P.nonmax_map) P.nonmax_map[(size_t)gy * cols + gx] = 1;
+    if (!P.keys) continue;
     if (gx < P.border || gy < P.border || gx >= cols - P.border || gy >= rows - P.border) continue;
-    const int k = ((gy * scale) / P.cell_size) * P.n_cols + (gx * scale) / P.cell_size;
+    const int k = ((gy << L) / P.cell_size) * P.n_cols + (gx << L) / P.cell_size;
     if (P.occupancy && P.occupancy[(size_t)frame_local * P.n_cells + k]) continue;
     const unsigned order = ((unsigned)L << 28) | ((unsigned)gy << 14) | (unsigned)gx;
     const unsigned long long key = ((unsigned long long)(unsigned)sc << 32) | (unsigned long long)(0xFFFFFFFFu - order);
@@ -155,11 +241,26 @@ __global__ void fast_keys_decode_kernel(const unsigned long long* keys, size_t n
   out[i] = c;
 }
 
-int launchLevel(svo_cuda_ctx* ctx, const PyrView& v, const FastParams& P, int arc, int count) {
-  dim3 grid((v.cols[P.level] + kTW - 1) / kTW, (v.rows[P.level] + kTH - 1) / kTH, count);
-  if (arc == 9) fast_level_kernel<9><<<grid, 256, 0, ctx->stream>>>(v, P);
-  else fast_level_kernel<10><<<grid, 256, 0, ctx->stream>>>(v, P);
-  SVO_LAUNCH_CHECK(ctx);
+int launchLevels(svo_cuda_ctx* ctx, const PyrView& v, FastParams& P, int arc, int count) {
+  int n_tiles = 0;
+  for (int L = 0; L <= SVO_MAX_LEVELS; ++L) P.tile_base[L] = 0;
+  for (int L = P.min_level; L <= P.max_level; ++L) {
+    P.tile_base[L] = n_tiles;
+    P.tiles_x[L] = (v.cols[L] + kTW - 1) / kTW;
+    n_tiles += P.tiles_x[L] * ((v.rows[L] + kTH - 1) / kTH);
+    P.tile_base[L + 1] = n_tiles;
+  }
+  for (int f0 = 0; f0 < count; f0 += 65535) {  // grid.y limit
+    FastParams Q = P;
+    const int n = min(65535, count - f0);
+    Q.first = P.first + f0;
+    if (Q.keys) Q.keys += (size_t)f0 * P.n_cells;
+    if (Q.occupancy) Q.occupancy += (size_t)f0 * P.n_cells;
+    dim3 grid(n_tiles, n, 1);
+    if (arc == 9) fast_level_kernel<9><<<grid, kThreadsFast, 0, ctx->stream>>>(v, Q);
+    else fast_level_kernel<10><<<grid, kThreadsFast, 0, ctx->stream>>>(v, Q);
+    SVO_LAUNCH_CHECK(ctx);
+  }
   return SVO_OK;
 }
 
@@ -187,14 +288,12 @@ static int fastDetectImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first,
   fast_keys_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys, n, opt->threshold);
   SVO_LAUNCH_CHECK(ctx);
   const PyrView v = makeView(pyr);
-  for (int L = opt->min_level; L <= opt->max_level; ++L) {
-    FastParams P;
-    P.level = L; P.threshold = opt->threshold; P.border = opt->border; P.cell_size = opt->cell_size;
-    P.n_cols = n_cols; P.n_cells = n_cells; P.first = first;
-    P.keys = keys; P.occupancy = d_occ; P.score_map = nullptr; P.nonmax_map = nullptr;
-    const int rc = launchLevel(ctx, v, P, arc, count);
-    if (rc != SVO_OK) return rc;
-  }
+  FastParams P;
+  P.min_level = opt->min_level; P.max_level = opt->max_level; P.threshold = opt->threshold; P.border = opt->border;
+  P.cell_size = opt->cell_size; P.n_cols = n_cols; P.n_cells = n_cells; P.first = first;
+  P.keys = keys; P.occupancy = d_occ; P.score_map = nullptr; P.nonmax_map = nullptr;
+  const int rc = launchLevels(ctx, v, P, arc, count);
+  if (rc != SVO_OK) return rc;
   fast_keys_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys, n, opt->threshold, d_out);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -226,9 +325,9 @@ int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fra
   uint8_t* d_nm = st.out(nonmax_map, n);
   if (st.failed()) return st.finish();
   FastParams P;
-  P.level = level; P.threshold = threshold; P.border = 0; P.cell_size = 1; P.n_cols = 1; P.n_cells = 1; P.first = frame;
-  P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
-  const int rc = launchLevel(ctx, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
+  P.min_level = level; P.max_level = level; P.threshold = threshold; P.border = 0; P.cell_size = 1; P.n_cols = 1; P.n_cells = 1;
+  P.first = frame; P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
+  const int rc = launchLevels(ctx, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
   if (rc != SVO_OK) return rc;
   return st.finish();
 }
