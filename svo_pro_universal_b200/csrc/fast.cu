@@ -10,10 +10,10 @@
 //   margin = max over the 16 arcs of ARC contiguous pixels of max(min_arc d_i, -max_arc d_i) - 1
 // the pixel is a corner at barrier b iff margin >= b, and fast_corner_score_10 = max(b, margin).
 //
-// Kernel layout (one launch for all levels of all frames): a CTA owns a 128x16 interior tile of one level; the u8 tile
-// with a 4-pixel halo is staged in shared memory with one 128-bit load per thread. Three compacting stages keep every
+// Kernel layout (one launch for all levels of all frames): a CTA owns a 128x32 interior tile of one level; the u8 tile
+// with a 4-pixel halo is staged in shared memory with 128-bit loads. Three compacting stages keep every
 // lane busy on the rare pixels that need work:
-//   1. compass quick-reject on ALL pixels, 4 pixels per thread in 16x2 packed SIMD (VIMNMX.S16x2 / VIADD.16x2): an arc
+//   1. compass quick-reject on ALL pixels, 4 pixels per thread with byte SIMD (VABSDIFF4.U8 + carry compares): an arc
 //      of >= 9 circle pixels always contains two adjacent compass points, i.e. one of {N,S} and one of {E,W};
 //      survivors are pushed on a shared-memory candidate list;
 //   2. exact margin on the candidates only: bright (I_i - p) and dark (p - I_i) margins ride in the two 16-bit halves
@@ -26,10 +26,10 @@
 
 namespace {
 
-constexpr int kTW = 128, kTH = 16, kHalo = 4;
+constexpr int kTW = 128, kTH = 32, kHalo = 4;
 constexpr int kPadL = 16;                      // staged columns start at x0 - 16 so every 128-bit load is aligned
 constexpr int kSPitch = kTW + 2 * kPadL;       // 160 staged bytes per row
-constexpr int kSRows = kTH + 2 * kHalo;        // 24 staged rows
+constexpr int kSRows = kTH + 2 * kHalo;        // 40 staged rows
 constexpr int kThreadsFast = 256;
 
 // Circle offsets in the order of fast_10_score.cpp:3158-3175 (pixel[0] = (0,3), clockwise through (3,0), (0,-3), (-3,0)).
@@ -75,21 +75,36 @@ SVO_D int fastMargin(const uint8_t* p, int pitch) {
   return (int)max(b0 & 0xFFFFu, b0 >> 16) - 257;
 }
 
-// Quick reject for two horizontally adjacent pixels held as 16x2 halves: non-zero half <=> that pixel may be a corner.
-// bright needs (N > p+t or S > p+t) and (E > p+t or W > p+t)  <=>  min(max(N,S), max(E,W)) > p + t; dark is the mirror image.
-SVO_D unsigned quickPair(unsigned C, unsigned N, unsigned S, unsigned E, unsigned W, unsigned T, unsigned nT) {
-  const unsigned qb = __vmins2(__vmaxs2(N, S), __vmaxs2(E, W));
-  const unsigned qd = __vmaxs2(__vmins2(N, S), __vmins2(E, W));
-  const unsigned hi = __vadd2(C, T), lo = __vadd2(C, nT);
-  return (__vmaxs2(qb, hi) ^ hi) | (__vmins2(qd, lo) ^ lo);
+// Quick reject for 4 horizontally adjacent pixels (one byte each). An arc of >= 9 contiguous circle pixels contains two
+// adjacent compass points — one of {N,S} and one of {E,W} — that differ from the centre by more than t in the same
+// direction; the test below drops the "same direction" part (still a necessary condition) so that it runs on absolute
+// differences: 4 x VABSDIFF4.U8 + per-byte "x > t" by carry (t < 128: ((x & 0x7f) + (127 - t)) | x has bit 7 set).
+// Returns 0x80 in every byte whose pixel may be a corner.
+SVO_D unsigned quick4(unsigned C, unsigned N, unsigned S, unsigned E, unsigned W, unsigned K) {
+  const unsigned aN = __vabsdiffu4(N, C), aS = __vabsdiffu4(S, C), aE = __vabsdiffu4(E, C), aW = __vabsdiffu4(W, C);
+  const unsigned ns = ((aN & 0x7F7F7F7Fu) + K) | aN | ((aS & 0x7F7F7F7Fu) + K) | aS;
+  const unsigned ew = ((aE & 0x7F7F7F7Fu) + K) | aE | ((aW & 0x7F7F7F7Fu) + K) | aW;
+  return ns & ew & 0x80808080u;
 }
-SVO_D unsigned lo16x2(unsigned w) { return __byte_perm(w, 0u, 0x4140); }  // bytes 0,1 -> 16-bit halves
-SVO_D unsigned hi16x2(unsigned w) { return __byte_perm(w, 0u, 0x4342); }  // bytes 2,3 -> 16-bit halves
+// Any threshold (t up to 254): the same test with the carry computed in 16-bit lanes (even and odd bytes separately).
+SVO_D unsigned gt16(unsigned x, unsigned K2) {  // 0x80 per byte where byte > t, K2 = (255 - t) * 0x10001
+  const unsigned e = ((x & 0x00FF00FFu) + K2) >> 1, o = (((x >> 8) & 0x00FF00FFu) + K2) << 7;
+  return (e & 0x00800080u) | (o & 0x80008000u);
+}
+SVO_D unsigned quick4Wide(unsigned C, unsigned N, unsigned S, unsigned E, unsigned W, unsigned K2) {
+  const unsigned aN = __vabsdiffu4(N, C), aS = __vabsdiffu4(S, C), aE = __vabsdiffu4(E, C), aW = __vabsdiffu4(W, C);
+  return (gt16(aN, K2) | gt16(aS, K2)) & (gt16(aE, K2) | gt16(aW, K2));
+}
+
+// floor(x / d) for x * d < 2^32 as one multiply-high; magic = 0 stands for d == 1.
+inline unsigned divMagic(int d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned)d + 1ull); }
+SVO_D int divFast(int x, unsigned magic) { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
 
 struct FastParams {
   int min_level, max_level, threshold, border, cell_size, n_cols, n_cells, first;
   int tile_base[SVO_MAX_LEVELS + 1];  // first tile index of every level inside blockIdx.x
   int tiles_x[SVO_MAX_LEVELS];
+  unsigned tiles_x_magic[SVO_MAX_LEVELS], cell_magic;
   unsigned long long* keys;        // [count][n_cells] or nullptr
   const uint8_t* occupancy;        // [count][n_cells] or nullptr
   short* score_map;                // dense debug maps for one frame (level coords) or nullptr
@@ -107,32 +122,33 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
   int L = P.min_level;
   while (L < P.max_level && (int)blockIdx.x >= P.tile_base[L + 1]) ++L;
   const int tile = blockIdx.x - P.tile_base[L];
-  const int ty = tile / P.tiles_x[L], tx = tile - ty * P.tiles_x[L];
+  const int ty = divFast(tile, P.tiles_x_magic[L]), tx = tile - ty * P.tiles_x[L];
   const int cols = v.cols[L], rows = v.rows[L], pitch = v.pitch[L];
   const int frame_local = blockIdx.y;
   const uint8_t* img = v.level(P.first + frame_local, L);
   const int x0 = tx * kTW, y0 = ty * kTH;
   const int thr = P.threshold;
 
-  // stage tile + halo: one aligned 128-bit load per thread (x0 - 16 and the row pitch are multiples of 16)
-  if (tid < kSRows * (kSPitch / 16)) {
-    const int r = tid / (kSPitch / 16), q = tid - r * (kSPitch / 16);
+  // stage tile + halo with aligned 128-bit loads (x0 - 16 and the row pitch are multiples of 16)
+  for (int i = tid; i < kSRows * (kSPitch / 16); i += kThreadsFast) {
+    const int r = i / (kSPitch / 16), q = i - r * (kSPitch / 16);
     const int gy = y0 - kHalo + r, gx = x0 - kPadL + q * 16;
     uint4 w = make_uint4(0, 0, 0, 0);
     if (gy >= 0 && gy < rows && gx >= 0 && gx < pitch) w = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx));
     *reinterpret_cast<uint4*>(&s_img[r * kSPitch + q * 16]) = w;
   }
-  reinterpret_cast<uint4*>(s_score)[tid] = make_uint4(0, 0, 0, 0);  // 256 threads x 16 B = the whole score tile
+  for (int i = tid; i < kTH * kTW * 2 / 16; i += kThreadsFast) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) { s_ncand = 0; s_ncorner = 0; }
   __syncthreads();
 
   // stage 1: quick reject, one warp per tile row, 4 pixels per lane
   {
-    const unsigned T = (unsigned)thr * 0x10001u, nT = ((unsigned)(-thr) & 0xFFFFu) * 0x10001u;
     const int g = tid & 31;
     const int gx0 = x0 + 4 * g;
-    const int jlo = max(3 - gx0, 0), jhi = min(cols - 3 - gx0, 4);
-    const unsigned colmask = jhi > jlo ? (((1u << jhi) - 1u) & ~((1u << jlo) - 1u)) : 0u;
+    const int jlo = max(3 - gx0, 0), jhi = min(cols - 3 - gx0, 4);  // valid centres: 3 <= x < cols - 3
+    unsigned colmask = 0u;
+    if (jhi > jlo) colmask = (jhi >= 4 ? 0x80808080u : ((1u << (8 * jhi)) - 1u)) & ~((1u << (8 * jlo)) - 1u);
+    const unsigned K = (unsigned)(127 - thr) * 0x01010101u, K2 = (unsigned)(255 - thr) * 0x00010001u;
 #pragma unroll
     for (int rr = 0; rr < kTH / 8; ++rr) {
       const int r = (tid >> 5) + rr * 8;
@@ -143,17 +159,16 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
       const unsigned wn = *reinterpret_cast<const unsigned*>(base - 3 * kSPitch), ws = *reinterpret_cast<const unsigned*>(base + 3 * kSPitch);
       const unsigned we = __funnelshift_r(wc, wp, 24);  // pixels x+3 .. x+6
       const unsigned ww = __funnelshift_r(wm, wc, 8);   // pixels x-3 .. x
-      const unsigned e01 = quickPair(lo16x2(wc), lo16x2(wn), lo16x2(ws), lo16x2(we), lo16x2(ww), T, nT);
-      const unsigned e23 = quickPair(hi16x2(wc), hi16x2(wn), hi16x2(ws), hi16x2(we), hi16x2(ww), T, nT);
-      unsigned f = ((e01 & 0xFFFFu) ? 1u : 0u) | ((e01 >> 16) ? 2u : 0u) | ((e23 & 0xFFFFu) ? 4u : 0u) | ((e23 >> 16) ? 8u : 0u);
+      unsigned f = thr < 128 ? quick4(wc, wn, ws, we, ww, K) : quick4Wide(wc, wn, ws, we, ww, K2);
       f &= (gy >= 3 && gy < rows - 3) ? colmask : 0u;
       if (f) {
         int at = atomicAdd(&s_ncand, __popc(f));
-        while (f) {
-          const int j = __ffs(f) - 1;
+        const int id0 = (r << 7) | (4 * g);
+        do {
+          const int b = __ffs(f) - 1;  // bit 8j+7
           f &= f - 1;
-          s_cand[at++] = (unsigned short)((r << 7) | (4 * g + j));
-        }
+          s_cand[at++] = (unsigned short)(id0 + (b >> 3));
+        } while (f);
       }
     }
   }
@@ -190,29 +205,39 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
     const int gy = y0 + r, gx = x0 + c;
     const int sc = s_score[idx];
     bool keep = true;
+    if (r > 0 && r < kTH - 1 && c > 0 && c < kTW - 1) {  // all 8 neighbours inside the tile
+      const short* sp = &s_score[idx];
+      keep = !(sp[-kTW - 1] >= sc || sp[-kTW] >= sc || sp[-kTW + 1] >= sc || sp[-1] >= sc || sp[1] >= sc ||
+               sp[kTW - 1] >= sc || sp[kTW] >= sc || sp[kTW + 1] >= sc);
+    } else {  // tile edge: in-tile neighbours first, then (rarely) score the neighbours of other tiles from the halo
 #pragma unroll 1
-    for (int n = 0; n < 9 && keep; ++n) {
-      if (n == 4) continue;
-      const int dr = n / 3 - 1, dc = n - (n / 3) * 3 - 1;
-      const int rr = r + dr, cc = c + dc;
-      int nsc;
-      if ((unsigned)rr < (unsigned)kTH && (unsigned)cc < (unsigned)kTW) {
-        nsc = s_score[rr * kTW + cc];
-      } else {  // neighbour belongs to another tile: score it from the halo
-        const int ny = gy + dr, nx = gx + dc;
-        nsc = 0;
-        if (nx >= 3 && ny >= 3 && nx < cols - 3 && ny < rows - 3) {
-          const int m = fastMargin<ARC>(&s_img[(rr + kHalo) * kSPitch + kPadL + cc], kSPitch);
-          if (m >= thr) nsc = m;
+      for (int pass = 0; pass < 2 && keep; ++pass) {
+#pragma unroll 1
+        for (int n = 0; n < 9 && keep; ++n) {
+          if (n == 4) continue;
+          const int dr = n / 3 - 1, dc = n - (n / 3) * 3 - 1;
+          const int rr = r + dr, cc = c + dc;
+          const bool inside = (unsigned)rr < (unsigned)kTH && (unsigned)cc < (unsigned)kTW;
+          if (inside != (pass == 0)) continue;
+          int nsc = 0;
+          if (inside) {
+            nsc = s_score[rr * kTW + cc];
+          } else {
+            const int ny = gy + dr, nx = gx + dc;
+            if (nx >= 3 && ny >= 3 && nx < cols - 3 && ny < rows - 3) {
+              const int m = fastMargin<ARC>(&s_img[(rr + kHalo) * kSPitch + kPadL + cc], kSPitch);
+              if (m >= thr) nsc = m;
+            }
+          }
+          if (nsc >= sc) keep = false;
         }
       }
-      if (nsc >= sc) keep = false;
     }
     if (!keep) continue;
     if (P.nonmax_map) P.nonmax_map[(size_t)gy * cols + gx] = 1;
     if (!P.keys) continue;
     if (gx < P.border || gy < P.border || gx >= cols - P.border || gy >= rows - P.border) continue;
-    const int k = ((gy << L) / P.cell_size) * P.n_cols + (gx << L) / P.cell_size;
+    const int k = divFast(gy << L, P.cell_magic) * P.n_cols + divFast(gx << L, P.cell_magic);
     if (P.occupancy && P.occupancy[(size_t)frame_local * P.n_cells + k]) continue;
     const unsigned order = ((unsigned)L << 28) | ((unsigned)gy << 14) | (unsigned)gx;
     const unsigned long long key = ((unsigned long long)(unsigned)sc << 32) | (unsigned long long)(0xFFFFFFFFu - order);
@@ -244,9 +269,11 @@ __global__ void fast_keys_decode_kernel(const unsigned long long* keys, size_t n
 int launchLevels(svo_cuda_ctx* ctx, const PyrView& v, FastParams& P, int arc, int count) {
   int n_tiles = 0;
   for (int L = 0; L <= SVO_MAX_LEVELS; ++L) P.tile_base[L] = 0;
+  P.cell_magic = divMagic(P.cell_size);
   for (int L = P.min_level; L <= P.max_level; ++L) {
     P.tile_base[L] = n_tiles;
     P.tiles_x[L] = (v.cols[L] + kTW - 1) / kTW;
+    P.tiles_x_magic[L] = divMagic(P.tiles_x[L]);
     n_tiles += P.tiles_x[L] * ((v.rows[L] + kTH - 1) / kTH);
     P.tile_base[L + 1] = n_tiles;
   }

@@ -80,7 +80,7 @@ def test_fast_stages_match_oracle_random(ctx, orc):
         else:
             img = rng.integers(0, 256, (h, w)).astype(np.uint8)
         p = _gpu_pyr(ctx, img, 1)
-        for thr in (1, 7, 30, 120):
+        for thr in (1, 7, 30, 120, 127, 128, 200, 254):  # >= 128 takes the wide-compare quick-reject
             xy = orc.fast_detect(img, thr, 10)
             sc = orc.fast_score10(img, xy, thr)
             nm_idx = orc.fast_nonmax3x3(xy, sc)

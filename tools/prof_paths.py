@@ -24,12 +24,16 @@ for _ in range(REPS):
     cur.build()
     res = capi.sparse_align(ctx, [ref], [cur], [cam], pk["T_cam_imu"], pk["T_imu_world_ref"], pk["T_imu_world_cur"], pk["n_features"],
                             pk["px"], pk["f"], pk["depth"], pk["eligible"], capi.sparse_align_options())
-for _ in range(REPS):
-    capi.fast_detect(ctx, cur, capi.detector_options())
+print("align iters", res["iters"][:2].tolist(), "n", res["n_tracked"][:2])
+del ref
+# (a) detector on BASELINE configs[1]-shaped frames (the images bench_kernels.py times)
+uimg = np.stack([synth.make_image(200 + s) for s in range(16)])
+cur.upload(uimg[np.arange(B) % 16])
 for _ in range(REPS):
     capi.fast_detect(ctx, cur, capi.detector_options(), fused_pyramid=True)
-print("align iters", res["iters"][:2].tolist(), "n", res["n_tracked"][:2])
-del ref, cur
+for _ in range(REPS):
+    capi.fast_detect(ctx, cur, capi.detector_options())
+del cur
 
 # (c): matcher paths
 NP, NF, NU = 64, 2000, 4
