@@ -204,33 +204,24 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
     const int r = idx >> 7, c = idx & 127;
     const int gy = y0 + r, gx = x0 + c;
     const int sc = s_score[idx];
+    const bool edge = !(r > 0 && r < kTH - 1 && c > 0 && c < kTW - 1);
     bool keep = true;
-    if (r > 0 && r < kTH - 1 && c > 0 && c < kTW - 1) {  // all 8 neighbours inside the tile
-      const short* sp = &s_score[idx];
-      keep = !(sp[-kTW - 1] >= sc || sp[-kTW] >= sc || sp[-kTW + 1] >= sc || sp[-1] >= sc || sp[1] >= sc ||
-               sp[kTW - 1] >= sc || sp[kTW] >= sc || sp[kTW + 1] >= sc);
-    } else {  // tile edge: in-tile neighbours first, then (rarely) score the neighbours of other tiles from the halo
+#pragma unroll
+    for (int n = 0; n < 9; ++n) {  // neighbours inside the tile
+      if (n == 4) continue;
+      const int dr = n / 3 - 1, dc = n % 3 - 1;
+      const bool inside = !edge || ((unsigned)(r + dr) < (unsigned)kTH && (unsigned)(c + dc) < (unsigned)kTW);
+      if (inside && s_score[idx + dr * kTW + dc] >= sc) keep = false;
+    }
+    if (keep && edge) {  // rare: neighbours that belong to other tiles are scored from the halo
 #pragma unroll 1
-      for (int pass = 0; pass < 2 && keep; ++pass) {
-#pragma unroll 1
-        for (int n = 0; n < 9 && keep; ++n) {
-          if (n == 4) continue;
-          const int dr = n / 3 - 1, dc = n - (n / 3) * 3 - 1;
-          const int rr = r + dr, cc = c + dc;
-          const bool inside = (unsigned)rr < (unsigned)kTH && (unsigned)cc < (unsigned)kTW;
-          if (inside != (pass == 0)) continue;
-          int nsc = 0;
-          if (inside) {
-            nsc = s_score[rr * kTW + cc];
-          } else {
-            const int ny = gy + dr, nx = gx + dc;
-            if (nx >= 3 && ny >= 3 && nx < cols - 3 && ny < rows - 3) {
-              const int m = fastMargin<ARC>(&s_img[(rr + kHalo) * kSPitch + kPadL + cc], kSPitch);
-              if (m >= thr) nsc = m;
-            }
-          }
-          if (nsc >= sc) keep = false;
-        }
+      for (int n = 0; n < 9 && keep; ++n) {
+        const int dr = n / 3 - 1, dc = n - (n / 3) * 3 - 1;
+        const int rr = r + dr, cc = c + dc;
+        if ((unsigned)rr < (unsigned)kTH && (unsigned)cc < (unsigned)kTW) continue;
+        const int ny = gy + dr, nx = gx + dc;
+        if (nx >= 3 && ny >= 3 && nx < cols - 3 && ny < rows - 3 &&
+            fastMargin<ARC>(&s_img[(rr + kHalo) * kSPitch + kPadL + cc], kSPitch) >= sc) keep = false;
       }
     }
     if (!keep) continue;

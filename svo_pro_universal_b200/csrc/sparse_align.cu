@@ -71,6 +71,74 @@ SVO_D double warpSum(double v) {
   return v;
 }
 
+// Sum NP (power of two <= 32) per-lane values over the warp with a transposing butterfly: every step halves the number of
+// values a lane still carries, so NP values cost NP - 1 + log2(32 / NP) shuffled doubles instead of 5 * NP.
+// Returns, in every lane, the warp total of value number `lane / (32 / NP)` (NP == 32: value `lane`).
+template <int NP>
+SVO_D double warpSumMulti(double* v, int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NP; n > 1; n >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const double keep = up ? v[i + n / 2] : v[i];
+      const double send = up ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// 1/d to within an ulp: hardware seed + one cubic and one quadratic Newton step (6 dependent operations; the
+// IEEE-correct division the compiler emits is about twice as deep and sits on the serial path of every iteration).
+SVO_D double fastRcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, fma(e, e, e), x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
+
+// exact u8 -> double on the FP64 pipe (2^52 + b has b in its low mantissa bits), instead of I2F on the quarter-rate XU pipe
+SVO_D double u8ToDouble(unsigned b) { return __hiloint2double(0x43300000, (int)b) - 4503599627370496.0; }
+SVO_D unsigned byteAt(unsigned w, int i) { return __byte_perm(w, 0u, 0x4440 | i); }
+
+// cos(x) and sin(x)/x for y = x^2 <= 0.25 (Taylor to y^9: truncation < 1e-24), evaluated pairwise to keep the dependent chain short.
+SVO_D void cosSinc(double y, double& c, double& sc) {
+  const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
+  const double c01 = fma(y, -1.0 / 2.0, 1.0), c23 = fma(y, -1.0 / 720.0, 1.0 / 24.0);
+  const double c45 = fma(y, -1.0 / 3628800.0, 1.0 / 40320.0), c67 = fma(y, -1.0 / 87178291200.0, 1.0 / 479001600.0);
+  const double c89 = fma(y, -1.0 / 6402373705728000.0, 1.0 / 20922789888000.0);
+  c = fma(y8, c89, fma(y4, fma(y2, c67, c45), fma(y2, c23, c01)));
+  const double s01 = fma(y, -1.0 / 6.0, 1.0), s23 = fma(y, -1.0 / 5040.0, 1.0 / 120.0);
+  const double s45 = fma(y, -1.0 / 39916800.0, 1.0 / 362880.0), s67 = fma(y, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+  const double s89 = fma(y, -1.0 / 121645100408832000.0, 1.0 / 355687428096000.0);
+  sc = fma(y8, s89, fma(y4, fma(y2, s67, s45), fma(y2, s23, s01)));
+}
+// quatExp (common.cuh) with the polynomial above for |dx| <= 1 rad; same small-angle branch as the reference.
+SVO_D Quatd quatExpFast(const V3d& dx) {
+  const double th2 = dot3(dx, dx);
+  if (th2 > 1.0) return quatExp(dx);
+  double ct, sc;
+  cosSinc(0.25 * th2, ct, sc);
+  const double na = th2 < SVO_EPS4ROOT * SVO_EPS4ROOT ? 0.5 + th2 * (1.0 / 48.0) : 0.5 * sc;
+  return {ct, dx.x * na, dx.y * na, dx.z * na};
+}
+// q / |q| for a quaternion that is already unit up to rounding: 1/sqrt(1+e) = 1 - e/2 + 3e^2/8 (|e| < 1e-6 -> error < 1e-18)
+SVO_D void quatNormalizeFast(Quatd& q) {
+  const double e = quatSqNorm(q) - 1.0;
+  if (fabs(e) < 1e-6) {
+    const double sN = fma(e, fma(e, 0.375, -0.5), 1.0);
+    q.w *= sN; q.x *= sN; q.y *= sN; q.z *= sN;
+  } else {
+    quatNormalize(q);
+  }
+}
+
 // ref: src/vikit/vikit_solver/src/robust_cost.cpp:48-60 with b = 4.6851f (robust_cost.h:70)
 SVO_D float tukeyWeight(float error) {
   const float b_square = 4.6851f * 4.6851f;
@@ -86,7 +154,7 @@ SVO_D float tukeyWeight(float error) {
 // illumination parameters switched off) yields dx_k = 0, which is what Eigen's pivoted LDLT::solve returns for those
 // rows (mini_least_squares_solver.hpp:258). `tri` holds the upper triangle row-major ((0,0),(0,1)..(0,D-1),(1,1)..),
 // `diag_add` is added on the diagonal. Everything unrolls at compile time so the factor lives in registers; one
-// reciprocal per pivot.
+// Newton reciprocal per pivot.
 template <int D>
 SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double* g, double* dx) {
   double L[D][D], dd[D], rd[D];
@@ -98,7 +166,7 @@ SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double*
     for (int j = 0; j < k; ++j) { w[j] = L[k][j] * dd[j]; d -= L[k][j] * w[j]; }
     dd[k] = d;
     const bool ok = fabs(d) > 2.2250738585072014e-308;
-    rd[k] = ok ? 1.0 / d : 0.0;
+    rd[k] = ok ? fastRcp(d) : 0.0;
 #pragma unroll
     for (int i = k + 1; i < D; ++i) {
       double s = tri[k * D - (k * (k - 1)) / 2 + (i - k)];
@@ -168,12 +236,14 @@ SVO_D PatchSums unitWeightSums(const double* patch, int stride, bool est_gain, b
 // Rank-2 expansion of one patch's sums into the D(D+1)/2 upper-triangle entries of H, warp-reduced into red[0..NH).
 template <int D>
 SVO_D void reduceH(const PatchSums& p, const double* jp0, const double* jp1, double* red, int lane) {
+  constexpr int NH = D * (D + 1) / 2;
   double ua[6], va[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     ua[k] = p.sxx * jp0[k] + p.sxy * jp1[k];
     va[k] = p.sxy * jp0[k] + p.syy * jp1[k];
   }
+  double h[NH > 32 ? 40 : 32];
   int idx = 0;
 #pragma unroll
   for (int a = 0; a < D; ++a) {
@@ -183,10 +253,16 @@ SVO_D void reduceH(const PatchSums& p, const double* jp0, const double* jp1, dou
       if (b < 6) v = ua[a] * jp0[b] + va[a] * jp1[b];
       else if (a < 6) v = (b == 6) ? (jp0[a] * p.sx6 + jp1[a] * p.sy6) : (jp0[a] * p.sx7 + jp1[a] * p.sy7);
       else v = (a == 6 && b == 6) ? p.s66 : (a == 6 ? p.s67 : p.s77);
-      v = warpSum(v);
-      if (lane == 0) red[idx] += v;
-      ++idx;
+      h[idx++] = v;
     }
+  }
+#pragma unroll
+  for (int k = NH; k < (NH > 32 ? 40 : 32); ++k) h[k] = 0.0;
+  const double t = warpSumMulti<32>(h, lane);       // lane k holds entry k
+  if (lane < (NH < 32 ? NH : 32)) red[lane] += t;
+  if (NH > 32) {                                     // 8-DoF: entries 32..35
+    const double t2 = warpSumMulti<8>(h + 32, lane);  // lanes 4k hold entry 32 + k
+    if ((lane & 3) == 0 && 32 + (lane >> 2) < NH) red[32 + (lane >> 2)] += t2;
   }
 }
 
@@ -325,23 +401,28 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
         const int ui = (int)floor(u_tl), vi = (int)floor(v_tl);
         const double su = u_tl - ui, sv = v_tl - vi;
         const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
-        unsigned ra, rb;
-        loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
+        // 7x7 taps -> the 32 used values of the 6x6 interpolated patch; every tap is converted to double once
+        double tp[7], tn[7];
+        {
+          unsigned ra, rb;
+          loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
+#pragma unroll
+          for (int x = 0; x < 7; ++x) tp[x] = u8ToDouble(x < 4 ? byteAt(ra, x) : byteAt(rb, x - 4));
+        }
 #pragma unroll
         for (int y = 0; y < 6; ++y) {
           unsigned na, nb;
           loadRow8(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
 #pragma unroll
+          for (int x = 0; x < 7; ++x) tn[x] = u8ToDouble(x < 4 ? byteAt(na, x) : byteAt(nb, x - 4));
+#pragma unroll
           for (int x = 0; x < 6; ++x) {
             const bool used = (y >= 1 && y <= 4) || (x >= 1 && x <= 4);
             if (!used) continue;
-            const unsigned t0 = x < 4 ? byteOf(ra, x) : byteOf(rb, x - 4);
-            const unsigned t1 = (x + 1) < 4 ? byteOf(ra, x + 1) : byteOf(rb, x + 1 - 4);
-            const unsigned b0 = x < 4 ? byteOf(na, x) : byteOf(nb, x - 4);
-            const unsigned b1 = (x + 1) < 4 ? byteOf(na, x + 1) : byteOf(nb, x + 1 - 4);
-            s_patch[patchIdx(x, y) * stride + s] = wtl * t0 + wtr * t1 + wbl * b0 + wbr * b1;
+            s_patch[patchIdx(x, y) * stride + s] = wtl * tp[x] + wtr * tp[x + 1] + wbl * tn[x] + wbr * tn[x + 1];
           }
-          ra = na; rb = nb;
+#pragma unroll
+          for (int x = 0; x < 7; ++x) tp[x] = tn[x];
         }
       }
       __syncthreads();
@@ -383,23 +464,34 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
                 const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
                 const double gain = 1.0 + alpha_f;
                 const double* patch = s_patch + s;
-                unsigned ra, rb;
-                loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
+                // 5x5 taps, each converted once; the 32 stored patch values are read exactly once (rolling rows)
+                double tp[5], tn[5];
+                {
+                  unsigned ra, rb;
+                  loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
+#pragma unroll
+                  for (int x = 0; x < 5; ++x) tp[x] = u8ToDouble(x < 4 ? byteAt(ra, x) : byteAt(rb, 0));
+                }
+                double up[4], mid[6], low[6];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) up[x] = patch[patchIdx(x + 1, 0) * stride];
+#pragma unroll
+                for (int x = 0; x < 6; ++x) mid[x] = patch[patchIdx(x, 1) * stride];
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
                   unsigned na, nb;
                   loadRow8(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
 #pragma unroll
+                  for (int x = 0; x < 5; ++x) tn[x] = u8ToDouble(x < 4 ? byteAt(na, x) : byteAt(nb, 0));
+#pragma unroll
+                  for (int x = (y < 3 ? 0 : 1); x < (y < 3 ? 6 : 5); ++x) low[x] = patch[patchIdx(x, y + 2) * stride];
+#pragma unroll
                   for (int x = 0; x < 4; ++x) {
-                    const unsigned t0 = byteOf(ra, x);
-                    const unsigned t1 = x < 3 ? byteOf(ra, x + 1) : byteOf(rb, 0);
-                    const unsigned b0 = byteOf(na, x);
-                    const unsigned b1 = x < 3 ? byteOf(na, x + 1) : byteOf(nb, 0);
-                    const double I = wtl * t0 + wtr * t1 + wbl * b0 + wbr * b1;
-                    const double ref = patch[patchIdx(x + 1, y + 1) * stride];
+                    const double I = wtl * tp[x] + wtr * tp[x + 1] + wbl * tn[x] + wbr * tn[x + 1];
+                    const double ref = mid[x + 1];
                     // twice the central differences; the exact factor 0.5 is applied to the sums afterwards
-                    const double dx2 = patch[patchIdx(x + 2, y + 1) * stride] - patch[patchIdx(x, y + 1) * stride];
-                    const double dy2 = patch[patchIdx(x + 1, y + 2) * stride] - patch[patchIdx(x + 1, y) * stride];
+                    const double dx2 = mid[x + 2] - mid[x];
+                    const double dy2 = low[x + 1] - up[x];
                     const double res = (I * gain + beta_f) - ref;  // sparse_img_align.cpp:488-489
                     if (ROBUST) {
                       const double w = (double)tukeyWeight((float)(res / wscale_f));
@@ -422,7 +514,12 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
                       }
                     }
                   }
-                  ra = na; rb = nb;
+#pragma unroll
+                  for (int x = 0; x < 5; ++x) tp[x] = tn[x];
+#pragma unroll
+                  for (int x = 0; x < 4; ++x) up[x] = mid[x + 1];
+#pragma unroll
+                  for (int x = 0; x < 6; ++x) mid[x] = low[x];
                 }
                 gx *= 0.5; gy *= 0.5;
                 if (ROBUST) {
@@ -443,21 +540,25 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
             jp1[k] = s_jp[(6 + k) * stride + sl] * scale;
           }
           if (ROBUST) reduceH<D>(ps, jp0, jp1, red, lane);
-#pragma unroll
-          for (int a = 0; a < D; ++a) {
-            double v;
-            if (a < 6) v = -(jp0[a] * gx + jp1[a] * gy);
-            else v = (a == 6) ? -g6 : -g7;
-            v = warpSum(v);
-            if (lane == 0) red[NH + a] += v;
-          }
           {
-            double v = warpSum(chi);
-            if (lane == 0) red[NH + D] += v;
-            v = warpSum(vis ? 16.0 : 0.0);
-            if (lane == 0) red[NH + D + 1] += v;
+            double gv[8];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) gv[a] = -(jp0[a] * gx + jp1[a] * gy);
+            gv[6] = ILLUM ? -g6 : chi;
+            gv[7] = ILLUM ? -g7 : 0.0;
+            const double t = warpSumMulti<8>(gv, lane);  // lanes 4k hold value k
+            const int k = lane >> 2;
+            if ((lane & 3) == 0 && (ILLUM || k < 7)) red[NH + k] += t;  // g[0..D) (and chi right behind g when D == 6)
+            if (ILLUM) {
+              const double c = warpSum(chi);
+              if (lane == 0) red[NH + D] += c;
+            }
+            const unsigned visb = __ballot_sync(0xffffffffu, vis);
             const unsigned ch = __ballot_sync(0xffffffffu, changed);
-            if (lane == 0 && ch) red[NH + D + 2] += 1.0;
+            if (lane == 0) {
+              red[NH + D + 1] += 16.0 * __popc(visb);
+              if (ch) red[NH + D + 2] += 1.0;
+            }
           }
         }
         vis_prev = vis_now;
@@ -539,12 +640,15 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
             } else {
               // update, sparse_img_align_base.cpp:64-75
               SE3d inc;
-              inc.q = quatExp(V3d{-dx[3], -dx[4], -dx[5]});
+              inc.q = quatExpFast(V3d{-dx[3], -dx[4], -dx[5]});
               inc.t = V3d{-dx[0], -dx[1], -dx[2]};
               SE3d Tn = se3Mul(ctl.T, inc);
-              const double an = (ctl.alpha - dx[6]) / (1.0 + dx[6]);
-              const double bn = (ctl.beta - dx[7]) / (1.0 + dx[6]);
-              quatNormalize(Tn.q);
+              double an = ctl.alpha, bn = ctl.beta;
+              if (ILLUM) {
+                an = (ctl.alpha - dx[6]) / (1.0 + dx[6]);
+                bn = (ctl.beta - dx[7]) / (1.0 + dx[6]);
+              }
+              quatNormalizeFast(Tn.q);
               ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
               ctl.T = Tn; ctl.alpha = an; ctl.beta = bn;
               ctl.chi2 = new_chi2;
