@@ -8,29 +8,33 @@
 //
 // Mapping: one CTA per frame-bundle pair; the CTA walks all pyramid levels and all Gauss-Newton iterations on the
 // device (no host round trips). One thread per feature patch:
-//   setup      feature subset (b2) + base caches xyz_ref / 2x6 projection Jacobian (b3) -> shared memory (k-major, no
-//              bank conflicts), once per run;
+//   setup      feature subset (b2) + base caches (b3): xyz_ref and 1/z (pinhole Jacobian) or the 2x3 projection Jacobian
+//              (use_distortion_jacobian) -> shared memory (k-major, no bank conflicts), once per run;
 //   per level  6x6 bilinear reference patch (b4) -> 32 doubles per feature in shared memory (centre + the 4-neighbour
 //              values the central differences need);
 //   per iter   project, visibility test, 5x5 cur-image taps via aligned 32-bit loads, 16 residuals (b5);
-//              the per-pixel Jacobian factorises as J = [ (dx*Jp0 + dy*Jp1)*scale ; a6 ; a7 ], so H and g of a patch are
-//              a rank-2 expansion of a few weighted sums — 16x fewer outer products than the reference's per-pixel
-//              loop, identical in exact arithmetic (b6). Without robust weights H depends only on WHICH patches are
-//              visible, so it is reduced once per level and again only when the visibility pattern changes; every
-//              iteration reduces just g, chi2, the measurement count and a "visibility changed" flag;
-//              warp-shuffle + cross-warp reduction, then warp 0 runs the register-resident LDLT solve, prior,
-//              SE3/illumination update and the convergence test (b7, b8) — two block barriers per iteration.
+//              the per-pixel Jacobian factorises as J = [ (dx*Jp0 + dy*Jp1)*scale ; a6 ; a7 ] with
+//              Jp = Jproj * R_cam_imu * [I | -skew(p_imu)], so the gradient of a patch is
+//                  g_trans = -scale * R_imu_cam * c,   g_rot = -scale * (R_imu_cam * (xyz_ref x c) + t_imu_cam x R_imu_cam c),
+//              c = Jproj^T [sum dx*res ; sum dy*res]: every patch contributes 6 numbers (c, xyz_ref x c) that are summed per
+//              camera and rotated ONCE after the reduction — no per-patch 2x6 Jacobian is stored (b6). H is a rank-2
+//              expansion of a few patch sums with Jp rebuilt on the fly; without robust weights H depends only on WHICH
+//              patches are visible, so it is reduced and factorised (LDL^T) once per level and again only when the
+//              visibility pattern changes; every other iteration reduces 7 numbers and runs two triangular solves;
+//              warp 0 then applies the prior and the SE3/illumination update (b7, b8) and rebuilds the cameras'
+//              T_cur_ref lane-parallel — two block barriers per iteration.
 // All arithmetic is FP64 like the reference (FloatType = double, src/svo_common/include/svo/common/types.h:16);
 // Tukey weights and the alpha/beta handed to the residual are float, as in the reference signatures.
+// Shared memory: 36 doubles per feature -> 4 CTAs per SM for <= 180 features (3 with the distortion Jacobian).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
 constexpr int kThreads = 192;
 constexpr int kWarps = kThreads / 32;
-constexpr int kNVmax = 36 + 8 + 3;                // H upper triangle + g + chi2 + n_meas + changed
-constexpr int kPerSlotBytes = (3 + 12 + 32) * 8 + 4 + 1;  // xyz, Jp0|Jp1, patch (doubles) + source index + camera
-constexpr int kFixedSlots = 184;                  // compile-time stride for the common <= 184-feature case
+constexpr int kFixedSlots = 180;                  // compile-time stride for the common <= 180-feature case (max_fts)
+constexpr int kCamBlk = 36;                       // per camera: R_cam_imu (9) | R_imu_cam (9) | t_cam_imu (3) | t_imu_cam (3) | T_cur_ref (12)
 
 struct AlignParams {
   int n_cams, B, max_features, slots;
@@ -54,10 +58,8 @@ struct AlignParams {
 struct Ctl {
   SE3d T, T_old;
   double alpha, beta, alpha_old, beta_old;
-  SE3d T_cam_imu[SVO_MAX_CAMS], T_imu_cam[SVO_MAX_CAMS];
-  double Rt[SVO_MAX_CAMS][12];  // T_cur_ref of camera c: R row-major (9) + t (3)
   double I_prior[8];            // diagonal of I_prior_
-  double tot[kNVmax];
+  double L[28], rd[8];          // cached LDL^T factor of H (+ prior) and the pivot reciprocals
   double chi2;
   float alpha_f, beta_f;
   int stop, brk;
@@ -101,6 +103,15 @@ SVO_D double fastRcp(double d) {
   x = fma(x, fma(e, e, e), x);
   e = fma(-d, x, 1.0);
   return fma(x, e, x);
+}
+
+// Five taps x0..x0+4 of a row always lie inside two aligned 32-bit words: taps 0-3 in `a`, tap 4 in byte 0 of `b`.
+SVO_D void loadRow5(const uint8_t* row, int x0, unsigned& a, unsigned& b) {
+  const unsigned* w = reinterpret_cast<const unsigned*>(row + (x0 & ~3));
+  const unsigned w0 = __ldg(w), w1 = __ldg(w + 1);
+  const unsigned sh = (x0 & 3) * 8;
+  a = __funnelshift_r(w0, w1, sh);
+  b = w1 >> sh;
 }
 
 // exact u8 -> double on the FP64 pipe (2^52 + b has b in its low mantissa bits), instead of I2F on the quarter-rate XU pipe
@@ -150,13 +161,14 @@ SVO_D float tukeyWeight(float error) {
   return 0.0f;
 }
 
-// Symmetric solve H dx = g, LDL^T without pivoting; a zero pivot (an all-zero row/column of the PSD normal matrix:
-// illumination parameters switched off) yields dx_k = 0, which is what Eigen's pivoted LDLT::solve returns for those
-// rows (mini_least_squares_solver.hpp:258). `tri` holds the upper triangle row-major ((0,0),(0,1)..(0,D-1),(1,1)..),
-// `diag_add` is added on the diagonal. Everything unrolls at compile time so the factor lives in registers; one
-// Newton reciprocal per pivot.
+// Symmetric solve H dx = g by LDL^T without pivoting, split into factor (once per H) and solve (every iteration).
+// A zero pivot (an all-zero row/column of the PSD normal matrix: illumination parameters switched off) yields dx_k = 0,
+// which is what Eigen's pivoted LDLT::solve returns for those rows (mini_least_squares_solver.hpp:258). `tri` holds the
+// upper triangle row-major ((0,0),(0,1)..(0,D-1),(1,1)..), `diag_add` is added on the diagonal. Lf is the strict lower
+// triangle row-major (Lf[i*(i-1)/2 + j], j < i), rd the pivot reciprocals (0 for a zero pivot). Everything unrolls at
+// compile time; one Newton reciprocal per pivot.
 template <int D>
-SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double* g, double* dx) {
+SVO_D void ldltFactor(const double* tri, const double* diag_add, double* Lf, double* rdf) {
   double L[D][D], dd[D], rd[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
@@ -175,7 +187,20 @@ SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double*
       L[i][k] = ok ? s * rd[k] : s;
     }
   }
-  double x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    rdf[i] = rd[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) Lf[(i * (i - 1)) / 2 + j] = L[i][j];
+  }
+}
+template <int D>
+SVO_D void ldltSolve(const double* Lf, const double* rdf, const double* g, double* dx) {
+  double L[D][D], x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) L[i][j] = Lf[(i * (i - 1)) / 2 + j];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     double s = g[i];
@@ -184,7 +209,7 @@ SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double*
     x[i] = s;
   }
 #pragma unroll
-  for (int i = 0; i < D; ++i) x[i] *= rd[i];  // zero pivot -> 0, as Eigen's LDLT::solve
+  for (int i = 0; i < D; ++i) x[i] *= rdf[i];  // zero pivot -> 0, as Eigen's LDLT::solve
 #pragma unroll
   for (int i = D - 1; i >= 0; --i) {
     double s = x[i];
@@ -196,11 +221,30 @@ SVO_D void ldltSolveTri(const double* tri, const double* diag_add, const double*
   for (int i = 0; i < D; ++i) dx[i] = x[i];
 }
 
-SVO_D void storeRt(const SE3d& T, double* Rt) {
+// T_cur_ref of every camera from the IMU-frame state: R = R_ci R(q) R_ic, t = R_ci (R(q) t_ic + t) + t_ci, one output
+// element per lane (camera blocks hold the constant matrices, see kCamBlk).
+SVO_D void refreshCameraTransforms(const SE3d& T, double* camblk, int n_cams, int lane) {
   const M3d R = quatToMatrix(T.q);
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = R.m[r][c];
-  Rt[9] = T.t.x; Rt[10] = T.t.y; Rt[11] = T.t.z;
+  const double tv[3] = {T.t.x, T.t.y, T.t.z};
+  for (int idx = lane; idx < 12 * n_cams; idx += 32) {
+    const int c = idx / 12, e = idx - 12 * c;
+    double* cb = camblk + kCamBlk * c;
+    const double* Rci = cb;
+    const double* Ric = cb + 9;
+    double v;
+    if (e < 9) {
+      const int r = e / 3, col = e - 3 * r;
+      v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v += Rci[3 * r + k] * (R.m[k][0] * Ric[col] + R.m[k][1] * Ric[3 + col] + R.m[k][2] * Ric[6 + col]);
+    } else {
+      const int r = e - 9;
+      v = cb[18 + r];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v += Rci[3 * r + k] * (R.m[k][0] * cb[21] + R.m[k][1] * cb[22] + R.m[k][2] * cb[23] + tv[k]);
+    }
+    cb[24 + e] = v;
+  }
 }
 
 // index of patch element (X, Y) of the 6x6 interpolated reference patch among the 32 stored values
@@ -266,43 +310,94 @@ SVO_D void reduceH(const PatchSums& p, const double* jp0, const double* jp1, dou
   }
 }
 
-template <bool ILLUM, bool ROBUST, int SLOTS>
-__global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(const AlignParams P) {
+// 2x6 Jacobian rows of one patch, rebuilt from the caches (only needed when H is reduced):
+// Jp = (mult * Jproj) * R_cam_imu * [I | -skew(p_imu)] * scale (sparse_img_align.cpp:297-316, :373-376).
+template <bool DJ>
+SVO_D void patchJacobian(const double* xyz, const double* aux, int stride, const double* cb, double mult, double scale,
+                         double* jp0, double* jp1) {
+  const double X = xyz[0], Y = xyz[stride], Z = xyz[2 * stride];
+  double J[2][3];
+  if (DJ) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { J[0][k] = aux[k * stride]; J[1][k] = aux[(3 + k) * stride]; }
+  } else {
+    const double iz = aux[0], sI = -mult * iz;  // Frame::jacobian_xyz2uv_imu (frame.h:342-357) times the focal length
+    J[0][0] = sI; J[0][1] = 0.0; J[0][2] = -sI * X * iz;
+    J[1][0] = 0.0; J[1][1] = sI; J[1][2] = -sI * Y * iz;
+  }
+  const double* Rci = cb;
+  const double* Ric = cb + 9;
+  const double px = Ric[0] * X + Ric[1] * Y + Ric[2] * Z + cb[21];
+  const double py = Ric[3] * X + Ric[4] * Y + Ric[5] * Z + cb[22];
+  const double pz = Ric[6] * X + Ric[7] * Y + Ric[8] * Z + cb[23];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    double* jp = r == 0 ? jp0 : jp1;
+    const double b0 = (J[r][0] * Rci[0] + J[r][1] * Rci[3] + J[r][2] * Rci[6]) * scale;
+    const double b1 = (J[r][0] * Rci[1] + J[r][1] * Rci[4] + J[r][2] * Rci[7]) * scale;
+    const double b2 = (J[r][0] * Rci[2] + J[r][1] * Rci[5] + J[r][2] * Rci[8]) * scale;
+    jp[0] = b0; jp[1] = b1; jp[2] = b2;
+    jp[3] = b2 * py - b1 * pz;
+    jp[4] = b0 * pz - b2 * px;
+    jp[5] = b1 * px - b0 * py;
+  }
+}
+
+// ILL: 0 = no illumination parameters and alpha = beta = 0 (the subtraction of the reference pixel rides in the
+// interpolation's FMA chain), 1 = no illumination parameters but non-zero initial alpha/beta, 2 = gain and/or offset estimated.
+template <int ILL, bool ROBUST, bool DJ, int SLOTS>
+__global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) ? 3 : 4) : 1) sparse_align_kernel(const AlignParams P) {
+  constexpr bool ILLUM = ILL == 2;
+  constexpr bool unit_gain = ILL == 0;
   constexpr int D = ILLUM ? 8 : 6;
   constexpr int NH = D * (D + 1) / 2;
-  constexpr int NV = NH + D + 3;  // H | g | chi2 | n_meas | changed
+  constexpr int NAUX = DJ ? 6 : 1;
   extern __shared__ __align__(16) double smem[];
   const int stride = SLOTS ? SLOTS : P.slots;
-  double* s_xyz = smem;                   // [3][stride]
-  double* s_jp = s_xyz + 3 * stride;      // [12][stride]
-  double* s_patch = s_jp + 12 * stride;   // [32][stride]
-  double* s_red = s_patch + 32 * stride;  // [kWarps][kNVmax]
-  Ctl& ctl = *reinterpret_cast<Ctl*>(s_red + kWarps * kNVmax);
+  const int n_cams = P.n_cams;
+  // per-warp accumulators: H | (c, xyz x c) per camera | g6 g7 | chi2 | n_meas | changed
+  const int iCM = NH, iG6 = NH + 6 * n_cams, iChi = iG6 + (ILLUM ? 2 : 0), iN = iChi + 1, iCh = iChi + 2, NV = iChi + 3;
+  double* s_xyz = smem;                          // [3][stride]
+  double* s_aux = s_xyz + 3 * stride;            // [NAUX][stride]  1/z, or the 2x3 projection Jacobian
+  double* s_patch = s_aux + NAUX * stride;       // [32][stride]
+  double* s_red = s_patch + 32 * stride;         // [kWarps][NV]
+  double* s_tot = s_red + kWarps * NV;           // [NV]
+  double* s_camblk = s_tot + NV;                 // [n_cams][kCamBlk]
+  Ctl& ctl = *reinterpret_cast<Ctl*>(s_camblk + kCamBlk * n_cams);
   int* s_src = reinterpret_cast<int*>(&ctl + 1);                // [stride] feature index inside its camera's array
   uint8_t* s_cam = reinterpret_cast<uint8_t*>(s_src + stride);  // [stride]
 
   const int pair = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_cams = P.n_cams;
   const svo_sparse_align_options& opt = P.opt;
 
   // ---- setup -----------------------------------------------------------------------------------------------
-  if (tid == 0) {
-    for (int c = 0; c < n_cams; ++c) {
-      ctl.T_cam_imu[c] = se3Load(P.T_cam_imu[c]);
-      ctl.T_imu_cam[c] = se3Inv(ctl.T_cam_imu[c]);
-    }
+  if (tid < n_cams) {
+    const SE3d Tci = se3Load(P.T_cam_imu[tid]);
+    const SE3d Tic = se3Inv(Tci);
+    const M3d Rci = quatToMatrix(Tci.q), Ric = quatToMatrix(Tic.q);
+    double* cb = s_camblk + kCamBlk * tid;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) { cb[3 * r + c] = Rci.m[r][c]; cb[9 + 3 * r + c] = Ric.m[r][c]; }
+    cb[18] = Tci.t.x; cb[19] = Tci.t.y; cb[20] = Tci.t.z;
+    cb[21] = Tic.t.x; cb[22] = Tic.t.y; cb[23] = Tic.t.z;
+  }
+  if (tid == 32) {
     const SE3d T_iref_world = se3Load(P.T_imu_world_ref + 7 * (size_t)pair);
     const SE3d T_icur_world = se3Load(P.T_imu_world_cur + 7 * (size_t)pair);
     ctl.T = se3Mul(T_icur_world, se3Inv(T_iref_world));  // sparse_img_align.cpp:74-75
-    ctl.alpha = opt.alpha_init;
-    ctl.beta = opt.beta_init;
-    ctl.stop = 0;
+    ctl.T_old = ctl.T;
+    ctl.alpha = ctl.alpha_old = opt.alpha_init;
+    ctl.beta = ctl.beta_old = opt.beta_init;
+    ctl.alpha_f = (float)opt.alpha_init;
+    ctl.beta_f = (float)opt.beta_init;
+    ctl.stop = 0; ctl.brk = 0;
     ctl.chi2 = 1e10;  // reset(): mini_least_squares_solver.hpp:243
     for (int i = 0; i < SVO_MAX_LEVELS; ++i) ctl.iters[i] = 0;
-    for (int i = 0; i < 8; ++i) ctl.I_prior[i] = 0.0;
-    for (int i = 0; i < kNVmax; ++i) ctl.tot[i] = 0.0;
+    for (int i = 0; i < 8; ++i) { ctl.I_prior[i] = 0.0; ctl.rd[i] = 0.0; }
+    for (int i = 0; i < 28; ++i) ctl.L[i] = 0.0;
   }
+  for (int i = tid; i < NV; i += kThreads) s_tot[i] = 0.0;
   __syncthreads();
 
   // b2 + b3: ordered compaction of the eligible, in-bounds features of every ref camera, base caches
@@ -314,7 +409,6 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
     const int ml = opt.max_level;
     const double scale_max = 1.0f / (1 << ml);
     const int rows_m2 = rp.rows[ml] - 2, cols_m2 = rp.cols[ml] - 2;
-    const svo_camera& cam = P.cams[c];
     for (int base = 0; base < n; base += kThreads) {
       const int i = base + tid;
       bool ok = false;
@@ -336,33 +430,17 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
       if (ok) {
         const int s = off + __popc(bal & ((1u << lane) - 1u));
         if (s < stride) {
-          // sparse_img_align.cpp:262-317
+          // sparse_img_align.cpp:262-317: xyz_ref = f * depth; the point in the ref camera frame is xyz_ref itself
           const double depth = P.depth[fbase + i];
-          const V3d fv{P.f[3 * (fbase + i)], P.f[3 * (fbase + i) + 1], P.f[3 * (fbase + i) + 2]};
-          const V3d xyz_ref = fv * depth;
-          const V3d p_imu = se3Apply(ctl.T_imu_cam[c], xyz_ref);
-          const SE3d& Tci = ctl.T_cam_imu[c];
-          const V3d pc = se3Apply(Tci, p_imu);
-          const M3d R = quatToMatrix(Tci.q);
-          double Jp[2][3];
-          double mult;
-          if (!opt.use_distortion_jacobian) {  // Frame::jacobian_xyz2uv_imu, frame.h:342-357, times focal length
-            const double sI = -1.0 / pc.z;
-            Jp[0][0] = sI; Jp[0][1] = 0.0; Jp[0][2] = sI * (-pc.x / pc.z);
-            Jp[1][0] = 0.0; Jp[1][1] = sI; Jp[1][2] = sI * (-pc.y / pc.z);
-            mult = fabs(cam.fx);
-          } else {  // Frame::jacobian_xyz2image_imu, frame.cpp:274-290, times -1
-            camProject3Jac(cam, pc, Jp);
-            mult = -1.0;
+          const V3d xyz_ref = V3d{P.f[3 * (fbase + i)], P.f[3 * (fbase + i) + 1], P.f[3 * (fbase + i) + 2]} * depth;
+          if (DJ) {  // Frame::jacobian_xyz2image_imu, frame.cpp:274-290, times -1
+            double Jp[2][3];
+            camProject3Jac(P.cams[c], xyz_ref, Jp);
+            for (int r = 0; r < 2; ++r)
+              for (int k = 0; k < 3; ++k) s_aux[(3 * r + k) * stride + s] = -Jp[r][k];
+          } else {
+            s_aux[s] = 1.0 / xyz_ref.z;
           }
-          double Bm[2][3];
-          for (int r = 0; r < 2; ++r)
-            for (int k = 0; k < 3; ++k) Bm[r][k] = Jp[r][0] * R.m[0][k] + Jp[r][1] * R.m[1][k] + Jp[r][2] * R.m[2][k];
-          // G = [I | -skew(p_imu)]
-          const double G[3][6] = {{1, 0, 0, 0, p_imu.z, -p_imu.y}, {0, 1, 0, -p_imu.z, 0, p_imu.x}, {0, 0, 1, p_imu.y, -p_imu.x, 0}};
-          for (int r = 0; r < 2; ++r)
-            for (int k = 0; k < 6; ++k)
-              s_jp[(r * 6 + k) * stride + s] = (Bm[r][0] * G[0][k] + Bm[r][1] * G[1][k] + Bm[r][2] * G[2][k]) * mult;
           s_xyz[0 * stride + s] = xyz_ref.x; s_xyz[1 * stride + s] = xyz_ref.y; s_xyz[2 * stride + s] = xyz_ref.z;
           s_src[s] = i;
           s_cam[s] = (uint8_t)c;
@@ -375,12 +453,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
   n_total = min(n_total, stride);
 
   if (n_total > 0) {
-    if (tid == 0) {
-      for (int k = 0; k < n_cams; ++k) storeRt(se3Mul(se3Mul(ctl.T_cam_imu[k], ctl.T), ctl.T_imu_cam[k]), ctl.Rt[k]);
-      ctl.alpha_f = (float)ctl.alpha;
-      ctl.beta_f = (float)ctl.beta;
-      ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
-    }
+    if (warp == 0) refreshCameraTransforms(ctl.T, s_camblk, n_cams, lane);
     const bool est_gain = ILLUM && opt.estimate_illumination_gain;
     const bool est_off = ILLUM && opt.estimate_illumination_offset;
     const float wscale_f = (float)opt.weight_scale;
@@ -431,24 +504,30 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
       unsigned vis_prev = 0u;  // bit j: was slot tid + j*kThreads visible in the previous iteration of this level
       const int max_iter = opt.max_iter;
       for (int iter = 0; iter < max_iter; ++iter) {
-        for (int k = lane; k < NV; k += 32) s_red[warp * kNVmax + k] = 0.0;
+        double* red = s_red + warp * NV;
+        for (int k = lane; k < NV; k += 32) red[k] = 0.0;
         __syncwarp();
-        double* red = s_red + warp * kNVmax;
         const float alpha_f = ctl.alpha_f, beta_f = ctl.beta_f;
-        unsigned vis_now = 0u;
+                unsigned vis_now = 0u;
         int chunk_j = 0;
         for (int s = tid; s < n_round; s += kThreads, ++chunk_j) {
           bool vis = false;
+          int c = 0;
           double gx = 0, gy = 0, chi = 0, g6 = 0, g7 = 0;
           PatchSums ps = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
           if (s < n_total) {
-            const int c = s_cam[s];
-            const double* Rt = ctl.Rt[c];
+            c = s_cam[s];
+            const double* Rt = s_camblk + kCamBlk * c + 24;
             const double X = s_xyz[s], Y = s_xyz[stride + s], Z = s_xyz[2 * stride + s];
             const V3d pc{Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9], Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10],
                          Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11]};
             if (!(pc.z < 0.0)) {  // sparse_img_align.cpp:432-438
-              const V2d uvc = camProject3(P.cams[c], pc);
+              // PinholeProjection::project3 (pinhole_projection.hpp:30-44) with a Newton reciprocal for 1/z
+              const svo_camera& cm = P.cams[c];
+              const double z_inv = fastRcp(pc.z);
+              double ud, vd;
+              camDistort(cm, pc.x * z_inv, pc.y * z_inv, ud, vd);
+              const V2d uvc{cm.fx * ud + cm.cx, cm.fy * vd + cm.cy};
               const PyrView& cp = P.cur_pyr[c];
               const double u_tl = uvc.x * scale - 1.5, v_tl = uvc.y * scale - 1.5;
               // sparse_img_align.cpp:449-456 (NaN coordinates fall through as "visible" in the reference; they cannot
@@ -468,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
                 double tp[5], tn[5];
                 {
                   unsigned ra, rb;
-                  loadRow8(img + (size_t)vi * pitch, ui, ra, rb);
+                  loadRow5(img + (size_t)vi * pitch, ui, ra, rb);
 #pragma unroll
                   for (int x = 0; x < 5; ++x) tp[x] = u8ToDouble(x < 4 ? byteAt(ra, x) : byteAt(rb, 0));
                 }
@@ -480,19 +559,24 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
                   unsigned na, nb;
-                  loadRow8(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
+                  loadRow5(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
 #pragma unroll
                   for (int x = 0; x < 5; ++x) tn[x] = u8ToDouble(x < 4 ? byteAt(na, x) : byteAt(nb, 0));
 #pragma unroll
                   for (int x = (y < 3 ? 0 : 1); x < (y < 3 ? 6 : 5); ++x) low[x] = patch[patchIdx(x, y + 2) * stride];
 #pragma unroll
                   for (int x = 0; x < 4; ++x) {
-                    const double I = wtl * tp[x] + wtr * tp[x + 1] + wbl * tn[x] + wbr * tn[x + 1];
                     const double ref = mid[x + 1];
                     // twice the central differences; the exact factor 0.5 is applied to the sums afterwards
                     const double dx2 = mid[x + 2] - mid[x];
                     const double dy2 = low[x + 1] - up[x];
-                    const double res = (I * gain + beta_f) - ref;  // sparse_img_align.cpp:488-489
+                    double res;  // I_cur * (1 + alpha) + beta - I_ref, sparse_img_align.cpp:488-489
+                    if (unit_gain) {  // alpha == beta == 0: the subtraction rides in the interpolation's FMA chain
+                      res = fma(wbr, tn[x + 1], fma(wbl, tn[x], fma(wtr, tp[x + 1], fma(wtl, tp[x], -ref))));
+                    } else {
+                      const double I = wtl * tp[x] + wtr * tp[x + 1] + wbl * tn[x] + wbr * tn[x + 1];
+                      res = (I * gain + beta_f) - ref;
+                    }
                     if (ROBUST) {
                       const double w = (double)tukeyWeight((float)(res / wscale_f));
                       const double wdx = w * dx2, wdy = w * dy2;
@@ -531,34 +615,58 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
           }
           if (vis) vis_now |= (1u << chunk_j);
           const bool changed = (iter == 0) || (vis != (((vis_prev >> chunk_j) & 1u) != 0u));
-          if (__ballot_sync(0xffffffffu, vis || changed) == 0u) continue;
+          const unsigned visb = __ballot_sync(0xffffffffu, vis);
+          const unsigned chb = __ballot_sync(0xffffffffu, changed);
+          if ((visb | chb) == 0u) continue;
           const int sl = (s < n_total) ? s : 0;
-          double jp0[6], jp1[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            jp0[k] = s_jp[k * stride + sl] * scale;
-            jp1[k] = s_jp[(6 + k) * stride + sl] * scale;
+          if (ROBUST && visb) {
+            double jp0[6], jp1[6];
+            patchJacobian<DJ>(s_xyz + sl, s_aux + sl, stride, s_camblk + kCamBlk * c, fabs(P.cams[c].fx), scale, jp0, jp1);
+            reduceH<D>(ps, jp0, jp1, red, lane);
           }
-          if (ROBUST) reduceH<D>(ps, jp0, jp1, red, lane);
-          {
+          if (visb) {
+            // c = (mult * Jproj)^T [gx ; gy] in the camera frame and xyz_ref x c; rotated into the IMU frame after the reduction
             double gv[8];
+            {
+              const double X = s_xyz[sl], Y = s_xyz[stride + sl], Z = s_xyz[2 * stride + sl];
+              double cx, cy, cz;
+              if (DJ) {
+                cx = s_aux[sl] * gx + s_aux[3 * stride + sl] * gy;
+                cy = s_aux[stride + sl] * gx + s_aux[4 * stride + sl] * gy;
+                cz = s_aux[2 * stride + sl] * gx + s_aux[5 * stride + sl] * gy;
+              } else {
+                const double iz = s_aux[sl], sI = -fabs(P.cams[c].fx) * iz;
+                cx = sI * gx; cy = sI * gy;
+                cz = -(X * cx + Y * cy) * iz;
+              }
+              gv[0] = cx; gv[1] = cy; gv[2] = cz;
+              gv[3] = Y * cz - Z * cy; gv[4] = Z * cx - X * cz; gv[5] = X * cy - Y * cx;
+              gv[6] = ILLUM ? -g6 : chi;
+              gv[7] = ILLUM ? -g7 : 0.0;
+            }
+            for (int cc = 0; cc < n_cams; ++cc) {  // warps hold one camera except at a camera boundary
+              const unsigned mine = __ballot_sync(0xffffffffu, vis && c == cc);
+              if (mine == 0u) continue;
+              double v8[8];
+              const bool me = (mine >> lane) & 1u;
 #pragma unroll
-            for (int a = 0; a < 6; ++a) gv[a] = -(jp0[a] * gx + jp1[a] * gy);
-            gv[6] = ILLUM ? -g6 : chi;
-            gv[7] = ILLUM ? -g7 : 0.0;
-            const double t = warpSumMulti<8>(gv, lane);  // lanes 4k hold value k
-            const int k = lane >> 2;
-            if ((lane & 3) == 0 && (ILLUM || k < 7)) red[NH + k] += t;  // g[0..D) (and chi right behind g when D == 6)
+              for (int k = 0; k < 8; ++k) v8[k] = me ? gv[k] : 0.0;
+              const double t = warpSumMulti<8>(v8, lane);  // lanes 4k hold value k
+              const int k = lane >> 2;
+              if ((lane & 3) == 0) {
+                if (k < 6) red[iCM + 6 * cc + k] += t;
+                else if (ILLUM) red[iG6 + (k - 6)] += t;
+                else if (k == 6) red[iChi] += t;
+              }
+            }
             if (ILLUM) {
-              const double c = warpSum(chi);
-              if (lane == 0) red[NH + D] += c;
+              const double cs = warpSum(chi);
+              if (lane == 0) red[iChi] += cs;
             }
-            const unsigned visb = __ballot_sync(0xffffffffu, vis);
-            const unsigned ch = __ballot_sync(0xffffffffu, changed);
-            if (lane == 0) {
-              red[NH + D + 1] += 16.0 * __popc(visb);
-              if (ch) red[NH + D + 2] += 1.0;
-            }
+          }
+          if (lane == 0) {
+            red[iN] += 16.0 * __popc(visb);
+            if (chb) red[iCh] += 1.0;
           }
         }
         vis_prev = vis_now;
@@ -568,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
           // H depends only on the visible set: rebuild it when some patch entered or left the image
           double any = 0.0;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) any += s_red[w * kNVmax + NH + D + 2];
+          for (int w = 0; w < kWarps; ++w) any += s_red[w * NV + iCh];
           h_fresh = (any != 0.0);
           if (h_fresh) {
             int cj = 0;
@@ -576,14 +684,11 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
               const bool vis = (vis_now >> cj) & 1u;
               if (__ballot_sync(0xffffffffu, vis) == 0u) continue;
               const int sl = (s < n_total) ? s : 0;
+              const int c = s_cam[sl];
               PatchSums ps = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
               if (vis) ps = unitWeightSums<ILLUM>(s_patch + sl, stride, est_gain, est_off);
               double jp0[6], jp1[6];
-#pragma unroll
-              for (int k = 0; k < 6; ++k) {
-                jp0[k] = s_jp[k * stride + sl] * scale;
-                jp1[k] = s_jp[(6 + k) * stride + sl] * scale;
-              }
+              patchJacobian<DJ>(s_xyz + sl, s_aux + sl, stride, s_camblk + kCamBlk * c, fabs(P.cams[c].fx), scale, jp0, jp1);
               reduceH<D>(ps, jp0, jp1, red, lane);
             }
             __syncthreads();
@@ -591,32 +696,49 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
         }
         if (warp == 0) {
           // cross-warp totals: lane k owns accumulator k; the H part is refreshed only when it was re-reduced
-          for (int k = lane; k < NH + D + 2; k += 32) {
+          for (int k = lane; k < NV; k += 32) {
             if (k < NH && !h_fresh) continue;
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) t += s_red[w * kNVmax + k];
-            ctl.tot[k] = t;
+            for (int w = 0; w < kWarps; ++w) t += s_red[w * NV + k];
+            s_tot[k] = t;
           }
           __syncwarp();
           if (lane == 0) {
             ctl.iters[level_slot] = iter + 1;
             double g[D], dx[8], padd[D];
 #pragma unroll
-            for (int a = 0; a < D; ++a) { g[a] = ctl.tot[NH + a]; padd[a] = 0.0; }
-            const double new_chi2 = (double)(float)(ctl.tot[NH + D] / ctl.tot[NH + D + 1]);  // float chi2 / n_meas (:540)
+            for (int a = 0; a < D; ++a) { g[a] = 0.0; padd[a] = 0.0; }
+            for (int cc = 0; cc < n_cams; ++cc) {  // gradient of the pose block from the per-camera sums
+              const double* cb = s_camblk + kCamBlk * cc;
+              const double* Ric = cb + 9;
+              const double* cm = s_tot + iCM + 6 * cc;
+              double bv[3], mv[3];
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                bv[r] = Ric[3 * r] * cm[0] + Ric[3 * r + 1] * cm[1] + Ric[3 * r + 2] * cm[2];
+                mv[r] = Ric[3 * r] * cm[3] + Ric[3 * r + 1] * cm[4] + Ric[3 * r + 2] * cm[5];
+              }
+              const double tx = cb[21], ty = cb[22], tz = cb[23];
+              g[0] -= scale * bv[0]; g[1] -= scale * bv[1]; g[2] -= scale * bv[2];
+              g[3] -= scale * (mv[0] + (ty * bv[2] - tz * bv[1]));
+              g[4] -= scale * (mv[1] + (tz * bv[0] - tx * bv[2]));
+              g[5] -= scale * (mv[2] + (tx * bv[1] - ty * bv[0]));
+            }
+            if (ILLUM) { g[D - 2] = s_tot[iG6]; g[D - 1] = s_tot[iG6 + 1]; }
+            const double new_chi2 = (double)(float)(s_tot[iChi] / s_tot[iN]);  // float chi2 / n_meas (:540)
             if (P.priors) {  // applyPrior, sparse_img_align_base.cpp:77-107
               const svo_align_prior& pr = P.priors[pair];
               if (iter == 0) {
                 double mt = 0, mr = 0;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) mt = fmax(mt, fabs(ctl.tot[j * D - (j * (j - 1)) / 2]));
+                for (int j = 0; j < 3; ++j) mt = fmax(mt, fabs(s_tot[j * D - (j * (j - 1)) / 2]));
 #pragma unroll
-                for (int j = 3; j < 6; ++j) mr = fmax(mr, fabs(ctl.tot[j * D - (j * (j - 1)) / 2]));
+                for (int j = 3; j < 6; ++j) mr = fmax(mr, fabs(s_tot[j * D - (j * (j - 1)) / 2]));
                 for (int j = 0; j < 3; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_trans * mt;
                 for (int j = 3; j < 6; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_rot * mr;
-                ctl.I_prior[6] = (D == 8) ? opt.lambda_alpha * ctl.tot[6 * D - 15] : 0.0;
-                ctl.I_prior[7] = (D == 8) ? opt.lambda_beta * ctl.tot[7 * D - 21] : 0.0;
+                ctl.I_prior[6] = (D == 8) ? opt.lambda_alpha * s_tot[6 * D - 15] : 0.0;
+                ctl.I_prior[7] = (D == 8) ? opt.lambda_beta * s_tot[7 * D - 21] : 0.0;
               }
               const SE3d Tp = se3Load(pr.T);
               const SE3d E = se3Mul(se3Inv(Tp), ctl.T);
@@ -631,7 +753,8 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
               }
             }
             dx[6] = 0.0; dx[7] = 0.0;
-            ldltSolveTri<D>(ctl.tot, padd, g, dx);
+            if (h_fresh) ldltFactor<D>(s_tot, padd, ctl.L, ctl.rd);  // H (+ prior) is constant until the visible set changes
+            ldltSolve<D>(ctl.L, ctl.rd, g, dx);
             if (dx[0] != dx[0]) ctl.stop = 1;  // solveDefaultImpl: isnan(dx[0]) -> stop_
             int brk = 0;
             if (ctl.stop) {
@@ -639,17 +762,18 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
               brk = 1;
             } else {
               // update, sparse_img_align_base.cpp:64-75
+              const SE3d Tc = ctl.T;
               SE3d inc;
               inc.q = quatExpFast(V3d{-dx[3], -dx[4], -dx[5]});
               inc.t = V3d{-dx[0], -dx[1], -dx[2]};
-              SE3d Tn = se3Mul(ctl.T, inc);
+              SE3d Tn = se3Mul(Tc, inc);
               double an = ctl.alpha, bn = ctl.beta;
               if (ILLUM) {
                 an = (ctl.alpha - dx[6]) / (1.0 + dx[6]);
                 bn = (ctl.beta - dx[7]) / (1.0 + dx[6]);
               }
               quatNormalizeFast(Tn.q);
-              ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
+              ctl.T_old = Tc; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
               ctl.T = Tn; ctl.alpha = an; ctl.beta = bn;
               ctl.chi2 = new_chi2;
               double x_norm = -1.0;
@@ -662,7 +786,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
             ctl.brk = brk;
           }
           __syncwarp();
-          if (lane < n_cams) storeRt(se3Mul(se3Mul(ctl.T_cam_imu[lane], ctl.T), ctl.T_imu_cam[lane]), ctl.Rt[lane]);
+          refreshCameraTransforms(ctl.T, s_camblk, n_cams, lane);
         }
         __syncthreads();
         if (ctl.brk) break;
@@ -677,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
     const SE3d T_iref_world = se3Load(P.T_imu_world_ref + 7 * (size_t)pair);
     se3Store(ctl.T, r.T_icur_iref);
     for (int c = 0; c < SVO_MAX_CAMS; ++c) {
-      if (c < n_cams) se3Store(se3Mul(se3Mul(ctl.T_cam_imu[c], ctl.T), T_iref_world), r.T_f_w[c]);
+      if (c < n_cams) se3Store(se3Mul(se3Mul(se3Load(P.T_cam_imu[c]), ctl.T), T_iref_world), r.T_f_w[c]);
       else for (int k = 0; k < 7; ++k) r.T_f_w[c][k] = 0.0;
     }
     r.alpha = ctl.alpha;
@@ -688,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
     if (n_total > 0) {
       int idx = 0;
       for (int a = 0; a < D; ++a)
-        for (int b = a; b < D; ++b) { r.H[a * 8 + b] = ctl.tot[idx]; r.H[b * 8 + a] = ctl.tot[idx]; ++idx; }
+        for (int b = a; b < D; ++b) { r.H[a * 8 + b] = s_tot[idx]; r.H[b * 8 + a] = s_tot[idx]; ++idx; }
       if (P.priors) for (int j = 0; j < 8; ++j) r.H[j * 8 + j] += ctl.I_prior[j];
     }
     r.n_tracked = n_total;
@@ -697,12 +821,24 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? 3 : 1) sparse_align_kernel(c
   }
 }
 
-template <bool ILLUM, bool ROBUST, int SLOTS>
+inline size_t alignSmemBytes(int slots, int n_cams, bool illum, bool dj) {
+  const int D = illum ? 8 : 6, NH = D * (D + 1) / 2;
+  const int NV = NH + 6 * n_cams + (illum ? 2 : 0) + 3;
+  const size_t doubles = (size_t)slots * (3 + (dj ? 6 : 1) + 32) + (size_t)(kWarps + 1) * NV + (size_t)kCamBlk * n_cams;
+  return doubles * 8 + sizeof(Ctl) + (size_t)slots * 5 + 16;
+}
+
+template <int ILL, bool ROBUST, bool DJ, int SLOTS>
 cudaError_t launchAlign(const AlignParams& P, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<ILLUM, ROBUST, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<ILL, ROBUST, DJ, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  sparse_align_kernel<ILLUM, ROBUST, SLOTS><<<P.B, kThreads, smem, stream>>>(P);
+  sparse_align_kernel<ILL, ROBUST, DJ, SLOTS><<<P.B, kThreads, smem, stream>>>(P);
   return cudaGetLastError();
+}
+template <int ILL, bool ROBUST>
+cudaError_t launchAlignSel(const AlignParams& P, size_t smem, cudaStream_t stream, bool dj, bool fixed) {
+  if (dj) return fixed ? launchAlign<ILL, ROBUST, true, kFixedSlots>(P, smem, stream) : launchAlign<ILL, ROBUST, true, 0>(P, smem, stream);
+  return fixed ? launchAlign<ILL, ROBUST, false, kFixedSlots>(P, smem, stream) : launchAlign<ILL, ROBUST, false, 0>(P, smem, stream);
 }
 
 }  // namespace
@@ -736,7 +872,11 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   const int slots = fixed ? kFixedSlots : ((need + 7) / 8) * 8;
   if (slots > 32 * kThreads) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: too many features per bundle");
   P.slots = slots;
-  const size_t smem = (size_t)slots * kPerSlotBytes + (size_t)kWarps * kNVmax * 8 + sizeof(Ctl) + 32;
+  const bool illum = opt->estimate_illumination_gain || opt->estimate_illumination_offset;
+  const bool robust = opt->robustification != 0;
+  const bool dj = opt->use_distortion_jacobian != 0;
+  size_t smem = alignSmemBytes(slots, n_cams, illum, dj);
+  if (const char* pad = getenv("SVO_ALIGN_PAD_SMEM")) smem += (size_t)atoi(pad);  // occupancy experiments only
   if (smem > 227 * 1024) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: n_cams*max_features exceeds the shared-memory capacity (~590 features per bundle)");
   for (int c = 0; c < n_cams; ++c) {
     P.ref_pyr[c] = makeView(ref_pyr[c]);
@@ -760,16 +900,11 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   P.results = st.out(results, (size_t)B);
   if (st.failed()) return st.finish();
 
-  const bool illum = opt->estimate_illumination_gain || opt->estimate_illumination_offset;
-  const bool robust = opt->robustification != 0;
   cudaError_t e;
-  if (fixed) {
-    if (illum) e = robust ? launchAlign<true, true, kFixedSlots>(P, smem, ctx->stream) : launchAlign<true, false, kFixedSlots>(P, smem, ctx->stream);
-    else e = robust ? launchAlign<false, true, kFixedSlots>(P, smem, ctx->stream) : launchAlign<false, false, kFixedSlots>(P, smem, ctx->stream);
-  } else {
-    if (illum) e = robust ? launchAlign<true, true, 0>(P, smem, ctx->stream) : launchAlign<true, false, 0>(P, smem, ctx->stream);
-    else e = robust ? launchAlign<false, true, 0>(P, smem, ctx->stream) : launchAlign<false, false, 0>(P, smem, ctx->stream);
-  }
+  const bool unit = (float)opt->alpha_init == 0.0f && (float)opt->beta_init == 0.0f;  // residual uses float alpha/beta
+  if (illum) e = robust ? launchAlignSel<2, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<2, false>(P, smem, ctx->stream, dj, fixed);
+  else if (unit) e = robust ? launchAlignSel<0, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<0, false>(P, smem, ctx->stream, dj, fixed);
+  else e = robust ? launchAlignSel<1, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<1, false>(P, smem, ctx->stream, dj, fixed);
   ctx->launches++;
   SVO_CUDA_TRY(ctx, e);
   return st.finish();
