@@ -193,6 +193,21 @@ def ref_lib():
     return _ref
 
 
+_ref_direct = None
+
+
+def ref_direct_lib():
+    """The reference's own halfSample / align1D / align2D / alignPyr2D / ZMSSD / Tukey / radtan / seed / grid code compiled
+    against the container-only shims (oracle/_ref/libdirect_ref.so; None if it was never built)."""
+    global _ref_direct
+    if _ref_direct is None:
+        so = os.path.join(_HERE, "_ref", "libdirect_ref.so")
+        if not os.path.exists(so):
+            return None
+        _ref_direct = C.CDLL(so)
+    return _ref_direct
+
+
 def _u8(a):
     return a.ctypes.data_as(u8p)
 
@@ -395,3 +410,129 @@ def pyramid_align_batch(cur_l0_list, ref_frames, cur_frames, opt, n_levels=5, n_
     res = (AlignResult * B)()
     lib().orc_pyramid_align_batch(B, n_levels, ptrs, cols, rows, pyr_mode, R, Cc, C.byref(opt), res, n_threads)
     return res
+
+
+# ---- one-function-at-a-time entry points, `which` = "orc" (the restatement) or "ref" (the compiled reference) ------------
+def _which(which):
+    if which == "orc":
+        return lib(), "orc_"
+    L = ref_direct_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libdirect_ref.so not built")
+    return L, "ref_"
+
+
+def ref_create_img_pyramid(img0, n_levels):
+    """frame_utils::createImgPyramid through the reference's own vk::halfSample (64-byte aligned continuous buffers)."""
+    img0 = np.ascontiguousarray(img0, dtype=np.uint8)
+    rows, cols = img0.shape
+    sizes = pyramid_level_sizes(cols, rows, n_levels)
+    levels = [img0] + [np.zeros((r, c), np.uint8) for c, r in sizes[1:]]
+    ptrs = (C.c_void_p * n_levels)(*[l.ctypes.data for l in levels])
+    ref_direct_lib().ref_create_img_pyramid(_u8(img0), cols, rows, cols, n_levels, ptrs)
+    return levels
+
+
+def ref_half_sample(img, align_offset=0, extra_stride=0):
+    """One vk::halfSample call; align_offset / extra_stride move the input off 16-byte alignment / continuity to reach the
+    non-SSE2 branch (vision.cpp:80-87)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = img.shape
+    stride = cols + extra_stride
+    raw = np.zeros(stride * rows + 128, np.uint8)
+    base = (-raw.ctypes.data) % 64 + align_offset
+    view = np.lib.stride_tricks.as_strided(raw[base:], (rows, cols), (stride, 1))
+    view[:] = img
+    out = np.zeros((rows // 2, cols // 2), np.uint8)
+    ref_direct_lib().ref_half_sample(C.c_void_p(raw.ctypes.data + base), cols, rows, stride, _u8(out), cols // 2)
+    return out
+
+
+def align2d(img, patch_with_border, px, n_iter=10, est_offset=True, est_gain=False, which="orc"):
+    img = np.ascontiguousarray(img, np.uint8)
+    pwb = np.ascontiguousarray(patch_with_border, np.uint8).reshape(100).copy()
+    p = np.array(px, np.float64)
+    L, pre = _which(which)
+    if which == "orc":
+        ok = L.orc_align2d(_u8(img), img.shape[1], img.shape[0], img.strides[0], _u8(pwb), n_iter, int(est_offset), int(est_gain), _f64(p))
+    else:
+        patch = pwb.reshape(10, 10)[1:9, 1:9].copy()
+        ok = L.ref_align2d(_u8(img), img.shape[1], img.shape[0], img.strides[0], _u8(pwb), _u8(patch), n_iter, int(est_offset), int(est_gain), _f64(p))
+    return bool(ok), p
+
+
+def align1d(img, direction, patch_with_border, px, n_iter=10, est_offset=True, est_gain=False, which="orc"):
+    img = np.ascontiguousarray(img, np.uint8)
+    pwb = np.ascontiguousarray(patch_with_border, np.uint8).reshape(100).copy()
+    p = np.array(px, np.float64)
+    d = np.array(direction, np.float64)
+    hinv = C.c_double(0.0)
+    L, pre = _which(which)
+    if which == "orc":
+        ok = L.orc_align1d(_u8(img), img.shape[1], img.shape[0], img.strides[0], _f64(d), _u8(pwb), n_iter, int(est_offset), int(est_gain), _f64(p), C.byref(hinv))
+    else:
+        patch = pwb.reshape(10, 10)[1:9, 1:9].copy()
+        ok = L.ref_align1d(_u8(img), img.shape[1], img.shape[0], img.strides[0], _f64(d), _u8(pwb), _u8(patch), n_iter, int(est_offset), int(est_gain), _f64(p), C.byref(hinv))
+    return bool(ok), p, hinv.value
+
+
+def zmssd(ref_patch64, img, xy, which="orc"):
+    """ZMSSD<4> of the 8x8 reference patch against the 8x8 windows of img whose top-left corners are xy [n][2]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    rp = np.zeros(64 + 16, np.uint8)
+    off = (-rp.ctypes.data) % 16  # the SSE paths load the template with aligned loads
+    rp[off:off + 64] = np.ascontiguousarray(ref_patch64, np.uint8).reshape(64)
+    xy = np.asarray(xy, np.int64).reshape(-1, 2)
+    out = np.zeros(len(xy), np.int32)
+    if which == "orc":
+        for i, (x, y) in enumerate(xy):
+            out[i] = lib().orc_zmssd(C.c_void_p(rp.ctypes.data + off), C.c_void_p(img.ctypes.data + int(y) * img.strides[0] + int(x)), img.strides[0])
+    else:
+        offs = np.ascontiguousarray(xy[:, 1] * img.strides[0] + xy[:, 0], np.int32)
+        ref_direct_lib().ref_zmssd(C.c_void_p(rp.ctypes.data + off), _u8(img), img.strides[0], _i32(offs), len(xy), _i32(out), None)
+    return out
+
+
+def tukey_weight(err, b=4.6851, which="orc"):
+    e = np.ascontiguousarray(err, np.float32)
+    w = np.zeros_like(e)
+    L, pre = _which(which)
+    getattr(L, pre + "tukey_weight")(C.c_float(b), e.ctypes.data_as(C.c_void_p), len(e), w.ctypes.data_as(C.c_void_p))
+    return w
+
+
+def radtan(k, xy, mode, which="orc"):
+    """mode: 'distort' | 'undistort' | 'jacobian' on normalised points xy [n][2]."""
+    pts = np.array(xy, np.float64).reshape(-1, 2).copy()
+    jac = np.zeros((len(pts), 4), np.float64)
+    L, pre = _which(which)
+    getattr(L, pre + "radtan")(C.c_double(k[0]), C.c_double(k[1]), C.c_double(k[2]), C.c_double(k[3]),
+                               {"distort": 0, "undistort": 1, "jacobian": 2}[mode], _f64(pts), len(pts), _f64(jac))
+    return jac if mode == "jacobian" else pts
+
+
+def seed_helpers(state4, mu_range, thresh, depth, depth_sigma, which="orc"):
+    s = np.array(state4, np.float64)
+    out = np.zeros(6, np.float64)
+    L, pre = _which(which)
+    getattr(L, pre + "seed_helpers")(_f64(s), C.c_double(mu_range), C.c_double(thresh), C.c_double(depth), C.c_double(depth_sigma), _f64(out))
+    return out
+
+
+def grid_cell_index(cell_size, n_cols, n_rows, xy, scale, which="orc"):
+    xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+    sc = np.ascontiguousarray(scale, np.int32)
+    out = np.zeros(len(xy), np.int64)
+    if which == "orc":
+        lib().orc_grid_cell_index(cell_size, n_cols, _i32(xy), _i32(sc), len(xy), out.ctypes.data_as(C.c_void_p))
+    else:
+        ref_direct_lib().ref_grid_cell_index(cell_size, n_cols, n_rows, _i32(xy), _i32(sc), len(xy), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def patch_from_patch_with_border(pwb, which="orc"):
+    pwb = np.ascontiguousarray(pwb, np.uint8).reshape(100)
+    out = np.zeros(64, np.uint8)
+    L, pre = _which(which)
+    getattr(L, pre + "patch_from_patch_with_border")(_u8(pwb), 8, _u8(out))
+    return out

@@ -373,6 +373,40 @@ int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
 
 }  // extern "C"
 
+extern "C" {
+void orc_tukey_weight(float b, const float* err, int n, float* w) {
+  TukeyWeightFunction f(b);
+  for (int i = 0; i < n; ++i) w[i] = f.weight(err[i]);
+}
+void orc_radtan(double k1, double k2, double p1, double p2, int which, double* xy, int n, double* jac_out) {
+  Camera c{};
+  c.k1 = k1; c.k2 = k2; c.p1 = p1; c.p2 = p2; c.distortion = 1;
+  for (int i = 0; i < n; ++i) {
+    if (which == 0) { double xd, yd; c.distort(xy[2 * i], xy[2 * i + 1], xd, yd); xy[2 * i] = xd; xy[2 * i + 1] = yd; }
+    else if (which == 1) c.undistort(xy[2 * i], xy[2 * i + 1]);
+    else {
+      double J[2][2];
+      c.distJacobian(xy[2 * i], xy[2 * i + 1], J);
+      jac_out[4 * i] = J[0][0]; jac_out[4 * i + 1] = J[0][1]; jac_out[4 * i + 2] = J[1][0]; jac_out[4 * i + 3] = J[1][1];
+    }
+  }
+}
+void orc_seed_helpers(const double* s, double mu_range, double sigma2_convergence_threshold, double depth, double depth_sigma, double* out) {
+  out[0] = seed::getDepth(s);
+  out[1] = seed::getInvMinDepth(s);
+  out[2] = seed::getInvMaxDepth(s);
+  out[3] = seed::isConverged(s, mu_range, sigma2_convergence_threshold) ? 1.0 : 0.0;
+  out[4] = seed::getSigma2FromDepthSigma(depth, depth_sigma);
+  out[5] = seed::getInitSigma2FromMuRange(mu_range);
+}
+void orc_grid_cell_index(int cell_size, int n_cols, const int* xy, const int* scale, int n, long long* idx) {
+  for (int i = 0; i < n; ++i) idx[i] = (long long)gridCellIndex(xy[2 * i], xy[2 * i + 1], scale[i], cell_size, n_cols);
+}
+void orc_patch_from_patch_with_border(const uint8_t* patch_with_border, int patch_size, uint8_t* patch) {
+  createPatchFromPatchWithBorder(patch_with_border, patch_size, patch);
+}
+}  // extern "C"
+
 // One "frame pair step" of the hot path as the bench defines it: build the pyramid of the NEW (cur) frame from its level-0
 // image (frame_utils::createImgPyramid), then SparseImgAlign::run against the already-built ref frame. B independent pairs,
 // n_threads workers. cur[i] supplies camera/poses; its level pointers are ignored and rebuilt from cur_l0[i].

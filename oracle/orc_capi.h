@@ -151,6 +151,15 @@ int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
                      int check_visibility, int check_convergence, int use_vogiatzis, int* match_results, uint8_t* success,
                      int n_threads);
 
+/* small pieces exposed one by one so that tests can pin them against the compiled reference (oracle/_ref/libdirect_ref.so) */
+void orc_tukey_weight(float b, const float* err, int n, float* w);
+/* which: 0 distort, 1 undistort, 2 jacobian (jac_out [n][4] = J00, J01, J10, J11) */
+void orc_radtan(double k1, double k2, double p1, double p2, int which, double* xy, int n, double* jac_out);
+/* out[0..5] = getDepth, getInvMinDepth, getInvMaxDepth, isConverged, getSigma2FromDepthSigma, getInitSigma2FromMuRange */
+void orc_seed_helpers(const double* state4, double mu_range, double sigma2_convergence_threshold, double depth, double depth_sigma, double* out);
+void orc_grid_cell_index(int cell_size, int n_cols, const int* xy, const int* scale, int n, long long* idx);
+void orc_patch_from_patch_with_border(const uint8_t* patch_with_border, int patch_size, uint8_t* patch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,10 @@ fast_ref_golden.npz   outputs of the REFERENCE's own FAST code (oracle/_ref/libf
                       /root/reference does not exist.
 oracle_golden.npz     outputs of the CPU oracle (restated reference arithmetic) for pyramid / sparse alignment / matcher /
                       depth filter on seeded inputs: regression pins for the oracle itself ("parity unpinned" rows).
+direct_ref_golden.npz outputs of the REFERENCE's own halfSample / align1D / align2D / ZMSSD / Tukey / radtan / seed / grid code
+                      (oracle/_ref/libdirect_ref.so, compiled from /root/reference against the container-only shims in
+                      oracle/shim) on seeded inputs (tests/helpers.py:direct_cases): pins rows a1, c2-c5, parts of a5, b6,
+                      d1 and s1 for the oracle and the CUDA kernels on boxes where /root/reference does not exist.
 Usage: python tests/golden/make_golden.py
 """
 import hashlib
@@ -86,6 +90,16 @@ def oracle_golden():
     print("oracle_golden.npz", os.path.getsize(os.path.join(HERE, "oracle_golden.npz")))
 
 
+def direct_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_direct_lib() is not None, "oracle/_ref/libdirect_ref.so missing: run make -C oracle"
+    out = helpers.direct_outputs(orc, "ref")
+    np.savez_compressed(os.path.join(HERE, "direct_ref_golden.npz"), **out)
+    print("direct_ref_golden.npz", os.path.getsize(os.path.join(HERE, "direct_ref_golden.npz")))
+
+
 if __name__ == "__main__":
     fast_golden()
     oracle_golden()
+    direct_golden()

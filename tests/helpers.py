@@ -49,3 +49,66 @@ def gpu_align(ctx, pairs, gopt, priors=None, n_levels=5):
                             pk["T_imu_world_cur"], pk["n_features"], pk["px"], pk["f"], pk["depth"], pk["eligible"], gopt,
                             priors=priors)
     return res, ref, cur
+
+
+# ---- seeded cases for the rows pinned by the compiled reference (oracle/_ref/libdirect_ref.so) ------------------------------
+PYR_SHAPES = ((752, 480, 5), (640, 480, 4), (94, 60, 3), (47, 30, 2), (100, 75, 3), (33, 17, 2))
+N_ALIGN_CASES = 160
+
+
+def align_cases(seed=7, n=N_ALIGN_CASES):
+    """n seeded align2D / align1D problems on one synthetic 752x480 image: the 10x10 reference patch is cut at an integer
+    position of the same image and the start is displaced by up to 1.5 px (some cases sit at the image border so the
+    `break` paths run); affine flags and iteration counts vary."""
+    rng = np.random.default_rng(seed)
+    img = synth.make_image(seed)
+    cases = []
+    for i in range(n):
+        if i % 16 == 15:   # start closer than 4 px to the border -> immediate break, not converged
+            x, y = int(rng.integers(6, 740)), 6
+            px0 = (x + 0.3, 3.5)
+        else:
+            x, y = int(rng.integers(12, 740)), int(rng.integers(12, 468))
+            px0 = (x + rng.uniform(-1.5, 1.5), y + rng.uniform(-1.5, 1.5))
+        th = rng.uniform(0, 2 * np.pi)
+        cases.append(dict(pwb=img[y - 5:y + 5, x - 5:x + 5].copy(), px0=np.array(px0), dir=np.array([np.cos(th), np.sin(th)]),
+                          n_iter=(10, 10, 3, 30)[i % 4], est_offset=bool((i // 2) % 2 == 0), est_gain=bool(i % 8 == 5)))
+    return img, cases
+
+
+def direct_outputs(orc, which):
+    """Every pinned function evaluated through `which` ("orc" = the restatement, "ref" = the compiled reference)."""
+    import hashlib
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    out = {}
+    for w, h, nl in PYR_SHAPES:  # a1: pyramid bytes (752 -> SSE2 formula, 94/47/100/33 -> truncating mean, mixed chains)
+        img = synth.make_image(100 + w, w, h, n_rect=max(8, w * h // 400))
+        pyr = orc.create_img_pyramid(img, nl) if which == "orc" else orc.ref_create_img_pyramid(img, nl)
+        out[f"pyr_sha_{w}x{h}"] = np.array([sha(p) for p in pyr])
+    img, cases = align_cases()
+    a2 = np.zeros((len(cases), 3)); a1 = np.zeros((len(cases), 4))
+    for i, c in enumerate(cases):  # c3 / c4
+        ok, p = orc.align2d(img, c["pwb"], c["px0"], c["n_iter"], c["est_offset"], c["est_gain"], which=which)
+        a2[i] = (ok, p[0], p[1])
+        ok, p, hinv = orc.align1d(img, c["dir"], c["pwb"], c["px0"], c["n_iter"], c["est_offset"], c["est_gain"], which=which)
+        a1[i] = (ok, p[0], p[1], hinv)
+    out["align2d"], out["align1d"] = a2, a1
+    rng = np.random.default_rng(11)  # c2 / c5
+    xy = np.stack([rng.integers(0, 744, 400), rng.integers(0, 472, 400)], 1)
+    out["zmssd"] = np.stack([orc.zmssd(cases[k]["pwb"][1:9, 1:9], img, xy, which) for k in range(4)])
+    out["patch_from_border"] = np.stack([orc.patch_from_patch_with_border(cases[k]["pwb"], which) for k in range(4)])
+    err = np.concatenate([rng.normal(0, 3, 500), [0.0, 4.6851, -4.6851, 4.68509, 100.0]]).astype(np.float32)  # b6
+    out["tukey"] = orc.tukey_weight(err, which=which)
+    k = (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)  # s1: EuRoC cam0 radtan
+    pts = rng.uniform(-0.9, 0.9, (300, 2))
+    out["radtan_distort"] = orc.radtan(k, pts, "distort", which)
+    out["radtan_undistort"] = orc.radtan(k, pts, "undistort", which)
+    out["radtan_jacobian"] = orc.radtan(k, pts, "jacobian", which)
+    states = np.abs(rng.normal(0.5, 0.3, (50, 4))) + 1e-3  # d1: seed helpers
+    out["seed_helpers"] = np.stack([orc.seed_helpers(s, 1.0 / 1.5, (200.0, 500.0)[j % 2], 1.0 / s[0], 0.01 * (1 + j % 5), which)
+                                    for j, s in enumerate(states)])
+    gxy = np.stack([rng.integers(0, 752, 600), rng.integers(0, 480, 600)], 1).astype(np.int32)  # a5: cell index
+    lvl = rng.integers(0, 3, 600)
+    gxy = (gxy >> lvl[:, None]).astype(np.int32)
+    out["grid_cells"] = orc.grid_cell_index(30, 26, 16, gxy, (1 << lvl).astype(np.int32), which)
+    return out
