@@ -208,6 +208,36 @@ def ref_direct_lib():
     return _ref_direct
 
 
+_ref_frontend = None
+
+
+def ref_frontend_lib():
+    """The reference's own SparseImgAlign / Matcher / patch_warp / depth_filter code compiled against the shims
+    (oracle/_ref/libfrontend_ref.so; None if it was never built)."""
+    global _ref_frontend
+    if _ref_frontend is None:
+        so = os.path.join(_HERE, "_ref", "libfrontend_ref.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_compute_tau.restype = C.c_double
+        L.ref_px_error_angle.restype = C.c_double
+        L.ref_compute_tau.argtypes = [f64p, f64p, C.c_double, C.c_double]
+        L.ref_px_error_angle.argtypes = [C.POINTER(Frame), C.c_double]
+        L.ref_update_filter_vogiatzis.argtypes = [C.c_double, C.c_double, C.c_double, f64p]
+        L.ref_update_filter_gaussian.argtypes = [C.c_double, C.c_double, f64p]
+        L.ref_find_match_direct.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f64p, C.POINTER(Feature), C.c_double, f64p,
+                                            C.POINTER(MatcherOptions), C.POINTER(MatchOut)]
+        L.ref_find_epipolar_match_direct.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f64p, C.POINTER(Feature), C.c_double,
+                                                     C.c_double, C.c_double, C.POINTER(MatcherOptions), C.POINTER(MatchOut)]
+        L.ref_get_warp_matrix_affine.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f64p, f64p, C.c_double, f64p, C.c_int, f64p]
+        L.ref_update_seeds.argtypes = [C.POINTER(Frame), C.c_int, C.POINTER(Frame), f64p, C.c_int, C.POINTER(Feature), u8p, f64p,
+                                       C.c_double, C.POINTER(MatcherOptions), C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                       i32p, u8p]
+        _ref_frontend = L
+    return _ref_frontend
+
+
 def _u8(a):
     return a.ctypes.data_as(u8p)
 
@@ -536,3 +566,47 @@ def patch_from_patch_with_border(pwb, which="orc"):
     L, pre = _which(which)
     getattr(L, pre + "patch_from_patch_with_border")(_u8(pwb), 8, _u8(out))
     return out
+
+
+# ---- the compiled reference front-end (oracle/_ref/libfrontend_ref.so), same structs as the restatement ---------------------
+def ref_sparse_align(ref_frames, cur_frames, opt):
+    n = len(ref_frames)
+    R = (Frame * n)(*ref_frames)
+    Cc = (Frame * n)(*cur_frames)
+    res = AlignResult()
+    ref_frontend_lib().ref_sparse_align(n, R, Cc, C.byref(opt), C.byref(res))
+    return res
+
+
+def ref_find_match_direct_batch(ref, cur, T_cur_ref, ftrs, ref_depth, px_guess, opt):
+    M = len(ftrs)
+    out = (MatchOut * M)()
+    T = np.ascontiguousarray(T_cur_ref, np.float64)
+    L = ref_frontend_lib()
+    for i in range(M):
+        pg = np.ascontiguousarray(px_guess[i], np.float64)
+        L.ref_find_match_direct(C.byref(ref), C.byref(cur), _f64(T), C.byref(ftrs[i]), float(ref_depth[i]), _f64(pg), C.byref(opt), C.byref(out[i]))
+    return np.frombuffer(out, dtype=MATCH_OUT_NP).copy()
+
+
+def ref_find_epipolar_match_direct_batch(ref, cur, T_cur_ref, ftrs, d_inv3, opt):
+    M = len(ftrs)
+    out = (MatchOut * M)()
+    T = np.ascontiguousarray(T_cur_ref, np.float64)
+    L = ref_frontend_lib()
+    for i in range(M):
+        L.ref_find_epipolar_match_direct(C.byref(ref), C.byref(cur), _f64(T), C.byref(ftrs[i]), float(d_inv3[i][0]), float(d_inv3[i][1]),
+                                         float(d_inv3[i][2]), C.byref(opt), C.byref(out[i]))
+    return np.frombuffer(out, dtype=MATCH_OUT_NP).copy()
+
+
+def ref_update_seeds(ref, cur_frames, T_cur_ref, ftrs, types, states, mu_range, opt, sigma2_thresh=200.0, mappoint_thresh=500.0,
+                     check_visibility=1, check_convergence=0, use_vogiatzis=1):
+    n_obs, S = len(cur_frames), len(ftrs)
+    Cf = (Frame * n_obs)(*cur_frames)
+    T = np.ascontiguousarray(T_cur_ref, np.float64)
+    ok = np.zeros((n_obs, S), np.uint8)
+    n = ref_frontend_lib().ref_update_seeds(C.byref(ref), n_obs, Cf, _f64(T), S, ftrs, _u8(types), _f64(states), mu_range, C.byref(opt),
+                                            sigma2_thresh, mappoint_thresh, check_visibility, check_convergence, use_vogiatzis,
+                                            None, _u8(ok))
+    return n, ok

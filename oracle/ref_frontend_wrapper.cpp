@@ -1,0 +1,318 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// C wrapper around the REFERENCE's own SparseImgAlign, compiled from where it lies under /root/reference into
+// oracle/_ref/libfrontend_ref.so by oracle/Makefile:
+//   src/svo_img_align/src/sparse_img_align.cpp, sparse_img_align_base.cpp            (run, caches, residuals, H/g, update, prior)
+//   src/vikit/vikit_solver/include/vikit/solver/implementation/mini_least_squares_solver.hpp   (Gauss-Newton driver)
+//   src/vikit/vikit_solver/src/robust_cost.cpp                                         (Tukey weights)
+//   src/vikit/vikit_cameras/include/vikit/cameras/{camera_geometry*, pinhole_projection, radial_tangential_distortion}
+//   3rd/minkindr/include/kindr/minimal/*                                               (SE3 compose / inverse / exp / log)
+//   src/svo_direct/src/patch_warp.cpp                                                  (getWarpMatrixAffine, getBestSearchLevel, warpAffine)
+//   src/svo_direct/src/matcher.cpp, feature_alignment.cpp                              (findMatchDirect, findEpipolarMatchDirect, epipolar scans,
+//                                                                                       triangulation, align1D / align2D)
+//   src/svo_direct/src/depth_filter.cpp                                                (updateSeed, updateFilterVogiatzis / Gaussian, computeTau)
+// Eigen, OpenCV and glog resolve to the container-only stand-ins in oracle/shim (Eigen's LDLT / quaternion / small-matrix
+// arithmetic is restated there, see shim_eigen.hpp); svo::Frame / FrameBundle / Point are the reduced classes of
+// oracle/shim/svo_fake (same members, names and accessor semantics as the reference's). No reference source is copied here.
+// The structs are the oracle's own C API types, so tests feed the restatement and the compiled reference identically.
+#include <svo/img_align/sparse_img_align.h>
+#include <svo/direct/matcher.h>
+#include <svo/direct/patch_warp.h>
+#include <svo/direct/patch_score.h>
+#include <svo/direct/depth_filter.h>
+#include <svo/direct/feature_detection_utils.h>
+#include <svo/common/frame.h>
+#include <svo/common/camera.h>
+#include <cstring>
+#include "orc_capi.h"
+
+namespace {
+
+using svo::Transformation;
+
+Transformation toT(const double* a) {  // (qw qx qy qz tx ty tz)
+  return Transformation(svo::Quaternion(a[0], a[1], a[2], a[3]), Eigen::Vector3d(a[4], a[5], a[6]));
+}
+void fromT(const Transformation& T, double* a) {
+  const auto& q = T.getRotation().toImplementation();
+  a[0] = q.w(); a[1] = q.x(); a[2] = q.y(); a[3] = q.z();
+  a[4] = T.getPosition()[0]; a[5] = T.getPosition()[1]; a[6] = T.getPosition()[2];
+}
+
+svo::CameraPtr makeCamera(const orc_frame& f) {
+  using namespace vk::cameras;
+  if (f.distortion == 0) {
+    typedef PinholeProjection<NoDistortion> P;
+    return std::make_shared<CameraGeometry<P>>(f.width, f.height, P(f.cam[0], f.cam[1], f.cam[2], f.cam[3], NoDistortion()));
+  }
+  typedef PinholeProjection<RadialTangentialDistortion> P;
+  return std::make_shared<CameraGeometry<P>>(f.width, f.height,
+                                             P(f.cam[0], f.cam[1], f.cam[2], f.cam[3], RadialTangentialDistortion(f.cam[4], f.cam[5], f.cam[6], f.cam[7])));
+}
+
+svo::FramePtr makeFrame(const orc_frame& f) {
+  auto fr = std::make_shared<svo::Frame>();
+  fr->cam_ = makeCamera(f);
+  for (int l = 0; l < f.n_levels; ++l)
+    fr->img_pyr_.emplace_back(f.level_rows[l], f.level_cols[l], CV_8UC1, const_cast<uint8_t*>(f.level_data[l]), (size_t)f.level_step[l]);
+  fr->set_T_cam_imu(toT(f.T_cam_imu));
+  fr->T_f_w_ = fr->T_cam_imu() * toT(f.T_imu_world);
+  const int n = f.px ? f.n_features : 0;
+  fr->resizeFeatureStorage(n);
+  fr->num_features_ = n;
+  const Transformation T_world_cam = fr->T_world_cam();
+  for (int i = 0; i < n; ++i) {
+    fr->px_vec_.col(i) = Eigen::Vector2d(f.px[2 * i], f.px[2 * i + 1]);
+    const Eigen::Vector3d bearing(f.f[3 * i], f.f[3 * i + 1], f.f[3 * i + 2]);
+    fr->f_vec_.col(i) = bearing;
+    fr->type_vec_[i] = svo::FeatureType::kCorner;
+    // the reference reads the depth back as |landmark - camera centre| (sparse_img_align.cpp:283-286)
+    if (f.eligible[i]) fr->landmark_vec_[i] = std::make_shared<svo::Point>(T_world_cam * Eigen::Vector3d(bearing * f.depth[i]));
+  }
+  return fr;
+}
+
+struct Probe : public svo::SparseImgAlign {  // read access to the solver's protected counters
+  using svo::SparseImgAlign::SparseImgAlign;
+  size_t lastIter() const { return iter_; }
+  bool stopped() const { return stop_; }
+};
+
+}  // namespace
+
+extern "C" int ref_sparse_align(int n_cams, const orc_frame* ref, const orc_frame* cur, const orc_align_options* o, orc_align_result* res) {
+  std::vector<svo::FramePtr> rf, cf;
+  for (int c = 0; c < n_cams; ++c) { rf.push_back(makeFrame(ref[c])); cf.push_back(makeFrame(cur[c])); }
+  auto rb = std::make_shared<svo::FrameBundle>(rf), cb = std::make_shared<svo::FrameBundle>(cf);
+  svo::SparseImgAlignOptions opt;
+  opt.max_level = o->max_level; opt.min_level = o->min_level;
+  opt.estimate_illumination_gain = o->estimate_illumination_gain != 0;
+  opt.estimate_illumination_offset = o->estimate_illumination_offset != 0;
+  opt.use_distortion_jacobian = o->use_distortion_jacobian != 0;
+  opt.robustification = o->robustification != 0;
+  opt.weight_scale = o->weight_scale;
+  svo::SparseImgAlignBase::SolverOptions so = svo::SparseImgAlignBase::getDefaultSolverOptions();
+  so.max_iter = o->max_iter;
+  so.eps = o->eps;
+  Probe aligner(so, opt);
+  aligner.reset();  // callers always reset() first (frame_handler_base.cpp:621)
+  aligner.setAlphaInitialValue(o->alpha_init);
+  aligner.setBetaInitialValue(o->beta_init);
+  if (o->have_prior)
+    aligner.setWeightedPrior(toT(o->prior_T), o->prior_alpha, o->prior_beta, o->lambda_rot, o->lambda_trans, o->lambda_alpha, o->lambda_beta);
+  std::memset(res, 0, sizeof(*res));
+  res->n_tracked = (int)aligner.run(rb, cb);
+  // T_f_w_ = T_cam_imu * T_icur_iref * T_iref_world  (sparse_img_align.cpp:102-106)
+  const Transformation T_icur_iref = cf[0]->T_imu_cam() * cf[0]->T_f_w_ * rf[0]->T_imu_world().inverse();
+  fromT(T_icur_iref, res->T_icur_iref);
+  for (int c = 0; c < n_cams; ++c) fromT(cf[c]->T_f_w_, res->T_f_w[c]);
+  res->chi2 = aligner.getError();
+  const auto& H = aligner.getHessian();
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) res->H[8 * i + j] = H(i, j);
+  res->stop = aligner.stopped() ? 1 : 0;
+  return res->n_tracked;
+}
+
+// ---- (c) matcher ----------------------------------------------------------------------------------------------------------
+namespace {
+
+// The oracle's C API hands T_cur_ref over explicitly; the reference derives it from the frames' poses
+// (T_cur_ref = cur.T_f_w_ * ref.T_f_w_^-1, matcher.cpp:41, :166), so the ref frame sits at the identity.
+void poseFrames(svo::Frame& rf, svo::Frame& cf, const double* T_cur_ref) {
+  rf.T_f_w_ = Transformation();
+  cf.T_f_w_ = toT(T_cur_ref);
+}
+void setOptions(svo::Matcher& m, const orc_matcher_options* o) {
+  m.options_.align_1d = o->align_1d != 0;
+  m.options_.align_max_iter = o->align_max_iter;
+  m.options_.max_epi_search_steps = o->max_epi_search_steps;
+  m.options_.subpix_refinement = o->subpix_refinement != 0;
+  m.options_.epi_search_edgelet_filtering = o->epi_search_edgelet_filtering != 0;
+  m.options_.scan_on_unit_sphere = o->scan_on_unit_sphere != 0;
+  m.options_.epi_search_edgelet_max_angle = o->epi_search_edgelet_max_angle;
+  m.options_.affine_est_offset_ = o->affine_est_offset != 0;
+  m.options_.affine_est_gain_ = o->affine_est_gain != 0;
+  m.options_.max_patch_diff_ratio = o->max_patch_diff_ratio;
+}
+void fillOut(const svo::Matcher& m, svo::Matcher::MatchResult r, double depth, orc_match_out* out) {
+  out->result = int(r);
+  out->px_cur[0] = m.px_cur_[0]; out->px_cur[1] = m.px_cur_[1];
+  out->f_cur[0] = m.f_cur_[0]; out->f_cur[1] = m.f_cur_[1]; out->f_cur[2] = m.f_cur_[2];
+  out->search_level = m.search_level_;
+  out->A_cur_ref[0] = m.A_cur_ref_(0, 0); out->A_cur_ref[1] = m.A_cur_ref_(0, 1);
+  out->A_cur_ref[2] = m.A_cur_ref_(1, 0); out->A_cur_ref[3] = m.A_cur_ref_(1, 1);
+  out->h_inv = m.h_inv_;
+  out->epi_length_pyramid = m.epi_length_pyramid_;
+  out->reject = m.reject_;
+  out->depth = depth;
+  std::memcpy(out->patch_with_border, m.patch_with_border_, 100);
+}
+// a one-feature frame around the reference feature (FeatureWrapper binds to the frame's SoA columns)
+void setFeature(svo::Frame& rf, const orc_feature* f) {
+  rf.resizeFeatureStorage(1);
+  rf.num_features_ = 1;
+  rf.px_vec_.col(0) = Eigen::Vector2d(f->px[0], f->px[1]);
+  rf.f_vec_.col(0) = Eigen::Vector3d(f->f[0], f->f[1], f->f[2]);
+  rf.grad_vec_.col(0) = Eigen::Vector2d(f->grad[0], f->grad[1]);
+  rf.type_vec_[0] = static_cast<svo::FeatureType>(f->type);
+  rf.level_vec_(0) = f->level;
+}
+void initMatcher(svo::Matcher& m) {  // the members the reference leaves uninitialised are reported as zeros
+  std::memset(m.patch_, 0, sizeof(m.patch_));
+  std::memset(m.patch_with_border_, 0, sizeof(m.patch_with_border_));
+  m.A_cur_ref_.setZero(); m.epi_image_.setZero(); m.px_cur_.setZero(); m.f_cur_.setZero();
+  m.epi_length_pyramid_ = 0; m.h_inv_ = 0; m.search_level_ = 0; m.reject_ = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_find_match_direct(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], const orc_feature* ftr,
+                          double ref_depth, const double px_cur_in[2], const orc_matcher_options* opt, orc_match_out* out) {
+  svo::FramePtr rf = makeFrame(*ref), cf = makeFrame(*cur);
+  poseFrames(*rf, *cf, T_cur_ref);
+  setFeature(*rf, ftr);
+  svo::Matcher m;
+  initMatcher(m);
+  setOptions(m, opt);
+  svo::Keypoint px(px_cur_in[0], px_cur_in[1]);
+  m.px_cur_ = px;
+  svo::FeatureWrapper fw = rf->getFeatureWrapper(0);
+  const svo::Matcher::MatchResult r = m.findMatchDirect(*rf, *cf, fw, ref_depth, px);
+  fillOut(m, r, 0.0, out);
+  return int(r);
+}
+
+int ref_find_epipolar_match_direct(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], const orc_feature* ftr,
+                                   double d_estimate_inv, double d_min_inv, double d_max_inv, const orc_matcher_options* opt,
+                                   orc_match_out* out) {
+  svo::FramePtr rf = makeFrame(*ref), cf = makeFrame(*cur);
+  poseFrames(*rf, *cf, T_cur_ref);
+  setFeature(*rf, ftr);
+  svo::Matcher m;
+  initMatcher(m);
+  setOptions(m, opt);
+  double depth = 0.0;
+  svo::FeatureWrapper fw = rf->getFeatureWrapper(0);
+  const svo::Matcher::MatchResult r = m.findEpipolarMatchDirect(*rf, *cf, toT(T_cur_ref), fw, d_estimate_inv, d_min_inv, d_max_inv, depth);
+  fillOut(m, r, depth, out);
+  return int(r);
+}
+
+void ref_get_warp_matrix_affine(const orc_frame* ref, const orc_frame* cur, const double px_ref[2], const double f_ref[3],
+                                double depth_ref, const double T_cur_ref[7], int level_ref, double A_out[4]) {
+  svo::CameraPtr cr = makeCamera(*ref), cc = makeCamera(*cur);
+  svo::Keypoint px(px_ref[0], px_ref[1]);
+  svo::BearingVector f(f_ref[0], f_ref[1], f_ref[2]);
+  svo::warp::AffineTransformation2 A;
+  svo::warp::getWarpMatrixAffine(cr, cc, px, f, depth_ref, toT(T_cur_ref), level_ref, &A);
+  A_out[0] = A(0, 0); A_out[1] = A(0, 1); A_out[2] = A(1, 0); A_out[3] = A(1, 1);
+}
+
+int ref_get_best_search_level(const double A[4], int max_level) {
+  svo::warp::AffineTransformation2 M;
+  M << A[0], A[1], A[2], A[3];
+  return svo::warp::getBestSearchLevel(M, max_level);
+}
+
+int ref_warp_affine(const double A_cur_ref[4], const uint8_t* img, int cols, int rows, int step, const double px_ref[2],
+                    int level_ref, int search_level, int halfpatch_size, uint8_t* patch) {
+  svo::warp::AffineTransformation2 M;
+  M << A_cur_ref[0], A_cur_ref[1], A_cur_ref[2], A_cur_ref[3];
+  cv::Mat im(rows, cols, CV_8UC1, const_cast<uint8_t*>(img), (size_t)step);
+  svo::Keypoint px(px_ref[0], px_ref[1]);
+  return svo::warp::warpAffine(M, im, px, level_ref, search_level, halfpatch_size, patch) ? 1 : 0;
+}
+
+}  // extern "C"
+
+// ---- (d) depth filter -----------------------------------------------------------------------------------------------------
+// DepthFilter's constructor names the detector factory; the checker never builds a detector through it.
+namespace svo { namespace feature_detection_utils {
+AbstractDetectorPtr makeDetector(const DetectorOptions&, const CameraPtr&) { std::abort(); }
+} }
+
+extern "C" {
+
+int ref_update_filter_vogiatzis(double z, double tau2, double mu_range, double state[4]) {
+  svo::SeedState s;
+  s << state[0], state[1], state[2], state[3];
+  bool ok;
+  {
+    Eigen::Ref<svo::SeedState> r(s);
+    ok = svo::depth_filter_utils::updateFilterVogiatzis(z, tau2, mu_range, r);
+  }
+  for (int i = 0; i < 4; ++i) state[i] = s[i];
+  return ok ? 1 : 0;
+}
+
+int ref_update_filter_gaussian(double z, double tau2, double state[4]) {
+  svo::SeedState s;
+  s << state[0], state[1], state[2], state[3];
+  bool ok;
+  {
+    Eigen::Ref<svo::SeedState> r(s);
+    ok = svo::depth_filter_utils::updateFilterGaussian(z, tau2, r);
+  }
+  for (int i = 0; i < 4; ++i) state[i] = s[i];
+  return ok ? 1 : 0;
+}
+
+double ref_compute_tau(const double T_ref_cur[7], const double f[3], double z, double px_error_angle) {
+  return svo::depth_filter_utils::computeTau(toT(T_ref_cur), svo::BearingVector(f[0], f[1], f[2]), z, px_error_angle);
+}
+
+double ref_px_error_angle(const orc_frame* frame, double px_noise) { return makeCamera(*frame)->getAngleError(px_noise); }
+
+// S seeds of one ref frame observed, in order, by n_obs cur frames (same contract as orc_update_seeds). The reference keeps
+// px_error_angle in a function-local static initialised from the first camera it sees (depth_filter.cpp:383-384): every call
+// of one process must therefore use the same camera intrinsics.
+int ref_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frames, const double* T_cur_ref, int S,
+                     const orc_feature* ftrs, uint8_t* types, double* states, double seed_mu_range,
+                     const orc_matcher_options* opt, double sigma2_convergence_threshold,
+                     double mappoint_sigma2_convergence_threshold, int check_visibility, int check_convergence,
+                     int use_vogiatzis, int* match_results, uint8_t* success) {
+  svo::FramePtr rf = makeFrame(*ref);
+  rf->id_ = 0;
+  rf->T_f_w_ = Transformation();
+  rf->resizeFeatureStorage(S);
+  rf->num_features_ = S;
+  rf->seed_mu_range_ = seed_mu_range;
+  for (int s = 0; s < S; ++s) {
+    rf->px_vec_.col(s) = Eigen::Vector2d(ftrs[s].px[0], ftrs[s].px[1]);
+    rf->f_vec_.col(s) = Eigen::Vector3d(ftrs[s].f[0], ftrs[s].f[1], ftrs[s].f[2]);
+    rf->grad_vec_.col(s) = Eigen::Vector2d(ftrs[s].grad[0], ftrs[s].grad[1]);
+    rf->level_vec_(s) = ftrs[s].level;
+    rf->type_vec_[s] = static_cast<svo::FeatureType>(types[s]);
+    for (int k = 0; k < 4; ++k) rf->invmu_sigma2_a_b_vec_(k, s) = states[4 * s + k];
+  }
+  std::vector<svo::FramePtr> cfs;
+  for (int o = 0; o < n_obs; ++o) {
+    cfs.push_back(makeFrame(cur_frames[o]));
+    cfs.back()->id_ = o + 1;
+    cfs.back()->T_f_w_ = toT(T_cur_ref + 7 * o);
+  }
+  int n_success = 0;
+  for (int s = 0; s < S; ++s) {
+    svo::Matcher m;
+    initMatcher(m);
+    setOptions(m, opt);
+    for (int o = 0; o < n_obs; ++o) {
+      // DepthFilter::updateSeeds picks the threshold by seed type (depth_filter.cpp:214-221)
+      const svo::FeatureType type = rf->type_vec_[s];
+      const double thresh = svo::isMapPointSeed(type) ? mappoint_sigma2_convergence_threshold : sigma2_convergence_threshold;
+      const bool ok = svo::depth_filter_utils::updateSeed(*cfs[o], *rf, (size_t)s, m, thresh, check_visibility != 0,
+                                                          check_convergence != 0, use_vogiatzis != 0);
+      if (success) success[(size_t)o * S + s] = ok;
+      (void)match_results;
+      if (ok) ++n_success;
+    }
+  }
+  for (int s = 0; s < S; ++s) {
+    types[s] = static_cast<uint8_t>(rf->type_vec_[s]);
+    for (int k = 0; k < 4; ++k) states[4 * s + k] = rf->invmu_sigma2_a_b_vec_(k, s);
+  }
+  return n_success;
+}
+
+}  // extern "C"

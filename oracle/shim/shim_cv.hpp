@@ -113,6 +113,7 @@ class Mat {
     step.p[0] = stp ? stp : (size_t)c * elemSize();
   }
   Mat(const Mat& m, const Rect& roi);  // declared only
+  Mat(Size s, int type, const Scalar& fill);  // declared only
   void create(int r, int c, int type) {
     if (data && r == rows && c == cols && type == this->type() && owner_) return;
     flags = type; dims = 2; rows = r; cols = c;
@@ -173,5 +174,6 @@ void imshow(const std::string& name, const Mat& m);
 int waitKey(int delay = 0);
 void namedWindow(const std::string& name, int flags = 1);
 void split(const Mat& src, std::vector<Mat>& mv);
+void merge(const std::vector<Mat>& mv, Mat& dst);
 
 }  // namespace cv

@@ -1,0 +1,21 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): the few vikit/math_utils.h helpers the direct front-end uses (the reference header
+// also declares Lie-group utilities whose bodies need more of Eigen than the stand-in provides).
+#pragma once
+#include <cmath>
+#include <Eigen/Core>
+#include <kindr/minimal/quat-transformation.h>
+namespace vk {
+Eigen::Matrix3d skew(const Eigen::Vector3d& v);
+// vikit/math_utils.h:143-153
+inline Eigen::Vector2d project2(const Eigen::Vector3d& v) { return v.head<2>() / v(2); }
+inline Eigen::Vector3d unproject2d(const Eigen::Vector2d& v) { return Eigen::Vector3d(v[0], v[1], 1.0); }
+// vikit/math_utils.h:186-194
+template <class T> inline T normPdf(const T x, const T mean, const T sigma) {
+  T exponent = x - mean;
+  exponent *= -exponent;
+  exponent /= 2 * sigma * sigma;
+  T result = std::exp(exponent);
+  result /= sigma * std::sqrt(2 * M_PI);
+  return result;
+}
+}  // namespace vk

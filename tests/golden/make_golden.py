@@ -10,6 +10,9 @@ direct_ref_golden.npz outputs of the REFERENCE's own halfSample / align1D / alig
                       (oracle/_ref/libdirect_ref.so, compiled from /root/reference against the container-only shims in
                       oracle/shim) on seeded inputs (tests/helpers.py:direct_cases): pins rows a1, c2-c5, parts of a5, b6,
                       d1 and s1 for the oracle and the CUDA kernels on boxes where /root/reference does not exist.
+frontend_ref_golden.npz outputs of the REFERENCE's own SparseImgAlign::run, Matcher::findMatchDirect / findEpipolarMatchDirect and
+                      depth_filter_utils::updateSeed (oracle/_ref/libfrontend_ref.so: the reference sources compiled against
+                      oracle/shim) on seeded inputs (tests/helpers.py:frontend_outputs): pins rows b, c1, c6-c7, d1-d3.
 Usage: python tests/golden/make_golden.py
 """
 import hashlib
@@ -99,7 +102,17 @@ def direct_golden():
     print("direct_ref_golden.npz", os.path.getsize(os.path.join(HERE, "direct_ref_golden.npz")))
 
 
+def frontend_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_frontend_lib() is not None, "oracle/_ref/libfrontend_ref.so missing: run make -C oracle"
+    out = helpers.frontend_outputs(orc, "ref")
+    np.savez_compressed(os.path.join(HERE, "frontend_ref_golden.npz"), **out)
+    print("frontend_ref_golden.npz", os.path.getsize(os.path.join(HERE, "frontend_ref_golden.npz")))
+
+
 if __name__ == "__main__":
+    frontend_golden()
     fast_golden()
     oracle_golden()
     direct_golden()

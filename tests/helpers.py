@@ -112,3 +112,97 @@ def direct_outputs(orc, which):
     gxy = (gxy >> lvl[:, None]).astype(np.int32)
     out["grid_cells"] = orc.grid_cell_index(30, 26, 16, gxy, (1 << lvl).astype(np.int32), which)
     return out
+
+
+# ---- rows b / c1 / c6-c7 / d1-d3 through the restatement ("orc") or the compiled reference front-end ("ref") ---------------
+ALIGN_OPTION_SETS = (dict(), dict(estimate_illumination_gain=1, estimate_illumination_offset=1), dict(robustification=1),
+                     dict(estimate_illumination_gain=1, estimate_illumination_offset=1, robustification=1),
+                     dict(max_level=4, min_level=2, max_iter=5), dict(alpha_init=0.02, beta_init=-1.5))
+
+
+def stereo_case(seed=81):
+    """Two-camera bundle (11 cm baseline) around synth.make_align_pair(seed): per-camera images, features and T_cam_imu."""
+    d = synth.make_align_pair(seed)
+    T_c1_c0 = synth.se3_exp_small(np.zeros(3), np.array([-0.11, 0.0, 0.0]))
+    scene = d["scene"]
+    ref1 = scene.render(T_c1_c0)
+    cur1 = scene.render(synth.se3_mul(T_c1_c0, d["T_cur_ref_gt"]))
+    px1 = synth.pick_features(ref1, 150, 5)
+    f1 = synth.cam_backproject(d["cam"], px1)
+    R01, t01 = synth.se3_to_Rt(synth.se3_inv(T_c1_c0))
+    lam = (scene.d - scene.n @ t01) / ((f1 @ R01.T) @ scene.n)
+    X1 = f1 * lam[:, None]
+    depth1 = np.linalg.norm(X1, axis=1)
+    return d, dict(ref_img=ref1, cur_img=cur1, px=px1, f=X1 / depth1[:, None], depth=depth1, T_cam_imu=synth.se3_mul(T_c1_c0, d["T_cam_imu"]))
+
+
+def _align_arrays(r):
+    return np.concatenate([np.array(r.T_icur_iref), [r.alpha if hasattr(r, "alpha") else 0.0, r.beta if hasattr(r, "beta") else 0.0, r.chi2,
+                                                    r.n_tracked]]), np.array(r.H), np.array([list(t) for t in r.T_f_w])
+
+
+def frontend_outputs(orc, which):
+    align = orc.sparse_align if which == "orc" else orc.ref_sparse_align
+    fmd = (lambda *a: orc.find_match_direct_batch(*a, n_threads=8)) if which == "orc" else orc.ref_find_match_direct_batch
+    epi = (lambda *a: orc.find_epipolar_match_direct_batch(*a, n_threads=8)) if which == "orc" else orc.ref_find_epipolar_match_direct_batch
+    out, keep = {}, []
+    # b: SparseImgAlign::run, mono, every option set; radtan camera with the distortion Jacobian; weighted prior; stereo bundle
+    rows, Hs = [], []
+    for seed in (1, 2, 3):
+        d = synth.make_align_pair(seed)
+        rp, cp = orc.create_img_pyramid(d["ref_img"], 5), orc.create_img_pyramid(d["cur_img"], 5)
+        rf = orc.make_frame(rp, d["cam"], d["T_cam_imu"], d["T_imu_world_ref"], d["px"], d["f"], d["depth"], d["eligible"], keep=keep)
+        cf = orc.make_frame(cp, d["cam"], d["T_cam_imu"], d["T_imu_world_cur_init"], keep=keep)
+        for kw in ALIGN_OPTION_SETS:
+            a, H, _ = _align_arrays(align([rf], [cf], orc.default_align_options(**kw)))
+            rows.append(a); Hs.append(H)
+        o = orc.default_align_options(lambda_rot=0.5, lambda_trans=0.1)
+        o.have_prior = 1
+        o.prior_T[:] = list(synth.se3_mul(d["T_icur_iref_gt"], synth.se3_exp_small(np.array([1e-3, -2e-3, 1e-3]), np.array([2e-3, 0, -1e-3]))))
+        a, H, _ = _align_arrays(align([rf], [cf], o))
+        rows.append(a); Hs.append(H)
+    d = synth.make_align_pair(5, cam=synth.EUROC_CAM_RADTAN)
+    rf = orc.make_frame(orc.create_img_pyramid(d["ref_img"], 5), d["cam"], d["T_cam_imu"], d["T_imu_world_ref"], d["px"], d["f"], d["depth"], d["eligible"], keep=keep)
+    cf = orc.make_frame(orc.create_img_pyramid(d["cur_img"], 5), d["cam"], d["T_cam_imu"], d["T_imu_world_cur_init"], keep=keep)
+    for kw in (dict(), dict(use_distortion_jacobian=1)):
+        a, H, _ = _align_arrays(align([rf], [cf], orc.default_align_options(**kw)))
+        rows.append(a); Hs.append(H)
+    out["align_rows"], out["align_H"] = np.array(rows), np.array(Hs)
+    d0, c1 = stereo_case()
+    rfs = [orc.make_frame(orc.create_img_pyramid(d0["ref_img"], 5), d0["cam"], d0["T_cam_imu"], d0["T_imu_world_ref"], d0["px"], d0["f"], d0["depth"], keep=keep),
+           orc.make_frame(orc.create_img_pyramid(c1["ref_img"], 5), d0["cam"], c1["T_cam_imu"], d0["T_imu_world_ref"], c1["px"], c1["f"], c1["depth"], keep=keep)]
+    cfs = [orc.make_frame(orc.create_img_pyramid(d0["cur_img"], 5), d0["cam"], d0["T_cam_imu"], d0["T_imu_world_cur_init"], keep=keep),
+           orc.make_frame(orc.create_img_pyramid(c1["cur_img"], 5), d0["cam"], c1["T_cam_imu"], d0["T_imu_world_cur_init"], keep=keep)]
+    a, H, Tfw = _align_arrays(align(rfs, cfs, orc.default_align_options(estimate_illumination_gain=1, estimate_illumination_offset=1)))
+    out["stereo_row"], out["stereo_T_f_w"] = a, Tfw[:2]
+    # c: findMatchDirect / findEpipolarMatchDirect
+    ms = synth.make_match_set(7, n_features=240)
+    ms["px"][:8] = np.array([[3.0, 3.0]]) + np.arange(8)[:, None] * 0.25   # kFailVisibility
+    ms["depth"][8:16] = 0.05                                              # warp / alignment failures
+    rf = orc.make_frame(orc.create_img_pyramid(ms["ref_img"], 5), ms["cam"], keep=keep)
+    cf = orc.make_frame(orc.create_img_pyramid(ms["cur_img"], 5), ms["cam"], keep=keep)
+    oft = orc.make_features(ms["px"], ms["f"], ms["grad"], ms["type"], ms["level"])
+    fields = ("result", "px_cur", "f_cur", "search_level", "A_cur_ref", "h_inv", "epi_length_pyramid", "depth", "patch_with_border")
+    for name, kw in (("default", dict()), ("gain", dict(affine_est_gain=1))):
+        r = fmd(rf, cf, ms["T_cur_ref"], oft, ms["depth"], ms["px_guess"], orc.default_matcher_options(**kw))
+        for k in fields:
+            out[f"fmd_{name}_{k}"] = r[k]
+    d_inv = 1.0 / ms["depth"]
+    d3 = np.stack([d_inv * np.random.default_rng(1).uniform(0.9, 1.1, len(d_inv)), d_inv * 1.5, d_inv * 0.6], 1)
+    for name, kw in (("sphere", dict()), ("plane", dict(scan_on_unit_sphere=0)), ("a1d", dict(align_1d=1)), ("nosub", dict(subpix_refinement=0))):
+        r = epi(rf, cf, ms["T_cur_ref"], oft, d3, orc.default_matcher_options(**kw))
+        for k in fields:
+            out[f"epi_{name}_{k}"] = r[k]
+    # d: updateSeed chain over ordered observations
+    sq = synth.make_seed_sequence(17, n_seeds=160, n_obs=6)
+    rf = orc.make_frame(orc.create_img_pyramid(sq["ref_img"], 5), sq["cam"], keep=keep)
+    cfs = [orc.make_frame(orc.create_img_pyramid(im, 5), sq["cam"], keep=keep) for im in sq["cur_imgs"]]
+    oft = orc.make_features(sq["px"], sq["f"], sq["grad"], sq["type"].astype(np.int32), sq["level"])
+    for name, kw in (("vog", dict()), ("gauss", dict(use_vogiatzis=0)), ("conv", dict(check_convergence=1, sigma2_thresh=50.0))):
+        t, s = sq["type"].copy(), sq["state"].copy()
+        if which == "orc":
+            n, _, ok = orc.update_seeds(rf, cfs, sq["T_cur_ref"], oft, t, s, sq["mu_range"], orc.default_matcher_options(), **kw)
+        else:
+            n, ok = orc.ref_update_seeds(rf, cfs, sq["T_cur_ref"], oft, t, s, sq["mu_range"], orc.default_matcher_options(), **kw)
+        out[f"seeds_{name}_types"], out[f"seeds_{name}_state"], out[f"seeds_{name}_ok"], out[f"seeds_{name}_n"] = t, s, ok, np.array(n)
+    return out
