@@ -37,6 +37,9 @@ struct svo_cuda_pyr {
   int cols[SVO_MAX_LEVELS] = {0}, rows[SVO_MAX_LEVELS] = {0};
   size_t pitch[SVO_MAX_LEVELS] = {0}, frame_stride[SVO_MAX_LEVELS] = {0};
   uint8_t* data[SVO_MAX_LEVELS] = {nullptr};
+  // TMA descriptors (CUtensorMap, 128 opaque bytes) of the levels the pyramid kernel has read so far; built on first use
+  alignas(64) unsigned char tmap[SVO_MAX_LEVELS][128] = {};
+  bool tmap_ready[SVO_MAX_LEVELS] = {false};
 };
 
 // POD view of a pyramid batch passed to kernels by value.
