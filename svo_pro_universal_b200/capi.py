@@ -122,7 +122,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise SvoCudaError("libsvo_cuda.so is missing: build it with `make -C svo_pro_universal_b200/csrc` "
                                "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("SVO_CUDA_LIB", LIB_PATH))  # the override is for A/B experiments with alternative builds
         L.svo_cuda_last_error.restype = C.c_char_p
         L.svo_cuda_last_error.argtypes = [C.c_void_p]
         L.svo_cuda_launch_count.restype = C.c_longlong

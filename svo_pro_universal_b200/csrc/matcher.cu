@@ -47,7 +47,8 @@ SVO_D void writeOut(const Group& g, svo_match_out* out, int i, const MatchState&
 
 // mode 0: findMatchDirect, 1: findEpipolarMatchDirect, 2: warp only
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) match_kernel(const MatchParams P) {
+// 126 registers, 4 CTAs/SM: fastest of 4/5/6 on the B200 (1.58 / 2.94 ms for 512 k features)
+__global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P) {
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
   const Group g = makeGroup();
   const int gi = threadIdx.x / kGroup;
