@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 W, H, N_LEVELS, N_FEATURES = 752, 480, 5, 180
 # per frame pair, mono, levels 4->1: ref L1-L4 + cur L1-L4 (2 x 119,850 B) + 180 x 40 B features + 2 x 72 B state
 ALGO_BYTES_PER_PAIR = 247044
+# dram__bytes_read.sum + dram__bytes_write.sum of one sparse_align_kernel launch over 1184 pairs, ncu --set full
+# (profiles/r01b_current.md: 212.04 MB + 4.135 MB) -> bytes per pair; per launch = this x pairs per launch
+NCU_DRAM_BYTES_PER_PAIR = (212.04e6 + 4.135e6) / 1184
 METRIC = "aligned frame-pairs/sec (752x480, 4-level SparseImgAlign, ~180 features)"
 
 
@@ -268,7 +271,6 @@ def run_ours(args):
     launches = ctx.launches - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     align_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: host buffers through the C ABI ----
@@ -284,6 +286,7 @@ def run_ours(args):
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     e2e_wall = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * B * args.steps / (max(e2e_ms, e2e_wall) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None  # sampled from the start of the device-resident leg to the end of the e2e leg
     h2d = int(h_cur.numel() + sum(v.numel() * v.element_size() for v in h.values()))
     d2h = int(h_res.numel())
 
@@ -318,6 +321,29 @@ def run_ours(args):
         if i >= 20:
             lat.append(t_end - t); lat_align.append(t_end - t_mid)
 
+    # launch-latency breakdown of the single-frame call: device time of every stage (CUDA events on the launching stream)
+    # next to the host wall clock of the whole call; the gap is launch + staging + synchronisation overhead
+    d1 = {k: v[:1].to(dev) for k, v in h1.items()}
+    d1_res = torch.zeros(capi.ALIGN_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    stage_us = {"h2d_image": [], "pyramid_kernel": [], "align_kernel": [], "d2h_result": []}
+    for i in range(60):
+        evs[0].record(stream)
+        cur1.upload(h1_img)
+        evs[1].record(stream)
+        cur1.build()
+        evs[2].record(stream)
+        capi.sparse_align(ctx, [ref1], [cur1], [cam], pk["T_cam_imu"], d1["T_imu_world_ref"], d1["T_imu_world_cur"], d1["n_features"],
+                          d1["px"], d1["f"], d1["depth"], d1["eligible"], gopt, results=d1_res)
+        evs[3].record(stream)
+        h1_res.copy_(d1_res, non_blocking=True)
+        evs[4].record(stream)
+        ctx.synchronize(); torch.cuda.synchronize()
+        if i >= 10:
+            for k, (a, b) in zip(stage_us, zip(evs[:-1], evs[1:])):
+                stage_us[k].append(1e3 * a.elapsed_time(b))
+    breakdown = {k: float(np.median(v)) for k, v in stage_us.items()}
+
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----
     n_threads = os.cpu_count() or 1
     per_step = max(64, 16 * n_threads)
@@ -351,15 +377,18 @@ def run_ours(args):
                 "note": "new frames' level-0 images + feature arrays H2D from pinned memory, results D2H, every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "sparse_align_kernel<false>", "kernel_ms": align_ms,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PAIR * B,
+                     "traffic_note": "ncu dram bytes of one 1184-pair launch scaled to this launch's pairs (profiles/)",
+                     "kernel": "sparse_align_kernel<ILL=0, ROBUST=0, DJ=0, SLOTS=180>", "kernel_ms": align_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                     "note": "algorithmic bytes 247,044 B/pair; the kernel is FP64-issue/latency bound, not HBM bound (DESIGN.md)"},
+                     "note": "algorithmic bytes 247,044 B/pair; the kernel is FP64-issue / latency bound, not HBM bound: 28 % of its FP64-pipe bound (DESIGN.md 4b)"},
         "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": n_threads, "kind": "port", "sample": sample + ", ~10 s",
                          "latency_ms_p50_single_thread": 1e3 * float(np.median(cl))},
         "latency": {"p50_ms_pair_e2e": 1e3 * float(np.median(lat)), "p95_ms_pair_e2e": 1e3 * float(np.percentile(lat, 95)),
                     "p50_ms_align_call": 1e3 * float(np.median(lat_align)),
-                    "note": "B=1 through the host-buffer C ABI: image H2D + pyramid + align + result D2H"},
+                    "device_us_p50": breakdown,
+                    "note": "B=1 through the host-buffer C ABI: image H2D + pyramid + align + result D2H; device_us_p50 = CUDA-event "
+                            "time of each stage of one single-frame call (the rest of p50_ms_pair_e2e is launch, staging and sync overhead)"},
     }
     print(json.dumps(out))
     if world > 1:

@@ -220,6 +220,13 @@ int svo_cuda_align2d(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const int* fram
 int svo_cuda_align1d(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const int* frame_idx, const int* level, int M,
                      const double* dir, const uint8_t* patch_with_border, int n_iter, int affine_est_offset,
                      int affine_est_gain, double* px, double* h_inv, uint8_t* converged, svo_mem mem);
+/* feature_alignment::alignPyr2D / alignPyr2DVec (feature_alignment.h:57-80; .cpp:731-973): pyramidal KLT of M features from
+ * (ref frame ref_frame_idx[i]) into (cur frame cur_frame_idx[i]); px_ref_level_0 int [M][2]; px_cur double [M][2] in/out
+ * (level-0 px); patch_sizes [n_levels] (8 or 16 per level, indexed by level); status [M] = converged. */
+int svo_cuda_align_pyr2d(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const svo_cuda_pyr* cur_pyr, const int* ref_frame_idx,
+                         const int* cur_frame_idx, int M, const int* px_ref_level_0, double* px_cur, int max_level,
+                         int min_level, const int* patch_sizes, int n_iter, float min_update_squared, uint8_t* status,
+                         svo_mem mem);
 /* warp::getWarpMatrixAffine + getBestSearchLevel + warpAffine (src/svo_direct/src/patch_warp.cpp:20-60,97-156) followed by
  * the 10x10 -> 8x8 crop; outputs A [M][4], search_level [M], patch_with_border [M][100], ok [M]. Mostly for parity tests. */
 int svo_cuda_warp_affine(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const int* ref_frame_idx, const svo_camera* cam_ref,

@@ -610,3 +610,34 @@ def ref_update_seeds(ref, cur_frames, T_cur_ref, ftrs, types, states, mu_range, 
                                             sigma2_thresh, mappoint_thresh, check_visibility, check_convergence, use_vogiatzis,
                                             None, _u8(ok))
     return n, ok
+
+
+def align_pyr2d(ref_pyr, cur_pyr, px_ref_level_0, px_cur, max_level, min_level, patch_sizes, n_iter=30, min_update_squared=0.03 ** 2,
+                which="orc", n_threads=1):
+    """feature_alignment::alignPyr2D for M features sharing two pyramids (lists of uint8 level arrays).
+    Returns (px_cur [M][2] float64, status [M] uint8)."""
+    n_levels = len(ref_pyr)
+    pr = np.ascontiguousarray(px_ref_level_0, np.int32).reshape(-1, 2)
+    pc = np.array(px_cur, np.float64).reshape(-1, 2).copy()
+    M = len(pr)
+    st = np.zeros(M, np.uint8)
+    ps = np.ascontiguousarray(patch_sizes, np.int32)
+    assert len(ps) >= n_levels
+    if which == "orc":
+        cam = dict(fx=1.0, fy=1.0, cx=0.0, cy=0.0, width=ref_pyr[0].shape[1], height=ref_pyr[0].shape[0])
+        rf, cf = make_frame(ref_pyr, cam), make_frame(cur_pyr, cam)
+        lib().orc_align_pyr2d(C.byref(rf), C.byref(cf), max_level, min_level, _i32(ps), n_iter, C.c_float(min_update_squared), M, _i32(pr),
+                              _f64(pc), _u8(st), n_threads)
+    else:
+        L = ref_direct_lib()
+        rl = (C.c_void_p * n_levels)(*[l.ctypes.data for l in ref_pyr])
+        cl = (C.c_void_p * n_levels)(*[l.ctypes.data for l in cur_pyr])
+        ws = np.array([l.shape[1] for l in ref_pyr], np.int32)
+        hs = np.array([l.shape[0] for l in ref_pyr], np.int32)
+        ss = np.array([l.strides[0] for l in ref_pyr], np.int32)
+        for i in range(M):
+            p = pc[i].copy()
+            st[i] = L.ref_align_pyr2d(rl, cl, _i32(ws), _i32(hs), _i32(ss), n_levels, max_level, min_level, _i32(ps), len(ps), n_iter,
+                                      C.c_float(min_update_squared), _i32(pr[i].copy()), _f64(p))
+            pc[i] = p
+    return pc, st

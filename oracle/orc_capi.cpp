@@ -374,6 +374,20 @@ int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
 }  // extern "C"
 
 extern "C" {
+void orc_align_pyr2d(const orc_frame* ref, const orc_frame* cur, int max_level, int min_level, const int* patch_sizes, int n_iter,
+                     float min_update_squared, int M, const int* px_ref_level_0, double* px_cur, uint8_t* status, int n_threads) {
+  std::vector<Img> pr, pc;
+  for (int l = 0; l < ref->n_levels; ++l) {
+    pr.push_back(Img{ref->level_data[l], ref->level_cols[l], ref->level_rows[l], ref->level_step[l]});
+    pc.push_back(Img{cur->level_data[l], cur->level_cols[l], cur->level_rows[l], cur->level_step[l]});
+  }
+  const std::vector<int> ps(patch_sizes, patch_sizes + ref->n_levels);
+  parallelFor(M, n_threads, [&](int i) {
+    V2 px{px_cur[2 * i], px_cur[2 * i + 1]};
+    status[i] = alignPyr2D(pr, pc, max_level, min_level, ps, n_iter, min_update_squared, px_ref_level_0 + 2 * i, px) ? 1 : 0;
+    px_cur[2 * i] = px.x; px_cur[2 * i + 1] = px.y;
+  });
+}
 void orc_tukey_weight(float b, const float* err, int n, float* w) {
   TukeyWeightFunction f(b);
   for (int i = 0; i < n; ++i) w[i] = f.weight(err[i]);

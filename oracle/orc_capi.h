@@ -151,6 +151,9 @@ int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
                      int check_visibility, int check_convergence, int use_vogiatzis, int* match_results, uint8_t* success,
                      int n_threads);
 
+/* f3: alignPyr2D for M features sharing the two pyramids; px_ref_level_0 int [M][2]; px_cur [M][2] in/out; status [M] */
+void orc_align_pyr2d(const orc_frame* ref, const orc_frame* cur, int max_level, int min_level, const int* patch_sizes, int n_iter,
+                     float min_update_squared, int M, const int* px_ref_level_0, double* px_cur, uint8_t* status, int n_threads);
 /* small pieces exposed one by one so that tests can pin them against the compiled reference (oracle/_ref/libdirect_ref.so) */
 void orc_tukey_weight(float b, const float* err, int n, float* w);
 /* which: 0 distort, 1 undistort, 2 jacobian (jac_out [n][4] = J00, J01, J10, J11) */

@@ -152,6 +152,97 @@ inline void inverse4f(const float m[4][4], float r[4][4]) {
   for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r[i][j] = cofm[j][i] * invdet;
 }
 
+// f3. feature_alignment::alignPyr2D — ref: src/svo_direct/src/feature_alignment.cpp:761-973 (non-NEON path)
+// Pyramidal inverse-compositional KLT on integer gradients: the template is cut at the truncated reference position,
+// the current image is sampled with 7-bit fixed-point bilinear weights (rounded descale), H and Jres are float sums in
+// raster order, update = Hinv * Jres * 2 (the gradients are twice the central difference).
+inline bool alignPyr2D(const std::vector<Img>& img_pyr_ref, const std::vector<Img>& img_pyr_cur, const int max_level,
+                       const int min_level, const std::vector<int>& patch_sizes, const int n_iter,
+                       const float min_update_squared, const int px_ref_level_0[2], V2& px_cur_level_0) {
+  const int max_patch_area = patch_sizes[0] * patch_sizes[0];
+  std::vector<uint8_t> ref_patch(max_patch_area);
+  std::vector<int16_t> ref_patch_dx(max_patch_area), ref_patch_dy(max_patch_area);
+  bool converged = false;
+  for (int level = max_level; level >= min_level; --level) {
+    const int patch_size = patch_sizes[level];
+    const int halfpatch_size = patch_size / 2;
+    const int scale = (1 << level);
+    const Img& img_ref = img_pyr_ref[level];
+    const Img& img_cur = img_pyr_cur[level];
+    const int width = img_ref.cols;
+    const int height = img_ref.rows;
+    const int step = img_ref.step;
+    const float px_ref_flt[2] = {float(px_ref_level_0[0]) / scale - float(halfpatch_size),
+                                 float(px_ref_level_0[1]) / scale - float(halfpatch_size)};
+    const int px_ref[2] = {int(px_ref_flt[0]), int(px_ref_flt[1])};
+    const float px_ref_offset[2] = {px_ref_flt[0] - float(px_ref[0]), px_ref_flt[1] - float(px_ref[1])};
+    if (px_ref[0] < 1 || px_ref[1] < 1 || px_ref[0] >= width - patch_size - 1 || px_ref[1] >= height - patch_size - 1) continue;
+    uint8_t* it_patch = ref_patch.data();
+    int16_t* it_dx = ref_patch_dx.data();
+    int16_t* it_dy = ref_patch_dy.data();
+    float H[2][2] = {{0, 0}, {0, 0}};
+    for (int y = 0; y < patch_size; ++y) {
+      const uint8_t* it = img_ref.data + (px_ref[1] + y) * step + (px_ref[0]);
+      for (int x = 0; x < patch_size; ++x, ++it, ++it_patch, ++it_dx, ++it_dy) {
+        *it_patch = *it;
+        *it_dx = static_cast<int16_t>(it[1]) - it[-1];
+        *it_dy = static_cast<int16_t>(it[step]) - it[-step];
+        const float J[2] = {float(*it_dx), float(*it_dy)};
+        for (int r = 0; r < 2; ++r) for (int c = 0; c < 2; ++c) H[r][c] += J[r] * J[c];
+      }
+    }
+    // Eigen::Matrix2f::inverse(): compute_inverse_size2_helper (invdet multiply)
+    const float invdet = 1.0f / (H[0][0] * H[1][1] - H[1][0] * H[0][1]);
+    const float Hinv[2][2] = {{H[1][1] * invdet, -H[0][1] * invdet}, {-H[1][0] * invdet, H[0][0] * invdet}};
+    float u = float(px_cur_level_0.x / scale - halfpatch_size - px_ref_offset[0]);
+    float v = float(px_cur_level_0.y / scale - halfpatch_size - px_ref_offset[1]);
+    float update[2] = {0, 0};
+    bool go_to_next_level = false;
+    const int SHIFT_BITS = 7;
+    converged = false;
+    for (int iter = 0; iter < n_iter; ++iter) {
+      if (std::isnan(u) || std::isnan(v)) return false;
+      go_to_next_level = false;
+      const int u_r = std::floor(u);
+      const int v_r = std::floor(v);
+      if (u_r < 0 || v_r < 0 || u_r >= width - patch_size || v_r >= height - patch_size) {
+        go_to_next_level = true;
+        break;
+      }
+      const float subpix_x = u - u_r;
+      const float subpix_y = v - v_r;
+      const uint16_t wTL = static_cast<uint16_t>((1.0f - subpix_x) * (1.0f - subpix_y) * (1 << SHIFT_BITS));
+      const uint16_t wTR = static_cast<uint16_t>(subpix_x * (1.0f - subpix_y) * (1 << SHIFT_BITS));
+      const uint16_t wBL = static_cast<uint16_t>((1.0f - subpix_x) * subpix_y * (1 << SHIFT_BITS));
+      const uint16_t wBR = (1 << SHIFT_BITS) - wTL - wTR - wBL;
+      const uint8_t* it_ref = ref_patch.data();
+      float Jres[2] = {0, 0};
+      const int16_t* it_ref_dx = ref_patch_dx.data();
+      const int16_t* it_ref_dy = ref_patch_dy.data();
+      for (int y = 0; y < patch_size; ++y) {
+        const uint8_t* it = img_cur.data + (v_r + y) * step + (u_r);
+        for (int x = 0; x < patch_size; ++x, ++it, ++it_ref, ++it_ref_dx, ++it_ref_dy) {
+          const uint16_t cur = ((wTL * it[0] + wTR * it[1] + wBL * it[step] + wBR * it[step + 1]) + (1 << (SHIFT_BITS - 1))) >> SHIFT_BITS;
+          const float res = static_cast<float>(cur) - *it_ref;
+          Jres[0] -= res * (*it_ref_dx);
+          Jres[1] -= res * (*it_ref_dy);
+        }
+      }
+      update[0] = (Hinv[0][0] * Jres[0] + Hinv[0][1] * Jres[1]) * 2.0f;
+      update[1] = (Hinv[1][0] * Jres[0] + Hinv[1][1] * Jres[1]) * 2.0f;
+      u += update[0];
+      v += update[1];
+      if (update[0] * update[0] + update[1] * update[1] < min_update_squared) {
+        converged = true;
+        break;
+      }
+    }
+    px_cur_level_0 = V2{double((u + halfpatch_size + px_ref_offset[0]) * scale), double((v + halfpatch_size + px_ref_offset[1]) * scale)};
+    if (!converged && !go_to_next_level) return false;
+  }
+  return converged;
+}
+
 // c4. feature_alignment::align1D — ref: src/svo_direct/src/feature_alignment.cpp:31-209
 inline bool align1D(const Img& cur_img, const V2& dir, const uint8_t* ref_patch_with_border, const uint8_t* ref_patch,
                     const int n_iter, const bool affine_est_offset, const bool affine_est_gain,

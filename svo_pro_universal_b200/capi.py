@@ -147,6 +147,7 @@ def lib():
                                             vp, ci, vp, vp, vp, vp, C.POINTER(SparseAlignOptions), vp, vp, ci]
         L.svo_cuda_align2d.argtypes = [vp, vp, vp, vp, ci, vp, ci, ci, ci, vp, vp, ci]
         L.svo_cuda_align1d.argtypes = [vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, vp, vp, vp, ci]
+        L.svo_cuda_align_pyr2d.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, ci, vp, ci, C.c_float, vp, ci]
         L.svo_cuda_warp_affine.argtypes = [vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), vp, vp, ci, vp, vp, vp, vp, vp, vp, ci]
         L.svo_cuda_find_match_direct.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), vp, vp, ci, vp, vp,
                                                  vp, C.POINTER(MatcherOptions), vp, ci]
@@ -166,7 +167,7 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_pyr_build", "svo_cuda_pyr_download", "svo_cuda_pyr_level_info", "svo_cuda_grid_cells", "svo_cuda_fast_detect",
     "svo_cuda_pyramid_fast_detect", "svo_cuda_fast_level_maps", "svo_cuda_sparse_align", "svo_cuda_align2d", "svo_cuda_align1d",
     "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
-    "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds",
+    "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
 ]
 
 
@@ -348,6 +349,32 @@ def align1d(ctx, pyr, frame_idx, level, direction, patch_with_border, px, n_iter
     ctx.check(lib().svo_cuda_align1d(ctx._h, pyr._h, ps[0], ps[1], M, ps[2], ps[3], n_iter, int(est_offset), int(est_gain),
                                      ps[4], ps[5], ps[6], kind))
     return px, conv, hinv
+
+
+def align_pyr2d(ctx, ref_pyr, cur_pyr, px_ref_level_0, px_cur, max_level, min_level, patch_sizes, n_iter=30, min_update_squared=0.03 ** 2,
+                ref_frame_idx=None, cur_frame_idx=None):
+    """svo_cuda_align_pyr2d (feature_alignment::alignPyr2DVec). Returns (px_cur [M][2] float64, status [M] uint8)."""
+    dev = _is_torch(px_cur)
+    M = (px_cur.numel() // 2) if dev else len(px_cur)
+    if dev:
+        import torch
+        pc = px_cur.clone()
+        status = torch.zeros(M, dtype=torch.uint8, device=px_cur.device)
+        pr = px_ref_level_0
+    else:
+        pc = np.ascontiguousarray(px_cur, np.float64).reshape(-1, 2).copy()
+        status = np.zeros(M, np.uint8)
+        pr = np.ascontiguousarray(px_ref_level_0, np.int32).reshape(-1, 2)
+        ref_frame_idx = None if ref_frame_idx is None else np.ascontiguousarray(ref_frame_idx, np.int32)
+        cur_frame_idx = None if cur_frame_idx is None else np.ascontiguousarray(cur_frame_idx, np.int32)
+    ps_arr = np.zeros(8, np.int32)
+    ps_arr[:len(patch_sizes)] = patch_sizes
+    ptrs, kind = _ptrs(pr, pc, status)
+    rfi = _ptr(ref_frame_idx)[0] if ref_frame_idx is not None else None
+    cfi = _ptr(cur_frame_idx)[0] if cur_frame_idx is not None else None
+    ctx.check(lib().svo_cuda_align_pyr2d(ctx._h, ref_pyr._h, cur_pyr._h, rfi, cfi, M, ptrs[0], ptrs[1], max_level, min_level,
+                                         ps_arr.ctypes.data_as(C.c_void_p), n_iter, C.c_float(min_update_squared), ptrs[2], kind))
+    return pc, status
 
 
 def _n_features(ftrs):

@@ -13,6 +13,7 @@ direct_ref_golden.npz outputs of the REFERENCE's own halfSample / align1D / alig
 frontend_ref_golden.npz outputs of the REFERENCE's own SparseImgAlign::run, Matcher::findMatchDirect / findEpipolarMatchDirect and
                       depth_filter_utils::updateSeed (oracle/_ref/libfrontend_ref.so: the reference sources compiled against
                       oracle/shim) on seeded inputs (tests/helpers.py:frontend_outputs): pins rows b, c1, c6-c7, d1-d3.
+klt_ref_golden.npz    outputs of the REFERENCE's own alignPyr2D (libdirect_ref.so) on the cases of tests/test_klt_cpu.py.
 Usage: python tests/golden/make_golden.py
 """
 import hashlib
@@ -111,7 +112,16 @@ def frontend_golden():
     print("frontend_ref_golden.npz", os.path.getsize(os.path.join(HERE, "frontend_ref_golden.npz")))
 
 
+def klt_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_klt_cpu
+    out = test_klt_cpu.klt_outputs(orc, "ref")
+    np.savez_compressed(os.path.join(HERE, "klt_ref_golden.npz"), **out)
+    print("klt_ref_golden.npz", os.path.getsize(os.path.join(HERE, "klt_ref_golden.npz")))
+
+
 if __name__ == "__main__":
+    klt_golden()
     frontend_golden()
     fast_golden()
     oracle_golden()
