@@ -134,8 +134,11 @@ def orc_frames(orc, pairs, keep):
     return refs, curs, l0
 
 
-def cpu_step_fn(n_pairs_per_step, n_threads, seed0=1000, n_unique=16):
-    """Returns (fn, sample description); fn() runs one bounded CPU step (pyramid + SparseImgAlign::run per pair) on all threads."""
+def cpu_step_fn(n_pairs_per_step, n_threads, seed0=1000, n_unique=16, kind="auto"):
+    """Returns (fn, sample description, kind); fn() runs one bounded CPU step (pyramid + SparseImgAlign::run per pair) on all
+    threads. kind "reference" = the reference's own sources compiled into oracle/_ref/libfrontend_ref.so (vk::halfSample +
+    svo::SparseImgAlign::run; Eigen/OpenCV/glog resolved to the stand-ins of oracle/shim), "port" = the oracle restatement;
+    "auto" picks the compiled reference when it travelled to this box."""
     from oracle import orc
     uniq = make_unique_pairs(n_unique, seed0)
     keep = []
@@ -143,12 +146,50 @@ def cpu_step_fn(n_pairs_per_step, n_threads, seed0=1000, n_unique=16):
     idx = [i % n_unique for i in range(n_pairs_per_step)]
     R, Cc, L = [refs[i] for i in idx], [curs[i] for i in idx], [l0[i] for i in idx]
     opt = orc.default_align_options()
+    if kind == "auto":
+        kind = "reference" if orc.ref_frontend_lib() is not None else "port"
 
-    def fn():
-        return orc.pyramid_align_batch(L, R, Cc, opt, N_LEVELS, n_threads)
+    if kind == "reference":
+        def fn():
+            return orc.ref_pyramid_align_batch(L, R, Cc, opt, N_LEVELS, n_threads)
+        what = "the reference's own SparseImgAlign + halfSample sources compiled -O2 (oracle/_ref/libfrontend_ref.so)"
+    else:
+        def fn():
+            return orc.pyramid_align_batch(L, R, Cc, opt, N_LEVELS, n_threads)
+        what = "oracle port of the reference CPU path"
 
     fn._keep = (keep, uniq)
-    return fn, f"{n_pairs_per_step} pairs/step ({n_unique} unique synthetic pairs tiled), oracle port of the reference CPU path, {n_threads} threads"
+    return fn, f"{n_pairs_per_step} pairs/step ({n_unique} unique synthetic pairs tiled), {what}, {n_threads} threads", kind
+
+
+def cpu_baseline(n_threads, seconds):
+    """Throughput (all host threads) and single-thread p50 latency of the CPU path over about `seconds` of work; the compiled
+    reference is the baseline, the (faster) oracle port is reported next to it."""
+    per_step = max(64, 16 * n_threads)
+    out = {}
+    for kind in ("reference", "port"):
+        from oracle import orc
+        if kind == "reference" and orc.ref_frontend_lib() is None:
+            continue
+        fn, sample, _ = cpu_step_fn(per_step, n_threads, kind=kind)
+        fn()
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < seconds:
+            fn(); reps += 1
+        value = per_step * reps / (time.perf_counter() - t0)
+        lat_fn, _, _ = cpu_step_fn(1, 1, kind=kind)
+        cl = []
+        for _ in range(40):
+            t = time.perf_counter(); lat_fn(); cl.append(time.perf_counter() - t)
+        out[kind] = {"value": value, "sample": sample + ", ~%d s" % seconds, "latency_ms_p50_single_thread": 1e3 * float(np.median(cl))}
+    kind = "reference" if "reference" in out else "port"
+    cb = {"value": out[kind]["value"], "unit": "pairs/s", "cores": n_threads, "kind": kind, "sample": out[kind]["sample"],
+          "latency_ms_p50_single_thread": out[kind]["latency_ms_p50_single_thread"]}
+    if kind == "reference":
+        cb["port_value"] = out["port"]["value"]
+        cb["port_latency_ms_p50_single_thread"] = out["port"]["latency_ms_p50_single_thread"]
+        cb["port_note"] = "the oracle restatement (-O3, no Eigen stand-in) on the same sample, for comparison"
+    return cb
 
 
 def run_reference(args):
@@ -157,7 +198,7 @@ def run_reference(args):
         return  # other ranks exit 0 without work
     n_threads = os.cpu_count() or 1
     per_step = max(64, 16 * n_threads)
-    fn, sample = cpu_step_fn(per_step, n_threads)
+    fn, sample, kind = cpu_step_fn(per_step, n_threads)
     for _ in range(max(1, min(args.warmup, 3))):
         fn()
     t0 = time.perf_counter()
@@ -165,7 +206,7 @@ def run_reference(args):
         fn()
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    lat_fn, _ = cpu_step_fn(1, 1)
+    lat_fn, _, _ = cpu_step_fn(1, 1, kind=kind)
     lats = []
     for _ in range(50):
         t = time.perf_counter(); lat_fn(); lats.append(time.perf_counter() - t)
@@ -175,7 +216,7 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "SparseImgAlign batch: pyramid of the new frame + run() per pair, 752x480, levels 4->1, 180 features, 4x4 patches",
                    "pairs_per_step": per_step, "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": n_threads, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": n_threads, "kind": kind, "sample": sample,
                          "latency_ms_p50_single_thread": 1e3 * float(np.median(lats))},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -346,17 +387,7 @@ def run_ours(args):
 
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----
     n_threads = os.cpu_count() or 1
-    per_step = max(64, 16 * n_threads)
-    fn, sample = cpu_step_fn(per_step, n_threads)
-    fn()
-    t0 = time.perf_counter(); reps = 0
-    while time.perf_counter() - t0 < 10.0:
-        fn(); reps += 1
-    cpu_value = per_step * reps / (time.perf_counter() - t0)
-    lat_fn, _ = cpu_step_fn(1, 1)
-    cl = []
-    for _ in range(40):
-        t = time.perf_counter(); lat_fn(); cl.append(time.perf_counter() - t)
+    cpu_bl = cpu_baseline(n_threads, 8.0)
 
     peaks = {}
     try:
@@ -382,8 +413,7 @@ def run_ours(args):
                      "kernel": "sparse_align_kernel<ILL=0, ROBUST=0, DJ=0, SLOTS=180>", "kernel_ms": align_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "note": "algorithmic bytes 247,044 B/pair; the kernel is FP64-issue / latency bound, not HBM bound: 28 % of its FP64-pipe bound (DESIGN.md 4b)"},
-        "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": n_threads, "kind": "port", "sample": sample + ", ~10 s",
-                         "latency_ms_p50_single_thread": 1e3 * float(np.median(cl))},
+        "cpu_baseline": cpu_bl,
         "latency": {"p50_ms_pair_e2e": 1e3 * float(np.median(lat)), "p95_ms_pair_e2e": 1e3 * float(np.percentile(lat, 95)),
                     "p50_ms_align_call": 1e3 * float(np.median(lat_align)),
                     "device_us_p50": breakdown,

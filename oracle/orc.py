@@ -442,6 +442,22 @@ def pyramid_align_batch(cur_l0_list, ref_frames, cur_frames, opt, n_levels=5, n_
     return res
 
 
+def ref_pyramid_align_batch(cur_l0_list, ref_frames, cur_frames, opt, n_levels=5, n_threads=1):
+    """The same frame-pair step on the REFERENCE's own compiled code (vk::halfSample pyramid + SparseImgAlign::run,
+    oracle/_ref/libfrontend_ref.so). Returns None when that library was never built."""
+    L = ref_frontend_lib()
+    if L is None:
+        return None
+    B = len(cur_l0_list)
+    rows, cols = cur_l0_list[0].shape
+    ptrs = (u8p * B)(*[_u8(a) for a in cur_l0_list])
+    R = (Frame * B)(*ref_frames)
+    Cc = (Frame * B)(*cur_frames)
+    res = (AlignResult * B)()
+    L.ref_pyramid_align_batch(B, n_levels, ptrs, cols, rows, R, Cc, C.byref(opt), res, n_threads)
+    return res
+
+
 # ---- one-function-at-a-time entry points, `which` = "orc" (the restatement) or "ref" (the compiled reference) ------------
 def _which(which):
     if which == "orc":

@@ -112,6 +112,42 @@ extern "C" int ref_sparse_align(int n_cams, const orc_frame* ref, const orc_fram
   return res->n_tracked;
 }
 
+// One "frame pair step" as bench.py defines it, on the REFERENCE's own code: the pyramid of the new frame with vk::halfSample
+// in the loop of frame_utils::createImgPyramid (src/svo_common/src/frame.cpp:372-386: level 0 is the image, level i = halfSample
+// of level i-1 into a fresh (rows/2, cols/2) Mat), then SparseImgAlign::run. B independent pairs on n_threads std::threads
+// (the reference runs one pair per call on one thread; the batch only keeps every host core busy with such calls).
+#include <atomic>
+#include <thread>
+#include <vikit/vision.h>
+extern "C" int ref_pyramid_align_batch(int B, int n_levels, const uint8_t* const* cur_l0, int cols, int rows, const orc_frame* ref,
+                                       const orc_frame* cur, const orc_align_options* opt, orc_align_result* res, int n_threads) {
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
+      std::vector<cv::Mat> pyr(n_levels);
+      pyr[0] = cv::Mat(rows, cols, CV_8UC1, const_cast<uint8_t*>(cur_l0[i]), (size_t)cols).clone();  // frame_handler_base.cpp:184-186
+      for (int l = 1; l < n_levels; ++l) {
+        pyr[l] = cv::Mat(pyr[l - 1].rows / 2, pyr[l - 1].cols / 2, CV_8U);
+        vk::halfSample(pyr[l - 1], pyr[l]);
+      }
+      orc_frame cf = cur[i];
+      cf.n_levels = n_levels;
+      for (int l = 0; l < n_levels; ++l) {
+        cf.level_data[l] = pyr[l].data;
+        cf.level_cols[l] = pyr[l].cols;
+        cf.level_rows[l] = pyr[l].rows;
+        cf.level_step[l] = (int)pyr[l].step;
+      }
+      ref_sparse_align(1, ref + i, &cf, opt, res + i);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  return 0;
+}
+
 // ---- (c) matcher ----------------------------------------------------------------------------------------------------------
 namespace {
 

@@ -98,3 +98,23 @@ def test_live_compiled_reference_filter_and_tau(orc):
         f = rng.normal(size=3); f /= np.linalg.norm(f)
         z = rng.uniform(0.3, 12)
         assert orc.lib().orc_compute_tau(orc._f64(T), orc._f64(f), z, 0.00218) == L.ref_compute_tau(orc._f64(T), orc._f64(f), z, 0.00218)
+
+
+def test_bench_cpu_step_reference_equals_port(orc):
+    """bench.py's CPU legs: the frame-pair step on the compiled reference (vk::halfSample pyramid + SparseImgAlign::run) and on
+    the oracle port produce the same poses — the timed baseline is the computation the parity tests check."""
+    if orc.ref_frontend_lib() is None:
+        pytest.skip("oracle/_ref/libfrontend_ref.so not built on this box")
+    import sys
+    sys.path.insert(0, os.path.dirname(GOLD.rstrip("/")).rsplit("/tests", 1)[0])
+    import bench
+    uniq = bench.make_unique_pairs(3, 1000)
+    keep = []
+    refs, curs, l0 = bench.orc_frames(orc, uniq, keep)
+    opt = orc.default_align_options()
+    a = orc.pyramid_align_batch(l0, refs, curs, opt, bench.N_LEVELS, 2)
+    b = orc.ref_pyramid_align_batch(l0, refs, curs, opt, bench.N_LEVELS, 2)
+    for x, y in zip(a, b):
+        assert x.n_tracked == y.n_tracked > 100
+        dq, dt = helpers.pose_diff(np.array(x.T_icur_iref[:]), np.array(y.T_icur_iref[:]))
+        assert dq < 1e-9 and dt < 1e-9
