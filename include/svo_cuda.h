@@ -279,6 +279,76 @@ int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const 
                           const int* obs_T_idx, const double* T_cur_ref, const svo_matcher_options* mopt,
                           const svo_depth_filter_options* dopt, int* n_success, int* match_results, svo_mem mem);
 
+/* ---- (f1) svo::Reprojector candidate matching ----------------------------------------------------------------- */
+/* reprojector_utils::getCandidate / projectPointAndCheckVisibility / sortCandidatesByReprojStats / sortCandidatesByNumObs /
+ * matchCandidates / matchCandidate (src/svo/include/svo/reprojector.h:168-200; src/svo/src/reprojector.cpp:310-543) with
+ * Frame::isVisible (src/svo_common/src/frame.cpp:229-257) and Point::getCloseViewObs (src/svo_common/src/point.cpp:83-129).
+ * The map is handed over as flat tables: the keyframes' feature columns (Frame SoA, frame.h:62-73) and the landmarks'
+ * bookkeeping (point.h:82-91). The tables are read only; everything the reference mutates comes back per entry. */
+typedef struct {
+  int n_kfs, n_feat, n_points, n_obs;
+  const double* kf_T_f_w;          /* [n_kfs][7] Frame::T_f_w_ */
+  const double* kf_seed_mu_range;  /* [n_kfs] Frame::seed_mu_range_ */
+  const int* kf_frame_idx;         /* [n_kfs] frame of keyframe k inside ref_pyr (NULL = k) */
+  const svo_feature* feat;         /* [n_feat] px_vec_, f_vec_, grad_vec_, type_vec_, level_vec_ of all keyframes, back to back */
+  const double* feat_score;        /* [n_feat] score_vec_ */
+  const double* feat_seed_state;   /* [n_feat][4] invmu_sigma2_a_b_vec_ */
+  const int* feat_point;           /* [n_feat] landmark id, -1 = landmark_vec_[i] == nullptr (a seed) */
+  const int* feat_kf;              /* [n_feat] keyframe that holds the feature */
+  const double* pt_pos;            /* [n_points][3] Point::pos_ */
+  const int* pt_n_failed;          /* [n_points] Point::n_failed_reproj_ */
+  const int* pt_n_succeeded;       /* [n_points] Point::n_succeeded_reproj_ */
+  const int* pt_obs_begin;         /* [n_points+1] Point::obs_ of point p = obs_feat[begin[p] .. begin[p+1]) */
+  const int* obs_feat;             /* [n_obs] feature index (into feat) of each observation */
+} svo_reproj_map;
+
+typedef struct { /* ReprojectorOptions subset (reprojector.h:27-70) + the arguments of matchCandidates */
+  int cell_size;                   /* default 30 */
+  int max_n_features;              /* matchCandidates' max_n_features_per_frame; 0 = unlimited and occupancy ignored */
+  int affine_est_offset, affine_est_gain;
+  int sort_by_num_obs;             /* 0 = sortCandidatesByReprojStats, 1 = sortCandidatesByNumObs */
+  int _pad;
+  double seed_sigma2_thresh;       /* default 200 */
+  double px_error_angle;           /* updateSeed's function-static (depth_filter.cpp:383-384); <= 0 = derive from cam_cur */
+} svo_reprojector_options;
+
+typedef enum {
+  SVO_REPROJ_NOT_CANDIDATE = 0,    /* getCandidate returned false (not visible in the current frame) */
+  SVO_REPROJ_NOT_REACHED = 1,      /* behind the point where matchCandidates stopped: stays in candidates_ */
+  SVO_REPROJ_SKIPPED = 2,          /* its grid cell was occupied at its turn */
+  SVO_REPROJ_FAILED = 3,           /* tried, no match */
+  SVO_REPROJ_MATCHED = 4
+} svo_reproj_status;
+
+typedef struct {
+  double cur_px[2];                /* Candidate::cur_px */
+  double px[2], f[3], grad[2];     /* matched: what matchCandidate writes into the current frame's feature slot */
+  double seed_state[4];            /* the ref feature's seed state after the call (changed when an unconverged seed was tried) */
+  int status;                      /* svo_reproj_status */
+  int order;                       /* position in the sorted candidate list, -1 = not a candidate */
+  int slot;                        /* matched: feature slot in the current frame (num_features_ at that moment) */
+  int level;                       /* matched: matcher.search_level_ */
+  int type_out;                    /* the ref feature's type after the call (updateSeed may converge it / mark it an outlier) */
+  int match_result;                /* Matcher::MatchResult of the attempt, -1 = none */
+  int d_failed, d_succeeded;       /* increments of the landmark's n_failed_reproj_ / n_succeeded_reproj_ */
+} svo_reproj_result;
+
+typedef struct { int n_candidates, n_trials, n_matches, n_consumed; } svo_reproj_stats;
+
+/* F current frames at once (independent reprojections, e.g. the frames of a batch of sequences): frame j lives in
+ * cur_pyr frame cur_frame_idx[j] (NULL = j) with pose cur_T_f_w[j], holds n_features_in[j] features already, and reprojects
+ * the entries entry_feat[entry_begin[j] .. entry_begin[j+1]) (feature indices into map->feat, in the reference's visiting
+ * order: the features of the visible keyframes that pass the map bookkeeping of Reprojector::reprojectFrames).
+ * n_entries = entry_begin[F]. occupancy [F][n_cells] is the grid, in/out (n_cells from svo_cuda_grid_cells with cam_cur's
+ * size); results [n_entries]; stats [F]. Candidates that compare equal under the reference's sort keep their visiting order (the reference's
+ * std::sort leaves their order unspecified). At most 4096 entries per frame and 4096 grid cells. All arrays, including those inside `map`,
+ * follow `mem`. */
+int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const svo_cuda_pyr* cur_pyr, const svo_camera* cam_ref,
+                             const svo_camera* cam_cur, const svo_reproj_map* map, int F, const int* cur_frame_idx,
+                             const double* cur_T_f_w, const int* n_features_in, const int* entry_begin, int n_entries,
+                             const int* entry_feat, uint8_t* occupancy, const svo_reprojector_options* opt, svo_reproj_result* results,
+                             svo_reproj_stats* stats, svo_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -657,3 +657,47 @@ def align_pyr2d(ref_pyr, cur_pyr, px_ref_level_0, px_cur, max_level, min_level, 
                                       C.c_float(min_update_squared), _i32(pr[i].copy()), _f64(p))
             pc[i] = p
     return pc, st
+
+
+# ---- f1: Reprojector candidate matching ----------------------------------------------------------------------------------------
+class ReprojMap(C.Structure):
+    _fields_ = [("n_kfs", C.c_int), ("kfs", C.POINTER(Frame)), ("kf_seed_mu_range", f64p), ("kf_feat_begin", i32p),
+                ("feat", C.POINTER(Feature)), ("feat_score", f64p), ("feat_seed_state", f64p), ("feat_point", i32p), ("feat_kf", i32p),
+                ("n_points", C.c_int), ("pt_pos", f64p), ("pt_n_failed", i32p), ("pt_n_succeeded", i32p), ("pt_obs_begin", i32p),
+                ("obs_feat", i32p)]
+
+
+class ReprojOptions(C.Structure):
+    _fields_ = [("cell_size", C.c_int), ("max_n_features", C.c_int), ("affine_est_offset", C.c_int), ("affine_est_gain", C.c_int),
+                ("sort_by_num_obs", C.c_int), ("seed_sigma2_thresh", C.c_double), ("px_error_angle", C.c_double)]
+
+
+REPROJ_RESULT_DTYPE = np.dtype([("cur_px", "<f8", 2), ("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("seed_state", "<f8", 4),
+                                ("status", "<i4"), ("order", "<i4"), ("slot", "<i4"), ("level", "<i4"), ("type_out", "<i4"),
+                                ("match_result", "<i4"), ("d_failed", "<i4"), ("d_succeeded", "<i4")])
+REPROJ_STATS_DTYPE = np.dtype([("n_candidates", "<i4"), ("n_trials", "<i4"), ("n_matches", "<i4"), ("n_consumed", "<i4")])
+
+
+def reproject_match(kf_frames, tables, cur_frame, entry_feat, n_features_in, occupancy, opt, which="orc"):
+    """One current frame through getCandidate + sort + matchCandidates. kf_frames: Frame structs (pyramid, camera, pose) of the
+    keyframes; tables: dict of numpy arrays (see orc_reproj_map); occupancy uint8 [n_cells] updated in place.
+    which = "orc" (restatement) or "ref" (the reference's own reprojector.cpp, oracle/_ref/libfrontend_ref.so)."""
+    L = lib() if which == "orc" else ref_frontend_lib()
+    fn = L.orc_reproject_match if which == "orc" else L.ref_reproject_match
+    K = len(kf_frames)
+    kfs = (Frame * K)(*kf_frames)
+    feats = make_features(tables["feat"]["px"], tables["feat"]["f"], tables["feat"]["grad"], tables["feat"]["type"], tables["feat"]["level"])
+    keep = {k: np.ascontiguousarray(tables[k], dt) for k, dt in (
+        ("kf_seed_mu_range", np.float64), ("kf_feat_begin", np.int32), ("feat_score", np.float64), ("feat_seed_state", np.float64),
+        ("feat_point", np.int32), ("feat_kf", np.int32), ("pt_pos", np.float64), ("pt_n_failed", np.int32),
+        ("pt_n_succeeded", np.int32), ("pt_obs_begin", np.int32), ("obs_feat", np.int32))}
+    m = ReprojMap(K, kfs, _f64(keep["kf_seed_mu_range"]), _i32(keep["kf_feat_begin"]), feats, _f64(keep["feat_score"]),
+                  _f64(keep["feat_seed_state"]), _i32(keep["feat_point"]), _i32(keep["feat_kf"]), int(tables["n_points"]),
+                  _f64(keep["pt_pos"]), _i32(keep["pt_n_failed"]), _i32(keep["pt_n_succeeded"]), _i32(keep["pt_obs_begin"]),
+                  _i32(keep["obs_feat"]))
+    ef = np.ascontiguousarray(entry_feat, np.int32)
+    res = np.zeros(len(ef), REPROJ_RESULT_DTYPE)
+    st = np.zeros(1, REPROJ_STATS_DTYPE)
+    fn(C.byref(m), C.byref(cur_frame), len(ef), _i32(ef), int(n_features_in), _u8(occupancy), C.byref(opt),
+       res.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
+    return res, st[0]

@@ -10,6 +10,7 @@
 #include "orc_sparse_align.hpp"
 #include "orc_matcher.hpp"
 #include "orc_depth_filter.hpp"
+#include "orc_reprojector.hpp"
 
 using namespace orc;
 
@@ -441,4 +442,19 @@ extern "C" int orc_pyramid_align_batch(int B, int n_levels, const uint8_t* const
     orc_sparse_align(1, ref + i, &cf, opt, res + i);
   });
   return 0;
+}
+
+// f1
+extern "C" int orc_reproject_match(const orc_reproj_map* map, const orc_frame* cur, int E, const int* entry_feat, int n_features_in,
+                                   uint8_t* occupancy, const orc_reproj_options* opt, orc_reproj_result* results, orc_reproj_stats* stats) {
+  std::vector<ReprojFrame> kfs(map->n_kfs);
+  for (int k = 0; k < map->n_kfs; ++k) {
+    kfs[k].mf = matchFrameOf(&map->kfs[k]);
+    kfs[k].T_f_w = se3FromArray(map->kfs[k].T_cam_imu) * se3FromArray(map->kfs[k].T_imu_world);
+  }
+  ReprojFrame c;
+  c.mf = matchFrameOf(cur);
+  c.T_f_w = se3FromArray(cur->T_cam_imu) * se3FromArray(cur->T_imu_world);
+  reprojectMatch(*map, kfs, c, E, entry_feat, n_features_in, occupancy, *opt, results, stats);
+  return stats->n_matches;
 }

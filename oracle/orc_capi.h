@@ -151,6 +151,59 @@ int orc_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
                      int check_visibility, int check_convergence, int use_vogiatzis, int* match_results, uint8_t* success,
                      int n_threads);
 
+/* f1: Reprojector candidate matching (src/svo/src/reprojector.cpp:342-543). Flattened map tables: the keyframes' feature SoA
+ * columns and the landmarks' bookkeeping, exactly the members the reference reads. */
+typedef struct {
+  int n_kfs;
+  const orc_frame* kfs;             /* [K] pyramids, camera, T_cam_imu / T_imu_world (T_f_w = T_cam_imu * T_imu_world) */
+  const double* kf_seed_mu_range;   /* [K] Frame::seed_mu_range_ */
+  const int* kf_feat_begin;         /* [K+1] features of keyframe k are the global features [begin[k], begin[k+1]) */
+  const orc_feature* feat;          /* [NF] px, f, grad, level, type */
+  const double* feat_score;         /* [NF] score_vec_ */
+  const double* feat_seed_state;    /* [NF][4] invmu_sigma2_a_b_vec_ */
+  const int* feat_point;            /* [NF] landmark id, -1 = landmark_vec_[i] == nullptr */
+  const int* feat_kf;               /* [NF] keyframe of the feature */
+  int n_points;
+  const double* pt_pos;             /* [P][3] Point::pos_ */
+  const int* pt_n_failed;           /* [P] n_failed_reproj_ */
+  const int* pt_n_succeeded;        /* [P] n_succeeded_reproj_ */
+  const int* pt_obs_begin;          /* [P+1] Point::obs_ of point p = obs_feat[begin[p] .. begin[p+1]) */
+  const int* obs_feat;              /* [NO] global feature index of each observation */
+} orc_reproj_map;
+
+typedef struct {
+  int cell_size;
+  int max_n_features;               /* matchCandidates' max_n_features_per_frame (0 = unlimited, occupancy ignored) */
+  int affine_est_offset, affine_est_gain;
+  int sort_by_num_obs;              /* 0 = sortCandidatesByReprojStats, 1 = sortCandidatesByNumObs */
+  double seed_sigma2_thresh;
+  double px_error_angle;            /* updateSeed's function-static (depth_filter.cpp:383-384) */
+} orc_reproj_options;
+
+enum { ORC_REPROJ_NOT_CANDIDATE = 0, ORC_REPROJ_NOT_REACHED = 1, ORC_REPROJ_SKIPPED = 2, ORC_REPROJ_FAILED = 3, ORC_REPROJ_MATCHED = 4 };
+
+typedef struct {
+  double cur_px[2];                 /* Candidate::cur_px (projection into the current frame) */
+  double px[2];                     /* matched: feature.px / f / grad written into the current frame's slot */
+  double f[3];
+  double grad[2];
+  double seed_state[4];             /* the ref feature's seed state after the call (updated for unconverged seeds that were tried) */
+  int status;
+  int order;                        /* position in the sorted candidate list, -1 = not a candidate */
+  int slot;                         /* matched: feature slot in the current frame */
+  int level;                        /* matched: matcher.search_level_ */
+  int type_out;                     /* the ref feature's type after the call (updateSeed may converge it or make it an outlier) */
+  int match_result;                 /* Matcher::MatchResult of the attempt, -1 = none */
+  int d_failed, d_succeeded;        /* increments of the landmark's n_failed_reproj_ / n_succeeded_reproj_ */
+} orc_reproj_result;
+
+typedef struct { int n_candidates, n_trials, n_matches, n_consumed; } orc_reproj_stats;
+
+/* One current frame: getCandidate for the E entries (global feature indices, in the reference's visiting order), sort,
+ * matchCandidates. occupancy [n_cells] in/out; results [E]; n_features_in = frame->num_features_ before the call. */
+int orc_reproject_match(const orc_reproj_map* map, const orc_frame* cur, int E, const int* entry_feat, int n_features_in,
+                        uint8_t* occupancy, const orc_reproj_options* opt, orc_reproj_result* results, orc_reproj_stats* stats);
+
 /* f3: alignPyr2D for M features sharing the two pyramids; px_ref_level_0 int [M][2]; px_cur [M][2] in/out; status [M] */
 void orc_align_pyr2d(const orc_frame* ref, const orc_frame* cur, int max_level, int min_level, const int* patch_sizes, int n_iter,
                      float min_update_squared, int M, const int* px_ref_level_0, double* px_cur, uint8_t* status, int n_threads);

@@ -22,6 +22,8 @@
 #include <svo/direct/feature_detection_utils.h>
 #include <svo/common/frame.h>
 #include <svo/common/camera.h>
+#include <svo/common/occupancy_grid_2d.h>
+#include <svo/reprojector.h>
 #include <cstring>
 #include "orc_capi.h"
 
@@ -352,3 +354,140 @@ int ref_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
 }
 
 }  // extern "C"
+
+// ---- (f1) Reprojector candidate flow ------------------------------------------------------------------------------------------
+// The reference's own reprojector.cpp (src/svo/src/reprojector.cpp, compiled unmodified): getCandidate for every entry in
+// visiting order, sortCandidatesByReprojStats / sortCandidatesByNumObs, matchCandidates. The keyframes, their feature columns
+// and the landmarks with their observation lists are rebuilt from the flat tables as real svo::Frame / svo::Point objects.
+extern "C" int ref_reproject_match(const orc_reproj_map* map, const orc_frame* cur, int E, const int* entry_feat, int n_features_in,
+                                   uint8_t* occupancy, const orc_reproj_options* opt, orc_reproj_result* results,
+                                   orc_reproj_stats* stats) {
+  using namespace svo;
+  std::vector<FramePtr> kfs;
+  for (int k = 0; k < map->n_kfs; ++k) {
+    orc_frame f = map->kfs[k];
+    f.px = nullptr;  // features come from the tables below
+    FramePtr fr = makeFrame(f);
+    fr->id_ = k + 1;
+    const int b = map->kf_feat_begin[k], n = map->kf_feat_begin[k + 1] - b;
+    fr->resizeFeatureStorage(n);
+    fr->num_features_ = n;
+    fr->seed_mu_range_ = map->kf_seed_mu_range[k];
+    for (int i = 0; i < n; ++i) {
+      const orc_feature& q = map->feat[b + i];
+      fr->px_vec_.col(i) = Eigen::Vector2d(q.px[0], q.px[1]);
+      fr->f_vec_.col(i) = Eigen::Vector3d(q.f[0], q.f[1], q.f[2]);
+      fr->grad_vec_.col(i) = Eigen::Vector2d(q.grad[0], q.grad[1]);
+      fr->level_vec_(i) = q.level;
+      fr->type_vec_[i] = static_cast<FeatureType>(q.type);
+      fr->score_vec_(i) = map->feat_score[b + i];
+      for (int c = 0; c < 4; ++c) fr->invmu_sigma2_a_b_vec_(c, i) = map->feat_seed_state[4 * size_t(b + i) + c];
+    }
+    kfs.push_back(fr);
+  }
+  std::vector<PointPtr> pts;
+  for (int p = 0; p < map->n_points; ++p) {
+    auto pt = std::make_shared<Point>(Eigen::Vector3d(map->pt_pos[3 * p], map->pt_pos[3 * p + 1], map->pt_pos[3 * p + 2]));
+    pt->id_ = p;
+    pt->n_failed_reproj_ = map->pt_n_failed[p];
+    pt->n_succeeded_reproj_ = map->pt_n_succeeded[p];
+    for (int o = map->pt_obs_begin[p]; o < map->pt_obs_begin[p + 1]; ++o) {
+      const int fi = map->obs_feat[o], k = map->feat_kf[fi];
+      pt->obs_.emplace_back(kfs[k], size_t(fi - map->kf_feat_begin[k]));
+    }
+    pts.push_back(pt);
+  }
+  int n_feat = map->kf_feat_begin[map->n_kfs];
+  for (int fi = 0; fi < n_feat; ++fi)
+    if (map->feat_point[fi] >= 0) {
+      const int k = map->feat_kf[fi];
+      kfs[k]->landmark_vec_[fi - map->kf_feat_begin[k]] = pts[map->feat_point[fi]];
+    }
+  orc_frame cf = *cur;
+  cf.px = nullptr;
+  FramePtr frame = makeFrame(cf);
+  frame->id_ = 1000;
+  const size_t cap = size_t(n_features_in) + size_t(E) + 1;
+  frame->resizeFeatureStorage(cap);
+  frame->num_features_ = n_features_in;
+  for (int i = 0; i < n_features_in; ++i) frame->type_vec_[i] = FeatureType::kCorner;
+
+  OccupandyGrid2D grid(opt->cell_size, OccupandyGrid2D::getNCell(frame->cam()->imageWidth(), opt->cell_size),
+                       OccupandyGrid2D::getNCell(frame->cam()->imageHeight(), opt->cell_size));
+  grid.reset();
+  for (size_t c = 0; c < grid.occupancy_.size(); ++c) grid.occupancy_[c] = occupancy[c] != 0;
+  const std::vector<bool> occ_in = grid.occupancy_;
+
+  std::vector<int> entry_of_feat(n_feat, -1);
+  Reprojector::Candidates candidates;
+  for (int e = 0; e < E; ++e) {
+    const int fi = entry_feat[e], k = map->feat_kf[fi];
+    entry_of_feat[fi] = e;
+    orc_reproj_result& r = results[e];
+    std::memset(&r, 0, sizeof(r));
+    r.status = ORC_REPROJ_NOT_CANDIDATE; r.order = -1; r.slot = -1; r.match_result = -1;
+    Reprojector::Candidate c;
+    if (reprojector_utils::getCandidate(frame, kfs[k], size_t(fi - map->kf_feat_begin[k]), c)) {
+      r.cur_px[0] = c.cur_px[0]; r.cur_px[1] = c.cur_px[1];
+      candidates.push_back(c);
+    }
+  }
+  if (opt->sort_by_num_obs) reprojector_utils::sortCandidatesByNumObs(candidates);
+  else reprojector_utils::sortCandidatesByReprojStats(candidates);
+  auto featOf = [&](const Reprojector::Candidate& c) {
+    int k = 0;
+    while (kfs[k].get() != c.ref_frame.get()) ++k;
+    return map->kf_feat_begin[k] + int(c.ref_index);
+  };
+  const Reprojector::Candidates sorted = candidates;
+  for (size_t p = 0; p < sorted.size(); ++p) {
+    orc_reproj_result& r = results[entry_of_feat[featOf(sorted[p])]];
+    r.order = int(p);
+    r.status = ORC_REPROJ_NOT_REACHED;
+  }
+  Reprojector::Statistics st;
+  reprojector_utils::matchCandidates(frame, size_t(opt->max_n_features), opt->affine_est_offset != 0, opt->affine_est_gain != 0,
+                                     candidates, grid, st, opt->seed_sigma2_thresh);
+  stats->n_candidates = int(sorted.size());
+  stats->n_trials = int(st.n_trials);
+  stats->n_matches = int(st.n_matches);
+  stats->n_consumed = int(sorted.size() - candidates.size());
+  // which candidate filled which new slot: landmarks by feature.landmark, seeds by feature.seed_ref
+  for (size_t s = size_t(n_features_in); s < frame->num_features_; ++s) {
+    int fi = -1;
+    for (int e = 0; e < E && fi < 0; ++e) {
+      const int g = entry_feat[e], k = map->feat_kf[g];
+      if (results[e].order < 0 || results[e].order >= stats->n_consumed) continue;
+      if (map->feat_point[g] >= 0) { if (frame->landmark_vec_[s] == pts[map->feat_point[g]]) fi = g; }
+      else if (frame->seed_ref_vec_[s].keyframe == kfs[k] && frame->seed_ref_vec_[s].seed_id == g - map->kf_feat_begin[k]) fi = g;
+    }
+    if (fi < 0) continue;
+    orc_reproj_result& r = results[entry_of_feat[fi]];
+    r.status = ORC_REPROJ_MATCHED;
+    r.slot = int(s);
+    r.px[0] = frame->px_vec_(0, s); r.px[1] = frame->px_vec_(1, s);
+    r.f[0] = frame->f_vec_(0, s); r.f[1] = frame->f_vec_(1, s); r.f[2] = frame->f_vec_(2, s);
+    if (isEdgelet(frame->type_vec_[s])) { r.grad[0] = frame->grad_vec_(0, s); r.grad[1] = frame->grad_vec_(1, s); }
+    r.level = frame->level_vec_(s);
+  }
+  // consumed candidates that did not match: skipped when their cell was occupied at their turn, tried (and failed) otherwise
+  std::vector<bool> occ = occ_in;
+  for (int p = 0; p < stats->n_consumed; ++p) {
+    orc_reproj_result& r = results[entry_of_feat[featOf(sorted[p])]];
+    const size_t cell = grid.getCellIndex(sorted[p].cur_px.x(), sorted[p].cur_px.y(), 1);
+    if (opt->max_n_features > 0 && occ[cell]) { r.status = ORC_REPROJ_SKIPPED; continue; }
+    if (r.status == ORC_REPROJ_MATCHED) occ[cell] = true;
+    else r.status = ORC_REPROJ_FAILED;
+  }
+  for (size_t c = 0; c < grid.occupancy_.size(); ++c) occupancy[c] = grid.occupancy_[c] ? 1 : 0;
+  for (int e = 0; e < E; ++e) {
+    const int fi = entry_feat[e], k = map->feat_kf[fi], i = fi - map->kf_feat_begin[k];
+    for (int c = 0; c < 4; ++c) results[e].seed_state[c] = kfs[k]->invmu_sigma2_a_b_vec_(c, i);
+    results[e].type_out = int(kfs[k]->type_vec_[i]);
+    if (map->feat_point[fi] >= 0) {
+      results[e].d_failed = pts[map->feat_point[fi]]->n_failed_reproj_ - map->pt_n_failed[map->feat_point[fi]];
+      results[e].d_succeeded = pts[map->feat_point[fi]]->n_succeeded_reproj_ - map->pt_n_succeeded[map->feat_point[fi]];
+    }
+  }
+  return stats->n_matches;
+}

@@ -48,16 +48,23 @@ class Frame {
   TrackIds track_id_vec_;
   SeedRefs seed_ref_vec_;
   SeedStates invmu_sigma2_a_b_vec_;
+  std::vector<bool> in_ba_graph_vec_;
   FloatType seed_mu_range_ = 0;
 
   Frame() {}
   Frame(const Frame&) = delete;
   Frame& operator=(const Frame&) = delete;
 
-  void resizeFeatureStorage(size_t num) {
-    px_vec_.resize(2, num); f_vec_.resize(3, num); score_vec_.resize(num, 1); level_vec_.resize(num, 1);
-    grad_vec_.resize(2, num); type_vec_.assign(num, FeatureType::kCorner); landmark_vec_.assign(num, nullptr);
-    track_id_vec_.resize(num, 1); seed_ref_vec_.assign(num, SeedRef()); invmu_sigma2_a_b_vec_.resize(4, num);
+  void resizeFeatureStorage(size_t num) {  // frame.cpp:94-123 (contents are kept, new slots get the reference's initial values)
+    if (static_cast<size_t>(px_vec_.cols()) < num) {
+      const size_t n_old = px_vec_.cols();
+      px_vec_.conservativeResize(Eigen::NoChange, num); f_vec_.conservativeResize(Eigen::NoChange, num);
+      score_vec_.conservativeResize(num); level_vec_.conservativeResize(num); grad_vec_.conservativeResize(Eigen::NoChange, num);
+      invmu_sigma2_a_b_vec_.conservativeResize(Eigen::NoChange, num); track_id_vec_.conservativeResize(num);
+      type_vec_.resize(num, FeatureType::kCorner); landmark_vec_.resize(num, nullptr); seed_ref_vec_.resize(num);
+      in_ba_graph_vec_.resize(num, false);
+      for (size_t i = n_old; i < num; ++i) { level_vec_(i) = 0; track_id_vec_(i) = -1; score_vec_(i) = -1; }
+    }
   }
   void clearFeatureStorage() {  // frame.cpp:125-139
     px_vec_.resize(Eigen::NoChange, 0); f_vec_.resize(Eigen::NoChange, 0); score_vec_.resize(0); level_vec_.resize(0);
@@ -69,6 +76,20 @@ class Frame {
   FeatureWrapper getFeatureWrapper(size_t i) {
     return FeatureWrapper(type_vec_[i], px_vec_.col(i), f_vec_.col(i), grad_vec_.col(i), score_vec_(i), level_vec_(i),
                           landmark_vec_[i], seed_ref_vec_[i], track_id_vec_(i));
+  }
+  FeatureWrapper getEmptyFeatureWrapper() { return getFeatureWrapper(num_features_); }  // frame.cpp:166-169
+  inline bool isValidLandmark(size_t i) const { return (landmark_vec_.at(i) != nullptr); }  // frame.h:148-150
+  inline size_t numTrackedFeatures() const {  // frame.h:153-163
+    size_t count = 0;
+    for (size_t i = 0; i < num_features_; ++i)
+      if ((isValidLandmark(i) && !isFixedLandmark(type_vec_[i]) && !isMapPoint(type_vec_[i])) || isCornerEdgeletSeed(type_vec_[i])) ++count;
+    return count;
+  }
+  inline size_t numFixedLandmarks() const {  // frame.h:183-191
+    size_t count = 0;
+    for (size_t i = 0; i < num_features_; ++i)
+      if (isValidLandmark(i) && isFixedLandmark(type_vec_[i])) ++count;
+    return count;
   }
   inline FloatType getSeedDepth(size_t idx) const { return seed::getDepth(invmu_sigma2_a_b_vec_.col(idx)); }
   inline Position getSeedPosInFrame(size_t idx) const { return f_vec_.col(idx) * getSeedDepth(idx); }
@@ -135,6 +156,32 @@ class Frame {
     J = J_proj * T_cam_imu.getRotation().getRotationMatrix() * G_x;
   }
 };
+
+inline KeypointIdentifier::KeypointIdentifier(const FramePtr& _frame, const size_t _feature_index)  // point.cpp:19-23
+    : frame(_frame), frame_id(_frame->id_), keypoint_index_(_feature_index) {}
+
+// point.cpp:83-129
+inline bool Point::getCloseViewObs(const Eigen::Vector3d& framepos, FramePtr& ref_frame, size_t& ref_feature_index) const {
+  double min_cos_angle = 0.0;
+  Eigen::Vector3d obs_dir(framepos - pos_);
+  obs_dir.normalize();
+  for (const KeypointIdentifier& obs : obs_) {
+    if (FramePtr frame = obs.frame.lock()) {
+      Eigen::Vector3d dir(frame->pos() - pos_);
+      dir.normalize();
+      const double cos_angle = obs_dir.dot(dir);
+      if (cos_angle > min_cos_angle) {
+        min_cos_angle = cos_angle;
+        ref_frame = frame;
+        ref_feature_index = obs.keypoint_index_;
+      }
+    } else {
+      return false;
+    }
+  }
+  if (min_cos_angle < 0.4) return false;  // observations more than 60 degrees away are useless
+  return true;
+}
 
 class FrameBundle {
  public:

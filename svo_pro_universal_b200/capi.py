@@ -112,6 +112,34 @@ def depth_filter_options(**kw):
     return o
 
 
+class ReprojMap(C.Structure):
+    """svo_reproj_map: flat map tables (keyframe feature columns + landmark bookkeeping)."""
+    _fields_ = [("n_kfs", C.c_int), ("n_feat", C.c_int), ("n_points", C.c_int), ("n_obs", C.c_int),
+                ("kf_T_f_w", C.c_void_p), ("kf_seed_mu_range", C.c_void_p), ("kf_frame_idx", C.c_void_p), ("feat", C.c_void_p),
+                ("feat_score", C.c_void_p), ("feat_seed_state", C.c_void_p), ("feat_point", C.c_void_p), ("feat_kf", C.c_void_p),
+                ("pt_pos", C.c_void_p), ("pt_n_failed", C.c_void_p), ("pt_n_succeeded", C.c_void_p), ("pt_obs_begin", C.c_void_p),
+                ("obs_feat", C.c_void_p)]
+
+
+class ReprojectorOptions(C.Structure):
+    _fields_ = [("cell_size", C.c_int), ("max_n_features", C.c_int), ("affine_est_offset", C.c_int), ("affine_est_gain", C.c_int),
+                ("sort_by_num_obs", C.c_int), ("_pad", C.c_int), ("seed_sigma2_thresh", C.c_double), ("px_error_angle", C.c_double)]
+
+
+def reprojector_options(**kw):
+    """ReprojectorOptions defaults (reprojector.h:27-70): cell 30, 120 features, affine offset on / gain off, sigma2 thresh 200."""
+    o = ReprojectorOptions(30, 120, 1, 0, 0, 0, 200.0, 0.0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+REPROJ_RESULT_DTYPE = np.dtype([("cur_px", "<f8", 2), ("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("seed_state", "<f8", 4),
+                                ("status", "<i4"), ("order", "<i4"), ("slot", "<i4"), ("level", "<i4"), ("type_out", "<i4"),
+                                ("match_result", "<i4"), ("d_failed", "<i4"), ("d_succeeded", "<i4")])
+REPROJ_STATS_DTYPE = np.dtype([("n_candidates", "<i4"), ("n_trials", "<i4"), ("n_matches", "<i4"), ("n_consumed", "<i4")])
+REPROJ_NOT_CANDIDATE, REPROJ_NOT_REACHED, REPROJ_SKIPPED, REPROJ_FAILED, REPROJ_MATCHED = range(5)
+
 _lib = None
 
 
@@ -157,6 +185,8 @@ def lib():
         L.svo_cuda_compute_tau.argtypes = [vp, ci, vp, vp, vp, cd, vp, ci]
         L.svo_cuda_update_seeds.argtypes = [vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), ci, vp, vp, vp, vp, vp, ci, vp, vp,
                                             vp, C.POINTER(MatcherOptions), C.POINTER(DepthFilterOptions), vp, vp, ci]
+        L.svo_cuda_reproject_match.argtypes = [vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), C.POINTER(ReprojMap), ci, vp, vp, vp,
+                                               vp, ci, vp, vp, C.POINTER(ReprojectorOptions), vp, vp, ci]
         _lib = L
     return _lib
 
@@ -168,6 +198,7 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_pyramid_fast_detect", "svo_cuda_fast_level_maps", "svo_cuda_sparse_align", "svo_cuda_align2d", "svo_cuda_align1d",
     "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
+    "svo_cuda_reproject_match",
 ]
 
 
@@ -466,3 +497,32 @@ def update_seeds(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, ftrs, types, state, se
     ctx.check(lib().svo_cuda_update_seeds(ctx._h, ref_pyr._h, cur_pyr._h, C.byref(cam_ref), C.byref(cam_cur), S, ps[0], ps[1], ps[2],
                                           ps[3], ps[4], n_obs, ps[5], ps[6], ps[7], C.byref(mopt), C.byref(dopt), ps[8], ps[9], kind))
     return n_success, mr
+
+
+_REPROJ_MAP_ARRAYS = ("kf_T_f_w", "kf_seed_mu_range", "kf_frame_idx", "feat", "feat_score", "feat_seed_state", "feat_point", "feat_kf",
+                      "pt_pos", "pt_n_failed", "pt_n_succeeded", "pt_obs_begin", "obs_feat")
+
+
+def reproject_match(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, tables, cur_T_f_w, n_features_in, entry_begin, entry_feat, occupancy, opt,
+                    cur_frame_idx=None, results=None, stats=None):
+    """svo_cuda_reproject_match. `tables`: dict with the svo_reproj_map arrays (numpy or torch cuda; kf_frame_idx optional) plus
+    n_kfs / n_feat / n_points / n_obs. occupancy [F, n_cells] uint8 is updated in place. Returns (results, stats)."""
+    arrs = [tables.get(k) for k in _REPROJ_MAP_ARRAYS]
+    dev = _is_torch(occupancy) and occupancy.is_cuda
+    F = int(cur_T_f_w.shape[0])
+    n_entries = int(entry_feat.shape[0])
+    if results is None:
+        if dev:
+            import torch
+            results = torch.zeros(max(n_entries, 1) * REPROJ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=occupancy.device)
+            stats = torch.zeros(F * REPROJ_STATS_DTYPE.itemsize, dtype=torch.uint8, device=occupancy.device)
+        else:
+            results = np.zeros(n_entries, REPROJ_RESULT_DTYPE)
+            stats = np.zeros(F, REPROJ_STATS_DTYPE)
+    ps, kind = _ptrs(*arrs, cur_frame_idx, cur_T_f_w, n_features_in, entry_begin, entry_feat, occupancy, results, stats)
+    m = ReprojMap(int(tables["n_kfs"]), int(tables["n_feat"]), int(tables["n_points"]), int(tables["n_obs"]),
+                  *[(p.value if p is not None else None) for p in ps[:len(arrs)]])
+    q = ps[len(arrs):]
+    ctx.check(lib().svo_cuda_reproject_match(ctx._h, ref_pyr._h, cur_pyr._h, C.byref(cam_ref), C.byref(cam_cur), C.byref(m), F, q[0], q[1],
+                                             q[2], q[3], n_entries, q[4], q[5], C.byref(opt), q[6], q[7], kind))
+    return results, stats

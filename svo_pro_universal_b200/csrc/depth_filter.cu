@@ -11,71 +11,11 @@
 //   update_seeds_kernel   one 8-lane group per seed walks that seed's observations IN ORDER (the filter is sequential per
 //                         seed, seeds are independent): visibility gate, epipolar match (matcher_dev.cuh), tau, filter
 //                         update, convergence flag — the whole depth_filter_utils::updateSeed without leaving the device.
-#include "matcher_dev.cuh"
+#include "depth_filter_dev.cuh"
 
 using namespace svo_dev;
 
 namespace {
-
-SVO_D double normPdf(double x, double mean, double sigma) {
-  double exponent = x - mean;
-  exponent *= -exponent;
-  exponent /= 2 * sigma * sigma;
-  double result = exp(exponent);
-  result /= sigma * sqrt(2 * 3.14159265358979323846);
-  return result;
-}
-
-// depth_filter.cpp:501-552; s = (mu, sigma2, a, b) in/out
-SVO_D bool updateFilterVogiatzis(double z, double tau2, double mu_range, double s[4]) {
-  double mu = s[0], sigma2 = s[1], a = s[2], b = s[3];
-  const double norm_scale = sqrt(sigma2 + tau2);
-  if (norm_scale != norm_scale) return false;
-  const double oldsigma2 = sigma2;
-  const double s2 = 1.0 / (1.0 / sigma2 + 1.0 / tau2);
-  const double m = s2 * (mu / sigma2 + z / tau2);
-  const double uniform_x = 1.0 / mu_range;
-  double C1 = a / (a + b) * normPdf(z, mu, norm_scale);
-  double C2 = b / (a + b) * uniform_x;
-  const double normalization_constant = C1 + C2;
-  C1 /= normalization_constant;
-  C2 /= normalization_constant;
-  const double f = C1 * (a + 1.0) / (a + b + 1.0) + C2 * a / (a + b + 1.0);
-  const double e = C1 * (a + 1.0) * (a + 2.0) / ((a + b + 1.0) * (a + b + 2.0)) + C2 * a * (a + 1.0) / ((a + b + 1.0) * (a + b + 2.0));
-  const double mu_new = C1 * m + C2 * mu;
-  sigma2 = C1 * (s2 + m * m) + C2 * (sigma2 + mu * mu) - mu_new * mu_new;
-  mu = mu_new;
-  a = (e - f) / (f - e / f);
-  b = a * (1.0 - f) / f;
-  bool ok = true;
-  if (sigma2 < 0.0) sigma2 = oldsigma2;
-  if (mu < 0.0) { mu = 1.0; ok = false; }
-  s[0] = mu; s[1] = sigma2; s[2] = a; s[3] = b;
-  return ok;
-}
-
-// depth_filter.cpp:554-578
-SVO_D bool updateFilterGaussian(double z, double tau2, double s[4]) {
-  const double norm_scale = sqrt(s[1] + tau2);
-  if (norm_scale != norm_scale) return false;
-  const double denom = s[1] + tau2;
-  s[0] = (s[1] * z + tau2 * s[0]) / denom;
-  s[1] = s[1] * tau2 / denom;
-  return true;
-}
-
-// depth_filter.cpp:580-596
-SVO_D double computeTau(const V3d& t, const V3d& f, double z, double px_error_angle) {
-  const V3d a = f * z - t;
-  const double t_norm = norm3(t);
-  const double a_norm = norm3(a);
-  const double alpha = acos(dot3(f, t) / t_norm);
-  const double beta = acos(dot3(a, -t) / (t_norm * a_norm));
-  const double beta_plus = beta + px_error_angle;
-  const double gamma_plus = 3.14159265358979323846 - alpha - beta_plus;
-  const double z_plus = t_norm * sin(beta_plus) / sin(gamma_plus);
-  return z_plus - z;
-}
 
 __global__ void __launch_bounds__(256) vogiatzis_kernel(int n, const double* __restrict__ z, const double* __restrict__ tau2,
                                                         const double* __restrict__ mu_range, double* __restrict__ state,
@@ -141,61 +81,15 @@ __global__ void __launch_bounds__(kThreads, 6) update_seeds_kernel(const SeedPar
     const size_t oi = (size_t)o * P.S + s;
     int mr = -1;
     const int cf = P.obs_frame_idx[oi];
-    bool done = cf < 0;  // depth_filter.cpp:377-381 (cur frame == ref frame): the caller marks such observations
-    // :387-399
-    if (!done && type == kOutlier) done = true;
-    if (!done && (type == kCornerSeedConverged || type == kEdgeletSeedConverged || type == kMapPointSeedConverged) &&
-        P.dopt.check_convergence)
-      done = true;
-    if (!done) {
+    if (cf >= 0) {  // depth_filter.cpp:377-381 (cur frame == ref frame): the caller marks such observations with a negative index
       const SE3d T = se3Load(P.T_cur_ref + 7 * (size_t)P.obs_T_idx[oi]);
-      bool visible = true;
-      if (P.dopt.check_visibility) {  // :406-420
-        const V3d xyz_f = se3Apply(T, f_ref * (1.0 / st[0]));
-        const V2d px = camProject3(P.cam_cur, xyz_f);
-        visible = px.x >= 0.0 && px.y >= 0.0 && px.x < (double)P.cam_cur.width && px.y < (double)P.cam_cur.height;
-        if (visible) {
-          const int pxi0 = (int)px.x, pxi1 = (int)px.y;
-          const int boundary = 9;
-          visible = pxi0 >= boundary && pxi1 >= boundary && pxi0 < P.cam_cur.width - boundary && pxi1 < P.cam_cur.height - boundary;
-        }
-      }
-      if (visible) {
-        const bool align_1d = (type == kEdgeletSeed || type == kEdgeletSeedConverged);  // :423-427
-        ft.type = type;
-        MatchState m;
-        initMatchState(m);
-        double depth = 0.0;
-        // seed.h:115-128: d_estimate_inv = mu, d_min_inv = mu + sigma, d_max_inv = max(mu - sigma, 1e-8)
-        const double sig = sqrt(st[1]);
-        mr = findEpipolarMatchDirect(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, st[0], st[0] + sig,
-                                     fmax(st[0] - sig, 0.00000001), P.mopt, align_1d, pwb, m, &depth);
-        if (mr != kSuccess) {
-          if (!m.reject) st[3] += 1;  // seed::increaseOutlierProbability, :445-450
-        } else {
-          const SE3d T_ref_cur = se3Inv(T);
-          const double depth_sigma = computeTau(T_ref_cur.t, f_ref, depth, P.px_error_angle);  // :459
-          const double zi = 1.0 / depth;
-          // seed::getSigma2FromDepthSigma (seed.h:155-160)
-          const double sg = 0.5 * (1.0 / fmax(0.000000000001, depth - depth_sigma) - 1.0 / (depth + depth_sigma));
-          const double tau2 = sg * sg;
-          const bool ok = P.dopt.use_vogiatzis_update ? updateFilterVogiatzis(zi, tau2, mu_range, st) : updateFilterGaussian(zi, tau2, st);
-          if (!ok) {
-            type = kOutlier;  // :470-471, :481-482
-          } else {
-            // DepthFilter::updateSeeds picks the threshold by type (:214-221); isConverged: seed.h:145-153
-            const double cur_thresh = (type == kMapPointSeed || type == kMapPointSeedConverged)
-                                          ? P.dopt.mappoint_convergence_sigma2_thresh : P.dopt.seed_convergence_sigma2_thresh;
-            const double thresh = mu_range / cur_thresh;
-            if (st[1] < thresh * thresh) {
-              if (type == kCornerSeed) type = kCornerSeedConverged;
-              else if (type == kEdgeletSeed) type = kEdgeletSeedConverged;
-              else if (type == kMapPointSeed) type = kMapPointSeedConverged;
-            }
-            ++n_ok;
-          }
-        }
-      }
+      // DepthFilter::updateSeeds picks the threshold by type (:214-221)
+      const double cur_thresh = (type == kMapPointSeed || type == kMapPointSeedConverged) ? P.dopt.mappoint_convergence_sigma2_thresh
+                                                                                             : P.dopt.seed_convergence_sigma2_thresh;
+      MatchState m;
+      if (updateSeedOnce(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, type, st, mu_range, cur_thresh, P.px_error_angle,
+                         P.dopt.check_visibility != 0, P.dopt.check_convergence != 0, P.dopt.use_vogiatzis_update != 0, P.mopt, pwb, m, &mr))
+        ++n_ok;
     }
     if (P.match_results && g.r == 0) P.match_results[oi] = mr;
   }

@@ -323,3 +323,113 @@ def make_seed_sequence(seed, n_seeds=400, n_obs=8, cam=None, baseline_step=0.01,
     state[:, 2:] = 10.0
     return dict(ref_img=ref_img, cur_imgs=cur_imgs, T_cur_ref=np.array(T_cur_refs), cam=cam, px=px, f=f, level=level,
                 type=ftype, grad=grad, depth_true=depth, state=state, mu_range=mu_range, scene=scene)
+
+
+def make_reproject_scene(seed, n_kfs=4, n_per_kf=260, cam=None, integer_scores=False, max_rot_deg=2.5, max_trans=0.12, n_cur=1):
+    """A small map for the Reprojector: `n_kfs` keyframes and one current frame looking at the textured plane,
+    the keyframes' feature columns (landmarks with observation lists, converged and unconverged seeds, corners and edgelets) as
+    the flat tables of svo_reproj_map, and the entries Reprojector::reprojectFrames would visit (each landmark once, every seed).
+    World frame = camera frame of the texture image; T_f_w are the frame poses. `n_cur` current frames (cur_imgs, cur_Ts)
+    share the map."""
+    cam = dict(cam or EUROC_CAM)
+    base_img = make_image(seed, cam["width"], cam["height"], blur=1)
+    scene = PlaneScene(base_img, cam, normal=(0.1 * np.cos(seed), -0.12, 1.0), dist=3.5 + (seed % 3))
+    rng = np.random.default_rng(seed + 4242)
+    kf_T = [random_motion(seed * 17 + k, max_rot_deg, max_trans) for k in range(n_kfs)]
+    cur_Ts = [random_motion(seed * 17 + 99 + c, max_rot_deg, max_trans) for c in range(n_cur)]
+    kf_imgs = [scene.render(T) for T in kf_T]
+    cur_imgs = [scene.render(T) for T in cur_Ts]
+
+    def rays_to_world(T_f_w, px):
+        """3-D plane points (world) seen at pixels px of the frame with pose T_f_w, and their depth along the ray."""
+        f = cam_backproject(cam, px)
+        f = f / np.linalg.norm(f, axis=1)[:, None]
+        R_wf, t_wf = se3_to_Rt(se3_inv(T_f_w))
+        d_w = f @ R_wf.T
+        lam = (scene.d - scene.n @ t_wf) / (d_w @ scene.n)
+        return d_w * lam[:, None] + t_wf, f, lam
+
+    feats, score, state, point, feat_kf, kf_begin = [], [], [], [], [], [0]
+    pt_pos, pt_obs = [], []
+    depth_min = 1.5
+    mu_range = 1.0 / depth_min
+    for k in range(n_kfs):
+        img = kf_imgs[k]
+        px = pick_features(img, n_per_kf, seed * 31 + k, cell=20, lo=(24, 24), hi=(cam["width"] - 24, cam["height"] - 24))
+        Xw, f, lam = rays_to_world(kf_T[k], px)
+        g = img.astype(np.float64)
+        xi, yi = px[:, 0].astype(int), px[:, 1].astype(int)
+        gx = g[yi, xi + 1] - g[yi, xi - 1]
+        gy = g[yi + 1, xi] - g[yi - 1, xi]
+        nrm = np.hypot(gx, gy)
+        grad = np.stack([np.where(nrm > 0, gx / np.maximum(nrm, 1e-12), 1.0), np.where(nrm > 0, gy / np.maximum(nrm, 1e-12), 0.0)], -1)
+        for i in range(len(px)):
+            u = rng.uniform()
+            edgelet = rng.uniform() < 0.2
+            level = int(rng.integers(0, 3))
+            sc = float(rng.integers(11, 60)) if integer_scores else float(rng.uniform(11.0, 60.0))
+            st = np.array([1.0, 1.0, 10.0, 10.0])
+            pid = -1
+            if u < 0.5:      # landmark
+                ftype = K_EDGELET if edgelet else K_CORNER
+                pid = len(pt_pos)
+                pt_pos.append(Xw[i])
+                pt_obs.append([len(feats)])
+            elif u < 0.75:   # converged seed: tight around the true inverse depth
+                ftype = K_EDGELET_SEED_CONV if edgelet else K_CORNER_SEED_CONV
+                st[0] = (1.0 / lam[i]) * (1.0 + rng.normal() * 0.01)
+                st[1] = (mu_range / 300.0) ** 2
+            else:            # unconverged seed
+                ftype = K_EDGELET_SEED if edgelet else K_CORNER_SEED
+                if rng.uniform() < 0.3:   # one more good observation converges it (seed::isConverged at thresh 200)
+                    st[0] = (1.0 / lam[i]) * (1.0 + rng.normal() * 0.003)
+                    st[1] = (mu_range / 199.8) ** 2
+                else:
+                    st[0] = (1.0 / lam[i]) * (1.0 + rng.normal() * 0.05)
+                    st[1] = (0.08 * st[0]) ** 2
+            feats.append((px[i], f[i], grad[i], ftype, level))
+            score.append(sc); state.append(st); point.append(pid); feat_kf.append(k)
+        kf_begin.append(len(feats))
+    # a second observation of about half of the landmarks in the next keyframe (not an entry: the reprojector visits a point once)
+    n_first = len(feats)
+    extra = [[] for _ in range(n_kfs)]
+    for pid, X in enumerate(pt_pos):
+        if rng.uniform() < 0.5:
+            k2 = (feat_kf[pt_obs[pid][0]] + 1) % n_kfs
+            R, t = se3_to_Rt(kf_T[k2])
+            Xc = R @ X + t
+            px2 = cam_project(cam, Xc[None])[0]
+            if 30 <= px2[0] < cam["width"] - 30 and 30 <= px2[1] < cam["height"] - 30:
+                extra[k2].append((pid, px2, Xc / np.linalg.norm(Xc)))
+    # rebuild the tables keyframe by keyframe with the extra observations appended to each keyframe's block
+    new_feats, new_score, new_state, new_point, new_kf, new_begin, remap = [], [], [], [], [], [0], {}
+    for k in range(n_kfs):
+        for i in range(kf_begin[k], kf_begin[k + 1]):
+            remap[i] = len(new_feats)
+            new_feats.append(feats[i]); new_score.append(score[i]); new_state.append(state[i]); new_point.append(point[i]); new_kf.append(k)
+        for pid, px2, f2 in extra[k]:
+            pt_obs[pid].append(-len(new_feats) - 1)  # already a new index (negative marks "no remap")
+            new_feats.append((px2, f2, np.array([1.0, 0.0]), K_CORNER, int(rng.integers(0, 2))))
+            new_score.append(float(rng.uniform(11.0, 60.0))); new_state.append(np.array([1.0, 1.0, 10.0, 10.0]))
+            new_point.append(pid); new_kf.append(k)
+        new_begin.append(len(new_feats))
+    obs_begin, obs_feat = [0], []
+    for pid in range(len(pt_pos)):
+        for o in pt_obs[pid]:
+            obs_feat.append(remap[o] if o >= 0 else -o - 1)
+        obs_begin.append(len(obs_feat))
+    NF = len(new_feats)
+    feat = np.zeros(NF, np.dtype([("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("type", "<i4"), ("level", "<i4")]))
+    for i, (p, f, gr, t, l) in enumerate(new_feats):
+        feat["px"][i], feat["f"][i], feat["grad"][i], feat["type"][i], feat["level"][i] = p, f, gr, t, l
+    n_pts = len(pt_pos)
+    tables = dict(n_kfs=n_kfs, n_feat=NF, n_points=n_pts, n_obs=len(obs_feat),
+                  kf_T_f_w=np.array(kf_T), kf_seed_mu_range=np.full(n_kfs, mu_range), kf_feat_begin=np.array(new_begin, np.int32),
+                  feat=feat, feat_score=np.array(new_score), feat_seed_state=np.array(new_state), feat_point=np.array(new_point, np.int32),
+                  feat_kf=np.array(new_kf, np.int32), pt_pos=np.array(pt_pos).reshape(n_pts, 3),
+                  pt_n_failed=rng.integers(0, 4, n_pts).astype(np.int32), pt_n_succeeded=rng.integers(0, 6, n_pts).astype(np.int32),
+                  pt_obs_begin=np.array(obs_begin, np.int32), obs_feat=np.array(obs_feat, np.int32))
+    # entries: first observation of every landmark + every seed, keyframe by keyframe (= the original features)
+    entry_feat = np.array([remap[i] for i in range(n_first)], np.int32)
+    return dict(cam=cam, kf_imgs=kf_imgs, cur_img=cur_imgs[0], cur_T_f_w=cur_Ts[0], cur_imgs=cur_imgs, cur_Ts=np.array(cur_Ts),
+                tables=tables, entry_feat=entry_feat, scene=scene)

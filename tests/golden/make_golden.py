@@ -13,6 +13,8 @@ direct_ref_golden.npz outputs of the REFERENCE's own halfSample / align1D / alig
 frontend_ref_golden.npz outputs of the REFERENCE's own SparseImgAlign::run, Matcher::findMatchDirect / findEpipolarMatchDirect and
                       depth_filter_utils::updateSeed (oracle/_ref/libfrontend_ref.so: the reference sources compiled against
                       oracle/shim) on seeded inputs (tests/helpers.py:frontend_outputs): pins rows b, c1, c6-c7, d1-d3.
+reproject_ref_golden.npz outputs of the REFERENCE's own reprojector.cpp (getCandidate, sortCandidates*, matchCandidates,
+                      matchCandidate; compiled into libfrontend_ref.so) on the cases of tests/helpers.py:REPROJECT_CASES: pins row f1.
 klt_ref_golden.npz    outputs of the REFERENCE's own alignPyr2D (libdirect_ref.so) on the cases of tests/test_klt_cpu.py.
 Usage: python tests/golden/make_golden.py
 """
@@ -120,7 +122,21 @@ def klt_golden():
     print("klt_ref_golden.npz", os.path.getsize(os.path.join(HERE, "klt_ref_golden.npz")))
 
 
+def reproject_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_frontend_lib() is not None, "oracle/_ref/libfrontend_ref.so missing: run make -C oracle"
+    out = helpers.reproject_outputs(orc, "ref")
+    np.savez_compressed(os.path.join(HERE, "reproject_ref_golden.npz"), **out)
+    print("reproject_ref_golden.npz", os.path.getsize(os.path.join(HERE, "reproject_ref_golden.npz")))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # e.g. `make_golden.py reproject`: regenerate one fixture
+        for name in sys.argv[1:]:
+            globals()[name + "_golden"]()
+        sys.exit(0)
+    reproject_golden()
     klt_golden()
     frontend_golden()
     fast_golden()

@@ -206,3 +206,62 @@ def frontend_outputs(orc, which):
             n, ok = orc.ref_update_seeds(rf, cfs, sq["T_cur_ref"], oft, t, s, sq["mu_range"], orc.default_matcher_options(), **kw)
         out[f"seeds_{name}_types"], out[f"seeds_{name}_state"], out[f"seeds_{name}_ok"], out[f"seeds_{name}_n"] = t, s, ok, np.array(n)
     return out
+
+
+# ---- f1: Reprojector candidate matching ------------------------------------------------------------------------------------------
+IDENTITY7 = np.array([1.0, 0, 0, 0, 0, 0, 0])
+# (scene seed, max_n_features, n_features_in, occupied-cell fraction, sort_by_num_obs, scene kwargs)
+REPROJECT_CASES = [
+    (3, 120, 0, 0.10, 0, {}),
+    (3, 1000, 0, 0.10, 0, {}),                     # never reaches the cap: landmarks, converged and unconverged seeds are all tried
+    (4, 60, 10, 0.30, 0, {}),
+    (4, 0, 0, 0.0, 0, {}),                         # unlimited: occupancy ignored, every candidate tried
+    (5, 150, 0, 0.05, 1, {}),                      # sortCandidatesByNumObs
+    (6, 400, 200, 0.0, 0, dict(max_rot_deg=9.0, max_trans=0.5)),  # large motion: visibility / warp / alignment failures
+    (7, 30, 40, 0.0, 0, {}),                       # frame already holds more than max_n: exactly one more match is taken
+]
+REPROJ_INT_FIELDS = ("status", "order", "slot", "level", "type_out", "d_failed", "d_succeeded")
+REPROJ_FLOAT_FIELDS = ("cur_px", "px", "f", "grad", "seed_state")
+
+
+def reproject_px_error_angle(cam):
+    return float(np.arctan(1.0 / (2.0 * cam["fx"])) + np.arctan(1.0 / (2.0 * cam["fy"])))
+
+
+def reproject_case_inputs(case):
+    seed, max_n, n_in, occ_frac, by_obs, kw = case
+    sc = synth.make_reproject_scene(seed, **kw)
+    n_cells = ((sc["cam"]["width"] + 29) // 30) * ((sc["cam"]["height"] + 29) // 30)
+    occ = (np.random.default_rng(seed + 5).uniform(size=n_cells) < occ_frac).astype(np.uint8)
+    return sc, occ
+
+
+def reproject_outputs(orc, which):
+    """Every REPROJECT_CASES case through the oracle ("orc") or the reference's own compiled reprojector.cpp ("ref")."""
+    out = {}
+    for ci, case in enumerate(REPROJECT_CASES):
+        seed, max_n, n_in, occ_frac, by_obs, kw = case
+        sc, occ = reproject_case_inputs(case)
+        keep = []
+        kfs = [orc.make_frame(orc.create_img_pyramid(im, 5), sc["cam"], IDENTITY7, T, keep=keep)
+               for im, T in zip(sc["kf_imgs"], sc["tables"]["kf_T_f_w"])]
+        cur = orc.make_frame(orc.create_img_pyramid(sc["cur_img"], 5), sc["cam"], IDENTITY7, sc["cur_T_f_w"], keep=keep)
+        opt = orc.ReprojOptions(30, max_n, 1, 0, by_obs, 200.0, reproject_px_error_angle(sc["cam"]))
+        res, st = orc.reproject_match(kfs, sc["tables"], cur, sc["entry_feat"], n_in, occ, opt, which=which)
+        for k in REPROJ_INT_FIELDS + REPROJ_FLOAT_FIELDS:
+            out[f"c{ci}_{k}"] = res[k]
+        out[f"c{ci}_stats"] = np.array([st["n_candidates"], st["n_trials"], st["n_matches"], st["n_consumed"]])
+        out[f"c{ci}_occ"] = occ
+    return out
+
+
+def assert_reproject_equal(a, b, px_tol, rel_tol, tag=""):
+    """Two reproject_outputs dicts: integer fields identical, sub-pixel results within px_tol, seed states within rel_tol."""
+    for ci in range(len(REPROJECT_CASES)):
+        for k in REPROJ_INT_FIELDS + ("stats", "occ"):
+            assert np.array_equal(a[f"c{ci}_{k}"], b[f"c{ci}_{k}"]), (tag, ci, k)
+        assert np.abs(a[f"c{ci}_cur_px"] - b[f"c{ci}_cur_px"]).max() < 1e-9, (tag, ci)
+        assert np.abs(a[f"c{ci}_px"] - b[f"c{ci}_px"]).max() < px_tol, (tag, ci)
+        assert np.abs(a[f"c{ci}_f"] - b[f"c{ci}_f"]).max() < 1e-5, (tag, ci)
+        assert np.abs(a[f"c{ci}_grad"] - b[f"c{ci}_grad"]).max() < 1e-9, (tag, ci)
+        np.testing.assert_allclose(a[f"c{ci}_seed_state"], b[f"c{ci}_seed_state"], rtol=rel_tol, atol=1e-12)
