@@ -13,8 +13,9 @@
 //   reproj_candidates_kernel  one thread per entry: world point -> isVisible -> 8 px margin -> cur_px, grid cell, sort key
 //   reproj_sort_kernel        one CTA per frame: bitonic sort of the candidates by the reference's comparator (ties keep the
 //                             visiting order), then a second sort by (cell, position) that yields per-cell candidate queues
-//   reproj_match_kernel       one 8-lane group per (frame, cell): walks the cell's queue until the first match
-//                             (findMatchDirect for landmarks and converged seeds, updateSeed for unconverged seeds)
+//   reproj_match_kernel       one 8-lane group per (frame, cell): walks the cell's queue until the first match, in two
+//                             passes: <false> findMatchDirect only (landmarks, converged seeds); <true> continues the queues
+//                             that reached an unconverged seed without a winner (updateSeed with the epipolar search)
 //   reproj_commit_kernel      one CTA per frame: prefix count of the winners in list order, stop position, statuses, slots,
 //                             occupancy, statistics; attempts behind the stop position are rolled back to "not reached"
 // No host round trip between the stages.
@@ -26,7 +27,14 @@ using namespace svo_dev;
 namespace {
 
 constexpr int kMaxPerFrame = 4096;  // entries per current frame and grid cells (shared-memory sort capacity)
-constexpr int kThreads = 128;
+// CTA shape / occupancy target of the match stage (macros for A/B builds; measured on the B200, see profiles/).
+#ifndef SVO_REPROJ_THREADS
+#define SVO_REPROJ_THREADS 128
+#endif
+#ifndef SVO_REPROJ_MINB
+#define SVO_REPROJ_MINB 3
+#endif
+constexpr int kThreads = SVO_REPROJ_THREADS;
 constexpr int kGroupsPerCta = kThreads / kGroup;
 constexpr int kSortThreads = 512;
 
@@ -52,6 +60,9 @@ struct ReprojParams {
   unsigned* cell_list; // [E] (cell << 13 | position), grouped by cell, positions ascending
   int* cell_begin;     // [F][n_cells] first index into cell_list of the frame, -1 = empty cell
   int* cell_success;   // [F][n_cells] position of the cell's winner, -1 = none
+  int* resume_cell;    // [F * n_cells] compact list of (frame * n_cells + cell) handed over by the direct-match pass to the full pass
+  int* resume_q;       // [F * n_cells] queue index where each of them continues
+  int* resume_count;   // [1]
   int* n_cand;         // [F]
 };
 
@@ -238,46 +249,87 @@ SVO_D int closeViewObs(const svo_reproj_map& map, int pt, const V3d& pos, const 
   return min_cos_angle < 0.4 ? -1 : best;  // observations more than 60 degrees away are useless
 }
 
-__global__ void __launch_bounds__(kThreads) reproj_match_kernel(const ReprojParams P, int items_per_frame) {
+// FULL = false: the direct-match pass — findMatchDirect only (landmarks and converged seeds, which the reference's order puts
+// first). A queue that reaches an unconverged seed before it has a winner is handed over (cell_resume) to the FULL pass,
+// which also carries updateSeed with the epipolar search. Splitting keeps the common pass small: with everything inlined in
+// one kernel half of the warp stalls were instruction-fetch misses (profiles/).
+template <bool FULL>
+__global__ void __launch_bounds__(kThreads, FULL ? SVO_REPROJ_MINB : 4) reproj_match_kernel(const ReprojParams P, int items_per_frame, int from_resume) {
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
   const Group g = makeGroup();
   const int gi = threadIdx.x / kGroup;
-  const int item = blockIdx.x * kGroupsPerCta + gi;
-  const int j = blockIdx.y;
-  if (item >= items_per_frame) return;
+  int item = blockIdx.x * kGroupsPerCta + gi;
+  int j = blockIdx.y;
+  int q_resume = -1;
+  if (from_resume) {  // 1-D grid over the compact hand-over list: four busy queues per warp
+    const int k = item;
+    item = items_per_frame;  // no work unless the list holds an entry for this group
+    j = 0;
+    if (k < *P.resume_count) {
+      const int jc = P.resume_cell[k];
+      j = jc / P.n_cells;
+      item = jc - j * P.n_cells;
+      q_resume = P.resume_q[k];
+    }
+  }
   uint8_t* pwb = s_pwb + gi * kPwbPitch;
   int base;
   frameEntries(P, j, &base);
   const int n_cand = P.n_cand[j];
   const bool unlimited = P.opt.max_n_features <= 0;  // matchCandidates ignores the grid when max_n_features_per_frame == 0
-  int q, q_end;
+  int q = 0, q_end = 0;
   unsigned cell = 0;
   bool occupied = false;
-  if (unlimited) {
-    q = item; q_end = min(item + 1, n_cand);
-  } else {
-    q = P.cell_begin[(size_t)j * P.n_cells + item];
-    if (q < 0) return;
-    q_end = n_cand;
-    cell = (unsigned)item;
-    occupied = P.occupancy[(size_t)j * P.n_cells + item] != 0;
+  if (item < items_per_frame) {
+    if (unlimited) {
+      q = item; q_end = min(item + 1, n_cand);
+    } else {
+      q = from_resume ? q_resume : P.cell_begin[(size_t)j * P.n_cells + item];
+      q_end = q < 0 ? 0 : n_cand;
+      q = max(q, 0);
+      cell = (unsigned)item;
+      occupied = P.occupancy[(size_t)j * P.n_cells + item] != 0;
+    }
   }
   const SE3d T_cur_w = se3Load(P.cur_T_f_w + 7 * (size_t)j);
   const int cf = P.cur_frame_idx ? P.cur_frame_idx[j] : j;
   bool found = false;
-  for (; q < q_end; ++q) {
-    int p = q;
-    if (!unlimited) {
-      const unsigned key = P.cell_list[base + q];
-      if ((key >> 13) != cell) break;
-      p = (int)(key & 8191u);
+  // Rounds: every queue of the warp first skips ahead to its next candidate that needs an attempt (cheap, divergent), then
+  // the whole warp reconverges on the vote and the attempts of the round run in lock-step.
+  for (;;) {
+    int p = -1;
+    while (q < q_end) {
+      int pp = q;
+      if (!unlimited) {
+        const unsigned key = P.cell_list[base + q];
+        if ((key >> 13) != cell) { q = q_end; break; }
+        pp = (int)(key & 8191u);
+      }
+      if (occupied || found) {
+        if (g.r == 0) P.results[P.sorted_entry[base + pp]].status = SVO_REPROJ_SKIPPED;
+        ++q;
+        continue;
+      }
+      if (!FULL) {
+        const int t = P.map.feat[P.entry_feat[P.sorted_entry[base + pp]]].type;
+        if (P.map.feat_point[P.entry_feat[P.sorted_entry[base + pp]]] < 0 && (t == kEdgeletSeed || t == kCornerSeed || t == kMapPointSeed)) {
+          if (g.r == 0) {  // the full pass continues here
+            const int k = atomicAdd(P.resume_count, 1);
+            P.resume_cell[k] = j * P.n_cells + item;
+            P.resume_q[k] = q;
+          }
+          q = q_end;
+          break;
+        }
+      }
+      p = pp;
+      ++q;
+      break;
     }
+    if (!__any_sync(0xffffffffu, p >= 0)) break;
+    if (p < 0) continue;
     const int e = P.sorted_entry[base + p];
     svo_reproj_result* r = P.results + e;
-    if (occupied || found) {
-      if (g.r == 0) r->status = SVO_REPROJ_SKIPPED;
-      continue;
-    }
     const int fi = P.entry_feat[e];
     const int ctype = P.map.feat[fi].type;
     const int pt = P.map.feat_point[fi];
@@ -289,38 +341,40 @@ __global__ void __launch_bounds__(kThreads) reproj_match_kernel(const ReprojPara
                     P.map.feat_seed_state[4 * (size_t)fi + 2], P.map.feat_seed_state[4 * (size_t)fi + 3]};
     double grad_x = 0.0, grad_y = 0.0;
     bool ok = false;
+    // which reference feature is matched, from which keyframe, at which depth — then ONE call site per matcher entry point
+    // (the four cell queues of a warp run in lock-step as long as they are in the same code)
+    int mode = 0;  // 1 = findMatchDirect, 2 = updateSeed
+    int fr = fi;   // the feature whose patch is warped
+    double ref_depth = 0.0;
+    V3d pos{0, 0, 0};
     if (pt < 0) {
-      svo_feature ft = P.map.feat[fi];
-      const int kf = P.map.feat_kf[fi];
-      const int rf = P.map.kf_frame_idx ? P.map.kf_frame_idx[kf] : kf;
-      const SE3d T = se3Mul(T_cur_w, se3Inv(se3Load(P.map.kf_T_f_w + 7 * (size_t)kf)));
       if (ctype == kEdgeletSeedConverged || ctype == kCornerSeedConverged || ctype == kMapPointSeedConverged) {
-        mr = findMatchDirect(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, 1.0 / st[0], guess_x, guess_y, P.mopt, pwb, m);
-        ok = mr == kSuccess;
+        mode = 1;
+        ref_depth = 1.0 / st[0];  // getSeedDepth
       } else if (ctype == kEdgeletSeed || ctype == kCornerSeed || ctype == kMapPointSeed) {
+        mode = 2;
+      }
+    } else {
+      pos = V3d{P.map.pt_pos[3 * (size_t)pt], P.map.pt_pos[3 * (size_t)pt + 1], P.map.pt_pos[3 * (size_t)pt + 2]};
+      fr = closeViewObs(P.map, pt, pos, se3Inv(T_cur_w).t);
+      if (fr >= 0) mode = 1;
+    }
+    if (mode) {
+      svo_feature ft = P.map.feat[fr];
+      const int kf = P.map.feat_kf[fr];
+      const int rf = P.map.kf_frame_idx ? P.map.kf_frame_idx[kf] : kf;
+      const SE3d T_ref_w = se3Load(P.map.kf_T_f_w + 7 * (size_t)kf);
+      if (pt >= 0) ref_depth = norm3(se3Inv(T_ref_w).t - pos);  // (ref_frame->pos() - landmark->pos()).norm()
+      const SE3d T = se3Mul(T_cur_w, se3Inv(T_ref_w));
+      if (mode == 1) {
+        mr = findMatchDirect(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, ref_depth, guess_x, guess_y, P.mopt, pwb, m);
+        ok = mr == kSuccess;
+        if (pt >= 0) { d_failed = !ok; d_succeeded = ok; }
+      } else if (FULL) {
         ok = updateSeedOnce(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, type_out, st, P.map.kf_seed_mu_range[kf],
                             P.opt.seed_sigma2_thresh, P.px_error_angle, false, false, true, P.mopt, pwb, m, &mr);
       }
       grad_x = ft.grad[0]; grad_y = ft.grad[1];
-    } else {
-      const V3d pos{P.map.pt_pos[3 * (size_t)pt], P.map.pt_pos[3 * (size_t)pt + 1], P.map.pt_pos[3 * (size_t)pt + 2]};
-      const int fo = closeViewObs(P.map, pt, pos, se3Inv(T_cur_w).t);
-      if (fo >= 0) {
-        const svo_feature ft = P.map.feat[fo];
-        const int kf = P.map.feat_kf[fo];
-        const int rf = P.map.kf_frame_idx ? P.map.kf_frame_idx[kf] : kf;
-        const SE3d T_ref_w = se3Load(P.map.kf_T_f_w + 7 * (size_t)kf);
-        const double ref_depth = norm3(se3Inv(T_ref_w).t - pos);
-        const SE3d T = se3Mul(T_cur_w, se3Inv(T_ref_w));
-        mr = findMatchDirect(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, ref_depth, guess_x, guess_y, P.mopt, pwb, m);
-        if (mr != kSuccess) {
-          d_failed = 1;
-        } else {
-          d_succeeded = 1;
-          grad_x = ft.grad[0]; grad_y = ft.grad[1];
-          ok = true;
-        }
-      }
     }
     __syncwarp(g.mask);
     if (g.r == 0) {
@@ -495,6 +549,9 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   P.cell_list = (unsigned*)st.scratch(ne * sizeof(unsigned));
   P.cell_begin = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
   P.cell_success = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
+  P.resume_cell = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
+  P.resume_q = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
+  P.resume_count = (int*)st.scratch(sizeof(int));
   P.n_cand = (int*)st.scratch((size_t)F * sizeof(int));
   if (st.failed()) return st.finish();
 
@@ -515,8 +572,19 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   reproj_sort_kernel<<<F, kSortThreads, sort_smem, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   const int items = opt->max_n_features <= 0 ? per_frame_cap : P.n_cells;
-  reproj_match_kernel<<<dim3((items + kGroupsPerCta - 1) / kGroupsPerCta, F), kThreads, 0, ctx->stream>>>(P, items);
-  SVO_LAUNCH_CHECK(ctx);
+  const dim3 mgrid((items + kGroupsPerCta - 1) / kGroupsPerCta, F);
+  if (opt->max_n_features <= 0) {  // unlimited: one candidate per item, every kind of candidate
+    reproj_match_kernel<true><<<mgrid, kThreads, 0, ctx->stream>>>(P, items, 0);
+    SVO_LAUNCH_CHECK(ctx);
+  } else {
+    SVO_CUDA_TRY(ctx, cudaMemsetAsync(P.resume_count, 0, sizeof(int), ctx->stream));
+    reproj_match_kernel<false><<<mgrid, kThreads, 0, ctx->stream>>>(P, items, 0);
+    SVO_LAUNCH_CHECK(ctx);
+    // the hand-over list is at most F * n_cells long; groups beyond its actual length (known only on the device) exit at once
+    const long long all = (long long)F * P.n_cells;
+    reproj_match_kernel<true><<<(unsigned)((all + kGroupsPerCta - 1) / kGroupsPerCta), kThreads, 0, ctx->stream>>>(P, items, 1);
+    SVO_LAUNCH_CHECK(ctx);
+  }
   reproj_commit_kernel<<<F, 256, 0, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();

@@ -180,6 +180,45 @@ def main():
                 "config": f"{Sq} seeds x {O} ordered observations in ONE launch ({NSEQ_U} unique keyframes x {NOBS_U} unique observation frames, tiled)",
                 "seed_observations_per_s": Sq * O / (ms_s * 1e-3), "ms": ms_s, "success_frac": float(n_succ.item()) / (Sq * O),
                 "cpu_baseline": {"seed_observations_per_s": cpu_s, "cores": NT, "kind": "port"}})
+    # ---- (f1) Reprojector: getCandidate + candidate sort + per-cell matching for F current frames sharing one map ----
+    del ref, cur
+    sc = synth.make_reproject_scene(21, n_cur=8)
+    K, F = len(sc["kf_imgs"]), 1024
+    ref = capi.Pyramid(ctx, K, 752, 480, 5); cur = capi.Pyramid(ctx, 8, 752, 480, 5)
+    ref.upload(np.stack(sc["kf_imgs"])); cur.upload(np.stack(sc["cur_imgs"])); ref.build(); cur.build()
+    tb = dict(sc["tables"])
+    tb["feat"] = capi.make_features(tb["feat"]["px"], tb["feat"]["f"], tb["feat"]["grad"], tb["feat"]["type"], tb["feat"]["level"])
+    d_tb = {k: (t(v.view(np.uint8) if v.dtype.fields else v) if isinstance(v, np.ndarray) else v) for k, v in tb.items()}
+    ef = np.ascontiguousarray(sc["entry_feat"], np.int32)
+    E1 = len(ef)
+    d_idx = t((np.arange(F) % 8).astype(np.int32))
+    d_T = t(np.ascontiguousarray(sc["cur_Ts"][np.arange(F) % 8], np.float64))
+    d_nin, d_eb, d_ef = t(np.zeros(F, np.int32)), t((np.arange(F + 1) * E1).astype(np.int32)), t(np.tile(ef, F))
+    occ0 = torch.zeros((F, 416), dtype=torch.uint8, device=dev)
+    d_occ = occ0.clone()
+    d_res = torch.zeros(F * E1 * capi.REPROJ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(F * capi.REPROJ_STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    ropt = capi.reprojector_options(max_n_features=120)
+
+    def reproj():
+        d_occ.copy_(occ0)
+        capi.reproject_match(ctx, ref, cur, cam, cam, d_tb, d_T, d_nin, d_eb, d_ef, d_occ, ropt, cur_frame_idx=d_idx, results=d_res, stats=d_st)
+    ms_r = timed(reproj, stream)
+    stats = d_st.cpu().numpy().view(capi.REPROJ_STATS_DTYPE)
+    keep3 = []
+    ident = np.array([1.0, 0, 0, 0, 0, 0, 0])
+    okfs = [orc.make_frame(orc.create_img_pyramid(im, 5), sc["cam"], ident, T, keep=keep3) for im, T in zip(sc["kf_imgs"], sc["tables"]["kf_T_f_w"])]
+    ocur = [orc.make_frame(orc.create_img_pyramid(im, 5), sc["cam"], ident, T, keep=keep3) for im, T in zip(sc["cur_imgs"], sc["cur_Ts"])]
+    oopt = orc.ReprojOptions(30, 120, 1, 0, 0, 200.0, float(np.arctan(1 / (2 * sc["cam"]["fx"])) + np.arctan(1 / (2 * sc["cam"]["fy"]))))
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 4.0:
+        orc.reproject_match(okfs, sc["tables"], ocur[reps % 8], ef, 0, np.zeros(416, np.uint8), oopt); reps += 1
+    cpu_r = reps / (time.perf_counter() - t0)
+    out.append({"path": "f1: Reprojector (getCandidate + sort + matchCandidates with findMatchDirect / updateSeed)",
+                "config": f"{F} current frames x {E1} map features ({K} keyframes, 8 unique current frames tiled), max 120 features, cell 30",
+                "frames_per_s": F / (ms_r * 1e-3), "ms": ms_r, "mean_trials": float(stats["n_trials"].mean()),
+                "mean_matches": float(stats["n_matches"].mean()),
+                "cpu_baseline": {"frames_per_s_single_thread": cpu_r, "kind": "port (oracle; pinned to the reference's compiled reprojector.cpp)"}})
     for o in out:
         print(json.dumps(o))
 

@@ -77,3 +77,18 @@ for _ in range(REPS):
     ns, _ = capi.update_seeds(ctx, ref, cur, cam, cam, ftq, ty, st, np.full(n * rep, q["mu_range"]), obs, obs, q["T_cur_ref"], mopt,
                               capi.depth_filter_options(), want_match_results=False)
 print("update_seeds successes", ns)
+del ref, cur
+
+# (f1): reprojector, 296 current frames sharing one map
+sc = synth.make_reproject_scene(21, n_cur=8)
+K, F = len(sc["kf_imgs"]), 296
+ref = capi.Pyramid(ctx, K, 752, 480, 5); cur = capi.Pyramid(ctx, 8, 752, 480, 5)
+ref.upload(np.stack(sc["kf_imgs"])); cur.upload(np.stack(sc["cur_imgs"])); ref.build(); cur.build()
+tb = dict(sc["tables"])
+tb["feat"] = capi.make_features(tb["feat"]["px"], tb["feat"]["f"], tb["feat"]["grad"], tb["feat"]["type"], tb["feat"]["level"])
+ef = np.ascontiguousarray(sc["entry_feat"], np.int32)
+for _ in range(REPS):
+    res, st = capi.reproject_match(ctx, ref, cur, cam, cam, tb, np.ascontiguousarray(sc["cur_Ts"][np.arange(F) % 8]), np.zeros(F, np.int32),
+                                   (np.arange(F + 1) * len(ef)).astype(np.int32), np.tile(ef, F), np.zeros((F, 416), np.uint8),
+                                   capi.reprojector_options(max_n_features=120), cur_frame_idx=(np.arange(F) % 8).astype(np.int32))
+print("reproject matches/frame", float(st["n_matches"].mean()), "trials/frame", float(st["n_trials"].mean()))
