@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(kThreads, 6) update_seeds_kernel(const SeedPar
   double st[4] = {P.state[4 * (size_t)s], P.state[4 * (size_t)s + 1], P.state[4 * (size_t)s + 2], P.state[4 * (size_t)s + 3]};
   const double mu_range = P.seed_mu_range[s];
   const int rf = P.ref_frame_idx ? P.ref_frame_idx[s] : 0;
-  const V3d f_ref{ft.f[0], ft.f[1], ft.f[2]};
   int n_ok = 0;
   for (int o = 0; o < P.n_obs; ++o) {
     const size_t oi = (size_t)o * P.S + s;

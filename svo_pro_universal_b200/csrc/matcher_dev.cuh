@@ -14,7 +14,10 @@
 namespace svo_dev {
 
 constexpr int kGroup = 8;            // lanes per feature
-constexpr int kPwbPitch = 112;       // bytes of shared memory per group for the 10x10 patch (100 rounded up)
+constexpr int kPatchBytes = 112;     // the 10x10 patch (100 bytes rounded up to 16)
+constexpr int kRedStride = 68;       // floats per ordered-sum row: 64 terms + 4 of padding (conflict-free 128-bit reads)
+constexpr int kRedRows = 4;          // sums formed side by side (lanes 0..3 of the group)
+constexpr int kPwbPitch = kPatchBytes + kRedRows * kRedStride * 4;  // bytes of shared memory per group: patch + ordered-sum scratch
 
 enum MatchResult {  // svo::Matcher::MatchResult, matcher.h:56-68
   kSuccess = 0, kFailScore, kFailTriangulation, kFailVisibility, kFailWarp, kFailAlignment, kFailRange, kFailAngle,
@@ -164,16 +167,43 @@ SVO_D unsigned byte9(unsigned a, unsigned b, unsigned c, int i) { return i < 4 ?
 // interpolated intensities / residuals of its patch row in parallel, then the running sums are carried through the
 // rows in order (owner lane adds its 8 pixels, result is broadcast with a shuffle), so every float operation happens in
 // the reference's order. The translation unit is compiled with -fmad=false so no multiply-add is contracted.
-template <int NK>
-SVO_D void bcastFrom(const Group& g, float (&acc)[NK], int owner) {
+// Ordered float sums. Each lane holds 8 consecutive terms (its patch row) of each of NK sums over the 64 patch pixels. The
+// terms go through the group's shared-memory scratch so that lane k owns sum k and adds its 64 terms one by one in raster
+// order — the NK chains run side by side on NK lanes instead of one after the other on the row's owner lane, and every
+// float addition still happens in the reference's order. SUB: acc = acc - term (Jres), else acc = acc + term (H).
+// term(k, x): the x-th term of sum k in this lane's row; `first` = the sum handled by lane 0 (sums first..first+NK-1).
+template <int NK, bool SUB, class F>
+SVO_D void orderedSums(const Group& g, float* red, F term, float (&acc)[NK]) {
+  static_assert(NK <= kRedRows, "one sum per lane, kRedRows rows of scratch");
 #pragma unroll
-  for (int k = 0; k < NK; ++k) acc[k] = __shfl_sync(g.mask, acc[k], owner, kGroup);
+  for (int k = 0; k < NK; ++k) {
+    float4 lo, hi;
+    lo.x = term(k, 0); lo.y = term(k, 1); lo.z = term(k, 2); lo.w = term(k, 3);
+    hi.x = term(k, 4); hi.y = term(k, 5); hi.z = term(k, 6); hi.w = term(k, 7);
+    float4* dst = reinterpret_cast<float4*>(red + k * kRedStride + g.r * 8);
+    dst[0] = lo; dst[1] = hi;
+  }
+  __syncwarp(g.mask);
+  float a = 0.f;
+  if (g.r < NK) {
+    const float4* src = reinterpret_cast<const float4*>(red + g.r * kRedStride);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 v = src[i];
+      if (SUB) { a = a - v.x; a = a - v.y; a = a - v.z; a = a - v.w; }
+      else { a = a + v.x; a = a + v.y; a = a + v.z; a = a + v.w; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NK; ++k) acc[k] = __shfl_sync(g.mask, a, k, kGroup);
+  __syncwarp(g.mask);  // the scratch may be rewritten
 }
 
-// pwb: the group's 10x10 patch in shared memory. px in/out (level px). Returns converged.
-SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n_iter, bool est_offset, bool est_gain,
+// pwb: the group's 10x10 patch in shared memory, followed by the ordered-sum scratch. px in/out (level px). Returns converged.
+SVO_D bool align2D(const Group& g, const ImgView& img, uint8_t* pwb, int n_iter, bool est_offset, bool est_gain,
                    double& px_x, double& px_y) {
   const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
+  float* red = reinterpret_cast<float*>(pwb + kPatchBytes);
   float rdx[8], rdy[8], rref[8];
 #pragma unroll
   for (int x = 0; x < 8; ++x) {
@@ -182,17 +212,25 @@ SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n
     rref[x] = (float)it[x];
   }
   const float J2 = est_offset ? 1.0f : 0.0f;
-  float h[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33, H += J*J^T in raster order (:261)
-  for (int r = 0; r < kGroup; ++r) {
-    if (g.r == r) {
+  // H += J*J^T pixel by pixel in raster order (:261); 00 01 02 03 11 12 13 22 | 23 33
+  float h[10];
+  {
+    float ha[4], hb[4], hc[2];
+    orderedSums<4, false>(g, red, [&](int k, int x) {
+      const float J0 = rdx[x], J1 = rdy[x], J3 = est_gain ? -1.0f * rref[x] : 0.0f;
+      return k == 0 ? J0 * J0 : k == 1 ? J0 * J1 : k == 2 ? J0 * J2 : J0 * J3;
+    }, ha);
+    orderedSums<4, false>(g, red, [&](int k, int x) {
+      const float J1 = rdy[x], J3 = est_gain ? -1.0f * rref[x] : 0.0f;
+      return k == 0 ? J1 * J1 : k == 1 ? J1 * J2 : k == 2 ? J1 * J3 : J2 * J2;
+    }, hb);
+    orderedSums<2, false>(g, red, [&](int k, int x) {
+      const float J3 = est_gain ? -1.0f * rref[x] : 0.0f;
+      return k == 0 ? J2 * J3 : J3 * J3;
+    }, hc);
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const float J0 = rdx[x], J1 = rdy[x], J3 = est_gain ? -1.0f * rref[x] : 0.0f;
-        h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J0 * J3;
-        h[4] += J1 * J1; h[5] += J1 * J2; h[6] += J1 * J3; h[7] += J2 * J2; h[8] += J2 * J3; h[9] += J3 * J3;
-      }
-    }
-    bcastFrom(g, h, r);
+    for (int k = 0; k < 4; ++k) { h[k] = ha[k]; h[4 + k] = hb[k]; }
+    h[8] = hc[0]; h[9] = hc[1];
   }
   float H[4][4] = {{h[0], h[1], h[2], h[3]}, {h[1], h[4], h[5], h[6]}, {h[2], h[5], h[7], h[8]}, {h[3], h[6], h[8], h[9]}};
   if (!est_offset) H[2][2] = 1.0f;
@@ -221,19 +259,12 @@ SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n
                        wBL * (float)byte9(a1, b1, c1, x) + wBR * (float)byte9(a1, b1, c1, x + 1);
       res[x] = sp - alpha * rref[x] + mean_diff;  // :322-323
     }
-    float j[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; r < kGroup; ++r) {
-      if (g.r == r) {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          j[0] -= res[x] * rdx[x];
-          j[1] -= res[x] * rdy[x];
-          if (est_offset) j[2] -= res[x];
-          if (est_gain) j[3] -= (-1.0f * res[x]) * rref[x];
-        }
-      }
-      bcastFrom(g, j, r);
-    }
+    // Jres -= J * res in raster order (:325-328); the sums of disabled parameters are not formed (they are zeroed below)
+    float j[4];
+    orderedSums<4, true>(g, red, [&](int k, int x) {
+      return k == 0 ? res[x] * rdx[x] : k == 1 ? res[x] * rdy[x] : k == 2 ? (est_offset ? res[x] : 0.f)
+             : (est_gain ? (-1.0f * res[x]) * rref[x] : 0.f);
+    }, j);
     if (!est_offset) j[2] = 0.f;
     if (!est_gain) j[3] = 0.f;
     const float up0 = Hinv[0][0] * j[0] + Hinv[0][1] * j[1] + Hinv[0][2] * j[2] + Hinv[0][3] * j[3];
@@ -247,9 +278,10 @@ SVO_D bool align2D(const Group& g, const ImgView& img, const uint8_t* pwb, int n
   return converged;
 }
 
-SVO_D bool align1D(const Group& g, const ImgView& img, double dir_x, double dir_y, const uint8_t* pwb, int n_iter, bool est_offset,
+SVO_D bool align1D(const Group& g, const ImgView& img, double dir_x, double dir_y, uint8_t* pwb, int n_iter, bool est_offset,
                    bool est_gain, double& px_x, double& px_y, double* h_inv) {
   const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
+  float* red = reinterpret_cast<float*>(pwb + kPatchBytes);
   float rdv[8], rref[8];
 #pragma unroll
   for (int x = 0; x < 8; ++x) {
@@ -259,16 +291,20 @@ SVO_D bool align1D(const Group& g, const ImgView& img, double dir_x, double dir_
     rref[x] = (float)it[x];
   }
   const float J1 = est_offset ? 1.0f : 0.0f;
-  float h[6] = {0, 0, 0, 0, 0, 0};  // 00 01 02 11 12 22
-  for (int r = 0; r < kGroup; ++r) {
-    if (g.r == r) {
+  float h[6];  // 00 01 02 11 | 12 22
+  {
+    float ha[4], hb[2];
+    orderedSums<4, false>(g, red, [&](int k, int x) {
+      const float J0 = rdv[x], J2 = est_gain ? -1.0f * rref[x] : 0.0f;
+      return k == 0 ? J0 * J0 : k == 1 ? J0 * J1 : k == 2 ? J0 * J2 : J1 * J1;
+    }, ha);
+    orderedSums<2, false>(g, red, [&](int k, int x) {
+      const float J2 = est_gain ? -1.0f * rref[x] : 0.0f;
+      return k == 0 ? J1 * J2 : J2 * J2;
+    }, hb);
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const float J0 = rdv[x], J2 = est_gain ? -1.0f * rref[x] : 0.0f;
-        h[0] += J0 * J0; h[1] += J0 * J1; h[2] += J0 * J2; h[3] += J1 * J1; h[4] += J1 * J2; h[5] += J2 * J2;
-      }
-    }
-    bcastFrom(g, h, r);
+    for (int k = 0; k < 4; ++k) h[k] = ha[k];
+    h[4] = hb[0]; h[5] = hb[1];
   }
   float H[3][3] = {{h[0], h[1], h[2]}, {h[1], h[3], h[4]}, {h[2], h[4], h[5]}};
   if (!est_offset) H[1][1] = 1.0f;
@@ -298,18 +334,10 @@ SVO_D bool align1D(const Group& g, const ImgView& img, double dir_x, double dir_
                        wBL * (float)byte9(a1, b1, c1, x) + wBR * (float)byte9(a1, b1, c1, x + 1);
       res[x] = ci - alpha * rref[x] + mean_diff;  // :137-139
     }
-    float j[3] = {0.f, 0.f, 0.f};
-    for (int r = 0; r < kGroup; ++r) {
-      if (g.r == r) {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          j[0] -= res[x] * rdv[x];
-          if (est_offset) j[1] -= res[x];
-          if (est_gain) j[2] -= (-1.0f * res[x]) * rref[x];
-        }
-      }
-      bcastFrom(g, j, r);
-    }
+    float j[3];
+    orderedSums<3, true>(g, red, [&](int k, int x) {
+      return k == 0 ? res[x] * rdv[x] : k == 1 ? (est_offset ? res[x] : 0.f) : (est_gain ? (-1.0f * res[x]) * rref[x] : 0.f);
+    }, j);
     if (!est_offset) j[1] = 0.f;
     if (!est_gain) j[2] = 0.f;
     const float up0 = Hinv[0][0] * j[0] + Hinv[0][1] * j[1] + Hinv[0][2] * j[2];
@@ -381,7 +409,7 @@ SVO_D int findMatchDirect(const Group& g, const PyrView& ref_pyr, int ref_frame,
 
 // findLocalMatch (matcher.cpp:262-289)
 SVO_D int findLocalMatch(const Group& g, const PyrView& cur_pyr, int cur_frame, double dir_x, double dir_y, int patch_level,
-                         const svo_matcher_options& opt, bool align_1d, const uint8_t* pwb, MatchState& m) {
+                         const svo_matcher_options& opt, bool align_1d, uint8_t* pwb, MatchState& m) {
   const double sc = (double)(1 << patch_level);
   double ps_x = m.px_x / sc, ps_y = m.px_y / sc;
   const ImgView cur = levelView(cur_pyr, cur_frame, patch_level);
@@ -482,14 +510,13 @@ SVO_D int findEpipolarMatchDirect(const Group& g, const PyrView& ref_pyr, int re
   if (!warpAffine10(g, m.A, levelView(ref_pyr, ref_frame, ft.level), ft.px[0], ft.px[1], ft.level, m.search_level, pwb))
     return kFailWarp;
 
-  if (m.epi_length_pyramid < 2.0) {
+  // matcher.cpp:209-218: a short epipolar segment goes straight to the local (sub-pixel) match at its mid-point; the scan
+  // below is skipped. Both ways end in ONE findLocalMatch / triangulation call site (code size: these kernels stall on
+  // instruction fetch when every path carries its own inlined copy of the alignment code, profiles/).
+  const bool short_epi = m.epi_length_pyramid < 2.0;
+  if (short_epi) {
     m.px_x = (px_A.x + px_B.x) / 2.0; m.px_y = (px_A.y + px_B.y) / 2.0;
-    const int res = findLocalMatch(g, cur_pyr, cur_frame, epi_dir.x, epi_dir.y, m.search_level, opt, align_1d, pwb, m);
-    if (res != kSuccess) return res;
-    m.f_cur = normalized3(camBackProject3(cam_cur, m.px_x, m.px_y));
-    return depthFromTriangulation(T_cur_ref, f_ref, m.f_cur, depth);
-  }
-
+  } else {
   const ZmssdRef zref = makeZmssdRef(g, pwb);
   const V3d C = Rf + T_cur_ref.t * d_estimate_inv;
   const int pl = m.search_level;
@@ -559,15 +586,14 @@ SVO_D int findEpipolarMatchDirect(const Group& g, const PyrView& ref_pyr, int re
     m.px_x = pb.x; m.px_y = pb.y;
   }
 
-  if (zmssd_best < 2000 * 64) {
-    if (opt.subpix_refinement) {
-      const int res = findLocalMatch(g, cur_pyr, cur_frame, epi_dir.x, epi_dir.y, m.search_level, opt, align_1d, pwb, m);
-      if (res != kSuccess) return res;
-    }
-    m.f_cur = normalized3(camBackProject3(cam_cur, m.px_x, m.px_y));
-    return depthFromTriangulation(T_cur_ref, f_ref, m.f_cur, depth);
+  if (!(zmssd_best < 2000 * 64)) return kFailScore;
   }
-  return kFailScore;
+  if (short_epi || opt.subpix_refinement) {
+    const int res = findLocalMatch(g, cur_pyr, cur_frame, epi_dir.x, epi_dir.y, m.search_level, opt, align_1d, pwb, m);
+    if (res != kSuccess) return res;
+  }
+  m.f_cur = normalized3(camBackProject3(cam_cur, m.px_x, m.px_y));
+  return depthFromTriangulation(T_cur_ref, f_ref, m.f_cur, depth);
 }
 
 }  // namespace svo_dev
