@@ -701,3 +701,41 @@ def reproject_match(kf_frames, tables, cur_frame, entry_feat, n_features_in, occ
     fn(C.byref(m), C.byref(cur_frame), len(ef), _i32(ef), int(n_features_in), _u8(occupancy), C.byref(opt),
        res.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
     return res, st[0]
+
+
+def ref_reproject_frames(kf_frames, tables, n_visible, cur_frame, max_n_features=120, reproject_unconverged_seeds=True,
+                         max_unconverged_seeds_ratio=-1.0, min_required_features=0, remove_unconstrained_points=True):
+    """The reference's whole Reprojector::reprojectFrames (compiled reprojector.cpp) on the flat tables; the first n_visible
+    keyframes are the visible keyframes. Returns a dict of numpy arrays (features appended to the current frame, grid, stats,
+    landmark counters, seed states / types of the keyframes afterwards). None when the library was never built."""
+    L = ref_frontend_lib()
+    if L is None:
+        return None
+    K = len(kf_frames)
+    kfs = (Frame * K)(*kf_frames)
+    feats = make_features(tables["feat"]["px"], tables["feat"]["f"], tables["feat"]["grad"], tables["feat"]["type"], tables["feat"]["level"])
+    keep = {k: np.ascontiguousarray(tables[k], dt) for k, dt in (
+        ("kf_seed_mu_range", np.float64), ("kf_feat_begin", np.int32), ("feat_score", np.float64), ("feat_seed_state", np.float64),
+        ("feat_point", np.int32), ("feat_kf", np.int32), ("pt_pos", np.float64), ("pt_n_failed", np.int32),
+        ("pt_n_succeeded", np.int32), ("pt_obs_begin", np.int32), ("obs_feat", np.int32))}
+    m = ReprojMap(K, kfs, _f64(keep["kf_seed_mu_range"]), _i32(keep["kf_feat_begin"]), feats, _f64(keep["feat_score"]),
+                  _f64(keep["feat_seed_state"]), _i32(keep["feat_point"]), _i32(keep["feat_kf"]), int(tables["n_points"]),
+                  _f64(keep["pt_pos"]), _i32(keep["pt_n_failed"]), _i32(keep["pt_n_succeeded"]), _i32(keep["pt_obs_begin"]),
+                  _i32(keep["obs_feat"]))
+    cap = int(tables["n_feat"]) + 8
+    o = dict(type=np.zeros(cap, np.int32), px=np.zeros((cap, 2)), level=np.zeros(cap, np.int32), point=np.zeros(cap, np.int32),
+             seed_feat=np.zeros(cap, np.int32), state=np.zeros((cap, 4)), f=np.zeros((cap, 3)), grad=np.zeros((cap, 2)),
+             score=np.zeros(cap), occupancy=np.zeros(4096, np.uint8), stats=np.zeros(3, np.int32),
+             pt_counters=np.zeros((max(int(tables["n_points"]), 1), 2), np.int32), feat_state=np.zeros((int(tables["n_feat"]), 4)),
+             feat_type=np.zeros(int(tables["n_feat"]), np.int32))
+    L.ref_reproject_frames.argtypes = [C.POINTER(ReprojMap), C.c_int, C.POINTER(Frame), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                       i32p, f64p, i32p, i32p, i32p, f64p, f64p, f64p, f64p, u8p, i32p, i32p, f64p, i32p]
+    n = L.ref_reproject_frames(C.byref(m), int(n_visible), C.byref(cur_frame), int(max_n_features), int(reproject_unconverged_seeds),
+                               float(max_unconverged_seeds_ratio), int(min_required_features), int(remove_unconstrained_points),
+                               _i32(o["type"]), _f64(o["px"]), _i32(o["level"]), _i32(o["point"]), _i32(o["seed_feat"]), _f64(o["state"]),
+                               _f64(o["f"]), _f64(o["grad"]), _f64(o["score"]), _u8(o["occupancy"]), _i32(o["stats"]),
+                               _i32(o["pt_counters"]), _f64(o["feat_state"]), _i32(o["feat_type"]))
+    for k in ("type", "px", "level", "point", "seed_feat", "state", "f", "grad", "score"):
+        o[k] = o[k][:n]
+    o["n"] = n
+    return o

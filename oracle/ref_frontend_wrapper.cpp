@@ -359,11 +359,14 @@ int ref_update_seeds(const orc_frame* ref, int n_obs, const orc_frame* cur_frame
 // The reference's own reprojector.cpp (src/svo/src/reprojector.cpp, compiled unmodified): getCandidate for every entry in
 // visiting order, sortCandidatesByReprojStats / sortCandidatesByNumObs, matchCandidates. The keyframes, their feature columns
 // and the landmarks with their observation lists are rebuilt from the flat tables as real svo::Frame / svo::Point objects.
-extern "C" int ref_reproject_match(const orc_reproj_map* map, const orc_frame* cur, int E, const int* entry_feat, int n_features_in,
-                                   uint8_t* occupancy, const orc_reproj_options* opt, orc_reproj_result* results,
-                                   orc_reproj_stats* stats) {
+namespace {
+struct RefMap {
+  std::vector<svo::FramePtr> kfs;
+  std::vector<svo::PointPtr> pts;
+};
+RefMap buildRefMap(const orc_reproj_map* map) {
   using namespace svo;
-  std::vector<FramePtr> kfs;
+  RefMap m;
   for (int k = 0; k < map->n_kfs; ++k) {
     orc_frame f = map->kfs[k];
     f.px = nullptr;  // features come from the tables below
@@ -383,9 +386,8 @@ extern "C" int ref_reproject_match(const orc_reproj_map* map, const orc_frame* c
       fr->score_vec_(i) = map->feat_score[b + i];
       for (int c = 0; c < 4; ++c) fr->invmu_sigma2_a_b_vec_(c, i) = map->feat_seed_state[4 * size_t(b + i) + c];
     }
-    kfs.push_back(fr);
+    m.kfs.push_back(fr);
   }
-  std::vector<PointPtr> pts;
   for (int p = 0; p < map->n_points; ++p) {
     auto pt = std::make_shared<Point>(Eigen::Vector3d(map->pt_pos[3 * p], map->pt_pos[3 * p + 1], map->pt_pos[3 * p + 2]));
     pt->id_ = p;
@@ -393,16 +395,28 @@ extern "C" int ref_reproject_match(const orc_reproj_map* map, const orc_frame* c
     pt->n_succeeded_reproj_ = map->pt_n_succeeded[p];
     for (int o = map->pt_obs_begin[p]; o < map->pt_obs_begin[p + 1]; ++o) {
       const int fi = map->obs_feat[o], k = map->feat_kf[fi];
-      pt->obs_.emplace_back(kfs[k], size_t(fi - map->kf_feat_begin[k]));
+      pt->obs_.emplace_back(m.kfs[k], size_t(fi - map->kf_feat_begin[k]));
     }
-    pts.push_back(pt);
+    m.pts.push_back(pt);
   }
-  int n_feat = map->kf_feat_begin[map->n_kfs];
+  const int n_feat = map->kf_feat_begin[map->n_kfs];
   for (int fi = 0; fi < n_feat; ++fi)
     if (map->feat_point[fi] >= 0) {
       const int k = map->feat_kf[fi];
-      kfs[k]->landmark_vec_[fi - map->kf_feat_begin[k]] = pts[map->feat_point[fi]];
+      m.kfs[k]->landmark_vec_[fi - map->kf_feat_begin[k]] = m.pts[map->feat_point[fi]];
     }
+  return m;
+}
+}  // namespace
+
+extern "C" int ref_reproject_match(const orc_reproj_map* map, const orc_frame* cur, int E, const int* entry_feat, int n_features_in,
+                                   uint8_t* occupancy, const orc_reproj_options* opt, orc_reproj_result* results,
+                                   orc_reproj_stats* stats) {
+  using namespace svo;
+  RefMap rm = buildRefMap(map);
+  std::vector<FramePtr>& kfs = rm.kfs;
+  std::vector<PointPtr>& pts = rm.pts;
+  const int n_feat = map->kf_feat_begin[map->n_kfs];
   orc_frame cf = *cur;
   cf.px = nullptr;
   FramePtr frame = makeFrame(cf);
@@ -490,4 +504,61 @@ extern "C" int ref_reproject_match(const orc_reproj_map* map, const orc_frame* c
     }
   }
   return stats->n_matches;
+}
+
+// The whole Reprojector::reprojectFrames (reprojector.cpp:28-310) of the reference on the same tables: the first n_visible
+// keyframes are `visible_kfs` (in order). Outputs: the features the call appended to the current frame (slots 0..n-1), the grid,
+// the statistics, the landmarks' counters, the keyframes' seed states / types afterwards and the number of trashed points.
+extern "C" int ref_reproject_frames(const orc_reproj_map* map, int n_visible, const orc_frame* cur, int max_n_features_per_frame,
+                                    int reproject_unconverged_seeds, double max_unconverged_seeds_ratio, int min_required_features,
+                                    int remove_unconstrained_points, int* out_type, double* out_px, int* out_level, int* out_point,
+                                    int* out_seed_feat, double* out_state, double* out_f, double* out_grad, double* out_score,
+                                    uint8_t* occupancy_out, int* stats_out /* n_trials, n_matches, n_trash */, int* pt_counters_out,
+                                    double* feat_state_out, int* feat_type_out) {
+  using namespace svo;
+  RefMap rm = buildRefMap(map);
+  orc_frame cf = *cur;
+  cf.px = nullptr;
+  FramePtr frame = makeFrame(cf);
+  frame->id_ = 1000;
+  ReprojectorOptions o;
+  o.max_n_features_per_frame = size_t(max_n_features_per_frame);
+  o.reproject_unconverged_seeds = reproject_unconverged_seeds != 0;
+  o.max_unconverged_seeds_ratio = max_unconverged_seeds_ratio;
+  o.min_required_features = size_t(min_required_features);
+  o.remove_unconstrained_points = remove_unconstrained_points != 0;
+  Reprojector rp(o, 0);
+  std::vector<FramePtr> visible(rm.kfs.begin(), rm.kfs.begin() + n_visible);
+  std::vector<PointPtr> trash;
+  rp.reprojectFrames(frame, visible, trash);
+  const int n = int(frame->num_features_);
+  for (int s = 0; s < n; ++s) {
+    out_type[s] = int(frame->type_vec_[s]);
+    out_px[2 * s] = frame->px_vec_(0, s); out_px[2 * s + 1] = frame->px_vec_(1, s);
+    out_level[s] = frame->level_vec_(s);
+    out_point[s] = frame->landmark_vec_[s] ? frame->landmark_vec_[s]->id() : -1;
+    out_seed_feat[s] = -1;
+    if (frame->seed_ref_vec_[s].keyframe) {
+      int k = 0;
+      while (rm.kfs[k].get() != frame->seed_ref_vec_[s].keyframe.get()) ++k;
+      out_seed_feat[s] = map->kf_feat_begin[k] + frame->seed_ref_vec_[s].seed_id;
+    }
+    for (int c = 0; c < 4; ++c) out_state[4 * s + c] = frame->invmu_sigma2_a_b_vec_(c, s);
+    for (int c = 0; c < 3; ++c) out_f[3 * s + c] = frame->f_vec_(c, s);
+    const bool e = isEdgelet(frame->type_vec_[s]);
+    out_grad[2 * s] = e ? frame->grad_vec_(0, s) : 0.0; out_grad[2 * s + 1] = e ? frame->grad_vec_(1, s) : 0.0;
+    out_score[s] = frame->score_vec_(s);
+  }
+  for (size_t c = 0; c < rp.grid_->occupancy_.size(); ++c) occupancy_out[c] = rp.grid_->occupancy_[c] ? 1 : 0;
+  stats_out[0] = int(rp.stats_.n_trials); stats_out[1] = int(rp.stats_.n_matches); stats_out[2] = int(trash.size());
+  for (int p = 0; p < map->n_points; ++p) {
+    pt_counters_out[2 * p] = rm.pts[p]->n_failed_reproj_; pt_counters_out[2 * p + 1] = rm.pts[p]->n_succeeded_reproj_;
+  }
+  const int n_feat = map->kf_feat_begin[map->n_kfs];
+  for (int fi = 0; fi < n_feat; ++fi) {
+    const int k = map->feat_kf[fi], i = fi - map->kf_feat_begin[k];
+    for (int c = 0; c < 4; ++c) feat_state_out[4 * fi + c] = rm.kfs[k]->invmu_sigma2_a_b_vec_(c, i);
+    feat_type_out[fi] = int(rm.kfs[k]->type_vec_[i]);
+  }
+  return n;
 }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <numeric>
 
 namespace svo {
@@ -37,9 +38,19 @@ Transformation Transformation::operator*(const Transformation& b) const {  // qu
   return r;
 }
 
+KeypointIdentifier::KeypointIdentifier(const FramePtr& _frame, const size_t _feature_index)  // point.cpp:19-23
+    : frame(_frame), frame_id(_frame->id_), keypoint_index_(_feature_index) {}
+
+size_t Frame::numTrackedFeatures() const {  // frame.h:153-163
+  size_t count = 0;
+  for (size_t i = 0; i < num_features_; ++i)
+    if ((isValidLandmark(i) && !isFixedLandmark(type_vec_[i]) && !isMapPoint(type_vec_[i])) || isCornerEdgeletSeed(type_vec_[i])) ++count;
+  return count;
+}
+
 void Frame::clearFeatureStorage() {
   px_vec_.clear(); f_vec_.clear(); grad_vec_.clear(); score_vec_.clear(); level_vec_.clear(); type_vec_.clear();
-  depth_vec_.clear(); invmu_sigma2_a_b_vec_.clear();
+  depth_vec_.clear(); invmu_sigma2_a_b_vec_.clear(); landmark_vec_.clear(); seed_ref_vec_.clear();
   num_features_ = 0;
 }
 
@@ -368,6 +379,272 @@ size_t DepthFilter::updateSeeds(const std::vector<FramePtr>& ref_frames_with_see
     n_success += depth_filter_utils::updateSeedsOfFrame(*cur_frame, *ref_frame, seeds, matcher_, d);
   }
   return n_success;
+}
+
+// ---- Reprojector -----------------------------------------------------------------------------------------------------------------
+namespace {
+// The map tables of svo_reproj_map, flattened from the keyframes a reprojection can touch: the visible keyframes and the frames
+// holding the other observations of their landmarks (Point::getCloseViewObs may pick any of them, point.cpp:83-129).
+struct FlatMap {
+  std::vector<FramePtr> kfs;
+  std::map<const Frame*, int> index;
+  std::vector<int> begin;  // [K+1]
+  std::vector<double> T_f_w, mu_range, score, state, pt_pos;
+  std::vector<svo_feature> feat;
+  std::vector<int> feat_point, feat_kf, pt_failed, pt_succeeded, obs_begin, obs_feat;
+  std::vector<PointPtr> pts;
+  std::map<const Point*, int> pt_index;
+  std::map<int, int> cand_type;                       // candidate type at projection time (unconverged-seed pass)
+  std::vector<std::array<double, 2>> remaining;       // cur_px of the candidates the last pass left in candidates_
+  svo_cuda_pyr* pyr = nullptr;
+
+  int addFrame(const FramePtr& f) {
+    auto it = index.find(f.get());
+    if (it != index.end()) return it->second;
+    const int k = int(kfs.size());
+    index[f.get()] = k;
+    kfs.push_back(f);
+    return k;
+  }
+  ~FlatMap() { if (pyr) svo_cuda_pyr_destroy(b200::context(), pyr); }
+};
+
+void buildFlatMap(const std::vector<FramePtr>& visible_kfs, FlatMap& m) {
+  for (const FramePtr& f : visible_kfs) m.addFrame(f);
+  for (size_t k = 0; k < m.kfs.size(); ++k) {  // grows while the observation frames of the landmarks are added
+    const FramePtr f = m.kfs[k];
+    for (size_t i = 0; i < f->num_features_; ++i)
+      if (f->isValidLandmark(i))
+        for (const KeypointIdentifier& obs : f->landmark_vec_[i]->obs_)
+          if (FramePtr of = obs.frame.lock()) m.addFrame(of);
+  }
+  const int K = int(m.kfs.size());
+  m.begin.assign(1, 0);
+  for (int k = 0; k < K; ++k) {
+    const FramePtr& f = m.kfs[k];
+    double T[7];
+    f->T_f_w_.toArray(T);
+    m.T_f_w.insert(m.T_f_w.end(), T, T + 7);
+    m.mu_range.push_back(f->seed_mu_range_);
+    for (size_t i = 0; i < f->num_features_; ++i) {
+      svo_feature q{};
+      q.px[0] = f->px_vec_[i][0]; q.px[1] = f->px_vec_[i][1];
+      for (int c = 0; c < 3; ++c) q.f[c] = f->f_vec_[i][c];
+      q.grad[0] = f->grad_vec_[i][0]; q.grad[1] = f->grad_vec_[i][1];
+      q.type = int(f->type_vec_[i]);
+      q.level = f->level_vec_[i];
+      m.feat.push_back(q);
+      m.score.push_back(f->score_vec_[i]);
+      for (int c = 0; c < 4; ++c) m.state.push_back(f->invmu_sigma2_a_b_vec_[i][c]);
+      m.feat_kf.push_back(k);
+      int pid = -1;
+      if (f->isValidLandmark(i)) {
+        const PointPtr& p = f->landmark_vec_[i];
+        auto it = m.pt_index.find(p.get());
+        if (it == m.pt_index.end()) {
+          pid = int(m.pts.size());
+          m.pt_index[p.get()] = pid;
+          m.pts.push_back(p);
+        } else {
+          pid = it->second;
+        }
+      }
+      m.feat_point.push_back(pid);
+    }
+    m.begin.push_back(int(m.feat.size()));
+  }
+  m.obs_begin.assign(1, 0);
+  for (const PointPtr& p : m.pts) {
+    for (int c = 0; c < 3; ++c) m.pt_pos.push_back(p->pos_[c]);
+    m.pt_failed.push_back(p->n_failed_reproj_);
+    m.pt_succeeded.push_back(p->n_succeeded_reproj_);
+    for (const KeypointIdentifier& obs : p->obs_)
+      if (FramePtr of = obs.frame.lock()) m.obs_feat.push_back(m.begin[m.index[of.get()]] + int(obs.keypoint_index_));
+    m.obs_begin.push_back(int(m.obs_feat.size()));
+  }
+  // one pyramid batch holding every keyframe of the set: level 0 is copied device to device, the levels are rebuilt (same bytes)
+  svo_cuda_ctx* ctx = b200::context();
+  const b200::GpuPyramid& g0 = b200::ensureGpu(*m.kfs[0]);
+  b200::check(svo_cuda_pyr_create(ctx, K, g0.width(), g0.height(), g0.n_levels(), -1, &m.pyr), "svo_cuda_pyr_create");
+  for (int k = 0; k < K; ++k) {
+    const b200::GpuPyramid& g = b200::ensureGpu(*m.kfs[k]);
+    size_t pitch = 0, stride = 0;
+    void* ptr = nullptr;
+    svo_cuda_pyr_level_info(g.handle(), 0, nullptr, nullptr, &pitch, &stride, &ptr);
+    b200::check(svo_cuda_pyr_upload(ctx, m.pyr, k, 1, static_cast<const uint8_t*>(ptr), pitch, stride, SVO_MEM_DEVICE), "svo_cuda_pyr_upload");
+  }
+  b200::check(svo_cuda_pyr_build(ctx, m.pyr, 0, K), "svo_cuda_pyr_build");
+}
+}  // namespace
+
+void Reprojector::reprojectFrames(const FramePtr& cur_frame, const std::vector<FramePtr>& visible_kfs, std::vector<PointPtr>& trash_points) {
+  if (options_.max_n_features_per_frame == 0) throw b200::Error("Reprojector: max_n_features_per_frame must be > 0");  // CHECK_GT, :38
+  const svo_camera& cam = cur_frame->cam_->model;
+  if (!grid_) {
+    int n_cols = 0, n_rows = 0;
+    svo_cuda_grid_cells(cam.width, cam.height, int(options_.cell_size), &n_cols, &n_rows);
+    grid_.reset(new OccupandyGrid2D(int(options_.cell_size), n_cols, n_rows));
+  }
+  grid_->reset();
+  stats_.reset();
+  if (visible_kfs.empty()) return;
+  const size_t max_total_n_features = options_.max_n_features_per_frame;  // + max_fixed_landmarks only with the global map
+  FlatMap m;
+  buildFlatMap(visible_kfs, m);
+  cur_frame->landmark_vec_.resize(cur_frame->num_features_);
+  cur_frame->seed_ref_vec_.resize(cur_frame->num_features_);
+  const b200::GpuPyramid& cur_gpu = b200::ensureGpu(*cur_frame);
+  double T_cur[7];
+  cur_frame->T_f_w_.toArray(T_cur);
+  const auto cur_pos = cur_frame->pos();
+
+  svo_reproj_map tables{};
+  tables.n_kfs = int(m.kfs.size()); tables.n_feat = int(m.feat.size()); tables.n_points = int(m.pts.size()); tables.n_obs = int(m.obs_feat.size());
+  auto bindTables = [&]() {
+    tables.kf_T_f_w = m.T_f_w.data(); tables.kf_seed_mu_range = m.mu_range.data(); tables.kf_frame_idx = nullptr;
+    tables.feat = m.feat.data(); tables.feat_score = m.score.data(); tables.feat_seed_state = m.state.data();
+    tables.feat_point = m.feat_point.data(); tables.feat_kf = m.feat_kf.data(); tables.pt_pos = m.pt_pos.data();
+    tables.pt_n_failed = m.pt_failed.data(); tables.pt_n_succeeded = m.pt_succeeded.data(); tables.pt_obs_begin = m.obs_begin.data();
+    tables.obs_feat = m.obs_feat.data();
+  };
+  // One matchCandidates round (getCandidate + sort + match) on the GPU; project_only = only setGridCellsOccupied(candidates)
+  // (reprojector.cpp:545-555), done by handing over a fully occupied grid so that nothing is tried.
+  auto pass = [&](const std::vector<int>& entries, size_t max_n, bool project_only, Statistics* st) {
+    if (entries.empty()) return;
+    bindTables();
+    svo_reprojector_options o{};
+    o.cell_size = int(options_.cell_size); o.max_n_features = int(max_n);
+    o.affine_est_offset = options_.affine_est_offset; o.affine_est_gain = options_.affine_est_gain;
+    o.seed_sigma2_thresh = options_.seed_sigma2_thresh;
+    std::vector<uint8_t> occ = grid_->occupancy_;
+    if (project_only) std::fill(occ.begin(), occ.end(), 1);
+    const int n_in = int(cur_frame->num_features_);
+    const int eb[2] = {0, int(entries.size())};
+    std::vector<svo_reproj_result> res(entries.size());
+    svo_reproj_stats rs{};
+    b200::check(svo_cuda_reproject_match(b200::context(), m.pyr, cur_gpu.handle(), &cam, &cam, &tables, 1, nullptr, T_cur, &n_in, eb,
+                                         int(entries.size()), entries.data(), occ.data(), &o, res.data(), &rs, SVO_MEM_HOST),
+                "svo_cuda_reproject_match");
+    if (project_only) {
+      for (const svo_reproj_result& r : res)
+        if (r.status != SVO_REPROJ_NOT_CANDIDATE) grid_->occupancy_[grid_->getCellIndex(int(r.cur_px[0]), int(r.cur_px[1]), 1)] = 1;
+      return;
+    }
+    grid_->occupancy_ = occ;
+    if (st) { st->n_trials += size_t(rs.n_trials); st->n_matches += size_t(rs.n_matches); }
+    // everything the reference mutates: landmark counters, seed states / types of the keyframes, the new features of the frame
+    std::vector<int> matched;
+    for (size_t e = 0; e < res.size(); ++e) {
+      const svo_reproj_result& r = res[e];
+      const int fi = entries[e], k = m.feat_kf[fi], i = fi - m.begin[k], pid = m.feat_point[fi];
+      if (pid >= 0) {
+        m.pts[pid]->n_failed_reproj_ += r.d_failed; m.pts[pid]->n_succeeded_reproj_ += r.d_succeeded;
+        m.pt_failed[pid] = m.pts[pid]->n_failed_reproj_; m.pt_succeeded[pid] = m.pts[pid]->n_succeeded_reproj_;
+      } else {
+        for (int c = 0; c < 4; ++c) { m.kfs[k]->invmu_sigma2_a_b_vec_[i][c] = r.seed_state[c]; m.state[4 * size_t(fi) + c] = r.seed_state[c]; }
+        m.kfs[k]->type_vec_[i] = FeatureType(r.type_out);
+        m.feat[fi].type = r.type_out;
+      }
+      if (r.status == SVO_REPROJ_MATCHED) matched.push_back(int(e));
+    }
+    std::sort(matched.begin(), matched.end(), [&](int a, int b) { return res[a].slot < res[b].slot; });
+    for (int e : matched) {  // matchCandidate, reprojector.cpp:462-484 (the candidate's type is the one it had when it was projected)
+      const svo_reproj_result& r = res[e];
+      const int fi = entries[e], k = m.feat_kf[fi], i = fi - m.begin[k], pid = m.feat_point[fi];
+      cur_frame->type_vec_.push_back(pid >= 0 ? m.kfs[k]->type_vec_[i] : FeatureType(m.cand_type.count(fi) ? m.cand_type[fi] : r.type_out));
+      cur_frame->px_vec_.push_back({r.px[0], r.px[1]});
+      cur_frame->f_vec_.push_back({r.f[0], r.f[1], r.f[2]});
+      cur_frame->grad_vec_.push_back({r.grad[0], r.grad[1]});
+      cur_frame->level_vec_.push_back(r.level);
+      cur_frame->score_vec_.push_back(m.score[fi]);
+      cur_frame->invmu_sigma2_a_b_vec_.push_back({r.seed_state[0], r.seed_state[1], r.seed_state[2], r.seed_state[3]});
+      cur_frame->landmark_vec_.push_back(pid >= 0 ? m.pts[pid] : nullptr);
+      SeedRef sr;
+      std::array<double, 3> xyz_w;
+      if (pid >= 0) {
+        xyz_w = m.pts[pid]->pos_;
+      } else {
+        sr.keyframe = m.kfs[k]; sr.seed_id = i;
+        const Transformation T_w_ref = m.kfs[k]->T_f_w_.inverse();
+        const double d = 1.0 / r.seed_state[0];
+        const auto v = rotate(T_w_ref.q, {m.feat[fi].f[0] * d, m.feat[fi].f[1] * d, m.feat[fi].f[2] * d});
+        xyz_w = {v[0] + T_w_ref.t[0], v[1] + T_w_ref.t[1], v[2] + T_w_ref.t[2]};
+      }
+      cur_frame->seed_ref_vec_.push_back(sr);
+      cur_frame->depth_vec_.push_back(std::sqrt((xyz_w[0] - cur_pos[0]) * (xyz_w[0] - cur_pos[0]) + (xyz_w[1] - cur_pos[1]) * (xyz_w[1] - cur_pos[1]) +
+                                                (xyz_w[2] - cur_pos[2]) * (xyz_w[2] - cur_pos[2])));
+      ++cur_frame->num_features_;
+    }
+    // candidates the loop never reached stay in candidates_ (reprojector.cpp:380): remembered for setGridCellsOccupied
+    m.remaining.clear();
+    for (const svo_reproj_result& r : res)
+      if (r.status == SVO_REPROJ_NOT_REACHED) m.remaining.push_back({r.cur_px[0], r.cur_px[1]});
+  };
+  auto occupyRemaining = [&]() {
+    for (const auto& px : m.remaining) grid_->occupancy_[grid_->getCellIndex(int(px[0]), int(px[1]), 1)] = 1;
+  };
+
+  // ---- landmarks (reprojector.cpp:133-190)
+  std::vector<int> entries;
+  for (const FramePtr& ref_frame : visible_kfs) {
+    const int k = m.index[ref_frame.get()];
+    for (size_t i = 0; i < ref_frame->num_features_; ++i) {
+      const FeatureType type = ref_frame->type_vec_[i];
+      if (!ref_frame->isValidLandmark(i) || type == FeatureType::kOutlier || isMapPoint(type) || isFixedLandmark(type)) continue;
+      const PointPtr& point = ref_frame->landmark_vec_[i];
+      if (point->n_failed_reproj_ > 10) { trash_points.push_back(point); continue; }
+      if (point->last_projected_kf_id_.at(camera_index_) == cur_frame->id_) continue;
+      point->last_projected_kf_id_[camera_index_] = cur_frame->id_;
+      if (point->obs_.size() < 2 && options_.remove_unconstrained_points) { trash_points.push_back(point); continue; }
+      entries.push_back(m.begin[k] + int(i));
+    }
+  }
+  Statistics lm_stats;
+  pass(entries, max_total_n_features, false, &lm_stats);
+  stats_.add(lm_stats);
+  if (doesFrameHaveEnoughFeatures(cur_frame)) occupyRemaining();
+
+  // ---- converged seeds (:192-235)
+  auto seedEntries = [&](bool converged) {
+    entries.clear();
+    for (const FramePtr& ref_frame : visible_kfs) {
+      const int k = m.index[ref_frame.get()];
+      for (size_t i = 0; i < ref_frame->num_features_; ++i)
+        if (converged ? isConvergedCornerEdgeletSeed(ref_frame->type_vec_[i]) : isUnconvergedCornerEdgeletSeed(ref_frame->type_vec_[i]))
+          entries.push_back(m.begin[k] + int(i));
+    }
+  };
+  seedEntries(true);
+  if (doesFrameHaveEnoughFeatures(cur_frame)) {
+    pass(entries, max_total_n_features, true, nullptr);
+    return;
+  }
+  m.remaining.clear();
+  Statistics sd_stats;
+  pass(entries, max_total_n_features, false, &sd_stats);
+  stats_.add(sd_stats);
+  if (doesFrameHaveEnoughFeatures(cur_frame) || !options_.reproject_unconverged_seeds) {
+    occupyRemaining();
+    return;
+  }
+
+  // ---- unconverged seeds (:237-300)
+  seedEntries(false);
+  size_t max_allowed_total = max_total_n_features;
+  if (options_.max_unconverged_seeds_ratio > 0) {
+    const double min_lm_seeds_ratio = 1 - options_.max_unconverged_seeds_ratio;
+    const size_t alt = static_cast<size_t>(cur_frame->numTrackedFeatures() / min_lm_seeds_ratio);
+    if (max_allowed_total > alt) max_allowed_total = alt;
+  }
+  if (max_allowed_total < options_.min_required_features) max_allowed_total = options_.min_required_features;
+  m.remaining.clear();
+  Statistics un_sd_stats;
+  // the candidate's type is read before updateSeed may converge it (matchCandidate: feature.type = c.type)
+  m.cand_type.clear();
+  for (int fi : entries) m.cand_type[fi] = m.feat[fi].type;
+  pass(entries, max_allowed_total, false, &un_sd_stats);
+  stats_.add(un_sd_stats);
+  if (doesFrameHaveEnoughFeatures(cur_frame)) occupyRemaining();
 }
 
 // ---- FAST detector ----------------------------------------------------------------------------------------------------------------

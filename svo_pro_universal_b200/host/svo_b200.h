@@ -53,6 +53,12 @@ enum class FeatureType : uint8_t {  // src/svo_common/include/svo/common/types.h
   kMapPointSeedConverged = 5, kEdgelet = 6, kCorner = 7, kMapPoint = 8, kFixedLandmark = 9, kOutlier = 10
 };
 inline bool isSeed(FeatureType t) { return static_cast<uint8_t>(t) < 6; }
+inline bool isCornerEdgeletSeed(FeatureType t) {
+  return t == FeatureType::kEdgeletSeedConverged || t == FeatureType::kCornerSeedConverged || t == FeatureType::kEdgeletSeed || t == FeatureType::kCornerSeed;
+}
+inline bool isConvergedCornerEdgeletSeed(FeatureType t) { return t == FeatureType::kEdgeletSeedConverged || t == FeatureType::kCornerSeedConverged; }
+inline bool isUnconvergedCornerEdgeletSeed(FeatureType t) { return t == FeatureType::kEdgeletSeed || t == FeatureType::kCornerSeed; }
+inline bool isFixedLandmark(FeatureType t) { return t == FeatureType::kFixedLandmark; }
 inline bool isMapPoint(FeatureType t) { return t == FeatureType::kMapPoint || t == FeatureType::kMapPointSeed || t == FeatureType::kMapPointSeedConverged; }
 
 struct Camera {  // vk::cameras::CameraGeometry<PinholeProjection<...>>
@@ -63,6 +69,31 @@ struct Camera {  // vk::cameras::CameraGeometry<PinholeProjection<...>>
 using CameraPtr = std::shared_ptr<Camera>;
 
 namespace b200 { class GpuPyramid; }
+
+struct Frame;
+using FramePtr = std::shared_ptr<Frame>;
+struct KeypointIdentifier {  // src/svo_common/include/svo/common/point.h:36-60
+  std::weak_ptr<Frame> frame;
+  int frame_id;
+  size_t keypoint_index_;
+  KeypointIdentifier(const FramePtr& _frame, const size_t _feature_index);
+};
+// svo::Point reduced to the members the Reprojector reads / writes (point.h:82-91)
+struct Point {
+  int id_ = -1;
+  std::array<double, 3> pos_{{0, 0, 0}};
+  std::vector<KeypointIdentifier> obs_;
+  std::array<int, 8> last_projected_kf_id_;
+  int n_failed_reproj_ = 0;
+  int n_succeeded_reproj_ = 0;
+  Point() { last_projected_kf_id_.fill(-1); }
+  int id() const { return id_; }
+};
+using PointPtr = std::shared_ptr<Point>;
+struct SeedRef {  // src/svo_common/include/svo/common/feature_wrapper.h:15-26
+  FramePtr keyframe;
+  int seed_id = -1;
+};
 
 // svo::Frame reduced to the members the hot path reads / writes (src/svo_common/include/svo/common/frame.h:30-424)
 struct Frame {
@@ -83,16 +114,20 @@ struct Frame {
   // (replaces the landmark_vec_ / seed_ref_vec_ pointer walk of sparse_img_align.cpp:282-293, done by the adapter).
   std::vector<double> depth_vec_;
   std::vector<SeedState> invmu_sigma2_a_b_vec_;
+  std::vector<PointPtr> landmark_vec_;   // used by the Reprojector; may stay empty for the other facades
+  std::vector<SeedRef> seed_ref_vec_;
   double seed_mu_range_ = 0.0;
   mutable std::shared_ptr<b200::GpuPyramid> gpu_;  // device-resident copy of img_pyr_ (the analogue of the reference's FrameGpu)
 
   const CameraPtr& cam() const { return cam_; }
   Transformation T_imu_world() const { return T_cam_imu_.inverse() * T_f_w_; }
+  std::array<double, 3> pos() const { return T_f_w_.inverse().t; }  // T_world_cam().getPosition()
+  bool isValidLandmark(size_t i) const { return i < landmark_vec_.size() && landmark_vec_[i] != nullptr; }
+  size_t numFeatures() const { return num_features_; }
+  size_t numTrackedFeatures() const;  // frame.h:153-163
   const Transformation& T_cam_imu() const { return T_cam_imu_; }
   void clearFeatureStorage();
 };
-using FramePtr = std::shared_ptr<Frame>;
-
 struct FrameBundle {  // frame.h:426-543
   using Ptr = std::shared_ptr<FrameBundle>;
   std::vector<FramePtr> frames_;
@@ -296,6 +331,42 @@ class FastDetector {  // src/svo_direct/include/svo/direct/feature_detection.h:2
   // computes unit bearing vectors, resets the grid.
   void detect(const FramePtr& frame);
   void resetGrid() { grid_.reset(); }
+};
+
+// ---- (f1) Reprojector ---------------------------------------------------------------------------------------------------------
+struct ReprojectorOptions {  // src/svo/include/svo/reprojector.h:27-70 (without the global-map options)
+  size_t max_n_features_per_frame = 120;
+  size_t cell_size = 30;
+  bool reproject_unconverged_seeds = true;
+  double max_unconverged_seeds_ratio = -1.0;
+  size_t min_required_features = 0;
+  double seed_sigma2_thresh = 200;
+  bool remove_unconstrained_points = true;
+  bool affine_est_offset = true;
+  bool affine_est_gain = false;
+};
+
+class Reprojector {  // reprojector.h:77-166
+ public:
+  using Ptr = std::shared_ptr<Reprojector>;
+  ReprojectorOptions options_;
+  struct Statistics {
+    size_t n_matches = 0, n_trials = 0;
+    void reset() { n_matches = 0; n_trials = 0; }
+    void add(const Statistics s) { n_matches += s.n_matches; n_trials += s.n_trials; }
+    double successRate() const { return n_trials == 0 ? 0.0 : n_matches / (1.0 * n_trials); }
+  } stats_;
+  std::unique_ptr<OccupandyGrid2D> grid_;
+  size_t camera_index_;
+  Reprojector(const ReprojectorOptions& options, size_t camera_index) : options_(options), camera_index_(camera_index) {}
+  // Project the landmarks and seeds of visible_kfs into cur_frame and match at most one per grid cell
+  // (reprojector.cpp:28-310): up to three svo_cuda_reproject_match calls (landmarks, converged seeds, unconverged seeds).
+  void reprojectFrames(const FramePtr& cur_frame, const std::vector<FramePtr>& visible_kfs, std::vector<PointPtr>& trash_points);
+
+ private:
+  bool doesFrameHaveEnoughFeatures(const FramePtr& frame) const {
+    return options_.max_n_features_per_frame > 0 && frame->numTrackedFeatures() >= options_.max_n_features_per_frame;
+  }
 };
 
 // ---- device plumbing --------------------------------------------------------------------------------------------------------

@@ -127,6 +127,7 @@ def reproject_golden():
     import helpers
     assert orc.ref_frontend_lib() is not None, "oracle/_ref/libfrontend_ref.so missing: run make -C oracle"
     out = helpers.reproject_outputs(orc, "ref")
+    out.update(helpers.reproject_frames_reference(orc))   # the whole Reprojector::reprojectFrames, for the C++ facade
     np.savez_compressed(os.path.join(HERE, "reproject_ref_golden.npz"), **out)
     print("reproject_ref_golden.npz", os.path.getsize(os.path.join(HERE, "reproject_ref_golden.npz")))
 

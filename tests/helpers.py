@@ -265,3 +265,30 @@ def assert_reproject_equal(a, b, px_tol, rel_tol, tag=""):
         assert np.abs(a[f"c{ci}_f"] - b[f"c{ci}_f"]).max() < 1e-5, (tag, ci)
         assert np.abs(a[f"c{ci}_grad"] - b[f"c{ci}_grad"]).max() < 1e-9, (tag, ci)
         np.testing.assert_allclose(a[f"c{ci}_seed_state"], b[f"c{ci}_seed_state"], rtol=rel_tol, atol=1e-12)
+
+
+# (scene seed, max_n_features_per_frame, reproject_unconverged_seeds, max_unconverged_seeds_ratio, min_required_features, remove_unconstrained)
+REPROJECT_FRAMES_CASES = [
+    (3, 120, 1, -1.0, 0, 1),     # stops inside the landmark pass
+    (3, 400, 1, -1.0, 0, 0),     # all three passes: landmarks, converged seeds, unconverged seeds (updateSeed)
+    (4, 260, 1, 0.3, 0, 1),      # unconverged seeds capped by the ratio
+    (5, 300, 0, -1.0, 0, 1),     # unconverged seeds not reprojected
+    (6, 150, 1, -1.0, 0, 0),     # enough features after the landmark pass: converged seeds only occupy cells
+]
+REPROJ_FRAMES_KEYS = ("type", "px", "level", "point", "seed_feat", "state", "f", "grad", "score", "occupancy", "stats", "pt_counters",
+                      "feat_state", "feat_type")
+
+
+def reproject_frames_reference(orc):
+    """The reference's whole Reprojector::reprojectFrames (compiled reprojector.cpp) on every REPROJECT_FRAMES_CASES case."""
+    out = {}
+    for ci, (seed, max_n, unconv, ratio, min_req, rm) in enumerate(REPROJECT_FRAMES_CASES):
+        sc = synth.make_reproject_scene(seed)
+        keep = []
+        kfs = [orc.make_frame(orc.create_img_pyramid(im, 5), sc["cam"], IDENTITY7, T, keep=keep)
+               for im, T in zip(sc["kf_imgs"], sc["tables"]["kf_T_f_w"])]
+        cur = orc.make_frame(orc.create_img_pyramid(sc["cur_img"], 5), sc["cam"], IDENTITY7, sc["cur_T_f_w"], keep=keep)
+        o = orc.ref_reproject_frames(kfs, sc["tables"], len(kfs), cur, max_n, unconv, ratio, min_req, rm)
+        for k in REPROJ_FRAMES_KEYS:
+            out[f"rf{ci}_{k}"] = o[k][:416] if k == "occupancy" else o[k]
+    return out

@@ -101,3 +101,67 @@ def test_cpp_facades_match_oracle(orc, tmp_path):
     assert n_succ == n_o > N // 4
     np.testing.assert_allclose(sd[:, :4], st, rtol=1e-4)
     assert np.array_equal(sd[:, 4].astype(np.uint8), types)
+
+
+def test_cpp_reprojector_facade_matches_reference(tmp_path):
+    """svo::Reprojector::reprojectFrames of the C++ facade (three svo_cuda_reproject_match passes + the host bookkeeping of
+    reprojector.cpp:28-310) against the outputs of the REFERENCE's own compiled Reprojector::reprojectFrames
+    (tests/golden/reproject_ref_golden.npz): same features in the same slots, same grid, statistics, trashed points, landmark
+    counters and seed states."""
+    import helpers
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "svo_pro_universal_b200", "host")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reproject_ref_golden.npz"))
+    for ci, (seed, max_n, unconv, ratio, min_req, rm) in enumerate(helpers.REPROJECT_FRAMES_CASES):
+        sc = synth.make_reproject_scene(seed)
+        t, cam = sc["tables"], sc["cam"]
+        K, NF, NP, NO = t["n_kfs"], t["n_feat"], t["n_points"], t["n_obs"]
+        fin, fout = tmp_path / f"rin{ci}.bin", tmp_path / f"rout{ci}.bin"
+        with open(fin, "wb") as f:
+            np.array([752, 480, 5, K, K, NF, NP, NO, max_n, unconv, min_req, rm], np.int32).tofile(f)
+            np.array([ratio], np.float64).tofile(f)
+            np.array([cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")], np.float64).tofile(f)
+            np.array([cam["width"], cam["height"], cam["distortion"]], np.int32).tofile(f)
+            for im in sc["kf_imgs"]:
+                im.tofile(f)
+            sc["cur_img"].tofile(f)
+            np.ascontiguousarray(t["kf_T_f_w"], np.float64).tofile(f)
+            np.ascontiguousarray(sc["cur_T_f_w"], np.float64).tofile(f)
+            np.ascontiguousarray(t["kf_seed_mu_range"], np.float64).tofile(f)
+            np.ascontiguousarray(t["kf_feat_begin"], np.int32).tofile(f)
+            for k in ("px", "f", "grad"):
+                np.ascontiguousarray(t["feat"][k], np.float64).tofile(f)
+            for k in ("type", "level"):
+                np.ascontiguousarray(t["feat"][k], np.int32).tofile(f)
+            np.ascontiguousarray(t["feat_score"], np.float64).tofile(f)
+            np.ascontiguousarray(t["feat_seed_state"], np.float64).tofile(f)
+            np.ascontiguousarray(t["feat_point"], np.int32).tofile(f)
+            np.ascontiguousarray(t["pt_pos"], np.float64).tofile(f)
+            for k in ("pt_n_failed", "pt_n_succeeded", "pt_obs_begin", "obs_feat"):
+                np.ascontiguousarray(t[k], np.int32).tofile(f)
+        r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "reproject_driver"), str(fin), str(fout)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = np.fromfile(fout, np.float64)
+        n = int(out[0]); p = 1
+        rows = out[p:p + 16 * n].reshape(n, 16); p += 16 * n
+        n_cells = int(out[p]); p += 1
+        occ = out[p:p + n_cells]; p += n_cells
+        stats = out[p:p + 3]; p += 3
+        ptc = out[p:p + 2 * NP].reshape(NP, 2); p += 2 * NP
+        fs = out[p:p + 5 * NF].reshape(NF, 5); p += 5 * NF
+        g = {k: gold[f"rf{ci}_{k}"] for k in helpers.REPROJ_FRAMES_KEYS}
+        assert n == len(g["type"]) > 100, (ci, n, len(g["type"]))
+        assert np.array_equal(rows[:, 0].astype(int), g["type"]), ci
+        assert np.abs(rows[:, 1:3] - g["px"]).max() < 1e-3, ci                     # north_star: 1e-3 px
+        assert np.array_equal(rows[:, 3].astype(int), g["level"]), ci
+        assert np.array_equal(rows[:, 4].astype(int), g["point"]), ci
+        assert np.array_equal(rows[:, 5].astype(int), g["seed_feat"]), ci
+        np.testing.assert_allclose(rows[:, 6:10], g["state"], rtol=1e-4, atol=1e-12)   # north_star: 1e-4 relative
+        assert np.abs(rows[:, 10:13] - g["f"]).max() < 1e-5, ci
+        assert np.abs(rows[:, 13:15] - g["grad"]).max() < 1e-9, ci
+        assert np.array_equal(rows[:, 15], g["score"]), ci
+        assert np.array_equal(occ.astype(np.uint8), g["occupancy"][:n_cells]), ci
+        assert np.array_equal(stats.astype(int), g["stats"]), (ci, stats, g["stats"])
+        assert np.array_equal(ptc.astype(int), g["pt_counters"]), ci
+        np.testing.assert_allclose(fs[:, :4], g["feat_state"], rtol=1e-4, atol=1e-12)
+        assert np.array_equal(fs[:, 4].astype(int), g["feat_type"]), ci
