@@ -60,6 +60,8 @@ struct ReprojParams {
   unsigned* cell_list; // [E] (cell << 13 | position), grouped by cell, positions ascending
   int* cell_begin;     // [F][n_cells] first index into cell_list of the frame, -1 = empty cell
   int* cell_success;   // [F][n_cells] position of the cell's winner, -1 = none
+  int* cell_items;     // [F][n_cells] the non-empty cells of the frame, compacted (any order)
+  int* n_nonempty;     // [F]
   int* resume_cell;    // [F * n_cells] compact list of (frame * n_cells + cell) handed over by the direct-match pass to the full pass
   int* resume_q;       // [F * n_cells] queue index where each of them continues
   int* resume_count;   // [1]
@@ -146,7 +148,7 @@ SVO_D bool before(const SortSmem& s, int a, int b) {
 
 __global__ void __launch_bounds__(kSortThreads) reproj_sort_kernel(const ReprojParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ int s_count;
+  __shared__ int s_count, s_nz;
   const int j = blockIdx.x, tid = threadIdx.x;
   int base;
   const int n = frameEntries(P, j, &base);
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kSortThreads) reproj_sort_kernel(const ReprojP
   s.hi = reinterpret_cast<unsigned long long*>(s_raw);
   s.lo = s.hi + npad;
   s.idx = reinterpret_cast<int*>(s.lo + npad);
-  if (tid == 0) s_count = 0;
+  if (tid == 0) { s_count = 0; s_nz = 0; }
   for (int c = tid; c < P.n_cells; c += kSortThreads) {
     P.cell_begin[(size_t)j * P.n_cells + c] = -1;
     P.cell_success[(size_t)j * P.n_cells + c] = -1;
@@ -229,9 +231,13 @@ __global__ void __launch_bounds__(kSortThreads) reproj_sort_kernel(const ReprojP
   for (int q = tid; q < n_cand; q += kSortThreads) {
     const unsigned key = ck[q];
     P.cell_list[base + q] = key;
-    if (q == 0 || (ck[q - 1] >> 13) != (key >> 13)) P.cell_begin[(size_t)j * P.n_cells + (key >> 13)] = q;
+    if (q == 0 || (ck[q - 1] >> 13) != (key >> 13)) {
+      P.cell_begin[(size_t)j * P.n_cells + (key >> 13)] = q;
+      P.cell_items[(size_t)j * P.n_cells + atomicAdd(&s_nz, 1)] = (int)(key >> 13);  // the match stage only visits these
+    }
   }
-  if (tid == 0) P.n_cand[j] = n_cand;
+  __syncthreads();
+  if (tid == 0) { P.n_cand[j] = n_cand; P.n_nonempty[j] = s_nz; }
 }
 
 // ---- stage 3: matchCandidate per cell queue ----------------------------------------------------------------------------
@@ -283,7 +289,8 @@ __global__ void __launch_bounds__(kThreads, FULL ? SVO_REPROJ_MINB : 4) reproj_m
   if (item < items_per_frame) {
     if (unlimited) {
       q = item; q_end = min(item + 1, n_cand);
-    } else {
+    } else if (from_resume || item < P.n_nonempty[j]) {
+      if (!from_resume) item = P.cell_items[(size_t)j * P.n_cells + item];  // item-th non-empty cell of the frame
       q = from_resume ? q_resume : P.cell_begin[(size_t)j * P.n_cells + item];
       q_end = q < 0 ? 0 : n_cand;
       q = max(q, 0);
@@ -549,6 +556,8 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   P.cell_list = (unsigned*)st.scratch(ne * sizeof(unsigned));
   P.cell_begin = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
   P.cell_success = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
+  P.cell_items = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
+  P.n_nonempty = (int*)st.scratch((size_t)F * sizeof(int));
   P.resume_cell = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
   P.resume_q = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
   P.resume_count = (int*)st.scratch(sizeof(int));

@@ -1,0 +1,127 @@
+"""BASELINE.json configs[4]: the full front-end batch (pyramid + 2-camera sparse align + Reprojector feature alignment + depth
+filter + FAST detector) on --pairs synthetic stereo frame pairs, sharded over the ranks of a torchrun launch by contiguous
+blocks of pairs (strong scaling: the total is fixed), no collective inside the path; one JSON line on rank 0.
+    python tools/bench_frontend.py --pairs 8192
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_frontend.py --pairs 8192
+Timing: CUDA events on the launching stream around --steps passes, max over ranks. The CPU line is the oracle port of the
+same chain, single thread, on the unique scenes."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def cpu_chain(scenes, seconds=6.0):
+    """Oracle port of the same per-pair chain (single thread): stereo pairs per second."""
+    import helpers
+    from oracle import orc
+    from svo_pro_universal_b200 import synth
+    prepared = []
+    for sc in scenes:
+        keep = []
+        pyr_r = {c: orc.create_img_pyramid(sc["imgs"][f"r{c}"], 5) for c in range(2)}
+        prepared.append((sc, keep, pyr_r))
+    ang = helpers.reproject_px_error_angle(scenes[0]["cam"])
+    t0 = time.perf_counter(); n = 0
+    while time.perf_counter() - t0 < seconds:
+        sc, keep, pyr_r = prepared[n % len(prepared)]
+        cam = sc["cam"]
+        pyr_c = {c: orc.create_img_pyramid(sc["imgs"][f"c{c}"], 5) for c in range(2)}
+        rfs = [orc.make_frame(pyr_r[c], cam, sc["T_cam_imu"][c], sc["T_imu_world_ref"], sc["px"][c], sc["f"][c], sc["depth"][c], keep=keep) for c in range(2)]
+        cfs = [orc.make_frame(pyr_c[c], cam, sc["T_cam_imu"][c], sc["T_imu_world_ref"], keep=keep) for c in range(2)]
+        r = orc.sparse_align(rfs, cfs, orc.default_align_options(estimate_illumination_gain=1, estimate_illumination_offset=1))
+        for c in range(2):
+            m = len(sc["px"][c])
+            kf = orc.make_frame(pyr_r[c], cam, helpers.IDENTITY7, sc["T_f_w_ref"][c], keep=keep)
+            cf = orc.make_frame(pyr_c[c], cam, helpers.IDENTITY7, np.array(r.T_f_w[c][:]), keep=keep)
+            st = np.tile([1.0, 1e-6, 10.0, 10.0], (m, 1)); st[:, 0] = 1.0 / sc["depth"][c]
+            R, tt = synth.se3_to_Rt(synth.se3_inv(sc["T_f_w_ref"][0]))
+            feat = np.zeros(m, [("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("type", "<i4"), ("level", "<i4")])
+            feat["px"], feat["f"], feat["grad"], feat["type"] = sc["px"][c], sc["f"][c], [1.0, 0.0], 7 if c == 0 else 4
+            tb = dict(n_kfs=1, n_feat=m, n_points=m if c == 0 else 0, kf_seed_mu_range=np.array([1 / 1.5]), kf_feat_begin=np.array([0, m], np.int32),
+                      feat=feat, feat_score=np.linspace(60.0, 11.0, m), feat_seed_state=st,
+                      feat_point=(np.arange(m) if c == 0 else np.full(m, -1)).astype(np.int32), feat_kf=np.zeros(m, np.int32),
+                      pt_pos=((sc["f"][0] * sc["depth"][0][:, None]) @ R.T + tt) if c == 0 else np.zeros((1, 3)),
+                      pt_n_failed=np.zeros(max(m, 1), np.int32), pt_n_succeeded=np.zeros(max(m, 1), np.int32),
+                      pt_obs_begin=(np.arange(m + 1) if c == 0 else np.zeros(1)).astype(np.int32),
+                      obs_feat=(np.arange(m) if c == 0 else np.zeros(1)).astype(np.int32))
+            orc.reproject_match([kf], tb, cf, np.arange(m, dtype=np.int32), 0, np.zeros(416, np.uint8), orc.ReprojOptions(30, 120, 1, 0, 0, 200.0, ang))
+        ns = len(sc["seed_px"])
+        oft = orc.make_features(sc["seed_px"], sc["seed_f"], np.tile([1.0, 0.0], (ns, 1)), np.full(ns, 1, np.int32), np.zeros(ns, np.int32))
+        orc.update_seeds(rfs[0], [cfs[0]], sc["T_cur_ref_gt"].reshape(1, 7), oft, np.full(ns, 1, np.uint8), sc["seed_state"].copy(),
+                         sc["seed_mu_range"], orc.default_matcher_options())
+        orc.fast_detector(sc["imgs"]["c0"])
+        n += 1
+    return n / (time.perf_counter() - t0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=8192, help="stereo frame pairs in total (sharded over the ranks)")
+    ap.add_argument("--unique", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from svo_pro_universal_b200 import capi, frontend, shard
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = capi.Context(local)
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
+    lo, hi = shard.partition(args.pairs, world, rank)
+    scenes = [frontend.make_stereo_scene(81 + s) for s in range(args.unique)]
+    fb = frontend.StereoFrontendBatch(ctx, scenes, hi - lo, dev)
+    for _ in range(args.warmup):
+        fb.step()
+    sync = lambda: (torch.cuda.synchronize(), dist.barrier() if world > 1 else None, torch.cuda.synchronize())
+    sync()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        fb.step()
+    e1.record(stream)
+    sync()
+    ms = e0.elapsed_time(e1) / args.steps
+    # stage breakdown of one more pass (events between the stages)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    evs[0].record(stream)
+    fb.step(lambda i: evs[i + 1].record(stream))
+    torch.cuda.synchronize()
+    stages = {n: evs[i].elapsed_time(evs[i + 1]) for i, n in enumerate(fb.STAGES)}
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+    out = fb.results()
+    assert (out["align"]["n_tracked"] > 250).all() and out["reproj_stats"]["n_matches"].mean() > 60
+    if world > 1:  # the only collective: gather the per-pair poses to rank 0
+        g = shard.gather_to_rank0(out["align"]["T_icur_iref"].copy(), args.pairs)
+        assert rank != 0 or g.shape == (args.pairs, 7)
+    if rank == 0:
+        cpu = cpu_chain(scenes)
+        print(json.dumps({"path": "configs[4]: full front-end batch (pyramid + stereo sparse align + Reprojector + depth filter + FAST)",
+                          "config": f"{args.pairs} synthetic stereo frame pairs ({args.unique} unique scenes tiled; every frame resident in HBM: "
+                                    f"{4 * (hi - lo) * 483360 / 1e9:.1f} GB of pyramids per GPU), 180 + 150 features, 120 seeds per pair",
+                          "n_gpus": world, "stereo_pairs_per_s": args.pairs / (ms * 1e-3), "ms_per_step": ms, "scaling": "strong",
+                          "stage_ms_rank0": stages,
+                          "gpu_launches_per_step": (ctx.launches - l0) // args.steps,
+                          "mean_matches_per_frame": float(out["reproj_stats"]["n_matches"].mean()),
+                          "seed_success_frac": out["n_seed_ok"] / max(1, fb.S),
+                          "cpu_baseline": {"stereo_pairs_per_s_single_thread": cpu, "kind": "port (oracle chain)", "cores": 1}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
