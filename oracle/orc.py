@@ -739,3 +739,35 @@ def ref_reproject_frames(kf_frames, tables, n_visible, cur_frame, max_n_features
         o[k] = o[k][:n]
     o["n"] = n
     return o
+
+
+# ---- f4: PoseOptimizer ---------------------------------------------------------------------------------------------------------
+class PoseOptOptions(C.Structure):
+    _fields_ = [("err_type", C.c_int), ("max_iter", C.c_int), ("eps", C.c_double), ("reproj_thresh_px", C.c_double),
+                ("have_prior", C.c_int), ("prior_q", C.c_double * 4), ("prior_lambda", C.c_double)]
+
+
+def pose_opt_options(err_type=0, max_iter=10, eps=0.000001, reproj_thresh_px=2.0, prior_q=None, prior_lambda=0.0):
+    """PoseOptimizer::getDefaultSolverOptions (pose_optimizer.cpp:22-29), poseoptim_thresh default 2.0 px."""
+    o = PoseOptOptions(err_type, max_iter, eps, reproj_thresh_px, 0, (C.c_double * 4)(1, 0, 0, 0), prior_lambda)
+    if prior_q is not None:
+        o.have_prior = 1
+        o.prior_q[:] = list(prior_q)
+    return o
+
+
+def pose_optimize(case, opt, which="orc"):
+    """PoseOptimizer::run on a synth.make_pose_opt_case dict. Returns (n_final, T_imu_world[7], outlier[N], stats[6])."""
+    L = lib() if which == "orc" else ref_frontend_lib()
+    fn = L.orc_pose_optimize if which == "orc" else L.ref_pose_optimize
+    keep = []
+    dummy = [np.zeros((8, 8), np.uint8)]
+    frames = [make_frame(dummy, case["cam"], T, case["T_imu_world_init"], keep=keep) for T in case["T_cam_imu"]]
+    n_cams, N = len(frames), len(case["px"])
+    fr = (Frame * n_cams)(*frames)
+    ft = make_features(case["px"], case["f"], case["grad"], case["type"], case["level"])
+    T = np.zeros(7); outl = np.zeros(N, np.uint8); stats = np.zeros(6)
+    xyz = np.ascontiguousarray(case["xyz_world"], np.float64)
+    n = fn(n_cams, fr, N, ft, _i32(np.ascontiguousarray(case["feat_cam"], np.int32)), _f64(xyz), _u8(np.ascontiguousarray(case["has_xyz"], np.uint8)),
+           C.byref(opt), _f64(T), _u8(outl), _f64(stats))
+    return n, T, outl, stats

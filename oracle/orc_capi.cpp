@@ -11,6 +11,7 @@
 #include "orc_matcher.hpp"
 #include "orc_depth_filter.hpp"
 #include "orc_reprojector.hpp"
+#include "orc_pose_optimizer.hpp"
 
 using namespace orc;
 
@@ -457,4 +458,32 @@ extern "C" int orc_reproject_match(const orc_reproj_map* map, const orc_frame* c
   c.T_f_w = se3FromArray(cur->T_cam_imu) * se3FromArray(cur->T_imu_world);
   reprojectMatch(*map, kfs, c, E, entry_feat, n_features_in, occupancy, *opt, results, stats);
   return stats->n_matches;
+}
+
+// f4
+extern "C" int orc_pose_optimize(int n_cams, const orc_frame* frames, int N, const orc_feature* ftrs, const int* feat_cam,
+                                 const double* xyz_world, const uint8_t* has_xyz, const orc_pose_opt_options* opt,
+                                 double T_imu_world_out[7], uint8_t* outlier, double stats[6]) {
+  std::vector<PoseOptCam> cams(n_cams);
+  for (int c = 0; c < n_cams; ++c) { cams[c].cam = camOf(&frames[c]); cams[c].T_cam_imu = se3FromArray(frames[c].T_cam_imu); }
+  std::vector<PoseOptFeature> fts(N);
+  for (int i = 0; i < N; ++i) {
+    const FeatureRef r = featureOf(&ftrs[i]);
+    fts[i].px = r.px; fts[i].f = r.f; fts[i].grad = r.grad; fts[i].level = r.level; fts[i].type = r.type;
+    fts[i].xyz_world = {xyz_world[3 * i], xyz_world[3 * i + 1], xyz_world[3 * i + 2]};
+    fts[i].has_xyz = has_xyz[i] != 0;
+    fts[i].cam = feat_cam[i];
+  }
+  PoseOptimizer po;
+  po.err_type = opt->err_type; po.max_iter = opt->max_iter; po.eps = opt->eps;
+  if (opt->have_prior) {
+    po.have_prior = true;
+    po.prior.q = {opt->prior_q[0], opt->prior_q[1], opt->prior_q[2], opt->prior_q[3]};
+    po.prior.t = {0, 0, 0};
+    po.prior_lambda = opt->prior_lambda;
+  }
+  SE3 T = se3FromArray(frames[0].T_imu_world);
+  const size_t n = po.run(fts, cams, T, opt->reproj_thresh_px, outlier, stats);
+  se3ToArray(T, T_imu_world_out);
+  return int(n);
 }

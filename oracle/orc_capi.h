@@ -204,6 +204,22 @@ typedef struct { int n_candidates, n_trials, n_matches, n_consumed; } orc_reproj
 int orc_reproject_match(const orc_reproj_map* map, const orc_frame* cur, int E, const int* entry_feat, int n_features_in,
                         uint8_t* occupancy, const orc_reproj_options* opt, orc_reproj_result* results, orc_reproj_stats* stats);
 
+/* f4: PoseOptimizer::run (src/svo/src/pose_optimizer.cpp). One frame bundle: frames[c] carry camera c and T_cam_imu; the state
+ * starts at frames[0].T_imu_world. N features over all cameras: ftrs (px, f, grad, level, type), feat_cam, xyz_world [N][3],
+ * has_xyz [N] (landmark or corner/edgelet seed reference present). stats = (measurement sigma, median error before, after
+ * [px-equivalent], GN iterations, n_meas, chi2). Returns n_meas - deleted outliers. */
+typedef struct {
+  int err_type;            /* 0 kUnitPlane, 1 kBearingVectorDiff, 2 kImagePlane */
+  int max_iter;
+  double eps;
+  double reproj_thresh_px;
+  int have_prior;          /* setRotationPrior(R_frame_world, lambda) */
+  double prior_q[4];
+  double prior_lambda;
+} orc_pose_opt_options;
+int orc_pose_optimize(int n_cams, const orc_frame* frames, int N, const orc_feature* ftrs, const int* feat_cam, const double* xyz_world,
+                      const uint8_t* has_xyz, const orc_pose_opt_options* opt, double T_imu_world_out[7], uint8_t* outlier, double stats[6]);
+
 /* f3: alignPyr2D for M features sharing the two pyramids; px_ref_level_0 int [M][2]; px_cur [M][2] in/out; status [M] */
 void orc_align_pyr2d(const orc_frame* ref, const orc_frame* cur, int max_level, int min_level, const int* patch_sizes, int n_iter,
                      float min_update_squared, int M, const int* px_ref_level_0, double* px_cur, uint8_t* status, int n_threads);

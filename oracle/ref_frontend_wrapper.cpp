@@ -24,6 +24,7 @@
 #include <svo/common/camera.h>
 #include <svo/common/occupancy_grid_2d.h>
 #include <svo/reprojector.h>
+#include <svo/pose_optimizer.h>
 #include <cstring>
 #include "orc_capi.h"
 
@@ -561,4 +562,52 @@ extern "C" int ref_reproject_frames(const orc_reproj_map* map, int n_visible, co
     feat_type_out[fi] = int(rm.kfs[k]->type_vec_[i]);
   }
   return n;
+}
+
+// ---- (f4) PoseOptimizer -------------------------------------------------------------------------------------------------------
+// The reference's own pose_optimizer.cpp (src/svo/src/pose_optimizer.cpp, compiled unmodified) on a bundle rebuilt from the flat
+// arrays: every feature with has_xyz gets a landmark at xyz_world (the seed branch of evaluateErrorImpl computes the same point
+// from the seed's keyframe); the others keep landmark == nullptr and a non-seed type, i.e. they are skipped.
+extern "C" int ref_pose_optimize(int n_cams, const orc_frame* frames, int N, const orc_feature* ftrs, const int* feat_cam,
+                                 const double* xyz_world, const uint8_t* has_xyz, const orc_pose_opt_options* opt,
+                                 double T_imu_world_out[7], uint8_t* outlier, double stats[6]) {
+  using namespace svo;
+  std::vector<FramePtr> fr;
+  std::vector<std::vector<int>> idx(n_cams);
+  for (int i = 0; i < N; ++i) idx[feat_cam[i]].push_back(i);
+  for (int c = 0; c < n_cams; ++c) {
+    orc_frame f = frames[c];
+    f.px = nullptr;
+    for (int k = 0; k < 7; ++k) f.T_imu_world[k] = frames[0].T_imu_world[k];
+    FramePtr p = makeFrame(f);
+    const int n = int(idx[c].size());
+    p->resizeFeatureStorage(n);
+    p->num_features_ = n;
+    for (int j = 0; j < n; ++j) {
+      const int i = idx[c][j];
+      const orc_feature& q = ftrs[i];
+      p->px_vec_.col(j) = Eigen::Vector2d(q.px[0], q.px[1]);
+      p->f_vec_.col(j) = Eigen::Vector3d(q.f[0], q.f[1], q.f[2]);
+      p->grad_vec_.col(j) = Eigen::Vector2d(q.grad[0], q.grad[1]);
+      p->level_vec_(j) = q.level;
+      p->type_vec_[j] = static_cast<FeatureType>(q.type);
+      if (has_xyz[i]) p->landmark_vec_[j] = std::make_shared<Point>(Eigen::Vector3d(xyz_world[3 * i], xyz_world[3 * i + 1], xyz_world[3 * i + 2]));
+    }
+    fr.push_back(p);
+  }
+  auto bundle = std::make_shared<FrameBundle>(fr);
+  PoseOptimizer::SolverOptions so = PoseOptimizer::getDefaultSolverOptions();
+  so.max_iter = opt->max_iter;
+  so.eps = opt->eps;
+  PoseOptimizer po(so);
+  po.reset();  // frame_handler_base.cpp:757
+  po.setErrorType(static_cast<PoseOptimizer::ErrorType>(opt->err_type));
+  if (opt->have_prior) po.setRotationPrior(svo::Quaternion(opt->prior_q[0], opt->prior_q[1], opt->prior_q[2], opt->prior_q[3]), opt->prior_lambda);
+  const size_t n = po.run(bundle, opt->reproj_thresh_px);
+  fromT(fr[0]->T_imu_world(), T_imu_world_out);
+  for (int c = 0; c < n_cams; ++c)
+    for (size_t j = 0; j < idx[c].size(); ++j) outlier[idx[c][j]] = fr[c]->type_vec_[j] == FeatureType::kOutlier && ftrs[idx[c][j]].type != int(FeatureType::kOutlier);
+  stats[0] = po.measurement_sigma_; stats[1] = po.stats_.reproj_error_before; stats[2] = po.stats_.reproj_error_after;
+  stats[3] = double(po.iterCount()); stats[4] = 0.0; stats[5] = po.getError();
+  return int(n);
 }

@@ -167,6 +167,8 @@ class Matrix<T, R, C, Opt, MR, MC, typename std::enable_if<(R > 0 && C > 0)>::ty
   T d[R * C];  // column-major
 
   Matrix() {}
+  template <int RR = R, int CC = C, typename std::enable_if<(RR != CC) && (RR == 1 || CC == 1), int>::type = 0>
+  Matrix(const Matrix<T, CC, RR>& v) { for (int i = 0; i < R * C; ++i) d[i] = v.d[i]; }  // row <-> column vector (Eigen allows it)
   template <int RR = R, int CC = C, typename std::enable_if<RR * CC == 2, int>::type = 0>
   Matrix(T x, T y) { d[0] = x; d[1] = y; }
   template <int RR = R, int CC = C, typename std::enable_if<RR * CC == 3, int>::type = 0>
@@ -262,6 +264,10 @@ class Matrix<T, R, C, Opt, MR, MC, typename std::enable_if<(R > 0 && C > 0)>::ty
   template <int P, int Q> BlockRef<Matrix, P, Q> topLeftCorner() { return BlockRef<Matrix, P, Q>(*this, 0, 0); }
   template <int P, int Q> Matrix<T, P, Q> topRightCorner() const { return block<P, Q>(0, C - Q); }
   template <int P, int Q> BlockRef<Matrix, P, Q> topRightCorner() { return BlockRef<Matrix, P, Q>(*this, 0, C - Q); }
+  template <int P, int Q> Matrix<T, P, Q> bottomRightCorner() const { return block<P, Q>(R - P, C - Q); }
+  template <int P, int Q> BlockRef<Matrix, P, Q> bottomRightCorner() { return BlockRef<Matrix, P, Q>(*this, R - P, C - Q); }
+  template <int P, int Q> Matrix<T, P, Q> bottomLeftCorner() const { return block<P, Q>(R - P, 0); }
+  template <int P, int Q> BlockRef<Matrix, P, Q> bottomLeftCorner() { return BlockRef<Matrix, P, Q>(*this, R - P, 0); }
   template <int Q> Matrix<T, R, Q> leftCols() const { return block<R, Q>(0, 0); }
   template <int Q> BlockRef<Matrix, R, Q> leftCols() { return BlockRef<Matrix, R, Q>(*this, 0, 0); }
   template <int Q> Matrix<T, R, Q> rightCols() const { return block<R, Q>(0, C - Q); }

@@ -143,6 +143,31 @@ class Frame {
     J_proj << 1, 0, -p_in_cam[0] / p_in_cam[2], 0, 1, -p_in_cam[1] / p_in_cam[2];
     J = -1.0 / p_in_cam[2] * J_proj * T_cam_imu.getRotation().getRotationMatrix() * G_x;
   }
+  // frame.h:360-371
+  inline static void jacobian_xyz2img_imu(const Transformation& T_cam_imu, const Eigen::Vector3d& p_in_imu,
+                                          const Eigen::Matrix<double, 2, 3>& J_cam, Eigen::Matrix<double, 2, 6>& J) {
+    Eigen::Matrix<double, 3, 6> G_x;
+    G_x.block<3, 3>(0, 0) = Eigen::Matrix3d::Identity();
+    G_x.block<3, 3>(0, 3) = -vk::skew(p_in_imu);
+    J = J_cam * T_cam_imu.getRotation().getRotationMatrix() * G_x;
+  }
+  // frame.h:374-397
+  inline static void jacobian_xyz2f_imu(const Transformation& T_cam_imu, const Eigen::Vector3d& p_in_imu, Eigen::Matrix<double, 3, 6>& J) {
+    Eigen::Matrix<double, 3, 6> G_x;
+    G_x.block<3, 3>(0, 0) = Eigen::Matrix3d::Identity();
+    G_x.block<3, 3>(0, 3) = -vk::skew(p_in_imu);
+    const Eigen::Vector3d p_in_cam = T_cam_imu * p_in_imu;
+    Eigen::Matrix<double, 3, 3> J_normalize;
+    double x2 = p_in_cam[0] * p_in_cam[0];
+    double y2 = p_in_cam[1] * p_in_cam[1];
+    double z2 = p_in_cam[2] * p_in_cam[2];
+    double xy = p_in_cam[0] * p_in_cam[1];
+    double yz = p_in_cam[1] * p_in_cam[2];
+    double zx = p_in_cam[2] * p_in_cam[0];
+    J_normalize << y2 + z2, -xy, -zx, -xy, x2 + z2, -yz, -zx, -yz, x2 + y2;
+    J_normalize *= 1 / std::pow(x2 + y2 + z2, 1.5);
+    J = J_normalize * T_cam_imu.getRotationMatrix() * G_x;
+  }
   // frame.cpp:274-290
   static void jacobian_xyz2image_imu(const Camera& cam, const Transformation& T_cam_imu, const Eigen::Vector3d& p_in_imu,
                                      Eigen::Matrix<double, 2, 6>& J) {
@@ -191,6 +216,7 @@ class FrameBundle {
   inline const FramePtr& at(size_t i) const { return frames_.at(i); }
   inline size_t size() const { return frames_.size(); }
   inline bool empty() const { return frames_.empty(); }
+  size_t numFeatures() const { size_t n = 0; for (const FramePtr& f : frames_) n += f->numFeatures(); return n; }  // frame.cpp:313-319
   Transformation get_T_W_B() const { return frames_[0]->T_world_imu(); }
   void set_T_W_B(const Transformation& T_W_B) {
     for (const FramePtr& frame : frames_) frame->T_f_w_ = (T_W_B * frame->T_body_cam_).inverse();

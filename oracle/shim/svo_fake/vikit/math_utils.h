@@ -1,7 +1,10 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): the few vikit/math_utils.h helpers the direct front-end uses (the reference header
 // also declares Lie-group utilities whose bodies need more of Eigen than the stand-in provides).
 #pragma once
+#include <algorithm>
+#include <cassert>
 #include <cmath>
+#include <vector>
 #include <Eigen/Core>
 #include <kindr/minimal/quat-transformation.h>
 namespace vk {
@@ -17,5 +20,12 @@ template <class T> inline T normPdf(const T x, const T mean, const T sigma) {
   T result = std::exp(exponent);
   result /= sigma * std::sqrt(2 * M_PI);
   return result;
+}
+// vikit/math_utils.h:165-172
+template <class T> T getMedian(std::vector<T>& data_vec) {
+  assert(!data_vec.empty());
+  typename std::vector<T>::iterator it = data_vec.begin() + std::floor(data_vec.size() / 2);
+  std::nth_element(data_vec.begin(), it, data_vec.end());
+  return *it;
 }
 }  // namespace vk

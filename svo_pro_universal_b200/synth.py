@@ -433,3 +433,41 @@ def make_reproject_scene(seed, n_kfs=4, n_per_kf=260, cam=None, integer_scores=F
     entry_feat = np.array([remap[i] for i in range(n_first)], np.int32)
     return dict(cam=cam, kf_imgs=kf_imgs, cur_img=cur_imgs[0], cur_T_f_w=cur_Ts[0], cur_imgs=cur_imgs, cur_Ts=np.array(cur_Ts),
                 tables=tables, entry_feat=entry_feat, scene=scene)
+
+
+def make_pose_opt_case(seed, n_per_cam=150, n_cams=1, cam=None, px_noise=0.4, outlier_frac=0.06, edgelet_frac=0.25, rot_err=0.01, trans_err=0.03):
+    """A frame bundle for PoseOptimizer::run (SURVEY §8 f4): n_cams cameras (stereo baseline 11 cm) observing random 3-D points;
+    measurements = projections at the true pose + Gaussian pixel noise, a few gross outliers, a few features without a 3-D
+    point; the initial IMU pose is the true one perturbed by (rot_err rad, trans_err m)."""
+    cam = dict(cam or EUROC_CAM)
+    rng = np.random.default_rng(seed + 6000)
+    T_cam_imu = [euroc_T_cam_imu()]
+    if n_cams == 2:
+        T_cam_imu.append(se3_mul(se3_exp_small(np.zeros(3), np.array([-0.11, 0.0, 0.0])), T_cam_imu[0]))
+    T_imu_world_true = se3_exp_small(rng.normal(size=3) * 0.2, rng.normal(size=3))
+    px, f, grad, level, ftype, xyz, has, fcam = [], [], [], [], [], [], [], []
+    for c in range(n_cams):
+        T_f_w = se3_mul(T_cam_imu[c], T_imu_world_true)
+        R, t = se3_to_Rt(T_f_w)
+        p = np.stack([rng.uniform(20, cam["width"] - 20, n_per_cam), rng.uniform(20, cam["height"] - 20, n_per_cam)], 1)
+        d = rng.uniform(2.0, 8.0, n_per_cam)
+        fb = cam_backproject(cam, p)
+        fb /= np.linalg.norm(fb, axis=1)[:, None]
+        Xc = fb * d[:, None]
+        Xw = (Xc - t) @ R          # R^T (Xc - t)
+        lv = rng.integers(0, 3, n_per_cam)
+        meas = p + rng.normal(size=p.shape) * px_noise * (1 << lv)[:, None]
+        out = rng.uniform(size=n_per_cam) < outlier_frac
+        meas[out] += rng.uniform(-25, 25, (int(out.sum()), 2))
+        fm = cam_backproject(cam, meas)
+        fm /= np.linalg.norm(fm, axis=1)[:, None]
+        g = rng.normal(size=(n_per_cam, 2)); g /= np.linalg.norm(g, axis=1)[:, None]
+        ty = np.where(rng.uniform(size=n_per_cam) < edgelet_frac, K_EDGELET, K_CORNER)
+        hx = rng.uniform(size=n_per_cam) > 0.05
+        ty = np.where(hx, ty, K_OUTLIER)
+        px.append(meas); f.append(fm); grad.append(g); level.append(lv); ftype.append(ty); xyz.append(Xw); has.append(hx); fcam.append(np.full(n_per_cam, c))
+    T_init = se3_mul(se3_exp_small(rng.normal(size=3) * rot_err, rng.normal(size=3) * trans_err), T_imu_world_true)
+    cat = np.concatenate
+    return dict(cam=cam, T_cam_imu=T_cam_imu, T_imu_world_true=T_imu_world_true, T_imu_world_init=T_init, px=cat(px), f=cat(f), grad=cat(grad),
+                level=cat(level).astype(np.int32), type=cat(ftype).astype(np.int32), xyz_world=cat(xyz), has_xyz=cat(has).astype(np.uint8),
+                feat_cam=cat(fcam).astype(np.int32))
