@@ -349,6 +349,40 @@ int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, con
                              const int* entry_feat, uint8_t* occupancy, const svo_reprojector_options* opt, svo_reproj_result* results,
                              svo_reproj_stats* stats, svo_mem mem);
 
+/* ---- (f4) svo::PoseOptimizer ------------------------------------------------------------------------------------ */
+typedef struct { /* PoseOptimizer::getDefaultSolverOptions (src/svo/src/pose_optimizer.cpp:22-29) + run()'s arguments */
+  int err_type;             /* PoseOptimizer::ErrorType: 0 kUnitPlane (default), 1 kBearingVectorDiff, 2 kImagePlane */
+  int max_iter;             /* 10 */
+  double eps;               /* 0.000001 */
+  double reproj_thresh_px;  /* run(frame_bundle, reproj_thresh_px): outlier threshold, default poseoptim_thresh = 2.0 */
+  double prior_lambda;      /* setRotationPrior(R_frame_world, lambda); used when prior_q is passed */
+} svo_pose_optimizer_options;
+
+typedef struct {
+  double T_imu_world[7];           /* optimised state */
+  double T_f_w[SVO_MAX_CAMS][7];   /* frame->T_f_w_ = T_cam_imu * T_imu_world of every camera (pose_optimizer.cpp:58-61) */
+  double measurement_sigma;        /* MAD scale of the start errors */
+  double reproj_error_before, reproj_error_after;  /* stats_ (medians, scaled by the focal length for kUnitPlane) */
+  double chi2;
+  int n_meas_final;                /* run()'s return value: measurements minus removed outliers */
+  int n_meas;
+  int iters;                       /* iterCount() */
+  int stop;
+} svo_pose_opt_result;
+
+/* PoseOptimizer::run (src/svo/include/svo/pose_optimizer.h:20-103; src/svo/src/pose_optimizer.cpp:39-94) for B independent
+ * frame bundles of n_cams cameras (cams[c], T_cam_imu [n_cams][7] shared by all bundles). Bundle b starts at
+ * T_imu_world[b] and owns the features [feat_begin[b], feat_begin[b+1]) of ftrs (px, f, grad, level, type of the current
+ * frames' columns), observed by camera feat_cam[i] (NULL = camera 0), with the 3-D point xyz_world[i] where has_xyz[i] (the
+ * landmark's position, or the seed's position from its reference keyframe; features with neither are skipped as in
+ * evaluateErrorImpl, :123-137). prior_q: NULL or [B][4], the rotation prior R_frame_world of setRotationPrior.
+ * outlier [n_features] receives 1 where removeOutliers marks the feature kOutlier (:283-290; the caller resets the landmark /
+ * seed reference). At most 2048 features per bundle. n_features = feat_begin[B]. */
+int svo_cuda_pose_optimize(svo_cuda_ctx* ctx, int n_cams, const svo_camera* cams, const double* T_cam_imu, int B,
+                           const double* T_imu_world, const int* feat_begin, int n_features, const svo_feature* ftrs,
+                           const int* feat_cam, const double* xyz_world, const uint8_t* has_xyz, const double* prior_q,
+                           const svo_pose_optimizer_options* opt, svo_pose_opt_result* results, uint8_t* outlier, svo_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,22 @@ def reprojector_options(**kw):
     return o
 
 
+class PoseOptimizerOptions(C.Structure):
+    _fields_ = [("err_type", C.c_int), ("max_iter", C.c_int), ("eps", C.c_double), ("reproj_thresh_px", C.c_double),
+                ("prior_lambda", C.c_double)]
+
+
+def pose_optimizer_options(**kw):
+    """PoseOptimizer::getDefaultSolverOptions (pose_optimizer.cpp:22-29), kUnitPlane, poseoptim_thresh 2.0 px."""
+    o = PoseOptimizerOptions(0, 10, 0.000001, 2.0, 0.0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+POSE_OPT_RESULT_DTYPE = np.dtype([("T_imu_world", "<f8", 7), ("T_f_w", "<f8", (MAX_CAMS, 7)), ("measurement_sigma", "<f8"),
+                                  ("reproj_error_before", "<f8"), ("reproj_error_after", "<f8"), ("chi2", "<f8"),
+                                  ("n_meas_final", "<i4"), ("n_meas", "<i4"), ("iters", "<i4"), ("stop", "<i4")])
 REPROJ_RESULT_DTYPE = np.dtype([("cur_px", "<f8", 2), ("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("seed_state", "<f8", 4),
                                 ("status", "<i4"), ("order", "<i4"), ("slot", "<i4"), ("level", "<i4"), ("type_out", "<i4"),
                                 ("match_result", "<i4"), ("d_failed", "<i4"), ("d_succeeded", "<i4")])
@@ -187,6 +203,8 @@ def lib():
                                             vp, C.POINTER(MatcherOptions), C.POINTER(DepthFilterOptions), vp, vp, ci]
         L.svo_cuda_reproject_match.argtypes = [vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), C.POINTER(ReprojMap), ci, vp, vp, vp,
                                                vp, ci, vp, vp, C.POINTER(ReprojectorOptions), vp, vp, ci]
+        L.svo_cuda_pose_optimize.argtypes = [vp, ci, C.POINTER(Camera), vp, ci, vp, vp, ci, vp, vp, vp, vp, vp,
+                                             C.POINTER(PoseOptimizerOptions), vp, vp, ci]
         _lib = L
     return _lib
 
@@ -198,7 +216,7 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_pyramid_fast_detect", "svo_cuda_fast_level_maps", "svo_cuda_sparse_align", "svo_cuda_align2d", "svo_cuda_align1d",
     "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
-    "svo_cuda_reproject_match",
+    "svo_cuda_reproject_match", "svo_cuda_pose_optimize",
 ]
 
 
@@ -526,3 +544,26 @@ def reproject_match(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, tables, cur_T_f_w, 
     ctx.check(lib().svo_cuda_reproject_match(ctx._h, ref_pyr._h, cur_pyr._h, C.byref(cam_ref), C.byref(cam_cur), C.byref(m), F, q[0], q[1],
                                              q[2], q[3], n_entries, q[4], q[5], C.byref(opt), q[6], q[7], kind))
     return results, stats
+
+
+def pose_optimize(ctx, cams, T_cam_imu, T_imu_world, feat_begin, ftrs, feat_cam, xyz_world, has_xyz, opt, prior_q=None, results=None,
+                  outlier=None):
+    """svo_cuda_pose_optimize: B bundles. Arrays numpy (host) or torch cuda. Returns (results, outlier)."""
+    n_cams = len(cams)
+    cam_arr = (Camera * n_cams)(*cams)
+    T_cam_imu = np.ascontiguousarray(T_cam_imu, np.float64).reshape(n_cams, 7)
+    B = int(T_imu_world.shape[0])
+    N = _n_features(ftrs)
+    dev = _is_torch(T_imu_world) and T_imu_world.is_cuda
+    if results is None:
+        if dev:
+            import torch
+            results = torch.zeros(B * POSE_OPT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=T_imu_world.device)
+            outlier = torch.zeros(max(N, 1), dtype=torch.uint8, device=T_imu_world.device)
+        else:
+            results = np.zeros(B, POSE_OPT_RESULT_DTYPE)
+            outlier = np.zeros(N, np.uint8)
+    ps, kind = _ptrs(T_imu_world, feat_begin, ftrs, feat_cam, xyz_world, has_xyz, prior_q, results, outlier)
+    ctx.check(lib().svo_cuda_pose_optimize(ctx._h, n_cams, cam_arr, C.c_void_p(T_cam_imu.ctypes.data), B, ps[0], ps[1], N, ps[2], ps[3],
+                                           ps[4], ps[5], ps[6], C.byref(opt), ps[7], ps[8], kind))
+    return results, outlier

@@ -15,6 +15,8 @@ frontend_ref_golden.npz outputs of the REFERENCE's own SparseImgAlign::run, Matc
                       oracle/shim) on seeded inputs (tests/helpers.py:frontend_outputs): pins rows b, c1, c6-c7, d1-d3.
 reproject_ref_golden.npz outputs of the REFERENCE's own reprojector.cpp (getCandidate, sortCandidates*, matchCandidates,
                       matchCandidate; compiled into libfrontend_ref.so) on the cases of tests/helpers.py:REPROJECT_CASES: pins row f1.
+pose_opt_ref_golden.npz outputs of the REFERENCE's own PoseOptimizer::run (pose_optimizer.cpp compiled into libfrontend_ref.so) on
+                      tests/helpers.py:POSE_OPT_CASES: pins row f4.
 klt_ref_golden.npz    outputs of the REFERENCE's own alignPyr2D (libdirect_ref.so) on the cases of tests/test_klt_cpu.py.
 Usage: python tests/golden/make_golden.py
 """
@@ -122,6 +124,14 @@ def klt_golden():
     print("klt_ref_golden.npz", os.path.getsize(os.path.join(HERE, "klt_ref_golden.npz")))
 
 
+def pose_opt_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_frontend_lib() is not None, "oracle/_ref/libfrontend_ref.so missing: run make -C oracle"
+    np.savez_compressed(os.path.join(HERE, "pose_opt_ref_golden.npz"), **helpers.pose_opt_outputs(orc, "ref"))
+    print("pose_opt_ref_golden.npz", os.path.getsize(os.path.join(HERE, "pose_opt_ref_golden.npz")))
+
+
 def reproject_golden():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
@@ -137,6 +147,7 @@ if __name__ == "__main__":
         for name in sys.argv[1:]:
             globals()[name + "_golden"]()
         sys.exit(0)
+    pose_opt_golden()
     reproject_golden()
     klt_golden()
     frontend_golden()

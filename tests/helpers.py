@@ -292,3 +292,25 @@ def reproject_frames_reference(orc):
         for k in REPROJ_FRAMES_KEYS:
             out[f"rf{ci}_{k}"] = o[k][:416] if k == "occupancy" else o[k]
     return out
+
+
+# ---- f4: PoseOptimizer -----------------------------------------------------------------------------------------------------------
+# (case seed, cameras, error type, radtan camera, rotation prior)
+POSE_OPT_CASES = [(1, 1, 0, False, False), (2, 2, 0, False, True), (3, 1, 2, False, False), (4, 1, 1, False, True), (5, 2, 1, True, False),
+                  (6, 1, 2, True, True), (7, 2, 2, False, False), (8, 1, 0, True, False)]
+
+
+def pose_opt_case(spec):
+    seed, n_cams, err_type, radtan, prior = spec
+    c = synth.make_pose_opt_case(seed, n_cams=n_cams, cam=synth.EUROC_CAM_RADTAN if radtan else None)
+    return c, (c["T_imu_world_true"][:4].copy() if prior else None)
+
+
+def pose_opt_outputs(orc, which):
+    """Every POSE_OPT_CASES case through the oracle ("orc") or the reference's own compiled pose_optimizer.cpp ("ref")."""
+    out = {}
+    for ci, spec in enumerate(POSE_OPT_CASES):
+        c, prior = pose_opt_case(spec)
+        n, T, outl, stats = orc.pose_optimize(c, orc.pose_opt_options(err_type=spec[2], prior_q=prior, prior_lambda=0.5), which)
+        out[f"p{ci}_n"], out[f"p{ci}_T"], out[f"p{ci}_outlier"], out[f"p{ci}_stats"] = np.array(n), T, outl, stats[:4]
+    return out
