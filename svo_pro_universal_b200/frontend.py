@@ -4,6 +4,7 @@ configs[4]) — every stage a C-ABI call on device-resident arrays, no host roun
     pyramid of the two new frames                     svo_cuda_pyr_build            (frame_handler_base.cpp:184-186)
  -> SparseImgAlign::run on the 2-camera bundle        svo_cuda_sparse_align         (frame_handler_base.cpp:610-643)
  -> Reprojector::reprojectFrames per camera           svo_cuda_reproject_match      (frame_handler_base.cpp:646-743)
+ -> PoseOptimizer::run on the matched features        svo_cuda_pose_optimize        (frame_handler_base.cpp:746-790)
  -> DepthFilter::updateSeeds of the last keyframe     svo_cuda_update_seeds         (frame_handler_stereo.cpp:82)
  -> FastDetector on the new left frame                svo_cuda_fast_detect          (depth_filter.cpp:255-365, new keyframe)
 
@@ -55,6 +56,10 @@ class StereoFrontendBatch:
     def __init__(self, ctx, scenes, B, device, max_features=180):
         import torch
         self.torch, self.ctx, self.B, self.dev, self.F = torch, ctx, B, device, max_features
+        # ONE stream for the library's kernels and for torch's glue ops (slicing the aligner's poses, resetting the grid):
+        # the context is switched to a torch stream and every step runs with that stream current
+        self.stream = torch.cuda.Stream(device=device)
+        ctx.set_stream(self.stream.cuda_stream)
         U = len(scenes)
         self.scenes, self.sid = scenes, np.arange(B) % U
         sid = self.sid
@@ -121,6 +126,20 @@ class StereoFrontendBatch:
                            pt_n_failed=t(np.zeros(n_pts, np.int32)), pt_n_succeeded=t(np.zeros(n_pts, np.int32)),
                            pt_obs_begin=t(np.arange(n_pts + 1, dtype=np.int32)), obs_feat=t(obs_feat))
         self.host_tables = dict(feat=feat, feat_kf=feat_kf, feat_point=point, eb=eb)
+        # ---- pose optimiser: bundle i = the entries of both cameras of pair i; an entry is a measurement once it is matched.
+        # Its 3-D point: the landmark, or the converged seed's position from its reference keyframe (pose_optimizer.cpp:123-137)
+        R1 = [synth.se3_to_Rt(synth.se3_inv(sc["T_f_w_ref"][1])) for sc in scenes]
+        xyz_blocks = [np.concatenate([blocks[u]["Xw"], (scenes[u]["f"][1] * scenes[u]["depth"][1][:, None]) @ R1[u][0].T + R1[u][1]]) for u in range(U)]
+        self.po_xyz = t(np.concatenate([xyz_blocks[s_] for s_ in sid]))
+        self.po_cam = t((~is_left).astype(np.int32))
+        self.po_begin = t(eb[::2].copy())
+        self.po_type = t(feat["type"].astype(np.int32))
+        self.po_ftrs = torch.zeros((len(feat), 8), dtype=torch.float64, device=device)   # svo_feature rows (64 bytes)
+        self.po_opt = capi.pose_optimizer_options()
+        self.d_po = torch.zeros(B * capi.POSE_OPT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=device)
+        self.d_po_outlier = torch.zeros(len(feat), dtype=torch.uint8, device=device)
+        q_ic, t_ic = synth.se3_inv(scenes[0]["T_cam_imu"][0])[:4], synth.se3_inv(scenes[0]["T_cam_imu"][0])[4:]
+        self.q_ic, self.t_ic = t(q_ic), t(t_ic)
         self.entry_begin, self.entry_feat = t(eb), t(ef)
         self.n_entries = int(eb[-1])
         self.reproj_cur_idx = t(np.array([c * B + i for i in range(B) for c in range(2)], np.int32))  # frame j = 2i+c
@@ -153,15 +172,38 @@ class StereoFrontendBatch:
         # ---- detector
         self.det_opt = capi.detector_options()
         self.d_corners = torch.zeros(B * self.n_cells * capi.CORNER_DTYPE.itemsize, dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)   # the uploads above ran on torch's default stream
 
-    STAGES = ("pyramid", "sparse_align", "reproject", "update_seeds", "fast_detect")
+    def release(self):
+        """Give the context its own stream back (the batch object must not be stepped afterwards)."""
+        self.torch.cuda.synchronize(self.dev)
+        self.ctx.set_stream(0)
+
+    STAGES = ("pyramid", "sparse_align", "reproject", "pose_optimize", "update_seeds", "fast_detect")
+
+    def _imu_pose(self, T_f_w0):
+        """T_imu_world = T_imu_cam0 * T_f_w of the left camera ([B,7] quaternion + translation), on the device."""
+        torch = self.torch
+        a, b = self.q_ic, T_f_w0[:, :4]
+        aw, ax, ay, az = a[0], a[1], a[2], a[3]
+        bw, bx, by, bz = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+        q = torch.stack([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                         aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw], 1)
+        v = T_f_w0[:, 4:7]
+        u = a[1:4].expand_as(v)
+        uv = torch.cross(u, v, dim=1)
+        rot = v + 2.0 * (aw * uv + torch.cross(u, uv, dim=1))
+        return torch.cat([q, rot + self.t_ic], 1).contiguous()
 
     def step(self, mark=None):
         """One pass of the whole front-end over the batch; everything stays on the device. mark(i) is called after stage i
         (bench: records a CUDA event on the stream)."""
+        with self.torch.cuda.stream(self.stream):
+            self._step(mark or (lambda i: None))
+
+    def _step(self, mark):
         torch = self.torch
         B, a = self.B, self.align_in
-        mark = mark or (lambda i: None)
         self.cur.build()
         mark(0)
         capi.sparse_align(self.ctx, [self.ref, self.ref], [self.cur, self.cur], [self.cam, self.cam], self.T_cam_imu, self.T_imu_world_ref,
@@ -175,21 +217,37 @@ class StereoFrontendBatch:
         capi.reproject_match(self.ctx, self.ref, self.cur, self.cam, self.cam, self.tables, cur_T, self.n_in, self.entry_begin, self.entry_feat,
                              self.occ, self.reproj_opt, cur_frame_idx=self.reproj_cur_idx, results=self.d_reproj, stats=self.d_rstats)
         mark(2)
+        # the matched entries become the measurements of the pose optimiser: (px, f, grad) of the match, the candidate's type
+        nE = self.n_entries
+        r64 = self.d_reproj.view(torch.float64).view(nE, 17)
+        r32 = self.d_reproj.view(torch.int32).view(nE, 34)
+        self.po_ftrs[:, 0:7] = r64[:, 2:9]
+        f32 = self.po_ftrs.view(torch.int32).view(nE, 16)
+        f32[:, 14] = self.po_type
+        f32[:, 15] = r32[:, 29]
+        self.po_has = (r32[:, 26] == capi.REPROJ_MATCHED).to(torch.uint8)
+        self.po_T0 = self._imu_pose(cur_T.view(B, 2, 7)[:, 0])
+        capi.pose_optimize(self.ctx, [self.cam, self.cam], self.T_cam_imu, self.po_T0, self.po_begin, self.po_ftrs.view(torch.uint8).view(-1),
+                           self.po_cam, self.po_xyz, self.po_has, self.po_opt, results=self.d_po, outlier=self.d_po_outlier)
+        mark(3)
         self.seed_types.copy_(self.seed_types0); self.seed_state.copy_(self.seed_state0)
         self.n_seed_ok, _ = capi.update_seeds(self.ctx, self.ref, self.cur, self.cam, self.cam, self.seed_ftrs, self.seed_types, self.seed_state,
                                               self.seed_mu_range, self.seed_obs_frame, self.seed_obs_T, self.seed_T, self.mopt, self.dopt,
                                               ref_frame_idx=self.seed_ref_idx, want_match_results=False)
-        mark(3)
-        capi.fast_detect(self.ctx, self.cur, self.det_opt, first=0, count=B, corners_out=self.d_corners)
         mark(4)
+        capi.fast_detect(self.ctx, self.cur, self.det_opt, first=0, count=B, corners_out=self.d_corners)
+        mark(5)
 
     def results(self):
         """Host copies of every stage's outputs (numpy)."""
         self.ctx.synchronize()
+        self.torch.cuda.synchronize(self.dev)
         return dict(align=self.d_align.cpu().numpy().view(capi.ALIGN_RESULT_DTYPE),
                     reproj=self.d_reproj.cpu().numpy().view(capi.REPROJ_RESULT_DTYPE),
                     reproj_stats=self.d_rstats.cpu().numpy().view(capi.REPROJ_STATS_DTYPE), occupancy=self.occ.cpu().numpy(),
                     seed_types=self.seed_types.cpu().numpy(), seed_state=self.seed_state.cpu().numpy(),
-                    n_seed_ok=int(self.n_seed_ok.item()),
+                    n_seed_ok=int(self.n_seed_ok.item()), pose_opt=self.d_po.cpu().numpy().view(capi.POSE_OPT_RESULT_DTYPE),
+                    pose_opt_outlier=self.d_po_outlier.cpu().numpy(), pose_opt_T0=self.po_T0.cpu().numpy(),
+                    pose_opt_has=self.po_has.cpu().numpy(), pose_opt_xyz=self.po_xyz.cpu().numpy(),
                     corners=self.d_corners.cpu().numpy().view(capi.CORNER_DTYPE).reshape(self.B, self.n_cells),
                     entry_begin=self.entry_begin.cpu().numpy())

@@ -20,6 +20,7 @@ def test_stereo_frontend_chain_matches_oracle(ctx, orc):
     fb.step()
     fb.step()   # a second pass over the same batch gives the same answer (state is reset per step)
     out = fb.results()
+    fb.release()
     ang = helpers.reproject_px_error_angle(scenes[0]["cam"])
     n_match_total = 0
     for i in range(B):
@@ -73,6 +74,27 @@ def test_stereo_frontend_chain_matches_oracle(ctx, orc):
                    (so["n_candidates"], so["n_trials"], so["n_matches"], so["n_consumed"])
             assert np.array_equal(out["occupancy"][j], occ)
             n_match_total += int(so["n_matches"])
+        # ---- PoseOptimizer::run on the matched entries of both cameras (same start pose, same measurements)
+        lo, hi = out["entry_begin"][2 * i], out["entry_begin"][2 * i + 2]
+        rg = out["reproj"][lo:hi]
+        n0 = out["entry_begin"][2 * i + 1] - lo
+        case = dict(cam=cam, T_cam_imu=sc["T_cam_imu"], T_imu_world_init=out["pose_opt_T0"][i], px=rg["px"], f=rg["f"], grad=rg["grad"],
+                    level=rg["level"], type=np.where(np.arange(hi - lo) < n0, synth.K_CORNER, synth.K_CORNER_SEED_CONV).astype(np.int32),
+                    xyz_world=out["pose_opt_xyz"][lo:hi], has_xyz=(rg["status"] == 4).astype(np.uint8),
+                    feat_cam=(np.arange(hi - lo) >= n0).astype(np.int32))
+        n_po, T_po, outl_po, st_po = orc.pose_optimize(case, orc.pose_opt_options())
+        pg = out["pose_opt"][i]
+        dq, dt = helpers.pose_diff(pg["T_imu_world"], T_po)
+        if not (dq < 1e-9 and dt < 1e-9):
+            import os
+            os.makedirs("gpurun_out", exist_ok=True)
+            np.savez("gpurun_out/chain_po_debug.npz", T_gpu=pg["T_imu_world"], T_orc=T_po, st_orc=st_po, sigma_gpu=pg["measurement_sigma"],
+                     iters_gpu=pg["iters"], n_gpu=pg["n_meas"], outl_gpu=out["pose_opt_outlier"][lo:hi], outl_orc=outl_po,
+                     **{"case_" + k: np.asarray(v) for k, v in case.items() if k != "cam"})
+        assert dq < 1e-9 and dt < 1e-9 and pg["n_meas_final"] == n_po and pg["iters"] == int(st_po[3]), (i, dq, dt)
+        assert np.array_equal(out["pose_opt_outlier"][lo:hi], outl_po) and pg["n_meas"] > 200
+        dq, dt = helpers.pose_diff(synth.se3_mul(sc["T_cam_imu"][0], pg["T_imu_world"]), T_true)   # still at the true pose
+        assert dq < 2e-3 and dt < 5e-3
         # ---- FAST detector on the new left frame
         co = orc.fast_detector(sc["imgs"]["c0"])
         cg = out["corners"][i]

@@ -79,10 +79,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ctx = capi.Context(local)
-    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
     lo, hi = shard.partition(args.pairs, world, rank)
     scenes = [frontend.make_stereo_scene(81 + s) for s in range(args.unique)]
     fb = frontend.StereoFrontendBatch(ctx, scenes, hi - lo, dev)
+    stream = fb.stream
+    torch.cuda.set_stream(stream)
     for _ in range(args.warmup):
         fb.step()
     sync = lambda: (torch.cuda.synchronize(), dist.barrier() if world > 1 else None, torch.cuda.synchronize())
@@ -96,7 +97,7 @@ def main():
     sync()
     ms = e0.elapsed_time(e1) / args.steps
     # stage breakdown of one more pass (events between the stages)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(fb.STAGES) + 1)]
     evs[0].record(stream)
     fb.step(lambda i: evs[i + 1].record(stream))
     torch.cuda.synchronize()
@@ -110,7 +111,7 @@ def main():
         assert rank != 0 or g.shape == (args.pairs, 7)
     if rank == 0:
         cpu = cpu_chain(scenes)
-        print(json.dumps({"path": "configs[4]: full front-end batch (pyramid + stereo sparse align + Reprojector + depth filter + FAST)",
+        print(json.dumps({"path": "configs[4]: full front-end batch (pyramid + stereo sparse align + Reprojector + pose optimizer + depth filter + FAST)",
                           "config": f"{args.pairs} synthetic stereo frame pairs ({args.unique} unique scenes tiled; every frame resident in HBM: "
                                     f"{4 * (hi - lo) * 483360 / 1e9:.1f} GB of pyramids per GPU), 180 + 150 features, 120 seeds per pair",
                           "n_gpus": world, "stereo_pairs_per_s": args.pairs / (ms * 1e-3), "ms_per_step": ms, "scaling": "strong",
