@@ -647,6 +647,88 @@ void Reprojector::reprojectFrames(const FramePtr& cur_frame, const std::vector<F
   if (doesFrameHaveEnoughFeatures(cur_frame)) occupyRemaining();
 }
 
+// ---- PoseOptimizer -----------------------------------------------------------------------------------------------------------------
+PoseOptimizer::SolverOptions PoseOptimizer::getDefaultSolverOptions() {
+  SolverOptions options;
+  options.max_iter = 10;
+  options.eps = 0.000001;
+  return options;
+}
+void PoseOptimizer::setRotationPrior(const std::array<double, 4>& R_frame_world, double lambda) {
+  have_prior_ = true;
+  prior_q_ = R_frame_world;
+  prior_lambda_ = lambda;
+}
+size_t PoseOptimizer::run(const FrameBundle::Ptr& frame_bundle, double reproj_thresh_px) {
+  if (!frame_bundle || frame_bundle->empty()) throw b200::Error("PoseOptimizer: FrameBundle is empty");  // CHECK, :41
+  const size_t n_cams = frame_bundle->size();
+  if (n_cams > SVO_MAX_CAMS) throw b200::Error("PoseOptimizer: too many cameras");
+  std::vector<svo_camera> cams;
+  std::vector<double> T_cam_imu, xyz;
+  std::vector<svo_feature> ftrs;
+  std::vector<int> feat_cam;
+  std::vector<uint8_t> has;
+  for (size_t c = 0; c < n_cams; ++c) {
+    const Frame& f = *frame_bundle->at(c);
+    cams.push_back(f.cam_->model);
+    double T[7];
+    f.T_cam_imu_.toArray(T);
+    T_cam_imu.insert(T_cam_imu.end(), T, T + 7);
+    for (size_t i = 0; i < f.num_features_; ++i) {
+      svo_feature q{};
+      q.px[0] = f.px_vec_[i][0]; q.px[1] = f.px_vec_[i][1];
+      for (int k = 0; k < 3; ++k) q.f[k] = f.f_vec_[i][k];
+      q.grad[0] = f.grad_vec_[i][0]; q.grad[1] = f.grad_vec_[i][1];
+      q.type = int(f.type_vec_[i]);
+      q.level = f.level_vec_[i];
+      std::array<double, 3> p{{0, 0, 0}};
+      uint8_t h = 0;
+      if (f.isValidLandmark(i)) {  // evaluateErrorImpl, :123-137
+        p = f.landmark_vec_[i]->pos_;
+        h = 1;
+      } else if (isCornerEdgeletSeed(f.type_vec_[i]) && i < f.seed_ref_vec_.size() && f.seed_ref_vec_[i].keyframe) {
+        const Frame& kf = *f.seed_ref_vec_[i].keyframe;
+        const int id = f.seed_ref_vec_[i].seed_id;
+        const Transformation T_w_kf = kf.T_f_w_.inverse();
+        const double d = 1.0 / kf.invmu_sigma2_a_b_vec_[id][0];
+        const auto v = rotate(T_w_kf.q, {kf.f_vec_[id][0] * d, kf.f_vec_[id][1] * d, kf.f_vec_[id][2] * d});
+        p = {v[0] + T_w_kf.t[0], v[1] + T_w_kf.t[1], v[2] + T_w_kf.t[2]};
+        h = 1;
+      }
+      ftrs.push_back(q); feat_cam.push_back(int(c)); has.push_back(h);
+      xyz.insert(xyz.end(), p.begin(), p.end());
+    }
+  }
+  if (ftrs.empty()) throw b200::Error("PoseOptimizer: No features in frames");  // CHECK_GT, :42
+  double T0[7];
+  frame_bundle->at(0)->T_imu_world().toArray(T0);
+  const int feat_begin[2] = {0, int(ftrs.size())};
+  svo_pose_optimizer_options o{};
+  o.err_type = int(err_type_); o.max_iter = int(solver_options_.max_iter); o.eps = solver_options_.eps;
+  o.reproj_thresh_px = reproj_thresh_px; o.prior_lambda = prior_lambda_;
+  svo_pose_opt_result r{};
+  std::vector<uint8_t> outlier(ftrs.size());
+  b200::check(svo_cuda_pose_optimize(b200::context(), int(n_cams), cams.data(), T_cam_imu.data(), 1, T0, feat_begin, int(ftrs.size()), ftrs.data(),
+                                     feat_cam.data(), xyz.data(), has.data(), have_prior_ ? prior_q_.data() : nullptr, &o, &r, outlier.data(),
+                                     SVO_MEM_HOST), "svo_cuda_pose_optimize");
+  size_t k = 0;
+  for (size_t c = 0; c < n_cams; ++c) {
+    Frame& f = *frame_bundle->at(c);
+    f.T_f_w_ = Transformation::fromArray(r.T_f_w[c]);
+    for (size_t i = 0; i < f.num_features_; ++i, ++k)
+      if (outlier[k]) {  // removeOutliers, :283-290
+        f.type_vec_[i] = FeatureType::kOutlier;
+        if (i < f.seed_ref_vec_.size()) f.seed_ref_vec_[i].keyframe.reset();
+        if (i < f.landmark_vec_.size()) f.landmark_vec_[i] = nullptr;
+      }
+  }
+  measurement_sigma_ = r.measurement_sigma;
+  stats_.reproj_error_before = r.reproj_error_before;
+  stats_.reproj_error_after = r.reproj_error_after;
+  iter_ = size_t(r.iters);
+  return size_t(r.n_meas_final);
+}
+
 // ---- FAST detector ----------------------------------------------------------------------------------------------------------------
 namespace feature_detection_utils {
 void fastDetector(const b200::GpuPyramid& gpu, const int threshold, const int border, const size_t min_level, const size_t max_level,

@@ -369,6 +369,36 @@ class Reprojector {  // reprojector.h:77-166
   }
 };
 
+// ---- (f4) PoseOptimizer ---------------------------------------------------------------------------------------------------------
+class PoseOptimizer {  // src/svo/include/svo/pose_optimizer.h:20-103
+ public:
+  using Ptr = std::shared_ptr<PoseOptimizer>;
+  using SolverOptions = solver::MiniLeastSquaresSolverOptions;
+  enum class ErrorType { kUnitPlane, kBearingVectorDiff, kImagePlane };
+  struct Statistics {
+    double reproj_error_after = 0.0;
+    double reproj_error_before = 0.0;
+  } stats_;
+  explicit PoseOptimizer(SolverOptions solver_options) : solver_options_(solver_options) {}
+  static SolverOptions getDefaultSolverOptions();  // pose_optimizer.cpp:22-29: GaussNewton, max_iter 10, eps 1e-6
+  // Optimises frame->T_f_w_ of every frame of the bundle over its landmark / seed observations, marks outliers
+  // (type kOutlier, landmark and seed reference dropped) and returns the number of remaining measurements (:39-94).
+  size_t run(const FrameBundle::Ptr& frame_bundle, double reproj_thresh_px);
+  void setRotationPrior(const std::array<double, 4>& R_frame_world, double lambda);  // quaternion (w,x,y,z), :30-37
+  void reset() { have_prior_ = false; iter_ = 0; }  // MiniLeastSquaresSolver::reset
+  size_t iterCount() const { return iter_; }
+  void setErrorType(ErrorType type) { err_type_ = type; }
+  double measurement_sigma_ = 1.0;
+  ErrorType err_type_ = ErrorType::kUnitPlane;
+  SolverOptions solver_options_;
+
+ private:
+  bool have_prior_ = false;
+  std::array<double, 4> prior_q_{{1, 0, 0, 0}};
+  double prior_lambda_ = 0.0;
+  size_t iter_ = 0;
+};
+
 // ---- device plumbing --------------------------------------------------------------------------------------------------------
 namespace b200 {
 struct Error : std::runtime_error { using std::runtime_error::runtime_error; };

@@ -165,3 +165,37 @@ def test_cpp_reprojector_facade_matches_reference(tmp_path):
         assert np.array_equal(ptc.astype(int), g["pt_counters"]), ci
         np.testing.assert_allclose(fs[:, :4], g["feat_state"], rtol=1e-4, atol=1e-12)
         assert np.array_equal(fs[:, 4].astype(int), g["feat_type"]), ci
+
+
+def test_cpp_pose_optimizer_facade_matches_reference(tmp_path):
+    """svo::PoseOptimizer::run of the C++ facade against the outputs of the REFERENCE's own compiled PoseOptimizer::run
+    (tests/golden/pose_opt_ref_golden.npz): pose, remaining measurements, outlier marks, MAD sigma, iterations."""
+    import helpers
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "svo_pro_universal_b200", "host")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "pose_opt_ref_golden.npz"))
+    for ci, spec in enumerate(helpers.POSE_OPT_CASES):
+        c, prior = helpers.pose_opt_case(spec)
+        cam, N = c["cam"], len(c["px"])
+        fin, fout = tmp_path / f"pin{ci}.bin", tmp_path / f"pout{ci}.bin"
+        with open(fin, "wb") as f:
+            np.array([spec[1], N, spec[2], int(prior is not None)], np.int32).tofile(f)
+            np.array([cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")], np.float64).tofile(f)
+            np.array([cam["width"], cam["height"], cam["distortion"]], np.int32).tofile(f)
+            np.ascontiguousarray(np.stack(c["T_cam_imu"]), np.float64).tofile(f)
+            np.ascontiguousarray(c["T_imu_world_init"], np.float64).tofile(f)
+            np.ascontiguousarray(prior if prior is not None else [1.0, 0, 0, 0], np.float64).tofile(f)
+            for k in ("px", "f", "grad", "xyz_world"):
+                np.ascontiguousarray(c[k], np.float64).tofile(f)
+            for k in ("level", "type", "feat_cam"):
+                np.ascontiguousarray(c[k], np.int32).tofile(f)
+            np.ascontiguousarray(c["has_xyz"], np.uint8).tofile(f)
+        r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "pose_opt_driver"), str(fin), str(fout)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = np.fromfile(fout, np.float64)
+        assert int(out[0]) == int(gold[f"p{ci}_n"]), ci
+        dq, dt = pose_diff(out[1:8], gold[f"p{ci}_T"])
+        assert dq < 1e-4 and dt < 1e-4 and dq < 1e-9 and dt < 1e-9, (ci, dq, dt)
+        np.testing.assert_allclose(out[8:11], gold[f"p{ci}_stats"][:3], rtol=1e-6)
+        assert int(out[11]) == int(gold[f"p{ci}_stats"][3])
+        assert np.array_equal(out[12:12 + N].astype(np.uint8), gold[f"p{ci}_outlier"]), ci
