@@ -219,6 +219,36 @@ def main():
                 "frames_per_s": F / (ms_r * 1e-3), "ms": ms_r, "mean_trials": float(stats["n_trials"].mean()),
                 "mean_matches": float(stats["n_matches"].mean()),
                 "cpu_baseline": {"frames_per_s_single_thread": cpu_r, "kind": "port (oracle; pinned to the reference's compiled reprojector.cpp)"}})
+    # ---- (f4) PoseOptimizer: B frame bundles, ~145 measurements each ----
+    del ref, cur
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    pcs = [synth.make_pose_opt_case(40 + s) for s in range(16)]
+    BP = 16384
+    pidx = np.arange(BP) % 16
+    pft = [capi.make_features(c["px"], c["f"], c["grad"], c["type"], c["level"]) for c in pcs]
+    pbeg = np.concatenate([[0], np.cumsum([len(pft[i]) for i in pidx])]).astype(np.int32)
+    d_pT, d_pbeg = t(np.stack([pcs[i]["T_imu_world_init"] for i in pidx])), t(pbeg)
+    d_pft = t(np.concatenate([pft[i] for i in pidx]).view(np.uint8))
+    d_pxyz, d_phas = t(np.concatenate([pcs[i]["xyz_world"] for i in pidx])), t(np.concatenate([pcs[i]["has_xyz"] for i in pidx]))
+    d_pres = torch.zeros(BP * capi.POSE_OPT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_pout = torch.zeros(int(pbeg[-1]), dtype=torch.uint8, device=dev)
+    pcam, popt = [capi.Camera.from_dict(pcs[0]["cam"])], capi.pose_optimizer_options()
+    ms_p = timed(lambda: capi.pose_optimize(ctx, pcam, np.stack(pcs[0]["T_cam_imu"]), d_pT, d_pbeg, d_pft, None, d_pxyz, d_phas, popt,
+                                            results=d_pres, outlier=d_pout), stream)
+    pres = d_pres.cpu().numpy().view(capi.POSE_OPT_RESULT_DTYPE)
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 3.0:
+        orc.pose_optimize(pcs[reps % 16], orc.pose_opt_options()); reps += 1
+    cpu_p = reps / (time.perf_counter() - t0)
+    n_meas = float(pres["n_meas"].mean())
+    out.append({"path": "f4: PoseOptimizer::run (MAD scale + Gauss-Newton + outlier removal)",
+                "config": f"{BP} frame bundles x {n_meas:.0f} measurements (16 unique, tiled), kUnitPlane, ONE launch",
+                "bundles_per_s": BP / (ms_p * 1e-3), "ms": ms_p, "mean_iterations": float(pres["iters"].mean()),
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_bundle": int(n_meas * (64 + 24 + 1 + 1) + 56 + 328),
+                             "achieved_GBs": (n_meas * 90 + 384) * BP / (ms_p * 1e-3) / 1e9, "peak_GBs": PEAK,
+                             "frac": (n_meas * 90 + 384) * BP / (ms_p * 1e-3) / 1e9 / PEAK,
+                             "note": "compulsory bytes once per bundle; the features are re-read from L1/L2 every iteration (FP64 issue bound)"},
+                "cpu_baseline": {"bundles_per_s_single_thread": cpu_p, "kind": "port (oracle; pinned to the reference's compiled pose_optimizer.cpp)"}})
     for o in out:
         print(json.dumps(o))
 

@@ -92,3 +92,17 @@ for _ in range(REPS):
                                    (np.arange(F + 1) * len(ef)).astype(np.int32), np.tile(ef, F), np.zeros((F, 416), np.uint8),
                                    capi.reprojector_options(max_n_features=120), cur_frame_idx=(np.arange(F) % 8).astype(np.int32))
 print("reproject matches/frame", float(st["n_matches"].mean()), "trials/frame", float(st["n_trials"].mean()))
+del ref, cur
+
+# (f4): pose optimizer, 4736 bundles
+pcs = [synth.make_pose_opt_case(40 + s) for s in range(8)]
+BP = 4736
+pidx = np.arange(BP) % 8
+pft = [capi.make_features(c["px"], c["f"], c["grad"], c["type"], c["level"]) for c in pcs]
+pbeg = np.concatenate([[0], np.cumsum([len(pft[i]) for i in pidx])]).astype(np.int32)
+for _ in range(REPS):
+    pres, _ = capi.pose_optimize(ctx, [capi.Camera.from_dict(pcs[0]["cam"])], np.stack(pcs[0]["T_cam_imu"]),
+                                 np.stack([pcs[i]["T_imu_world_init"] for i in pidx]), pbeg, np.concatenate([pft[i] for i in pidx]), None,
+                                 np.concatenate([pcs[i]["xyz_world"] for i in pidx]), np.concatenate([pcs[i]["has_xyz"] for i in pidx]),
+                                 capi.pose_optimizer_options())
+print("pose optimizer iterations", float(pres["iters"].mean()), "measurements", float(pres["n_meas"].mean()))
