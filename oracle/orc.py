@@ -771,3 +771,109 @@ def pose_optimize(case, opt, which="orc"):
     n = fn(n_cams, fr, N, ft, _i32(np.ascontiguousarray(case["feat_cam"], np.int32)), _f64(xyz), _u8(np.ascontiguousarray(case["has_xyz"], np.uint8)),
            C.byref(opt), _f64(T), _u8(outl), _f64(stats))
     return n, T, outl, stats
+
+
+# ---- f2: edgelet detector / detector classes (restatement = liborc.so, compiled reference = oracle/_ref/libdetect_ref.so) ---------
+_ref_detect = None
+CORNER_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4"), ("angle", "<f4")])
+DETECTOR_FAST, DETECTOR_FAST_GRAD, DETECTOR_GRID_GRAD = 0, 2, 5  # svo::DetectorType
+
+
+def ref_detect_lib():
+    """The reference's own feature_detection.cpp / feature_detection_utils.cpp / fast_neon sources compiled against the shims
+    (oracle/_ref/libdetect_ref.so; None if it was never built)."""
+    global _ref_detect
+    if _ref_detect is None:
+        so = os.path.join(_HERE, "_ref", "libdetect_ref.so")
+        if not os.path.exists(so):
+            return None
+        _ref_detect = C.CDLL(so)
+    return _ref_detect
+
+
+def _detect_fn(name, which):
+    L = lib() if which == "orc" else ref_detect_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libdetect_ref.so not built")
+    fn = getattr(L, ("orc_" if which == "orc" else "ref_") + name)
+    return fn
+
+
+def _pyr_args(pyr, keep):
+    lv = [np.ascontiguousarray(p, np.uint8) for p in pyr]
+    keep.extend(lv)
+    n = len(lv)
+    data = (C.c_void_p * n)(*[p.ctypes.data for p in lv])
+    cols = (C.c_int * n)(*[p.shape[1] for p in lv])
+    rows = (C.c_int * n)(*[p.shape[0] for p in lv])
+    step = (C.c_int * n)(*[p.strides[0] for p in lv])
+    return n, data, cols, rows, step
+
+
+def gaussian_blur3x3(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur3x3(_u8(img), img.shape[1], img.shape[0], img.strides[0], _u8(out))
+    return out
+
+
+def scharr3x3(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    dx = np.empty(img.shape, np.int16)
+    dy = np.empty(img.shape, np.int16)
+    lib().orc_scharr3x3(_u8(img), img.shape[1], img.shape[0], img.strides[0], dx.ctypes.data_as(i16p), dy.ctypes.data_as(i16p))
+    return dx, dy
+
+
+def edgelet_detector_v2(pyr, threshold=100, border=8, cell_size=30, occupancy=None, which="orc"):
+    """feature_detection_utils::edgeletDetector_V2 on a pyramid (list of level images) -> per-cell Corners."""
+    keep = []
+    n, data, cols, rows, step = _pyr_args(pyr, keep)
+    n_cells = (-(-pyr[0].shape[1] // cell_size)) * (-(-pyr[0].shape[0] // cell_size))
+    corners = (Corner * n_cells)()
+    occ = None if occupancy is None else _u8(np.ascontiguousarray(occupancy, np.uint8))
+    _detect_fn("edgelet_detector_v2", which)(n, data, cols, rows, step, int(threshold), int(border), int(cell_size), occ, corners)
+    return np.frombuffer(corners, dtype=CORNER_DT).copy()
+
+
+def fast_detector_pyr(pyr, threshold=10, border=8, min_level=0, max_level=2, cell_size=30, occupancy=None, which="orc"):
+    """feature_detection_utils::fastDetector on a given pyramid -> per-cell Corners."""
+    keep = []
+    n, data, cols, rows, step = _pyr_args(pyr, keep)
+    n_cells = (-(-pyr[0].shape[1] // cell_size)) * (-(-pyr[0].shape[0] // cell_size))
+    corners = (Corner * n_cells)()
+    occ = None if occupancy is None else _u8(np.ascontiguousarray(occupancy, np.uint8))
+    name = "fast_detector_pyr" if which == "orc" else "fast_detector"
+    _detect_fn(name, which)(n, data, cols, rows, step, int(threshold), int(border), int(min_level), int(max_level), int(cell_size),
+                            occ, corners)
+    return np.frombuffer(corners, dtype=CORNER_DT).copy()
+
+
+def angle_at_pixel_histogram(img, x, y, halfpatch=4, which="orc"):
+    img = np.ascontiguousarray(img, np.uint8)
+    fn = _detect_fn("angle_at_pixel_histogram", which)
+    fn.restype = C.c_double
+    return fn(_u8(img), img.shape[1], img.shape[0], img.strides[0], int(x), int(y), int(halfpatch))
+
+
+def angle_histogram_bin(gx, gy):
+    return lib().orc_angle_histogram_bin(int(gx), int(gy))
+
+
+def detect_features(detector_type, pyr, threshold_primary=10.0, threshold_secondary=100.0, border=8, min_level=0, max_level=2,
+                    cell_size=30, occupancy=None, max_n=None, which="orc"):
+    """AbstractDetector::detect of the detector makeDetector builds (DETECTOR_FAST / DETECTOR_FAST_GRAD / DETECTOR_GRID_GRAD) with an
+    empty mask -> dict(px [n,2], score [n], level [n], grad [n,2], type [n])."""
+    keep = []
+    n, data, cols, rows, step = _pyr_args(pyr, keep)
+    n_cells = (-(-pyr[0].shape[1] // cell_size)) * (-(-pyr[0].shape[0] // cell_size))
+    max_n = n_cells if max_n is None else int(max_n)
+    cap = max(2 * n_cells, max_n, 1)
+    px = np.zeros((cap, 2)); sc = np.zeros(cap); lv = np.zeros(cap, np.int32); gr = np.zeros((cap, 2)); ty = np.zeros(cap, np.int32)
+    occ = None if occupancy is None else _u8(np.ascontiguousarray(occupancy, np.uint8))
+    fn = _detect_fn("detect_features", which)
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                   C.c_int, u8p, C.c_int, f64p, f64p, i32p, f64p, i32p]
+    m = fn(int(detector_type), n, data, cols, rows, step, float(threshold_primary), float(threshold_secondary), int(border),
+           int(min_level), int(max_level), int(cell_size), occ, max_n, _f64(px), _f64(sc), _i32(lv), _f64(gr), _i32(ty))
+    return {"px": px[:m].copy(), "score": sc[:m].copy(), "level": lv[:m].copy(), "grad": gr[:m].copy(), "type": ty[:m].copy()}

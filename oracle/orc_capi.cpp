@@ -178,6 +178,79 @@ int orc_fast_detect_features(const uint8_t* img0, int cols, int rows, int n_leve
   return n;
 }
 
+static std::vector<Img> pyrOf(int n_levels, const uint8_t* const* data, const int* cols, const int* rows, const int* step) {
+  std::vector<Img> pyr;
+  for (int l = 0; l < n_levels; ++l) pyr.push_back(Img{data[l], cols[l], rows[l], step[l]});
+  return pyr;
+}
+
+void orc_gaussian_blur3x3(const uint8_t* img, int cols, int rows, int step, uint8_t* out) {
+  std::vector<uint8_t> o;
+  gaussianBlur3x3(Img{img, cols, rows, step}, o);
+  std::memcpy(out, o.data(), o.size());
+}
+
+void orc_scharr3x3(const uint8_t* img, int cols, int rows, int step, int16_t* dx, int16_t* dy) {
+  std::vector<uint8_t> tight(size_t(cols) * rows);
+  for (int y = 0; y < rows; ++y) std::memcpy(&tight[size_t(y) * cols], img + size_t(y) * step, cols);
+  std::vector<int16_t> a, b;
+  scharr3x3(tight.data(), cols, rows, a, b);
+  std::memcpy(dx, a.data(), a.size() * 2);
+  std::memcpy(dy, b.data(), b.size() * 2);
+}
+
+void orc_edgelet_detector_v2(int n_levels, const uint8_t* const* data, const int* cols, const int* rows, const int* step,
+                             int threshold, int border, int cell_size, const uint8_t* occupancy, orc_corner* corners_out) {
+  const int n_cols = int(std::ceil(double(cols[0]) / cell_size));
+  const int n_rows = int(std::ceil(double(rows[0]) / cell_size));
+  std::vector<Corner> corners(size_t(n_cols) * n_rows, Corner{0, 0, 0, float(threshold), 0.0f});
+  std::vector<uint8_t> occ(corners.size(), 0);
+  if (occupancy) occ.assign(occupancy, occupancy + occ.size());
+  edgeletDetectorV2(pyrOf(n_levels, data, cols, rows, step), threshold, border, corners, occ, cell_size, n_cols);
+  for (size_t i = 0; i < corners.size(); ++i)
+    corners_out[i] = orc_corner{corners[i].x, corners[i].y, corners[i].level, corners[i].score, corners[i].angle};
+}
+
+double orc_angle_at_pixel_histogram(const uint8_t* img, int cols, int rows, int step, int x, int y, int halfpatch_size) {
+  return angleAtPixelUsingHistogram(Img{img, cols, rows, step}, x, y, halfpatch_size);
+}
+
+int orc_angle_histogram_bin(int gx, int gy) { return angleHistogramBin(gx, gy); }
+
+void orc_fast_detector_pyr(int n_levels, const uint8_t* const* data, const int* cols, const int* rows, const int* step, int threshold,
+                           int border, int min_level, int max_level, int cell_size, const uint8_t* occupancy, orc_corner* corners_out) {
+  const int n_cols = int(std::ceil(double(cols[0]) / cell_size));
+  const int n_rows = int(std::ceil(double(rows[0]) / cell_size));
+  std::vector<Corner> corners(size_t(n_cols) * n_rows, Corner{0, 0, 0, float(threshold), 0.0f});
+  std::vector<uint8_t> occ(corners.size(), 0);
+  if (occupancy) occ.assign(occupancy, occupancy + occ.size());
+  fastDetector(pyrOf(n_levels, data, cols, rows, step), threshold, border, min_level, max_level, corners, occ, cell_size, n_cols);
+  for (size_t i = 0; i < corners.size(); ++i)
+    corners_out[i] = orc_corner{corners[i].x, corners[i].y, corners[i].level, corners[i].score, corners[i].angle};
+}
+
+int orc_detect_features(int detector_type, int n_levels, const uint8_t* const* data, const int* cols, const int* rows,
+                        const int* step, double threshold_primary, double threshold_secondary, int border, int min_level,
+                        int max_level, int cell_size, const uint8_t* occupancy, int max_n, double* px_out, double* score_out,
+                        int* level_out, double* grad_out, int* type_out) {
+  const int n_cols = int(std::ceil(double(cols[0]) / cell_size));
+  const int n_rows = int(std::ceil(double(rows[0]) / cell_size));
+  std::vector<uint8_t> occ(size_t(n_cols) * n_rows, 0);
+  if (occupancy) occ.assign(occupancy, occupancy + occ.size());
+  DetectedFeatures out;
+  detectFeatures(detector_type, pyrOf(n_levels, data, cols, rows, step), threshold_primary, threshold_secondary, border, min_level,
+                 max_level, cell_size, occ, size_t(max_n), out);
+  const int n = int(out.score.size());
+  for (int i = 0; i < n && i < max_n; ++i) {
+    px_out[2 * i] = out.px[2 * i]; px_out[2 * i + 1] = out.px[2 * i + 1];
+    grad_out[2 * i] = out.grad[2 * i]; grad_out[2 * i + 1] = out.grad[2 * i + 1];
+    score_out[i] = out.score[i];
+    level_out[i] = out.level[i];
+    type_out[i] = out.type[i];
+  }
+  return n;
+}
+
 int orc_sparse_align(int n_cams, const orc_frame* ref, const orc_frame* cur, const orc_align_options* opt, orc_align_result* res) {
   std::vector<AlignFrame> rf, cf;
   for (int i = 0; i < n_cams; ++i) { rf.push_back(alignFrameOf(&ref[i])); cf.push_back(alignFrameOf(&cur[i])); }

@@ -107,6 +107,19 @@ void orc_fast_detector(const uint8_t* img0, int cols, int rows, int n_levels, in
 int orc_fast_detect_features(const uint8_t* img0, int cols, int rows, int n_levels, int pyr_mode, double threshold, int border,
                              int min_level, int max_level, int cell_size, const uint8_t* occupancy, int max_n,
                              double* px_out, double* score_out, int* level_out);
+/* f2: edgelet detector + the detector classes. Pyramid levels are passed in (n_levels pointers / cols / rows / step). */
+void orc_gaussian_blur3x3(const uint8_t* img, int cols, int rows, int step, uint8_t* out);
+void orc_scharr3x3(const uint8_t* img, int cols, int rows, int step, int16_t* dx, int16_t* dy);
+void orc_edgelet_detector_v2(int n_levels, const uint8_t* const* data, const int* cols, const int* rows, const int* step,
+                             int threshold, int border, int cell_size, const uint8_t* occupancy, orc_corner* corners_out);
+double orc_angle_at_pixel_histogram(const uint8_t* img, int cols, int rows, int step, int x, int y, int halfpatch_size);
+int orc_angle_histogram_bin(int gx, int gy);
+void orc_fast_detector_pyr(int n_levels, const uint8_t* const* data, const int* cols, const int* rows, const int* step, int threshold,
+                           int border, int min_level, int max_level, int cell_size, const uint8_t* occupancy, orc_corner* corners_out);
+int orc_detect_features(int detector_type, int n_levels, const uint8_t* const* data, const int* cols, const int* rows,
+                        const int* step, double threshold_primary, double threshold_secondary, int border, int min_level,
+                        int max_level, int cell_size, const uint8_t* occupancy, int max_n, double* px_out, double* score_out,
+                        int* level_out, double* grad_out, int* type_out);
 /* b */
 int orc_sparse_align(int n_cams, const orc_frame* ref, const orc_frame* cur, const orc_align_options* opt, orc_align_result* res);
 /* B independent problems: ref/cur hold B*n_cams frames; n_threads worker threads (one problem per task). */

@@ -238,4 +238,160 @@ inline void fillFeatures(const std::vector<Corner>& corners, const uint8_t* mask
   }
 }
 
+// ---------------------------------------------------------------------------
+// f2. Edgelet detector: edgeletDetector_V2 + the gradient-orientation histogram.
+// OpenCV pieces, restated from OpenCV's documented 8-bit behaviour and PINNED against cv2 4.13 (tests/golden/cv_imgproc_golden.npz):
+//   cv::GaussianBlur(u8, Size(3,3), 0)  = one rounding of the 1-2-1 x 1-2-1 window: (sum + 8) >> 4, BORDER_REFLECT_101
+//   cv::Scharr(u8 -> CV_16S)            = exact 3-10-3 differences, BORDER_REFLECT_101
+inline int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+  return i;
+}
+inline void gaussianBlur3x3(const Img& im, std::vector<uint8_t>& out) {
+  out.resize(size_t(im.cols) * im.rows);
+  for (int y = 0; y < im.rows; ++y) {
+    const uint8_t* ra = im.data + reflect101(y - 1, im.rows) * im.step;
+    const uint8_t* rb = im.data + y * im.step;
+    const uint8_t* rc = im.data + reflect101(y + 1, im.rows) * im.step;
+    for (int x = 0; x < im.cols; ++x) {
+      const int l = reflect101(x - 1, im.cols), r = reflect101(x + 1, im.cols);
+      const int s = (ra[l] + rc[l] + ra[r] + rc[r]) + 2 * (ra[x] + rc[x] + rb[l] + rb[r]) + 4 * rb[x];
+      out[size_t(y) * im.cols + x] = uint8_t((s + 8) >> 4);
+    }
+  }
+}
+inline void scharr3x3(const uint8_t* g, int cols, int rows, std::vector<int16_t>& dx, std::vector<int16_t>& dy) {
+  dx.resize(size_t(cols) * rows); dy.resize(size_t(cols) * rows);
+  for (int y = 0; y < rows; ++y) {
+    const uint8_t* ra = g + size_t(reflect101(y - 1, rows)) * cols;
+    const uint8_t* rb = g + size_t(y) * cols;
+    const uint8_t* rc = g + size_t(reflect101(y + 1, rows)) * cols;
+    for (int x = 0; x < cols; ++x) {
+      const int l = reflect101(x - 1, cols), r = reflect101(x + 1, cols);
+      dx[size_t(y) * cols + x] = int16_t(3 * ((ra[r] - ra[l]) + (rc[r] - rc[l])) + 10 * (rb[r] - rb[l]));
+      dy[size_t(y) * cols + x] = int16_t(3 * ((rc[l] - ra[l]) + (rc[r] - ra[r])) + 10 * (rc[x] - ra[x]));
+    }
+  }
+}
+
+// angle_hist::{angleHistogram, gradientAndMagnitudeAtPixel, smoothOrientationHistogram, getDominantAngle} and
+// getAngleAtPixelUsingHistogram — ref: src/svo_direct/src/feature_detection_utils.cpp:831-839, 945-1009;
+// n_bins = 36 (include/svo/direct/feature_detection_utils.h:168).
+inline int angleHistogramBin(int gx, int gy) {  // bin of a central-difference gradient (gx, gy)
+  const double angle = std::atan2(double(gy), double(gx));
+  size_t bin = size_t(std::round(36 * (angle + M_PI) / (2.0 * M_PI)));
+  return int(bin < 36 ? bin : 0u);
+}
+inline double angleAtPixelUsingHistogram(const Img& im, int px, int py, int halfpatch) {
+  double hist[36];
+  for (double& h : hist) h = 0.0;
+  for (int v = py - halfpatch; v <= py + halfpatch; ++v)
+    for (int u = px - halfpatch; u <= px + halfpatch; ++u) {
+      if (!(v > 0 && v < im.rows - 1 && u > 0 && u < im.cols - 1)) continue;
+      const int gx = int(im.data[v * im.step + u + 1]) - int(im.data[v * im.step + u - 1]);
+      const int gy = int(im.data[(v + 1) * im.step + u]) - int(im.data[(v - 1) * im.step + u]);
+      hist[angleHistogramBin(gx, gy)] += std::sqrt(double(gx) * gx + double(gy) * gy);
+    }
+  // circular 1-2-1 smoothing, in place, each bin reading its un-smoothed neighbours
+  double prev = hist[35];
+  const double first = hist[0];
+  for (int i = 0; i < 36; ++i) {
+    const double here = hist[i];
+    hist[i] = 0.25 * prev + 0.5 * here + 0.25 * (i == 35 ? first : hist[i + 1]);
+    prev = here;
+  }
+  int best = 0;
+  for (int i = 1; i < 36; ++i)
+    if (hist[i] > hist[best]) best = i;
+  return best * 2.0 * M_PI / 36;
+}
+
+// edgeletDetector_V2 — ref: src/svo_direct/src/feature_detection_utils.cpp:313-385. Works on pyramid level 1 only
+// (:324-325) and reports level 0 (`level-1`, :379) with px = 2 * level-1 pixel.
+// Quirk kept: the 8-neighbour test uses `stride = score.step` — a BYTE step — as a float-pointer offset (:352, :363-364), so
+// the "vertical" neighbours it compares are 4 rows away: (x, y+-4) and (x+-1, y+-4). The loops need border >= 4 to stay inside
+// the score map.
+inline void edgeletDetectorV2(const std::vector<Img>& img_pyr, int threshold, int border, std::vector<Corner>& corners,
+                              const std::vector<uint8_t>& occupancy, int cell_size, int n_cols) {
+  const Img& im = img_pyr[1];
+  const int W = im.cols, H = im.rows;
+  std::vector<uint8_t> blur;
+  std::vector<int16_t> gx, gy;
+  gaussianBlur3x3(im, blur);
+  scharr3x3(blur.data(), W, H, gx, gy);
+  std::vector<float> score(size_t(W) * H, 0.0f);
+  for (int y = border; y < H - border; ++y)
+    for (int x = border; x < W - border; ++x) {
+      const int a = gx[size_t(y) * W + x], b = gy[size_t(y) * W + x];
+      const float mag = float(std::sqrt(double(a * a + b * b)));  // std::sqrt(int) is the double overload (:343)
+      score[size_t(y) * W + x] = (mag > threshold) ? mag : 0.0f;
+    }
+  const int vstep = 4 * W;  // see the quirk above
+  for (int y = border; y < H - border; ++y)
+    for (int x = border; x < W - border; ++x) {
+      const size_t k = gridCellIndex(x, y, 2, cell_size, n_cols);
+      if (occupancy.at(k)) continue;
+      const float* c = &score[size_t(y) * W + x];
+      const float s = *c;
+      if (s < threshold) continue;
+      if (c[1] >= s || c[-1] > s) continue;
+      if (c[vstep] >= s || c[-vstep] > s) continue;
+      if (c[vstep + 1] >= s || c[vstep - 1] > s) continue;
+      if (c[-vstep + 1] >= s || c[-vstep - 1] > s) continue;
+      if (s > corners.at(k).score)
+        corners.at(k) = Corner{2 * x, 2 * y, 0, s, float(angleAtPixelUsingHistogram(im, x, y, 4))};
+    }
+}
+
+// AbstractDetector::detect(img_pyr, mask = empty, ...) for the three grid detectors of this path —
+// ref: src/svo_direct/src/feature_detection.cpp:53-74 (FastDetector), :130-151 (GradientDetectorGrid), :154-194 (FastGradDetector).
+// detector_type follows svo::DetectorType (feature_detection_types.h:33-45): 0 kFast, 2 kFastGrad, 5 kGridGrad.
+// fillFeatures turns Corner::angle (float) into the gradient with the float overloads of cos / sin (:101).
+struct DetectedFeatures {
+  std::vector<double> px, grad, score;
+  std::vector<int> level, type;
+};
+inline void appendFeatures(const std::vector<Corner>& corners, int type, double threshold, size_t max_n, DetectedFeatures& out,
+                           std::vector<uint8_t>& occupancy, int cell_size, int n_cols) {
+  std::vector<size_t> keep;
+  for (size_t k = 0; k < corners.size(); ++k)
+    if (corners[k].score > threshold) {
+      keep.push_back(k);
+      occupancy[gridCellIndex(corners[k].x, corners[k].y, 1, cell_size, n_cols)] = 1;
+    }
+  std::sort(keep.begin(), keep.end(), [&](size_t a, size_t b) { return double(corners[a].score) > double(corners[b].score); });
+  const size_t n_new = std::min(max_n, keep.size());
+  for (size_t i = 0; i < n_new; ++i) {
+    const Corner& c = corners[keep[i]];
+    out.px.push_back(c.x); out.px.push_back(c.y);
+    out.grad.push_back(std::cos(c.angle)); out.grad.push_back(std::sin(c.angle));  // float overloads, as the reference
+    out.score.push_back(c.score);
+    out.level.push_back(c.level);
+    out.type.push_back(type);
+  }
+}
+inline void detectFeatures(int detector_type, const std::vector<Img>& img_pyr, double threshold_primary, double threshold_secondary,
+                           int border, int min_level, int max_level, int cell_size, std::vector<uint8_t> occupancy, size_t max_n,
+                           DetectedFeatures& out) {
+  const int n_cols = int(std::ceil(double(img_pyr[0].cols) / cell_size));
+  const int n_rows = int(std::ceil(double(img_pyr[0].rows) / cell_size));
+  const size_t n_cells = size_t(n_cols) * n_rows;
+  occupancy.resize(n_cells, 0);
+  const int kCorner = 7, kEdgelet = 6;  // svo::FeatureType (src/svo_common/include/svo/common/types.h:60-73)
+  if (detector_type == 0 || detector_type == 2) {
+    std::vector<Corner> corners(n_cells, Corner{0, 0, 0, float(threshold_primary), 0.0f});
+    fastDetector(img_pyr, int(threshold_primary), border, size_t(min_level), size_t(max_level), corners, occupancy, cell_size, n_cols);
+    appendFeatures(corners, kCorner, threshold_primary, max_n, out, occupancy, cell_size, n_cols);
+  }
+  if (detector_type == 5 || detector_type == 2) {
+    const long room = detector_type == 2 ? long(max_n) - long(out.score.size()) : long(max_n);
+    if (room > 0) {
+      std::vector<Corner> corners(n_cells, Corner{0, 0, 0, float(threshold_secondary), 0.0f});
+      edgeletDetectorV2(img_pyr, int(threshold_secondary), border, corners, occupancy, cell_size, n_cols);
+      appendFeatures(corners, kEdgelet, threshold_secondary, size_t(room), out, occupancy, cell_size, n_cols);
+    }
+  }
+}
+
 }  // namespace orc

@@ -113,7 +113,13 @@ class Mat {
     step.p[0] = stp ? stp : (size_t)c * elemSize();
   }
   Mat(const Mat& m, const Rect& roi);  // declared only
-  Mat(Size s, int type, const Scalar& fill);  // declared only
+  // Constant-filled image (edgeletDetector_V2's score / angle maps): 8-bit and float single-channel only.
+  Mat(Size s, int type, const Scalar& fill) : Mat() {
+    create(s.height, s.width, type);
+    if (type == CV_8UC1) { for (int r = 0; r < rows; ++r) std::memset(ptr(r), (int)fill.val[0], (size_t)cols); }
+    else if (type == CV_32FC1) { for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) at<float>(r, c) = (float)fill.val[0]; }
+    else std::abort();
+  }
   void create(int r, int c, int type) {
     if (data && r == rows && c == cols && type == this->type() && owner_) return;
     flags = type; dims = 2; rows = r; cols = c;
@@ -152,6 +158,9 @@ class Mat {
   template <typename T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step.p[0]))[c]; }
   void convertTo(Mat& m, int rtype, double alpha = 1, double beta = 0) const;  // declared only
   Mat& operator=(const Scalar& s);                                              // declared only
+  static Mat zeros(Size s, int type);                                           // declared only
+  Mat mul(const Mat& m, double scale = 1) const;                                // declared only
+  Mat t() const;                                                                // declared only
 
  private:
   std::shared_ptr<uchar> owner_;
@@ -175,5 +184,36 @@ int waitKey(int delay = 0);
 void namedWindow(const std::string& name, int flags = 1);
 void split(const Mat& src, std::vector<Mat>& mv);
 void merge(const std::vector<Mat>& mv, Mat& dst);
+Mat operator+(double a, const Mat& b);
+Mat operator*(double a, const Mat& b);
+Mat operator/(const Mat& a, const Mat& b);
+Mat operator==(const Mat& a, double b);
+template <typename T> struct Mat_ : Mat {
+  Mat_(int r, int c) : Mat(r, c, DataType<T>::type) {}
+};
+template <typename T> struct MatCommaInitializer_ {
+  MatCommaInitializer_& operator,(double) { std::abort(); }
+  operator Mat() const { std::abort(); }
+};
+template <typename T> inline MatCommaInitializer_<T> operator<<(const Mat_<T>&, double) { std::abort(); }
+enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4 };
+enum { THRESH_BINARY = 0, THRESH_BINARY_INV = 1 };
+// The two imgproc functions the reference's *edgelet detector* really runs (feature_detection_utils.cpp:331-333) are restated
+// in shim_cv_imgproc.cpp for exactly the argument patterns used there (8-bit 3x3 sigma-0 blur; 8U -> 16S 3x3 Scharr, scale 1,
+// delta 0, BORDER_REFLECT_101) and pinned against the real OpenCV (cv2 4.13) by tests/golden/cv_imgproc_golden.npz; any other
+// argument pattern aborts.
+void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT);
+void Scharr(const Mat& src, Mat& dst, int ddepth, int dx, int dy, double scale = 1, double delta = 0, int borderType = BORDER_DEFAULT);
+// Declared only (other detectors / drawing code; reaching one aborts).
+void Sobel(const Mat& src, Mat& dst, int ddepth, int dx, int dy, int ksize = 3, double scale = 1, double delta = 0, int borderType = BORDER_DEFAULT);
+void filter2D(const Mat& src, Mat& dst, int ddepth, const Mat& kernel, Point anchor = Point(-1, -1), double delta = 0, int borderType = BORDER_DEFAULT);
+void blur(const Mat& src, Mat& dst, Size ksize, Point anchor = Point(-1, -1), int borderType = BORDER_DEFAULT);
+void Canny(const Mat& image, Mat& edges, double threshold1, double threshold2, int apertureSize = 3, bool L2gradient = false);
+void convertScaleAbs(const Mat& src, Mat& dst, double alpha = 1, double beta = 0);
+void addWeighted(const Mat& src1, double alpha, const Mat& src2, double beta, double gamma, Mat& dst, int dtype = -1);
+double threshold(const Mat& src, Mat& dst, double thresh, double maxval, int type);
+int countNonZero(const Mat& src);
+void rectangle(Mat& img, Point2f pt1, Point2f pt2, const Scalar& color, int thickness = 1, int lineType = 8, int shift = 0);
+void circle(Mat& img, Point2f center, int radius, const Scalar& color, int thickness = 1, int lineType = 8, int shift = 0);
 
 }  // namespace cv

@@ -360,6 +360,7 @@ class Matrix<T, R, C, Opt, MR, MC, typename std::enable_if<(R < 0 || C < 0)>::ty
   DynBlockRef<Matrix> middleCols(int j0, int n) { return DynBlockRef<Matrix>(*this, 0, j0, r_, n); }
   DynBlockRef<Matrix> segment(int i0, int n) { return C == 1 ? DynBlockRef<Matrix>(*this, i0, 0, n, 1) : DynBlockRef<Matrix>(*this, 0, i0, 1, n); }
   void setConstant(T v) { for (int i = 0; i < r_ * c_; ++i) data()[i] = v; }
+  void setConstant(int n, T v) { resize(n); setConstant(v); }
   void conservativeResize(int n) { if (C == 1) conservativeResize(n, 1); else conservativeResize(r_, n); }
   void conservativeResize(NoChange_t, int c) { conservativeResize(r_, c); }
   void conservativeResize(int r, NoChange_t) { conservativeResize(r, c_); }
