@@ -128,6 +128,27 @@ int svo_cuda_pyramid_fast_detect(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first
 int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int threshold, int arc_length,
                              int16_t* score_map, uint8_t* nonmax_map, svo_mem mem);
 
+/* ---- (f2) edgelet detector and the FastGrad combination (the reference's default detector, svo_factory.cpp:292-295) ------ */
+/* feature_detection_utils::edgeletDetector_V2 (src/svo_direct/include/svo/direct/feature_detection_utils.h:75-82;
+ * src/svo_direct/src/feature_detection_utils.cpp:313-385) with getAngleAtPixelUsingHistogram (:831-839, 945-1009) for the
+ * winners, i.e. the device part of GradientDetectorGrid::detect (src/svo_direct/src/feature_detection.cpp:130-151).
+ * Works on pyramid level 1 (the pyramid needs >= 2 levels, already built); per-cell result in corners_out [count][n_cells]:
+ * level 0, px = 2 * the level-1 pixel, score = gradient magnitude (float), angle = dominant histogram angle; cells without an
+ * edgelet hold (0,0,0,score=threshold,0). threshold = DetectorOptions::threshold_secondary as the reference's int.
+ * border >= 4 is required: the reference's neighbour test reads 4 rows up and down (it offsets a float pointer by a byte step). */
+int svo_cuda_edgelet_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, int threshold, int border,
+                            int cell_size, const uint8_t* occupancy_in, svo_corner* corners_out, svo_mem mem);
+/* FastGradDetector::detect (feature_detection.h:133-150; feature_detection.cpp:154-194) up to fillFeatures' sort: FAST corners
+ * per cell (opt, as svo_cuda_fast_detect) into corners_out, then edgelets (threshold_secondary) into edgelets_out for the cells
+ * that neither occupancy_in nor a FAST corner occupies; the edgelet stage is skipped for frames whose corners already reach
+ * max_n_features (:176-177). Both outputs are [count][n_cells]. */
+int svo_cuda_fastgrad_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
+                             int threshold_secondary, int max_n_features, const uint8_t* occupancy_in, svo_corner* corners_out,
+                             svo_corner* edgelets_out, svo_mem mem);
+/* Raw stage for parity tests: angle_hist::angleHistogram's bin (feature_detection_utils.cpp:945-962) of every central-difference
+ * gradient (gx, gy) in [-255, 255]^2; bins_out [511][511] int8, row gy + 255, column gx + 255. */
+int svo_cuda_angle_histogram_bins(svo_cuda_ctx* ctx, int8_t* bins_out, svo_mem mem);
+
 /* ---- (b) svo::SparseImgAlign (src/svo_img_align/include/svo/img_align/sparse_img_align.h:30-77,
  *      sparse_img_align_base.h:37-163; run(): src/svo_img_align/src/sparse_img_align.cpp:34-113) ---------- */
 typedef struct {

@@ -216,7 +216,8 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_pyramid_fast_detect", "svo_cuda_fast_level_maps", "svo_cuda_sparse_align", "svo_cuda_align2d", "svo_cuda_align1d",
     "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
-    "svo_cuda_reproject_match", "svo_cuda_pose_optimize",
+    "svo_cuda_reproject_match", "svo_cuda_pose_optimize", "svo_cuda_edgelet_detect", "svo_cuda_fastgrad_detect",
+    "svo_cuda_angle_histogram_bins",
 ]
 
 
@@ -347,6 +348,40 @@ def fast_detect(ctx, pyr, opt, first=0, count=None, occupancy=None, corners_out=
     fn = lib().svo_cuda_pyramid_fast_detect if fused_pyramid else lib().svo_cuda_fast_detect
     ctx.check(fn(ctx._h, pyr._h, first, count, C.byref(opt), po, pc, kind))
     return corners_out
+
+
+def edgelet_detect(ctx, pyr, threshold=100, border=8, cell_size=30, first=0, count=None, occupancy=None, corners_out=None):
+    """edgeletDetector_V2 for frames [first, first+count): per-cell edgelets [count, n_cells] (CORNER_DTYPE)."""
+    count = pyr.n_frames - first if count is None else count
+    n_cells, _, _ = grid_cells(pyr.width, pyr.height, cell_size)
+    if corners_out is None:
+        corners_out = np.zeros((count, n_cells), CORNER_DTYPE)
+    (po, pc), kind = _ptrs(occupancy, corners_out)
+    ctx.check(lib().svo_cuda_edgelet_detect(ctx._h, pyr._h, first, count, int(threshold), int(border), int(cell_size), po, pc, kind))
+    return corners_out
+
+
+def fastgrad_detect(ctx, pyr, opt, threshold_secondary=100, max_n_features=None, first=0, count=None, occupancy=None,
+                    corners_out=None, edgelets_out=None):
+    """FastGradDetector::detect up to fillFeatures' sort: (FAST corners, edgelets), both [count, n_cells] (CORNER_DTYPE)."""
+    count = pyr.n_frames - first if count is None else count
+    n_cells, _, _ = grid_cells(pyr.width, pyr.height, opt.cell_size)
+    max_n_features = n_cells if max_n_features is None else int(max_n_features)
+    if corners_out is None:
+        corners_out = np.zeros((count, n_cells), CORNER_DTYPE)
+    if edgelets_out is None:
+        edgelets_out = np.zeros((count, n_cells), CORNER_DTYPE) if not _is_torch(corners_out) else corners_out.new_zeros(corners_out.shape)
+    (po, pc, pe), kind = _ptrs(occupancy, corners_out, edgelets_out)
+    ctx.check(lib().svo_cuda_fastgrad_detect(ctx._h, pyr._h, first, count, C.byref(opt), int(threshold_secondary), max_n_features,
+                                             po, pc, pe, kind))
+    return corners_out, edgelets_out
+
+
+def angle_histogram_bins(ctx):
+    """Bins of angle_hist::angleHistogram for every gradient (gx, gy) in [-255, 255]^2: int8 [511, 511], row gy + 255."""
+    out = np.zeros((511, 511), np.int8)
+    ctx.check(lib().svo_cuda_angle_histogram_bins(ctx._h, C.c_void_p(out.ctypes.data), MEM_HOST))
+    return out
 
 
 def fast_level_maps(ctx, pyr, frame, level, threshold=10, arc_length=10):

@@ -286,7 +286,7 @@ int launchLevels(svo_cuda_ctx* ctx, const PyrView& v, FastParams& P, int arc, in
 
 int svoPyrBuildLaunch(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count);
 
-static int fastDetectImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
+int svoFastDetectImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
                           const uint8_t* occupancy_in, svo_corner* corners_out, svo_mem mem) {
   if (!ctx || !pyr || !opt || !corners_out || first < 0 || count < 0 || first + count > pyr->n_frames)
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_fast_detect: bad arguments");
@@ -321,7 +321,7 @@ extern "C" {
 
 int svo_cuda_fast_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
                          const uint8_t* occupancy_in, svo_corner* corners_out, svo_mem mem) {
-  return fastDetectImpl(ctx, pyr, first, count, opt, occupancy_in, corners_out, mem);
+  return svoFastDetectImpl(ctx, pyr, first, count, opt, occupancy_in, corners_out, mem);
 }
 
 int svo_cuda_pyramid_fast_detect(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
@@ -330,7 +330,7 @@ int svo_cuda_pyramid_fast_detect(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_pyramid_fast_detect: bad arguments");
   const int rc = svoPyrBuildLaunch(ctx, pyr, first, count);
   if (rc != SVO_OK) return rc;
-  return fastDetectImpl(ctx, pyr, first, count, opt, occupancy_in, corners_out, mem);
+  return svoFastDetectImpl(ctx, pyr, first, count, opt, occupancy_in, corners_out, mem);
 }
 
 int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int threshold, int arc_length,

@@ -17,6 +17,11 @@ reproject_ref_golden.npz outputs of the REFERENCE's own reprojector.cpp (getCand
                       matchCandidate; compiled into libfrontend_ref.so) on the cases of tests/helpers.py:REPROJECT_CASES: pins row f1.
 pose_opt_ref_golden.npz outputs of the REFERENCE's own PoseOptimizer::run (pose_optimizer.cpp compiled into libfrontend_ref.so) on
                       tests/helpers.py:POSE_OPT_CASES: pins row f4.
+detect_ref_golden.npz outputs of the REFERENCE's own detectors (feature_detection.cpp / feature_detection_utils.cpp / fast_neon compiled into
+                      oracle/_ref/libdetect_ref.so; its GaussianBlur / Scharr calls resolve to the cv2-pinned restatements of
+                      oracle/shim/shim_cv_imgproc.cpp) on tests/helpers.py:DETECT_CASES: pins rows a5, a6 and f2.
+cv_imgproc_golden.npz outputs of the REAL OpenCV (python module cv2, version stored inside) for GaussianBlur(3x3, sigma 0) and
+                      Scharr(8U -> 16S) on seeded images: pins the two imgproc restatements (oracle + shim) the edgelet detector uses.
 klt_ref_golden.npz    outputs of the REFERENCE's own alignPyr2D (libdirect_ref.so) on the cases of tests/test_klt_cpu.py.
 Usage: python tests/golden/make_golden.py
 """
@@ -142,11 +147,38 @@ def reproject_golden():
     print("reproject_ref_golden.npz", os.path.getsize(os.path.join(HERE, "reproject_ref_golden.npz")))
 
 
+def detect_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_detect_lib() is not None, "oracle/_ref/libdetect_ref.so missing: run make -C oracle"
+    np.savez_compressed(os.path.join(HERE, "detect_ref_golden.npz"), **helpers.detect_outputs(orc, "ref"))
+    print("wrote detect_ref_golden.npz")
+
+
+def cv_imgproc_golden():
+    import cv2
+    out = {"cv2_version": np.array(cv2.__version__)}
+    rng = np.random.default_rng(77)
+    shapes = [(120, 188), (60, 94), (30, 47), (17, 33), (5, 7), (3, 3), (1, 9), (9, 1), (2, 2)]
+    out["shapes"] = np.array(shapes, np.int32)
+    for i, (h, w) in enumerate(shapes):
+        img = rng.integers(0, 256, (h, w)).astype(np.uint8) if i % 2 == 0 else synth.make_image(i, w, h, n_rect=max(4, w * h // 200))
+        g = cv2.GaussianBlur(img, (3, 3), 0)
+        out[f"img_{i}"] = img
+        out[f"blur_{i}"] = g
+        out[f"dx_{i}"] = cv2.Scharr(g, cv2.CV_16S, 1, 0, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+        out[f"dy_{i}"] = cv2.Scharr(g, cv2.CV_16S, 0, 1, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+    np.savez_compressed(os.path.join(HERE, "cv_imgproc_golden.npz"), **out)
+    print("wrote cv_imgproc_golden.npz (cv2 " + cv2.__version__ + ")")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:  # e.g. `make_golden.py reproject`: regenerate one fixture
         for name in sys.argv[1:]:
             globals()[name + "_golden"]()
         sys.exit(0)
+    detect_golden()
+    cv_imgproc_golden()
     pose_opt_golden()
     reproject_golden()
     klt_golden()

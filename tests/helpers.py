@@ -314,3 +314,67 @@ def pose_opt_outputs(orc, which):
         n, T, outl, stats = orc.pose_optimize(c, orc.pose_opt_options(err_type=spec[2], prior_q=prior, prior_lambda=0.5), which)
         out[f"p{ci}_n"], out[f"p{ci}_T"], out[f"p{ci}_outlier"], out[f"p{ci}_stats"] = np.array(n), T, outl, stats[:4]
     return out
+
+
+# ---- f2: edgelet detector / detector classes (oracle/_ref/libdetect_ref.so) ----------------------------------------------------------
+# (seed, width, height, n_levels, kind, threshold_secondary, border, with_occupancy)
+DETECT_CASES = [(11, 752, 480, 5, "rect", 100, 8, False), (12, 752, 480, 5, "rect", 30, 8, True), (13, 640, 480, 4, "rect", 100, 4, False),
+                (14, 500, 300, 3, "stripes", 60, 8, False), (15, 752, 480, 5, "noise", 100, 8, True), (16, 376, 240, 2, "rect", 250, 10, False),
+                (17, 100, 75, 2, "rect", 40, 8, False), (18, 44, 40, 2, "noise", 20, 8, False)]
+CORNER_FIELDS = ("x", "y", "level", "score", "angle")
+
+
+def detect_image(seed, w, h, kind):
+    """Level-0 test image: piece-wise constant rectangles, 8-periodic stripes with many equal gradient scores, or noise."""
+    rng = np.random.default_rng(seed)
+    if kind == "rect":
+        return synth.make_image(seed, w, h, n_rect=max(8, w * h // 400))
+    if kind == "stripes":
+        yy, xx = np.mgrid[0:h, 0:w]
+        return (((xx // 8 + yy // 16) % 2) * 150 + 40 + rng.integers(0, 2, (h, w))).astype(np.uint8)
+    return rng.integers(0, 256, (h, w)).astype(np.uint8)
+
+
+def detect_case_inputs(orc, case):
+    seed, w, h, n_levels, kind, thr2, border, with_occ = case
+    img = detect_image(seed, w, h, kind)
+    pyr = orc.create_img_pyramid(img, n_levels)
+    n_cells = (-(-w // 30)) * (-(-h // 30))
+    occ = (np.random.default_rng(seed + 100).random(n_cells) < 0.3).astype(np.uint8) if with_occ else None
+    return img, pyr, occ
+
+
+def detect_outputs(orc, which):
+    """Per-cell edgelets / FAST corners and the three detectors' feature lists for DETECT_CASES, from the oracle restatement
+    (which="orc") or the reference's own compiled detectors (which="ref")."""
+    out = {}
+    for i, case in enumerate(DETECT_CASES):
+        seed, w, h, n_levels, kind, thr2, border, with_occ = case
+        img, pyr, occ = detect_case_inputs(orc, case)
+        e = orc.edgelet_detector_v2(pyr, thr2, border, 30, occ, which=which)
+        f = orc.fast_detector_pyr(pyr, 10, border, 0, min(2, n_levels - 1), 30, occ, which=which)
+        for k in CORNER_FIELDS:
+            out[f"edgelet_{i}_{k}"] = e[k]
+            out[f"fast_{i}_{k}"] = f[k]
+        for t, max_n in ((orc.DETECTOR_FAST, None), (orc.DETECTOR_FAST_GRAD, None), (orc.DETECTOR_GRID_GRAD, None),
+                         (orc.DETECTOR_FAST_GRAD, 60)):
+            d = orc.detect_features(t, pyr, 10.0, float(thr2), border, 0, min(2, n_levels - 1), 30, occ, max_n, which=which)
+            for k, v in d.items():
+                out[f"det_{i}_{t}_{max_n}_{k}"] = v
+    g = np.random.default_rng(5)
+    img = detect_image(21, 376, 240, "rect")
+    pts = np.stack([g.integers(0, 376, 200), g.integers(0, 240, 200)], 1)
+    pts[:8] = [[0, 0], [375, 239], [1, 1], [3, 236], [374, 5], [4, 4], [0, 120], [200, 239]]
+    out["hist_pts"] = pts
+    out["hist_angle"] = np.array([orc.angle_at_pixel_histogram(img, x, y, 4, which=which) for x, y in pts])
+    return out
+
+
+def assert_features_equal(a, b, tag=""):
+    """Feature lists of AbstractDetector::detect: fillFeatures sorts by score with std::sort (unstable), so features with equal
+    scores are compared as sets."""
+    assert len(a["score"]) == len(b["score"]), tag
+    assert np.array_equal(a["score"], b["score"]) and np.array_equal(a["type"], b["type"]), tag
+    ka = sorted(zip(a["score"], a["px"][:, 0], a["px"][:, 1], a["level"], a["grad"][:, 0], a["grad"][:, 1]))
+    kb = sorted(zip(b["score"], b["px"][:, 0], b["px"][:, 1], b["level"], b["grad"][:, 0], b["grad"][:, 1]))
+    assert ka == kb, tag

@@ -59,7 +59,31 @@ def main():
                              "peak_GBs": PEAK, "frac": bytes_frame * B / (ms_all * 1e-3) / 1e9 / PEAK,
                              "pyramid_only_frac": (360960 + 119850) * B / (ms_pyr * 1e-3) / 1e9 / PEAK},
                 "cpu_baseline": {"frames_per_s_single_thread": cpu_fps_1t, "kind": "port (oracle; FAST rows pinned to the reference's own code)"}})
-    del pyr, imgs, corners
+    # ---- (f2) edgelet detector + FastGrad (the reference's default detector) on the same 1024 frames ----
+    pyr.build()
+    edgelets = torch.zeros(B * 416 * 20, dtype=torch.uint8, device=dev)
+    ms_edge = timed(lambda: capi.edgelet_detect(ctx, pyr, 100, 8, 30, corners_out=edgelets), stream)
+    ms_fg = timed(lambda: capi.fastgrad_detect(ctx, pyr, opt, 100, corners_out=corners, edgelets_out=edgelets), stream)
+    ne = int((edgelets.cpu().numpy().view(capi.CORNER_DTYPE)["score"] > 100).sum())
+    pyrs = [orc.create_img_pyramid(uniq[i], 3) for i in range(16)]
+    t0 = time.perf_counter(); n_cpu = 0
+    while time.perf_counter() - t0 < 4.0:
+        orc.edgelet_detector_v2(pyrs[n_cpu % 16]); n_cpu += 1
+    cpu_edge = n_cpu / (time.perf_counter() - t0)
+    t0 = time.perf_counter(); n_cpu = 0
+    while time.perf_counter() - t0 < 4.0:
+        orc.detect_features(orc.DETECTOR_FAST_GRAD, pyrs[n_cpu % 16]); n_cpu += 1
+    cpu_fg = n_cpu / (time.perf_counter() - t0)
+    eb = 92160 + 416 * 20  # read level 1 (pitch 384 x 240) + write the per-cell edgelets
+    out.append({"path": "f2: edgelet detector (Gaussian 3x3 + Scharr + neighbour test + cell argmax + angle histogram) and FastGrad",
+                "config": "1024 synthetic 752x480 frames (level 1 = 376x240), threshold 100, border 8, cell 30",
+                "frames_per_s": {"edgelets": B / (ms_edge * 1e-3), "fastgrad": B / (ms_fg * 1e-3)}, "ms": {"edgelets": ms_edge, "fastgrad": ms_fg},
+                "edgelets_per_frame_after_fast": ne / B,
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": eb, "achieved_GBs": eb * B / (ms_edge * 1e-3) / 1e9, "peak_GBs": PEAK,
+                             "frac": eb * B / (ms_edge * 1e-3) / 1e9 / PEAK, "note": "level 1 is 1/4 of the frame: issue bound, see DESIGN.md"},
+                "cpu_baseline": {"edgelet_frames_per_s_single_thread": cpu_edge, "fastgrad_frames_per_s_single_thread": cpu_fg,
+                                 "kind": "port (oracle; identical to the reference's own compiled detectors)"}})
+    del pyr, imgs, corners, edgelets
 
     # ---- (c) BASELINE configs[2]: align2D / align1D via findMatchDirect, 2000 features x 256 pairs; epipolar search ----
     NP, NF, NU = 256, 2000, 8

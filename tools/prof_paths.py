@@ -33,6 +33,10 @@ for _ in range(REPS):
     capi.fast_detect(ctx, cur, capi.detector_options(), fused_pyramid=True)
 for _ in range(REPS):
     capi.fast_detect(ctx, cur, capi.detector_options())
+for _ in range(REPS):  # (f2): edgelet detector alone, then FastGrad (FAST + merge + edgelets)
+    capi.edgelet_detect(ctx, cur, 100, 8, 30)
+for _ in range(REPS):
+    capi.fastgrad_detect(ctx, cur, capi.detector_options(), 100)
 del cur
 
 # (c): matcher paths
