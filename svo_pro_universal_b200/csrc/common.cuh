@@ -26,6 +26,7 @@ struct svo_cuda_ctx {
   cudaStream_t stream = nullptr;
   long long launches = 0;
   int sm_count = 148;
+  int8_t* angle_bins = nullptr;  // 511 x 511 orientation-histogram bins of every u8 central-difference gradient (edgelet.cu), built on first use
   std::string last_error;
 };
 

@@ -85,6 +85,7 @@ int svo_cuda_ctx_destroy(svo_cuda_ctx* ctx) {
   if (!ctx) return SVO_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->angle_bins) cudaFree(ctx->angle_bins);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return SVO_OK;

@@ -13,10 +13,13 @@
 // Scores exist on [border, cols-border) x [border, rows-border) and are 0 elsewhere; border >= 4 keeps the reference inside
 // its score map and is required here (it also means no BORDER_REFLECT_101 pixel is ever read).
 //
-// Kernel layout: one CTA per 96x48 tile of the level-1 image of one frame. The u8 tile with a 3 (x) / 6 (y) pixel halo is staged
-// in shared memory with aligned 32-bit loads, blurred into a second u8 tile (halo 2 / 5), turned into a float score tile
-// (halo 1 / 4; the float is the reference's float(std::sqrt(double(int)))), and the survivors of the neighbour test go to a 64-bit
+// Kernel layout: one CTA per 96x48 tile of the level-1 image of one frame. The u8 tile with a 4 (x) / 6 (y) pixel halo is staged
+// in shared memory with aligned 32-bit loads, blurred into a second u8 tile (y halo 5), turned into a float score tile
+// (y halo 4; the float is the reference's float(std::sqrt(double(int)))), and the survivors of the neighbour test go to a 64-bit
 // atomicMax per grid cell (score bits << 32 | ~raster order: strict `>` keeps the first of equal scores in raster order).
+// Blur and Scharr run on 2 x 4 pixels per thread in 16-bit SIMD lanes of ordinary 32-bit integer instructions (byte-permute to
+// split a word into even / odd pixels, biased lanes so no borrow crosses a lane), and the score tile holds the squared magnitude
+// as an integer (see suppressedSlow) so that the float square root is taken for the few survivors only.
 // A second kernel, one warp per cell, builds the 9x9 orientation histogram of each winner: lanes evaluate atan2 / sqrt for the
 // 81 pixels, the per-bin sums are then formed in the reference's raster order (lane b walks the 81 terms of bin b), smoothed
 // and arg-maxed.
@@ -25,16 +28,18 @@
 namespace {
 
 constexpr int kETW = 96, kETH = 48;
-constexpr int kIX = 4, kIY = 6;                 // staged image halo (x halo 3, rounded up to a word)
-constexpr int kIPitch = kETW + 2 * kIX;         // 104 bytes
-constexpr int kIRows = kETH + 2 * kIY;          // 60
-constexpr int kBX = 2, kBY = 5;                 // blur halo
-constexpr int kBPitch = kETW + 2 * kBX + 4;     // 104 (100 used)
-constexpr int kBRows = kETH + 2 * kBY;          // 58
-constexpr int kSX = 1, kSY = 4;                 // score halo
-constexpr int kSPitchE = kETW + 2 * kSX + 1;    // 99 floats (odd pitch: the +-4-row reads of a warp hit different banks)
-constexpr int kSRowsE = kETH + 2 * kSY;         // 56
+// Shared-memory tiles. Image and blur rows are 32 words = 128 bytes starting at the 16-byte aligned pixel x0 - 16 (word w covers
+// x0 - 16 + 4 w ... + 3), so rows are staged with 16-byte cp.async; rows: image y0 - 6 ..., blur y0 - 5 ..., score y0 - 4 ...
+// Blur is computed for words 2 .. 29, scores for words 3 .. 28 (pixels x0 - 4 .. x0 + 99; score column c = pixel x0 - 4 + c).
+constexpr int kPitchW = 32;
+constexpr int kBlurW0 = 2, kBlurWords = 28;
+constexpr int kScoreW0 = 3, kWords = 26;
+constexpr int kIRows = kETH + 12;               // 60 image rows
+constexpr int kBRows = kETH + 10;               // 58 blur rows
+constexpr int kSRowsE = kETH + 8;               // 56 score rows
+constexpr int kSPitchE = 4 * kWords;            // 104 ints
 constexpr int kThreadsE = 256;
+constexpr int kExactBelow = 1 << 22;            // squared magnitudes below this map to distinct floats (see suppressedSlow)
 
 inline unsigned divMagicE(int d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned)d + 1ull); }
 SVO_D int divFastE(int x, unsigned magic) { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
@@ -49,15 +54,62 @@ struct EdgeletParams {
 // float(std::sqrt(double(n))) for 0 <= n < 2^31. Below 2^24 the int -> float conversion is exact and the correctly rounded float
 // square root equals the double square root rounded to float (sqrt of an integer < 2^24 is never within double precision of a
 // float midpoint unless it is an integer); above, take the double path.
-SVO_D float sqrtIntAsFloat(int n) {
+__device__ __noinline__ float sqrtIntAsFloat(int n) {  // out of line: rare (survivors of the neighbour test, huge gradients)
   if (n < (1 << 24)) return __fsqrt_rn((float)n);
   return (float)sqrt((double)n);
 }
 
+// The score tile holds the SQUARED gradient magnitude n = dx^2 + dy^2 (0 = no score) instead of the reference's float
+// mag(n) = float(sqrt(n)). mag is monotone, strictly so below 2^22 (sqrt(n+1) - sqrt(n) > one float ulp of sqrt(n) there); above,
+// up to 5 consecutive integers collapse onto one float (n < 2^25.1: ulp <= 2^-11, sqrt(b) - sqrt(a) < ulp needs b - a <= 5).
+// Hence every comparison of the reference is decided by the integers except in a window of 8 around equality at n >= 2^22,
+// where the floats are formed and compared — out of line: the straight-line code of the common path must stay small (a version
+// with the float path inlined at every comparison was instruction-fetch bound and 5x slower), and rare (a version that took
+// the float path for every n >= 2^22 spent a quarter of its instructions there on sharp synthetic edges).
+// Only the survivors of the neighbour test need their float score (arg-max key, output).
+constexpr int kCollapse = 8;
+// ge / gt = the largest neighbour compared with >= / > (the test "any neighbour's mag >= mag(s)" is the test on the largest one)
+__device__ __noinline__ bool suppressedSlow(int ge, int gt, int s) {
+  const float fs = sqrtIntAsFloat(s);
+  return sqrtIntAsFloat(ge) >= fs || sqrtIntAsFloat(gt) > fs;
+}
+__device__ __noinline__ int scoreSlow(int n, int thr) { return sqrtIntAsFloat(n) > (float)thr ? n : 0; }
+// High word of the per-cell arg-max key: ordered like mag(n) and equal exactly when the floats are equal. Below 2^22 that is n
+// itself (the float is formed once per cell by the decode kernel); from 2^22 on it is the bit pattern of the float, which is
+// >= 0x45000000 (2048.0f) and so stays above every small key.
+__device__ __noinline__ unsigned scoreKeySlow(int n) { return __float_as_uint(sqrtIntAsFloat(n)); }
+SVO_D unsigned scoreKey(int n) { return n < kExactBelow ? (unsigned)n : scoreKeySlow(n); }
+SVO_D float scoreOfKey(unsigned k) { return k < (unsigned)kExactBelow ? __fsqrt_rn((float)k) : __uint_as_float(k); }
+
+// Four neighbouring pixels x .. x+3 of one row as 16-bit lanes: "even" registers hold (x, x+2), "odd" ones (x+1, x+3).
+//   le = (x-1, x+1), ce = (x, x+2), co = (x+1, x+3), ro = (x+2, x+4)
+struct Lanes { unsigned le, ce, co, ro; };
+SVO_D Lanes splitRow(const unsigned* r) {  // r points at the word of x .. x+3; r[-1] and r[1] are staged too
+  const unsigned w0 = r[-1], w1 = r[0], w2 = r[1];
+  const unsigned l = __byte_perm(w0, w1, 0x6543);  // bytes x-1, x, x+1, x+2
+  const unsigned rr = __byte_perm(w1, w2, 0x4321); // bytes x+1, x+2, x+3, x+4
+  Lanes o;
+  o.le = l & 0x00FF00FFu;
+  o.ce = w1 & 0x00FF00FFu;
+  o.co = __byte_perm(w1, 0u, 0x4341);
+  o.ro = __byte_perm(rr, 0u, 0x4341);
+  return o;
+}
+
+// squared magnitude of one pixel from its biased Scharr responses (dx + 4096, dy + 4096); 0 unless mag > threshold
+SVO_D int edgeletScore(unsigned bdx, unsigned bdy, int thr, int thr2) {
+  const int dx = (int)bdx - 4096, dy = (int)bdy - 4096;
+  const int n = dx * dx + dy * dy;
+  if (n <= thr2) return 0;  // mag(thr^2) = thr exactly, so n <= thr^2 means mag <= threshold
+  // thresholds >= 2048 only: within the collapse window above thr^2 the float comparison decides
+  if (n >= kExactBelow && n <= thr2 + kCollapse) return scoreSlow(n, thr);
+  return n;
+}
+
 __global__ void __launch_bounds__(kThreadsE) edgelet_score_kernel(PyrView v, EdgeletParams P) {
-  __shared__ __align__(16) uint8_t s_img[kIRows * kIPitch];
-  __shared__ __align__(16) uint8_t s_blur[kBRows * kBPitch];
-  __shared__ float s_score[kSRowsE * kSPitchE];
+  __shared__ __align__(16) unsigned s_img[kIRows * kPitchW];
+  __shared__ __align__(16) unsigned s_blur[kBRows * kPitchW];
+  __shared__ __align__(16) int s_score[kSRowsE * kSPitchE];
   const int tid = threadIdx.x;
   const int ty = divFastE(blockIdx.x, P.tiles_x_magic), tx = blockIdx.x - ty * P.tiles_x;
   const int cols = v.cols[1], rows = v.rows[1], pitch = v.pitch[1];
@@ -65,73 +117,122 @@ __global__ void __launch_bounds__(kThreadsE) edgelet_score_kernel(PyrView v, Edg
   const uint8_t* img = v.level(P.first + frame_local, 1);
   const int x0 = tx * kETW, y0 = ty * kETH;
 
-  // stage: words [x0 - 4, x0 + 100) of rows [y0 - 6, y0 + 54), rows clamped, words outside the row read as 0 (never used:
-  // scores exist only `border` >= 4 pixels inside the image)
-  for (int i = tid; i < kIRows * (kIPitch / 4); i += kThreadsE) {
-    const int r = i / (kIPitch / 4), w = i - r * (kIPitch / 4);
-    const int gy = min(max(y0 - kIY + r, 0), rows - 1), gx = x0 - kIX + 4 * w;
-    unsigned val = 0;
-    if (gx >= 0 && gx < pitch) val = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)gy * pitch + gx));
-    reinterpret_cast<unsigned*>(s_img)[i] = val;
+  // stage 60 rows x 128 bytes with 16-byte cp.async (x0 - 16 and the row pitch are multiples of 16); rows are clamped, chunks
+  // outside the row are zero-filled (src-size 0) — never used for a score: scores exist only `border` >= 4 pixels inside the image
+  for (int i = tid; i < kIRows * (kPitchW / 4); i += kThreadsE) {
+    const int r = i >> 3, c = i & 7;
+    const int gy = min(max(y0 - 6 + r, 0), rows - 1), gx = x0 - 16 + 16 * c;
+    const bool in = gx >= 0 && gx < pitch;
+    const uint8_t* src = img + (size_t)gy * pitch + (in ? gx : 0);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_img[r * kPitchW + 4 * c]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  // blur tile: pixel (bx, by) of the blur tile is image pixel (x0 - 2 + bx, y0 - 5 + by) = s_img[(by + 1) * pitch + bx + 2]
-  for (int i = tid; i < kBRows * (kETW + 2 * kBX); i += kThreadsE) {
-    const int by = i / (kETW + 2 * kBX), bx = i - by * (kETW + 2 * kBX);
-    const uint8_t* p = &s_img[(by + 1) * kIPitch + bx + 2];
-    const int sum = (p[-kIPitch - 1] + p[-kIPitch + 1] + p[kIPitch - 1] + p[kIPitch + 1]) +
-                    2 * (p[-kIPitch] + p[kIPitch] + p[-1] + p[1]) + 4 * p[0];
-    s_blur[by * kBPitch + bx] = (uint8_t)((sum + 8) >> 4);
-  }
-  __syncthreads();
-
-  // score tile: pixel (sx, sy) is image pixel (x0 - 1 + sx, y0 - 4 + sy) = s_blur[(sy + 1) * pitch + sx + 1]
-  const int thr = P.threshold;
-  const long long thr2 = (long long)thr * thr;
-  for (int i = tid; i < kSRowsE * (kETW + 2 * kSX); i += kThreadsE) {
-    const int sy = i / (kETW + 2 * kSX), sx = i - sy * (kETW + 2 * kSX);
-    const int gx = x0 - kSX + sx, gy = y0 - kSY + sy;
-    float sc = 0.0f;
-    if (gx >= P.border && gy >= P.border && gx < cols - P.border && gy < rows - P.border) {
-      const uint8_t* p = &s_blur[(sy + 1) * kBPitch + sx + 1];
-      const int a = p[-kBPitch - 1], b = p[-kBPitch], c = p[-kBPitch + 1];
-      const int d = p[-1], e = p[1];
-      const int f = p[kBPitch - 1], g = p[kBPitch], h = p[kBPitch + 1];
-      const int dx = 3 * ((c - a) + (h - f)) + 10 * (e - d);
-      const int dy = 3 * ((f - a) + (h - c)) + 10 * (g - b);
-      const int n = dx * dx + dy * dy;
-      if ((long long)n > thr2) {  // necessary for mag > threshold; the float comparison below is the reference's
-        const float mag = sqrtIntAsFloat(n);
-        if (mag > (float)thr) sc = mag;
-      }
+  // blur: an item is (row pair, word) = 2 x 4 pixels from 4 image rows. Horizontal 1-2-1 sums in 16-bit lanes (<= 1020), vertical
+  // 1-2-1 (<= 4080), + 8, >> 4.
+  // (a warp owns a row pair, lane = word: 28 of 32 lanes busy, no two lanes of a warp on one shared-memory bank)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int rp = warp; rp < kBRows / 2; rp += kThreadsE / 32) {
+    if (lane >= kBlurWords) continue;
+    const int w = lane + kBlurW0;
+    const unsigned* r = &s_img[(2 * rp) * kPitchW + w];  // blur row b reads image rows b, b+1, b+2
+    unsigned he[4], ho[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Lanes a = splitRow(r + j * kPitchW);
+      he[j] = a.le + 2u * a.ce + a.co;
+      ho[j] = a.ce + 2u * a.co + a.ro;
     }
-    s_score[sy * kSPitchE + sx] = sc;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const unsigned be = ((he[j] + 2u * he[j + 1] + he[j + 2] + 0x00080008u) >> 4) & 0x00FF00FFu;
+      const unsigned bo = ((ho[j] + 2u * ho[j + 1] + ho[j + 2] + 0x00080008u) >> 4) & 0x00FF00FFu;
+      s_blur[(2 * rp + j) * kPitchW + w] = __byte_perm(be, bo, 0x6240);
+    }
   }
   __syncthreads();
 
-  // neighbour test + cell arg-max
-  for (int i = tid; i < kETH * kETW; i += kThreadsE) {
-    const int r = i / kETW, c = i - r * kETW;
-    const float* q = &s_score[(r + kSY) * kSPitchE + c + kSX];
-    const float s = q[0];
-    if (s == 0.0f) continue;  // 0 = below the threshold, outside the scored region or outside the image
-    if (q[1] >= s || q[-1] > s) continue;
-    if (q[4 * kSPitchE] >= s || q[-4 * kSPitchE] > s) continue;
-    if (q[4 * kSPitchE + 1] >= s || q[4 * kSPitchE - 1] > s) continue;
-    if (q[-4 * kSPitchE + 1] >= s || q[-4 * kSPitchE - 1] > s) continue;
-    const int gx = x0 + c, gy = y0 + r;
-    const int k = divFastE(2 * gy, P.cell_magic) * P.n_cols + divFastE(2 * gx, P.cell_magic);
-    if (P.occupancy && P.occupancy[(size_t)frame_local * P.n_cells + k]) continue;
-    const unsigned order = ((unsigned)gy << 14) | (unsigned)gx;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - order);
-    atomicMax(&P.keys[(size_t)frame_local * P.n_cells + k], key);
+  // score: an item is (row pair, word) = 2 x 4 pixels from 4 blur rows. Scharr in biased 16-bit lanes:
+  //   D = b(x+1) - b(x-1) + 256, H = 3 b(x-1) + 10 b(x) + 3 b(x+1);  dx + 4096 = 3 D(y-1) + 10 D(y) + 3 D(y+1),
+  //   dy + 4096 = H(y+1) - H(y-1) + 4096.
+  const int thr = P.threshold, thr2 = thr * thr;
+  for (int rp = warp; rp < kSRowsE / 2; rp += kThreadsE / 32) {
+    if (lane >= kWords) continue;
+    const int wi = lane;
+    const unsigned* r = &s_blur[(2 * rp) * kPitchW + wi + kScoreW0];  // score row s reads blur rows s, s+1, s+2
+    unsigned de[4], dod[4], he[4], ho[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Lanes a = splitRow(r + j * kPitchW);
+      de[j] = a.co + 0x01000100u - a.le;
+      dod[j] = a.ro + 0x01000100u - a.ce;
+      he[j] = 3u * (a.le + a.co) + 10u * a.ce;
+      ho[j] = 3u * (a.ce + a.ro) + 10u * a.co;
+    }
+    const int gx = x0 - 4 + 4 * wi;
+    const int lo = P.border - gx, hi = cols - P.border - gx;  // pixel k of the word is scored iff lo <= k < hi
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int gy = y0 - 4 + 2 * rp + j;
+      int4 sc = make_int4(0, 0, 0, 0);
+      if (gy >= P.border && gy < rows - P.border && hi > 0 && lo < 4) {
+        const unsigned dxe = 3u * (de[j] + de[j + 2]) + 10u * de[j + 1];
+        const unsigned dxo = 3u * (dod[j] + dod[j + 2]) + 10u * dod[j + 1];
+        const unsigned dye = he[j + 2] + 0x10001000u - he[j];
+        const unsigned dyo = ho[j + 2] + 0x10001000u - ho[j];
+        sc.x = edgeletScore(dxe & 0xFFFFu, dye & 0xFFFFu, thr, thr2);
+        sc.y = edgeletScore(dxo & 0xFFFFu, dyo & 0xFFFFu, thr, thr2);
+        sc.z = edgeletScore(dxe >> 16, dye >> 16, thr, thr2);
+        sc.w = edgeletScore(dxo >> 16, dyo >> 16, thr, thr2);
+        if (lo > 0 || hi < 4) {  // the word straddles the border of the scored region
+          if (!(0 >= lo && 0 < hi)) sc.x = 0;
+          if (!(1 >= lo && 1 < hi)) sc.y = 0;
+          if (!(2 >= lo && 2 < hi)) sc.z = 0;
+          if (!(3 >= lo && 3 < hi)) sc.w = 0;
+        }
+      }
+      *reinterpret_cast<int4*>(&s_score[(2 * rp + j) * kSPitchE + 4 * wi]) = sc;
+    }
+  }
+  __syncthreads();
+
+  // neighbour test + cell arg-max: an item is 4 interior pixels; their 3 x 6 neighbourhood (rows y-4, y, y+4) is read with three
+  // 128-bit and six 32-bit loads, and the four tests run in registers
+  for (int i = tid; i < kETH * (kETW / 4); i += kThreadsE) {
+    const int r = i / (kETW / 4), w = i - r * (kETW / 4);
+    const int* q4 = &s_score[(r + 4) * kSPitchE + 4 + 4 * w];
+    const int4 s4 = *reinterpret_cast<const int4*>(q4);
+    if ((s4.x | s4.y | s4.z | s4.w) == 0) continue;  // 0 = below threshold / not scored / outside
+    const int4 a4 = *reinterpret_cast<const int4*>(q4 + 4 * kSPitchE), b4 = *reinterpret_cast<const int4*>(q4 - 4 * kSPitchE);
+    const int c[6] = {q4[-1], s4.x, s4.y, s4.z, s4.w, q4[4]};
+    const int a[6] = {q4[4 * kSPitchE - 1], a4.x, a4.y, a4.z, a4.w, q4[4 * kSPitchE + 4]};   // row y + 4
+    const int b[6] = {q4[-4 * kSPitchE - 1], b4.x, b4.y, b4.z, b4.w, q4[-4 * kSPitchE + 4]}; // row y - 4
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int s = c[k + 1];
+      if (s == 0) continue;
+      const int ge = max(max(c[k + 2], a[k + 1]), max(a[k + 2], b[k + 2]));  // (+1,0) (0,+4) (+1,+4) (+1,-4): compared with >=
+      const int gt = max(max(c[k], b[k + 1]), max(a[k], b[k]));              // (-1,0) (0,-4) (-1,+4) (-1,-4): compared with >
+      if (ge >= s || gt > s + kCollapse) continue;              // suppressed for certain (mag is monotone)
+      if (gt > s || ge >= s - kCollapse) {                      // inside the window around equality
+        if (max(gt, s) < kExactBelow) { if (gt > s) continue; } // exact integer domain: ge < s, so only gt decides
+        else if (suppressedSlow(ge, gt, s)) continue;
+      }
+      const int gx = x0 + 4 * w + k, gy = y0 + r;
+      const int cell = divFastE(2 * gy, P.cell_magic) * P.n_cols + divFastE(2 * gx, P.cell_magic);
+      if (P.occupancy && P.occupancy[(size_t)frame_local * P.n_cells + cell]) continue;
+      const unsigned order = ((unsigned)gy << 14) | (unsigned)gx;
+      atomicMax(&P.keys[(size_t)frame_local * P.n_cells + cell], ((unsigned long long)scoreKey(s) << 32) | (unsigned long long)(0xFFFFFFFFu - order));
+    }
   }
 }
 
 __global__ void edgelet_keys_init_kernel(unsigned long long* keys, size_t n, int threshold) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = ((unsigned long long)__float_as_uint((float)threshold) << 32) | 0xFFFFFFFFull;
+  const int t2 = threshold * threshold;  // mag(threshold^2) == threshold: an empty cell holds the key of score = threshold
+  if (i < n) keys[i] = ((unsigned long long)(t2 < kExactBelow ? (unsigned)t2 : __float_as_uint((float)threshold)) << 32) | 0xFFFFFFFFull;
 }
 
 // angle_hist::angleHistogram bin of a central-difference gradient: round(36 * (atan2(gy, gx) + pi) / (2 pi)), 36 -> 0.
@@ -156,7 +257,8 @@ constexpr int kHistWarps = 8;
 
 // One warp per (frame, cell): decode the winner and compute its gradient-orientation histogram angle (half patch 4).
 __global__ void __launch_bounds__(kHistWarps * 32) edgelet_decode_kernel(PyrView v, int first, const unsigned long long* keys,
-                                                                       int n_cells, size_t n, int threshold, svo_corner* out) {
+                                                                       int n_cells, size_t n, int threshold,
+                                                                       const int8_t* __restrict__ bins, svo_corner* out) {
   __shared__ double s_mag[kHistWarps][81];
   __shared__ int8_t s_bin[kHistWarps][84];
   __shared__ double s_hist[kHistWarps][36];
@@ -164,7 +266,7 @@ __global__ void __launch_bounds__(kHistWarps * 32) edgelet_decode_kernel(PyrView
   const size_t i = (size_t)blockIdx.x * kHistWarps + warp;
   if (i >= n) return;
   const unsigned long long key = keys[i];
-  const float sc = __uint_as_float((unsigned)(key >> 32));
+  const float sc = scoreOfKey((unsigned)(key >> 32));
   svo_corner c;
   if (!(sc > (float)threshold)) {
     if (lane == 0) { c.x = 0; c.y = 0; c.level = 0; c.score = (float)threshold; c.angle = 0.0f; out[i] = c; }
@@ -175,6 +277,7 @@ __global__ void __launch_bounds__(kHistWarps * 32) edgelet_decode_kernel(PyrView
   const int frame = first + (int)(i / (size_t)n_cells);
   const uint8_t* img = v.level(frame, 1);
   const int cols = v.cols[1], rows = v.rows[1], pitch = v.pitch[1];
+  bool any_high = false;
   for (int t = lane; t < 81; t += 32) {
     const int dv = t / 9, du = t - dv * 9;
     const int u = px + du - 4, w = py + dv - 4;
@@ -184,19 +287,21 @@ __global__ void __launch_bounds__(kHistWarps * 32) edgelet_decode_kernel(PyrView
       const int gx = (int)img[(size_t)w * pitch + u + 1] - (int)img[(size_t)w * pitch + u - 1];
       const int gy = (int)img[(size_t)(w + 1) * pitch + u] - (int)img[(size_t)(w - 1) * pitch + u];
       mag = sqrt((double)(gx * gx + gy * gy));
-      bin = angleBin(gx, gy);
+      bin = bins[(gy + 255) * 511 + gx + 255];  // angleBin(gx, gy), tabulated once per context (FP64 atan2 was 85 % of this kernel)
     }
     s_mag[warp][t] = mag;
     s_bin[warp][t] = (int8_t)bin;
+    any_high |= bin >= 32;
   }
+  const bool high_bins = __any_sync(0xFFFFFFFFu, any_high);
   __syncwarp();
   // ordered per-bin sums: lane b owns bins b and b + 32 and walks the 81 terms in raster order
+  // (branch-free: adding +0.0 leaves a non-negative partial sum unchanged; bins 32 .. 35 get their own pass only when one occurs)
   double h0 = 0.0, h1 = 0.0;
-  for (int t = 0; t < 81; ++t) {
-    const int b = s_bin[warp][t];
-    const double m = s_mag[warp][t];
-    if (b == lane) h0 = __dadd_rn(h0, m);
-    if (b == lane + 32) h1 = __dadd_rn(h1, m);
+#pragma unroll 9
+  for (int t = 0; t < 81; ++t) h0 = __dadd_rn(h0, s_bin[warp][t] == lane ? s_mag[warp][t] : 0.0);
+  if (high_bins) {
+    for (int t = 0; t < 81; ++t) h1 = __dadd_rn(h1, s_bin[warp][t] == lane + 32 ? s_mag[warp][t] : 0.0);
   }
   s_hist[warp][lane] = h0;
   if (lane < 4) s_hist[warp][lane + 32] = h1;
@@ -253,11 +358,26 @@ __global__ void fastgrad_merge_kernel(const svo_corner* fast_corners, const uint
     for (int k = threadIdx.x; k < n_cells; k += blockDim.x) occ_out[(size_t)frame * n_cells + k] = 1;
 }
 
+// The bin table lives as long as the context; the one-time build is synchronised so that later calls may use any stream.
+int ensureAngleBins(svo_cuda_ctx* ctx) {
+  if (ctx->angle_bins) return SVO_OK;
+  int8_t* p = nullptr;
+  SVO_CUDA_TRY(ctx, cudaMalloc(&p, (size_t)511 * 511));
+  angle_bin_table_kernel<<<(511 * 511 + 255) / 256, 256, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFree(p); return SVO_FAIL(ctx, SVO_ERR_CUDA, cudaGetErrorString(e)); }
+  ctx->angle_bins = p;
+  return SVO_OK;
+}
+
 int edgeletDeviceImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, int threshold, int border, int cell_size,
                       const uint8_t* d_occ, svo_corner* d_out, unsigned long long* keys) {
   int n_cols, n_rows;
   const int n_cells = svo_cuda_grid_cells(pyr->cols[0], pyr->rows[0], cell_size, &n_cols, &n_rows);
   const size_t n = (size_t)n_cells * count;
+  const int rcb = ensureAngleBins(ctx);
+  if (rcb != SVO_OK) return rcb;
   edgelet_keys_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys, n, threshold);
   SVO_LAUNCH_CHECK(ctx);
   const PyrView v = makeView(pyr);
@@ -276,7 +396,7 @@ int edgeletDeviceImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int
     SVO_LAUNCH_CHECK(ctx);
   }
   edgelet_decode_kernel<<<(unsigned)((n + kHistWarps - 1) / kHistWarps), kHistWarps * 32, 0, ctx->stream>>>(v, first, keys, n_cells, n,
-                                                                                                        threshold, d_out);
+                                                                                                        threshold, ctx->angle_bins, d_out);
   SVO_LAUNCH_CHECK(ctx);
   return SVO_OK;
 }

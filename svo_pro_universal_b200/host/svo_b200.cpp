@@ -741,38 +741,109 @@ void fastDetector(const b200::GpuPyramid& gpu, const int threshold, const int bo
   for (size_t k = 0; k < out.size(); ++k)
     if (out[k].score > corners[k].score) corners[k] = Corner(out[k].x, out[k].y, out[k].score, out[k].level, out[k].angle);
 }
+void edgeletDetector_V2(const b200::GpuPyramid& gpu, const int threshold, const int border, const int /*min_level*/, const int /*max_level*/,
+                        Corners& corners, OccupandyGrid2D& grid) {
+  if (corners.size() != grid.occupancy_.size()) throw b200::Error("edgeletDetector_V2: corners/grid size mismatch");  // CHECK_EQ of :322
+  std::vector<svo_corner> out(corners.size());
+  b200::check(svo_cuda_edgelet_detect(b200::context(), gpu.handle(), 0, 1, threshold, border, grid.cell_size, grid.occupancy_.data(),
+                                      out.data(), SVO_MEM_HOST), "svo_cuda_edgelet_detect");
+  for (size_t k = 0; k < out.size(); ++k)
+    if (out[k].score > corners[k].score) corners[k] = Corner(out[k].x, out[k].y, out[k].score, out[k].level, out[k].angle);
+}
+
+void fillFeatures(const Corners& corners, const FeatureType& type, const double& threshold, const size_t max_n_features,
+                  Keypoints& keypoints, Scores& scores, Levels& levels, Gradients& gradients, FeatureTypes& types, OccupandyGrid2D& grid) {
+  std::vector<size_t> idx;
+  for (size_t k = 0; k < corners.size(); ++k)
+    if (corners[k].score > threshold) {
+      idx.push_back(k);
+      grid.occupancy_[grid.getCellIndex(corners[k].x, corners[k].y)] = 1;
+    }
+  std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return corners[a].score > corners[b].score; });
+  if (idx.size() > max_n_features) idx.resize(max_n_features);
+  for (size_t k : idx) {
+    const Corner& c = corners[k];
+    keypoints.push_back({double(c.x), double(c.y)});
+    gradients.push_back({std::cos(c.angle), std::sin(c.angle)});  // float overloads, as feature_detection_utils.cpp:101
+    scores.push_back(c.score);
+    levels.push_back(c.level);
+    types.push_back(type);
+  }
+}
+
+AbstractDetector::Ptr makeDetector(const DetectorOptions& options, const CameraPtr& cam) {
+  switch (options.detector_type) {
+    case DetectorType::kFast: return std::make_shared<FastDetector>(options, cam);
+    case DetectorType::kFastGrad: return std::make_shared<FastGradDetector>(options, cam);
+    case DetectorType::kGridGrad: return std::make_shared<GradientDetectorGrid>(options, cam);
+    default: throw b200::Error("makeDetector: only kFast, kFastGrad and kGridGrad are implemented on the B200 path");
+  }
+}
 }  // namespace feature_detection_utils
 
-FastDetector::FastDetector(const DetectorOptions& options, const CameraPtr& cam)
+AbstractDetector::AbstractDetector(const DetectorOptions& options, const CameraPtr& cam)
     : options_(options),
       grid_(int(options.cell_size), int(std::ceil(double(cam->imageWidth()) / options.cell_size)),
             int(std::ceil(double(cam->imageHeight()) / options.cell_size))) {}
 
-void FastDetector::detect(const FramePtr& frame) {
-  // FastDetector::detect (feature_detection.cpp:53-74) + fillFeatures (feature_detection_utils.cpp:72-142)
+void FastDetector::detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec, Levels& level_vec,
+                          Gradients& grad_vec, FeatureTypes& types_vec) {
   Corners corners(size_t(grid_.n_cols) * grid_.n_rows, Corner(0, 0, float(options_.threshold_primary), 0, 0.0f));
-  feature_detection_utils::fastDetector(b200::ensureGpu(*frame), int(options_.threshold_primary), options_.border, options_.min_level,
-                                        options_.max_level, corners, grid_);
-  std::vector<size_t> idx;
-  for (size_t k = 0; k < corners.size(); ++k)
-    if (corners[k].score > options_.threshold_primary) {
-      idx.push_back(k);
-      grid_.occupancy_[grid_.getCellIndex(corners[k].x, corners[k].y)] = 1;
-    }
-  std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return corners[a].score > corners[b].score; });
+  feature_detection_utils::fastDetector(gpu, int(options_.threshold_primary), options_.border, options_.min_level, options_.max_level,
+                                        corners, grid_);
+  feature_detection_utils::fillFeatures(corners, FeatureType::kCorner, options_.threshold_primary, max_n_features, px_vec, score_vec,
+                                        level_vec, grad_vec, types_vec, grid_);
+  resetGrid();
+}
+
+void GradientDetectorGrid::detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec,
+                                  Levels& level_vec, Gradients& grad_vec, FeatureTypes& types_vec) {
+  Corners corners(size_t(grid_.n_cols) * grid_.n_rows, Corner(0, 0, float(options_.threshold_secondary), 0, 0.0f));
+  feature_detection_utils::edgeletDetector_V2(gpu, int(options_.threshold_secondary), options_.border, options_.min_level,
+                                              options_.max_level, corners, grid_);
+  feature_detection_utils::fillFeatures(corners, FeatureType::kEdgelet, options_.threshold_secondary, max_n_features, px_vec, score_vec,
+                                        level_vec, grad_vec, types_vec, grid_);
+  resetGrid();
+}
+
+void FastGradDetector::detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec,
+                              Levels& level_vec, Gradients& grad_vec, FeatureTypes& types_vec) {
+  // One device call covers both stages (FAST -> cells with a corner become occupied -> edgelets in the remaining cells, skipped when
+  // the corners already reach max_n_features); the two fillFeatures passes of feature_detection.cpp:166-190 follow on the host.
+  const size_t n_cells = size_t(grid_.n_cols) * grid_.n_rows;
+  if (int(options_.max_level) > gpu.n_levels() - 1) throw b200::Error("FastGradDetector: max_level beyond the pyramid");
+  svo_detector_options o{int(options_.threshold_primary), options_.border, options_.min_level, options_.max_level, grid_.cell_size, 10};
+  std::vector<svo_corner> fast(n_cells), edge(n_cells);
+  b200::check(svo_cuda_fastgrad_detect(b200::context(), gpu.handle(), 0, 1, &o, int(options_.threshold_secondary), int(max_n_features),
+                                       grid_.occupancy_.data(), fast.data(), edge.data(), SVO_MEM_HOST), "svo_cuda_fastgrad_detect");
+  Corners corners(n_cells, Corner(0, 0, float(options_.threshold_primary), 0, 0.0f));
+  for (size_t k = 0; k < n_cells; ++k)
+    if (fast[k].score > corners[k].score) corners[k] = Corner(fast[k].x, fast[k].y, fast[k].score, fast[k].level, fast[k].angle);
+  const size_t n_before = px_vec.size();
+  feature_detection_utils::fillFeatures(corners, FeatureType::kCorner, options_.threshold_primary, max_n_features, px_vec, score_vec,
+                                        level_vec, grad_vec, types_vec, grid_);
+  const long max_features = long(max_n_features) - long(px_vec.size() - n_before) - long(n_before);
+  if (max_features > 0) {
+    Corners edgelets(n_cells, Corner(0, 0, float(options_.threshold_secondary), 0, 0.0f));
+    for (size_t k = 0; k < n_cells; ++k)
+      if (edge[k].score > edgelets[k].score) edgelets[k] = Corner(edge[k].x, edge[k].y, edge[k].score, edge[k].level, edge[k].angle);
+    feature_detection_utils::fillFeatures(edgelets, FeatureType::kEdgelet, options_.threshold_secondary, size_t(max_features), px_vec,
+                                          score_vec, level_vec, grad_vec, types_vec, grid_);
+  }
+  resetGrid();
+}
+
+void AbstractDetector::detect(const FramePtr& frame) {
+  // feature_detection.cpp:40-50: detect into the frame's columns, then frame_utils::computeNormalizedBearingVectors
+  const size_t n_old = frame->px_vec_.size();
+  detect(b200::ensureGpu(*frame), grid_.size(), frame->px_vec_, frame->score_vec_, frame->level_vec_, frame->grad_vec_, frame->type_vec_);
   const svo_camera& cm = frame->cam_->model;
-  for (size_t k : idx) {
-    const Corner& c = corners[k];
-    frame->px_vec_.push_back({double(c.x), double(c.y)});
-    frame->grad_vec_.push_back({std::cos(c.angle), std::sin(c.angle)});
-    frame->score_vec_.push_back(c.score);
-    frame->level_vec_.push_back(c.level);
-    frame->type_vec_.push_back(FeatureType::kCorner);
+  for (size_t i = n_old; i < frame->px_vec_.size(); ++i) {
     frame->depth_vec_.push_back(-1.0);
     frame->invmu_sigma2_a_b_vec_.push_back({0, 0, 0, 0});
     // frame_utils::computeNormalizedBearingVectors (frame.cpp:427-439): f = normalize(backProject3(px)); <= n_cells keypoints
     // per keyframe, host glue (pinhole_projection.hpp:30-41, radial_tangential_distortion.h:80-95)
-    double x = (c.x - cm.cx) * (1.0 / cm.fx), y = (c.y - cm.cy) * (1.0 / cm.fy);
+    double x = (frame->px_vec_[i][0] - cm.cx) * (1.0 / cm.fx), y = (frame->px_vec_[i][1] - cm.cy) * (1.0 / cm.fy);
     if (cm.distortion) {
       const double x0 = x, y0 = y;
       for (int it = 0; it < 5; ++it) {
@@ -787,7 +858,6 @@ void FastDetector::detect(const FramePtr& frame) {
     frame->f_vec_.push_back({x / n, y / n, 1.0 / n});
   }
   frame->num_features_ = frame->px_vec_.size();
-  resetGrid();
 }
 
 }  // namespace svo

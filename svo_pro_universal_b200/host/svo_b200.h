@@ -297,12 +297,18 @@ struct Corner {  // src/svo_direct/include/svo/direct/feature_detection_types.h:
 };
 using Corners = std::vector<Corner>;
 
-struct DetectorOptions {  // feature_detection_types.h:49-84 (FAST-relevant subset)
+enum class DetectorType {  // feature_detection_types.h:33-45 (the grid detectors of this path are implemented)
+  kFast, kGrad, kFastGrad, kShiTomasi, kShiTomasiGrad, kGridGrad, kAll, kGradHuangMumford, kCanny, kSobel
+};
+
+struct DetectorOptions {  // feature_detection_types.h:49-84
   size_t cell_size = 30;
   int max_level = 2;
   int min_level = 0;
   int border = 8;
+  DetectorType detector_type = DetectorType::kFast;
   double threshold_primary = 10.0;
+  double threshold_secondary = 100.0;
 };
 
 class OccupandyGrid2D {  // src/svo_common/include/svo/common/occupancy_grid_2d.h:10-110
@@ -316,22 +322,69 @@ class OccupandyGrid2D {  // src/svo_common/include/svo/common/occupancy_grid_2d.
   size_t getCellIndex(int x, int y, int scale = 1) const { return size_t((scale * y) / cell_size) * n_cols + size_t((scale * x) / cell_size); }
 };
 
+using Keypoints = std::vector<Keypoint>;
+using Gradients = std::vector<GradientVector>;
+using Scores = std::vector<double>;
+using Levels = std::vector<int>;
+using FeatureTypes = std::vector<FeatureType>;
+
 namespace feature_detection_utils {
 // src/svo_direct/include/svo/direct/feature_detection_utils.h:43-50; `gpu` is the frame's device pyramid.
 void fastDetector(const b200::GpuPyramid& gpu, const int threshold, const int border, const size_t min_level, const size_t max_level,
                   Corners& corners, OccupandyGrid2D& grid);
+// feature_detection_utils.h:75-82 (runs on pyramid level 1, reports level 0; min_level / max_level are unused there too)
+void edgeletDetector_V2(const b200::GpuPyramid& gpu, const int threshold, const int border, const int min_level, const int max_level,
+                        Corners& corners, OccupandyGrid2D& grid);
+// feature_detection_utils.h:27-38 without the mask (the facades run with an empty mask): score > threshold, grid marking, sort by
+// score, at most max_n_features appended.
+void fillFeatures(const Corners& corners, const FeatureType& type, const double& threshold, const size_t max_n_features,
+                  Keypoints& keypoints, Scores& scores, Levels& levels, Gradients& gradients, FeatureTypes& types, OccupandyGrid2D& grid);
 }  // namespace feature_detection_utils
 
-class FastDetector {  // src/svo_direct/include/svo/direct/feature_detection.h:20-81
+class AbstractDetector {  // src/svo_direct/include/svo/direct/feature_detection.h:20-64
  public:
+  using Ptr = std::shared_ptr<AbstractDetector>;
   DetectorOptions options_;
   OccupandyGrid2D grid_;
-  FastDetector(const DetectorOptions& options, const CameraPtr& cam);
-  // AbstractDetector::detect(const FramePtr&) (feature_detection.cpp:40-50): appends corners to the frame's SoA arrays,
-  // computes unit bearing vectors, resets the grid.
+  AbstractDetector(const DetectorOptions& options, const CameraPtr& cam);
+  virtual ~AbstractDetector() = default;
+  // AbstractDetector::detect(const FramePtr&) (feature_detection.cpp:40-50): appends the features to the frame's SoA arrays and
+  // computes their unit bearing vectors. max_n_features = grid size.
   void detect(const FramePtr& frame);
+  // The virtual detect of the reference (feature_detection.h:41-49) with the frame's device pyramid in place of (img_pyr, mask).
+  virtual void detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec, Levels& level_vec,
+                      Gradients& grad_vec, FeatureTypes& types_vec) = 0;
   void resetGrid() { grid_.reset(); }
 };
+
+class FastDetector : public AbstractDetector {  // feature_detection.h:66-81; feature_detection.cpp:53-74
+ public:
+  using AbstractDetector::AbstractDetector;
+  using AbstractDetector::detect;
+  void detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec, Levels& level_vec,
+              Gradients& grad_vec, FeatureTypes& types_vec) override;
+};
+
+class GradientDetectorGrid : public AbstractDetector {  // feature_detection.h:105-122; feature_detection.cpp:130-151
+ public:
+  using AbstractDetector::AbstractDetector;
+  using AbstractDetector::detect;
+  void detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec, Levels& level_vec,
+              Gradients& grad_vec, FeatureTypes& types_vec) override;
+};
+
+class FastGradDetector : public AbstractDetector {  // feature_detection.h:133-150; feature_detection.cpp:154-194 (the default detector)
+ public:
+  using AbstractDetector::AbstractDetector;
+  using AbstractDetector::detect;
+  void detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec, Levels& level_vec,
+              Gradients& grad_vec, FeatureTypes& types_vec) override;
+};
+
+namespace feature_detection_utils {
+// feature_detection_utils.h:21-25: kFast, kFastGrad and kGridGrad are available; the other types throw b200::Error.
+AbstractDetector::Ptr makeDetector(const DetectorOptions& options, const CameraPtr& cam);
+}  // namespace feature_detection_utils
 
 // ---- (f1) Reprojector ---------------------------------------------------------------------------------------------------------
 struct ReprojectorOptions {  // src/svo/include/svo/reprojector.h:27-70 (without the global-map options)

@@ -62,6 +62,20 @@ int main(int argc, char** argv) {
       out.push_back(cs);
       ref->clearFeatureStorage();
     }
+    // (a') makeDetector(kFastGrad) / makeDetector(kGridGrad) ->detect on the ref frame (the reference's default detector)
+    for (DetectorType t : {DetectorType::kFastGrad, DetectorType::kGridGrad}) {
+      DetectorOptions o;
+      o.detector_type = t;
+      AbstractDetector::Ptr det = feature_detection_utils::makeDetector(o, cam);
+      det->detect(ref);
+      out.push_back(double(ref->num_features_));
+      for (size_t i = 0; i < ref->num_features_; ++i) {
+        out.push_back(ref->px_vec_[i][0]); out.push_back(ref->px_vec_[i][1]); out.push_back(ref->score_vec_[i]); out.push_back(ref->level_vec_[i]);
+        out.push_back(double(int(ref->type_vec_[i]))); out.push_back(ref->grad_vec_[i][0]); out.push_back(ref->grad_vec_[i][1]);
+        out.push_back(ref->f_vec_[i][2]);
+      }
+      ref->clearFeatureStorage();
+    }
     // features of the test set
     for (int i = 0; i < N; ++i) {
       ref->px_vec_.push_back({px[2 * i], px[2 * i + 1]});

@@ -320,7 +320,10 @@ def pose_opt_outputs(orc, which):
 # (seed, width, height, n_levels, kind, threshold_secondary, border, with_occupancy)
 DETECT_CASES = [(11, 752, 480, 5, "rect", 100, 8, False), (12, 752, 480, 5, "rect", 30, 8, True), (13, 640, 480, 4, "rect", 100, 4, False),
                 (14, 500, 300, 3, "stripes", 60, 8, False), (15, 752, 480, 5, "noise", 100, 8, True), (16, 376, 240, 2, "rect", 250, 10, False),
-                (17, 100, 75, 2, "rect", 40, 8, False), (18, 44, 40, 2, "noise", 20, 8, False)]
+                (17, 100, 75, 2, "rect", 40, 8, False), (18, 44, 40, 2, "noise", 20, 8, False),
+                # 0 / 255 blobs: squared magnitudes beyond 2^22, where float(sqrt(n)) stops being injective (edgelet.cu's slow paths),
+                # the second one with a threshold above 2048 as well
+                (19, 376, 240, 2, "binary", 100, 8, False), (20, 376, 240, 2, "binary", 2500, 8, True)]
 CORNER_FIELDS = ("x", "y", "level", "score", "angle")
 
 
@@ -329,6 +332,10 @@ def detect_image(seed, w, h, kind):
     rng = np.random.default_rng(seed)
     if kind == "rect":
         return synth.make_image(seed, w, h, n_rect=max(8, w * h // 400))
+    if kind == "binary":
+        yy, xx = np.mgrid[0:h, 0:w]
+        blobs = np.sin(xx / 7.0 + seed) * np.cos(yy / 5.0) + 0.3 * np.sin((xx + 2 * yy) / 11.0) + 0.15 * rng.standard_normal((h, w))
+        return np.where(blobs > 0, 255, 0).astype(np.uint8)
     if kind == "stripes":
         yy, xx = np.mgrid[0:h, 0:w]
         return (((xx // 8 + yy // 16) % 2) * 150 + 40 + rng.integers(0, 2, (h, w))).astype(np.uint8)

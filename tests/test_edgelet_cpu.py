@@ -69,7 +69,13 @@ def test_fastgrad_semantics(orc):
 def test_float_sqrt_claim():
     """The CUDA kernel computes float(std::sqrt(double(n))) as a correctly rounded float sqrt for n < 2^24 (edgelet.cu)."""
     n = np.arange(0, 1 << 24, dtype=np.int64)
-    assert np.array_equal(np.sqrt(n.astype(np.float64)).astype(np.float32), np.sqrt(n.astype(np.float32)))
+    f = np.sqrt(n.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(f, np.sqrt(n.astype(np.float32)))
+    # ... and keeps the SQUARED magnitude in its score tile: n -> float(sqrt(n)) is strictly increasing below 2^22, so integer
+    # comparisons decide the reference's float comparisons there (scoreGE / scoreGT in edgelet.cu), and non-decreasing above
+    assert (np.diff(f[:1 << 22]) > 0).all() and (np.diff(f) >= 0).all()
+    t = np.arange(0, 2048, dtype=np.int64)
+    assert np.array_equal(f[t * t], t.astype(np.float32))  # mag(thr^2) == thr exactly
 
 
 def test_angle_bins_on_the_diagonals(orc):

@@ -65,6 +65,19 @@ def test_cpp_facades_match_oracle(orc, tmp_path):
     cs_o = sum(float((im.astype(np.float64) * ((np.arange(im.shape[1])[None, :] + 3 * np.arange(im.shape[0])[:, None]) % 7 + 1)).sum()) for im in pyr)
     assert cs == cs_o  # host mirror of the GPU pyramid is bit-exact
 
+    # (a') FastGradDetector / GradientDetectorGrid ::detect == the oracle's (identical to the reference's own compiled detectors)
+    for det_type in (orc.DETECTOR_FAST_GRAD, orc.DETECTOR_GRID_GRAD):
+        n_det = int(out[p]); p += 1
+        det = out[p:p + 8 * n_det].reshape(n_det, 8); p += 8 * n_det
+        o = orc.detect_features(det_type, pyr)
+        assert n_det == len(o["score"]) > 300
+        got = {"px": det[:, 0:2], "score": det[:, 2], "level": det[:, 3].astype(np.int32), "type": det[:, 4].astype(np.int32), "grad": det[:, 5:7]}
+        from helpers import assert_features_equal
+        assert_features_equal(got, o, f"facade detector {det_type}")
+        assert (det[:, 7] > 0.5).all()  # unit bearing vectors computed for the new features
+        if det_type == orc.DETECTOR_FAST_GRAD:
+            assert (got["type"] == 6).sum() > 5 and (got["type"] == 7).sum() > 100
+
     # (b) SparseImgAlign::run writes cur->T_f_w_
     n_tracked = int(out[p]); p += 1
     T_f_w = out[p:p + 7]; p += 7
