@@ -270,6 +270,36 @@ int svo_cuda_find_epipolar_match_direct(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
                                         const svo_feature* ftrs, const double* d_inv, const svo_matcher_options* opt,
                                         svo_match_out* out, svo_mem mem);
 
+/* ---- (f3) svo::StereoTriangulation ------------------------------------------------------------------------------- */
+typedef enum { SVO_STEREO_NOT_REACHED = 0, SVO_STEREO_FAILED = 1, SVO_STEREO_SUCCESS = 2 } svo_stereo_status;
+typedef struct { /* what StereoTriangulation::compute writes per matched feature (stereo_triangulation.cpp:102-129) */
+  double px_cur[2], f_cur[3];   /* matcher.px_cur_, matcher.f_cur_ -> frame1's px_vec_ / f_vec_ column */
+  double grad_cur[2];           /* (A_cur_ref * ref grad).normalized() -> frame1's grad_vec_ column */
+  double xyz_world[3];          /* the new Point: frame0->T_world_cam() * (f * depth) */
+  double depth;
+  int status;                   /* svo_stereo_status */
+  int slot;                     /* success: feature slot in frame1 (num_features_ at that moment) */
+  int match_result;             /* Matcher::MatchResult, -1 = not reached */
+  int level, type;              /* success: copied from the frame0 feature */
+  int _pad;
+} svo_stereo_result;
+typedef struct { int n_succeeded, n_failed; } svo_stereo_stats;
+
+/* StereoTriangulation::compute (src/svo/include/svo/stereo_triangulation.h:20-37; src/svo/src/stereo_triangulation.cpp:87-137: the
+ * matching loop) for B independent stereo pairs: frame0 of pair b = frame frame0_idx[b] of pyr0 (NULL = b), frame1 likewise in pyr1;
+ * T_f1f0 [7] = frame1->T_cam_body_ * frame0->T_body_cam_ (the rig's extrinsics, shared); T_world_cam0 [B][7]. Pair b tries the
+ * features ftrs[feat_begin[b] .. feat_begin[b+1]) of frame0 IN THIS ORDER (the caller has detected them and applied the reference's
+ * two std::random_shuffle calls, :34-79) with Matcher::findEpipolarMatchDirect (align_1d = isEdgelet(type), the inverse-depth
+ * range given) until n_desired[b] = triangulate_n_features - frame0->numLandmarks() of them succeeded; n_features_in_frame1[b] =
+ * frame1->num_features_ before the call. mopt: the Matcher options (the reference sets max_epi_search_steps = 500 and
+ * subpix_refinement = true, :90-91; its align_1d field is ignored). results [n_features], stats [B]. n_features = feat_begin[B]. */
+int svo_cuda_stereo_triangulate(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr0, const svo_cuda_pyr* pyr1, const int* frame0_idx,
+                                const int* frame1_idx, const svo_camera* cam0, const svo_camera* cam1, const double* T_f1f0,
+                                const double* T_world_cam0, int B, const int* feat_begin, int n_features, const svo_feature* ftrs,
+                                const int* n_desired, const int* n_features_in_frame1, double mean_depth_inv, double min_depth_inv,
+                                double max_depth_inv, const svo_matcher_options* mopt, svo_stereo_result* results,
+                                svo_stereo_stats* stats, svo_mem mem);
+
 /* ---- (d) svo::DepthFilter seed update ---------------------------------------------------------------------- */
 /* depth_filter_utils::updateFilterVogiatzis (src/svo_direct/include/svo/direct/depth_filter.h:201-205;
  * src/svo_direct/src/depth_filter.cpp:501-552): n independent updates; state [n][4] = (mu, sigma2, a, b) in/out;

@@ -877,3 +877,50 @@ def detect_features(detector_type, pyr, threshold_primary=10.0, threshold_second
     m = fn(int(detector_type), n, data, cols, rows, step, float(threshold_primary), float(threshold_secondary), int(border),
            int(min_level), int(max_level), int(cell_size), occ, max_n, _f64(px), _f64(sc), _i32(lv), _f64(gr), _i32(ty))
     return {"px": px[:m].copy(), "score": sc[:m].copy(), "level": lv[:m].copy(), "grad": gr[:m].copy(), "type": ty[:m].copy()}
+
+
+# ---- f3: StereoTriangulation::compute ---------------------------------------------------------------------------------------------
+STEREO_RESULT_DT = np.dtype([("px_cur", "<f8", 2), ("f_cur", "<f8", 3), ("grad_cur", "<f8", 2), ("xyz_world", "<f8", 3), ("depth", "<f8"),
+                             ("status", "<i4"), ("slot", "<i4"), ("match_result", "<i4"), ("level", "<i4"), ("type", "<i4"), ("_pad", "<i4")])
+
+
+def stereo_triangulate(frame0, frame1, ftrs, n_desired, n_features_in_frame1=0, mean_depth_inv=1.0 / 3.0, min_depth_inv=1.0,
+                       max_depth_inv=1.0 / 50.0):
+    """The matching loop of StereoTriangulation::compute on features in visiting order (make_features array)
+    -> (results [n] STEREO_RESULT_DT, n_succeeded, n_failed)."""
+    n = len(ftrs)
+    res = np.zeros(n, STEREO_RESULT_DT)
+    nf = C.c_int(0)
+    fn = lib().orc_stereo_triangulate
+    fn.argtypes = [C.POINTER(Frame), C.POINTER(Frame), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                   C.c_void_p, C.POINTER(C.c_int)]
+    ns = fn(C.byref(frame0), C.byref(frame1), n, C.cast(ftrs, C.c_void_p), int(n_desired), int(n_features_in_frame1), mean_depth_inv,
+            min_depth_inv, max_depth_inv, res.ctypes.data, C.byref(nf))
+    return res, ns, nf.value
+
+
+def ref_stereo_shuffle_order(seed, n_old, n_corners, n_new):
+    """The visiting order the reference's two std::random_shuffle calls produce after srand(seed) (frame0 feature indices)."""
+    order = np.zeros(n_new, np.int32)
+    ref_frontend_lib().ref_stereo_shuffle_order(C.c_uint(seed), int(n_old), int(n_corners), int(n_new), _i32(order))
+    return order
+
+
+def ref_stereo_triangulation_compute(frame0, frame1, detector_type=DETECTOR_FAST_GRAD, threshold_primary=10.0, threshold_secondary=100.0,
+                                     triangulate_n_features=120, mean_depth_inv=1.0 / 3.0, min_depth_inv=1.0, max_depth_inv=1.0 / 50.0,
+                                     seed=1, cap=1024):
+    """The reference's own StereoTriangulation::compute on two feature-less frames -> dict of frame0's and frame1's new columns."""
+    L = ref_frontend_lib()
+    fn = L.ref_stereo_triangulation_compute
+    fn.argtypes = [C.POINTER(Frame), C.POINTER(Frame), C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
+                   C.c_uint, C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 13
+    n0 = C.c_int(0)
+    px0 = np.zeros((cap, 2)); level0 = np.zeros(cap, np.int32); type0 = np.zeros(cap, np.int32); score0 = np.zeros(cap); grad0 = np.zeros((cap, 2))
+    px1 = np.zeros((cap, 2)); f1 = np.zeros((cap, 3)); grad1 = np.zeros((cap, 2)); level1 = np.zeros(cap, np.int32)
+    type1 = np.zeros(cap, np.int32); score1 = np.zeros(cap); xyz1 = np.zeros((cap, 3)); ref1 = np.zeros(cap, np.int32)
+    n1 = fn(C.byref(frame0), C.byref(frame1), int(detector_type), threshold_primary, threshold_secondary, int(triangulate_n_features),
+            mean_depth_inv, min_depth_inv, max_depth_inv, C.c_uint(seed), cap, C.byref(n0),
+            *[a.ctypes.data for a in (px0, level0, type0, score0, grad0, px1, f1, grad1, level1, type1, score1, xyz1, ref1)])
+    a, b = n0.value, n1
+    return dict(n0=a, px0=px0[:a], level0=level0[:a], type0=type0[:a], score0=score0[:a], grad0=grad0[:a], n1=b, px1=px1[:b], f1=f1[:b],
+                grad1=grad1[:b], level1=level1[:b], type1=type1[:b], score1=score1[:b], xyz1=xyz1[:b], ref_index1=ref1[:b])

@@ -357,6 +357,54 @@ int orc_find_epipolar_match_direct(const orc_frame* ref, const orc_frame* cur, c
   return int(r);
 }
 
+// StereoTriangulation::compute from the matching loop on — ref: src/svo/src/stereo_triangulation.cpp:87-137.
+// (Detection, bearing vectors and the two std::random_shuffle calls, :34-79, happen before: `ftrs` is the shuffled visiting order.)
+int orc_stereo_triangulate(const orc_frame* frame0, const orc_frame* frame1, int n, const orc_feature* ftrs, int n_desired,
+                           int n_features_in_frame1, double mean_depth_inv, double min_depth_inv, double max_depth_inv,
+                           orc_stereo_result* results, int* n_failed_out) {
+  const MatchFrame f0 = matchFrameOf(frame0), f1 = matchFrameOf(frame1);
+  const SE3 T_c0_w = se3FromArray(frame0->T_cam_imu) * se3FromArray(frame0->T_imu_world);
+  const SE3 T_c1_w = se3FromArray(frame1->T_cam_imu) * se3FromArray(frame1->T_imu_world);
+  const SE3 T_f1f0 = se3FromArray(frame1->T_cam_imu) * inverse(se3FromArray(frame0->T_cam_imu));  // T_cam_body(1) * T_body_cam(0), :92
+  const SE3 T_w_c0 = inverse(T_c0_w);
+  (void)T_c1_w;
+  Matcher matcher;
+  matcher.options_.max_epi_search_steps = 500;  // :90-91
+  matcher.options_.subpix_refinement = true;
+  int n_succeeded = 0, n_failed = 0;
+  for (int i = 0; i < n; ++i) { results[i] = orc_stereo_result{}; results[i].match_result = -1; results[i].slot = -1; }
+  for (int i = 0; i < n; ++i) {
+    const FeatureRef ft = featureOf(&ftrs[i]);
+    matcher.options_.align_1d = isEdgelet(ft.type);  // :95
+    double depth = 0.0;
+    const Matcher::MatchResult res = matcher.findEpipolarMatchDirect(f0, f1, T_f1f0, ft, mean_depth_inv, min_depth_inv, max_depth_inv, depth);
+    orc_stereo_result& r = results[i];
+    r.match_result = int(res);
+    if (res == Matcher::MatchResult::kSuccess) {
+      const V3 xyz = T_w_c0 * (ft.f * depth);  // :104-105
+      r.status = 2;
+      r.slot = n_features_in_frame1 + n_succeeded;  // frame1->num_features_ at that moment, :111
+      r.depth = depth;
+      r.xyz_world[0] = xyz.x; r.xyz_world[1] = xyz.y; r.xyz_world[2] = xyz.z;
+      r.px_cur[0] = matcher.px_cur_.x; r.px_cur[1] = matcher.px_cur_.y;
+      r.f_cur[0] = matcher.f_cur_.x; r.f_cur[1] = matcher.f_cur_.y; r.f_cur[2] = matcher.f_cur_.z;
+      const double gx = matcher.A_cur_ref_[0][0] * ft.grad.x + matcher.A_cur_ref_[0][1] * ft.grad.y;  // :118-119
+      const double gy = matcher.A_cur_ref_[1][0] * ft.grad.x + matcher.A_cur_ref_[1][1] * ft.grad.y;
+      const double n2 = gx * gx + gy * gy;
+      const double nn = n2 > 0.0 ? std::sqrt(n2) : 1.0;  // Eigen's normalized() leaves a zero vector alone
+      r.grad_cur[0] = gx / nn; r.grad_cur[1] = gy / nn;
+      r.level = ft.level; r.type = int(ft.type);
+      ++n_succeeded;
+    } else {
+      r.status = 1;
+      ++n_failed;
+    }
+    if (n_succeeded >= n_desired) break;  // :131-132
+  }
+  if (n_failed_out) *n_failed_out = n_failed;
+  return n_succeeded;
+}
+
 int orc_find_match_direct_batch(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], int M,
                                 const orc_feature* ftrs, const double* ref_depth, const double* px_cur_in,
                                 const orc_matcher_options* opt, orc_match_out* out, int n_threads) {

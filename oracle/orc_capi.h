@@ -120,6 +120,15 @@ int orc_detect_features(int detector_type, int n_levels, const uint8_t* const* d
                         const int* step, double threshold_primary, double threshold_secondary, int border, int min_level,
                         int max_level, int cell_size, const uint8_t* occupancy, int max_n, double* px_out, double* score_out,
                         int* level_out, double* grad_out, int* type_out);
+/* f3 (StereoTriangulation::compute after detection and shuffling): entry i = feature ftrs[i] of frame0 in visiting order.
+ * status: 0 = not reached (n_desired successes came first), 1 = tried and failed, 2 = success. */
+typedef struct {
+  double px_cur[2], f_cur[3], grad_cur[2], xyz_world[3], depth;
+  int status, slot, match_result, level, type, _pad;
+} orc_stereo_result;
+int orc_stereo_triangulate(const orc_frame* frame0, const orc_frame* frame1, int n, const orc_feature* ftrs, int n_desired,
+                           int n_features_in_frame1, double mean_depth_inv, double min_depth_inv, double max_depth_inv,
+                           orc_stereo_result* results, int* n_failed);
 /* b */
 int orc_sparse_align(int n_cams, const orc_frame* ref, const orc_frame* cur, const orc_align_options* opt, orc_align_result* res);
 /* B independent problems: ref/cur hold B*n_cams frames; n_threads worker threads (one problem per task). */

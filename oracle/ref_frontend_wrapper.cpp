@@ -266,10 +266,7 @@ int ref_warp_affine(const double A_cur_ref[4], const uint8_t* img, int cols, int
 }  // extern "C"
 
 // ---- (d) depth filter -----------------------------------------------------------------------------------------------------
-// DepthFilter's constructor names the detector factory; the checker never builds a detector through it.
-namespace svo { namespace feature_detection_utils {
-AbstractDetectorPtr makeDetector(const DetectorOptions&, const CameraPtr&) { std::abort(); }
-} }
+// (DepthFilter's constructor names the detector factory: the reference's own makeDetector is linked in, see f3 below.)
 
 extern "C" {
 
@@ -610,4 +607,60 @@ extern "C" int ref_pose_optimize(int n_cams, const orc_frame* frames, int N, con
   stats[0] = po.measurement_sigma_; stats[1] = po.stats_.reproj_error_before; stats[2] = po.stats_.reproj_error_after;
   stats[3] = double(po.iterCount()); stats[4] = 0.0; stats[5] = po.getError();
   return int(n);
+}
+
+// ---- f3: StereoTriangulation::compute (src/svo/src/stereo_triangulation.cpp:23-139), the whole function: detection with the detector
+// makeDetector builds, bearing vectors, the two std::random_shuffle calls (srand(seed) first, so that ref_stereo_shuffle_order
+// reproduces the visiting order), the epipolar matching loop and the bookkeeping of both frames.
+#include <svo/stereo_triangulation.h>
+#include <svo/direct/feature_detection.h>
+#include <svo/direct/feature_detection_utils.h>
+#include <algorithm>
+#include <numeric>
+
+extern "C" void ref_stereo_shuffle_order(unsigned seed, int n_old, int n_corners, int n_new, int* order) {
+  std::vector<size_t> indices(static_cast<size_t>(n_new));
+  std::iota(indices.begin(), indices.end(), n_old);
+  srand(seed);
+  std::random_shuffle(indices.begin(), indices.begin() + n_corners);
+  std::random_shuffle(indices.begin() + n_corners, indices.end());
+  for (int i = 0; i < n_new; ++i) order[i] = (int)indices[i];
+}
+
+// Outputs: frame0's new feature columns (cap0 entries of room) and, per feature frame1 received, its columns, the landmark position
+// and the frame0 feature index its landmark was created from. Returns frame1's feature count; *n0_out = frame0's feature count.
+extern "C" int ref_stereo_triangulation_compute(const orc_frame* f0, const orc_frame* f1, int detector_type, double threshold_primary,
+                                                double threshold_secondary, int triangulate_n_features, double mean_depth_inv,
+                                                double min_depth_inv, double max_depth_inv, unsigned seed, int cap, int* n0_out,
+                                                double* px0, int* level0, int* type0, double* score0, double* grad0, double* px1,
+                                                double* fv1, double* grad1, int* level1, int* type1, double* score1, double* xyz1,
+                                                int* ref_index1) {
+  svo::FramePtr frame0 = makeFrame(*f0), frame1 = makeFrame(*f1);
+  frame0->id_ = 1; frame1->id_ = 2;
+  svo::DetectorOptions o;
+  o.detector_type = static_cast<svo::DetectorType>(detector_type);
+  o.threshold_primary = threshold_primary; o.threshold_secondary = threshold_secondary;
+  svo::StereoTriangulationOptions so;
+  so.triangulate_n_features = (size_t)triangulate_n_features;
+  so.mean_depth_inv = mean_depth_inv; so.min_depth_inv = min_depth_inv; so.max_depth_inv = max_depth_inv;
+  svo::StereoTriangulation st(so, svo::feature_detection_utils::makeDetector(o, frame0->cam_));
+  srand(seed);
+  st.compute(frame0, frame1);
+  const int n0 = (int)frame0->num_features_, n1 = (int)frame1->num_features_;
+  *n0_out = n0;
+  for (int i = 0; i < n0 && i < cap; ++i) {
+    px0[2 * i] = frame0->px_vec_(0, i); px0[2 * i + 1] = frame0->px_vec_(1, i);
+    level0[i] = frame0->level_vec_(i); type0[i] = (int)frame0->type_vec_[i]; score0[i] = frame0->score_vec_(i);
+    grad0[2 * i] = frame0->grad_vec_(0, i); grad0[2 * i + 1] = frame0->grad_vec_(1, i);
+  }
+  for (int i = 0; i < n1 && i < cap; ++i) {
+    px1[2 * i] = frame1->px_vec_(0, i); px1[2 * i + 1] = frame1->px_vec_(1, i);
+    for (int k = 0; k < 3; ++k) fv1[3 * i + k] = frame1->f_vec_(k, i);
+    grad1[2 * i] = frame1->grad_vec_(0, i); grad1[2 * i + 1] = frame1->grad_vec_(1, i);
+    level1[i] = frame1->level_vec_(i); type1[i] = (int)frame1->type_vec_[i]; score1[i] = frame1->score_vec_(i);
+    const svo::PointPtr& p = frame1->landmark_vec_[i];
+    for (int k = 0; k < 3; ++k) xyz1[3 * i + k] = p ? p->pos_[k] : 0.0;
+    ref_index1[i] = p && !p->obs_.empty() ? (int)p->obs_[0].keypoint_index_ : -1;
+  }
+  return n1;
 }

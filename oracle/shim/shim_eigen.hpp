@@ -68,6 +68,8 @@ template <typename M> struct CommaInit {
 };
 
 // Writable P x Q window into a matrix (block<P,Q>(i,j), col(j), head<N>(), ...). Reads convert to a value.
+template <typename M, int P, int Q> struct BlockRef;
+template <typename M, int P, int Q> using Block = BlockRef<M, P, Q>;  // only named in declarations of the tracker headers
 template <typename M, int P, int Q> struct BlockRef {
   typedef typename M::Scalar T;
   typedef Matrix<T, P, Q> Value;

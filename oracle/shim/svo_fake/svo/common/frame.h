@@ -4,6 +4,7 @@
 // map / bundle-adjustment / serialisation parts of the real class. The three Jacobian helpers are restated from
 // frame.h:342-357 (jacobian_xyz2uv_imu) and frame.cpp:264-290 (getErrorMultiplier, getAngleError, jacobian_xyz2image_imu).
 #pragma once
+#include <algorithm>
 #include <memory>
 #include <vector>
 #include <opencv2/core/core.hpp>
@@ -84,6 +85,9 @@ class Frame {
     for (size_t i = 0; i < num_features_; ++i)
       if ((isValidLandmark(i) && !isFixedLandmark(type_vec_[i]) && !isMapPoint(type_vec_[i])) || isCornerEdgeletSeed(type_vec_[i])) ++count;
     return count;
+  }
+  inline size_t numLandmarks() const {  // frame.h:176-181
+    return static_cast<size_t>(std::count_if(landmark_vec_.begin(), landmark_vec_.end(), [](const PointPtr& p) { return p != nullptr; }));
   }
   inline size_t numFixedLandmarks() const {  // frame.h:183-191
     size_t count = 0;
@@ -186,6 +190,13 @@ inline KeypointIdentifier::KeypointIdentifier(const FramePtr& _frame, const size
     : frame(_frame), frame_id(_frame->id_), keypoint_index_(_feature_index) {}
 
 // point.cpp:83-129
+inline void Point::addObservation(const FramePtr& frame, const size_t feature_index) {  // point.cpp:41-58
+  CHECK_NOTNULL(frame.get());
+  const auto id = frame->id();
+  auto it = std::find_if(obs_.begin(), obs_.end(), [&](const KeypointIdentifier& i) { return i.frame_id == id; });
+  if (it == obs_.end()) obs_.emplace_back(KeypointIdentifier(frame, feature_index));
+  else CHECK_EQ(it->keypoint_index_, feature_index);
+}
 inline bool Point::getCloseViewObs(const Eigen::Vector3d& framepos, FramePtr& ref_frame, size_t& ref_feature_index) const {
   double min_cos_angle = 0.0;
   Eigen::Vector3d obs_dir(framepos - pos_);

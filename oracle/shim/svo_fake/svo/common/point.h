@@ -32,6 +32,7 @@ class Point {
   explicit Point(const Position& pos) : pos_(pos) { last_projected_kf_id_.fill(-1); }  // point.cpp:29-35
   const Position& pos() const { return pos_; }
   int id() const { return id_; }
+  inline void addObservation(const FramePtr& frame, const size_t feature_index);  // point.cpp:41-58, defined after Frame (frame.h)
   inline bool getCloseViewObs(const Eigen::Vector3d& framepos, FramePtr& ref_frame, size_t& ref_feature_index) const;
 };
 using PointPtr = std::shared_ptr<Point>;

@@ -154,6 +154,10 @@ REPROJ_RESULT_DTYPE = np.dtype([("cur_px", "<f8", 2), ("px", "<f8", 2), ("f", "<
                                 ("status", "<i4"), ("order", "<i4"), ("slot", "<i4"), ("level", "<i4"), ("type_out", "<i4"),
                                 ("match_result", "<i4"), ("d_failed", "<i4"), ("d_succeeded", "<i4")])
 REPROJ_STATS_DTYPE = np.dtype([("n_candidates", "<i4"), ("n_trials", "<i4"), ("n_matches", "<i4"), ("n_consumed", "<i4")])
+STEREO_RESULT_DTYPE = np.dtype([("px_cur", "<f8", 2), ("f_cur", "<f8", 3), ("grad_cur", "<f8", 2), ("xyz_world", "<f8", 3), ("depth", "<f8"),
+                                ("status", "<i4"), ("slot", "<i4"), ("match_result", "<i4"), ("level", "<i4"), ("type", "<i4"), ("_pad", "<i4")])
+STEREO_STATS_DTYPE = np.dtype([("n_succeeded", "<i4"), ("n_failed", "<i4")])
+STEREO_NOT_REACHED, STEREO_FAILED, STEREO_SUCCESS = range(3)
 REPROJ_NOT_CANDIDATE, REPROJ_NOT_REACHED, REPROJ_SKIPPED, REPROJ_FAILED, REPROJ_MATCHED = range(5)
 
 _lib = None
@@ -217,7 +221,7 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
     "svo_cuda_reproject_match", "svo_cuda_pose_optimize", "svo_cuda_edgelet_detect", "svo_cuda_fastgrad_detect",
-    "svo_cuda_angle_histogram_bins",
+    "svo_cuda_angle_histogram_bins", "svo_cuda_stereo_triangulate",
 ]
 
 
@@ -578,6 +582,33 @@ def reproject_match(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, tables, cur_T_f_w, 
     q = ps[len(arrs):]
     ctx.check(lib().svo_cuda_reproject_match(ctx._h, ref_pyr._h, cur_pyr._h, C.byref(cam_ref), C.byref(cam_cur), C.byref(m), F, q[0], q[1],
                                              q[2], q[3], n_entries, q[4], q[5], C.byref(opt), q[6], q[7], kind))
+    return results, stats
+
+
+def stereo_triangulate(ctx, pyr0, pyr1, cam0, cam1, T_f1f0, T_world_cam0, feat_begin, ftrs, n_desired, n_features_in_frame1, mopt,
+                       mean_depth_inv=1.0 / 3.0, min_depth_inv=1.0, max_depth_inv=1.0 / 50.0, frame0_idx=None, frame1_idx=None,
+                       results=None, stats=None):
+    """svo_cuda_stereo_triangulate: B stereo pairs, features in visiting order. Arrays numpy (host) or torch cuda (T_f1f0 always a
+    host 7-vector). Returns (results [n] STEREO_RESULT_DTYPE, stats [B] STEREO_STATS_DTYPE) or the tensors passed in."""
+    T_f1f0 = np.ascontiguousarray(T_f1f0, np.float64).reshape(7)
+    B = int(T_world_cam0.shape[0])
+    N = _n_features(ftrs)
+    if results is None:
+        if _is_torch(T_world_cam0) and T_world_cam0.is_cuda:
+            import torch
+            results = torch.zeros(max(N, 1) * STEREO_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=T_world_cam0.device)
+            stats = torch.zeros(B * STEREO_STATS_DTYPE.itemsize, dtype=torch.uint8, device=T_world_cam0.device)
+        else:
+            results = np.zeros(N, STEREO_RESULT_DTYPE)
+            stats = np.zeros(B, STEREO_STATS_DTYPE)
+    ps, kind = _ptrs(frame0_idx, frame1_idx, T_world_cam0, feat_begin, ftrs, n_desired, n_features_in_frame1, results, stats)
+    pf0, pf1, pT, pb, pf, pn, ps1, pr, pst = ps
+    fn = lib().svo_cuda_stereo_triangulate
+    fn.argtypes = [C.c_void_p] * 5 + [C.POINTER(Camera), C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(MatcherOptions), C.c_void_p,
+                                      C.c_void_p, C.c_int]
+    ctx.check(fn(ctx._h, pyr0._h, pyr1._h, pf0, pf1, C.byref(cam0), C.byref(cam1), C.c_void_p(T_f1f0.ctypes.data), pT, B, pb, N, pf, pn, ps1,
+                 mean_depth_inv, min_depth_inv, max_depth_inv, C.byref(mopt), pr, pst, kind))
     return results, stats
 
 

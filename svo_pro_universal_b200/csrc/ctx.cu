@@ -51,7 +51,7 @@ int svo_cuda_sizeof(const char* n) {
   SVO_SZ(svo_align_prior); SVO_SZ(svo_align_result); SVO_SZ(svo_matcher_options); SVO_SZ(svo_feature);
   SVO_SZ(svo_match_out); SVO_SZ(svo_depth_filter_options);
   SVO_SZ(svo_reproj_map); SVO_SZ(svo_reprojector_options); SVO_SZ(svo_reproj_result); SVO_SZ(svo_reproj_stats);
-  SVO_SZ(svo_pose_optimizer_options); SVO_SZ(svo_pose_opt_result);
+  SVO_SZ(svo_pose_optimizer_options); SVO_SZ(svo_pose_opt_result); SVO_SZ(svo_stereo_result); SVO_SZ(svo_stereo_stats);
 #undef SVO_SZ
   return -1;
 }

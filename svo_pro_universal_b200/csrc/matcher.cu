@@ -27,6 +27,8 @@ struct MatchParams {
   int* search_level_out;
   uint8_t* pwb_out;
   uint8_t* ok_out;
+  int align1d_from_type;  // findEpipolarMatchDirect: align_1d = isEdgelet(type) per feature (StereoTriangulation::compute)
+  int depth_shared;        // one (estimate, min, max) inverse-depth triple for all features
 };
 
 SVO_D void writeOut(const Group& g, svo_match_out* out, int i, const MatchState& m, int result, double depth) {
@@ -68,8 +70,10 @@ __global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P)
     writeOut(g, P.out, i, m, res, 0.0);
   } else if (MODE == 1) {
     double depth = 0.0;
-    const int res = findEpipolarMatchDirect(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, P.depth[3 * i],
-                                            P.depth[3 * i + 1], P.depth[3 * i + 2], P.opt, P.opt.align_1d != 0, pwb, m, &depth);
+    const double* dd = P.depth + (P.depth_shared ? 0 : 3 * (size_t)i);
+    const bool a1d = P.align1d_from_type ? isEdgeletType(ft.type) : P.opt.align_1d != 0;
+    const int res = findEpipolarMatchDirect(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, dd[0], dd[1], dd[2], P.opt, a1d,
+                                            pwb, m, &depth);
     writeOut(g, P.out, i, m, res, depth);
   } else {
     const V3d f_ref{ft.f[0], ft.f[1], ft.f[2]};
@@ -120,6 +124,75 @@ __global__ void __launch_bounds__(kThreads) align_only_kernel(const AlignOnlyPar
     P.px[2 * i] = x; P.px[2 * i + 1] = y;
     P.converged[i] = conv ? 1 : 0;
     if (P.h_inv) P.h_inv[i] = hinv;
+  }
+}
+
+__global__ void stereo_entry_frames_kernel(const int* feat_begin, const int* frame0_idx, const int* frame1_idx, int* e0, int* e1) {
+  const int b = blockIdx.x;
+  const int f0 = frame0_idx ? frame0_idx[b] : b, f1 = frame1_idx ? frame1_idx[b] : b;
+  for (int i = feat_begin[b] + threadIdx.x; i < feat_begin[b + 1]; i += blockDim.x) { e0[i] = f0; e1[i] = f1; }
+}
+
+// StereoTriangulation::compute's sequential bookkeeping (stereo_triangulation.cpp:93-133) on top of speculative matches of ALL
+// entries: one CTA per stereo pair scans its entries in visiting order; entry i is accepted iff it matched and fewer than n_desired
+// entries before it did; everything behind the n_desired-th success is "not reached" (the reference breaks out of its loop).
+__global__ void stereo_commit_kernel(const svo_match_out* match, const svo_feature* ftrs, const int* feat_begin, const int* n_desired,
+                                     const int* n_features_in_frame1, const double* T_world_cam0, svo_stereo_result* out,
+                                     svo_stereo_stats* stats) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_failed;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int lo = feat_begin[b], hi = feat_begin[b + 1], want = n_desired[b], slot0 = n_features_in_frame1[b];
+  const SE3d T_w_c = se3Load(T_world_cam0 + 7 * (size_t)b);
+  if (tid == 0) { s_base = 0; s_failed = 0; }
+  __syncthreads();
+  for (int c0 = lo; c0 < hi; c0 += blockDim.x) {
+    const int i = c0 + tid;
+    const bool ok = i < hi && match[i].result == 0;  // Matcher::MatchResult::kSuccess
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;  // successes before this entry
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    before += __popc(bal & ((1u << lane) - 1u));
+    int chunk = 0;
+    for (int w = 0; w < nwarp; ++w) chunk += s_warp[w];
+    if (i < hi) {
+      svo_stereo_result r;
+      memset(&r, 0, sizeof(r));
+      r.slot = -1;
+      r.match_result = -1;
+      const bool reached = before < want;  // the loop is still running when it gets to entry i
+      if (reached) {
+        const svo_match_out m = match[i];
+        r.match_result = m.result;
+        if (ok) {
+          const svo_feature ft = ftrs[i];
+          const V3d xyz = se3Apply(T_w_c, V3d{ft.f[0] * m.depth, ft.f[1] * m.depth, ft.f[2] * m.depth});
+          const V2d gc = normalized2(V2d{m.A_cur_ref[0] * ft.grad[0] + m.A_cur_ref[1] * ft.grad[1],
+                                         m.A_cur_ref[2] * ft.grad[0] + m.A_cur_ref[3] * ft.grad[1]});
+          r.status = SVO_STEREO_SUCCESS;
+          r.slot = slot0 + before;
+          r.depth = m.depth;
+          r.xyz_world[0] = xyz.x; r.xyz_world[1] = xyz.y; r.xyz_world[2] = xyz.z;
+          r.px_cur[0] = m.px_cur[0]; r.px_cur[1] = m.px_cur[1];
+          r.f_cur[0] = m.f_cur[0]; r.f_cur[1] = m.f_cur[1]; r.f_cur[2] = m.f_cur[2];
+          r.grad_cur[0] = gc.x; r.grad_cur[1] = gc.y;
+          r.level = ft.level; r.type = ft.type;
+        } else {
+          r.status = SVO_STEREO_FAILED;
+          atomicAdd(&s_failed, 1);
+        }
+      }
+      out[i] = r;
+    }
+    __syncthreads();
+    if (tid == 0) s_base += chunk;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    stats[b].n_succeeded = min(s_base, want);
+    stats[b].n_failed = s_failed;
   }
 }
 
@@ -265,6 +338,64 @@ int svo_cuda_find_epipolar_match_direct(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   countT(T_idx, M, mem, &n_T);
   return matchCommon(1, ctx, ref_pyr, cur_pyr, ref_frame_idx, cur_frame_idx, cam_ref, cam_cur, T_cur_ref, T_idx, n_T, M, ftrs, d_inv, 3,
                      nullptr, opt, out, nullptr, nullptr, nullptr, nullptr, mem);
+}
+
+int svo_cuda_stereo_triangulate(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr0, const svo_cuda_pyr* pyr1, const int* frame0_idx,
+                                const int* frame1_idx, const svo_camera* cam0, const svo_camera* cam1, const double* T_f1f0,
+                                const double* T_world_cam0, int B, const int* feat_begin, int n_features, const svo_feature* ftrs,
+                                const int* n_desired, const int* n_features_in_frame1, double mean_depth_inv, double min_depth_inv,
+                                double max_depth_inv, const svo_matcher_options* mopt, svo_stereo_result* results,
+                                svo_stereo_stats* stats, svo_mem mem) {
+  if (!ctx || !pyr0 || !pyr1 || !cam0 || !cam1 || !T_f1f0 || !T_world_cam0 || B < 0 || !feat_begin || n_features < 0 || !n_desired ||
+      !n_features_in_frame1 || !mopt || !stats || (n_features > 0 && (!ftrs || !results)))
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_stereo_triangulate: bad arguments");
+  if (B == 0) return SVO_OK;
+  cudaSetDevice(ctx->device);
+  Stager st(ctx, mem);
+  const int* d_begin = st.in(feat_begin, (size_t)B + 1);
+  const svo_feature* d_ftrs = st.in(ftrs, (size_t)n_features);
+  const int* d_want = st.in(n_desired, (size_t)B);
+  const int* d_slot0 = st.in(n_features_in_frame1, (size_t)B);
+  const double* d_Twc = st.in(T_world_cam0, (size_t)B * 7);
+  const int* d_f0 = st.in(frame0_idx, (size_t)B);
+  const int* d_f1 = st.in(frame1_idx, (size_t)B);
+  svo_stereo_result* d_res = st.out(results, (size_t)n_features);
+  svo_stereo_stats* d_stats = st.out(stats, (size_t)B);
+  // per-entry frame indices (entry -> pair) and the shared transformation / depth triple, built on the device side of the call
+  const double h_shared[10] = {T_f1f0[0], T_f1f0[1], T_f1f0[2], T_f1f0[3], T_f1f0[4], T_f1f0[5], T_f1f0[6], mean_depth_inv, min_depth_inv,
+                               max_depth_inv};
+  double* d_shared = (double*)st.scratch(sizeof(h_shared));
+  int* d_e0 = (int*)st.scratch(sizeof(int) * (size_t)(n_features > 0 ? n_features : 1));
+  int* d_e1 = (int*)st.scratch(sizeof(int) * (size_t)(n_features > 0 ? n_features : 1));
+  svo_match_out* d_match = (svo_match_out*)st.scratch(sizeof(svo_match_out) * (size_t)(n_features > 0 ? n_features : 1));
+  if (st.failed() || !d_shared || !d_e0 || !d_e1 || !d_match) return st.finish();
+  SVO_CUDA_TRY(ctx, cudaMemcpyAsync(d_shared, h_shared, sizeof(h_shared), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_features > 0) {
+    stereo_entry_frames_kernel<<<B, 128, 0, ctx->stream>>>(d_begin, d_f0, d_f1, d_e0, d_e1);
+    SVO_LAUNCH_CHECK(ctx);
+    MatchParams P;
+    memset(&P, 0, sizeof(P));
+    P.ref_pyr = makeView(pyr0);
+    P.cur_pyr = makeView(pyr1);
+    P.cam_ref = *cam0;
+    P.cam_cur = *cam1;
+    P.ref_frame_idx = d_e0;
+    P.cur_frame_idx = d_e1;
+    P.T_cur_ref = d_shared;
+    P.T_idx = nullptr;
+    P.M = n_features;
+    P.ftrs = d_ftrs;
+    P.depth = d_shared + 7;
+    P.depth_shared = 1;
+    P.align1d_from_type = 1;
+    P.opt = *mopt;
+    P.out = d_match;
+    match_kernel<1><<<(n_features + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
+    SVO_LAUNCH_CHECK(ctx);
+  }
+  stereo_commit_kernel<<<B, 256, 0, ctx->stream>>>(d_match, d_ftrs, d_begin, d_want, d_slot0, d_Twc, d_res, d_stats);
+  SVO_LAUNCH_CHECK(ctx);
+  return st.finish();
 }
 
 }  // extern "C"

@@ -6,7 +6,8 @@ configs[4]) — every stage a C-ABI call on device-resident arrays, no host roun
  -> Reprojector::reprojectFrames per camera           svo_cuda_reproject_match      (frame_handler_base.cpp:646-743)
  -> PoseOptimizer::run on the matched features        svo_cuda_pose_optimize        (frame_handler_base.cpp:746-790)
  -> DepthFilter::updateSeeds of the last keyframe     svo_cuda_update_seeds         (frame_handler_stereo.cpp:82)
- -> FastDetector on the new left frame                svo_cuda_fast_detect          (depth_filter.cpp:255-365, new keyframe)
+ -> FastGradDetector on the new left frame            svo_cuda_fastgrad_detect      (depth_filter.cpp:255-365, new keyframe; the
+                                                                                      default detector, svo_factory.cpp:292-295)
 
 The per-pair units are independent, so a batch shards over GPUs by contiguous blocks of pairs (shard.partition) with no
 collective in the path. PyTorch only holds the device arrays and reshapes the aligner's poses into the reprojector's input.
@@ -171,7 +172,9 @@ class StereoFrontendBatch:
         self.mopt, self.dopt = capi.matcher_options(), capi.depth_filter_options()
         # ---- detector
         self.det_opt = capi.detector_options()
+        self.threshold_secondary = 100
         self.d_corners = torch.zeros(B * self.n_cells * capi.CORNER_DTYPE.itemsize, dtype=torch.uint8, device=device)
+        self.d_edgelets = torch.zeros_like(self.d_corners)
         torch.cuda.synchronize(device)   # the uploads above ran on torch's default stream
 
     def release(self):
@@ -179,7 +182,7 @@ class StereoFrontendBatch:
         self.torch.cuda.synchronize(self.dev)
         self.ctx.set_stream(0)
 
-    STAGES = ("pyramid", "sparse_align", "reproject", "pose_optimize", "update_seeds", "fast_detect")
+    STAGES = ("pyramid", "sparse_align", "reproject", "pose_optimize", "update_seeds", "fastgrad_detect")
 
     def _imu_pose(self, T_f_w0):
         """T_imu_world = T_imu_cam0 * T_f_w of the left camera ([B,7] quaternion + translation), on the device."""
@@ -235,7 +238,8 @@ class StereoFrontendBatch:
                                               self.seed_mu_range, self.seed_obs_frame, self.seed_obs_T, self.seed_T, self.mopt, self.dopt,
                                               ref_frame_idx=self.seed_ref_idx, want_match_results=False)
         mark(4)
-        capi.fast_detect(self.ctx, self.cur, self.det_opt, first=0, count=B, corners_out=self.d_corners)
+        capi.fastgrad_detect(self.ctx, self.cur, self.det_opt, self.threshold_secondary, first=0, count=B, corners_out=self.d_corners,
+                             edgelets_out=self.d_edgelets)
         mark(5)
 
     def results(self):
@@ -250,4 +254,5 @@ class StereoFrontendBatch:
                     pose_opt_outlier=self.d_po_outlier.cpu().numpy(), pose_opt_T0=self.po_T0.cpu().numpy(),
                     pose_opt_has=self.po_has.cpu().numpy(), pose_opt_xyz=self.po_xyz.cpu().numpy(),
                     corners=self.d_corners.cpu().numpy().view(capi.CORNER_DTYPE).reshape(self.B, self.n_cells),
+                    edgelets=self.d_edgelets.cpu().numpy().view(capi.CORNER_DTYPE).reshape(self.B, self.n_cells),
                     entry_begin=self.entry_begin.cpu().numpy())

@@ -22,6 +22,9 @@ detect_ref_golden.npz outputs of the REFERENCE's own detectors (feature_detectio
                       oracle/shim/shim_cv_imgproc.cpp) on tests/helpers.py:DETECT_CASES: pins rows a5, a6 and f2.
 cv_imgproc_golden.npz outputs of the REAL OpenCV (python module cv2, version stored inside) for GaussianBlur(3x3, sigma 0) and
                       Scharr(8U -> 16S) on seeded images: pins the two imgproc restatements (oracle + shim) the edgelet detector uses.
+stereo_tri_ref_golden.npz what the REFERENCE's own StereoTriangulation::compute (stereo_triangulation.cpp compiled into
+                      libfrontend_ref.so, with its detectors, matcher and std::random_shuffle after srand(seed)) leaves in both frames on
+                      tests/helpers.py:STEREO_TRI_CASES, plus the visiting orders: pins row f3 (stereo part).
 klt_ref_golden.npz    outputs of the REFERENCE's own alignPyr2D (libdirect_ref.so) on the cases of tests/test_klt_cpu.py.
 Usage: python tests/golden/make_golden.py
 """
@@ -147,6 +150,14 @@ def reproject_golden():
     print("reproject_ref_golden.npz", os.path.getsize(os.path.join(HERE, "reproject_ref_golden.npz")))
 
 
+def stereo_tri_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_frontend_lib() is not None
+    np.savez_compressed(os.path.join(HERE, "stereo_tri_ref_golden.npz"), **helpers.stereo_tri_reference(orc))
+    print("wrote stereo_tri_ref_golden.npz")
+
+
 def detect_golden():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
@@ -179,6 +190,7 @@ if __name__ == "__main__":
         sys.exit(0)
     detect_golden()
     cv_imgproc_golden()
+    stereo_tri_golden()
     pose_opt_golden()
     reproject_golden()
     klt_golden()

@@ -385,3 +385,53 @@ def assert_features_equal(a, b, tag=""):
     ka = sorted(zip(a["score"], a["px"][:, 0], a["px"][:, 1], a["level"], a["grad"][:, 0], a["grad"][:, 1]))
     kb = sorted(zip(b["score"], b["px"][:, 0], b["px"][:, 1], b["level"], b["grad"][:, 0], b["grad"][:, 1]))
     assert ka == kb, tag
+
+
+# ---- f3: StereoTriangulation::compute ------------------------------------------------------------------------------------------------
+# (scene seed, srand seed, detector type, triangulate_n_features, mean / min / max inverse depth)
+STEREO_TRI_CASES = [(81, 5, 2, 120, 1 / 3.0, 1.0, 1 / 50.0),    # the defaults on the FastGrad detector: stops after 120 successes
+                    (82, 9, 0, 1000, 1 / 3.0, 1.0, 1 / 50.0),   # FAST only, more wanted than exist: every feature is tried
+                    (83, 3, 5, 40, 1 / 3.0, 1.0, 1 / 50.0),     # edgelets only (align_1d for every feature)
+                    (84, 7, 2, 200, 1 / 2.0, 1 / 1.5, 1 / 4.2)]  # a depth range that cuts part of the scene off: many failures
+
+
+def stereo_tri_frames(orc, case, keep):
+    d, s1 = stereo_case(case[0])
+    p0, p1 = orc.create_img_pyramid(d["ref_img"], 5), orc.create_img_pyramid(s1["ref_img"], 5)
+    f0 = orc.make_frame(p0, d["cam"], d["T_cam_imu"], d["T_imu_world_ref"], keep=keep)
+    f1 = orc.make_frame(p1, d["cam"], s1["T_cam_imu"], d["T_imu_world_ref"], keep=keep)
+    return d, s1, p0, p1, f0, f1
+
+
+def stereo_tri_entries(orc, case, d, p0, order):
+    """frame0's detected features (the oracle's detector, identical to the reference's) in the visiting order `order`."""
+    det = orc.detect_features(case[2], p0)
+    f = synth.cam_backproject(d["cam"], det["px"][order])
+    f = f / np.linalg.norm(f, axis=1, keepdims=True)
+    return det, f
+
+
+def stereo_tri_reference(orc):
+    """The reference's own StereoTriangulation::compute on STEREO_TRI_CASES (oracle/_ref/libfrontend_ref.so) + the visiting orders."""
+    out = {}
+    for i, case in enumerate(STEREO_TRI_CASES):
+        keep = []
+        d, s1, p0, p1, f0, f1 = stereo_tri_frames(orc, case, keep)
+        r = orc.ref_stereo_triangulation_compute(f0, f1, case[2], 10.0, 100.0, case[3], case[4], case[5], case[6], seed=case[1])
+        n_c = int((r["type0"] == 7).sum())
+        out[f"order_{i}"] = orc.ref_stereo_shuffle_order(case[1], 0, n_c, r["n0"])
+        for k, v in r.items():
+            out[f"{k}_{i}"] = np.asarray(v)
+    return out
+
+
+def assert_stereo_matches_reference(res, order, g, i, tol=1e-9):
+    """Per-entry results (oracle or CUDA) against what the reference's compute() left in frame1."""
+    ok = res[res["status"] == 2]
+    assert len(ok) == int(g[f"n1_{i}"]), (i, len(ok), int(g[f"n1_{i}"]))
+    assert np.array_equal(order[res["status"] == 2], g[f"ref_index1_{i}"]), i   # the same frame0 features, in the same order
+    assert np.array_equal(ok["slot"], np.arange(len(ok))) and np.array_equal(ok["level"], g[f"level1_{i}"]) and np.array_equal(ok["type"], g[f"type1_{i}"])
+    np.testing.assert_allclose(ok["px_cur"], g[f"px1_{i}"], rtol=0, atol=1e-3)   # sub-pixel results within 1e-3 px (north_star)
+    np.testing.assert_allclose(ok["f_cur"], g[f"f1_{i}"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(ok["grad_cur"], g[f"grad1_{i}"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(ok["xyz_world"], g[f"xyz1_{i}"], rtol=1e-4, atol=1e-6)

@@ -40,6 +40,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.MatcherOptions) == sz("svo_matcher_options")
     assert C.sizeof(capi.DepthFilterOptions) == sz("svo_depth_filter_options")
     assert C.sizeof(capi.DetectorOptions) == sz("svo_detector_options")
+    assert capi.STEREO_RESULT_DTYPE.itemsize == sz("svo_stereo_result") and capi.STEREO_STATS_DTYPE.itemsize == sz("svo_stereo_stats")
     assert sz("nope") == -1
 
 

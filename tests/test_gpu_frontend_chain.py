@@ -1,6 +1,6 @@
 """GPU parity test of the whole batched stereo front-end (BASELINE.json configs[4]: detect + sparse align + feature align +
 depth filter): svo_pro_universal_b200.frontend.StereoFrontendBatch chains pyramid -> 2-camera SparseImgAlign -> Reprojector ->
-DepthFilter::updateSeeds -> FAST on device-resident arrays; every stage is compared with the oracle on the same inputs (the
+DepthFilter::updateSeeds -> FastGrad detector (FAST + edgelets) on device-resident arrays; every stage is compared with the oracle on the same inputs (the
 oracle's reprojection stage is fed the poses the aligner produced, so that each stage is checked on identical inputs).
 Tolerances: poses 1e-4 rad / 1e-4 m (measured ~1e-12), sub-pixel 1e-3 px, seed states 1e-4 relative, corners bit-exact."""
 import numpy as np
@@ -95,11 +95,15 @@ def test_stereo_frontend_chain_matches_oracle(ctx, orc):
         assert np.array_equal(out["pose_opt_outlier"][lo:hi], outl_po) and pg["n_meas"] > 200
         dq, dt = helpers.pose_diff(synth.se3_mul(sc["T_cam_imu"][0], pg["T_imu_world"]), T_true)   # still at the true pose
         assert dq < 2e-3 and dt < 5e-3
-        # ---- FAST detector on the new left frame
+        # ---- FastGrad detector on the new left frame: FAST corners, then edgelets in the cells without a corner
         co = orc.fast_detector(sc["imgs"]["c0"])
         cg = out["corners"][i]
         for k in ("x", "y", "level", "score"):
             assert np.array_equal(cg[k], co[k]), (i, k)
+        eo = orc.edgelet_detector_v2(orc.create_img_pyramid(sc["imgs"]["c0"], 5), 100, 8, 30, (co["score"] > 10).astype(np.uint8))
+        eg = out["edgelets"][i]
+        for k in ("x", "y", "level", "score", "angle"):
+            assert np.array_equal(eg[k], eo[k]), (i, k)
     assert n_match_total > 100 * B
     # ---- DepthFilter::updateSeeds: the seeds of every left reference frame against the new left frame
     p = 0

@@ -1,5 +1,5 @@
 """BASELINE.json configs[4]: the full front-end batch (pyramid + 2-camera sparse align + Reprojector feature alignment + depth
-filter + FAST detector) on --pairs synthetic stereo frame pairs, sharded over the ranks of a torchrun launch by contiguous
+filter + FastGrad detector) on --pairs synthetic stereo frame pairs, sharded over the ranks of a torchrun launch by contiguous
 blocks of pairs (strong scaling: the total is fixed), no collective inside the path; one JSON line on rank 0.
     python tools/bench_frontend.py --pairs 8192
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_frontend.py --pairs 8192
@@ -57,7 +57,7 @@ def cpu_chain(scenes, seconds=6.0):
         oft = orc.make_features(sc["seed_px"], sc["seed_f"], np.tile([1.0, 0.0], (ns, 1)), np.full(ns, 1, np.int32), np.zeros(ns, np.int32))
         orc.update_seeds(rfs[0], [cfs[0]], sc["T_cur_ref_gt"].reshape(1, 7), oft, np.full(ns, 1, np.uint8), sc["seed_state"].copy(),
                          sc["seed_mu_range"], orc.default_matcher_options())
-        orc.fast_detector(sc["imgs"]["c0"])
+        orc.detect_features(orc.DETECTOR_FAST_GRAD, pyr_c[0])
         n += 1
     return n / (time.perf_counter() - t0)
 
@@ -111,7 +111,7 @@ def main():
         assert rank != 0 or g.shape == (args.pairs, 7)
     if rank == 0:
         cpu = cpu_chain(scenes)
-        print(json.dumps({"path": "configs[4]: full front-end batch (pyramid + stereo sparse align + Reprojector + pose optimizer + depth filter + FAST)",
+        print(json.dumps({"path": "configs[4]: full front-end batch (pyramid + stereo sparse align + Reprojector + pose optimizer + depth filter + FastGrad detector)",
                           "config": f"{args.pairs} synthetic stereo frame pairs ({args.unique} unique scenes tiled; every frame resident in HBM: "
                                     f"{4 * (hi - lo) * 483360 / 1e9:.1f} GB of pyramids per GPU), 180 + 150 features, 120 seeds per pair",
                           "n_gpus": world, "stereo_pairs_per_s": args.pairs / (ms * 1e-3), "ms_per_step": ms, "scaling": "strong",
