@@ -833,6 +833,24 @@ void FastGradDetector::detect(const b200::GpuPyramid& gpu, const size_t max_n_fe
   resetGrid();
 }
 
+// frame_utils::computeNormalizedBearingVectors (frame.cpp:427-439) for one keypoint: f = normalize(backProject3(px)); <= n_cells
+// keypoints per keyframe, host glue (pinhole_projection.hpp:30-41, radial_tangential_distortion.h:80-95)
+static BearingVector normalizedBearing(const svo_camera& cm, const Keypoint& px) {
+  double x = (px[0] - cm.cx) * (1.0 / cm.fx), y = (px[1] - cm.cy) * (1.0 / cm.fy);
+  if (cm.distortion) {
+    const double x0 = x, y0 = y;
+    for (int it = 0; it < 5; ++it) {
+      const double xx = x * x, yy = y * y, xy = x * y, xy2 = 2 * xy, r2 = xx + yy;
+      const double icdist = 1.0 / (1.0 + (cm.k1 + cm.k2 * r2) * r2);
+      const double ddx = cm.p1 * xy2 + cm.p2 * (r2 + 2.0 * xx), ddy = cm.p2 * xy2 + cm.p1 * (r2 + 2.0 * yy);
+      x = (x0 - ddx) * icdist;
+      y = (y0 - ddy) * icdist;
+    }
+  }
+  const double n = std::sqrt(x * x + y * y + 1.0);
+  return {x / n, y / n, 1.0 / n};
+}
+
 void AbstractDetector::detect(const FramePtr& frame) {
   // feature_detection.cpp:40-50: detect into the frame's columns, then frame_utils::computeNormalizedBearingVectors
   const size_t n_old = frame->px_vec_.size();
@@ -841,23 +859,103 @@ void AbstractDetector::detect(const FramePtr& frame) {
   for (size_t i = n_old; i < frame->px_vec_.size(); ++i) {
     frame->depth_vec_.push_back(-1.0);
     frame->invmu_sigma2_a_b_vec_.push_back({0, 0, 0, 0});
-    // frame_utils::computeNormalizedBearingVectors (frame.cpp:427-439): f = normalize(backProject3(px)); <= n_cells keypoints
-    // per keyframe, host glue (pinhole_projection.hpp:30-41, radial_tangential_distortion.h:80-95)
-    double x = (frame->px_vec_[i][0] - cm.cx) * (1.0 / cm.fx), y = (frame->px_vec_[i][1] - cm.cy) * (1.0 / cm.fy);
-    if (cm.distortion) {
-      const double x0 = x, y0 = y;
-      for (int it = 0; it < 5; ++it) {
-        const double xx = x * x, yy = y * y, xy = x * y, xy2 = 2 * xy, r2 = xx + yy;
-        const double icdist = 1.0 / (1.0 + (cm.k1 + cm.k2 * r2) * r2);
-        const double ddx = cm.p1 * xy2 + cm.p2 * (r2 + 2.0 * xx), ddy = cm.p2 * xy2 + cm.p1 * (r2 + 2.0 * yy);
-        x = (x0 - ddx) * icdist;
-        y = (y0 - ddy) * icdist;
-      }
-    }
-    const double n = std::sqrt(x * x + y * y + 1.0);
-    frame->f_vec_.push_back({x / n, y / n, 1.0 / n});
+    frame->f_vec_.push_back(normalizedBearing(cm, frame->px_vec_[i]));
   }
   frame->num_features_ = frame->px_vec_.size();
+}
+
+// ---- StereoTriangulation ------------------------------------------------------------------------------------------------------------
+// libstdc++'s std::random_shuffle(first, last) (bits/stl_algo.h; removed from C++17 but what the reference's build runs):
+// for i = 1 .. n-1: swap(a[i], a[std::rand() % (i + 1)]).
+template <class It>
+static void randomShuffleLikeReference(It first, It last) {
+  if (first == last) return;
+  for (It i = first + 1; i != last; ++i) {
+    It j = first + std::rand() % ((i - first) + 1);
+    if (i != j) std::iter_swap(i, j);
+  }
+}
+
+void StereoTriangulation::compute(const FramePtr& frame0, const FramePtr& frame1) {
+  if (frame0->numLandmarks() >= options_.triangulate_n_features) return;  // :27-32
+  // detect new features (:34-47), bearing vectors (:49-51), append to frame0 (:53-66)
+  Keypoints new_px; Scores new_scores; Levels new_levels; Gradients new_grads; FeatureTypes new_types;
+  const size_t max_n_features = feature_detector_->grid_.size();
+  feature_detector_->detect(b200::ensureGpu(*frame0), max_n_features, new_px, new_scores, new_levels, new_grads, new_types);
+  if (new_px.empty()) return;
+  const size_t n_old = frame0->numFeatures(), n_new = new_px.size();
+  frame0->landmark_vec_.resize(n_old, nullptr);
+  frame0->seed_ref_vec_.resize(n_old);
+  for (size_t i = 0; i < n_new; ++i) {
+    frame0->px_vec_.push_back(new_px[i]);
+    frame0->f_vec_.push_back(normalizedBearing(frame0->cam_->model, new_px[i]));
+    frame0->grad_vec_.push_back(new_grads[i]);
+    frame0->score_vec_.push_back(new_scores[i]);
+    frame0->level_vec_.push_back(new_levels[i]);
+    frame0->type_vec_.push_back(new_types[i]);
+    frame0->depth_vec_.push_back(-1.0);
+    frame0->invmu_sigma2_a_b_vec_.push_back({0, 0, 0, 0});
+    frame0->landmark_vec_.push_back(nullptr);
+    frame0->seed_ref_vec_.push_back(SeedRef());
+  }
+  frame0->num_features_ += n_new;
+  // visiting order (:68-79)
+  std::vector<size_t> indices(n_new);
+  std::iota(indices.begin(), indices.end(), n_old);
+  const long n_corners = std::count_if(new_types.begin(), new_types.end(), [](const FeatureType& t) { return t == FeatureType::kCorner; });
+  randomShuffleLikeReference(indices.begin(), indices.begin() + n_corners);
+  randomShuffleLikeReference(indices.begin() + n_corners, indices.end());
+  const size_t n_desired = options_.triangulate_n_features - frame0->numLandmarks();
+  // the matching loop (:87-133) in one device call
+  std::vector<svo_feature> ftrs(n_new);
+  for (size_t k = 0; k < n_new; ++k) {
+    const size_t i = indices[k];
+    svo_feature q{};
+    q.px[0] = frame0->px_vec_[i][0]; q.px[1] = frame0->px_vec_[i][1];
+    for (int a = 0; a < 3; ++a) q.f[a] = frame0->f_vec_[i][a];
+    q.grad[0] = frame0->grad_vec_[i][0]; q.grad[1] = frame0->grad_vec_[i][1];
+    q.type = int(frame0->type_vec_[i]); q.level = frame0->level_vec_[i];
+    ftrs[k] = q;
+  }
+  Matcher matcher;
+  matcher.options_.max_epi_search_steps = 500;
+  matcher.options_.subpix_refinement = true;
+  const svo_matcher_options mo = matcher.cOptions();
+  double T_f1f0[7], T_w_c0[7];
+  (frame1->T_cam_imu_ * frame0->T_cam_imu_.inverse()).toArray(T_f1f0);  // frame1->T_cam_body_ * frame0->T_body_cam_ (:92)
+  frame0->T_f_w_.inverse().toArray(T_w_c0);
+  const int begin[2] = {0, int(n_new)}, want = int(n_desired), first_slot = int(frame1->numFeatures()), zero = 0;
+  std::vector<svo_stereo_result> res(n_new);
+  svo_stereo_stats stats{};
+  b200::check(svo_cuda_stereo_triangulate(b200::context(), b200::ensureGpu(*frame0).handle(), b200::ensureGpu(*frame1).handle(), &zero, &zero,
+                                          &frame0->cam_->model, &frame1->cam_->model, T_f1f0, T_w_c0, 1, begin, int(n_new), ftrs.data(), &want,
+                                          &first_slot, options_.mean_depth_inv, options_.min_depth_inv, options_.max_depth_inv, &mo,
+                                          res.data(), &stats, SVO_MEM_HOST), "svo_cuda_stereo_triangulate");
+  // bookkeeping of both frames (:102-129), in visiting order = slot order
+  frame1->landmark_vec_.resize(frame1->numFeatures(), nullptr);
+  frame1->seed_ref_vec_.resize(frame1->numFeatures());
+  for (size_t k = 0; k < n_new; ++k) {
+    const svo_stereo_result& r = res[k];
+    if (r.status != SVO_STEREO_SUCCESS) continue;
+    const size_t i_ref = indices[k];
+    auto new_point = std::make_shared<Point>();
+    new_point->pos_ = {r.xyz_world[0], r.xyz_world[1], r.xyz_world[2]};
+    frame0->landmark_vec_[i_ref] = new_point;
+    new_point->obs_.emplace_back(frame0, i_ref);
+    const size_t i_cur = frame1->num_features_;
+    frame1->type_vec_.push_back(FeatureType(r.type));
+    frame1->level_vec_.push_back(r.level);
+    frame1->px_vec_.push_back({r.px_cur[0], r.px_cur[1]});
+    frame1->f_vec_.push_back({r.f_cur[0], r.f_cur[1], r.f_cur[2]});
+    frame1->score_vec_.push_back(frame0->score_vec_[i_ref]);
+    frame1->grad_vec_.push_back({r.grad_cur[0], r.grad_cur[1]});
+    frame1->depth_vec_.push_back(-1.0);
+    frame1->invmu_sigma2_a_b_vec_.push_back({0, 0, 0, 0});
+    frame1->landmark_vec_.push_back(new_point);
+    frame1->seed_ref_vec_.push_back(SeedRef());
+    new_point->obs_.emplace_back(frame1, i_cur);
+    frame1->num_features_++;
+  }
 }
 
 }  // namespace svo

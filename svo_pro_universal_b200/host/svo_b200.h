@@ -123,6 +123,7 @@ struct Frame {
   Transformation T_imu_world() const { return T_cam_imu_.inverse() * T_f_w_; }
   std::array<double, 3> pos() const { return T_f_w_.inverse().t; }  // T_world_cam().getPosition()
   bool isValidLandmark(size_t i) const { return i < landmark_vec_.size() && landmark_vec_[i] != nullptr; }
+  size_t numLandmarks() const { size_t n = 0; for (const PointPtr& p : landmark_vec_) n += p != nullptr; return n; }  // frame.h:176-181
   size_t numFeatures() const { return num_features_; }
   size_t numTrackedFeatures() const;  // frame.h:153-163
   const Transformation& T_cam_imu() const { return T_cam_imu_; }
@@ -420,6 +421,28 @@ class Reprojector {  // reprojector.h:77-166
   bool doesFrameHaveEnoughFeatures(const FramePtr& frame) const {
     return options_.max_n_features_per_frame > 0 && frame->numTrackedFeatures() >= options_.max_n_features_per_frame;
   }
+};
+
+// ---- (f3) StereoTriangulation ---------------------------------------------------------------------------------------------------
+struct StereoTriangulationOptions {  // src/svo/include/svo/stereo_triangulation.h:12-18
+  size_t triangulate_n_features = 120;
+  double mean_depth_inv = 1.0 / 3.0;
+  double min_depth_inv = 1.0 / 1.0;
+  double max_depth_inv = 1.0 / 50.0;
+};
+
+class StereoTriangulation {  // stereo_triangulation.h:20-37
+ public:
+  typedef std::shared_ptr<StereoTriangulation> Ptr;
+  StereoTriangulationOptions options_;
+  AbstractDetector::Ptr feature_detector_;
+  StereoTriangulation(const StereoTriangulationOptions& options, const AbstractDetector::Ptr& feature_detector)
+      : options_(options), feature_detector_(feature_detector) {}
+  // src/svo/src/stereo_triangulation.cpp:23-139: detects new features in frame0, visits them in the order of the reference's two
+  // std::random_shuffle calls (libstdc++'s std::rand() based algorithm, corners first), matches them along the epipolar line in
+  // frame1 (ONE svo_cuda_stereo_triangulate call for all of them) and creates a Point + the frame1 feature for the first
+  // triangulate_n_features - numLandmarks() successes.
+  void compute(const FramePtr& frame0, const FramePtr& frame1);
 };
 
 // ---- (f4) PoseOptimizer ---------------------------------------------------------------------------------------------------------

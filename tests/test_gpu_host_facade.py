@@ -212,3 +212,38 @@ def test_cpp_pose_optimizer_facade_matches_reference(tmp_path):
         np.testing.assert_allclose(out[8:11], gold[f"p{ci}_stats"][:3], rtol=1e-6)
         assert int(out[11]) == int(gold[f"p{ci}_stats"][3])
         assert np.array_equal(out[12:12 + N].astype(np.uint8), gold[f"p{ci}_outlier"]), ci
+
+
+def test_stereo_triangulation_facade_matches_reference(orc, tmp_path):
+    """svo::StereoTriangulation::compute through makeDetector + the facade (C++ driver) leaves in both frames what the REFERENCE's
+    own compiled compute() left there for the same srand seed (tests/golden/stereo_tri_ref_golden.npz)."""
+    import helpers
+    g = np.load(os.path.join(ROOT, "tests", "golden", "stereo_tri_ref_golden.npz"))
+    for i, case in enumerate(helpers.STEREO_TRI_CASES):
+        d, s1 = helpers.stereo_case(case[0])
+        cam = d["cam"]
+        fin, fout = tmp_path / f"st_in_{i}.bin", tmp_path / f"st_out_{i}.bin"
+        with open(fin, "wb") as f:
+            np.array([5, case[2], case[3], case[1], 752, 480], np.int32).tofile(f)
+            np.array([cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")], np.float64).tofile(f)
+            np.array([cam["width"], cam["height"], cam["distortion"]], np.int32).tofile(f)
+            for T in (d["T_cam_imu"], s1["T_cam_imu"], d["T_imu_world_ref"]):
+                np.asarray(T, np.float64).tofile(f)
+            np.array(case[4:7], np.float64).tofile(f)
+            d["ref_img"].tofile(f); s1["ref_img"].tofile(f)
+        r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "stereo_tri_driver"), str(fin), str(fout)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = np.fromfile(fout, np.float64)
+        n0, n1 = int(out[0]), int(out[1])
+        assert n0 == int(g[f"n0_{i}"]) and n1 == int(g[f"n1_{i}"]), (i, n0, n1)
+        a = out[2:2 + 4 * n0].reshape(n0, 4)
+        b = out[2 + 4 * n0:].reshape(n1, 15)
+        assert np.array_equal(a[:, :2], g[f"px0_{i}"]) and np.array_equal(a[:, 2], g[f"type0_{i}"])
+        assert np.array_equal(b[:, 13].astype(np.int32), g[f"ref_index1_{i}"])            # the same frame0 features in the same slots
+        assert np.array_equal(np.flatnonzero(a[:, 3]), np.sort(g[f"ref_index1_{i}"]))     # ... and they own the new landmarks
+        assert (b[:, 14] == 2).all()                                                     # observed by both frames
+        assert np.array_equal(b[:, 7], g[f"level1_{i}"]) and np.array_equal(b[:, 8], g[f"type1_{i}"]) and np.array_equal(b[:, 9], g[f"score1_{i}"])
+        np.testing.assert_allclose(b[:, 0:2], g[f"px1_{i}"], rtol=0, atol=1e-3)
+        np.testing.assert_allclose(b[:, 2:5], g[f"f1_{i}"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(b[:, 5:7], g[f"grad1_{i}"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(b[:, 10:13], g[f"xyz1_{i}"], rtol=1e-4, atol=1e-6)

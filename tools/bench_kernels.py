@@ -273,6 +273,44 @@ def main():
                              "frac": (n_meas * 90 + 384) * BP / (ms_p * 1e-3) / 1e9 / PEAK,
                              "note": "compulsory bytes once per bundle; the features are re-read from L1/L2 every iteration (FP64 issue bound)"},
                 "cpu_baseline": {"bundles_per_s_single_thread": cpu_p, "kind": "port (oracle; pinned to the reference's compiled pose_optimizer.cpp)"}})
+    # ---- (f3) StereoTriangulation::compute: every detected feature of the left frame matched along the epipolar line (500 steps) ----
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers  # noqa: E402
+    BS, NU2 = 512, 4
+    keepS, pairs = [], []
+    for c in helpers.STEREO_TRI_CASES:
+        dS, s1S, p0S, p1S, f0S, f1S = helpers.stereo_tri_frames(orc, c, keepS)
+        detS = orc.detect_features(orc.DETECTOR_FAST_GRAD, p0S)
+        fS = synth.cam_backproject(dS["cam"], detS["px"]); fS /= np.linalg.norm(fS, axis=1, keepdims=True)
+        pairs.append(dict(d=dS, s1=s1S, f0=f0S, f1=f1S, det=detS, f=fS,
+                          ft=capi.make_features(detS["px"], fS, detS["grad"], detS["type"], detS["level"]),
+                          oft=orc.make_features(detS["px"], fS, detS["grad"], detS["type"], detS["level"])))
+    p0 = capi.Pyramid(ctx, NU2, 752, 480, 5); p1 = capi.Pyramid(ctx, NU2, 752, 480, 5)
+    p0.upload(np.stack([q["d"]["ref_img"] for q in pairs])); p1.upload(np.stack([q["s1"]["ref_img"] for q in pairs])); p0.build(); p1.build()
+    sid = np.arange(BS) % NU2
+    beginS = np.concatenate([[0], np.cumsum([len(pairs[i]["ft"]) for i in sid])]).astype(np.int32)
+    ftS = np.concatenate([pairs[i]["ft"] for i in sid])
+    TwcS = np.stack([synth.se3_inv(synth.se3_mul(pairs[i]["d"]["T_cam_imu"], pairs[i]["d"]["T_imu_world_ref"])) for i in sid])
+    T_f1f0 = synth.se3_mul(pairs[0]["s1"]["T_cam_imu"], synth.se3_inv(pairs[0]["d"]["T_cam_imu"]))
+    camS = capi.Camera.from_dict(pairs[0]["d"]["cam"])
+    moS = capi.matcher_options(max_epi_search_steps=500, subpix_refinement=1)
+    d_args = [t(TwcS), t(beginS), t(ftS.view(np.uint8)), t(np.full(BS, 120, np.int32)), t(np.zeros(BS, np.int32))]
+    d_resS = torch.zeros(len(ftS) * capi.STEREO_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_stS = torch.zeros(BS * capi.STEREO_STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    ms_st = timed(lambda: capi.stereo_triangulate(ctx, p0, p1, camS, camS, T_f1f0, *d_args, moS, frame0_idx=t(sid.astype(np.int32)),
+                                                  frame1_idx=t(sid.astype(np.int32)), results=d_resS, stats=d_stS), stream, reps=5)
+    stS = d_stS.cpu().numpy().view(capi.STEREO_STATS_DTYPE)
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 4.0:
+        q = pairs[reps % NU2]
+        orc.stereo_triangulate(q["f0"], q["f1"], q["oft"], 120); reps += 1
+    cpu_st = reps / (time.perf_counter() - t0)
+    out.append({"path": "f3: StereoTriangulation::compute (epipolar match of the detected features, 500 steps, first 120 successes)",
+                "config": f"{BS} stereo pairs x ~{len(ftS) // BS} detected features ({NU2} unique pairs tiled), 11 cm baseline",
+                "pairs_per_s": BS / (ms_st * 1e-3), "features_per_s": len(ftS) / (ms_st * 1e-3), "ms": ms_st,
+                "mean_triangulated": float(stS["n_succeeded"].mean()),
+                "note": "every feature is matched speculatively; the sequential stop of the reference is applied by the commit kernel",
+                "cpu_baseline": {"pairs_per_s_single_thread": cpu_st, "kind": "port (oracle, stops after 120 successes like the reference)"}})
     for o in out:
         print(json.dumps(o))
 
