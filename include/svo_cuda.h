@@ -434,6 +434,16 @@ int svo_cuda_pose_optimize(svo_cuda_ctx* ctx, int n_cams, const svo_camera* cams
                            const int* feat_cam, const double* xyz_world, const uint8_t* has_xyz, const double* prior_q,
                            const svo_pose_optimizer_options* opt, svo_pose_opt_result* results, uint8_t* outlier, svo_mem mem);
 
+/* Point::optimize (src/svo_common/include/svo/common/point.h:155, 170-204; src/svo_common/src/point.cpp:216-325) for P independent
+ * points, as FrameHandlerBase::optimizeStructure runs it over the landmarks of a frame (src/svo/src/frame_handler_base.cpp:785-825):
+ * point i (pos [P][3], in/out) is observed by obs_frame[o] with unit bearing obs_f[o] for o in [obs_begin[i], obs_begin[i+1]);
+ * T_f_w [n_frames][7] are the observing frames' poses. Points with fewer than two observations are left alone (:255-259).
+ * using_bearing_vector selects the unit-sphere residual (omni cameras), else the unit plane. iters_out [P] (may be NULL) receives
+ * the number of Gauss-Newton iterations started. n_obs = obs_begin[P]. */
+int svo_cuda_optimize_points(svo_cuda_ctx* ctx, int P, double* pos, const int* obs_begin, int n_obs, const int* obs_frame,
+                             const double* obs_f, int n_frames, const double* T_f_w, int n_iter, int using_bearing_vector,
+                             int* iters_out, svo_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -924,3 +924,28 @@ def ref_stereo_triangulation_compute(frame0, frame1, detector_type=DETECTOR_FAST
     a, b = n0.value, n1
     return dict(n0=a, px0=px0[:a], level0=level0[:a], type0=type0[:a], score0=score0[:a], grad0=grad0[:a], n1=b, px1=px1[:b], f1=f1[:b],
                 grad1=grad1[:b], level1=level1[:b], type1=type1[:b], score1=score1[:b], xyz1=xyz1[:b], ref_index1=ref1[:b])
+
+
+# ---- f4 (second half): Point::optimize ------------------------------------------------------------------------------------------------
+_ref_point = None
+
+
+def ref_point_lib():
+    """The reference's own point.h / point.cpp compiled against the shims (oracle/_ref/libpoint_ref.so; None if never built)."""
+    global _ref_point
+    if _ref_point is None:
+        so = os.path.join(_HERE, "_ref", "libpoint_ref.so")
+        if not os.path.exists(so):
+            return None
+        _ref_point = C.CDLL(so)
+    return _ref_point
+
+
+def point_optimize(T_f_w, f, pos, n_iter=5, using_bearing_vector=False, which="orc"):
+    """Point::optimize on one point: T_f_w [n_obs, 7], f [n_obs, 3], pos [3] -> (optimised pos, iterations started or None)."""
+    T = np.ascontiguousarray(T_f_w, np.float64).reshape(-1, 7)
+    fv = np.ascontiguousarray(f, np.float64).reshape(-1, 3)
+    p = np.array(pos, np.float64).reshape(3).copy()
+    fn = lib().orc_point_optimize if which == "orc" else ref_point_lib().ref_point_optimize
+    it = fn(len(T), _f64(T), _f64(fv), _f64(p), int(n_iter), int(bool(using_bearing_vector)))
+    return p, (it if which == "orc" else None)

@@ -12,6 +12,7 @@
 #include "orc_depth_filter.hpp"
 #include "orc_reprojector.hpp"
 #include "orc_pose_optimizer.hpp"
+#include "orc_point.hpp"
 
 using namespace orc;
 
@@ -403,6 +404,15 @@ int orc_stereo_triangulate(const orc_frame* frame0, const orc_frame* frame1, int
   }
   if (n_failed_out) *n_failed_out = n_failed;
   return n_succeeded;
+}
+
+int orc_point_optimize(int n_obs, const double* T_f_w, const double* f, double pos[3], int n_iter, int using_bearing_vector) {
+  std::vector<PointObservation> obs;
+  for (int i = 0; i < n_obs; ++i) obs.push_back(PointObservation{se3FromArray(T_f_w + 7 * i), V3{f[3 * i], f[3 * i + 1], f[3 * i + 2]}});
+  V3 p{pos[0], pos[1], pos[2]};
+  const int it = pointOptimize(obs, p, size_t(n_iter), using_bearing_vector != 0);
+  pos[0] = p.x; pos[1] = p.y; pos[2] = p.z;
+  return it;
 }
 
 int orc_find_match_direct_batch(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], int M,

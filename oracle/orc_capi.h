@@ -129,6 +129,9 @@ typedef struct {
 int orc_stereo_triangulate(const orc_frame* frame0, const orc_frame* frame1, int n, const orc_feature* ftrs, int n_desired,
                            int n_features_in_frame1, double mean_depth_inv, double min_depth_inv, double max_depth_inv,
                            orc_stereo_result* results, int* n_failed);
+/* f4 (second half): Point::optimize on one point with n_obs observations (T_f_w [n_obs][7], f [n_obs][3]); pos in/out.
+ * Returns the number of iterations started. */
+int orc_point_optimize(int n_obs, const double* T_f_w, const double* f, double pos[3], int n_iter, int using_bearing_vector);
 /* b */
 int orc_sparse_align(int n_cams, const orc_frame* ref, const orc_frame* cur, const orc_align_options* opt, orc_align_result* res);
 /* B independent problems: ref/cur hold B*n_cams frames; n_threads worker threads (one problem per task). */

@@ -33,6 +33,27 @@ enum { ComputeFullU = 4, ComputeFullV = 16, ComputeThinU = 8, ComputeThinV = 32 
 template <typename T> using aligned_allocator = std::allocator<T>;
 
 template <typename T, int R, int C, int Opt = 0, int MR = R, int MC = C, typename Enable = void> class Matrix;
+// Stands for any Eigen expression the checker never evaluates (Point::triangulateLinear's row-wise / column-wise reductions and its
+// rank-revealing QR, src/svo_common/src/point.cpp:169-213): it type-checks, and aborts when reached.
+struct ShimAny {
+  ShimAny transpose() const { std::abort(); }
+  ShimAny sum() const { std::abort(); }
+  ShimAny squaredNorm() const { std::abort(); }
+  ShimAny asDiagonal() const { std::abort(); }
+  ShimAny inverse() const { std::abort(); }
+  ShimAny rowwise() const { std::abort(); }
+  ShimAny colwise() const { std::abort(); }
+  template <typename X> ShimAny cwiseProduct(const X&) const { std::abort(); }
+  template <typename M> operator M() const { std::abort(); }
+};
+template <typename X> inline ShimAny operator*(const X&, const ShimAny&) { std::abort(); }
+template <typename X> inline ShimAny operator-(const X&, const ShimAny&) { std::abort(); }
+inline ShimAny operator-(const ShimAny&, const ShimAny&) { std::abort(); }
+template <typename M> struct ColPivHouseholderQR {  // declared for type-checking only
+  void setThreshold(double) { std::abort(); }
+  size_t rank() const { std::abort(); }
+  template <typename B> ShimAny solve(const B&) const { std::abort(); }
+};
 
 // CRTP base so that reference templates written against Eigen::MatrixBase<Derived> (occupancy_grid_2d.h:82-88) bind.
 template <typename Derived> struct MatrixBase {
@@ -281,6 +302,7 @@ class Matrix<T, R, C, Opt, MR, MC, typename std::enable_if<(R > 0 && C > 0)>::ty
   Matrix<T, (R < C ? R : C), 1> diagonal() const { Matrix<T, (R < C ? R : C), 1> v; for (int i = 0; i < (R < C ? R : C); ++i) v[i] = (*this)(i, i); return v; }
   Matrix<T, R * C, R * C> asDiagonal() const { Matrix<T, R * C, R * C> m = Matrix<T, R * C, R * C>::Zero(); for (int i = 0; i < R * C; ++i) m(i, i) = d[i]; return m; }
   LDLTSolver<T, R> ldlt() const { static_assert(R == C, "ldlt: square only"); return LDLTSolver<T, R>(*this); }
+  ColPivHouseholderQR<Matrix> colPivHouseholderQr() const { std::abort(); }
   bool isApprox(const Matrix& o, T prec = T(1e-12)) const { return (*this - o).squaredNorm() <= prec * prec * std::min(squaredNorm(), o.squaredNorm()); }
   Matrix& setRandom() { for (int i = 0; i < R * C; ++i) d[i] = T(2) * T(std::rand()) / T(RAND_MAX) - T(1); return *this; }
   friend std::ostream& operator<<(std::ostream& os, const Matrix& m) {
@@ -363,6 +385,10 @@ class Matrix<T, R, C, Opt, MR, MC, typename std::enable_if<(R < 0 || C < 0)>::ty
   DynBlockRef<Matrix> segment(int i0, int n) { return C == 1 ? DynBlockRef<Matrix>(*this, i0, 0, n, 1) : DynBlockRef<Matrix>(*this, 0, i0, 1, n); }
   void setConstant(T v) { for (int i = 0; i < r_ * c_; ++i) data()[i] = v; }
   void setConstant(int n, T v) { resize(n); setConstant(v); }
+  ShimAny transpose() const { std::abort(); }
+  ShimAny rowwise() const { std::abort(); }
+  ShimAny colwise() const { std::abort(); }
+  template <typename X> ShimAny cwiseProduct(const X&) const { std::abort(); }
   void conservativeResize(int n) { if (C == 1) conservativeResize(n, 1); else conservativeResize(r_, n); }
   void conservativeResize(NoChange_t, int c) { conservativeResize(r_, c); }
   void conservativeResize(int r, NoChange_t) { conservativeResize(r, c_); }

@@ -186,6 +186,7 @@ class Frame {
   }
 };
 
+#ifndef SVO_SHIM_REAL_POINT  // libpoint_ref.so compiles the reference's own point.h / point.cpp, which define these themselves
 inline KeypointIdentifier::KeypointIdentifier(const FramePtr& _frame, const size_t _feature_index)  // point.cpp:19-23
     : frame(_frame), frame_id(_frame->id_), keypoint_index_(_feature_index) {}
 
@@ -218,6 +219,7 @@ inline bool Point::getCloseViewObs(const Eigen::Vector3d& framepos, FramePtr& re
   if (min_cos_angle < 0.4) return false;  // observations more than 60 degrees away are useless
   return true;
 }
+#endif  // SVO_SHIM_REAL_POINT
 
 class FrameBundle {
  public:

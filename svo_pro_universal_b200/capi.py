@@ -221,7 +221,7 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
     "svo_cuda_reproject_match", "svo_cuda_pose_optimize", "svo_cuda_edgelet_detect", "svo_cuda_fastgrad_detect",
-    "svo_cuda_angle_histogram_bins", "svo_cuda_stereo_triangulate",
+    "svo_cuda_angle_histogram_bins", "svo_cuda_stereo_triangulate", "svo_cuda_optimize_points",
 ]
 
 
@@ -610,6 +610,24 @@ def stereo_triangulate(ctx, pyr0, pyr1, cam0, cam1, T_f1f0, T_world_cam0, feat_b
     ctx.check(fn(ctx._h, pyr0._h, pyr1._h, pf0, pf1, C.byref(cam0), C.byref(cam1), C.c_void_p(T_f1f0.ctypes.data), pT, B, pb, N, pf, pn, ps1,
                  mean_depth_inv, min_depth_inv, max_depth_inv, C.byref(mopt), pr, pst, kind))
     return results, stats
+
+
+def optimize_points(ctx, pos, obs_begin, obs_frame, obs_f, T_f_w, n_iter=5, using_bearing_vector=False, iters_out=None):
+    """svo_cuda_optimize_points: Point::optimize for P points; pos [P, 3] is updated in place (numpy or torch cuda). Returns iters_out."""
+    P = int(pos.shape[0])
+    n_obs, n_frames = int(obs_frame.shape[0]), int(T_f_w.shape[0])
+    if iters_out is None:
+        if _is_torch(pos) and pos.is_cuda:
+            import torch
+            iters_out = torch.zeros(P, dtype=torch.int32, device=pos.device)
+        else:
+            iters_out = np.zeros(P, np.int32)
+    (pp, pb, pfr, pf, pT, pi), kind = _ptrs(pos, obs_begin, obs_frame, obs_f, T_f_w, iters_out)
+    fn = lib().svo_cuda_optimize_points
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                   C.c_void_p, C.c_int]
+    ctx.check(fn(ctx._h, P, pp, pb, n_obs, pfr, pf, n_frames, pT, int(n_iter), int(bool(using_bearing_vector)), pi, kind))
+    return iters_out
 
 
 def pose_optimize(ctx, cams, T_cam_imu, T_imu_world, feat_begin, ftrs, feat_cam, xyz_world, has_xyz, opt, prior_q=None, results=None,

@@ -864,6 +864,66 @@ void AbstractDetector::detect(const FramePtr& frame) {
   frame->num_features_ = frame->px_vec_.size();
 }
 
+// ---- Point::optimize / optimizeStructure ------------------------------------------------------------------------------------------
+static void optimizePointsOnDevice(const std::vector<Point*>& pts, size_t n_iter, bool sphere) {
+  std::vector<double> pos, obs_f, T_f_w;
+  std::vector<int> begin{0}, obs_frame;
+  std::vector<const Frame*> frames;  // observing frames, deduplicated
+  for (Point* pt : pts) {
+    for (const KeypointIdentifier& o : pt->obs_) {
+      const FramePtr fr = o.frame.lock();
+      if (!fr) continue;  // "could not unlock weak_ptr<Frame>" (point.cpp:292): the observation is skipped
+      size_t k = 0;
+      while (k < frames.size() && frames[k] != fr.get()) ++k;
+      if (k == frames.size()) {
+        frames.push_back(fr.get());
+        double T[7];
+        fr->T_f_w_.toArray(T);
+        T_f_w.insert(T_f_w.end(), T, T + 7);
+      }
+      obs_frame.push_back(int(k));
+      const BearingVector& f = fr->f_vec_.at(o.keypoint_index_);
+      obs_f.insert(obs_f.end(), f.begin(), f.end());
+    }
+    // the reference tests obs_.size() < 2 (expired frames included): keep such a point out by giving it no observations
+    if (pt->obs_.size() < 2) { obs_frame.resize(size_t(begin.back())); obs_f.resize(size_t(begin.back()) * 3); }
+    begin.push_back(int(obs_frame.size()));
+    pos.insert(pos.end(), pt->pos_.begin(), pt->pos_.end());
+  }
+  if (pts.empty()) return;
+  b200::check(svo_cuda_optimize_points(b200::context(), int(pts.size()), pos.data(), begin.data(), int(obs_frame.size()), obs_frame.data(),
+                                       obs_f.data(), int(frames.size()), T_f_w.data(), int(n_iter), sphere ? 1 : 0, nullptr, SVO_MEM_HOST),
+              "svo_cuda_optimize_points");
+  for (size_t i = 0; i < pts.size(); ++i) pts[i]->pos_ = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+}
+
+void Point::optimize(const size_t n_iter, bool using_bearing_vector) { optimizePointsOnDevice({this}, n_iter, using_bearing_vector); }
+
+void optimizeStructure(const FrameBundle::Ptr& frames, int max_n_pts, int max_iter, bool optimize_on_sphere) {
+  if (max_n_pts == 0) return;
+  for (const FramePtr& frame : frames->frames_) {
+    std::vector<Point*> pts;
+    for (size_t i = 0; i < frame->num_features_; ++i) {
+      if (!frame->isValidLandmark(i) || isEdgelet(frame->type_vec_[i])) continue;
+      pts.push_back(frame->landmark_vec_[i].get());
+    }
+    if (max_n_pts > 0) {  // favour points that have not been optimised in a while (only an ordering in the reference, see the header)
+      const size_t n = std::min(size_t(max_n_pts), pts.size());
+      std::nth_element(pts.begin(), pts.begin() + n, pts.end(),
+                       [](const Point* l, const Point* r) { return l->last_structure_optim_ < r->last_structure_optim_; });
+    }
+    // a landmark seen twice in one frame would be optimised twice in a row by the reference; the batch runs every point once per
+    // occurrence in order, so duplicates go through separate calls
+    std::vector<Point*> batch;
+    for (Point* p : pts) {
+      if (std::find(batch.begin(), batch.end(), p) != batch.end()) { optimizePointsOnDevice(batch, size_t(max_iter), optimize_on_sphere); batch.clear(); }
+      batch.push_back(p);
+    }
+    optimizePointsOnDevice(batch, size_t(max_iter), optimize_on_sphere);
+    for (Point* p : pts) p->last_structure_optim_ = frame->id_;
+  }
+}
+
 // ---- StereoTriangulation ------------------------------------------------------------------------------------------------------------
 // libstdc++'s std::random_shuffle(first, last) (bits/stl_algo.h; removed from C++17 but what the reference's build runs):
 // for i = 1 .. n-1: swap(a[i], a[std::rand() % (i + 1)]).

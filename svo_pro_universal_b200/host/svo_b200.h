@@ -58,6 +58,7 @@ inline bool isCornerEdgeletSeed(FeatureType t) {
 }
 inline bool isConvergedCornerEdgeletSeed(FeatureType t) { return t == FeatureType::kEdgeletSeedConverged || t == FeatureType::kCornerSeedConverged; }
 inline bool isUnconvergedCornerEdgeletSeed(FeatureType t) { return t == FeatureType::kEdgeletSeed || t == FeatureType::kCornerSeed; }
+inline bool isEdgelet(FeatureType t) { return t == FeatureType::kEdgelet || t == FeatureType::kEdgeletSeed || t == FeatureType::kEdgeletSeedConverged; }
 inline bool isFixedLandmark(FeatureType t) { return t == FeatureType::kFixedLandmark; }
 inline bool isMapPoint(FeatureType t) { return t == FeatureType::kMapPoint || t == FeatureType::kMapPointSeed || t == FeatureType::kMapPointSeedConverged; }
 
@@ -86,7 +87,11 @@ struct Point {
   std::array<int, 8> last_projected_kf_id_;
   int n_failed_reproj_ = 0;
   int n_succeeded_reproj_ = 0;
+  int last_structure_optim_ = 0;  // point.h:89: frame id of the last Point::optimize
   Point() { last_projected_kf_id_.fill(-1); }
+  // Point::optimize (point.h:155; point.cpp:248-325) for this one point: ONE svo_cuda_optimize_points call with P = 1
+  // (optimizeStructure below batches all landmarks of a frame into one call).
+  void optimize(const size_t n_iter, bool using_bearing_vector = false);
   int id() const { return id_; }
 };
 using PointPtr = std::shared_ptr<Point>;
@@ -444,6 +449,11 @@ class StereoTriangulation {  // stereo_triangulation.h:20-37
   // triangulate_n_features - numLandmarks() successes.
   void compute(const FramePtr& frame0, const FramePtr& frame1);
 };
+
+// FrameHandlerBase::optimizeStructure (src/svo/src/frame_handler_base.cpp:785-825): Point::optimize for the non-edgelet landmarks of
+// every frame of the bundle — one svo_cuda_optimize_points call per frame — and last_structure_optim_ = frame id. As in the
+// reference, max_n_pts only reorders the points (its loop runs over all of them, :812-816); 0 returns at once, -1 means all.
+void optimizeStructure(const FrameBundle::Ptr& frames, int max_n_pts, int max_iter, bool optimize_on_sphere = false);
 
 // ---- (f4) PoseOptimizer ---------------------------------------------------------------------------------------------------------
 class PoseOptimizer {  // src/svo/include/svo/pose_optimizer.h:20-103

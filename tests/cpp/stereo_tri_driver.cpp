@@ -66,6 +66,15 @@ int main(int argc, char** argv) {
       out.push_back(double(p->obs_.at(0).keypoint_index_));
       out.push_back(double(p->obs_.size()));
     }
+    // FrameHandlerBase::optimizeStructure on the bundle: every new landmark (2 observations) through Point::optimize, 5 iterations
+    auto bundle = std::make_shared<FrameBundle>();
+    bundle->frames_ = {frame0, frame1};
+    optimizeStructure(bundle, -1, 5);
+    for (size_t i = 0; i < frame1->num_features_; ++i) {
+      const PointPtr& p = frame1->landmark_vec_[i];
+      for (int k = 0; k < 3; ++k) out.push_back(p->pos_[k]);
+      out.push_back(double(p->last_structure_optim_));
+    }
     std::ofstream of(argv[2], std::ios::binary);
     of.write(reinterpret_cast<const char*>(out.data()), sizeof(double) * out.size());
     return 0;

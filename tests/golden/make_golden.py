@@ -25,6 +25,8 @@ cv_imgproc_golden.npz outputs of the REAL OpenCV (python module cv2, version sto
 stereo_tri_ref_golden.npz what the REFERENCE's own StereoTriangulation::compute (stereo_triangulation.cpp compiled into
                       libfrontend_ref.so, with its detectors, matcher and std::random_shuffle after srand(seed)) leaves in both frames on
                       tests/helpers.py:STEREO_TRI_CASES, plus the visiting orders: pins row f3 (stereo part).
+point_opt_ref_golden.npz outputs of the REFERENCE's own Point::optimize (point.h / point.cpp compiled into libpoint_ref.so) on the 400
+                      points of tests/helpers.py:point_opt_cases, unit plane and unit sphere: pins row f4 (second half).
 klt_ref_golden.npz    outputs of the REFERENCE's own alignPyr2D (libdirect_ref.so) on the cases of tests/test_klt_cpu.py.
 Usage: python tests/golden/make_golden.py
 """
@@ -158,6 +160,14 @@ def stereo_tri_golden():
     print("wrote stereo_tri_ref_golden.npz")
 
 
+def point_opt_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_point_lib() is not None
+    np.savez_compressed(os.path.join(HERE, "point_opt_ref_golden.npz"), **helpers.point_opt_outputs(orc, "ref"))
+    print("wrote point_opt_ref_golden.npz")
+
+
 def detect_golden():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
@@ -191,6 +201,7 @@ if __name__ == "__main__":
     detect_golden()
     cv_imgproc_golden()
     stereo_tri_golden()
+    point_opt_golden()
     pose_opt_golden()
     reproject_golden()
     klt_golden()

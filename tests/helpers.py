@@ -435,3 +435,40 @@ def assert_stereo_matches_reference(res, order, g, i, tol=1e-9):
     np.testing.assert_allclose(ok["f_cur"], g[f"f1_{i}"], rtol=0, atol=1e-5)
     np.testing.assert_allclose(ok["grad_cur"], g[f"grad1_{i}"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(ok["xyz_world"], g[f"xyz1_{i}"], rtol=1e-4, atol=1e-6)
+
+
+# ---- f4 (second half): Point::optimize -------------------------------------------------------------------------------------------------
+def point_opt_cases(seed=17, n_points=400, n_frames=12):
+    """Seeded structure-refinement problems: n_frames camera poses around the origin, n_points landmarks 2-8 m in front of them, each
+    observed by 1-10 of the frames with bearing noise, starting from a perturbed position (a few hard cases: 1 observation, a start
+    far off, observations from nearly the same place)."""
+    rng = np.random.default_rng(seed)
+    T_f_w = np.stack([synth.se3_exp_small(rng.normal(0, 0.05, 3), rng.normal(0, 0.25, 3)) for _ in range(n_frames)])
+    pos_true = np.stack([rng.uniform(-2, 2, n_points), rng.uniform(-1.5, 1.5, n_points), rng.uniform(2, 8, n_points)], 1)
+    begin, obs_frame, obs_f, pos0 = [0], [], [], []
+    for i in range(n_points):
+        k = 1 if i % 57 == 0 else int(rng.integers(2, 11))
+        fr = rng.choice(n_frames, k, replace=False)
+        for j in fr:
+            R, t = synth.se3_to_Rt(T_f_w[j])
+            p = R @ pos_true[i] + t
+            b = p / np.linalg.norm(p) + rng.normal(0, 2e-3, 3)
+            obs_f.append(b / np.linalg.norm(b))
+            obs_frame.append(j)
+        begin.append(len(obs_frame))
+        pos0.append(pos_true[i] + rng.normal(0, 0.15 if i % 13 else 1.5, 3))
+    return dict(T_f_w=T_f_w, pos_true=pos_true, pos0=np.array(pos0), obs_begin=np.array(begin, np.int32),
+                obs_frame=np.array(obs_frame, np.int32), obs_f=np.array(obs_f))
+
+
+def point_opt_outputs(orc, which, n_iter=5):
+    c = point_opt_cases()
+    out = {}
+    for sphere in (0, 1):
+        res = []
+        for i in range(len(c["pos0"])):
+            lo, hi = c["obs_begin"][i], c["obs_begin"][i + 1]
+            p, _ = orc.point_optimize(c["T_f_w"][c["obs_frame"][lo:hi]], c["obs_f"][lo:hi], c["pos0"][i], n_iter, bool(sphere), which=which)
+            res.append(p)
+        out[f"pos_{sphere}"] = np.array(res)
+    return out

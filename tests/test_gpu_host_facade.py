@@ -237,7 +237,8 @@ def test_stereo_triangulation_facade_matches_reference(orc, tmp_path):
         n0, n1 = int(out[0]), int(out[1])
         assert n0 == int(g[f"n0_{i}"]) and n1 == int(g[f"n1_{i}"]), (i, n0, n1)
         a = out[2:2 + 4 * n0].reshape(n0, 4)
-        b = out[2 + 4 * n0:].reshape(n1, 15)
+        b = out[2 + 4 * n0:2 + 4 * n0 + 15 * n1].reshape(n1, 15)
+        opt = out[2 + 4 * n0 + 15 * n1:].reshape(n1, 4)
         assert np.array_equal(a[:, :2], g[f"px0_{i}"]) and np.array_equal(a[:, 2], g[f"type0_{i}"])
         assert np.array_equal(b[:, 13].astype(np.int32), g[f"ref_index1_{i}"])            # the same frame0 features in the same slots
         assert np.array_equal(np.flatnonzero(a[:, 3]), np.sort(g[f"ref_index1_{i}"]))     # ... and they own the new landmarks
@@ -247,3 +248,16 @@ def test_stereo_triangulation_facade_matches_reference(orc, tmp_path):
         np.testing.assert_allclose(b[:, 2:5], g[f"f1_{i}"], rtol=0, atol=1e-5)
         np.testing.assert_allclose(b[:, 5:7], g[f"grad1_{i}"], rtol=0, atol=1e-6)
         np.testing.assert_allclose(b[:, 10:13], g[f"xyz1_{i}"], rtol=1e-4, atol=1e-6)
+        # optimizeStructure: every landmark refined from its two observations == the oracle's Point::optimize (bit-equal to the
+        # reference's compiled point.cpp, tests/test_point_optimizer_cpu.py); frame1 is visited last
+        T0, T1 = synth.se3_mul(d["T_cam_imu"], d["T_imu_world_ref"]), synth.se3_mul(s1["T_cam_imu"], d["T_imu_world_ref"])
+        f0 = synth.cam_backproject(cam, a[b[:, 13].astype(int), :2])
+        f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+        for k in range(0, n1, 7):
+            # frame0's pass optimises the point first, frame1's pass (non-edgelets again) a second time from that result
+            p1, _ = orc.point_optimize(np.stack([T0, T1]), np.stack([f0[k], b[k, 2:5]]), b[k, 10:13], 5)
+            edgelet = int(b[k, 8]) == 6
+            p2 = p1 if edgelet else orc.point_optimize(np.stack([T0, T1]), np.stack([f0[k], b[k, 2:5]]), p1, 5)[0]
+            want = b[k, 10:13] if edgelet else p2
+            np.testing.assert_allclose(opt[k, :3], want, rtol=0, atol=1e-9)
+        assert (opt[b[:, 8] != 6, 3] == 2).all()

@@ -1,0 +1,41 @@
+"""GPU parity test, row f4 (second half): svo_cuda_optimize_points against the oracle and the committed outputs of the reference's
+own compiled Point::optimize, through the C ABI (host arrays and device arrays)."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from svo_pro_universal_b200 import capi
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_optimize_points_matches_reference(ctx, orc):
+    import torch
+    g = np.load(os.path.join(GOLD, "point_opt_ref_golden.npz"))
+    c = helpers.point_opt_cases()
+    for sphere in (0, 1):
+        pos = c["pos0"].copy()
+        iters = capi.optimize_points(ctx, pos, c["obs_begin"], c["obs_frame"], c["obs_f"], c["T_f_w"], 5, bool(sphere))
+        # same operations in the same order, no FMA contraction: tolerance 1e-12 m (bit-equal on almost every point)
+        np.testing.assert_allclose(pos, g[f"pos_{sphere}"], rtol=0, atol=1e-12)
+        o_it = []
+        for i in range(len(pos)):
+            lo, hi = c["obs_begin"][i], c["obs_begin"][i + 1]
+            _, it = orc.point_optimize(c["T_f_w"][c["obs_frame"][lo:hi]], c["obs_f"][lo:hi], c["pos0"][i], 5, bool(sphere))
+            o_it.append(it)
+        assert np.array_equal(iters, np.array(o_it, np.int32))
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dpos = t(c["pos0"])
+        capi.optimize_points(ctx, dpos, t(c["obs_begin"]), t(c["obs_frame"]), t(c["obs_f"]), t(c["T_f_w"]), 5, bool(sphere))
+        ctx.synchronize()
+        assert np.array_equal(dpos.cpu().numpy(), pos)
+
+
+def test_optimize_points_arguments(ctx):
+    import ctypes as C
+    L = capi.lib()
+    assert L.svo_cuda_optimize_points(ctx._h, 4, None, None, 0, None, None, 0, None, 5, 0, None, 0) == -1
+    assert L.svo_cuda_optimize_points(ctx._h, 0, None, None, 0, None, None, 0, None, 5, 0, None, 0) == 0
