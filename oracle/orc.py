@@ -949,3 +949,83 @@ def point_optimize(T_f_w, f, pos, n_iter=5, using_bearing_vector=False, which="o
     fn = lib().orc_point_optimize if which == "orc" else ref_point_lib().ref_point_optimize
     it = fn(len(T), _f64(T), _f64(fv), _f64(p), int(n_iter), int(bool(using_bearing_vector)))
     return p, (it if which == "orc" else None)
+
+
+# ---- f3 (tracker part): FeatureTracker::trackAndDetect ----------------------------------------------------------------------------
+KLT_PATCH_SIZES = (16, 16, 16, 8, 8)  # FeatureTrackerOptions defaults (feature_tracking_types.h:11-42)
+
+
+def feature_tracker_sequence(pyrs, detector_type=DETECTOR_FAST, threshold_primary=10.0, threshold_secondary=100.0, min_tracks_to_detect=50,
+                             reset_before_detection=True, template_is_first=True, klt_max_level=4, klt_min_level=0, klt_max_iter=30,
+                             klt_min_update_squared=0.001):
+    """FeatureTracker::trackAndDetect over a mono sequence of pyramids (src/svo_tracker/src/feature_tracker.cpp:32-187): the host
+    bookkeeping restated around the oracle's alignPyr2D and detectors. Returns per frame dict(px, track_id, score, n_active,
+    n_terminated, disparity)."""
+    tracks = []          # each: dict(id, obs=[(frame index, feature index)])
+    frames = []          # per frame: dict(px, score, track_id)
+    out, next_id = [], 0
+    for k, pyr in enumerate(pyrs):
+        cur = dict(px=np.zeros((0, 2)), score=np.zeros(0), track_id=np.zeros(0, np.int64))
+        frames.append(cur)
+        # trackFrameBundle (:52-127)
+        terminated = 0
+        if tracks:
+            ref_obs = [t["obs"][0] if template_is_first else t["obs"][-1] for t in tracks]
+            last_obs = [t["obs"][-1] for t in tracks]
+            ref_px = np.array([frames[a]["px"][b] for a, b in ref_obs]).astype(np.int32)      # getPx().cast<int>()
+            cur_px = np.array([frames[a]["px"][b] for a, b in last_obs])
+            new_px, ok = np.zeros_like(cur_px), np.zeros(len(tracks), bool)
+            for fi in sorted(set(a for a, _ in ref_obs)):                                        # one batch per template frame
+                sel = np.flatnonzero([a == fi for a, _ in ref_obs])
+                p, s = align_pyr2d(pyrs[fi], pyr, ref_px[sel], cur_px[sel], klt_max_level, klt_min_level, KLT_PATCH_SIZES, klt_max_iter,
+                                   klt_min_update_squared)
+                new_px[sel], ok[sel] = p, s.astype(bool)
+            kept, px, sc, ids = [], [], [], []
+            for t, (ra, rb), p, good in zip(tracks, ref_obs, new_px, ok):
+                if good:
+                    px.append(p); sc.append(frames[ra]["score"][rb]); ids.append(t["id"])
+                    t["obs"].append((k, len(px) - 1))
+                    kept.append(t)
+                else:
+                    terminated += 1
+            tracks = kept
+            cur["px"], cur["score"], cur["track_id"] = np.array(px).reshape(-1, 2), np.array(sc), np.array(ids, np.int64)
+        # trackAndDetect (:32-50)
+        if len(tracks) < min_tracks_to_detect:
+            if reset_before_detection:
+                tracks = []
+                cur["px"], cur["score"], cur["track_id"] = np.zeros((0, 2)), np.zeros(0), np.zeros(0, np.int64)
+            # initializeNewTracks (:129-187): grid filled with the frame's keypoints, detect, append, one track per new feature
+            n_cols, n_rows = -(-pyr[0].shape[1] // 30), -(-pyr[0].shape[0] // 30)
+            occ = np.zeros(n_cols * n_rows, np.uint8)
+            for x, y in cur["px"]:
+                occ[(int(y) // 30) * n_cols + int(x) // 30] = 1
+            det = detect_features(detector_type, pyr, threshold_primary, threshold_secondary, occupancy=occ)
+            n_old = len(cur["px"])
+            cur["px"] = np.concatenate([cur["px"], det["px"]])
+            cur["score"] = np.concatenate([cur["score"], det["score"]])
+            new_ids = np.arange(next_id, next_id + len(det["px"]))
+            next_id += len(det["px"])
+            cur["track_id"] = np.concatenate([cur["track_id"], new_ids])
+            for j, tid in enumerate(new_ids):
+                tracks.append(dict(id=int(tid), obs=[(k, n_old + j)]))
+        disp = [np.linalg.norm(frames[t["obs"][0][0]]["px"][t["obs"][0][1]] - frames[t["obs"][-1][0]]["px"][t["obs"][-1][1]]) for t in tracks]
+        pivot = int(np.floor(0.5 * len(disp))) if disp else 0
+        out.append(dict(px=cur["px"].copy(), track_id=cur["track_id"].copy(), score=cur["score"].copy(), n_active=len(tracks),
+                        n_terminated=terminated, disparity=float(np.sort(disp)[::-1][pivot]) if disp else 0.0))
+    return out
+
+
+def ref_feature_tracker_sequence(frames, detector_type=DETECTOR_FAST, threshold_primary=10.0, threshold_secondary=100.0,
+                                 min_tracks_to_detect=50, reset_before_detection=True, template_is_first=True, cap=1024):
+    """The reference's own FeatureTracker::trackAndDetect over a mono sequence of oracle frames (oracle/_ref/libfrontend_ref.so)."""
+    n = len(frames)
+    arr = (Frame * n)(*frames)
+    nf = np.zeros(n, np.int32); px = np.zeros((n, cap, 2)); tid = np.zeros((n, cap), np.int32); sc = np.zeros((n, cap))
+    na = np.zeros(n, np.int32); nt = np.zeros(n, np.int32); disp = np.zeros(n)
+    fn = ref_frontend_lib().ref_feature_tracker_sequence
+    fn.argtypes = [C.c_int, C.POINTER(Frame), C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+    fn(n, arr, int(detector_type), threshold_primary, threshold_secondary, int(min_tracks_to_detect), int(reset_before_detection),
+       int(template_is_first), cap, *[a.ctypes.data for a in (nf, px, tid, sc, na, nt, disp)])
+    return [dict(px=px[k, :nf[k]].copy(), track_id=tid[k, :nf[k]].astype(np.int64), score=sc[k, :nf[k]].copy(), n_active=int(na[k]),
+                 n_terminated=int(nt[k]), disparity=float(disp[k])) for k in range(n)]

@@ -664,3 +664,47 @@ extern "C" int ref_stereo_triangulation_compute(const orc_frame* f0, const orc_f
   }
   return n1;
 }
+
+// ---- f3 (tracker part): FeatureTracker::trackAndDetect (src/svo_tracker/src/feature_tracker.cpp:14-248) over a mono sequence: detector
+// from makeDetector, pyramidal KLT of every active track from its first observation (alignPyr2D), track bookkeeping, re-detection when
+// fewer than min_tracks tracks survive. Per frame k the frame's columns after the call are written to row k of the outputs (cap each).
+#include <svo/tracker/feature_tracker.h>
+#include <svo/tracker/feature_tracking_types.h>
+
+extern "C" int ref_feature_tracker_sequence(int n_frames, const orc_frame* frames, int detector_type, double threshold_primary,
+                                            double threshold_secondary, int min_tracks_to_detect, int reset_before_detection,
+                                            int template_is_first, int cap, int* n_features, double* px, int* track_id, double* score,
+                                            int* n_active, int* n_terminated, double* disparity) {
+  svo::FeatureTrackerOptions to;
+  to.min_tracks_to_detect_new_features = (size_t)min_tracks_to_detect;
+  to.reset_before_detection = reset_before_detection != 0;
+  to.klt_template_is_first_observation = template_is_first != 0;
+  svo::DetectorOptions o;
+  o.detector_type = static_cast<svo::DetectorType>(detector_type);
+  o.threshold_primary = threshold_primary; o.threshold_secondary = threshold_secondary;
+  auto cams = std::make_shared<vk::cameras::NCamera>(std::vector<std::shared_ptr<vk::cameras::CameraGeometryBase>>{makeCamera(frames[0])});
+  svo::FeatureTracker tracker(to, o, cams);
+  std::vector<svo::FrameBundlePtr> keep;  // tracks reference their bundles
+  int first_id = -1;
+  for (int k = 0; k < n_frames; ++k) {
+    svo::FramePtr fr = makeFrame(frames[k]);
+    fr->id_ = k + 1;
+    auto bundle = std::make_shared<svo::FrameBundle>(std::vector<svo::FramePtr>{fr});
+    keep.push_back(bundle);
+    tracker.trackAndDetect(bundle);
+    const int n = (int)fr->num_features_;
+    n_features[k] = n;
+    for (int i = 0; i < n && i < cap; ++i) {
+      if (first_id < 0) first_id = fr->track_id_vec_(i);
+      px[((size_t)k * cap + i) * 2] = fr->px_vec_(0, i); px[((size_t)k * cap + i) * 2 + 1] = fr->px_vec_(1, i);
+      track_id[(size_t)k * cap + i] = fr->track_id_vec_(i) - first_id;  // ids come from a process-wide counter
+      score[(size_t)k * cap + i] = fr->score_vec_(i);
+    }
+    n_active[k] = (int)tracker.getTotalActiveTracks();
+    n_terminated[k] = (int)tracker.terminated_tracks_.at(0).size();
+    std::vector<size_t> nt; std::vector<double> disp;
+    tracker.getNumTrackedAndDisparityPerFrame(0.5, &nt, &disp);
+    disparity[k] = disp.at(0);
+  }
+  return 0;
+}

@@ -387,8 +387,32 @@ class Matrix<T, R, C, Opt, MR, MC, typename std::enable_if<(R < 0 || C < 0)>::ty
   void setConstant(int n, T v) { resize(n); setConstant(v); }
   ShimAny transpose() const { std::abort(); }
   ShimAny rowwise() const { std::abort(); }
-  ShimAny colwise() const { std::abort(); }
   template <typename X> ShimAny cwiseProduct(const X&) const { std::abort(); }
+  // `m.array().rowwise() / m.colwise().norm().array()` (normalise every column: feature_tracker.cpp:156) is evaluated for real
+  struct ColNorms { std::vector<T> n; const ColNorms& array() const { return *this; } };
+  struct Colwise {
+    const Matrix& m;
+    ColNorms norm() const {
+      ColNorms r;
+      for (int j = 0; j < m.cols(); ++j) { T s = T(0); for (int i = 0; i < m.rows(); ++i) s += m(i, j) * m(i, j); r.n.push_back(std::sqrt(s)); }
+      return r;
+    }
+    ShimAny squaredNorm() const { std::abort(); }
+    ShimAny sum() const { std::abort(); }
+  };
+  struct Rowwise {
+    const Matrix& m;
+    Matrix operator/(const ColNorms& c) const {
+      Matrix r = m;
+      for (int j = 0; j < m.cols(); ++j) for (int i = 0; i < m.rows(); ++i) r(i, j) = m(i, j) / c.n[j];
+      return r;
+    }
+  };
+  struct ArrayView { const Matrix& m; Rowwise rowwise() const { return Rowwise{m}; } };
+  Colwise colwise() const { return Colwise{*this}; }
+  ArrayView array() const { return ArrayView{*this}; }
+  Matrix head(int n) const { Matrix r; r.resize(n); for (int i = 0; i < n; ++i) r.data()[i] = data()[i]; return r; }           // vectors
+  Matrix leftCols(int n) const { Matrix r; r.resize(r_, n); for (int j = 0; j < n; ++j) for (int i = 0; i < r_; ++i) r(i, j) = (*this)(i, j); return r; }
   void conservativeResize(int n) { if (C == 1) conservativeResize(n, 1); else conservativeResize(r_, n); }
   void conservativeResize(NoChange_t, int c) { conservativeResize(r_, c); }
   void conservativeResize(int r, NoChange_t) { conservativeResize(r, c_); }

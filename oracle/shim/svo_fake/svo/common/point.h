@@ -4,6 +4,7 @@
 // getCloseViewObs is restated from src/svo_common/src/point.cpp:83-129 (that file pulls in the bundle-adjustment types).
 #pragma once
 #include <array>
+#include <atomic>
 #include <memory>
 #include <vector>
 #include <svo/common/types.h>
@@ -11,6 +12,14 @@ namespace svo {
 class Frame;
 using FramePtr = std::shared_ptr<Frame>;
 using FrameWeakPtr = std::weak_ptr<Frame>;
+
+class PointIdProvider {  // point.h:22-34 (thread-safe point-ID provider; the tracker draws its track ids from it)
+ public:
+  PointIdProvider() = delete;
+  static int getNewPointId() { return last_id_.fetch_add(1); }
+ private:
+  static inline std::atomic<int> last_id_{0};  // point.cpp:14
+};
 
 struct KeypointIdentifier {  // point.h:36-60
   FrameWeakPtr frame;

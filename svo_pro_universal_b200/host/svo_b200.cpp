@@ -4,6 +4,7 @@
 #include "svo_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -50,7 +51,7 @@ size_t Frame::numTrackedFeatures() const {  // frame.h:153-163
 
 void Frame::clearFeatureStorage() {
   px_vec_.clear(); f_vec_.clear(); grad_vec_.clear(); score_vec_.clear(); level_vec_.clear(); type_vec_.clear();
-  depth_vec_.clear(); invmu_sigma2_a_b_vec_.clear(); landmark_vec_.clear(); seed_ref_vec_.clear();
+  depth_vec_.clear(); invmu_sigma2_a_b_vec_.clear(); landmark_vec_.clear(); seed_ref_vec_.clear(); track_id_vec_.clear();
   num_features_ = 0;
 }
 
@@ -922,6 +923,177 @@ void optimizeStructure(const FrameBundle::Ptr& frames, int max_n_pts, int max_it
     optimizePointsOnDevice(batch, size_t(max_iter), optimize_on_sphere);
     for (Point* p : pts) p->last_structure_optim_ = frame->id_;
   }
+}
+
+// ---- FeatureTracker -------------------------------------------------------------------------------------------------------------------
+namespace feature_alignment {
+void alignPyr2DVec(const Frame& ref_frame, const Frame& cur_frame, int max_level, int min_level, const std::vector<int>& patch_sizes,
+                   int n_iter, float min_update_squared, const std::vector<std::array<int, 2>>& px_ref, std::vector<Keypoint>& px_cur,
+                   std::vector<uint8_t>& status) {
+  const int M = int(px_ref.size());
+  status.assign(size_t(M), 0);
+  if (M == 0) return;
+  std::vector<int> ps(SVO_MAX_LEVELS, 8);
+  for (size_t l = 0; l < patch_sizes.size() && l < ps.size(); ++l) ps[l] = patch_sizes[l];
+  b200::check(svo_cuda_align_pyr2d(b200::context(), b200::ensureGpu(ref_frame).handle(), b200::ensureGpu(cur_frame).handle(), nullptr, nullptr, M,
+                                   &px_ref[0][0], &px_cur[0][0], max_level, min_level, ps.data(), n_iter, min_update_squared, status.data(),
+                                   SVO_MEM_HOST), "svo_cuda_align_pyr2d");
+}
+}  // namespace feature_alignment
+
+int PointIdProvider::getNewPointId() {
+  static std::atomic<int> last_id{0};
+  return last_id.fetch_add(1);
+}
+
+double FeatureTrack::getDisparity() const {
+  const Keypoint &a = front().getPx(), &b = back().getPx();
+  return std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]));
+}
+
+namespace feature_tracking_utils {
+double getTracksDisparityPercentile(const FeatureTracks& tracks, double pivot_ratio) {
+  if (!(pivot_ratio > 0.0 && pivot_ratio < 1.0)) throw b200::Error("getTracksDisparityPercentile: pivot_ratio needs to be in (0,1)");
+  if (tracks.empty()) return 0.0;
+  std::vector<double> disparities;
+  disparities.reserve(tracks.size());
+  for (const FeatureTrack& track : tracks) disparities.push_back(track.getDisparity());
+  const size_t pivot = size_t(std::floor(pivot_ratio * disparities.size()));
+  std::nth_element(disparities.begin(), disparities.begin() + pivot, disparities.end(), std::greater<double>());
+  return disparities[pivot];
+}
+}  // namespace feature_tracking_utils
+
+FeatureTracker::FeatureTracker(const FeatureTrackerOptions& options, const DetectorOptions& detector_options, const std::vector<CameraPtr>& cams)
+    : options_(options), bundle_size_(cams.size()), active_tracks_(cams.size()), terminated_tracks_(cams.size()) {
+  for (const CameraPtr& cam : cams) detectors_.push_back(feature_detection_utils::makeDetector(detector_options, cam));
+}
+
+void FeatureTracker::trackAndDetect(const FrameBundle::Ptr& nframe_kp1) {
+  const size_t n_tracked = trackFrameBundle(nframe_kp1);
+  if (n_tracked < options_.min_tracks_to_detect_new_features) {
+    if (options_.reset_before_detection) {
+      resetActiveTracks();
+      for (const FramePtr& frame : nframe_kp1->frames_) frame->clearFeatureStorage();
+    }
+    initializeNewTracks(nframe_kp1);
+  }
+}
+
+size_t FeatureTracker::trackFrameBundle(const FrameBundle::Ptr& nframe_kp1) {
+  resetTerminatedTracks();
+  for (size_t frame_index = 0; frame_index < bundle_size_; ++frame_index) {
+    FeatureTracks& tracks = active_tracks_.at(frame_index);
+    const FramePtr& cur_frame = nframe_kp1->frames_.at(frame_index);
+    const size_t n = tracks.size();
+    // KLT of all tracks, batched per template frame
+    std::vector<Keypoint> cur_px(n);
+    std::vector<uint8_t> success(n, 0);
+    std::vector<const Frame*> ref_frames(n);
+    for (size_t t = 0; t < n; ++t) {
+      const FeatureRef& ref = options_.klt_template_is_first_observation ? tracks[t].front() : tracks[t].back();
+      ref_frames[t] = ref.getFrame().get();
+      cur_px[t] = tracks[t].back().getPx();
+    }
+    std::vector<uint8_t> done(n, 0);
+    for (size_t t0 = 0; t0 < n; ++t0) {
+      if (done[t0]) continue;
+      std::vector<size_t> sel;
+      std::vector<std::array<int, 2>> px_ref;
+      std::vector<Keypoint> px_cur;
+      for (size_t t = t0; t < n; ++t)
+        if (!done[t] && ref_frames[t] == ref_frames[t0]) {
+          const FeatureRef& ref = options_.klt_template_is_first_observation ? tracks[t].front() : tracks[t].back();
+          sel.push_back(t);
+          px_ref.push_back({int(ref.getPx()[0]), int(ref.getPx()[1])});  // getPx().cast<int>() (:80)
+          px_cur.push_back(cur_px[t]);
+          done[t] = 1;
+        }
+      std::vector<uint8_t> st;
+      feature_alignment::alignPyr2DVec(*ref_frames[t0], *cur_frame, options_.klt_max_level, options_.klt_min_level, options_.klt_patch_sizes,
+                                       options_.klt_max_iter, float(options_.klt_min_update_squared), px_ref, px_cur, st);
+      for (size_t k = 0; k < sel.size(); ++k) { cur_px[sel[k]] = px_cur[k]; success[sel[k]] = st[k]; }
+    }
+    // bookkeeping in track order (:67-115)
+    cur_frame->clearFeatureStorage();
+    FeatureTracks kept;
+    kept.reserve(n);
+    for (size_t t = 0; t < n; ++t) {
+      FeatureTrack& track = tracks[t];
+      if (success[t]) {
+        const FeatureRef& ref = options_.klt_template_is_first_observation ? track.front() : track.back();
+        const size_t slot = cur_frame->px_vec_.size();
+        cur_frame->px_vec_.push_back(cur_px[t]);
+        cur_frame->score_vec_.push_back(ref.getFrame()->score_vec_.at(ref.getFeatureIndex()));
+        cur_frame->track_id_vec_.push_back(track.getTrackId());
+        // resizeFeatureStorage's initial values for the other columns (frame.cpp:94-123)
+        cur_frame->grad_vec_.push_back({0.0, 0.0});
+        cur_frame->level_vec_.push_back(0);
+        cur_frame->type_vec_.push_back(FeatureType::kCorner);
+        cur_frame->depth_vec_.push_back(-1.0);
+        cur_frame->invmu_sigma2_a_b_vec_.push_back({0, 0, 0, 0});
+        cur_frame->f_vec_.push_back(normalizedBearing(cur_frame->cam_->model, cur_px[t]));  // computeNormalizedBearingVectors (:119-121)
+        track.pushBack(nframe_kp1, frame_index, slot);
+        kept.push_back(track);
+      } else {
+        terminated_tracks_.at(frame_index).push_back(track);
+      }
+    }
+    tracks.swap(kept);
+    cur_frame->num_features_ = cur_frame->px_vec_.size();
+  }
+  return getTotalActiveTracks();
+}
+
+size_t FeatureTracker::initializeNewTracks(const FrameBundle::Ptr& nframe) {
+  for (size_t frame_index = 0; frame_index < bundle_size_; ++frame_index) {
+    const FramePtr& frame = nframe->frames_.at(frame_index);
+    AbstractDetector& det = *detectors_.at(frame_index);
+    det.resetGrid();
+    for (const Keypoint& px : frame->px_vec_) det.grid_.occupancy_.at(det.grid_.getCellIndex(int(px[0]), int(px[1]), 1)) = 1;  // fillWithKeypoints
+    Keypoints new_px; Scores new_scores; Levels new_levels; Gradients new_grads; FeatureTypes new_types;
+    det.detect(b200::ensureGpu(*frame), det.grid_.size(), new_px, new_scores, new_levels, new_grads, new_types);
+    const size_t n_old = frame->num_features_;
+    FeatureTracks& tracks = active_tracks_.at(frame_index);
+    for (size_t i = 0; i < new_px.size(); ++i) {
+      frame->px_vec_.push_back(new_px[i]);
+      frame->f_vec_.push_back(normalizedBearing(frame->cam_->model, new_px[i]));
+      frame->grad_vec_.push_back(new_grads[i]);
+      frame->score_vec_.push_back(new_scores[i]);
+      frame->level_vec_.push_back(new_levels[i]);
+      frame->type_vec_.push_back(FeatureType::kCorner);  // the reference leaves type_vec_ at its initial value ("TODO(cfo)", :169)
+      frame->depth_vec_.push_back(-1.0);
+      frame->invmu_sigma2_a_b_vec_.push_back({0, 0, 0, 0});
+      const int new_track_id = PointIdProvider::getNewPointId();
+      tracks.emplace_back(new_track_id);
+      tracks.back().pushBack(nframe, frame_index, n_old + i);
+      frame->track_id_vec_.resize(n_old + i, -1);
+      frame->track_id_vec_.push_back(new_track_id);
+    }
+    frame->num_features_ = frame->px_vec_.size();
+  }
+  return getTotalActiveTracks();
+}
+
+size_t FeatureTracker::getTotalActiveTracks() const {
+  size_t n = 0;
+  for (const FeatureTracks& t : active_tracks_) n += t.size();
+  return n;
+}
+
+void FeatureTracker::getNumTrackedAndDisparityPerFrame(double pivot_ratio, std::vector<size_t>* num_tracked, std::vector<double>* disparity) const {
+  num_tracked->resize(bundle_size_);
+  disparity->resize(bundle_size_);
+  for (size_t i = 0; i < bundle_size_; ++i) {
+    num_tracked->at(i) = active_tracks_[i].size();
+    disparity->at(i) = feature_tracking_utils::getTracksDisparityPercentile(active_tracks_[i], pivot_ratio);
+  }
+}
+
+void FeatureTracker::reset() {
+  resetActiveTracks();
+  resetTerminatedTracks();
+  for (auto& d : detectors_) d->resetGrid();
 }
 
 // ---- StereoTriangulation ------------------------------------------------------------------------------------------------------------

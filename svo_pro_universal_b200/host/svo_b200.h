@@ -119,6 +119,7 @@ struct Frame {
   // (replaces the landmark_vec_ / seed_ref_vec_ pointer walk of sparse_img_align.cpp:282-293, done by the adapter).
   std::vector<double> depth_vec_;
   std::vector<SeedState> invmu_sigma2_a_b_vec_;
+  std::vector<int> track_id_vec_;        // frame.h:73 (KLT track ids, written by the FeatureTracker)
   std::vector<PointPtr> landmark_vec_;   // used by the Reprojector; may stay empty for the other facades
   std::vector<SeedRef> seed_ref_vec_;
   double seed_mu_range_ = 0.0;
@@ -426,6 +427,91 @@ class Reprojector {  // reprojector.h:77-166
   bool doesFrameHaveEnoughFeatures(const FramePtr& frame) const {
     return options_.max_n_features_per_frame > 0 && frame->numTrackedFeatures() >= options_.max_n_features_per_frame;
   }
+};
+
+// ---- (f3) FeatureTracker (pyramidal KLT tracks) --------------------------------------------------------------------------------
+namespace feature_alignment {
+// feature_alignment::alignPyr2DVec (src/svo_direct/include/svo/direct/feature_alignment.h:68-80; .cpp:761-798) for features whose
+// templates all live in ref_frame: ONE svo_cuda_align_pyr2d call. px_ref are truncated to integers as the tracker does.
+void alignPyr2DVec(const Frame& ref_frame, const Frame& cur_frame, int max_level, int min_level, const std::vector<int>& patch_sizes,
+                   int n_iter, float min_update_squared, const std::vector<std::array<int, 2>>& px_ref, std::vector<Keypoint>& px_cur,
+                   std::vector<uint8_t>& status);
+}  // namespace feature_alignment
+
+struct PointIdProvider {  // src/svo_common/include/svo/common/point.h:22-34
+  static int getNewPointId();
+};
+
+struct FeatureTrackerOptions {  // src/svo_tracker/include/svo/tracker/feature_tracking_types.h:9-43
+  int klt_max_level = 4;
+  int klt_min_level = 0;
+  std::vector<int> klt_patch_sizes = {16, 16, 16, 8, 8};
+  int klt_max_iter = 30;
+  double klt_min_update_squared = 0.001;
+  bool klt_template_is_first_observation = true;
+  size_t min_tracks_to_detect_new_features = 50;
+  bool reset_before_detection = true;
+};
+
+class FeatureRef {  // feature_tracking_types.h:46-77
+ public:
+  FeatureRef(const FrameBundle::Ptr& frame_bundle, size_t frame_index, size_t feature_index)
+      : frame_bundle_(frame_bundle), frame_index_(frame_index), feature_index_(feature_index) {}
+  const FrameBundle::Ptr getFrameBundle() const { return frame_bundle_; }
+  size_t getFrameIndex() const { return frame_index_; }
+  size_t getFeatureIndex() const { return feature_index_; }
+  const Keypoint& getPx() const { return frame_bundle_->frames_.at(frame_index_)->px_vec_.at(feature_index_); }
+  const BearingVector& getBearing() const { return frame_bundle_->frames_.at(frame_index_)->f_vec_.at(feature_index_); }
+  const FramePtr getFrame() const { return frame_bundle_->frames_.at(frame_index_); }
+ private:
+  FrameBundle::Ptr frame_bundle_;
+  size_t frame_index_, feature_index_;
+};
+
+class FeatureTrack {  // feature_tracking_types.h:83-146
+ public:
+  explicit FeatureTrack(int track_id) : track_id_(track_id) { feature_track_.reserve(10); }
+  int getTrackId() const { return track_id_; }
+  const std::vector<FeatureRef>& getFeatureTrack() const { return feature_track_; }
+  size_t size() const { return feature_track_.size(); }
+  bool empty() const { return feature_track_.empty(); }
+  const FeatureRef& front() const { return feature_track_.front(); }
+  const FeatureRef& back() const { return feature_track_.back(); }
+  const FeatureRef& at(size_t i) const { return feature_track_.at(i); }
+  void pushBack(const FrameBundle::Ptr& frame_bundle, size_t frame_index, size_t feature_index) {
+    feature_track_.emplace_back(frame_bundle, frame_index, feature_index);
+  }
+  double getDisparity() const;  // feature_tracking_types.cpp:38-41
+ private:
+  int track_id_;
+  std::vector<FeatureRef> feature_track_;
+};
+using FeatureTracks = std::vector<FeatureTrack>;
+
+namespace feature_tracking_utils {
+double getTracksDisparityPercentile(const FeatureTracks& tracks, double pivot_ratio);  // feature_tracking_utils.cpp:11-33
+}
+
+class FeatureTracker {  // src/svo_tracker/include/svo/tracker/feature_tracker.h:14-84
+ public:
+  // `cams` stands for the CameraBundle: one camera per frame of the bundles that will be tracked.
+  FeatureTracker(const FeatureTrackerOptions& options, const DetectorOptions& detector_options, const std::vector<CameraPtr>& cams);
+  void trackAndDetect(const FrameBundle::Ptr& nframe_kp1);         // feature_tracker.cpp:32-50
+  // :52-127 — every active track of a camera goes through ONE svo_cuda_align_pyr2d call per template frame (one call in all
+  // when the templates are first observations of the same detection, the default)
+  size_t trackFrameBundle(const FrameBundle::Ptr& nframe_kp1);
+  size_t initializeNewTracks(const FrameBundle::Ptr& nframe_k);    // :129-187
+  const FeatureTracks& getActiveTracks(size_t frame_index) const { return active_tracks_.at(frame_index); }
+  size_t getTotalActiveTracks() const;
+  void getNumTrackedAndDisparityPerFrame(double pivot_ratio, std::vector<size_t>* num_tracked, std::vector<double>* disparity) const;
+  FrameBundle::Ptr getOldestFrameInTrack(size_t frame_index) const { return active_tracks_.at(frame_index).front().at(0).getFrameBundle(); }
+  void resetActiveTracks() { for (auto& t : active_tracks_) t.clear(); }
+  void resetTerminatedTracks() { for (auto& t : terminated_tracks_) t.clear(); }
+  void reset();
+  FeatureTrackerOptions options_;
+  const size_t bundle_size_;
+  std::vector<AbstractDetector::Ptr> detectors_;
+  std::vector<FeatureTracks> active_tracks_, terminated_tracks_;
 };
 
 // ---- (f3) StereoTriangulation ---------------------------------------------------------------------------------------------------

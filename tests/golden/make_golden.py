@@ -27,6 +27,10 @@ stereo_tri_ref_golden.npz what the REFERENCE's own StereoTriangulation::compute 
                       tests/helpers.py:STEREO_TRI_CASES, plus the visiting orders: pins row f3 (stereo part).
 point_opt_ref_golden.npz outputs of the REFERENCE's own Point::optimize (point.h / point.cpp compiled into libpoint_ref.so) on the 400
                       points of tests/helpers.py:point_opt_cases, unit plane and unit sphere: pins row f4 (second half).
+tracker_ref_golden.npz what the REFERENCE's own FeatureTracker::trackAndDetect (feature_tracker.cpp + feature_tracking_types / utils compiled
+                      into libfrontend_ref.so, with its detectors and alignPyr2D) leaves in every frame of three mono sequences
+                      (tests/helpers.py:TRACKER_CASES: plain tracking, reset + re-detection, detection without reset and with the last
+                      observation as template): pins row f3 (tracker part).
 klt_ref_golden.npz    outputs of the REFERENCE's own alignPyr2D (libdirect_ref.so) on the cases of tests/test_klt_cpu.py.
 Usage: python tests/golden/make_golden.py
 """
@@ -168,6 +172,14 @@ def point_opt_golden():
     print("wrote point_opt_ref_golden.npz")
 
 
+def tracker_golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    assert orc.ref_frontend_lib() is not None
+    np.savez_compressed(os.path.join(HERE, "tracker_ref_golden.npz"), **helpers.tracker_outputs(orc, "ref"))
+    print("wrote tracker_ref_golden.npz")
+
+
 def detect_golden():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
@@ -202,6 +214,7 @@ if __name__ == "__main__":
     cv_imgproc_golden()
     stereo_tri_golden()
     point_opt_golden()
+    tracker_golden()
     pose_opt_golden()
     reproject_golden()
     klt_golden()

@@ -472,3 +472,37 @@ def point_opt_outputs(orc, which, n_iter=5):
             res.append(p)
         out[f"pos_{sphere}"] = np.array(res)
     return out
+
+
+# ---- f3 (tracker part): FeatureTracker::trackAndDetect ---------------------------------------------------------------------------------
+# (scene seed, number of frames, detector type, min_tracks_to_detect_new_features, reset_before_detection, template = first observation)
+TRACKER_CASES = [(91, 5, 0, 50, True, True), (92, 5, 2, 381, True, True), (93, 4, 0, 366, False, False)]
+
+
+def tracker_sequence(case):
+    """A mono sequence: the textured plane of synth.make_align_pair(seed) seen from a camera that moves a little more every frame."""
+    seed, n = case[0], case[1]
+    d = synth.make_align_pair(seed)
+    rng = np.random.default_rng(seed)
+    imgs, T = [d["ref_img"]], synth.IDENTITY.copy()
+    for _ in range(n - 1):
+        T = synth.se3_mul(synth.se3_exp_small(rng.normal(0, 0.004, 3), rng.normal(0, 0.03, 3)), T)
+        imgs.append(d["scene"].render(T))
+    return d, imgs
+
+
+def tracker_outputs(orc, which):
+    out = {}
+    for i, case in enumerate(TRACKER_CASES):
+        d, imgs = tracker_sequence(case)
+        pyrs = [orc.create_img_pyramid(im, 5) for im in imgs]
+        if which == "ref":
+            keep = []
+            frames = [orc.make_frame(p, d["cam"], keep=keep) for p in pyrs]
+            seq = orc.ref_feature_tracker_sequence(frames, case[2], 10.0, 100.0, case[3], case[4], case[5])
+        else:
+            seq = orc.feature_tracker_sequence(pyrs, case[2], 10.0, 100.0, case[3], case[4], case[5])
+        for k, fr in enumerate(seq):
+            for key, v in fr.items():
+                out[f"{key}_{i}_{k}"] = np.asarray(v)
+    return out

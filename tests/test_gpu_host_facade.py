@@ -261,3 +261,34 @@ def test_stereo_triangulation_facade_matches_reference(orc, tmp_path):
             want = b[k, 10:13] if edgelet else p2
             np.testing.assert_allclose(opt[k, :3], want, rtol=0, atol=1e-9)
         assert (opt[b[:, 8] != 6, 3] == 2).all()
+
+
+def test_feature_tracker_facade_matches_reference(tmp_path):
+    """svo::FeatureTracker::trackAndDetect through the facade (C++ driver; every active track of a frame in one svo_cuda_align_pyr2d
+    call) leaves in every frame of three sequences what the REFERENCE's own compiled tracker left there
+    (tests/golden/tracker_ref_golden.npz): plain tracking, reset + re-detection, detection on top of live tracks."""
+    import helpers
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tracker_ref_golden.npz"))
+    for i, case in enumerate(helpers.TRACKER_CASES):
+        d, imgs = helpers.tracker_sequence(case)
+        cam = d["cam"]
+        fin, fout = tmp_path / f"tr_in_{i}.bin", tmp_path / f"tr_out_{i}.bin"
+        with open(fin, "wb") as f:
+            np.array([case[1], case[2], case[3], int(case[4]), int(case[5]), 752, 480, 5], np.int32).tofile(f)
+            np.array([cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")], np.float64).tofile(f)
+            np.array([cam["width"], cam["height"], cam["distortion"]], np.int32).tofile(f)
+            for im in imgs:
+                np.ascontiguousarray(im, np.uint8).tofile(f)
+        r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "tracker_driver"), str(fin), str(fout)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = np.fromfile(fout, np.float64)
+        p = 0
+        for k in range(case[1]):
+            n = int(out[p]); p += 1
+            cols = out[p:p + 4 * n].reshape(n, 4); p += 4 * n
+            n_active, n_term, disp = out[p:p + 3]; p += 3
+            assert n == len(g[f"px_{i}_{k}"]), (i, k, n)
+            assert np.array_equal(cols[:, 2].astype(np.int64), g[f"track_id_{i}_{k}"]) and np.array_equal(cols[:, 3], g[f"score_{i}_{k}"])
+            np.testing.assert_allclose(cols[:, :2], g[f"px_{i}_{k}"], rtol=0, atol=1e-3)   # KLT positions (bit-equal in practice)
+            assert int(n_active) == int(g[f"n_active_{i}_{k}"]) and int(n_term) == int(g[f"n_terminated_{i}_{k}"])
+            assert abs(disp - float(g[f"disparity_{i}_{k}"])) < 1e-3
