@@ -255,23 +255,40 @@ SVO_D int angleBin(int gx, int gy) {
 
 constexpr int kHistWarps = 8;
 
-// One warp per (frame, cell): decode the winner and compute its gradient-orientation histogram angle (half patch 4).
+// A CTA decodes 256 cells: empty ones at once, then one warp per winner computes the gradient-orientation histogram angle (half patch 4).
 __global__ void __launch_bounds__(kHistWarps * 32) edgelet_decode_kernel(PyrView v, int first, const unsigned long long* keys,
                                                                        int n_cells, size_t n, int threshold,
                                                                        const int8_t* __restrict__ bins, svo_corner* out) {
   __shared__ double s_mag[kHistWarps][81];
   __shared__ int8_t s_bin[kHistWarps][84];
   __shared__ double s_hist[kHistWarps][36];
+  __shared__ int s_list[kHistWarps * 32];
+  __shared__ int s_count;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t i = (size_t)blockIdx.x * kHistWarps + warp;
-  if (i >= n) return;
+  // pass 1, one thread per cell: empty cells are written at once, winners are compacted (most cells are empty when FAST corners
+  // already occupy the grid: ~17 winners per frame of 416 cells)
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  {
+    const size_t ci = (size_t)blockIdx.x * (kHistWarps * 32) + threadIdx.x;
+    if (ci < n) {
+      const float sc0 = scoreOfKey((unsigned)(keys[ci] >> 32));
+      if (sc0 > (float)threshold) {
+        s_list[atomicAdd(&s_count, 1)] = threadIdx.x;
+      } else {
+        svo_corner e;
+        e.x = 0; e.y = 0; e.level = 0; e.score = (float)threshold; e.angle = 0.0f;
+        out[ci] = e;
+      }
+    }
+  }
+  __syncthreads();
+  // pass 2, one warp per winner
+  for (int wi = warp; wi < s_count; wi += kHistWarps) {
+  const size_t i = (size_t)blockIdx.x * (kHistWarps * 32) + s_list[wi];
   const unsigned long long key = keys[i];
   const float sc = scoreOfKey((unsigned)(key >> 32));
   svo_corner c;
-  if (!(sc > (float)threshold)) {
-    if (lane == 0) { c.x = 0; c.y = 0; c.level = 0; c.score = (float)threshold; c.angle = 0.0f; out[i] = c; }
-    return;
-  }
   const unsigned order = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
   const int py = (order >> 14) & 0x3FFF, px = order & 0x3FFF;
   const int frame = first + (int)(i / (size_t)n_cells);
@@ -331,6 +348,8 @@ __global__ void __launch_bounds__(kHistWarps * 32) edgelet_decode_kernel(PyrView
     c.x = 2 * px; c.y = 2 * py; c.level = 0; c.score = sc; c.angle = (float)angle;
     out[i] = c;
   }
+  __syncwarp();
+  }  // winners of this CTA
 }
 
 __global__ void angle_bin_table_kernel(int8_t* out) {  // bins of every gradient (gx, gy) in [-255, 255]^2, row = gy + 255
@@ -395,7 +414,7 @@ int edgeletDeviceImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int
     edgelet_score_kernel<<<dim3(n_tiles, nf, 1), kThreadsE, 0, ctx->stream>>>(v, P);
     SVO_LAUNCH_CHECK(ctx);
   }
-  edgelet_decode_kernel<<<(unsigned)((n + kHistWarps - 1) / kHistWarps), kHistWarps * 32, 0, ctx->stream>>>(v, first, keys, n_cells, n,
+  edgelet_decode_kernel<<<(unsigned)((n + kHistWarps * 32 - 1) / (kHistWarps * 32)), kHistWarps * 32, 0, ctx->stream>>>(v, first, keys, n_cells, n,
                                                                                                         threshold, ctx->angle_bins, d_out);
   SVO_LAUNCH_CHECK(ctx);
   return SVO_OK;

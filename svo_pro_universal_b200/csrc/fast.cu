@@ -129,16 +129,19 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
   const int x0 = tx * kTW, y0 = ty * kTH;
   const int thr = P.threshold;
 
-  // stage tile + halo with aligned 128-bit loads (x0 - 16 and the row pitch are multiples of 16)
+  // stage tile + halo with 16-byte cp.async (x0 - 16 and the row pitch are multiples of 16; chunks outside the image are zero-filled
+  // through src-size 0); the score tile is cleared while the copies are in flight
   for (int i = tid; i < kSRows * (kSPitch / 16); i += kThreadsFast) {
     const int r = i / (kSPitch / 16), q = i - r * (kSPitch / 16);
     const int gy = y0 - kHalo + r, gx = x0 - kPadL + q * 16;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (gy >= 0 && gy < rows && gx >= 0 && gx < pitch) w = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx));
-    *reinterpret_cast<uint4*>(&s_img[r * kSPitch + q * 16]) = w;
+    const bool in = gy >= 0 && gy < rows && gx >= 0 && gx < pitch;
+    const uint8_t* src = in ? img + (size_t)gy * pitch + gx : img;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_img[r * kSPitch + q * 16]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
   }
   for (int i = tid; i < kTH * kTW * 2 / 16; i += kThreadsFast) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) { s_ncand = 0; s_ncorner = 0; }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   // stage 1: quick reject, one warp per tile row, 4 pixels per lane

@@ -11,8 +11,8 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def test_oracle_matches_reference_golden(orc):
     g = np.load(os.path.join(GOLD, "point_opt_ref_golden.npz"))
-    o = helpers.point_opt_outputs(orc, "orc")
-    c = helpers.point_opt_cases()
+    c = {k: g[k] for k in helpers.POINT_OPT_INPUT_KEYS}  # the stored inputs (see helpers.point_opt_outputs)
+    o = helpers.point_opt_outputs(orc, "orc", c=c)
     for sphere in (0, 1):
         assert np.array_equal(o[f"pos_{sphere}"], g[f"pos_{sphere}"])  # bit for bit
         err0 = np.linalg.norm(c["pos0"] - c["pos_true"], axis=1)
@@ -26,6 +26,6 @@ def test_compiled_reference_agrees_with_golden(orc):
     if orc.ref_point_lib() is None:
         return
     g = np.load(os.path.join(GOLD, "point_opt_ref_golden.npz"))
-    r = helpers.point_opt_outputs(orc, "ref")
+    r = helpers.point_opt_outputs(orc, "ref", c={k: g[k] for k in helpers.POINT_OPT_INPUT_KEYS})
     for k in r:
         assert np.array_equal(r[k], g[k]), k
