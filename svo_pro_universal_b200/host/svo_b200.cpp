@@ -865,6 +865,54 @@ void AbstractDetector::detect(const FramePtr& frame) {
   frame->num_features_ = frame->px_vec_.size();
 }
 
+// ---- DepthFilter::addKeyframe / initializeSeeds ---------------------------------------------------------------------------------------
+DepthFilter::DepthFilter(const DepthFilterOptions& options, const DetectorOptions& detector_options, const CameraPtr& cam)
+    : DepthFilter(options) {
+  feature_detector_ = feature_detection_utils::makeDetector(detector_options, cam);
+}
+
+void DepthFilter::addKeyframe(const FramePtr& frame, const double depth_mean, const double depth_min, const double depth_max) {
+  if (!feature_detector_) throw b200::Error("DepthFilter::addKeyframe: no feature detector (use the detector-building constructor)");
+  depth_filter_utils::initializeSeeds(frame, feature_detector_, options_.max_n_seeds_per_frame, float(depth_min), float(depth_max),
+                                      float(depth_mean));
+}
+
+namespace depth_filter_utils {
+void initializeSeeds(const FramePtr& frame, const std::shared_ptr<AbstractDetector>& feature_detector, const size_t max_n_seeds,
+                     const float depth_min, const float depth_max, const float depth_mean) {
+  const int max_n_features = int(max_n_seeds) - int(frame->numFeatures());
+  if (max_n_features <= 0) return;  // "Have already enough features."
+  Keypoints new_px; Scores new_scores; Levels new_levels; Gradients new_grads; FeatureTypes new_types;
+  feature_detector->detect(b200::ensureGpu(*frame), size_t(max_n_features), new_px, new_scores, new_levels, new_grads, new_types);
+  // (the reference writes straight into the frame when it has no features yet and through temporaries otherwise, :283-320; the
+  // resulting columns are the same)
+  (void)depth_max;
+  frame->seed_mu_range_ = 1.0 / double(depth_min);                                 // seed::getMeanRangeFromDepthMinMax (seed.h:135-138)
+  const double mu = 1.0 / double(depth_mean);                                       // seed::getMeanFromDepth (seed.h:130-133)
+  const double sigma2 = frame->seed_mu_range_ * frame->seed_mu_range_ / 36.0;       // seed::getInitSigma2FromMuRange (seed.h:140-143)
+  frame->landmark_vec_.resize(frame->numFeatures(), nullptr);
+  frame->seed_ref_vec_.resize(frame->numFeatures());
+  for (size_t i = 0; i < new_px.size(); ++i) {
+    FeatureType t;
+    if (new_types[i] == FeatureType::kCorner) t = FeatureType::kCornerSeed;
+    else if (new_types[i] == FeatureType::kEdgelet) t = FeatureType::kEdgeletSeed;
+    else if (new_types[i] == FeatureType::kMapPoint) t = FeatureType::kMapPointSeed;
+    else throw b200::Error("initializeSeeds: unknown feature type");
+    frame->px_vec_.push_back(new_px[i]);
+    frame->f_vec_.push_back(normalizedBearing(frame->cam_->model, new_px[i]));
+    frame->grad_vec_.push_back(new_grads[i]);
+    frame->score_vec_.push_back(new_scores[i]);
+    frame->level_vec_.push_back(new_levels[i]);
+    frame->type_vec_.push_back(t);
+    frame->depth_vec_.push_back(-1.0);
+    frame->invmu_sigma2_a_b_vec_.push_back({mu, sigma2, 10.0, 10.0});
+    frame->landmark_vec_.push_back(nullptr);
+    frame->seed_ref_vec_.push_back(SeedRef());
+  }
+  frame->num_features_ = frame->px_vec_.size();
+}
+}  // namespace depth_filter_utils
+
 // ---- Point::optimize / optimizeStructure ------------------------------------------------------------------------------------------
 static void optimizePointsOnDevice(const std::vector<Point*>& pts, size_t n_iter, bool sphere) {
   std::vector<double> pos, obs_f, T_f_w;

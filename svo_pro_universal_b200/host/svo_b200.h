@@ -273,9 +273,18 @@ struct DepthFilterOptions {  // src/svo_direct/include/svo/direct/depth_filter.h
   bool scan_epi_unit_sphere = false;
   bool affine_est_offset = true;
   bool affine_est_gain = false;
+  size_t max_n_seeds_per_frame = 200;  // depth_filter.h:61
 };
 
+class AbstractDetector;
+struct DetectorOptions;
+
 namespace depth_filter_utils {  // depth_filter.h:179-236
+// depth_filter.h:181-188; depth_filter.cpp:254-365: detect new features in the cells the detector's grid leaves free (device call
+// through the detector facade), append them as corner / edgelet seeds with mu = 1 / depth_mean, sigma2 = (1 / depth_min)^2 / 36,
+// a = b = 10, and set the frame's seed_mu_range_.
+void initializeSeeds(const FramePtr& frame, const std::shared_ptr<AbstractDetector>& feature_detector, const size_t max_n_seeds,
+                     const float depth_min, const float depth_max, const float depth_mean);
 bool updateSeed(const Frame& cur_frame, Frame& ref_frame, const size_t& seed_index, Matcher& matcher,
                 const FloatType sigma2_convergence_threshold, const bool check_visibility = true, const bool check_convergence = false,
                 const bool use_vogiatzis_update = true);
@@ -286,7 +295,13 @@ double computeTau(const Transformation& T_ref_cur, const BearingVector& f, const
 class DepthFilter {
  public:
   DepthFilterOptions options_;
+  std::shared_ptr<AbstractDetector> feature_detector_;  // depth_filter.h:95 (set by the detector-building constructor)
   explicit DepthFilter(const DepthFilterOptions& options);
+  // depth_filter.h:80-84: the constructor that builds its own detector through makeDetector
+  DepthFilter(const DepthFilterOptions& options, const DetectorOptions& detector_options, const CameraPtr& cam);
+  // DepthFilter::addKeyframe (depth_filter.cpp:89-133, non-threaded branch): initializeSeeds on the new keyframe
+  void addKeyframe(const FramePtr& frame, const double depth_mean, const double depth_min, const double depth_max);
+  void reset() {}  // depth_filter.cpp:135-144 clears the worker thread's job queue; there is no worker thread here
   // DepthFilter::updateSeeds (depth_filter.cpp:200-249, non-threaded branch): every seed of every ref frame against cur_frame,
   // one batched launch; returns the number of successful updates.
   size_t updateSeeds(const std::vector<FramePtr>& ref_frames_with_seeds, const FramePtr& cur_frame);

@@ -76,6 +76,23 @@ int main(int argc, char** argv) {
       }
       ref->clearFeatureStorage();
     }
+    // (d4) DepthFilter::addKeyframe -> depth_filter_utils::initializeSeeds on the ref frame (FastGrad detector, at most 200 seeds)
+    {
+      DetectorOptions o;
+      o.detector_type = DetectorType::kFastGrad;
+      DepthFilter df(DepthFilterOptions(), o, cam);
+      df.addKeyframe(ref, 3.0, 1.0, 10.0);
+      out.push_back(double(ref->num_features_));
+      out.push_back(ref->seed_mu_range_);
+      for (size_t i = 0; i < ref->num_features_; ++i) {
+        out.push_back(ref->px_vec_[i][0]); out.push_back(ref->px_vec_[i][1]); out.push_back(ref->score_vec_[i]); out.push_back(ref->level_vec_[i]);
+        out.push_back(double(int(ref->type_vec_[i])));
+        for (int k = 0; k < 4; ++k) out.push_back(ref->invmu_sigma2_a_b_vec_[i][k]);
+      }
+      df.addKeyframe(ref, 3.0, 1.0, 10.0);  // already 200 features: nothing is added
+      out.push_back(double(ref->num_features_));
+      ref->clearFeatureStorage();
+    }
     // features of the test set
     for (int i = 0; i < N; ++i) {
       ref->px_vec_.push_back({px[2 * i], px[2 * i + 1]});

@@ -78,6 +78,21 @@ def test_cpp_facades_match_oracle(orc, tmp_path):
         if det_type == orc.DETECTOR_FAST_GRAD:
             assert (got["type"] == 6).sum() > 5 and (got["type"] == 7).sum() > 100
 
+    # (d4) DepthFilter::addKeyframe: the 200 best FastGrad features become seeds with the reference's initial state
+    n_seed = int(out[p]); p += 1
+    mu_range = out[p]; p += 1
+    seeds = out[p:p + 9 * n_seed].reshape(n_seed, 9); p += 9 * n_seed
+    n_after = int(out[p]); p += 1
+    o = orc.detect_features(orc.DETECTOR_FAST_GRAD, pyr, max_n=200)
+    assert n_seed == len(o["score"]) == 200 == n_after and mu_range == 1.0
+    assert np.array_equal(seeds[:, 2], o["score"])
+    cut = o["score"].min()
+    keep = seeds[:, 2] > cut  # std::sort is unstable: entries at the cut score may differ
+    assert sorted(map(tuple, seeds[keep][:, :4])) == sorted(zip(o["px"][o["score"] > cut, 0], o["px"][o["score"] > cut, 1], o["score"][o["score"] > cut],
+                                                            o["level"][o["score"] > cut].astype(float)))
+    assert set(seeds[:, 4]) <= {0.0, 1.0} and (seeds[:, 4] == 1.0).sum() > 100      # kCornerSeed / kEdgeletSeed
+    assert np.array_equal(seeds[:, 5:9], np.tile([1.0 / 3.0, 1.0 / 36.0, 10.0, 10.0], (n_seed, 1)))
+
     # (b) SparseImgAlign::run writes cur->T_f_w_
     n_tracked = int(out[p]); p += 1
     T_f_w = out[p:p + 7]; p += 7
