@@ -14,6 +14,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _build_drivers():
+    """The facade library and the C++ drivers are built once per module (no-ops when they travelled with the snapshot)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "svo_pro_universal_b200", "host")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+
+
 def _T_f_w(T_cam_imu, T_imu_world):
     return synth.se3_mul(T_cam_imu, T_imu_world)
 

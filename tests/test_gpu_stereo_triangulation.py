@@ -92,3 +92,30 @@ def test_stereo_triangulation_arguments(ctx):
     L = capi.lib()
     assert L.svo_cuda_stereo_triangulate(ctx._h, pyr._h, pyr._h, None, None, None, None, None, None, 1, None, 0, None, None, None,
                                          C.c_double(0.3), C.c_double(1.0), C.c_double(0.02), None, None, None, 0) == -1
+
+
+def test_stereo_triangulation_ragged_and_empty_pairs(ctx, orc):
+    """Pairs without entries and pairs that want nothing (n_desired = 0) sit between ordinary pairs in one call."""
+    g = np.load(os.path.join(GOLD, "stereo_tri_ref_golden.npz"))
+    case = helpers.STEREO_TRI_CASES[0]
+    pyr0, pyr1, cam, T_f1f0, Twc, begin, ftrs, orders, oracle = _setup(ctx, orc, [case], g, [0])
+    n = len(ftrs)
+    # pair 0: ordinary; pair 1: no entries; pair 2: same entries, wants 0; pair 3: wants 5
+    begin4 = np.array([0, n, n, 2 * n, 3 * n], np.int32)
+    ft4 = np.concatenate([ftrs, ftrs, ftrs])
+    idx = np.zeros(4, np.int32)
+    mopt = capi.matcher_options(max_epi_search_steps=500, subpix_refinement=1)
+    res, stats = capi.stereo_triangulate(ctx, pyr0, pyr1, cam, cam, T_f1f0, np.repeat(Twc, 4, 0), begin4, ft4, np.array([case[3], 7, 0, 5], np.int32),
+                                         np.zeros(4, np.int32), mopt, case[4], case[5], case[6], frame0_idx=idx, frame1_idx=idx)
+    o, ns, nf = oracle[0]
+    assert np.array_equal(res["status"][:n], o["status"]) and stats["n_succeeded"][0] == ns and stats["n_failed"][0] == nf
+    assert stats["n_succeeded"][1] == 0 and stats["n_failed"][1] == 0
+    assert (res["status"][n:2 * n] == capi.STEREO_NOT_REACHED).all() and stats["n_succeeded"][2] == 0 and stats["n_failed"][2] == 0
+    r3 = res[2 * n:]
+    first5 = np.flatnonzero(o["match_result"] == 0)[:5]
+    assert stats["n_succeeded"][3] == 5 and np.array_equal(np.flatnonzero(r3["status"] == 2), first5)
+    assert (r3["status"][first5[-1] + 1:] == capi.STEREO_NOT_REACHED).all()
+    # an empty batch is fine
+    res0, stats0 = capi.stereo_triangulate(ctx, pyr0, pyr1, cam, cam, T_f1f0, Twc, np.zeros(2, np.int32), ftrs[:0], np.array([3], np.int32),
+                                           np.zeros(1, np.int32), mopt)
+    assert stats0["n_succeeded"][0] == 0 and len(res0) == 0
