@@ -1,11 +1,13 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header for the rules).
 //
-// Rows a1-a6 of SURVEY.md §8: image pyramid, FAST-10 detect / score / 3x3 non-max,
-// grid-cell arg-max (fastDetector) and fillFeatures.
+// Rows a1-a6 and f2 of SURVEY.md §8: image pyramid, FAST-10 detect / score / 3x3 non-max, grid-cell arg-max (fastDetector),
+// fillFeatures, the edgelet detector (Gaussian 3x3, Scharr, the reference's neighbour test, angle histogram) and the three grid
+// detector classes (FastDetector, GradientDetectorGrid, FastGradDetector).
 //
-// Parity status: a2-a4 are PINNED against the reference's own fast_neon sources compiled
-// into oracle/_ref/libfast_ref.so (tests/test_oracle_fast.py); a1, a5, a6 are
-// restatements ("parity unpinned": the reference ships no vectors and needs OpenCV).
+// Parity status: PINNED. a2-a4 against the reference's own fast_neon sources (oracle/_ref/libfast_ref.so), a1 against its
+// vision.cpp (libdirect_ref.so), a5 / a6 / f2 against its feature_detection.cpp + feature_detection_utils.cpp (libdetect_ref.so);
+// the two OpenCV imgproc functions the edgelet detector executes are restated here and pinned bit-for-bit against the real
+// OpenCV (cv2 4.13) through tests/golden/cv_imgproc_golden.npz. Tests: tests/test_reference_pins_cpu.py, tests/test_edgelet_cpu.py.
 #pragma once
 #include <vector>
 #include <numeric>
