@@ -292,7 +292,9 @@ typedef struct { int n_succeeded, n_failed; } svo_stereo_stats;
  * two std::random_shuffle calls, :34-79) with Matcher::findEpipolarMatchDirect (align_1d = isEdgelet(type), the inverse-depth
  * range given) until n_desired[b] = triangulate_n_features - frame0->numLandmarks() of them succeeded; n_features_in_frame1[b] =
  * frame1->num_features_ before the call. mopt: the Matcher options (the reference sets max_epi_search_steps = 500 and
- * subpix_refinement = true, :90-91; its align_1d field is ignored). results [n_features], stats [B]. n_features = feat_begin[B]. */
+ * subpix_refinement = true, :90-91; its align_1d field is ignored). results [n_features], stats [B]. n_features = feat_begin[B].
+ * Entries whose `type` is negative are holes: they are not matched, not counted and come back SVO_STEREO_NOT_REACHED, so that a
+ * device-resident caller can pass fixed-shape lists (e.g. one slot per grid cell) without compacting them on the host. */
 int svo_cuda_stereo_triangulate(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr0, const svo_cuda_pyr* pyr1, const int* frame0_idx,
                                 const int* frame1_idx, const svo_camera* cam0, const svo_camera* cam1, const double* T_f1f0,
                                 const double* T_world_cam0, int B, const int* feat_begin, int n_features, const svo_feature* ftrs,

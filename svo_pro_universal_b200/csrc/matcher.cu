@@ -69,6 +69,10 @@ __global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P)
                                     P.px_guess[2 * i + 1], P.opt, pwb, m);
     writeOut(g, P.out, i, m, res, 0.0);
   } else if (MODE == 1) {
+    if (P.align1d_from_type && ft.type < 0) {  // a hole in a fixed-shape entry list (svo_cuda_stereo_triangulate): nothing to match
+      if (g.r == 0) { svo_match_out o; memset(&o, 0, sizeof(o)); o.result = -2; P.out[i] = o; }
+      return;
+    }
     double depth = 0.0;
     const double* dd = P.depth + (P.depth_shared ? 0 : 3 * (size_t)i);
     const bool a1d = P.align1d_from_type ? isEdgeletType(ft.type) : P.opt.align_1d != 0;
@@ -149,6 +153,7 @@ __global__ void stereo_commit_kernel(const svo_match_out* match, const svo_featu
   for (int c0 = lo; c0 < hi; c0 += blockDim.x) {
     const int i = c0 + tid;
     const bool ok = i < hi && match[i].result == 0;  // Matcher::MatchResult::kSuccess
+    const bool hole = i < hi && match[i].result == -2;  // entry with a negative type: not part of the list
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
     if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
@@ -163,7 +168,7 @@ __global__ void stereo_commit_kernel(const svo_match_out* match, const svo_featu
       r.slot = -1;
       r.match_result = -1;
       const bool reached = before < want;  // the loop is still running when it gets to entry i
-      if (reached) {
+      if (reached && !hole) {
         const svo_match_out m = match[i];
         r.match_result = m.result;
         if (ok) {

@@ -54,9 +54,10 @@ def make_stereo_scene(seed, n0=180, n1=150):
 class StereoFrontendBatch:
     """B stereo frame pairs made of `scenes` (unique synthetic stereo scenes, tiled) resident on one GPU."""
 
-    def __init__(self, ctx, scenes, B, device, max_features=180):
+    def __init__(self, ctx, scenes, B, device, max_features=180, stereo_triangulation=False):
         import torch
         self.torch, self.ctx, self.B, self.dev, self.F = torch, ctx, B, device, max_features
+        self.with_stereo = bool(stereo_triangulation)
         # ONE stream for the library's kernels and for torch's glue ops (slicing the aligner's poses, resetting the grid):
         # the context is switched to a torch stream and every step runs with that stream current
         self.stream = torch.cuda.Stream(device=device)
@@ -175,6 +176,22 @@ class StereoFrontendBatch:
         self.threshold_secondary = 100
         self.d_corners = torch.zeros(B * self.n_cells * capi.CORNER_DTYPE.itemsize, dtype=torch.uint8, device=device)
         self.d_edgelets = torch.zeros_like(self.d_corners)
+        # ---- optional keyframe stage: StereoTriangulation::compute on the features just detected in the new left frame
+        # (stereo_triangulation.cpp:87-137; the visiting order is corners then edgelets in cell order instead of the reference's
+        # std::random_shuffle, entries of empty cells are holes) against the new right frame
+        if self.with_stereo:
+            nE = 2 * self.n_cells
+            self.st_T_f1f0 = synth.se3_mul(self.T_cam_imu[1], synth.se3_inv(self.T_cam_imu[0]))
+            self.st_begin = t((np.arange(B + 1) * nE).astype(np.int32))
+            self.st_want = t(np.full(B, 120, np.int32))
+            self.st_slot0 = t(np.zeros(B, np.int32))
+            self.st_f0 = t(np.arange(B, dtype=np.int32))
+            self.st_f1 = t((B + np.arange(B)).astype(np.int32))
+            self.st_ftrs = torch.zeros((B * nE, 8), dtype=torch.float64, device=device)
+            self.st_mopt = capi.matcher_options(max_epi_search_steps=500, subpix_refinement=1)
+            self.d_stereo = torch.zeros(B * nE * capi.STEREO_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=device)
+            self.d_stereo_stats = torch.zeros(B * capi.STEREO_STATS_DTYPE.itemsize, dtype=torch.uint8, device=device)
+            self.st_Twc = torch.zeros((B, 7), dtype=torch.float64, device=device)
         torch.cuda.synchronize(device)   # the uploads above ran on torch's default stream
 
     def release(self):
@@ -183,6 +200,7 @@ class StereoFrontendBatch:
         self.ctx.set_stream(0)
 
     STAGES = ("pyramid", "sparse_align", "reproject", "pose_optimize", "update_seeds", "fastgrad_detect")
+    STEREO_STAGE = "stereo_triangulate"  # stage 6 when the batch was built with stereo_triangulation=True
 
     def _imu_pose(self, T_f_w0):
         """T_imu_world = T_imu_cam0 * T_f_w of the left camera ([B,7] quaternion + translation), on the device."""
@@ -241,6 +259,42 @@ class StereoFrontendBatch:
         capi.fastgrad_detect(self.ctx, self.cur, self.det_opt, self.threshold_secondary, first=0, count=B, corners_out=self.d_corners,
                              edgelets_out=self.d_edgelets)
         mark(5)
+        if self.with_stereo:
+            self._stereo_stage(cur_T)
+            mark(6)
+
+    def _stereo_stage(self, cur_T):
+        """Device-side glue: the per-cell corners / edgelets of the new left frames become svo_feature records (holes where a cell is
+        empty), the aligner's left pose is inverted, then ONE svo_cuda_stereo_triangulate call for the whole batch."""
+        torch = self.torch
+        B, nc = self.B, self.n_cells
+        cam = self.scenes[0]["cam"]
+        ci = torch.cat([self.d_corners.view(torch.int32).view(B, nc, 5), self.d_edgelets.view(torch.int32).view(B, nc, 5)], 1)
+        cf = torch.cat([self.d_corners.view(torch.float32).view(B, nc, 5), self.d_edgelets.view(torch.float32).view(B, nc, 5)], 1)
+        thr = torch.cat([torch.full((nc,), float(self.det_opt.threshold), device=self.dev),
+                         torch.full((nc,), float(self.threshold_secondary), device=self.dev)]).to(torch.float32)
+        ftype = torch.cat([torch.full((nc,), 7, device=self.dev), torch.full((nc,), 6, device=self.dev)]).to(torch.int32)  # kCorner, kEdgelet
+        valid = cf[..., 3] > thr[None, :]
+        x, y = ci[..., 0].to(torch.float64), ci[..., 1].to(torch.float64)
+        bx, by = (x - cam["cx"]) / cam["fx"], (y - cam["cy"]) / cam["fy"]  # pinhole without distortion (the chain's cameras)
+        n = torch.sqrt(bx * bx + by * by + 1.0)
+        rec = self.st_ftrs.view(B, 2 * nc, 8)
+        rec[..., 0], rec[..., 1] = x, y
+        rec[..., 2], rec[..., 3], rec[..., 4] = bx / n, by / n, 1.0 / n
+        rec[..., 5], rec[..., 6] = torch.cos(cf[..., 4]).to(torch.float64), torch.sin(cf[..., 4]).to(torch.float64)
+        r32 = self.st_ftrs.view(torch.int32).view(B, 2 * nc, 16)
+        r32[..., 14] = torch.where(valid, ftype[None, :].expand(B, -1), torch.full_like(ci[..., 0], -1))
+        r32[..., 15] = ci[..., 2]
+        # T_world_cam of the new left frames = inverse of the aligner's T_f_w
+        T = cur_T.view(B, 2, 7)[:, 0]
+        qi = T[:, :4] * torch.tensor([1.0, -1.0, -1.0, -1.0], dtype=torch.float64, device=self.dev)
+        u, v, aw = qi[:, 1:4], T[:, 4:7], qi[:, 0:1]
+        uv = torch.cross(u, v, dim=1)
+        self.st_Twc[:, :4] = qi
+        self.st_Twc[:, 4:] = -(v + 2.0 * (aw * uv + torch.cross(u, uv, dim=1)))
+        capi.stereo_triangulate(self.ctx, self.cur, self.cur, self.cam, self.cam, self.st_T_f1f0, self.st_Twc, self.st_begin,
+                                self.st_ftrs.view(torch.uint8).view(-1), self.st_want, self.st_slot0, self.st_mopt, frame0_idx=self.st_f0,
+                                frame1_idx=self.st_f1, results=self.d_stereo, stats=self.d_stereo_stats)
 
     def results(self):
         """Host copies of every stage's outputs (numpy)."""
@@ -255,4 +309,9 @@ class StereoFrontendBatch:
                     pose_opt_has=self.po_has.cpu().numpy(), pose_opt_xyz=self.po_xyz.cpu().numpy(),
                     corners=self.d_corners.cpu().numpy().view(capi.CORNER_DTYPE).reshape(self.B, self.n_cells),
                     edgelets=self.d_edgelets.cpu().numpy().view(capi.CORNER_DTYPE).reshape(self.B, self.n_cells),
-                    entry_begin=self.entry_begin.cpu().numpy())
+                    entry_begin=self.entry_begin.cpu().numpy(),
+                    **(dict(stereo=self.d_stereo.cpu().numpy().view(capi.STEREO_RESULT_DTYPE).reshape(self.B, 2 * self.n_cells),
+                            stereo_stats=self.d_stereo_stats.cpu().numpy().view(capi.STEREO_STATS_DTYPE),
+                            stereo_ftrs=self.st_ftrs.cpu().numpy().view(capi.FEATURE_DTYPE).reshape(self.B, 2 * self.n_cells),
+                            stereo_Twc=self.st_Twc.cpu().numpy(), align_T_f_w=self.d_align.cpu().numpy().view(capi.ALIGN_RESULT_DTYPE)["T_f_w"])
+                       if self.with_stereo else {}))

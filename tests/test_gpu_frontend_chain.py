@@ -123,3 +123,46 @@ def test_stereo_frontend_chain_matches_oracle(ctx, orc):
         n_ok += k_ok
         p += n
     assert out["n_seed_ok"] == n_ok > 0
+
+
+def test_chain_stereo_triangulation_stage(ctx, orc):
+    """The optional keyframe stage of the chain: the corners / edgelets FastGrad just found in the new left frame are triangulated
+    against the new right frame on the device (fixed-shape entry lists with holes, pose from the aligner). Checked against the
+    oracle's StereoTriangulation loop on the very features and pose the device stage used."""
+    import torch
+    scenes = [frontend.make_stereo_scene(s) for s in (81, 82)]
+    B = 3
+    fb = frontend.StereoFrontendBatch(ctx, scenes, B, torch.device("cuda", 0), stereo_triangulation=True)
+    fb.step()
+    out = fb.results()
+    fb.release()
+    n_tri = 0
+    for i in range(B):
+        sc = scenes[i % 2]
+        keep = []
+        ft_all, res_all = out["stereo_ftrs"][i], out["stereo"][i]
+        sel = np.flatnonzero(ft_all["type"] >= 0)
+        assert len(sel) > 300 and (res_all["status"][ft_all["type"] < 0] == capi.STEREO_NOT_REACHED).all()
+        # the entry list = corners then edgelets in cell order, exactly what the detector stage reported
+        cg, eg = out["corners"][i], out["edgelets"][i]
+        exp_px = np.concatenate([np.stack([cg["x"], cg["y"]], 1)[cg["score"] > 10], np.stack([eg["x"], eg["y"]], 1)[eg["score"] > 100]])
+        assert np.array_equal(ft_all["px"][sel], exp_px.astype(np.float64))
+        # oracle frames: the new left / right images, left pose = what the aligner produced (T_f_w of camera 0)
+        T_f_w0 = out["align_T_f_w"][i][0]
+        T_imu_world = synth.se3_mul(synth.se3_inv(sc["T_cam_imu"][0]), T_f_w0)
+        dq, dt = helpers.pose_diff(synth.se3_inv(T_f_w0), out["stereo_Twc"][i])
+        assert dq < 1e-12 and dt < 1e-12
+        f0 = orc.make_frame(orc.create_img_pyramid(sc["imgs"]["c0"], 5), sc["cam"], sc["T_cam_imu"][0], T_imu_world, keep=keep)
+        f1 = orc.make_frame(orc.create_img_pyramid(sc["imgs"]["c1"], 5), sc["cam"], sc["T_cam_imu"][1], T_imu_world, keep=keep)
+        ft = ft_all[sel]
+        oft = orc.make_features(ft["px"], ft["f"], ft["grad"], ft["type"], ft["level"])
+        o, ns, nf = orc.stereo_triangulate(f0, f1, oft, 120)
+        r = res_all[sel]
+        for k in ("status", "slot", "match_result", "level", "type"):
+            assert np.array_equal(r[k], o[k]), (i, k)
+        ok = r["status"] == 2
+        np.testing.assert_allclose(r["px_cur"][ok], o["px_cur"][ok], rtol=0, atol=1e-3)
+        np.testing.assert_allclose(r["xyz_world"][ok], o["xyz_world"][ok], rtol=1e-4, atol=1e-6)
+        assert out["stereo_stats"]["n_succeeded"][i] == ns and out["stereo_stats"]["n_failed"][i] == nf
+        n_tri += ns
+    assert n_tri > 200

@@ -68,6 +68,7 @@ def main():
     ap.add_argument("--unique", type=int, default=4)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--stereo", action="store_true", help="add the keyframe stage: StereoTriangulation of the features just detected")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -81,7 +82,8 @@ def main():
     ctx = capi.Context(local)
     lo, hi = shard.partition(args.pairs, world, rank)
     scenes = [frontend.make_stereo_scene(81 + s) for s in range(args.unique)]
-    fb = frontend.StereoFrontendBatch(ctx, scenes, hi - lo, dev)
+    fb = frontend.StereoFrontendBatch(ctx, scenes, hi - lo, dev, stereo_triangulation=args.stereo)
+    stage_names = fb.STAGES + ((fb.STEREO_STAGE,) if args.stereo else ())
     stream = fb.stream
     torch.cuda.set_stream(stream)
     for _ in range(args.warmup):
@@ -97,11 +99,11 @@ def main():
     sync()
     ms = e0.elapsed_time(e1) / args.steps
     # stage breakdown of one more pass (events between the stages)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(fb.STAGES) + 1)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)]
     evs[0].record(stream)
     fb.step(lambda i: evs[i + 1].record(stream))
     torch.cuda.synchronize()
-    stages = {n: evs[i].elapsed_time(evs[i + 1]) for i, n in enumerate(fb.STAGES)}
+    stages = {n: evs[i].elapsed_time(evs[i + 1]) for i, n in enumerate(stage_names)}
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
     out = fb.results()
@@ -118,6 +120,7 @@ def main():
                           "stage_ms_rank0": stages,
                           "gpu_launches_per_step": (ctx.launches - l0) // args.steps,
                           "mean_matches_per_frame": float(out["reproj_stats"]["n_matches"].mean()),
+                          "mean_triangulated_per_pair": float(out["stereo_stats"]["n_succeeded"].mean()) if args.stereo else None,
                           "seed_success_frac": out["n_seed_ok"] / max(1, fb.S),
                           "cpu_baseline": {"stereo_pairs_per_s_single_thread": cpu, "kind": "port (oracle chain)", "cores": 1}}))
     if world > 1:
