@@ -110,3 +110,43 @@ for _ in range(REPS):
                                  np.concatenate([pcs[i]["xyz_world"] for i in pidx]), np.concatenate([pcs[i]["has_xyz"] for i in pidx]),
                                  capi.pose_optimizer_options())
 print("pose optimizer iterations", float(pres["iters"].mean()), "measurements", float(pres["n_meas"].mean()))
+
+# (f3): StereoTriangulation — 256 stereo pairs x ~390 detected features (FastGrad on the device), progressive epipolar matching + commit
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers  # noqa: E402
+prs = [helpers.stereo_case(81), helpers.stereo_case(82)]
+BS = 256
+sidS = np.arange(BS) % 2
+q0 = capi.Pyramid(ctx, 2, 752, 480, 5); q1 = capi.Pyramid(ctx, 2, 752, 480, 5)
+q0.upload(np.stack([p[0]["ref_img"] for p in prs])); q1.upload(np.stack([p[1]["ref_img"] for p in prs])); q0.build(); q1.build()
+cS, eS = capi.fastgrad_detect(ctx, q0, capi.detector_options(), 100)
+ftU = []
+for k in range(2):
+    sel = [(cS[k], 10.0, 7), (eS[k], 100.0, 6)]
+    px = np.concatenate([np.stack([a["x"], a["y"]], 1)[a["score"] > t] for a, t, _ in sel]).astype(np.float64)
+    ang = np.concatenate([a["angle"][a["score"] > t] for a, t, _ in sel])
+    lv = np.concatenate([a["level"][a["score"] > t] for a, t, _ in sel])
+    ty = np.concatenate([np.full(int((a["score"] > t).sum()), v, np.int32) for a, t, v in sel])
+    fS = synth.cam_backproject(prs[k][0]["cam"], px); fS /= np.linalg.norm(fS, axis=1, keepdims=True)
+    ftU.append(capi.make_features(px, fS, np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float64), ty, lv))
+begS = np.concatenate([[0], np.cumsum([len(ftU[i]) for i in sidS])]).astype(np.int32)
+ftS = np.concatenate([ftU[i] for i in sidS])
+TwcS = np.stack([synth.se3_inv(synth.se3_mul(prs[i][0]["T_cam_imu"], prs[i][0]["T_imu_world_ref"])) for i in sidS])
+T_f1f0 = synth.se3_mul(prs[0][1]["T_cam_imu"], synth.se3_inv(prs[0][0]["T_cam_imu"]))
+camS = capi.Camera.from_dict(prs[0][0]["cam"])
+for _ in range(REPS):
+    rS, sS = capi.stereo_triangulate(ctx, q0, q1, camS, camS, T_f1f0, TwcS, begS, ftS, np.full(BS, 120, np.int32), np.zeros(BS, np.int32),
+                                     capi.matcher_options(max_epi_search_steps=500, subpix_refinement=1),
+                                     frame0_idx=sidS.astype(np.int32), frame1_idx=sidS.astype(np.int32))
+print("stereo triangulated per pair", float(sS["n_succeeded"].mean()))
+
+# (f4, second half): Point::optimize — 400 points x 128 copies
+cP = helpers.point_opt_cases()
+KP = 128
+nP, nO = len(cP["pos0"]), len(cP["obs_frame"])
+posP = np.tile(cP["pos0"], (KP, 1))
+begP = np.concatenate([[0], (cP["obs_begin"][1:][None, :] + nO * np.arange(KP)[:, None]).ravel()]).astype(np.int32)
+for _ in range(REPS):
+    pp = posP.copy()
+    itP = capi.optimize_points(ctx, pp, begP, np.tile(cP["obs_frame"], KP), np.tile(cP["obs_f"], (KP, 1)), cP["T_f_w"], 5, False)
+print("point optimizer iterations", float(itP.mean()))
