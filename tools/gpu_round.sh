@@ -28,7 +28,7 @@ if has launches; then
       python tools/prof_paths.py > gpurun_out/${tag}_launches_paths.log 2>&1
 fi
 if has ncu; then
-  for k in sparse_align_kernel pyr_down fast_level match_kernel update_seeds_kernel vogiatzis_kernel reproj_match reproj_sort pose_optimize_kernel edgelet_score edgelet_decode; do
+  for k in sparse_align_kernel pyr_down fast_level match_kernel update_seeds_kernel vogiatzis_kernel reproj_match reproj_sort pose_optimize_kernel edgelet_score edgelet_decode optimize_points_kernel stereo_commit; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/${tag}_ncu_$k \
         python tools/prof_paths.py > gpurun_out/${tag}_ncu_$k.log 2>&1
   done
