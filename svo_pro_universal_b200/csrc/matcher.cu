@@ -439,7 +439,10 @@ int svo_cuda_stereo_triangulate(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr0, con
     // Progressive matching: the reference stops a list at its n_desired-th success, so the lists are matched in chunks of list
     // positions and a list drops out once it has its successes (4 chunks, then the rest in one launch). Matching everything at
     // once visits ~3x the entries of the reference's loop at the default 120 of ~390 features.
-    constexpr int kChunk = 160, kChunks = 4;
+#ifndef SVO_STEREO_CHUNK
+#define SVO_STEREO_CHUNK 160  // A/B on the B200 (tools/time_stereo.py, chain keyframe stage per 2048 pairs): 96 -> 4.09 ms, 128 -> 4.81, 160 -> 3.66, 224 -> 4.42
+#endif
+    constexpr int kChunk = SVO_STEREO_CHUNK, kChunks = 4;
     for (int c = 0; c <= kChunks; ++c) {
       P.chunk_lo = c * kChunk;
       P.chunk_hi = c < kChunks ? (c + 1) * kChunk : 0x7FFFFFFF;
