@@ -308,6 +308,13 @@ int svo_cuda_stereo_triangulate(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr0, con
  * ok [n] (0 = the reference returns false). */
 int svo_cuda_update_filter_vogiatzis(svo_cuda_ctx* ctx, int n, const double* z, const double* tau2, const double* mu_range,
                                      double* state, uint8_t* ok, svo_mem mem);
+/* n_obs ORDERED updates per seed in ONE launch (the filter state stays in registers): z, tau2 [n_obs][n] (observation-major),
+ * state [n][4] in/out, ok [n_obs][n] (may be NULL). Equivalent to n_obs successive calls of updateFilterVogiatzis (gaussian == 0;
+ * depth_filter.h:201-205, depth_filter.cpp:501-552) or updateFilterGaussian (gaussian != 0; depth_filter.h:207-211,
+ * depth_filter.cpp:554-578; mu_range is not read and may be NULL) on the same seed. The Vogiatzis quotients are formed with shared
+ * reciprocals: results agree with the reference's to a few ulp per update, not bit for bit. */
+int svo_cuda_update_filter_seq(svo_cuda_ctx* ctx, int n, int n_obs, const double* z, const double* tau2, const double* mu_range,
+                               double* state, uint8_t* ok, int gaussian, svo_mem mem);
 /* depth_filter_utils::computeTau (depth_filter.cpp:580-596): T_ref_cur [n][7], f [n][3], z [n] -> tau [n]. */
 int svo_cuda_compute_tau(svo_cuda_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z,
                          double px_error_angle, double* tau, svo_mem mem);

@@ -167,10 +167,10 @@ def lib():
     """Load libsvo_cuda.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise SvoCudaError("libsvo_cuda.so is missing: build it with `make -C svo_pro_universal_b200/csrc` "
-                               "(there is no CPU fallback)")
-        L = C.CDLL(os.environ.get("SVO_CUDA_LIB", LIB_PATH))  # the override is for A/B experiments with alternative builds
+        path = os.environ.get("SVO_CUDA_LIB", LIB_PATH)  # the override is for A/B experiments with alternative builds
+        if not os.path.exists(path):
+            raise SvoCudaError(f"{path} is missing: build it with `make -C svo_pro_universal_b200/csrc` (there is no CPU fallback)")
+        L = C.CDLL(path)
         L.svo_cuda_last_error.restype = C.c_char_p
         L.svo_cuda_last_error.argtypes = [C.c_void_p]
         L.svo_cuda_launch_count.restype = C.c_longlong
@@ -202,6 +202,14 @@ def lib():
         L.svo_cuda_find_epipolar_match_direct.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), vp, vp, ci,
                                                           vp, vp, C.POINTER(MatcherOptions), vp, ci]
         L.svo_cuda_update_filter_vogiatzis.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci]
+        if hasattr(L, "svo_cuda_update_filter_seq"):  # absent from older A/B builds selected through SVO_CUDA_LIB
+            L.svo_cuda_update_filter_seq.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, ci, ci]
+        L.svo_cuda_edgelet_detect.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, ci]
+        L.svo_cuda_fastgrad_detect.argtypes = [vp, vp, ci, ci, C.POINTER(DetectorOptions), ci, ci, vp, vp, vp, ci]
+        L.svo_cuda_angle_histogram_bins.argtypes = [vp, vp, ci]
+        L.svo_cuda_stereo_triangulate.argtypes = [vp] * 5 + [C.POINTER(Camera), C.POINTER(Camera), vp, vp, ci, vp, ci, vp, vp, vp, cd, cd, cd,
+                                                             C.POINTER(MatcherOptions), vp, vp, ci]
+        L.svo_cuda_optimize_points.argtypes = [vp, ci, vp, vp, ci, vp, vp, ci, vp, ci, ci, vp, ci]
         L.svo_cuda_compute_tau.argtypes = [vp, ci, vp, vp, vp, cd, vp, ci]
         L.svo_cuda_update_seeds.argtypes = [vp, vp, vp, C.POINTER(Camera), C.POINTER(Camera), ci, vp, vp, vp, vp, vp, ci, vp, vp,
                                             vp, C.POINTER(MatcherOptions), C.POINTER(DepthFilterOptions), vp, vp, ci]
@@ -221,12 +229,36 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_warp_affine", "svo_cuda_find_match_direct", "svo_cuda_find_epipolar_match_direct",
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
     "svo_cuda_reproject_match", "svo_cuda_pose_optimize", "svo_cuda_edgelet_detect", "svo_cuda_fastgrad_detect",
-    "svo_cuda_angle_histogram_bins", "svo_cuda_stereo_triangulate", "svo_cuda_optimize_points",
+    "svo_cuda_angle_histogram_bins", "svo_cuda_stereo_triangulate", "svo_cuda_optimize_points", "svo_cuda_update_filter_seq",
 ]
 
 
 def _is_torch(a):
     return hasattr(a, "data_ptr")
+
+
+_TORCH_NAMES = {"float64": "f8", "float32": "f4", "int32": "i4", "int64": "i8", "uint8": "u1", "int8": "i1", "int16": "i2"}
+
+
+def _check(a, code, n_items=None, what="array"):
+    """The C ABI takes raw pointers: verify the element type (numpy dtype / torch dtype; "u1" also accepts a byte view of a
+    struct array) and, when given, the minimum number of items, so that a float32 / int64 / short array is an error, not garbage."""
+    if a is None:
+        return a
+    if _is_torch(a):
+        got = _TORCH_NAMES.get(str(a.dtype).replace("torch.", ""), str(a.dtype))
+        n = a.numel()
+    else:
+        assert isinstance(a, np.ndarray), f"{what}: expected a numpy array or torch tensor"
+        got = a.dtype.str.lstrip("<|=") if a.dtype.fields is None else "struct"
+        n = a.size
+    if code == "struct":  # POD records: a numpy structured array or a uint8 tensor holding the same bytes
+        assert got in ("struct", "u1"), f"{what}: expected a record array or its byte view, got {got}"
+    else:
+        assert got == code, f"{what}: expected element type {code}, got {got}"
+        if n_items is not None:
+            assert n >= n_items, f"{what}: expected at least {n_items} items, got {n}"
+    return a
 
 
 def _ptr(a):
@@ -410,6 +442,12 @@ def sparse_align(ctx, ref_pyrs, cur_pyrs, cams, T_cam_imu, T_imu_world_ref, T_im
     T_cam_imu = np.ascontiguousarray(T_cam_imu, np.float64).reshape(n_cams, 7)
     if results is None:
         results = np.zeros(B, ALIGN_RESULT_DTYPE)
+    nf = B * n_cams * max_features
+    _check(ref_frame_idx, "i4", B * n_cams, "ref_frame_idx"); _check(cur_frame_idx, "i4", B * n_cams, "cur_frame_idx")
+    _check(T_imu_world_ref, "f8", 7 * B, "T_imu_world_ref"); _check(T_imu_world_cur, "f8", 7 * B, "T_imu_world_cur")
+    _check(n_features, "i4", B * n_cams, "n_features"); _check(px, "f8", 2 * nf, "px"); _check(f, "f8", 3 * nf, "f")
+    _check(depth, "f8", nf, "depth"); _check(eligible, "u1", nf, "eligible"); _check(priors, "struct", None, "priors")
+    _check(results, "struct", None, "results")
     ps, kind = _ptrs(ref_frame_idx, cur_frame_idx, T_imu_world_ref, T_imu_world_cur, n_features, px, f, depth, eligible, priors, results)
     ctx.check(lib().svo_cuda_sparse_align(ctx._h, n_cams, rp, cp, ps[0], ps[1], cam_arr, C.c_void_p(T_cam_imu.ctypes.data), B,
                                           ps[2], ps[3], ps[4], max_features, ps[5], ps[6], ps[7], ps[8], C.byref(opt), ps[9],
@@ -528,6 +566,20 @@ def update_filter_vogiatzis(ctx, z, tau2, mu_range, state, ok=None):
     return ok
 
 
+def update_filter_seq(ctx, z, tau2, mu_range, state, ok=None, gaussian=False):
+    """svo_cuda_update_filter_seq: n_obs ordered updates per seed in one launch; z, tau2 [n_obs, n]; `state` [n, 4] in place.
+    Returns ok [n_obs, n] uint8 (numpy) or the tensor passed in (None on the device path when not requested)."""
+    n = state.shape[0]
+    n_obs = z.shape[0] if z.ndim == 2 else 1
+    if ok is None and not _is_torch(state):
+        ok = np.zeros((n_obs, n), np.uint8)
+    _check(z, "f8", n * n_obs, "z"); _check(tau2, "f8", n * n_obs, "tau2"); _check(mu_range, "f8", n, "mu_range")
+    _check(state, "f8", 4 * n, "state"); _check(ok, "u1", n * n_obs, "ok")
+    ps, kind = _ptrs(z, tau2, mu_range, state, ok)
+    ctx.check(lib().svo_cuda_update_filter_seq(ctx._h, n, n_obs, ps[0], ps[1], ps[2], ps[3], ps[4], int(bool(gaussian)), kind))
+    return ok
+
+
 def compute_tau(ctx, T_ref_cur, f, z, px_error_angle):
     n = len(z)
     tau = np.zeros(n)
@@ -550,6 +602,9 @@ def update_seeds(ctx, ref_pyr, cur_pyr, cam_ref, cam_cur, ftrs, types, state, se
     else:
         n_success = np.zeros(1, np.int32)
         mr = np.full((n_obs, S), -1, np.int32) if want_match_results else None
+    _check(ref_frame_idx, "i4", S, "ref_frame_idx"); _check(ftrs, "struct", None, "ftrs"); _check(types, "u1", S, "types")
+    _check(state, "f8", 4 * S, "state"); _check(seed_mu_range, "f8", S, "seed_mu_range"); _check(obs_frame_idx, "i4", n_obs * S, "obs_frame_idx")
+    _check(obs_T_idx, "i4", n_obs * S, "obs_T_idx"); _check(T_cur_ref, "f8", 7, "T_cur_ref")
     ps, kind = _ptrs(ref_frame_idx, ftrs, types, state, seed_mu_range, obs_frame_idx, obs_T_idx, T_cur_ref, n_success, mr)
     ctx.check(lib().svo_cuda_update_seeds(ctx._h, ref_pyr._h, cur_pyr._h, C.byref(cam_ref), C.byref(cam_cur), S, ps[0], ps[1], ps[2],
                                           ps[3], ps[4], n_obs, ps[5], ps[6], ps[7], C.byref(mopt), C.byref(dopt), ps[8], ps[9], kind))
@@ -604,9 +659,6 @@ def stereo_triangulate(ctx, pyr0, pyr1, cam0, cam1, T_f1f0, T_world_cam0, feat_b
     ps, kind = _ptrs(frame0_idx, frame1_idx, T_world_cam0, feat_begin, ftrs, n_desired, n_features_in_frame1, results, stats)
     pf0, pf1, pT, pb, pf, pn, ps1, pr, pst = ps
     fn = lib().svo_cuda_stereo_triangulate
-    fn.argtypes = [C.c_void_p] * 5 + [C.POINTER(Camera), C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(MatcherOptions), C.c_void_p,
-                                      C.c_void_p, C.c_int]
     ctx.check(fn(ctx._h, pyr0._h, pyr1._h, pf0, pf1, C.byref(cam0), C.byref(cam1), C.c_void_p(T_f1f0.ctypes.data), pT, B, pb, N, pf, pn, ps1,
                  mean_depth_inv, min_depth_inv, max_depth_inv, C.byref(mopt), pr, pst, kind))
     return results, stats
@@ -624,8 +676,6 @@ def optimize_points(ctx, pos, obs_begin, obs_frame, obs_f, T_f_w, n_iter=5, usin
             iters_out = np.zeros(P, np.int32)
     (pp, pb, pfr, pf, pT, pi), kind = _ptrs(pos, obs_begin, obs_frame, obs_f, T_f_w, iters_out)
     fn = lib().svo_cuda_optimize_points
-    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                   C.c_void_p, C.c_int]
     ctx.check(fn(ctx._h, P, pp, pb, n_obs, pfr, pf, n_frames, pT, int(n_iter), int(bool(using_bearing_vector)), pi, kind))
     return iters_out
 
@@ -647,6 +697,9 @@ def pose_optimize(ctx, cams, T_cam_imu, T_imu_world, feat_begin, ftrs, feat_cam,
         else:
             results = np.zeros(B, POSE_OPT_RESULT_DTYPE)
             outlier = np.zeros(N, np.uint8)
+    _check(T_imu_world, "f8", 7 * B, "T_imu_world"); _check(feat_begin, "i4", B + 1, "feat_begin"); _check(ftrs, "struct", None, "ftrs")
+    _check(feat_cam, "i4", N, "feat_cam"); _check(xyz_world, "f8", 3 * N, "xyz_world"); _check(has_xyz, "u1", N, "has_xyz")
+    _check(prior_q, "f8", 4 * B, "prior_q")
     ps, kind = _ptrs(T_imu_world, feat_begin, ftrs, feat_cam, xyz_world, has_xyz, prior_q, results, outlier)
     ctx.check(lib().svo_cuda_pose_optimize(ctx._h, n_cams, cam_arr, C.c_void_p(T_cam_imu.ctypes.data), B, ps[0], ps[1], N, ps[2], ps[3],
                                            ps[4], ps[5], ps[6], C.byref(opt), ps[7], ps[8], kind))

@@ -26,6 +26,7 @@ struct svo_cuda_ctx {
   cudaStream_t stream = nullptr;
   long long launches = 0;
   int sm_count = 148;
+  bool attr_pyr = false, attr_reproj = false;  // cudaFuncSetAttribute applied on THIS context's device (per device, not per process)
   int8_t* angle_bins = nullptr;  // 511 x 511 orientation-histogram bins of every u8 central-difference gradient (edgelet.cu), built on first use
   std::string last_error;
 };
@@ -72,6 +73,8 @@ int svoFail(svo_cuda_ctx* ctx, int code, const char* what, const char* file, int
     cudaError_t _e = (expr);                                                               \
     if (_e != cudaSuccess) return svoFail(ctx, SVO_ERR_CUDA, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
+// Every entry point runs on the context's device, whatever device the calling thread had current.
+#define SVO_BIND(ctx) SVO_CUDA_TRY(ctx, cudaSetDevice((ctx)->device))
 #define SVO_LAUNCH_CHECK(ctx)                     \
   do {                                            \
     (ctx)->launches++;                            \

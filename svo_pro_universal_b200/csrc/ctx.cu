@@ -99,6 +99,7 @@ int svo_cuda_ctx_set_stream(svo_cuda_ctx* ctx, void* s) {
 
 int svo_cuda_ctx_synchronize(svo_cuda_ctx* ctx) {
   if (!ctx) return SVO_ERR_INVALID_ARG;
+  SVO_BIND(ctx);
   SVO_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return SVO_OK;
 }
@@ -164,6 +165,7 @@ int svo_cuda_pyr_upload(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int cou
                         size_t src_frame_stride, svo_mem mem) {
   if (!ctx || !pyr || !src || first < 0 || count < 0 || first + count > pyr->n_frames || src_pitch < size_t(pyr->cols[0]))
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_pyr_upload: bad arguments");
+  SVO_BIND(ctx);
   const cudaMemcpyKind kind = mem == SVO_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const size_t w = pyr->cols[0], h = pyr->rows[0];
   if (src_pitch == w && pyr->pitch[0] == w && src_frame_stride == w * h && pyr->frame_stride[0] == w * h) {
@@ -186,6 +188,7 @@ int svo_cuda_pyr_download(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame,
   if (!ctx || !pyr || !dst || frame < 0 || frame >= pyr->n_frames || level < 0 || level >= pyr->n_levels ||
       dst_pitch < size_t(pyr->cols[level]))
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_pyr_download: bad arguments");
+  SVO_BIND(ctx);
   const cudaMemcpyKind kind = mem == SVO_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   SVO_CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, dst_pitch, pyr->data[level] + pyr->frame_stride[level] * frame, pyr->pitch[level],
                                       pyr->cols[level], pyr->rows[level], kind, ctx->stream));

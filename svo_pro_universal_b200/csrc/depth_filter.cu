@@ -7,10 +7,16 @@
 //
 // Kernels:
 //   vogiatzis_kernel      one thread per independent update; state is streamed as 2 x double2 (80 B per update in+out).
+//   filter_seq_kernel     one thread per seed applies n_obs ORDERED updates with the state in registers (16 B streamed per update).
 //   compute_tau_kernel    one thread per (T_ref_cur, f, z).
-//   update_seeds_kernel   one 8-lane group per seed walks that seed's observations IN ORDER (the filter is sequential per
-//                         seed, seeds are independent): visibility gate, epipolar match (matcher_dev.cuh), tau, filter
-//                         update, convergence flag — the whole depth_filter_utils::updateSeed without leaving the device.
+//   seed_step_kernel /    depth_filter_utils::updateSeed, phased. The filter is sequential per seed and seeds are independent, so
+//   seed_match_kernel     observation o of ALL seeds forms one wave: a one-thread-per-seed step kernel finishes the seeds' previous
+//                         observation (bearing, triangulation, tau, filter update, convergence flag) and prepares the next one
+//                         (type / visibility gates, epipolar geometry, affine warp matrix, scan parameters) into a compact work
+//                         list; a one-8-lane-group-per-work-item match kernel does what needs a patch (affine warp, ZMSSD scan,
+//                         sub-pixel alignment). All warps of a launch run the same short code (the all-in-one kernel of round 1
+//                         spent 71 % of its warp samples waiting for instructions) and the FP64 geometry is no longer computed
+//                         eight times per seed.
 #include "depth_filter_dev.cuh"
 
 using namespace svo_dev;
@@ -62,42 +68,210 @@ struct SeedParams {
   int* match_results;
 };
 
-// 80 registers: measured 27.4 ms vs 28.9 ms at the compiler default (150 registers) for 3.2 M seed-observations
-__global__ void __launch_bounds__(kThreads, 6) update_seeds_kernel(const SeedParams P) {
+// One pending observation of a seed, handed from the step kernel to the match kernel and back.
+struct SeedWork {
+  EpiSetup e;
+  int cur_frame, T_idx;
+  int align_1d;
+  int result;         // Matcher::MatchResult of the group part (match kernel)
+  double px_x, px_y;  // px_cur_ (match kernel)
+};
+
+// Wave o (0 <= o <= n_obs), one thread per seed: finish observation o - 1 of the seeds that had a match pending, then prepare
+// observation o. Between the two halves the seed's type and state are exactly what the sequential loop of the reference holds
+// between two updateSeed calls.
+__global__ void __launch_bounds__(kThreads) seed_step_kernel(const SeedParams P, int o, SeedWork* __restrict__ work, uint8_t* __restrict__ pending,
+                                                             int* __restrict__ list, int* __restrict__ counts) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool active = false;
+  int n_ok = 0;
+  if (s < P.S) {
+    int type = P.types[s];
+    double2* sp = reinterpret_cast<double2*>(P.state) + 2 * (size_t)s;
+    const double2 s01 = sp[0], s23 = sp[1];
+    double st[4] = {s01.x, s01.y, s23.x, s23.y};
+    svo_feature ft = P.ftrs[s];
+    const V3d f_ref{ft.f[0], ft.f[1], ft.f[2]};
+    bool dirty = false;
+    if (o > 0 && pending[s]) {  // depth_filter.cpp:441-498 for observation o - 1
+      const SeedWork& w = work[s];
+      const SE3d T = se3Load(P.T_cur_ref + 7 * (size_t)w.T_idx);
+      int mr = w.result;
+      double depth = 0.0;
+      if (mr == kSuccess) {
+        V3d f_cur;
+        mr = epiFinish(P.cam_cur, T, f_ref, w.px_x, w.px_y, f_cur, &depth);
+      }
+      if (mr != kSuccess) {
+        st[3] += 1;  // seed::increaseOutlierProbability (the matcher's reject_ flag is only set by the angle gate of the step kernel)
+      } else {
+        const double mu_range = P.seed_mu_range[s];
+        const double cur_thresh = (type == kMapPointSeed || type == kMapPointSeedConverged) ? P.dopt.mappoint_convergence_sigma2_thresh
+                                                                                               : P.dopt.seed_convergence_sigma2_thresh;
+        const SE3d T_ref_cur = se3Inv(T);
+        const double depth_sigma = computeTau(T_ref_cur.t, f_ref, depth, P.px_error_angle);  // :459
+        const double zi = 1.0 / depth;
+        const double sg = 0.5 * (1.0 / fmax(0.000000000001, depth - depth_sigma) - 1.0 / (depth + depth_sigma));  // seed.h:155-160
+        const double tau2 = sg * sg;
+        const bool ok = P.dopt.use_vogiatzis_update ? updateFilterVogiatzis(zi, tau2, mu_range, st) : updateFilterGaussian(zi, tau2, st);
+        if (!ok) {
+          type = kOutlier;  // :470-471, :481-482
+        } else {
+          const double thresh = mu_range / cur_thresh;  // seed::isConverged, seed.h:145-153
+          if (st[1] < thresh * thresh) {
+            if (type == kCornerSeed) type = kCornerSeedConverged;
+            else if (type == kEdgeletSeed) type = kEdgeletSeedConverged;
+            else if (type == kMapPointSeed) type = kMapPointSeedConverged;
+          }
+          n_ok = 1;
+        }
+      }
+      if (P.match_results) P.match_results[(size_t)(o - 1) * P.S + s] = mr;
+      dirty = true;
+    }
+    if (o < P.n_obs) {  // depth_filter.cpp:377-439 for observation o
+      const size_t oi = (size_t)o * P.S + s;
+      int mr = -1;
+      const int cf = P.obs_frame_idx[oi];
+      bool go = cf >= 0;  // :377-381 (cur frame == ref frame): the caller marks such observations with a negative index
+      if (go && type == kOutlier) go = false;  // :387-392
+      if (go && P.dopt.check_convergence && (type == kCornerSeedConverged || type == kEdgeletSeedConverged || type == kMapPointSeedConverged))
+        go = false;  // :394-399
+      if (go) {
+        const int ti = P.obs_T_idx[oi];
+        const SE3d T = se3Load(P.T_cur_ref + 7 * (size_t)ti);
+        if (P.dopt.check_visibility) {  // :406-420
+          const V3d xyz_f = se3Apply(T, f_ref * (1.0 / st[0]));
+          const V2d px = camProject3(P.cam_cur, xyz_f);
+          if (!(px.x >= 0.0 && px.y >= 0.0 && px.x < (double)P.cam_cur.width && px.y < (double)P.cam_cur.height)) go = false;
+          const int pxi0 = (int)px.x, pxi1 = (int)px.y;
+          const int boundary = 9;
+          if (go && !(pxi0 >= boundary && pxi1 >= boundary && pxi0 < P.cam_cur.width - boundary && pxi1 < P.cam_cur.height - boundary)) go = false;
+        }
+        if (go) {
+          ft.type = type;
+          // seed.h:115-128: d_estimate_inv = mu, d_min_inv = mu + sigma, d_max_inv = max(mu - sigma, 1e-8)
+          const double sig = sqrt(st[1]);
+          SeedWork w;
+          epiSetup(P.cam_ref, P.cam_cur, T, ft, st[0], st[0] + sig, fmax(st[0] - sig, 0.00000001), P.mopt, P.ref_pyr.n_levels - 1, w.e);
+          if (w.e.early >= 0) {
+            mr = w.e.early;  // the angle gate: reject_ is set, the outlier count stays (:445-450)
+          } else {
+            w.cur_frame = cf; w.T_idx = ti;
+            w.align_1d = (type == kEdgeletSeed || type == kEdgeletSeedConverged) ? 1 : 0;  // :423-427
+            w.result = -1; w.px_x = 0.0; w.px_y = 0.0;
+            work[s] = w;
+            active = true;
+          }
+        }
+      }
+      if (!active && P.match_results) P.match_results[oi] = mr;
+      pending[s] = active ? 1 : 0;
+    }
+    if (dirty) {
+      P.types[s] = (uint8_t)type;
+      sp[0] = make_double2(st[0], st[1]);
+      sp[1] = make_double2(st[2], st[3]);
+    }
+  }
+  // compact work list of this wave (one atomic per warp; the order inside a warp is the seed order)
+  const unsigned bal = __ballot_sync(0xffffffffu, active);
+  if (bal) {
+    int base = 0;
+    const int leader = __ffs((int)bal) - 1;
+    if (lane == leader) base = atomicAdd(&counts[o], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (active) list[base + __popc(bal & ((1u << lane) - 1u))] = s;
+  }
+  const unsigned okb = __ballot_sync(0xffffffffu, n_ok != 0);
+  if (okb && lane == 0) atomicAdd(P.n_success, __popc(okb));
+}
+
+// One 8-lane group per work item of wave o: affine warp of the reference patch, ZMSSD scan, sub-pixel alignment.
+template <int SCAN>
+__global__ void __launch_bounds__(kThreads, 4) seed_match_kernel(const SeedParams P, int o, SeedWork* __restrict__ work, const int* __restrict__ list,
+                                                                 const int* __restrict__ counts) {
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
   const Group g = makeGroup();
   const int gi = threadIdx.x / kGroup;
-  const int s = blockIdx.x * kGroupsPerCta + gi;
-  if (s >= P.S) return;
+  const int k = blockIdx.x * kGroupsPerCta + gi;
+  if (k >= counts[o]) return;
+  const int s = list[k];
   uint8_t* pwb = s_pwb + gi * kPwbPitch;
-  svo_feature ft = P.ftrs[s];
-  int type = P.types[s];
-  double st[4] = {P.state[4 * (size_t)s], P.state[4 * (size_t)s + 1], P.state[4 * (size_t)s + 2], P.state[4 * (size_t)s + 3]};
-  const double mu_range = P.seed_mu_range[s];
+  SeedWork& w = work[s];
+  const EpiSetup e = w.e;
+  const svo_feature ft = P.ftrs[s];
   const int rf = P.ref_frame_idx ? P.ref_frame_idx[s] : 0;
-  int n_ok = 0;
-  for (int o = 0; o < P.n_obs; ++o) {
-    const size_t oi = (size_t)o * P.S + s;
-    int mr = -1;
-    const int cf = P.obs_frame_idx[oi];
-    if (cf >= 0) {  // depth_filter.cpp:377-381 (cur frame == ref frame): the caller marks such observations with a negative index
-      const SE3d T = se3Load(P.T_cur_ref + 7 * (size_t)P.obs_T_idx[oi]);
-      // DepthFilter::updateSeeds picks the threshold by type (:214-221)
-      const double cur_thresh = (type == kMapPointSeed || type == kMapPointSeedConverged) ? P.dopt.mappoint_convergence_sigma2_thresh
-                                                                                             : P.dopt.seed_convergence_sigma2_thresh;
-      MatchState m;
-      if (updateSeedOnce(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, type, st, mu_range, cur_thresh, P.px_error_angle,
-                         P.dopt.check_visibility != 0, P.dopt.check_convergence != 0, P.dopt.use_vogiatzis_update != 0, P.mopt, pwb, m, &mr))
-        ++n_ok;
-    }
-    if (P.match_results && g.r == 0) P.match_results[oi] = mr;
+  double px_x = 0.0, px_y = 0.0, h_inv = 0.0;
+  const int res = epiMatch<SCAN>(g, P.ref_pyr, rf, P.cur_pyr, w.cur_frame, P.cam_cur, ft, e, P.mopt, w.align_1d != 0, pwb, px_x, px_y, &h_inv);
+  if (g.r == 0) { w.result = res; w.px_x = px_x; w.px_y = px_y; }
+}
+
+// n_obs ordered filter updates per seed with the state in registers: z / tau2 are [n_obs][n] (observation-major, coalesced).
+// The reference's nineteen divisions per update are folded into two reciprocals (vogiatzisRational below): the kernel is bound by the
+// FP64 pipe and by the length of one update's dependent chain, and the result differs from the reference's IEEE divisions by a few
+// ulp per update (tests: rtol 1e-9 after 64 updates; the north-star tolerance for seed mean / variance is 1e-4).
+SVO_D double rcpGuarded(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, fma(e, e, e), x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x == x ? x : 1.0 / d;  // zero, infinite and denormal divisors take the IEEE path
+}
+// updateFilterVogiatzis as ONE rational expression per output: with c1 = a N(z; mu, sigma2 + tau2), c2 = b / mu_range (the common
+// factor 1 / (a + b) of C1, C2 cancels), f = Nf / Df and e = Ne / (Df (a + b + 2)),
+//   a' = (Ne - Nf ab2) Nf / (Nf^2 ab2 - Ne Df),   b' = (Ne - Nf ab2) (Df - Nf) / (Nf^2 ab2 - Ne Df),
+//   s2 = sigma2 tau2 / (sigma2 + tau2),   m = (mu tau2 + z sigma2) / (sigma2 + tau2),
+// so an update costs one rsqrt, one exp and two reciprocals on its dependent chain instead of nineteen divisions.
+SVO_D bool vogiatzisRational(double z, double tau2, double inv_range, double s[4]) {
+  const double mu = s[0], sigma2 = s[1], a = s[2], b = s[3];
+  const double v = sigma2 + tau2;
+  if (!(v >= 0.0)) return false;  // sqrt(sigma2 + tau2) is NaN (depth_filter.cpp:509-512)
+  const double rs = rsqrt(v), rs2 = rs * rs;  // 1 / norm_scale, 1 / (sigma2 + tau2)
+  const double s2 = sigma2 * tau2 * rs2;
+  const double m = (mu * tau2 + z * sigma2) * rs2;
+  const double d = z - mu;
+  const double pdf = exp(-(d * d) * (0.5 * rs2)) * (rs * 0.3989422804014326779);  // vk::normPdf(z, mu, norm_scale)
+  const double c1 = a * pdf, c2 = b * inv_range;
+  const double ic = rcpGuarded(c1 + c2);
+  const double ab1 = a + b + 1.0, ab2 = a + b + 2.0;
+  const double Nf = c1 * (a + 1.0) + c2 * a;
+  const double Ne = (c1 * (a + 2.0) + c2 * a) * (a + 1.0);
+  const double Df = (c1 + c2) * ab1;
+  const double iden = rcpGuarded(Nf * Nf * ab2 - Ne * Df);
+  const double t = Ne - Nf * ab2;
+  const double mu_new = (c1 * m + c2 * mu) * ic;
+  double sigma2_new = (c1 * (s2 + m * m) + c2 * (sigma2 + mu * mu)) * ic - mu_new * mu_new;
+  bool ok = true;
+  double mu_out = mu_new;
+  if (sigma2_new < 0.0) sigma2_new = sigma2;
+  if (mu_out < 0.0) { mu_out = 1.0; ok = false; }
+  s[0] = mu_out; s[1] = sigma2_new; s[2] = t * Nf * iden; s[3] = t * (Df - Nf) * iden;
+  return ok;
+}
+
+template <bool GAUSS>
+__global__ void __launch_bounds__(64) filter_seq_kernel(int n, int n_obs, const double* __restrict__ z, const double* __restrict__ tau2,
+                                                        const double* __restrict__ mu_range, double* __restrict__ state,
+                                                        uint8_t* __restrict__ ok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2* sp = reinterpret_cast<double2*>(state) + 2 * (size_t)i;
+  const double2 s01 = sp[0], s23 = sp[1];
+  double s[4] = {s01.x, s01.y, s23.x, s23.y};
+  const double inv_range = GAUSS ? 0.0 : rcpGuarded(mu_range[i]);
+  double zn = z[i], tn = tau2[i];
+  for (int o = 0; o < n_obs; ++o) {
+    const double zc = zn, tc = tn;
+    if (o + 1 < n_obs) { zn = z[(size_t)(o + 1) * n + i]; tn = tau2[(size_t)(o + 1) * n + i]; }  // next observation in flight
+    const bool r = GAUSS ? updateFilterGaussian(zc, tc, s) : vogiatzisRational(zc, tc, inv_range, s);
+    if (ok) ok[(size_t)o * n + i] = r ? 1 : 0;
   }
-  if (g.r == 0) {
-    P.types[s] = (uint8_t)type;
-    P.state[4 * (size_t)s] = st[0]; P.state[4 * (size_t)s + 1] = st[1];
-    P.state[4 * (size_t)s + 2] = st[2]; P.state[4 * (size_t)s + 3] = st[3];
-    if (n_ok) atomicAdd(P.n_success, n_ok);
-  }
+  sp[0] = make_double2(s[0], s[1]);
+  sp[1] = make_double2(s[2], s[3]);
 }
 
 }  // namespace
@@ -109,7 +283,7 @@ int svo_cuda_update_filter_vogiatzis(svo_cuda_ctx* ctx, int n, const double* z, 
   if (!ctx || n < 0 || !z || !tau2 || !mu_range || !state)
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_update_filter_vogiatzis: bad arguments");
   if (n == 0) return SVO_OK;
-  cudaSetDevice(ctx->device);
+  SVO_BIND(ctx);
   Stager st(ctx, mem);
   const double* dz = st.in(z, (size_t)n);
   const double* dt = st.in(tau2, (size_t)n);
@@ -122,11 +296,31 @@ int svo_cuda_update_filter_vogiatzis(svo_cuda_ctx* ctx, int n, const double* z, 
   return st.finish();
 }
 
+int svo_cuda_update_filter_seq(svo_cuda_ctx* ctx, int n, int n_obs, const double* z, const double* tau2, const double* mu_range,
+                               double* state, uint8_t* ok, int gaussian, svo_mem mem) {
+  if (!ctx || n < 0 || n_obs < 0 || !z || !tau2 || (!gaussian && !mu_range) || !state)
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_update_filter_seq: bad arguments");
+  if (n == 0 || n_obs == 0) return SVO_OK;
+  SVO_BIND(ctx);
+  Stager st(ctx, mem);
+  const size_t no = (size_t)n * n_obs;
+  const double* dz = st.in(z, no);
+  const double* dt = st.in(tau2, no);
+  const double* dm = st.in(mu_range, (size_t)n);
+  double* ds = st.inout(state, (size_t)n * 4);
+  uint8_t* dok = st.out(ok, no);
+  if (st.failed()) return st.finish();
+  if (gaussian) filter_seq_kernel<true><<<(n + 63) / 64, 64, 0, ctx->stream>>>(n, n_obs, dz, dt, dm, ds, dok);
+  else filter_seq_kernel<false><<<(n + 63) / 64, 64, 0, ctx->stream>>>(n, n_obs, dz, dt, dm, ds, dok);
+  SVO_LAUNCH_CHECK(ctx);
+  return st.finish();
+}
+
 int svo_cuda_compute_tau(svo_cuda_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z, double px_error_angle,
                          double* tau, svo_mem mem) {
   if (!ctx || n < 0 || !T_ref_cur || !f || !z || !tau) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_compute_tau: bad arguments");
   if (n == 0) return SVO_OK;
-  cudaSetDevice(ctx->device);
+  SVO_BIND(ctx);
   Stager st(ctx, mem);
   const double* dT = st.in(T_ref_cur, (size_t)n * 7);
   const double* df = st.in(f, (size_t)n * 3);
@@ -146,7 +340,7 @@ int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const 
   if (!ctx || !ref_pyr || !cur_pyr || !cam_ref || !cam_cur || S < 0 || !ftrs || !types || !state || !seed_mu_range || n_obs < 0 ||
       !obs_frame_idx || !obs_T_idx || !T_cur_ref || !mopt || !dopt || !n_success)
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_update_seeds: bad arguments");
-  cudaSetDevice(ctx->device);
+  SVO_BIND(ctx);
   Stager st(ctx, mem);
   SeedParams P;
   memset(&P, 0, sizeof(P));
@@ -174,11 +368,25 @@ int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const 
   int* d_ns = st.out(n_success, 1);
   P.n_success = d_ns;
   P.match_results = st.out(match_results, so);
-  if (st.failed()) return st.finish();
+  // wave scratch: one work item / pending flag / list slot per seed, one counter per wave
+  SeedWork* d_work = (SeedWork*)st.scratch(sizeof(SeedWork) * (size_t)(S > 0 ? S : 1));
+  uint8_t* d_pending = (uint8_t*)st.scratch((size_t)(S > 0 ? S : 1));
+  int* d_list = (int*)st.scratch(sizeof(int) * (size_t)(S > 0 ? S : 1));
+  int* d_counts = (int*)st.scratch(sizeof(int) * (size_t)(n_obs + 1));
+  if (st.failed() || !d_work || !d_pending || !d_list || !d_counts) return st.finish();
   SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_ns, 0, sizeof(int), ctx->stream));
   if (S > 0 && n_obs > 0) {
-    update_seeds_kernel<<<(S + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
-    SVO_LAUNCH_CHECK(ctx);
+    SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)(n_obs + 1), ctx->stream));
+    const int step_grid = (S + kThreads - 1) / kThreads, match_grid = (S + kGroupsPerCta - 1) / kGroupsPerCta;
+    for (int o = 0; o <= n_obs; ++o) {
+      seed_step_kernel<<<step_grid, kThreads, 0, ctx->stream>>>(P, o, d_work, d_pending, d_list, d_counts);
+      SVO_LAUNCH_CHECK(ctx);
+      if (o < n_obs) {
+        if (mopt->scan_on_unit_sphere) seed_match_kernel<1><<<match_grid, kThreads, 0, ctx->stream>>>(P, o, d_work, d_list, d_counts);
+        else seed_match_kernel<0><<<match_grid, kThreads, 0, ctx->stream>>>(P, o, d_work, d_list, d_counts);
+        SVO_LAUNCH_CHECK(ctx);
+      }
+    }
   }
   return st.finish();
 }

@@ -445,6 +445,7 @@ int svo_cuda_edgelet_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int firs
   if (rc != SVO_OK) return rc;
   if (!corners_out) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_edgelet_detect: corners_out is NULL");
   if (count == 0) return SVO_OK;
+  SVO_BIND(ctx);
   const size_t n = (size_t)svo_cuda_grid_cells(pyr->cols[0], pyr->rows[0], cell_size, nullptr, nullptr) * count;
   Stager st(ctx, mem);
   const uint8_t* d_occ = st.in(occupancy_in, n);
@@ -458,6 +459,7 @@ int svo_cuda_edgelet_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int firs
 
 int svo_cuda_angle_histogram_bins(svo_cuda_ctx* ctx, int8_t* bins_out, svo_mem mem) {
   if (!ctx || !bins_out) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_angle_histogram_bins: bad arguments");
+  SVO_BIND(ctx);
   Stager st(ctx, mem);
   int8_t* d = st.out(bins_out, (size_t)511 * 511);
   if (st.failed()) return st.finish();
@@ -476,6 +478,7 @@ int svo_cuda_fastgrad_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fir
   if (!corners_out || !edgelets_out || max_n_features < 0)
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_fastgrad_detect: bad arguments");
   if (count == 0) return SVO_OK;
+  SVO_BIND(ctx);
   const int n_cells = svo_cuda_grid_cells(pyr->cols[0], pyr->rows[0], opt->cell_size, nullptr, nullptr);
   const size_t n = (size_t)n_cells * count;
   Stager st(ctx, mem);

@@ -299,6 +299,7 @@ int svoFastDetectImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_fast_detect: bad detector options");
   const int arc = opt->arc_length == 9 ? 9 : 10;
   if (count == 0) return SVO_OK;
+  SVO_BIND(ctx);
   int n_cols, n_rows;
   const int n_cells = svo_cuda_grid_cells(pyr->cols[0], pyr->rows[0], opt->cell_size, &n_cols, &n_rows);
   const size_t n = (size_t)n_cells * count;
@@ -342,6 +343,7 @@ int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fra
   if (!ctx || !pyr || frame < 0 || frame >= pyr->n_frames || level < 0 || level >= pyr->n_levels || threshold < 1 || threshold > 254)
     return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_fast_level_maps: bad arguments");
   const size_t n = (size_t)pyr->cols[level] * pyr->rows[level];
+  SVO_BIND(ctx);
   Stager st(ctx, mem);
   int16_t* d_sc = st.out(score_map, n);
   uint8_t* d_nm = st.out(nonmax_map, n);

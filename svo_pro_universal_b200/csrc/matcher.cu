@@ -53,8 +53,8 @@ SVO_D void writeOut(const Group& g, svo_match_out* out, int i, const MatchState&
   out[i] = o;
 }
 
-// mode 0: findMatchDirect, 1: findEpipolarMatchDirect, 2: warp only
-template <int MODE>
+// mode 0: findMatchDirect, 1: findEpipolarMatchDirect, 2: warp only; SCAN: the epipolar scan compiled in (1 sphere, 0 plane)
+template <int MODE, int SCAN = 2>
 // 126 registers, 4 CTAs/SM: fastest of 4/5/6 on the B200 (1.58 / 2.94 ms for 512 k features)
 __global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P) {
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P)
     double depth = 0.0;
     const double* dd = P.depth + (P.depth_shared ? 0 : 3 * (size_t)i);
     const bool a1d = P.align1d_from_type ? isEdgeletType(ft.type) : P.opt.align_1d != 0;
-    const int res = findEpipolarMatchDirect(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, dd[0], dd[1], dd[2], P.opt, a1d,
+    const int res = findEpipolarMatchDirect<SCAN>(g, P.ref_pyr, rf, P.cur_pyr, cf, P.cam_ref, P.cam_cur, T, ft, dd[0], dd[1], dd[2], P.opt, a1d,
                                             pwb, m, &depth);
     writeOut(g, P.out, i, m, res, depth);
   } else {
@@ -322,7 +322,8 @@ static int matchCommon(int mode, svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr,
   if (st.failed()) return st.finish();
   const int grid = (M + kGroupsPerCta - 1) / kGroupsPerCta;
   if (mode == 0) match_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(P);
-  else if (mode == 1) match_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(P);
+  else if (mode == 1 && P.opt.scan_on_unit_sphere) match_kernel<1, 1><<<grid, kThreads, 0, ctx->stream>>>(P);
+  else if (mode == 1) match_kernel<1, 0><<<grid, kThreads, 0, ctx->stream>>>(P);
   else match_kernel<2><<<grid, kThreads, 0, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -446,7 +447,8 @@ int svo_cuda_stereo_triangulate(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr0, con
     for (int c = 0; c <= kChunks; ++c) {
       P.chunk_lo = c * kChunk;
       P.chunk_hi = c < kChunks ? (c + 1) * kChunk : 0x7FFFFFFF;
-      match_kernel<1><<<(n_features + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
+      if (P.opt.scan_on_unit_sphere) match_kernel<1, 1><<<(n_features + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
+      else match_kernel<1, 0><<<(n_features + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
       SVO_LAUNCH_CHECK(ctx);
       if (c < kChunks) {
         stereo_progress_kernel<<<B, 128, 0, ctx->stream>>>(d_match, d_begin, d_want, P.chunk_lo, P.chunk_hi, d_succ, d_done);

@@ -187,7 +187,7 @@ SVO_D void orderedSums(const Group& g, float* red, F term, float (&acc)[NK]) {
   float a = 0.f;
   if (g.r < NK) {
     const float4* src = reinterpret_cast<const float4*>(red + g.r * kRedStride);
-#pragma unroll
+#pragma unroll 4  // the chain of 64 dependent additions is latency bound; a short loop body keeps the kernels' code small
     for (int i = 0; i < 16; ++i) {
       const float4 v = src[i];
       if (SUB) { a = a - v.x; a = a - v.y; a = a - v.z; a = a - v.w; }
@@ -407,52 +407,50 @@ SVO_D int findMatchDirect(const Group& g, const PyrView& ref_pyr, int ref_frame,
   return kSuccess;
 }
 
-// findLocalMatch (matcher.cpp:262-289)
-SVO_D int findLocalMatch(const Group& g, const PyrView& cur_pyr, int cur_frame, double dir_x, double dir_y, int patch_level,
-                         const svo_matcher_options& opt, bool align_1d, uint8_t* pwb, MatchState& m) {
-  const double sc = (double)(1 << patch_level);
-  double ps_x = m.px_x / sc, ps_y = m.px_y / sc;
-  const ImgView cur = levelView(cur_pyr, cur_frame, patch_level);
-  bool res;
-  if (align_1d) res = align1D(g, cur, dir_x, dir_y, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y, &m.h_inv);
-  else res = align2D(g, cur, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y);
-  if (!res) return kFailAlignment;
-  m.px_x = ps_x * sc; m.px_y = ps_y * sc;
-  return kSuccess;
-}
-
-// ZMSSD<4> against the strided 8x8 window whose top-left is (x0, y0): lane r scores row r (patch_score.h:264-283)
+// ---- c5: ZMSSD<4> (patch_score.h:43-109, 264-283) -------------------------------------------------------------------
+// The epipolar scans score ONE candidate position per lane: a lane holds the whole 8x8 reference patch as 16 packed words and
+// forms sumB, sumBB, sumAB of its own candidate window with byte dot products (IDP4A), so the 8 lanes of a group evaluate 8
+// consecutive scan steps at once and no shuffle is needed per score. All sums are exact integers, as in the reference.
 struct ZmssdRef {
-  unsigned ref_lo, ref_hi;  // this lane's row of the reference patch (8 bytes)
+  unsigned ref[16];  // row y of the reference patch = bytes of ref[2y], ref[2y+1]
   int sumA, sumAA;
 };
-SVO_D ZmssdRef makeZmssdRef(const Group& g, const uint8_t* pwb) {
+SVO_D ZmssdRef makeZmssdRef(const Group& g, uint8_t* pwb) {
   const uint8_t* it = pwb + (g.r + 1) * 10 + 1;
+  const unsigned lo = it[0] | (it[1] << 8) | (it[2] << 16) | (it[3] << 24);
+  const unsigned hi = it[4] | (it[5] << 8) | (it[6] << 16) | (it[7] << 24);
+  // the group's rows go through its ordered-sum scratch (16-byte aligned, unused during the scan)
+  unsigned* sh = reinterpret_cast<unsigned*>(pwb + kPatchBytes);
+  __syncwarp(g.mask);
+  sh[2 * g.r] = lo; sh[2 * g.r + 1] = hi;
+  __syncwarp(g.mask);
   ZmssdRef z;
-  z.ref_lo = it[0] | (it[1] << 8) | (it[2] << 16) | (it[3] << 24);
-  z.ref_hi = it[4] | (it[5] << 8) | (it[6] << 16) | (it[7] << 24);
-  int sA = 0, sAA = 0;
 #pragma unroll
-  for (int x = 0; x < 8; ++x) { const int n = it[x]; sA += n; sAA += n * n; }
+  for (int k = 0; k < 4; ++k) {
+    const uint4 v = reinterpret_cast<const uint4*>(sh)[k];
+    z.ref[4 * k] = v.x; z.ref[4 * k + 1] = v.y; z.ref[4 * k + 2] = v.z; z.ref[4 * k + 3] = v.w;
+  }
+  __syncwarp(g.mask);  // the scratch may be rewritten
+  const int sA = (int)__dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, 0u));
+  const int sAA = (int)__dp4a(lo, lo, __dp4a(hi, hi, 0u));
   z.sumA = groupSum(g, sA);
   z.sumAA = groupSum(g, sAA);
   return z;
 }
-SVO_D int zmssdScore(const Group& g, const ZmssdRef& z, const ImgView& img, int x0, int y0) {
-  unsigned a, b;
-  loadRow8(img.data + (size_t)(y0 + g.r) * img.pitch, x0, a, b);
-  int sB = 0, sBB = 0, sAB = 0;
+// score of the 8x8 window whose top-left pixel is (x0, y0), computed by ONE lane
+SVO_D int zmssdScore(const ZmssdRef& z, const ImgView& img, int x0, int y0) {
+  const uint8_t* row = img.data + (size_t)y0 * img.pitch;
+  unsigned sB = 0u, sBB = 0u, sAB = 0u;
 #pragma unroll
-  for (int x = 0; x < 8; ++x) {
-    const int c = x < 4 ? byteOf(a, x) : byteOf(b, x - 4);
-    const int rf = x < 4 ? byteOf(z.ref_lo, x) : byteOf(z.ref_hi, x - 4);
-    sB += c; sBB += c * c; sAB += c * rf;
+  for (int y = 0; y < 8; ++y) {
+    unsigned a, b;
+    loadRow8(row + (size_t)y * img.pitch, x0, a, b);
+    sB = __dp4a(a, 0x01010101u, sB); sB = __dp4a(b, 0x01010101u, sB);
+    sBB = __dp4a(a, a, sBB); sBB = __dp4a(b, b, sBB);
+    sAB = __dp4a(a, z.ref[2 * y], sAB); sAB = __dp4a(b, z.ref[2 * y + 1], sAB);
   }
-  sB = groupSum(g, sB); sBB = groupSum(g, sBB); sAB = groupSum(g, sAB);
-  return z.sumAA - 2 * sAB + sBB - (z.sumA * z.sumA - 2 * z.sumA * sB + sB * sB) / 64;
-}
-SVO_D bool isPatchWithinImage(const svo_camera& cam, int px, int py, int patch_level) {  // matcher.cpp:314-322
-  return !(px < 8 || py < 8 || px >= (cam.width / (1 << patch_level) - 8) || py >= (cam.height / (1 << patch_level) - 8));
+  const int B = (int)sB;
+  return z.sumAA - 2 * (int)sAB + (int)sBB - (z.sumA * z.sumA - 2 * z.sumA * B + B * B) / 64;
 }
 
 SVO_D V3d angleAxisRotate(const V3d& axis, double angle, const V3d& v) {  // Eigen::AngleAxisd::toRotationMatrix() * v
@@ -484,116 +482,265 @@ SVO_D int depthFromTriangulation(const SE3d& T_search_ref, const V3d& f_ref, con
   return kSuccess;
 }
 
-// c7. Matcher::findEpipolarMatchDirect (matcher.cpp:157-241)
-SVO_D int findEpipolarMatchDirect(const Group& g, const PyrView& ref_pyr, int ref_frame, const PyrView& cur_pyr, int cur_frame,
-                                  const svo_camera& cam_ref, const svo_camera& cam_cur, const SE3d& T_cur_ref, const svo_feature& ft,
-                                  double d_estimate_inv, double d_min_inv, double d_max_inv, const svo_matcher_options& opt,
-                                  bool align_1d, uint8_t* pwb, MatchState& m, double* depth) {
-  int zmssd_best = 2000 * 64;
+// ---- c7. Matcher::findEpipolarMatchDirect (matcher.cpp:157-241) in three pieces -----------------------------------------
+//   epiSetup   scalar geometry of one feature: epipolar segment, affine warp matrix, edgelet angle gate, search level and
+//              the scan parameters (one thread suffices; the phased seed / match pipelines run it one thread per feature);
+//   epiMatch   the 8-lane group part: affine warp of the reference patch, ZMSSD scan along the segment, sub-pixel alignment;
+//   epiFinish  scalar: bearing vector of the match and the triangulated depth.
+// findEpipolarMatchDirect() below chains the three inside one group for the callers that want everything in one kernel.
+struct EpiSetup {
+  double A[2][2];                          // A_cur_ref_
+  double epi_x, epi_y, epi_length_pyramid; // epi_image_, epi_length_pyramid_
+  double dir_x, dir_y;                     // epi_image_.normalized()
+  double px0_x, px0_y;                     // short segment: mid-point of its end points, the local match starts there
+  int search_level, reject;
+  int early;                               // < 0: go on with epiMatch, else the MatchResult findEpipolarMatchDirect returns at once
+  int short_epi;
+  int n_steps, half_steps;                 // scan length (after the max_epi_search_steps cap); unit sphere: n_steps / 2
+  double step;                             // unit sphere: angle per step
+  V3d axis, f_C;                           // unit sphere: rotation axis and the bearing of the depth estimate
+  double step_x, step_y, uvC_x, uvC_y;     // unit plane: step and start on the plane z = 1
+};
+
+SVO_D void epiSetup(const svo_camera& cam_ref, const svo_camera& cam_cur, const SE3d& T_cur_ref, const svo_feature& ft, double d_estimate_inv,
+                    double d_min_inv, double d_max_inv, const svo_matcher_options& opt, int max_level, EpiSetup& e) {
   const V3d f_ref{ft.f[0], ft.f[1], ft.f[2]};
   const V3d Rf = quatRotate(T_cur_ref.q, f_ref);
   const V3d A = Rf + T_cur_ref.t * d_min_inv;
   const V3d B = Rf + T_cur_ref.t * d_max_inv;
   const V2d px_A = camProject3(cam_cur, A), px_B = camProject3(cam_cur, B);
-  m.epi_x = px_A.x - px_B.x; m.epi_y = px_A.y - px_B.y;
-  getWarpMatrixAffine(cam_ref, cam_cur, ft.px[0], ft.px[1], f_ref, 1.0 / fmax(0.000001, d_estimate_inv), T_cur_ref, ft.level, m.A);
-  m.reject = 0;
+  e.epi_x = px_A.x - px_B.x; e.epi_y = px_A.y - px_B.y;
+  getWarpMatrixAffine(cam_ref, cam_cur, ft.px[0], ft.px[1], f_ref, 1.0 / fmax(0.000001, d_estimate_inv), T_cur_ref, ft.level, e.A);
+  e.reject = 0; e.early = -1; e.short_epi = 0;
+  e.search_level = 0; e.epi_length_pyramid = 0.0; e.dir_x = e.dir_y = e.px0_x = e.px0_y = 0.0;
+  e.n_steps = e.half_steps = 0; e.step = 0.0; e.axis = V3d{0, 0, 0}; e.f_C = V3d{0, 0, 0};
+  e.step_x = e.step_y = e.uvC_x = e.uvC_y = 0.0;
   if (isEdgeletType(ft.type) && opt.epi_search_edgelet_filtering) {
-    const V2d gc = normalized2(V2d{m.A[0][0] * ft.grad[0] + m.A[0][1] * ft.grad[1], m.A[1][0] * ft.grad[0] + m.A[1][1] * ft.grad[1]});
-    const V2d en = normalized2(V2d{m.epi_x, m.epi_y});
+    const V2d gc = normalized2(V2d{e.A[0][0] * ft.grad[0] + e.A[0][1] * ft.grad[1], e.A[1][0] * ft.grad[0] + e.A[1][1] * ft.grad[1]});
+    const V2d en = normalized2(V2d{e.epi_x, e.epi_y});
     const double cosangle = fabs(gc.x * en.x + gc.y * en.y);
-    if (cosangle < opt.epi_search_edgelet_max_angle) { m.reject = 1; return kFailAngle; }
+    if (cosangle < opt.epi_search_edgelet_max_angle) { e.reject = 1; e.early = kFailAngle; return; }
   }
-  m.search_level = getBestSearchLevel(m.A, ref_pyr.n_levels - 1);
-  m.epi_length_pyramid = sqrt(m.epi_x * m.epi_x + m.epi_y * m.epi_y) / (1 << m.search_level);
-  const V2d epi_dir = normalized2(V2d{m.epi_x, m.epi_y});
-  if (!warpAffine10(g, m.A, levelView(ref_pyr, ref_frame, ft.level), ft.px[0], ft.px[1], ft.level, m.search_level, pwb))
-    return kFailWarp;
-
-  // matcher.cpp:209-218: a short epipolar segment goes straight to the local (sub-pixel) match at its mid-point; the scan
-  // below is skipped. Both ways end in ONE findLocalMatch / triangulation call site (code size: these kernels stall on
-  // instruction fetch when every path carries its own inlined copy of the alignment code, profiles/).
-  const bool short_epi = m.epi_length_pyramid < 2.0;
-  if (short_epi) {
-    m.px_x = (px_A.x + px_B.x) / 2.0; m.px_y = (px_A.y + px_B.y) / 2.0;
-  } else {
-  const ZmssdRef zref = makeZmssdRef(g, pwb);
+  e.search_level = getBestSearchLevel(e.A, max_level);
+  e.epi_length_pyramid = sqrt(e.epi_x * e.epi_x + e.epi_y * e.epi_y) / (1 << e.search_level);
+  const V2d epi_dir = normalized2(V2d{e.epi_x, e.epi_y});
+  e.dir_x = epi_dir.x; e.dir_y = epi_dir.y;
+  // matcher.cpp:209-218: a short epipolar segment goes straight to the local (sub-pixel) match at its mid-point
+  if (e.epi_length_pyramid < 2.0) {
+    e.short_epi = 1;
+    e.px0_x = (px_A.x + px_B.x) / 2.0; e.px0_y = (px_A.y + px_B.y) / 2.0;
+    return;
+  }
   const V3d C = Rf + T_cur_ref.t * d_estimate_inv;
-  const int pl = m.search_level;
-  const ImgView cur = levelView(cur_pyr, cur_frame, pl);
-  const double plscale = (double)(1 << pl);
-  if (opt.scan_on_unit_sphere) {  // matcher.cpp:415-488
-    size_t n_steps = (size_t)(m.epi_length_pyramid / 0.7);
+  size_t n_steps = (size_t)(e.epi_length_pyramid / 0.7);
+  if (opt.scan_on_unit_sphere) {  // matcher.cpp:415-441
     n_steps = n_steps > (size_t)opt.max_epi_search_steps ? (size_t)opt.max_epi_search_steps : n_steps;
-    const size_t half_steps = n_steps / 2;
     const V3d f_A = normalized3(A), f_B = normalized3(B);
-    const double step = acos(dot3(f_A, f_B)) / n_steps;
-    const V3d axis = normalized3(cross3(f_B, f_A));
-    const V3d f_C = normalized3(C);
-    V3d f_best = f_C;
-    int last_x = 0, last_y = 0;
-    for (size_t i = 0; i < n_steps; i++) {
-      double angle;
-      if (i < half_steps) angle = i * step;
-      else angle = (i - half_steps) * (-step);
-      const V3d f = angleAxisRotate(axis, angle, f_C);
-      const V2d px = camProject3(cam_cur, f);
-      const int pxi0 = (int)(px.x / plscale + 0.5), pxi1 = (int)(px.y / plscale + 0.5);
-      if (pxi0 == last_x && pxi1 == last_y) continue;
-      last_x = pxi0; last_y = pxi1;
-      if (!isPatchWithinImage(cam_cur, pxi0, pxi1, pl)) {
-        if (i < half_steps) { i = half_steps; continue; }
-        else break;
-      }
-      const int z = zmssdScore(g, zref, cur, pxi0 - 4, pxi1 - 4);
-      if (z < zmssd_best) { zmssd_best = z; f_best = f; }
-    }
-    const V2d pb = camProject3(cam_cur, f_best);
-    m.px_x = pb.x; m.px_y = pb.y;
-  } else {  // matcher.cpp:340-413
-    size_t n_steps = (size_t)(m.epi_length_pyramid / 0.7);
-    double step_x = (A.x / A.z - B.x / B.z) / n_steps, step_y = (A.y / A.z - B.y / B.z) / n_steps;
+    e.step = acos(dot3(f_A, f_B)) / n_steps;
+    e.axis = normalized3(cross3(f_B, f_A));
+    e.f_C = normalized3(C);
+    e.n_steps = (int)n_steps;
+    e.half_steps = (int)(n_steps / 2);
+  } else {  // matcher.cpp:340-362
+    e.step_x = (A.x / A.z - B.x / B.z) / n_steps; e.step_y = (A.y / A.z - B.y / B.z) / n_steps;
     if (n_steps > (size_t)opt.max_epi_search_steps) n_steps = (size_t)opt.max_epi_search_steps;
-    const double uvC_x = C.x / C.z, uvC_y = C.y / C.z;
-    double uv_x = uvC_x, uv_y = uvC_y, best_x = uv_x, best_y = uv_y;
-    bool forward = true;
-    int last_x = 0, last_y = 0;
-    for (size_t i = 0; i < n_steps; ++i, uv_x += step_x, uv_y += step_y) {
-      const V2d px = camProject3(cam_cur, V3d{uv_x, uv_y, 1.0});
-      const int pxi0 = (int)(px.x / plscale + 0.5), pxi1 = (int)(px.y / plscale + 0.5);
-      if (pxi0 == last_x && pxi1 == last_y) continue;
-      last_x = pxi0; last_y = pxi1;
-      if (!isPatchWithinImage(cam_cur, pxi0, pxi1, pl)) {
-        if (forward) {
-          i = (size_t)(n_steps * 0.5);
-          step_x = -step_x; step_y = -step_y;
-          uv_x = uvC_x; uv_y = uvC_y;
-          forward = false;
-          continue;
-        } else {
-          break;
-        }
-      }
-      const int z = zmssdScore(g, zref, cur, pxi0 - 4, pxi1 - 4);
-      if (z < zmssd_best) { zmssd_best = z; best_x = uv_x; best_y = uv_y; }
-      if (forward && (double)i > n_steps * 0.5) {
-        step_x = -step_x; step_y = -step_y;
-        uv_x = uvC_x; uv_y = uvC_y;
-        forward = false;
-      }
-    }
-    const V2d pb = camProject3(cam_cur, V3d{best_x, best_y, 1.0});
-    m.px_x = pb.x; m.px_y = pb.y;
+    e.uvC_x = C.x / C.z; e.uvC_y = C.y / C.z;
+    e.n_steps = (int)n_steps;
   }
+}
 
-  if (!(zmssd_best < 2000 * 64)) return kFailScore;
+// Group arg-min of the lanes' scores; ties go to the lowest lane = the earliest scan step (the reference keeps the first
+// minimum: strict <).
+SVO_D void groupArgMin(const Group& g, int& z, int& lane) {
+#pragma unroll
+  for (int o = 1; o < kGroup; o <<= 1) {
+    const int oz = __shfl_xor_sync(g.mask, z, o), ol = __shfl_xor_sync(g.mask, lane, o);
+    if (oz < z || (oz == z && ol < lane)) { z = oz; lane = ol; }
   }
-  if (short_epi || opt.subpix_refinement) {
-    const int res = findLocalMatch(g, cur_pyr, cur_frame, epi_dir.x, epi_dir.y, m.search_level, opt, align_1d, pwb, m);
-    if (res != kSuccess) return res;
+}
+SVO_D double groupBroadcast(const Group& g, double v, int src) { return __shfl_sync(g.mask, v, src, kGroup); }
+// index of the first lane of the group whose predicate holds, kGroup if none
+SVO_D int groupFirst(const Group& g, bool p) {
+  const unsigned b = (__ballot_sync(g.mask, p) & g.mask) >> ((threadIdx.x & 31) & ~(kGroup - 1));
+  return b ? __ffs((int)b) - 1 : kGroup;
+}
+
+struct WithinBox { int x_hi, y_hi; };  // matcher.cpp:314-322 with the divisions hoisted: 8 <= p < hi
+SVO_D WithinBox makeWithinBox(const svo_camera& cam, int patch_level) {
+  return WithinBox{cam.width / (1 << patch_level) - 8, cam.height / (1 << patch_level) - 8};
+}
+SVO_D bool withinBox(const WithinBox& b, int px, int py) { return !(px < 8 || py < 8 || px >= b.x_hi || py >= b.y_hi); }
+
+// Matcher::scanEpipolarUnitSphere (matcher.cpp:415-488). Lane r of the group evaluates loop iteration i_base + r: the angle,
+// the rotated bearing and its pixel depend on i only. The loop's sequential rules are applied per chunk of 8 iterations: an
+// iteration is skipped when its pixel equals the previous iteration's pixel (`last` always holds the previous iteration's
+// pixel); the first out-of-image pixel of a chunk ends the chunk (first half: jump to half_steps + 1, second half: stop) and
+// the lanes behind it are discarded. Returns the best ZMSSD score and the pixel of the best bearing.
+SVO_D int scanEpipolarUnitSphere(const Group& g, const EpiSetup& e, const svo_camera& cam_cur, const ImgView& cur, int pl,
+                                 const ZmssdRef& zref, double& px_x, double& px_y) {
+  const double inv_pl = 1.0 / (double)(1 << pl);  // exact: x / 2^pl == x * 2^-pl
+  const WithinBox box = makeWithinBox(cam_cur, pl);
+  const double neg_step = -e.step;
+  int zmssd_best = 2000 * 64;
+  V3d f_best = e.f_C;
+  int last_x = 0, last_y = 0;
+  int i_base = 0;
+  while (i_base < e.n_steps) {
+    const int i = i_base + g.r;
+    const bool valid = i < e.n_steps;
+    const double angle = i < e.half_steps ? (double)i * e.step : (double)(i - e.half_steps) * neg_step;
+    const V3d f = angleAxisRotate(e.axis, angle, e.f_C);
+    const V2d px = camProject3(cam_cur, f);
+    const int pxi0 = (int)(px.x * inv_pl + 0.5), pxi1 = (int)(px.y * inv_pl + 0.5);
+    int prev_x = __shfl_up_sync(g.mask, pxi0, 1, kGroup), prev_y = __shfl_up_sync(g.mask, pxi1, 1, kGroup);
+    if (g.r == 0) { prev_x = last_x; prev_y = last_y; }
+    const bool differs = !(pxi0 == prev_x && pxi1 == prev_y);
+    const bool within = withinBox(box, pxi0, pxi1);
+    const int r_out = groupFirst(g, valid && differs && !within);
+    int z = 0x7fffffff, zl = g.r;
+    if (valid && differs && within && g.r < r_out) z = zmssdScore(zref, cur, pxi0 - 4, pxi1 - 4);
+    groupArgMin(g, z, zl);
+    if (z < zmssd_best) {
+      zmssd_best = z;
+      f_best = V3d{groupBroadcast(g, f.x, zl), groupBroadcast(g, f.y, zl), groupBroadcast(g, f.z, zl)};
+    }
+    const int src = r_out < kGroup ? r_out : kGroup - 1;
+    last_x = __shfl_sync(g.mask, pxi0, src, kGroup); last_y = __shfl_sync(g.mask, pxi1, src, kGroup);
+    if (r_out < kGroup) {
+      if (i_base + r_out < e.half_steps) i_base = e.half_steps + 1;  // `i = half_steps; continue;` -> ++i
+      else break;
+    } else {
+      i_base += kGroup;
+    }
   }
-  m.f_cur = normalized3(camBackProject3(cam_cur, m.px_x, m.px_y));
-  return depthFromTriangulation(T_cur_ref, f_ref, m.f_cur, depth);
+  const V2d pb = camProject3(cam_cur, f_best);
+  px_x = pb.x; px_y = pb.y;
+  return zmssd_best;
+}
+
+// Matcher::scanEpipolarUnitPlane (matcher.cpp:340-413). The position on the plane z = 1 is a running sum uv += step, so a
+// chunk forms the 8 prefix sums by the same sequence of additions (every lane forms all eight and keeps its own); besides
+// the rules above, the first scored iteration with i > n_steps / 2 of the forward pass reverses the scan after its score.
+SVO_D int scanEpipolarUnitPlane(const Group& g, const EpiSetup& e, const svo_camera& cam_cur, const ImgView& cur, int pl,
+                                const ZmssdRef& zref, double& px_x, double& px_y) {
+  const double inv_pl = 1.0 / (double)(1 << pl);
+  const WithinBox box = makeWithinBox(cam_cur, pl);
+  const double half_n = e.n_steps * 0.5;
+  int zmssd_best = 2000 * 64;
+  double step_x = e.step_x, step_y = e.step_y;
+  double base_x = e.uvC_x, base_y = e.uvC_y, best_x = e.uvC_x, best_y = e.uvC_y;
+  bool forward = true;
+  int last_x = 0, last_y = 0;
+  int i_base = 0;
+  while (i_base < e.n_steps) {
+    const int i = i_base + g.r;
+    const bool valid = i < e.n_steps;
+    double uv_x = base_x, uv_y = base_y, run_x = base_x, run_y = base_y;
+#pragma unroll
+    for (int t = 1; t <= kGroup; ++t) {
+      run_x += step_x; run_y += step_y;
+      if (t == g.r) { uv_x = run_x; uv_y = run_y; }
+    }
+    double ud, vd;
+    camDistort(cam_cur, uv_x, uv_y, ud, vd);  // project3 of (uv, 1): 1 / 1.0 and the products with it are exact
+    const double pxx = cam_cur.fx * ud + cam_cur.cx, pxy = cam_cur.fy * vd + cam_cur.cy;
+    const int pxi0 = (int)(pxx * inv_pl + 0.5), pxi1 = (int)(pxy * inv_pl + 0.5);
+    int prev_x = __shfl_up_sync(g.mask, pxi0, 1, kGroup), prev_y = __shfl_up_sync(g.mask, pxi1, 1, kGroup);
+    if (g.r == 0) { prev_x = last_x; prev_y = last_y; }
+    const bool differs = !(pxi0 == prev_x && pxi1 == prev_y);
+    const bool within = withinBox(box, pxi0, pxi1);
+    const int r_out = groupFirst(g, valid && differs && !within);
+    const int r_flip = groupFirst(g, forward && valid && differs && within && (double)i > half_n);
+    int z = 0x7fffffff, zl = g.r;
+    if (valid && differs && within && g.r < r_out && g.r <= r_flip) z = zmssdScore(zref, cur, pxi0 - 4, pxi1 - 4);
+    groupArgMin(g, z, zl);
+    if (z < zmssd_best) {
+      zmssd_best = z;
+      best_x = groupBroadcast(g, uv_x, zl); best_y = groupBroadcast(g, uv_y, zl);
+    }
+    const int r_end = r_out < r_flip ? r_out : r_flip;
+    const int src = r_end < kGroup ? r_end : kGroup - 1;
+    last_x = __shfl_sync(g.mask, pxi0, src, kGroup); last_y = __shfl_sync(g.mask, pxi1, src, kGroup);
+    if (r_end < kGroup) {
+      if (r_out < r_flip) {  // left the image
+        if (!forward) break;
+        i_base = (int)(size_t)(e.n_steps * 0.5) + 1;  // `i = n_steps * 0.5; ...; continue;` -> ++i
+      } else {               // scored, then reversed
+        i_base = i_base + r_flip + 1;
+      }
+      step_x = -step_x; step_y = -step_y;
+      base_x = e.uvC_x + step_x; base_y = e.uvC_y + step_y;  // uv = uvC, then the loop's uv += step
+      forward = false;
+    } else {
+      base_x = run_x; base_y = run_y;  // uv of iteration i_base + 8
+      i_base += kGroup;
+    }
+  }
+  double ud, vd;
+  camDistort(cam_cur, best_x, best_y, ud, vd);
+  px_x = cam_cur.fx * ud + cam_cur.cx; px_y = cam_cur.fy * vd + cam_cur.cy;
+  return zmssd_best;
+}
+
+// findLocalMatch (matcher.cpp:262-289): px in/out (level-0 pixels)
+SVO_D int findLocalMatch(const Group& g, const PyrView& cur_pyr, int cur_frame, double dir_x, double dir_y, int patch_level,
+                         const svo_matcher_options& opt, bool align_1d, uint8_t* pwb, double& px_x, double& px_y, double* h_inv) {
+  const double sc = (double)(1 << patch_level);
+  double ps_x = px_x / sc, ps_y = px_y / sc;
+  const ImgView cur = levelView(cur_pyr, cur_frame, patch_level);
+  bool res;
+  if (align_1d) res = align1D(g, cur, dir_x, dir_y, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y, h_inv);
+  else res = align2D(g, cur, pwb, opt.align_max_iter, opt.affine_est_offset != 0, opt.affine_est_gain != 0, ps_x, ps_y);
+  if (!res) return kFailAlignment;
+  px_x = ps_x * sc; px_y = ps_y * sc;
+  return kSuccess;
+}
+
+// The group part of findEpipolarMatchDirect (matcher.cpp:196-229): warp, scan, sub-pixel refinement. px_x / px_y receive px_cur_.
+// SCAN: 1 = unit sphere, 0 = unit plane, 2 = opt.scan_on_unit_sphere at run time (kernels whose launch knows the mode compile one scan).
+template <int SCAN = 2>
+SVO_D int epiMatch(const Group& g, const PyrView& ref_pyr, int ref_frame, const PyrView& cur_pyr, int cur_frame, const svo_camera& cam_cur,
+                   const svo_feature& ft, const EpiSetup& e, const svo_matcher_options& opt, bool align_1d, uint8_t* pwb, double& px_x,
+                   double& px_y, double* h_inv) {
+  if (!warpAffine10(g, e.A, levelView(ref_pyr, ref_frame, ft.level), ft.px[0], ft.px[1], ft.level, e.search_level, pwb))
+    return kFailWarp;
+  if (e.short_epi) {
+    px_x = e.px0_x; px_y = e.px0_y;
+  } else {
+    const ZmssdRef zref = makeZmssdRef(g, pwb);
+    const ImgView cur = levelView(cur_pyr, cur_frame, e.search_level);
+    const bool sphere = SCAN == 2 ? opt.scan_on_unit_sphere != 0 : SCAN == 1;
+    const int zmssd_best = sphere ? scanEpipolarUnitSphere(g, e, cam_cur, cur, e.search_level, zref, px_x, px_y)
+                                  : scanEpipolarUnitPlane(g, e, cam_cur, cur, e.search_level, zref, px_x, px_y);
+    if (!(zmssd_best < 2000 * 64)) return kFailScore;
+  }
+  // both ways end in ONE findLocalMatch call site (code size: these kernels stall on instruction fetch otherwise, profiles/)
+  if (e.short_epi || opt.subpix_refinement) return findLocalMatch(g, cur_pyr, cur_frame, e.dir_x, e.dir_y, e.search_level, opt, align_1d, pwb, px_x, px_y, h_inv);
+  return kSuccess;
+}
+
+// matcher.cpp:231-240: bearing of the match and its depth by triangulation
+SVO_D int epiFinish(const svo_camera& cam_cur, const SE3d& T_cur_ref, const V3d& f_ref, double px_x, double px_y, V3d& f_cur, double* depth) {
+  f_cur = normalized3(camBackProject3(cam_cur, px_x, px_y));
+  return depthFromTriangulation(T_cur_ref, f_ref, f_cur, depth);
+}
+
+template <int SCAN = 2>
+SVO_D int findEpipolarMatchDirect(const Group& g, const PyrView& ref_pyr, int ref_frame, const PyrView& cur_pyr, int cur_frame,
+                                  const svo_camera& cam_ref, const svo_camera& cam_cur, const SE3d& T_cur_ref, const svo_feature& ft,
+                                  double d_estimate_inv, double d_min_inv, double d_max_inv, const svo_matcher_options& opt,
+                                  bool align_1d, uint8_t* pwb, MatchState& m, double* depth) {
+  EpiSetup e;
+  epiSetup(cam_ref, cam_cur, T_cur_ref, ft, d_estimate_inv, d_min_inv, d_max_inv, opt, ref_pyr.n_levels - 1, e);
+  m.A[0][0] = e.A[0][0]; m.A[0][1] = e.A[0][1]; m.A[1][0] = e.A[1][0]; m.A[1][1] = e.A[1][1];
+  m.epi_x = e.epi_x; m.epi_y = e.epi_y;
+  m.reject = e.reject;
+  if (e.early >= 0) return e.early;
+  m.search_level = e.search_level;
+  m.epi_length_pyramid = e.epi_length_pyramid;
+  const int res = epiMatch<SCAN>(g, ref_pyr, ref_frame, cur_pyr, cur_frame, cam_cur, ft, e, opt, align_1d, pwb, m.px_x, m.px_y, &m.h_inv);
+  if (res != kSuccess) return res;
+  return epiFinish(cam_cur, T_cur_ref, V3d{ft.f[0], ft.f[1], ft.f[2]}, m.px_x, m.px_y, m.f_cur, depth);
 }
 
 }  // namespace svo_dev

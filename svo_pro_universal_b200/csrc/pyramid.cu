@@ -219,6 +219,7 @@ static int ensureTensorMap(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int l) {
 
 int svoPyrBuildLaunch(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count) {
   if (count == 0 || pyr->n_levels == 1) return SVO_OK;
+  SVO_BIND(ctx);
   PyrW v;
   for (int l = 0; l < pyr->n_levels; ++l) {
     v.cols[l] = pyr->cols[l]; v.rows[l] = pyr->rows[l]; v.pitch[l] = (int)pyr->pitch[l];
@@ -234,10 +235,9 @@ int svoPyrBuildLaunch(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count
     if (n_items > 0x7fffffffLL) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_pyr_build: too many tiles in one call");
     constexpr int kCtasPerSm = 5;  // 5 x (32 KB ring + 2.7 KB) of shared memory, 1280 threads
     const int grid = (int)std::min<long long>(n_items, (long long)ctx->sm_count * kCtasPerSm);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_pyr) {
       SVO_CUDA_TRY(ctx, cudaFuncSetAttribute(pyr_down_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kTileBytes));
-      attr_set = true;
+      ctx->attr_pyr = true;
     }
     const int rc = ensureTensorMap(ctx, pyr, l0);
     if (rc != SVO_OK) return rc;

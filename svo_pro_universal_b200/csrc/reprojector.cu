@@ -573,10 +573,9 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   int npad = 32;
   while (npad < per_frame_cap) npad <<= 1;
   const size_t sort_smem = (size_t)npad * (8 + 8 + 4);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->attr_reproj) {
     SVO_CUDA_TRY(ctx, cudaFuncSetAttribute(reproj_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPerFrame * 20));
-    attr_set = true;
+    ctx->attr_reproj = true;
   }
   reproj_sort_kernel<<<F, kSortThreads, sort_smem, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);

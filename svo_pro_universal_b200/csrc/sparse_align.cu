@@ -60,12 +60,27 @@ struct Ctl {
   double alpha, beta, alpha_old, beta_old;
   double I_prior[8];            // diagonal of I_prior_
   double L[28], rd[8];          // cached LDL^T factor of H (+ prior) and the pivot reciprocals
-  double chi2;
+  double chi_num, chi_den;      // chi2 = float(chi_num / chi_den) of the last accepted iteration, divided once at the end
   float alpha_f, beta_f;
   int stop, brk;
   int warp_cnt[kWarps];
   int iters[SVO_MAX_LEVELS];
+#ifdef SVO_ALIGN_TIMING
+  // phase clocks of thread 0 (profiling builds only; reported in the unused rows 6-7 of the result's H for 6-DoF runs):
+  // 0 total, 1 setup, 2 reference patches, 3 residual pass (thread 0's own), 4 wait at the first barrier, 5 H rebuild,
+  // 6 serial solve + update + camera refresh, 7 wait at the second barrier, 8 iterations, 9 H rebuilds, 10-15 residual pass of warps
+  // 0-5 (each warp's own clock), 16-20 the serial phase split: cross-warp totals, gradient (+ prior), solve, state update, camera refresh
+  long long tm[28];
+  long long t_mark;
+#endif
 };
+#ifdef SVO_ALIGN_TIMING
+#define SVO_TM_MARK() do { if (tid == 0) ctl.t_mark = clock64(); } while (0)
+#define SVO_TM_ADD(k) do { if (tid == 0) { const long long _t = clock64(); ctl.tm[k] += _t - ctl.t_mark; ctl.t_mark = _t; } } while (0)
+#else
+#define SVO_TM_MARK() do { } while (0)
+#define SVO_TM_ADD(k) do { } while (0)
+#endif
 
 SVO_D double warpSum(double v) {
 #pragma unroll
@@ -214,7 +229,7 @@ SVO_D void ldltSolve(const double* Lf, const double* rdf, const double* g, doubl
   for (int i = D - 1; i >= 0; --i) {
     double s = x[i];
 #pragma unroll
-    for (int j = i + 1; j < D; ++j) s -= L[j][i] * x[j];
+    for (int j = D - 1; j > i; --j) s -= L[j][i] * x[j];  // x[i+1], the newest unknown, enters last: one dependent FMA per row
     x[i] = s;
   }
 #pragma unroll
@@ -372,6 +387,10 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
   const svo_sparse_align_options& opt = P.opt;
 
   // ---- setup -----------------------------------------------------------------------------------------------
+#ifdef SVO_ALIGN_TIMING
+  const long long t_start = clock64();
+  if (tid == 0) { for (int i = 0; i < 28; ++i) ctl.tm[i] = 0; ctl.t_mark = t_start; }
+#endif
   if (tid < n_cams) {
     const SE3d Tci = se3Load(P.T_cam_imu[tid]);
     const SE3d Tic = se3Inv(Tci);
@@ -392,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     ctl.alpha_f = (float)opt.alpha_init;
     ctl.beta_f = (float)opt.beta_init;
     ctl.stop = 0; ctl.brk = 0;
-    ctl.chi2 = 1e10;  // reset(): mini_least_squares_solver.hpp:243
+    ctl.chi_num = 0.0; ctl.chi_den = 0.0;  // no accepted iteration yet: chi2 = 1e10 (reset(): mini_least_squares_solver.hpp:243)
     for (int i = 0; i < SVO_MAX_LEVELS; ++i) ctl.iters[i] = 0;
     for (int i = 0; i < 8; ++i) { ctl.I_prior[i] = 0.0; ctl.rd[i] = 0.0; }
     for (int i = 0; i < 28; ++i) ctl.L[i] = 0.0;
@@ -451,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     }
   }
   n_total = min(n_total, stride);
+  SVO_TM_ADD(1);
 
   if (n_total > 0) {
     if (warp == 0) refreshCameraTransforms(ctl.T, s_camblk, n_cams, lane);
@@ -499,12 +519,19 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
         }
       }
       __syncthreads();
+      SVO_TM_ADD(2);
 
       // ---- Gauss-Newton iterations of this level (mini_least_squares_solver.hpp:42-107) ----
       unsigned vis_prev = 0u;  // bit j: was slot tid + j*kThreads visible in the previous iteration of this level
       const int max_iter = opt.max_iter;
+      // optimizeGaussNewton starts with `old_state = state` (mini_least_squares_solver.hpp:45): a NaN step in the first
+      // iteration of a level leaves the state as the previous level left it. Thread 0 is the only reader / writer of these.
+      if (tid == 0) { ctl.T_old = ctl.T; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta; }
       for (int iter = 0; iter < max_iter; ++iter) {
         double* red = s_red + warp * NV;
+#ifdef SVO_ALIGN_TIMING
+        const long long t_warp0 = clock64();
+#endif
         for (int k = lane; k < NV; k += 32) red[k] = 0.0;
         __syncwarp();
         const float alpha_f = ctl.alpha_f, beta_f = ctl.beta_f;
@@ -670,7 +697,12 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
           }
         }
         vis_prev = vis_now;
+        SVO_TM_ADD(3);
+#ifdef SVO_ALIGN_TIMING
+        if (lane == 0) ctl.tm[10 + warp] += clock64() - t_warp0;  // every warp's own residual pass
+#endif
         __syncthreads();
+        SVO_TM_ADD(4);
         bool h_fresh = ROBUST;
         if (!ROBUST) {
           // H depends only on the visible set: rebuild it when some patch entered or left the image
@@ -692,8 +724,12 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
               reduceH<D>(ps, jp0, jp1, red, lane);
             }
             __syncthreads();
+#ifdef SVO_ALIGN_TIMING
+            if (tid == 0) ctl.tm[9] += 1;
+#endif
           }
         }
+        SVO_TM_ADD(5);
         if (warp == 0) {
           // cross-warp totals: lane k owns accumulator k; the H part is refreshed only when it was re-reduced
           for (int k = lane; k < NV; k += 32) {
@@ -704,6 +740,13 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
             s_tot[k] = t;
           }
           __syncwarp();
+#ifdef SVO_ALIGN_TIMING
+          long long t_s = 0;
+          if (tid == 0) { t_s = clock64(); ctl.tm[16] += t_s - ctl.t_mark; }
+#define SVO_TS(k) do { const long long _t = clock64(); ctl.tm[k] += _t - t_s; t_s = _t; } while (0)
+#else
+#define SVO_TS(k) do { } while (0)
+#endif
           if (lane == 0) {
             ctl.iters[level_slot] = iter + 1;
             double g[D], dx[8], padd[D];
@@ -726,7 +769,6 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
               g[5] -= scale * (mv[2] + (tx * bv[1] - ty * bv[0]));
             }
             if (ILLUM) { g[D - 2] = s_tot[iG6]; g[D - 1] = s_tot[iG6 + 1]; }
-            const double new_chi2 = (double)(float)(s_tot[iChi] / s_tot[iN]);  // float chi2 / n_meas (:540)
             if (P.priors) {  // applyPrior, sparse_img_align_base.cpp:77-107
               const svo_align_prior& pr = P.priors[pair];
               if (iter == 0) {
@@ -753,8 +795,10 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
               }
             }
             dx[6] = 0.0; dx[7] = 0.0;
+            SVO_TS(17);
             if (h_fresh) ldltFactor<D>(s_tot, padd, ctl.L, ctl.rd);  // H (+ prior) is constant until the visible set changes
             ldltSolve<D>(ctl.L, ctl.rd, g, dx);
+            SVO_TS(18);
             if (dx[0] != dx[0]) ctl.stop = 1;  // solveDefaultImpl: isnan(dx[0]) -> stop_
             int brk = 0;
             if (ctl.stop) {
@@ -775,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
               quatNormalizeFast(Tn.q);
               ctl.T_old = Tc; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
               ctl.T = Tn; ctl.alpha = an; ctl.beta = bn;
-              ctl.chi2 = new_chi2;
+              ctl.chi_num = s_tot[iChi]; ctl.chi_den = s_tot[iN];  // chi2_ = new_chi2 = float chi2 / n_meas (:540)
               double x_norm = -1.0;
 #pragma unroll
               for (int i = 0; i < 8; ++i) { const double a = fabs(dx[i]); if (a > x_norm) x_norm = a; }
@@ -784,11 +828,20 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
             ctl.alpha_f = (float)ctl.alpha;
             ctl.beta_f = (float)ctl.beta;
             ctl.brk = brk;
+            SVO_TS(19);
           }
           __syncwarp();
           refreshCameraTransforms(ctl.T, s_camblk, n_cams, lane);
+#ifdef SVO_ALIGN_TIMING
+          if (tid == 0) SVO_TS(20);
+#endif
         }
+        SVO_TM_ADD(6);
         __syncthreads();
+        SVO_TM_ADD(7);
+#ifdef SVO_ALIGN_TIMING
+        if (tid == 0) ctl.tm[8] += 1;
+#endif
         if (ctl.brk) break;
       }
       __syncthreads();
@@ -806,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     }
     r.alpha = ctl.alpha;
     r.beta = ctl.beta;
-    r.chi2 = ctl.chi2;
+    r.chi2 = ctl.chi_den != 0.0 ? (double)(float)(ctl.chi_num / ctl.chi_den) : 1e10;
     // getHessian(): the last evaluated H_ (incl. the prior information) rebuilt from the reduced upper triangle
     for (int i = 0; i < 64; ++i) r.H[i] = 0.0;
     if (n_total > 0) {
@@ -816,6 +869,13 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
       if (P.priors) for (int j = 0; j < 8; ++j) r.H[j * 8 + j] += ctl.I_prior[j];
     }
     r.n_tracked = n_total;
+#ifdef SVO_ALIGN_TIMING
+    ctl.tm[0] = clock64() - t_start;
+    if (D == 6) {  // rows 6-7, then columns 6-7 of rows 0-5: unused by a 6-DoF result
+      for (int i = 0; i < 16; ++i) r.H[48 + i] = (double)ctl.tm[i];
+      for (int i = 16; i < 28; ++i) r.H[((i - 16) >> 1) * 8 + 6 + ((i - 16) & 1)] = (double)ctl.tm[i];
+    }
+#endif
     for (int i = 0; i < SVO_MAX_LEVELS; ++i) r.iters[i] = ctl.iters[i];
     r.stop = ctl.stop;
   }

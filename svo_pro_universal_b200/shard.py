@@ -24,15 +24,17 @@ def gather_to_rank0(local, n_units, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     is_np = isinstance(local, np.ndarray)
+    # bytes per row from the element type, so that a rank with 0 local rows (n_units < world size) still forms a [0, row_bytes] block
     if is_np:
-        t = torch.from_numpy(np.ascontiguousarray(local).view(np.uint8).reshape(local.shape[0], -1))
+        row_bytes = int(local.dtype.itemsize * np.prod(local.shape[1:], dtype=np.int64))
+        t = torch.from_numpy(np.ascontiguousarray(local).reshape(-1).view(np.uint8).reshape(local.shape[0], row_bytes).copy())
     else:
-        t = local.contiguous().view(torch.uint8).reshape(local.shape[0], -1)
+        row_bytes = int(local.element_size() * np.prod(tuple(local.shape[1:]), dtype=np.int64))
+        t = local.contiguous().reshape(-1).view(torch.uint8).reshape(local.shape[0], row_bytes)
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     t = t.to(dev)
     max_rows = -(-n_units // world)
-    row_bytes = t.shape[1]
     pad = torch.zeros((max_rows, row_bytes), dtype=torch.uint8, device=dev)
     pad[: t.shape[0]] = t
     bufs = [torch.empty_like(pad) for _ in range(world)]

@@ -51,6 +51,80 @@ def test_vogiatzis_sequence_of_64_observations(ctx, orc):
     assert np.median(np.abs(got[:, 0] - true_inv)) < 5e-3
 
 
+def test_filter_seq_one_launch_equals_ordered_updates(ctx, orc):
+    """svo_cuda_update_filter_seq: 64 ordered Vogiatzis updates per seed in ONE launch == 64 oracle updates, the reference's return
+    value per update included (negative mean -> false, NaN norm_scale -> false and state untouched). One update agrees to 1e-9
+    relative; over a chain the variance update sigma2' = E[x^2] - mu'^2 amplifies last-bit differences (sigma2 ~ 1e-6 next to
+    mu^2 ~ 0.1), so the chain is held to the 1e-6 of test_vogiatzis_sequence_of_64_observations (north star: 1e-4)."""
+    rng = np.random.default_rng(18)
+    S, O = 6000, 64
+    true_inv = rng.uniform(0.1, 0.6, S)
+    state = np.tile(np.array([1 / 4.0, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (S, 1))
+    mu_range = rng.uniform(0.4, 1.0, S)
+    outlier = rng.uniform(size=(O, S)) < 0.1
+    z = np.where(outlier, rng.uniform(0.01, 0.66, (O, S)), true_inv[None, :] + rng.normal(size=(O, S)) * 0.01)
+    tau2 = np.ascontiguousarray(np.broadcast_to((1e-4 / (np.arange(O) + 1))[:, None], (O, S)))
+    tau2[9, 40:60] = np.nan                             # NaN norm_scale: update refused, state kept
+    exp, ok_exp = state.copy(), np.zeros((O, S), np.uint8)
+    for o in range(O):
+        zo, to = np.ascontiguousarray(z[o]), np.ascontiguousarray(tau2[o])
+        orc.lib().orc_update_filter_vogiatzis_batch(S, zo.ctypes.data_as(orc.f64p), to.ctypes.data_as(orc.f64p), mu_range.ctypes.data_as(orc.f64p),
+                                                    exp.ctypes.data_as(orc.f64p), ok_exp[o].ctypes.data_as(orc.u8p), 4)
+    # a second batch through the negative-mean branch (first update drives mu below zero: reset to 1, update refused)
+    st2 = np.tile(np.array([0.3, 100.0, 10.0, 10.0]), (S, 1))
+    z2 = np.ascontiguousarray(np.broadcast_to(np.array([-5.0, 0.4, 0.41])[:, None], (3, S)))
+    t2 = np.full((3, S), 1e-3)
+    mr2 = np.full(S, 1e4)                               # a wide uniform component: the inlier term wins, the mean follows z = -5
+    exp2, ok2_exp = st2.copy(), np.zeros((3, S), np.uint8)
+    for o in range(3):
+        orc.lib().orc_update_filter_vogiatzis_batch(S, np.ascontiguousarray(z2[o]).ctypes.data_as(orc.f64p), np.ascontiguousarray(t2[o]).ctypes.data_as(orc.f64p),
+                                                    mr2.ctypes.data_as(orc.f64p), exp2.ctypes.data_as(orc.f64p), ok2_exp[o].ctypes.data_as(orc.u8p), 4)
+    got2 = st2.copy()
+    ok2 = capi.update_filter_seq(ctx, z2, t2, mr2, got2)
+    assert np.array_equal(ok2, ok2_exp) and (ok2_exp[0] == 0).all()
+    np.testing.assert_allclose(got2, exp2, rtol=1e-8)
+    got = state.copy()
+    ok = capi.update_filter_seq(ctx, np.ascontiguousarray(z), tau2, mu_range, got)
+    assert np.array_equal(ok, ok_exp) and (ok_exp == 0).sum() == 20
+    np.testing.assert_allclose(got[:, :2], exp[:, :2], rtol=REL_TOL)
+    np.testing.assert_allclose(got, exp, rtol=1e-6)
+    # one update: 1e-9
+    one, one_exp = state.copy(), state.copy()
+    z0, t0 = np.ascontiguousarray(z[0]), np.ascontiguousarray(tau2[0])
+    orc.lib().orc_update_filter_vogiatzis_batch(S, z0.ctypes.data_as(orc.f64p), t0.ctypes.data_as(orc.f64p), mu_range.ctypes.data_as(orc.f64p),
+                                                one_exp.ctypes.data_as(orc.f64p), None, 4)
+    capi.update_filter_seq(ctx, z0.reshape(1, S), t0.reshape(1, S), mu_range, one)
+    np.testing.assert_allclose(one, one_exp, rtol=1e-9)
+    assert np.median(np.abs(got[:, 0] - true_inv)) < 5e-3
+    # device-resident arrays, no ok output
+    import torch
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dstate = d(state)
+    capi.update_filter_seq(ctx, d(z), d(tau2), d(mu_range), dstate)
+    ctx.synchronize(); torch.cuda.synchronize()
+    assert np.array_equal(dstate.cpu().numpy(), got)
+
+
+def test_filter_seq_gaussian(ctx, orc):
+    """depth_filter_utils::updateFilterGaussian (depth_filter.cpp:554-578), 16 ordered updates per seed (same operations as the reference)."""
+    rng = np.random.default_rng(19)
+    S, O = 3000, 16
+    state = np.stack([rng.uniform(0.05, 1.0, S), rng.uniform(1e-4, 0.05, S), np.full(S, 10.0), np.full(S, 10.0)], 1)
+    z = state[None, :, 0] + rng.normal(size=(O, S)) * 0.02
+    tau2 = rng.uniform(1e-6, 1e-3, (O, S))
+    tau2[3, :10] = np.nan
+    exp, ok_exp = state.copy(), np.ones((O, S), np.uint8)
+    for o in range(O):
+        for i in range(S):
+            row = np.ascontiguousarray(exp[i])
+            ok_exp[o, i] = orc.lib().orc_update_filter_gaussian(float(z[o, i]), float(tau2[o, i]), row.ctypes.data_as(orc.f64p))
+            exp[i] = row
+    got = state.copy()
+    ok = capi.update_filter_seq(ctx, np.ascontiguousarray(z), np.ascontiguousarray(tau2), None, got, gaussian=True)
+    assert np.array_equal(ok, ok_exp) and (ok_exp == 0).sum() == 10
+    np.testing.assert_allclose(got, exp, rtol=1e-13, atol=0)
+
+
 def test_compute_tau(ctx, orc):
     rng = np.random.default_rng(4)
     n = 1000

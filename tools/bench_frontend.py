@@ -19,46 +19,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def cpu_chain(scenes, seconds=6.0):
-    """Oracle port of the same per-pair chain (single thread): stereo pairs per second."""
-    import helpers
-    from oracle import orc
-    from svo_pro_universal_b200 import synth
-    prepared = []
-    for sc in scenes:
-        keep = []
-        pyr_r = {c: orc.create_img_pyramid(sc["imgs"][f"r{c}"], 5) for c in range(2)}
-        prepared.append((sc, keep, pyr_r))
-    ang = helpers.reproject_px_error_angle(scenes[0]["cam"])
+    """Oracle port of the same per-pair chain (single thread): stereo pairs per second (the chain itself lives in bench.py)."""
+    import bench
+    prep = bench.cpu_chain_prepare(scenes)
     t0 = time.perf_counter(); n = 0
     while time.perf_counter() - t0 < seconds:
-        sc, keep, pyr_r = prepared[n % len(prepared)]
-        cam = sc["cam"]
-        pyr_c = {c: orc.create_img_pyramid(sc["imgs"][f"c{c}"], 5) for c in range(2)}
-        rfs = [orc.make_frame(pyr_r[c], cam, sc["T_cam_imu"][c], sc["T_imu_world_ref"], sc["px"][c], sc["f"][c], sc["depth"][c], keep=keep) for c in range(2)]
-        cfs = [orc.make_frame(pyr_c[c], cam, sc["T_cam_imu"][c], sc["T_imu_world_ref"], keep=keep) for c in range(2)]
-        r = orc.sparse_align(rfs, cfs, orc.default_align_options(estimate_illumination_gain=1, estimate_illumination_offset=1))
-        for c in range(2):
-            m = len(sc["px"][c])
-            kf = orc.make_frame(pyr_r[c], cam, helpers.IDENTITY7, sc["T_f_w_ref"][c], keep=keep)
-            cf = orc.make_frame(pyr_c[c], cam, helpers.IDENTITY7, np.array(r.T_f_w[c][:]), keep=keep)
-            st = np.tile([1.0, 1e-6, 10.0, 10.0], (m, 1)); st[:, 0] = 1.0 / sc["depth"][c]
-            R, tt = synth.se3_to_Rt(synth.se3_inv(sc["T_f_w_ref"][0]))
-            feat = np.zeros(m, [("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("type", "<i4"), ("level", "<i4")])
-            feat["px"], feat["f"], feat["grad"], feat["type"] = sc["px"][c], sc["f"][c], [1.0, 0.0], 7 if c == 0 else 4
-            tb = dict(n_kfs=1, n_feat=m, n_points=m if c == 0 else 0, kf_seed_mu_range=np.array([1 / 1.5]), kf_feat_begin=np.array([0, m], np.int32),
-                      feat=feat, feat_score=np.linspace(60.0, 11.0, m), feat_seed_state=st,
-                      feat_point=(np.arange(m) if c == 0 else np.full(m, -1)).astype(np.int32), feat_kf=np.zeros(m, np.int32),
-                      pt_pos=((sc["f"][0] * sc["depth"][0][:, None]) @ R.T + tt) if c == 0 else np.zeros((1, 3)),
-                      pt_n_failed=np.zeros(max(m, 1), np.int32), pt_n_succeeded=np.zeros(max(m, 1), np.int32),
-                      pt_obs_begin=(np.arange(m + 1) if c == 0 else np.zeros(1)).astype(np.int32),
-                      obs_feat=(np.arange(m) if c == 0 else np.zeros(1)).astype(np.int32))
-            orc.reproject_match([kf], tb, cf, np.arange(m, dtype=np.int32), 0, np.zeros(416, np.uint8), orc.ReprojOptions(30, 120, 1, 0, 0, 200.0, ang))
-        ns = len(sc["seed_px"])
-        oft = orc.make_features(sc["seed_px"], sc["seed_f"], np.tile([1.0, 0.0], (ns, 1)), np.full(ns, 1, np.int32), np.zeros(ns, np.int32))
-        orc.update_seeds(rfs[0], [cfs[0]], sc["T_cur_ref_gt"].reshape(1, 7), oft, np.full(ns, 1, np.uint8), sc["seed_state"].copy(),
-                         sc["seed_mu_range"], orc.default_matcher_options())
-        orc.detect_features(orc.DETECTOR_FAST_GRAD, pyr_c[0])
-        n += 1
+        n += bench.cpu_chain_once(prep[n % len(prep)])
     return n / (time.perf_counter() - t0)
 
 

@@ -162,6 +162,14 @@ def main():
                 "roofline": {"bound": "hbm", "algorithmic_bytes_per_update": 80, "achieved_GBs": 80 * S * O / (ms_v * 1e-3) / 1e9, "peak_GBs": PEAK,
                              "frac": 80 * S * O / (ms_v * 1e-3) / 1e9 / PEAK, "note": "4 MB working set stays in L2; launch-latency bound at this size"},
                 "cpu_baseline": {"updates_per_s": cpu_v, "cores": NT, "kind": "port"}})
+    if hasattr(capi.lib(), "svo_cuda_update_filter_seq"):
+        d_zs, d_t2s = t(np.ascontiguousarray(np.broadcast_to(z, (O, S)))), t(np.full((O, S), 1e-4))
+        ms_vs = timed(lambda: capi.update_filter_seq(ctx, d_zs, d_t2s, d_mu, d_state), stream, warmup=2, reps=10)
+        out.append({"path": "d: updateFilterVogiatzis, fused (svo_cuda_update_filter_seq)", "config": f"{S} seeds x {O} ordered updates (ONE launch)",
+                    "updates_per_s": S * O / (ms_vs * 1e-3), "ms": ms_vs,
+                    "roofline": {"bound": "hbm", "algorithmic_bytes_per_update": 16 + 64 / O, "achieved_GBs": (16 * O + 64) * S / (ms_vs * 1e-3) / 1e9,
+                                 "peak_GBs": PEAK, "frac": (16 * O + 64) * S / (ms_vs * 1e-3) / 1e9 / PEAK,
+                                 "note": "FP64-pipe bound: ~150 FP64 instructions per update at 64 lanes / clk / SM"}})
     # full updateSeed chain: seeds spread over 125 reference keyframes x 400 seeds, 64 observation frames each (16 unique sequences)
     NSEQ_U, NOBS_U = 4, 16
     seqs = [synth.make_seed_sequence(400 + s, n_seeds=400, n_obs=NOBS_U) for s in range(NSEQ_U)]

@@ -16,7 +16,7 @@ for l in sass.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
     if m:
         fn = m.group(1)
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
+    if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
         per_fn[fn] += 1
         if fn and pat in fn:
             cnt[cur] += 1
