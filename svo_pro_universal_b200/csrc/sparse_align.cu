@@ -33,6 +33,11 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kWarps = kThreads / 32;
+// The warp that runs the serial part of an iteration. (Warps are dealt to the four SM sub-partitions round robin, so sub-partitions
+// 2 and 3 hold one warp of every resident CTA instead of two; moving the serial work there was measured on the B200: 0.888 ms
+// instead of 0.869 ms per 4096 pairs, so it stays on warp 0.)
+constexpr int kSerialWarp = 0;
+constexpr int kTimerTid = 32 * kSerialWarp;
 constexpr int kFixedSlots = 180;                  // compile-time stride for the common <= 180-feature case (max_fts)
 constexpr int kCamBlk = 36;                       // per camera: R_cam_imu (9) | R_imu_cam (9) | t_cam_imu (3) | t_imu_cam (3) | T_cur_ref (12)
 
@@ -61,9 +66,13 @@ struct Ctl {
   double I_prior[8];            // diagonal of I_prior_
   double L[28], rd[8];          // cached LDL^T factor of H (+ prior) and the pivot reciprocals
   double chi_num, chi_den;      // chi2 = float(chi_num / chi_den) of the last accepted iteration, divided once at the end
+  int chi_set;                  // 0 until an iteration was accepted (chi2 = 1e10, the solver's reset value)
   float alpha_f, beta_f;
+  double dx[8];                 // serial-solve path: lane 0 hands dx to the warp
   int stop, brk;
+  int h_dirty;                  // a patch entered or left the image in this iteration: H must be re-reduced
   int warp_cnt[kWarps];
+  int n_total;                  // features in the run (read from here inside the loops: a register copy would be spilled)
   int iters[SVO_MAX_LEVELS];
 #ifdef SVO_ALIGN_TIMING
   // phase clocks of thread 0 (profiling builds only; reported in the unused rows 6-7 of the result's H for 6-DoF runs):
@@ -75,8 +84,8 @@ struct Ctl {
 #endif
 };
 #ifdef SVO_ALIGN_TIMING
-#define SVO_TM_MARK() do { if (tid == 0) ctl.t_mark = clock64(); } while (0)
-#define SVO_TM_ADD(k) do { if (tid == 0) { const long long _t = clock64(); ctl.tm[k] += _t - ctl.t_mark; ctl.t_mark = _t; } } while (0)
+#define SVO_TM_MARK() do { if (tid == kTimerTid) ctl.t_mark = clock64(); } while (0)
+#define SVO_TM_ADD(k) do { if (tid == kTimerTid) { const long long _t = clock64(); ctl.tm[k] += _t - ctl.t_mark; ctl.t_mark = _t; } } while (0)
 #else
 #define SVO_TM_MARK() do { } while (0)
 #define SVO_TM_ADD(k) do { } while (0)
@@ -109,15 +118,13 @@ SVO_D double warpSumMulti(double* v, int lane) {
   return v[0];
 }
 
-// 1/d to within an ulp: hardware seed + one cubic and one quadratic Newton step (6 dependent operations; the
-// IEEE-correct division the compiler emits is about twice as deep and sits on the serial path of every iteration).
+// 1/d to within an ulp: hardware seed (relative error <= 2^-20) + one cubic Newton step (error e^3 < 2^-60): 3 dependent FMAs
+// behind the MUFU; the IEEE-correct division the compiler emits is about 80 cycles deep and sits on the serial path of every iteration.
 SVO_D double fastRcp(double d) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0);
-  x = fma(x, fma(e, e, e), x);
-  e = fma(-d, x, 1.0);
-  return fma(x, e, x);
+  const double e = fma(-d, x, 1.0);
+  return fma(x, fma(e, e, e), x);
 }
 
 // Five taps x0..x0+4 of a row always lie inside two aligned 32-bit words: taps 0-3 in `a`, tap 4 in byte 0 of `b`.
@@ -378,7 +385,10 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
   double* s_red = s_patch + 32 * stride;         // [kWarps][NV]
   double* s_tot = s_red + kWarps * NV;           // [NV]
   double* s_camblk = s_tot + NV;                 // [n_cams][kCamBlk]
-  Ctl& ctl = *reinterpret_cast<Ctl*>(s_camblk + kCamBlk * n_cams);
+  const int NG = 6 * n_cams + (ILLUM ? 2 : 0);   // gradient-related totals: per-camera (c, xyz x c), then g6 g7
+  double* s_Hinv = s_camblk + kCamBlk * n_cams;  // [D][D]   H^-1 (rebuilt with H)
+  double* s_P = s_Hinv + D * D;                  // [D][NG]  H^-1 M: dx = P * totals
+  Ctl& ctl = *reinterpret_cast<Ctl*>(s_P + D * NG + (NG & 1));
   int* s_src = reinterpret_cast<int*>(&ctl + 1);                // [stride] feature index inside its camera's array
   uint8_t* s_cam = reinterpret_cast<uint8_t*>(s_src + stride);  // [stride]
 
@@ -389,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
   // ---- setup -----------------------------------------------------------------------------------------------
 #ifdef SVO_ALIGN_TIMING
   const long long t_start = clock64();
-  if (tid == 0) { for (int i = 0; i < 28; ++i) ctl.tm[i] = 0; ctl.t_mark = t_start; }
+  if (tid == kTimerTid) { for (int i = 0; i < 28; ++i) ctl.tm[i] = 0; ctl.t_mark = t_start; }
 #endif
   if (tid < n_cams) {
     const SE3d Tci = se3Load(P.T_cam_imu[tid]);
@@ -410,8 +420,8 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     ctl.beta = ctl.beta_old = opt.beta_init;
     ctl.alpha_f = (float)opt.alpha_init;
     ctl.beta_f = (float)opt.beta_init;
-    ctl.stop = 0; ctl.brk = 0;
-    ctl.chi_num = 0.0; ctl.chi_den = 0.0;  // no accepted iteration yet: chi2 = 1e10 (reset(): mini_least_squares_solver.hpp:243)
+    ctl.stop = 0; ctl.brk = 0; ctl.h_dirty = 0;
+    ctl.chi_num = 0.0; ctl.chi_den = 0.0; ctl.chi_set = 0;  // no accepted iteration yet: chi2 = 1e10 (reset(): mini_least_squares_solver.hpp:243)
     for (int i = 0; i < SVO_MAX_LEVELS; ++i) ctl.iters[i] = 0;
     for (int i = 0; i < 8; ++i) { ctl.I_prior[i] = 0.0; ctl.rd[i] = 0.0; }
     for (int i = 0; i < 28; ++i) ctl.L[i] = 0.0;
@@ -470,6 +480,8 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     }
   }
   n_total = min(n_total, stride);
+  if (tid == 0) ctl.n_total = n_total;
+  __syncthreads();
   SVO_TM_ADD(1);
 
   if (n_total > 0) {
@@ -477,14 +489,16 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     const bool est_gain = ILLUM && opt.estimate_illumination_gain;
     const bool est_off = ILLUM && opt.estimate_illumination_offset;
     const float wscale_f = (float)opt.weight_scale;
-    const int n_round = ((n_total + kThreads - 1) / kThreads) * kThreads;
-    int level_slot = 0;
+    // Loop-carried scalars of the thread live in shared memory (the feature count in ctl, the visibility bits in the upper bits
+    // of s_cam): the residual pass needs every one of its 80 registers, and a spilled value is a local-memory load that misses
+    // the little L1 left beside the patch store (~260 cycles from L2, on the critical path of every iteration).
+    const volatile int* n_total_s = &ctl.n_total;
 
-    for (int level = opt.max_level; level >= opt.min_level; --level, ++level_slot) {
+    for (int level = opt.max_level; level >= opt.min_level; --level) {
       const double scale = 1.0f / (1 << level);
       // ---- b4: reference patches of this level (sparse_img_align.cpp:319-403) ----
-      for (int s = tid; s < n_total; s += kThreads) {
-        const int c = s_cam[s];
+      for (int s = tid; s < *n_total_s; s += kThreads) {
+        const int c = s_cam[s] & 3;
         const PyrView& rp = P.ref_pyr[c];
         const int rf = P.ref_frame_idx ? P.ref_frame_idx[(size_t)pair * n_cams + c] : pair;
         const uint8_t* img = rp.level(rf, level);
@@ -522,7 +536,6 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
       SVO_TM_ADD(2);
 
       // ---- Gauss-Newton iterations of this level (mini_least_squares_solver.hpp:42-107) ----
-      unsigned vis_prev = 0u;  // bit j: was slot tid + j*kThreads visible in the previous iteration of this level
       const int max_iter = opt.max_iter;
       // optimizeGaussNewton starts with `old_state = state` (mini_least_squares_solver.hpp:45): a NaN step in the first
       // iteration of a level leaves the state as the previous level left it. Thread 0 is the only reader / writer of these.
@@ -535,15 +548,17 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
         for (int k = lane; k < NV; k += 32) red[k] = 0.0;
         __syncwarp();
         const float alpha_f = ctl.alpha_f, beta_f = ctl.beta_f;
-                unsigned vis_now = 0u;
-        int chunk_j = 0;
-        for (int s = tid; s < n_round; s += kThreads, ++chunk_j) {
+        const int n_now = *n_total_s, n_round = ((n_now + kThreads - 1) / kThreads) * kThreads;
+        for (int s = tid; s < n_round; s += kThreads) {
           bool vis = false;
           int c = 0;
           double gx = 0, gy = 0, chi = 0, g6 = 0, g7 = 0;
           PatchSums ps = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-          if (s < n_total) {
-            c = s_cam[s];
+          bool vis_before = false;  // bit 7 of s_cam: the slot was visible in the previous iteration of this level
+          if (s < n_now) {
+            const unsigned cs = s_cam[s];
+            c = cs & 3u;
+            vis_before = (cs & 0x80u) != 0u;
             const double* Rt = s_camblk + kCamBlk * c + 24;
             const double X = s_xyz[s], Y = s_xyz[stride + s], Z = s_xyz[2 * stride + s];
             const V3d pc{Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9], Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10],
@@ -640,12 +655,12 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
               }
             }
           }
-          if (vis) vis_now |= (1u << chunk_j);
-          const bool changed = (iter == 0) || (vis != (((vis_prev >> chunk_j) & 1u) != 0u));
+          if (s < n_now) s_cam[s] = (uint8_t)(c | (vis ? 0x80 : 0));  // only the slot's own thread writes it
+          const bool changed = (iter == 0) || (vis != vis_before);
           const unsigned visb = __ballot_sync(0xffffffffu, vis);
           const unsigned chb = __ballot_sync(0xffffffffu, changed);
           if ((visb | chb) == 0u) continue;
-          const int sl = (s < n_total) ? s : 0;
+          const int sl = (s < n_now) ? s : 0;
           if (ROBUST && visb) {
             double jp0[6], jp1[6];
             patchJacobian<DJ>(s_xyz + sl, s_aux + sl, stride, s_camblk + kCamBlk * c, fabs(P.cams[c].fx), scale, jp0, jp1);
@@ -693,10 +708,9 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
           }
           if (lane == 0) {
             red[iN] += 16.0 * __popc(visb);
-            if (chb) red[iCh] += 1.0;
+            if (!ROBUST && chb) ctl.h_dirty = 1;  // benign race: every writer stores 1; read after the barrier, cleared by thread 0
           }
         }
-        vis_prev = vis_now;
         SVO_TM_ADD(3);
 #ifdef SVO_ALIGN_TIMING
         if (lane == 0) ctl.tm[10 + warp] += clock64() - t_warp0;  // every warp's own residual pass
@@ -705,18 +719,15 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
         SVO_TM_ADD(4);
         bool h_fresh = ROBUST;
         if (!ROBUST) {
-          // H depends only on the visible set: rebuild it when some patch entered or left the image
-          double any = 0.0;
-#pragma unroll
-          for (int w = 0; w < kWarps; ++w) any += s_red[w * NV + iCh];
-          h_fresh = (any != 0.0);
+          // H depends only on the visible set: rebuild it when some patch entered or left the image (flag raised by the residual pass)
+          h_fresh = ctl.h_dirty != 0;
           if (h_fresh) {
-            int cj = 0;
-            for (int s = tid; s < n_round; s += kThreads, ++cj) {
-              const bool vis = (vis_now >> cj) & 1u;
+            for (int s = tid; s < n_round; s += kThreads) {
+              const int sl = (s < n_now) ? s : 0;
+              const unsigned cs = s_cam[sl];
+              const bool vis = s < n_now && (cs & 0x80u) != 0u;
               if (__ballot_sync(0xffffffffu, vis) == 0u) continue;
-              const int sl = (s < n_total) ? s : 0;
-              const int c = s_cam[sl];
+              const int c = cs & 3u;
               PatchSums ps = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
               if (vis) ps = unitWeightSums<ILLUM>(s_patch + sl, stride, est_gain, est_off);
               double jp0[6], jp1[6];
@@ -724,85 +735,163 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
               reduceH<D>(ps, jp0, jp1, red, lane);
             }
             __syncthreads();
+            if (tid == 0) ctl.h_dirty = 0;  // every thread has read the flag (they all passed the barrier above)
 #ifdef SVO_ALIGN_TIMING
-            if (tid == 0) ctl.tm[9] += 1;
+            if (tid == kTimerTid) ctl.tm[9] += 1;
 #endif
           }
         }
         SVO_TM_ADD(5);
-        if (warp == 0) {
+        if (warp == kSerialWarp) {
+          // ---- the serial part of an iteration, kept as short as its data dependences allow (one warp, 8-cycle FP64 latency,
+          // ~30 cycles per shared-memory or shuffle hop): totals -> dx -> state update -> camera transforms.
           // cross-warp totals: lane k owns accumulator k; the H part is refreshed only when it was re-reduced
           for (int k = lane; k < NV; k += 32) {
             if (k < NH && !h_fresh) continue;
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) t += s_red[w * NV + k];
-            s_tot[k] = t;
+            const double* r0 = s_red + k;
+            s_tot[k] = ((r0[0] + r0[NV]) + (r0[2 * NV] + r0[3 * NV])) + (r0[4 * NV] + r0[5 * NV]);
           }
           __syncwarp();
 #ifdef SVO_ALIGN_TIMING
           long long t_s = 0;
-          if (tid == 0) { t_s = clock64(); ctl.tm[16] += t_s - ctl.t_mark; }
-#define SVO_TS(k) do { const long long _t = clock64(); ctl.tm[k] += _t - t_s; t_s = _t; } while (0)
+          if (tid == kTimerTid) { t_s = clock64(); ctl.tm[16] += t_s - ctl.t_mark; }
+#define SVO_TS(k) do { if (tid == kTimerTid) { const long long _t = clock64(); ctl.tm[k] += _t - t_s; t_s = _t; } } while (0)
 #else
 #define SVO_TS(k) do { } while (0)
 #endif
+#ifdef SVO_ALIGN_LEAN  // experiment: no prior path compiled in
+          const bool serial_solve = ROBUST;
+#else
+          const bool serial_solve = ROBUST || P.priors != nullptr;
+#endif
+          double dxk = 0.0;  // lane k < D: dx[k]
+          if (serial_solve) {
+            // robust weights (H changes every iteration) or a prior (its gradient needs log(T_prior^-1 T)): lane 0 forms g and
+            // solves with the LDL^T factor, as round 1 did for every case
+            if (lane == 0) {
+              double g[D], dx[8], padd[D];
+#pragma unroll
+              for (int a2 = 0; a2 < D; ++a2) { g[a2] = 0.0; padd[a2] = 0.0; }
+              for (int cc = 0; cc < n_cams; ++cc) {  // gradient of the pose block from the per-camera sums
+                const double* cb = s_camblk + kCamBlk * cc;
+                const double* Ric = cb + 9;
+                const double* cm = s_tot + iCM + 6 * cc;
+                double bv[3], mv[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                  bv[r] = Ric[3 * r] * cm[0] + Ric[3 * r + 1] * cm[1] + Ric[3 * r + 2] * cm[2];
+                  mv[r] = Ric[3 * r] * cm[3] + Ric[3 * r + 1] * cm[4] + Ric[3 * r + 2] * cm[5];
+                }
+                const double tx = cb[21], ty = cb[22], tz = cb[23];
+                g[0] -= scale * bv[0]; g[1] -= scale * bv[1]; g[2] -= scale * bv[2];
+                g[3] -= scale * (mv[0] + (ty * bv[2] - tz * bv[1]));
+                g[4] -= scale * (mv[1] + (tz * bv[0] - tx * bv[2]));
+                g[5] -= scale * (mv[2] + (tx * bv[1] - ty * bv[0]));
+              }
+              if (ILLUM) { g[D - 2] = s_tot[iG6]; g[D - 1] = s_tot[iG6 + 1]; }
+              if (P.priors) {  // applyPrior, sparse_img_align_base.cpp:77-107
+                const svo_align_prior& pr = P.priors[pair];
+                if (iter == 0) {
+                  double mt = 0, mr = 0;
+#pragma unroll
+                  for (int j = 0; j < 3; ++j) mt = fmax(mt, fabs(s_tot[j * D - (j * (j - 1)) / 2]));
+#pragma unroll
+                  for (int j = 3; j < 6; ++j) mr = fmax(mr, fabs(s_tot[j * D - (j * (j - 1)) / 2]));
+                  for (int j = 0; j < 3; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_trans * mt;
+                  for (int j = 3; j < 6; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_rot * mr;
+                  ctl.I_prior[6] = (D == 8) ? opt.lambda_alpha * s_tot[6 * D - 15] : 0.0;
+                  ctl.I_prior[7] = (D == 8) ? opt.lambda_beta * s_tot[7 * D - 21] : 0.0;
+                }
+                const SE3d Tp = se3Load(pr.T);
+                const SE3d E = se3Mul(se3Inv(Tp), ctl.T);
+                const V3d lr = quatLog(E.q);
+                const double l[6] = {E.t.x, E.t.y, E.t.z, lr.x, lr.y, lr.z};
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { padd[j] = ctl.I_prior[j]; g[j] += ctl.I_prior[j] * l[j]; }
+                if (D == 8) {
+                  padd[D - 2] = ctl.I_prior[6]; padd[D - 1] = ctl.I_prior[7];
+                  g[D - 2] += ctl.I_prior[6] * (pr.alpha - ctl.alpha);
+                  g[D - 1] += ctl.I_prior[7] * (pr.beta - ctl.beta);
+                }
+              }
+              dx[6] = 0.0; dx[7] = 0.0;
+              if (h_fresh) ldltFactor<D>(s_tot, padd, ctl.L, ctl.rd);  // H (+ prior) is constant until the visible set changes
+              ldltSolve<D>(ctl.L, ctl.rd, g, dx);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ctl.dx[i] = dx[i];
+            }
+          } else {
+            // H is constant between changes of the visible set, so dx = H^-1 g = (H^-1 M) * totals with g = M * totals linear in
+            // the reduced sums (M: the rotation of the per-camera sums into the IMU frame, see the header comment). P = H^-1 M is
+            // rebuilt with H; an iteration then costs one short dot product per lane instead of the gradient assembly and two
+            // triangular solves on one lane.
+            if (h_fresh) {
+              if (lane == 0) {
+                double padd[D];
+#pragma unroll
+                for (int a2 = 0; a2 < D; ++a2) padd[a2] = 0.0;
+                ldltFactor<D>(s_tot, padd, ctl.L, ctl.rd);
+              }
+              __syncwarp();
+              if (lane < D) {  // lane i: column i (= row i) of H^-1
+                double e[D], x[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) e[i] = (i == lane) ? 1.0 : 0.0;
+                ldltSolve<D>(ctl.L, ctl.rd, e, x);
+#pragma unroll
+                for (int i = 0; i < D; ++i) s_Hinv[lane * D + i] = x[i];
+              }
+              __syncwarp();
+              for (int idx = lane; idx < D * NG; idx += 32) {
+                const int k = idx / NG, j = idx - k * NG;
+                const double* hk = s_Hinv + k * D;
+                double v;
+                if (j < 6 * n_cams) {
+                  const int cc = j / 6, jj = j - 6 * cc;
+                  const double* cb = s_camblk + kCamBlk * cc;
+                  const double* Ric = cb + 9;
+                  const double tx = cb[21], ty = cb[22], tz = cb[23];
+                  const int col = jj < 3 ? jj : jj - 3;
+                  const double r0c = Ric[col], r1c = Ric[3 + col], r2c = Ric[6 + col];
+                  if (jj < 3) {  // translation sums: rows 0-2 through R_imu_cam, rows 3-5 through [t_imu_cam]x R_imu_cam
+                    v = (hk[0] * r0c + hk[1] * r1c + hk[2] * r2c) +
+                        (hk[3] * (ty * r2c - tz * r1c) + hk[4] * (tz * r0c - tx * r2c) + hk[5] * (tx * r1c - ty * r0c));
+                  } else {       // moment sums: rows 3-5 through R_imu_cam
+                    v = hk[3] * r0c + hk[4] * r1c + hk[5] * r2c;
+                  }
+                  v = -scale * v;
+                } else {         // illumination gradient entries pass straight through
+                  v = hk[6 + (j - 6 * n_cams)];
+                }
+                s_P[idx] = v;
+              }
+              __syncwarp();
+            }
+            if (lane < D) {
+              const double* pk = s_P + lane * NG;
+              const double* tg = s_tot + iCM;  // per-camera sums, then g6 g7: contiguous
+              double acc0 = 0.0, acc1 = 0.0;
+              for (int j = 0; j + 1 < NG; j += 2) { acc0 = fma(pk[j], tg[j], acc0); acc1 = fma(pk[j + 1], tg[j + 1], acc1); }
+              dxk = acc0 + acc1;
+            }
+          }
+          SVO_TS(17);
+          if (!serial_solve && lane < 8) ctl.dx[lane] = dxk;  // lanes D..7 hold 0
+          __syncwarp();
+          SVO_TS(18);
           if (lane == 0) {
-            ctl.iters[level_slot] = iter + 1;
-            double g[D], dx[8], padd[D];
+            // One lane applies the update out of shared memory: the residual pass owns the register file (80 registers at 4 CTAs / SM),
+            // and anything spilled here would go to local memory, which misses the 28 KB of L1 left beside the patch store.
+            double dx[8];
 #pragma unroll
-            for (int a = 0; a < D; ++a) { g[a] = 0.0; padd[a] = 0.0; }
-            for (int cc = 0; cc < n_cams; ++cc) {  // gradient of the pose block from the per-camera sums
-              const double* cb = s_camblk + kCamBlk * cc;
-              const double* Ric = cb + 9;
-              const double* cm = s_tot + iCM + 6 * cc;
-              double bv[3], mv[3];
-#pragma unroll
-              for (int r = 0; r < 3; ++r) {
-                bv[r] = Ric[3 * r] * cm[0] + Ric[3 * r + 1] * cm[1] + Ric[3 * r + 2] * cm[2];
-                mv[r] = Ric[3 * r] * cm[3] + Ric[3 * r + 1] * cm[4] + Ric[3 * r + 2] * cm[5];
-              }
-              const double tx = cb[21], ty = cb[22], tz = cb[23];
-              g[0] -= scale * bv[0]; g[1] -= scale * bv[1]; g[2] -= scale * bv[2];
-              g[3] -= scale * (mv[0] + (ty * bv[2] - tz * bv[1]));
-              g[4] -= scale * (mv[1] + (tz * bv[0] - tx * bv[2]));
-              g[5] -= scale * (mv[2] + (tx * bv[1] - ty * bv[0]));
-            }
-            if (ILLUM) { g[D - 2] = s_tot[iG6]; g[D - 1] = s_tot[iG6 + 1]; }
-            if (P.priors) {  // applyPrior, sparse_img_align_base.cpp:77-107
-              const svo_align_prior& pr = P.priors[pair];
-              if (iter == 0) {
-                double mt = 0, mr = 0;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) mt = fmax(mt, fabs(s_tot[j * D - (j * (j - 1)) / 2]));
-#pragma unroll
-                for (int j = 3; j < 6; ++j) mr = fmax(mr, fabs(s_tot[j * D - (j * (j - 1)) / 2]));
-                for (int j = 0; j < 3; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_trans * mt;
-                for (int j = 3; j < 6; ++j) ctl.I_prior[j] = 1.0 * opt.lambda_rot * mr;
-                ctl.I_prior[6] = (D == 8) ? opt.lambda_alpha * s_tot[6 * D - 15] : 0.0;
-                ctl.I_prior[7] = (D == 8) ? opt.lambda_beta * s_tot[7 * D - 21] : 0.0;
-              }
-              const SE3d Tp = se3Load(pr.T);
-              const SE3d E = se3Mul(se3Inv(Tp), ctl.T);
-              const V3d lr = quatLog(E.q);
-              const double l[6] = {E.t.x, E.t.y, E.t.z, lr.x, lr.y, lr.z};
-#pragma unroll
-              for (int j = 0; j < 6; ++j) { padd[j] = ctl.I_prior[j]; g[j] += ctl.I_prior[j] * l[j]; }
-              if (D == 8) {
-                padd[D - 2] = ctl.I_prior[6]; padd[D - 1] = ctl.I_prior[7];
-                g[D - 2] += ctl.I_prior[6] * (pr.alpha - ctl.alpha);
-                g[D - 1] += ctl.I_prior[7] * (pr.beta - ctl.beta);
-              }
-            }
-            dx[6] = 0.0; dx[7] = 0.0;
-            SVO_TS(17);
-            if (h_fresh) ldltFactor<D>(s_tot, padd, ctl.L, ctl.rd);  // H (+ prior) is constant until the visible set changes
-            ldltSolve<D>(ctl.L, ctl.rd, g, dx);
-            SVO_TS(18);
-            if (dx[0] != dx[0]) ctl.stop = 1;  // solveDefaultImpl: isnan(dx[0]) -> stop_
+            for (int i = 0; i < 8; ++i) dx[i] = ctl.dx[i];
+            int stop = ctl.stop;
+            if (dx[0] != dx[0]) stop = 1;  // solveDefaultImpl: isnan(dx[0]) -> stop_
             int brk = 0;
-            if (ctl.stop) {
-              ctl.T = ctl.T_old; ctl.alpha = ctl.alpha_old; ctl.beta = ctl.beta_old;  // rollback (:76-84)
+            ctl.iters[opt.max_level - level] = iter + 1;
+            if (stop) {
+              ctl.T = ctl.T_old; ctl.alpha = ctl.alpha_old; ctl.beta = ctl.beta_old;  // rollback (mini_least_squares_solver.hpp:76-84)
+              ctl.stop = 1;
               brk = 1;
             } else {
               // update, sparse_img_align_base.cpp:64-75
@@ -811,36 +900,35 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
               inc.q = quatExpFast(V3d{-dx[3], -dx[4], -dx[5]});
               inc.t = V3d{-dx[0], -dx[1], -dx[2]};
               SE3d Tn = se3Mul(Tc, inc);
-              double an = ctl.alpha, bn = ctl.beta;
-              if (ILLUM) {
-                an = (ctl.alpha - dx[6]) / (1.0 + dx[6]);
-                bn = (ctl.beta - dx[7]) / (1.0 + dx[6]);
-              }
               quatNormalizeFast(Tn.q);
-              ctl.T_old = Tc; ctl.alpha_old = ctl.alpha; ctl.beta_old = ctl.beta;
-              ctl.T = Tn; ctl.alpha = an; ctl.beta = bn;
-              ctl.chi_num = s_tot[iChi]; ctl.chi_den = s_tot[iN];  // chi2_ = new_chi2 = float chi2 / n_meas (:540)
+              ctl.T_old = Tc;
+              ctl.T = Tn;
+              const double alpha_c = ctl.alpha, beta_c = ctl.beta;
+              ctl.alpha_old = alpha_c; ctl.beta_old = beta_c;
+              if (ILLUM) {
+                ctl.alpha = (alpha_c - dx[6]) / (1.0 + dx[6]);
+                ctl.beta = (beta_c - dx[7]) / (1.0 + dx[6]);
+              }
+              ctl.chi_num = s_tot[iChi]; ctl.chi_den = s_tot[iN]; ctl.chi_set = 1;  // chi2_ = new_chi2 = float chi2 / n_meas (:540)
               double x_norm = -1.0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { const double a = fabs(dx[i]); if (a > x_norm) x_norm = a; }
+              for (int i = 0; i < 8; ++i) { const double a2 = fabs(dx[i]); if (a2 > x_norm) x_norm = a2; }
               if (x_norm < opt.eps) brk = 1;
             }
             ctl.alpha_f = (float)ctl.alpha;
             ctl.beta_f = (float)ctl.beta;
             ctl.brk = brk;
-            SVO_TS(19);
           }
           __syncwarp();
+          SVO_TS(19);
           refreshCameraTransforms(ctl.T, s_camblk, n_cams, lane);
-#ifdef SVO_ALIGN_TIMING
-          if (tid == 0) SVO_TS(20);
-#endif
+          SVO_TS(20);
         }
         SVO_TM_ADD(6);
         __syncthreads();
         SVO_TM_ADD(7);
 #ifdef SVO_ALIGN_TIMING
-        if (tid == 0) ctl.tm[8] += 1;
+        if (tid == kTimerTid) ctl.tm[8] += 1;
 #endif
         if (ctl.brk) break;
       }
@@ -859,16 +947,16 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     }
     r.alpha = ctl.alpha;
     r.beta = ctl.beta;
-    r.chi2 = ctl.chi_den != 0.0 ? (double)(float)(ctl.chi_num / ctl.chi_den) : 1e10;
+    r.chi2 = ctl.chi_set ? (double)(float)(ctl.chi_num / ctl.chi_den) : 1e10;  // 0 / 0 = NaN when no patch was visible, as the reference
     // getHessian(): the last evaluated H_ (incl. the prior information) rebuilt from the reduced upper triangle
     for (int i = 0; i < 64; ++i) r.H[i] = 0.0;
-    if (n_total > 0) {
+    if (ctl.n_total > 0) {
       int idx = 0;
       for (int a = 0; a < D; ++a)
         for (int b = a; b < D; ++b) { r.H[a * 8 + b] = s_tot[idx]; r.H[b * 8 + a] = s_tot[idx]; ++idx; }
       if (P.priors) for (int j = 0; j < 8; ++j) r.H[j * 8 + j] += ctl.I_prior[j];
     }
-    r.n_tracked = n_total;
+    r.n_tracked = ctl.n_total;
 #ifdef SVO_ALIGN_TIMING
     ctl.tm[0] = clock64() - t_start;
     if (D == 6) {  // rows 6-7, then columns 6-7 of rows 0-5: unused by a 6-DoF result
@@ -884,7 +972,9 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
 inline size_t alignSmemBytes(int slots, int n_cams, bool illum, bool dj) {
   const int D = illum ? 8 : 6, NH = D * (D + 1) / 2;
   const int NV = NH + 6 * n_cams + (illum ? 2 : 0) + 3;
-  const size_t doubles = (size_t)slots * (3 + (dj ? 6 : 1) + 32) + (size_t)(kWarps + 1) * NV + (size_t)kCamBlk * n_cams;
+  const int NG = 6 * n_cams + (illum ? 2 : 0);
+  const size_t doubles = (size_t)slots * (3 + (dj ? 6 : 1) + 32) + (size_t)(kWarps + 1) * NV + (size_t)kCamBlk * n_cams + (size_t)D * D +
+                         (size_t)D * NG + (NG & 1);
   return doubles * 8 + sizeof(Ctl) + (size_t)slots * 5 + 16;
 }
 

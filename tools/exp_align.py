@@ -35,5 +35,5 @@ if tm[:, 0].max() > 0:  # profiling build (make -C svo_pro_universal_b200/csrc t
     it = max(m[8], 1.0)
     print(f"per iteration: residual {m[3]/it:.0f}, barrier1 {m[4]/it:.0f}, H {m[5]/it:.0f}, serial {m[6]/it:.0f}, barrier2 {m[7]/it:.0f}; per level: patches {m[2]/4:.0f}")
     print("residual pass per warp / iteration: " + " ".join(f"w{w}={m[10+w]/it:.0f}" for w in range(6)))
-    print("serial phase / iteration: " + ", ".join(f"{n}={m[16+k]/it:.0f}" for k, n in enumerate(["totals", "gradient", "solve", "update", "refresh"])))
+    print("serial phase / iteration: " + ", ".join(f"{n}={m[16+k]/it:.0f}" for k, n in enumerate(["totals", "dx", "broadcast", "update", "store+refresh"])))
 print(f"lib={os.path.basename(os.environ.get('SVO_CUDA_LIB','libsvo_cuda.so'))} pad={os.environ.get('SVO_ALIGN_PAD_SMEM','0')} B={B} align_ms={e0.elapsed_time(e1)/10:.4f} iters_mean={res['iters'][:, :4].sum(1).mean():.2f} iters0={res['iters'][0][:4].tolist()}")
