@@ -209,17 +209,30 @@ def ref_direct_lib():
 
 
 _ref_frontend = None
+_frontend_libs = {}
+_frontend_variant = "ref"
+
+
+def use_frontend_lib(variant):
+    """Select which library the ref_* front-end entry points go through: "ref" = oracle/_ref/libfrontend_ref.so (the reference's
+    own sources), "swap" = oracle/_ref/libfrontend_swap.so (the same wrapper and reference sources with the hot-path functions
+    replaced, at link time, by svo_pro_universal_b200/host/ref_swap.cpp calling libsvo_cuda.so — needs a GPU)."""
+    global _frontend_variant, _ref_frontend
+    assert variant in ("ref", "swap")
+    _frontend_variant = variant
+    _ref_frontend = _frontend_libs.get(variant)
 
 
 def ref_frontend_lib():
     """The reference's own SparseImgAlign / Matcher / patch_warp / depth_filter code compiled against the shims
-    (oracle/_ref/libfrontend_ref.so; None if it was never built)."""
+    (oracle/_ref/libfrontend_ref.so; None if it was never built). See use_frontend_lib for the link-time-swap variant."""
     global _ref_frontend
     if _ref_frontend is None:
-        so = os.path.join(_HERE, "_ref", "libfrontend_ref.so")
+        so = os.path.join(_HERE, "_ref", "libfrontend_%s.so" % _frontend_variant)
         if not os.path.exists(so):
             return None
         L = C.CDLL(so)
+        _frontend_libs[_frontend_variant] = L
         L.ref_compute_tau.restype = C.c_double
         L.ref_px_error_angle.restype = C.c_double
         L.ref_compute_tau.argtypes = [f64p, f64p, C.c_double, C.c_double]

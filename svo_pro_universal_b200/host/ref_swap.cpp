@@ -28,6 +28,7 @@
 #include <svo/common/frame.h>
 #include <svo/common/camera.h>
 #include <svo/common/seed.h>
+#include <svo/common/logging.h>
 
 #include <cstdio>
 #include <cstdlib>

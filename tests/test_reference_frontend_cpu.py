@@ -110,7 +110,9 @@ def test_bench_cpu_step_reference_equals_port(orc):
     import bench
     uniq = bench.make_unique_pairs(3, 1000)
     keep = []
-    refs, curs, l0 = bench.orc_frames(orc, uniq, keep)
+    refs, l0 = bench.orc_frames(orc, uniq, keep)
+    T0 = bench.perturbed_initial_poses(np.stack([d["T_imu_world_ref"] for d in uniq]), 7)   # per-pair initial guess, as the bench legs
+    curs = [orc.make_frame([d["cur_img"]], d["cam"], d["T_cam_imu"], T0[k], keep=keep) for k, d in enumerate(uniq)]
     opt = orc.default_align_options()
     a = orc.pyramid_align_batch(l0, refs, curs, opt, bench.N_LEVELS, 2)
     b = orc.ref_pyramid_align_batch(l0, refs, curs, opt, bench.N_LEVELS, 2)
