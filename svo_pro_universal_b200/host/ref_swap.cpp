@@ -389,10 +389,19 @@ bool updateSeed(const Frame& cur_frame, Frame& ref_frame, const size_t& seed_ind
   b200swap::check(svo_cuda_update_seeds(b200swap::context(), b200swap::pyramids().get(ref_frame), b200swap::pyramids().get(cur_frame), &cr, &cc, 1, &zero, &ft,
                                         &type, state, &mu_range, 1, &zero, &zero, T, &mo, &dopt, &n_success, &match_result, SVO_MEM_HOST),
                   "svo_cuda_update_seeds");
-  // what the reference leaves behind: the seed's state and type, and the matcher's align_1d option (:423-427)
+  // What the reference leaves behind: the seed's state and type, the matcher's align_1d option (:423-427) and — read by
+  // Reprojector::matchCandidate right after updateSeed (reprojector.cpp:412-440) — the Matcher's public result members. The
+  // batched seed update keeps the match on the device, so the one match this call made is repeated through the Matcher entry
+  // point to fill them (a batch of one either way; the batched callers never need the members).
+  if (match_result >= 0) {
+    matcher.options_.align_1d = (ft.type == (int)FeatureType::kEdgeletSeed || ft.type == (int)FeatureType::kEdgeletSeedConverged);
+    Eigen::Ref<SeedState> before = ref_frame.invmu_sigma2_a_b_vec_.col(seed_index);  // still the state the match was made with
+    double depth = 0.0;
+    matcher.findEpipolarMatchDirect(ref_frame, cur_frame, cur_frame.T_f_w_ * ref_frame.T_f_w_.inverse(), ref_ftr, seed::getInvDepth(before),
+                                    seed::getInvMinDepth(before), seed::getInvMaxDepth(before), depth);
+  }
   for (int k = 0; k < 4; ++k) ref_frame.invmu_sigma2_a_b_vec_(k, seed_index) = state[k];
   ref_frame.type_vec_[seed_index] = static_cast<FeatureType>(type);
-  if (match_result >= 0 || n_success) matcher.options_.align_1d = (ft.type == (int)FeatureType::kEdgeletSeed || ft.type == (int)FeatureType::kEdgeletSeedConverged);
   return n_success != 0;
 }
 

@@ -10,11 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from svo_pro_universal_b200 import capi, synth, batch  # noqa: E402
 
-REPS = 3
+# PROF_SMALL=1: every path at a few CTAs (tools/sanitize.sh runs this under compute-sanitizer, which slows kernels 10-100x)
+SMALL = os.environ.get("PROF_SMALL", "0") == "1"
+REPS = 1 if SMALL else 3
 ctx = capi.Context(0)
 
 # (a)+(b): B pairs, pyramid + FAST + sparse alignment
-B = int(os.environ.get("PROF_PAIRS", "1184"))
+B = int(os.environ.get("PROF_PAIRS", "12" if SMALL else "1184"))
 uniq = [synth.make_align_pair(5000 + s) for s in range(8)]
 pk = batch.tile_batch(batch.pack_align_batch(uniq, max_features=180), B)
 ref = capi.Pyramid(ctx, B, 752, 480, 5); cur = capi.Pyramid(ctx, B, 752, 480, 5)
@@ -40,7 +42,7 @@ for _ in range(REPS):
 del cur
 
 # (c): matcher paths
-NP, NF, NU = 64, 2000, 4
+NP, NF, NU = (2, 300, 2) if SMALL else (64, 2000, 4)
 sets = [synth.make_match_set(300 + s, n_features=NF) for s in range(NU)]
 ref = capi.Pyramid(ctx, NU, 752, 480, 5); cur = capi.Pyramid(ctx, NU, 752, 480, 5)
 ref.upload(np.stack([m["ref_img"] for m in sets])); cur.upload(np.stack([m["cur_img"] for m in sets]))
@@ -63,16 +65,20 @@ print("epipolar success", float((r["result"] == 0).mean()))
 del ref, cur
 
 # (d): depth filter
-S = 50000
+S = 2000 if SMALL else 50000
 state = np.tile(np.array([0.25, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (S, 1))
 z = 0.25 + rng.normal(size=S) * 0.01
 for _ in range(REPS):
     capi.update_filter_vogiatzis(ctx, z, np.full(S, 1e-4), np.full(S, 1 / 1.5), state)
+if hasattr(capi.lib(), "svo_cuda_update_filter_seq"):
+    for _ in range(REPS):
+        capi.update_filter_seq(ctx, np.ascontiguousarray(np.broadcast_to(z, (16, S))), np.full((16, S), 1e-4), np.full(S, 1 / 1.5), state)
+        capi.update_filter_seq(ctx, np.ascontiguousarray(np.broadcast_to(z, (4, S))), np.full((4, S), 1e-4), None, state, gaussian=True)
 q = synth.make_seed_sequence(400, n_seeds=400, n_obs=8)
 n = len(q["px"])
 ref = capi.Pyramid(ctx, 1, 752, 480, 5); cur = capi.Pyramid(ctx, 8, 752, 480, 5)
 ref.upload(q["ref_img"][None]); cur.upload(np.stack(q["cur_imgs"])); ref.build(); cur.build()
-rep = 32
+rep = 1 if SMALL else 32
 ftq = capi.make_features(*(np.concatenate([q[k]] * rep) for k in ("px", "f", "grad")), np.concatenate([q["type"].astype(np.int32)] * rep),
                          np.concatenate([q["level"]] * rep))
 obs = np.tile(np.arange(8, dtype=np.int32)[:, None], (1, n * rep))
@@ -85,7 +91,7 @@ del ref, cur
 
 # (f1): reprojector, 296 current frames sharing one map
 sc = synth.make_reproject_scene(21, n_cur=8)
-K, F = len(sc["kf_imgs"]), 296
+K, F = len(sc["kf_imgs"]), (3 if SMALL else 296)
 ref = capi.Pyramid(ctx, K, 752, 480, 5); cur = capi.Pyramid(ctx, 8, 752, 480, 5)
 ref.upload(np.stack(sc["kf_imgs"])); cur.upload(np.stack(sc["cur_imgs"])); ref.build(); cur.build()
 tb = dict(sc["tables"])
@@ -100,7 +106,7 @@ del ref, cur
 
 # (f4): pose optimizer, 4736 bundles
 pcs = [synth.make_pose_opt_case(40 + s) for s in range(8)]
-BP = 4736
+BP = 24 if SMALL else 4736
 pidx = np.arange(BP) % 8
 pft = [capi.make_features(c["px"], c["f"], c["grad"], c["type"], c["level"]) for c in pcs]
 pbeg = np.concatenate([[0], np.cumsum([len(pft[i]) for i in pidx])]).astype(np.int32)
@@ -115,7 +121,7 @@ print("pose optimizer iterations", float(pres["iters"].mean()), "measurements", 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers  # noqa: E402
 prs = [helpers.stereo_case(81), helpers.stereo_case(82)]
-BS = 256
+BS = 4 if SMALL else 256
 sidS = np.arange(BS) % 2
 q0 = capi.Pyramid(ctx, 2, 752, 480, 5); q1 = capi.Pyramid(ctx, 2, 752, 480, 5)
 q0.upload(np.stack([p[0]["ref_img"] for p in prs])); q1.upload(np.stack([p[1]["ref_img"] for p in prs])); q0.build(); q1.build()
@@ -142,7 +148,7 @@ print("stereo triangulated per pair", float(sS["n_succeeded"].mean()))
 
 # (f4, second half): Point::optimize — 400 points x 128 copies
 cP = helpers.point_opt_cases()
-KP = 128
+KP = 1 if SMALL else 128
 nP, nO = len(cP["pos0"]), len(cP["obs_frame"])
 posP = np.tile(cP["pos0"], (KP, 1))
 begP = np.concatenate([[0], (cP["obs_begin"][1:][None, :] + nO * np.arange(KP)[:, None]).ravel()]).astype(np.int32)
