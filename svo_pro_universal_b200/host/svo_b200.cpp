@@ -2,6 +2,8 @@
 // include/svo_cuda.h, calls ONE entry point with host buffers (SVO_MEM_HOST) and unpacks the results; nothing here
 // computes the hot path on the CPU.
 #include "svo_b200.h"
+#include <cstdlib>
+#include <mutex>
 
 #include <algorithm>
 #include <atomic>
@@ -60,13 +62,27 @@ namespace b200 {
 static void check(int rc, const char* what) {
   if (rc != SVO_OK) throw Error(std::string(what) + " failed with status " + std::to_string(rc) + ": " + svo_cuda_last_error(context()));
 }
+// One context (= one stream) per host thread, on the device named by SVO_B200_DEVICE (default 0); it is destroyed when its thread
+// exits. Objects that outlive a thread (device pyramids cached on frames, the Reprojector's map copy) do not keep a context: they are
+// released through the releasing thread's context, and cudaFree synchronises the whole device.
+namespace {
+struct ThreadContext {
+  svo_cuda_ctx* ctx = nullptr;
+  ~ThreadContext() { if (ctx) svo_cuda_ctx_destroy(ctx); }
+};
+int facadeDevice() {
+  static const int dev = [] { const char* e = std::getenv("SVO_B200_DEVICE"); return e ? std::atoi(e) : 0; }();
+  return dev;
+}
+std::mutex& frameUploadMutex() { static std::mutex m; return m; }
+}  // namespace
 svo_cuda_ctx* context() {
-  static thread_local svo_cuda_ctx* ctx = nullptr;
-  if (!ctx) {
-    const int rc = svo_cuda_ctx_create(0, &ctx);
+  static thread_local ThreadContext tc;
+  if (!tc.ctx) {
+    const int rc = svo_cuda_ctx_create(facadeDevice(), &tc.ctx);
     if (rc != SVO_OK) throw Error("svo_cuda_ctx_create failed (no CUDA device? this front-end has no CPU fallback), status " + std::to_string(rc));
   }
-  return ctx;
+  return tc.ctx;
 }
 GpuPyramid::GpuPyramid(int width, int height, int n_levels) : width_(width), height_(height), n_levels_(n_levels) {
   check(svo_cuda_pyr_create(context(), 1, width, height, n_levels, -1, &pyr_), "svo_cuda_pyr_create");
@@ -74,13 +90,18 @@ GpuPyramid::GpuPyramid(int width, int height, int n_levels) : width_(width), hei
 GpuPyramid::~GpuPyramid() {
   if (pyr_) svo_cuda_pyr_destroy(context(), pyr_);
 }
+// Frames are shared between threads (the reference's tracking thread and its DepthFilter thread both hold FramePtrs), each with its
+// own stream: the lazy upload is serialised, and the copy is published only after the uploading stream has finished building it, so
+// whichever stream reads frame.gpu_ afterwards sees complete levels.
 const GpuPyramid& ensureGpu(const Frame& frame) {
+  std::lock_guard<std::mutex> lock(frameUploadMutex());
   if (!frame.gpu_) {
     if (frame.img_pyr_.empty() || frame.img_pyr_[0].empty()) throw Error("frame has no image");
     const Image& l0 = frame.img_pyr_[0];
     auto g = std::make_shared<GpuPyramid>(l0.cols, l0.rows, int(frame.img_pyr_.size()));
     check(svo_cuda_pyr_upload(context(), g->handle(), 0, 1, l0.data, l0.step, l0.step * l0.rows, SVO_MEM_HOST), "svo_cuda_pyr_upload");
     check(svo_cuda_pyr_build(context(), g->handle(), 0, 1), "svo_cuda_pyr_build");
+    check(svo_cuda_ctx_synchronize(context()), "svo_cuda_ctx_synchronize");
     frame.gpu_ = g;
   }
   return *frame.gpu_;

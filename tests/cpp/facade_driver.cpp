@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <cstring>
 #include <iostream>
+#include <thread>
 #include <vector>
 
 #include "../../svo_pro_universal_b200/host/svo_b200.h"
@@ -121,6 +123,7 @@ int main(int argc, char** argv) {
     }
     // (c) Matcher with the true relative pose
     cur->T_f_w_ = Transformation::fromArray(T_cur_true.data());
+    const size_t seq_matcher_at = out.size();
     {
       Matcher m;
       for (int i = 0; i < N; ++i) {
@@ -145,6 +148,58 @@ int main(int argc, char** argv) {
         for (double v : ref->invmu_sigma2_a_b_vec_[i]) out.push_back(v);
         out.push_back(double(int(ref->type_vec_[i])));
       }
+    }
+    // (e) two host threads on frames that have NO device copy yet: both race into the lazy upload (b200::ensureGpu), each thread
+    // runs on its own context / stream; every result must equal the sequential results of (c)
+    {
+      auto bare = [&](const FramePtr& src) {
+        auto f = std::make_shared<Frame>();
+        f->id_ = src->id_ + 10;
+        f->cam_ = cam;
+        for (const Image& im : src->img_pyr_) {
+          Image c(im.rows, im.cols);
+          for (int y = 0; y < im.rows; ++y) std::memcpy(c.data + size_t(y) * c.step, im.data + size_t(y) * im.step, size_t(im.cols));
+          f->img_pyr_.push_back(std::move(c));
+        }
+        for (Image& im : f->img_pyr_) im.data = im.storage.data();
+        f->T_f_w_ = src->T_f_w_;
+        f->T_cam_imu_ = src->T_cam_imu_;
+        return f;
+      };
+      FramePtr ref2 = bare(ref), cur2 = bare(cur);
+      std::vector<double> ra(3 * size_t(N)), rb(4 * size_t(N));
+      std::string err;
+      std::thread ta([&] {
+        try {
+          Matcher m;
+          for (int i = 0; i < N; ++i) {
+            FeatureWrapper fw{FeatureType(type[i]), ref->px_vec_[i], ref->f_vec_[i], ref->grad_vec_[i], level[i]};
+            Keypoint pc{guess[2 * i], guess[2 * i + 1]};
+            const auto r = m.findMatchDirect(*ref2, *cur2, fw, depth[i], pc);
+            ra[3 * i] = double(int(r)); ra[3 * i + 1] = pc[0]; ra[3 * i + 2] = pc[1];
+          }
+        } catch (const std::exception& e) { err = e.what(); }
+      });
+      std::thread tb([&] {
+        try {
+          Matcher m;
+          for (int i = 0; i < N; ++i) {
+            FeatureWrapper fw{FeatureType(type[i]), ref->px_vec_[i], ref->f_vec_[i], ref->grad_vec_[i], level[i]};
+            double d = 0;
+            const auto r2 = m.findEpipolarMatchDirect(*ref2, *cur2, fw, 1.0 / depth[i], 1.3 / depth[i], 0.7 / depth[i], d);
+            rb[4 * i] = double(int(r2)); rb[4 * i + 1] = d; rb[4 * i + 2] = m.px_cur_[0]; rb[4 * i + 3] = m.px_cur_[1];
+          }
+        } catch (const std::exception& e) { err = e.what(); }
+      });
+      ta.join(); tb.join();
+      if (!err.empty()) throw std::runtime_error("two-thread section: " + err);
+      size_t mismatches = 0;
+      for (int i = 0; i < N; ++i) {
+        const double* s7 = &out[seq_matcher_at + 7 * size_t(i)];
+        for (int k = 0; k < 3; ++k) mismatches += ra[3 * i + k] != s7[k];
+        for (int k = 0; k < 4; ++k) mismatches += rb[4 * i + k] != s7[3 + k];
+      }
+      out.push_back(double(mismatches));
     }
     std::ofstream o(argv[2], std::ios::binary);
     o.write(reinterpret_cast<const char*>(out.data()), sizeof(double) * out.size());

@@ -129,6 +129,9 @@ def test_cpp_facades_match_oracle(orc, tmp_path):
     # (d) DepthFilter::updateSeeds
     n_succ = int(out[p]); p += 1
     sd = out[p:p + 5 * N].reshape(N, 5); p += 5 * N
+    # (e) two host threads (own contexts / streams) racing into the lazy device upload of shared frames: same results as (c)
+    assert out[p] == 0.0, f"{int(out[p])} results differ between the two-thread and the sequential run"
+    p += 1
     assert p == len(out)
     types = np.where(ftype == synth.K_EDGELET, synth.K_EDGELET_SEED, synth.K_CORNER_SEED).astype(np.uint8)
     st = np.tile(np.array([0.25, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (N, 1))
