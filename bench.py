@@ -450,7 +450,14 @@ def leg_headline(rig, sample_n=64):
 
     ref = capi.Pyramid(ctx, B, W, H, N_LEVELS)
     cur = capi.Pyramid(ctx, B, W, H, N_LEVELS)
-    h_cur = rig.pin(pk["cur_imgs"])       # pinned host copies (the e2e leg reads these every step)
+    # page-locked host copies (the e2e leg reads these every step); the images optionally in write-combined pages (--pinned wc)
+    hb_cur = None
+    if args.pinned == "wc":
+        hb_cur = capi.HostBuffer(ctx, pk["cur_imgs"].shape, np.uint8, write_combined=True)
+        hb_cur.array[...] = pk["cur_imgs"]
+        h_cur = torch.from_numpy(hb_cur.array)
+    else:
+        h_cur = rig.pin(pk["cur_imgs"])
     h = {k: rig.pin(pk[k]) for k in ("T_imu_world_ref", "T_imu_world_cur", "n_features", "px", "f", "depth", "eligible")}
     h_res = torch.zeros(B * capi.ALIGN_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     d = {k: v.to(dev) for k, v in h.items()}   # device-resident copies (the `value` leg)
@@ -472,7 +479,7 @@ def leg_headline(rig, sample_n=64):
             ev[1].record(stream)
 
     def step_e2e():
-        cur.upload(h_cur)               # H2D of the new frames' level-0 images from pinned memory
+        cur.upload(h_cur, sync=False)   # H2D of the new frames' level-0 images from page-locked memory
         cur.build()
         capi.sparse_align(ctx, [ref], [cur], [cam], pk["T_cam_imu"], h["T_imu_world_ref"], h["T_imu_world_cur"], h["n_features"],
                           h["px"], h["f"], h["depth"], h["eligible"], gopt, results=h_res)  # stages H2D, copies results D2H, syncs
@@ -581,7 +588,8 @@ def leg_headline(rig, sample_n=64):
         "value": value, "ms_per_step": ms_total / args.steps, "gpu_launches": int(launches), "B": B,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "h2d_GBs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9,
-                "note": "new frames' level-0 images + feature arrays H2D from pinned memory, results D2H, every step"},
+                "host_pages": "write-combined page-locked (svo_cuda_host_alloc)" if args.pinned == "wc" else "page-locked (torch pin_memory)",
+                "note": "new frames' level-0 images + feature arrays H2D from page-locked memory, results D2H, every step"},
         "roofline": roofline("sparse_align_kernel<ILL=0, ROBUST=0, DJ=0, SLOTS=180>", ALGO_BYTES_PER_PAIR, B, align_ms, rig.peaks,
                              "algorithmic bytes 247,044 B/pair; the kernel is FP64-issue / latency bound, not HBM bound (DESIGN.md 4b)",
                              traffic=NCU_DRAM_BYTES_PER_UNIT["sparse_align_kernel"] * B),
@@ -1074,6 +1082,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="frame pairs per GPU per step (headline)")
     ap.add_argument("--unique", type=int, default=32, help="unique synthetic pairs generated per rank (tiled to --batch)")
+    ap.add_argument("--pinned", default="torch", choices=["torch", "wc"], help="host pages of the e2e image uploads: torch pin_memory or write-combined")
     ap.add_argument("--paths", default="fast_1024,match_512k,seeds_50k_x64,frontend_8192",
                     help="comma-separated BASELINE config legs to run after the headline ('' = none)")
     ap.add_argument("--fast-frames", type=int, default=1024)

@@ -57,6 +57,12 @@ int svo_cuda_device_count(void);
 /* sizeof() of a POD struct of this header by name (e.g. "svo_align_result"), -1 if unknown: lets bindings verify their layout. */
 int svo_cuda_sizeof(const char* struct_name);
 
+/* Page-locked host memory for the I/O arrays of SVO_MEM_HOST calls (asynchronous copies need it to overlap and to reach the link's
+ * bandwidth). write_combined != 0 allocates write-combined pages: the CPU should only WRITE them (reads are uncached and slow), the
+ * DMA engine reads them without snooping the CPU caches — meant for upload staging such as camera frames. */
+int svo_cuda_host_alloc(svo_cuda_ctx* ctx, size_t bytes, int write_combined, void** out);
+int svo_cuda_host_free(svo_cuda_ctx* ctx, void* ptr);
+
 /* ---- camera model -------------------------------------------------------------------------- */
 /* Pinhole with optional radial-tangential distortion:
  * vk::cameras::PinholeProjection<NoDistortion|RadialTangentialDistortion>

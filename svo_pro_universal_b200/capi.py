@@ -181,6 +181,9 @@ def lib():
         L.svo_cuda_ctx_destroy.argtypes = [vp]
         L.svo_cuda_ctx_set_stream.argtypes = [vp, vp]
         L.svo_cuda_ctx_synchronize.argtypes = [vp]
+        if hasattr(L, "svo_cuda_host_alloc"):
+            L.svo_cuda_host_alloc.argtypes = [vp, sz, ci, C.POINTER(vp)]
+            L.svo_cuda_host_free.argtypes = [vp, vp]
         L.svo_cuda_grid_cells.argtypes = [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
         L.svo_cuda_pyr_create.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(vp)]
         L.svo_cuda_pyr_destroy.argtypes = [vp, vp]
@@ -230,6 +233,7 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
     "svo_cuda_reproject_match", "svo_cuda_pose_optimize", "svo_cuda_edgelet_detect", "svo_cuda_fastgrad_detect",
     "svo_cuda_angle_histogram_bins", "svo_cuda_stereo_triangulate", "svo_cuda_optimize_points", "svo_cuda_update_filter_seq",
+    "svo_cuda_host_alloc", "svo_cuda_host_free",
 ]
 
 
@@ -320,6 +324,33 @@ class Context:
             pass
 
 
+class HostBuffer:
+    """Page-locked host memory from svo_cuda_host_alloc, exposed as a numpy array (`.array`): the staging buffer of SVO_MEM_HOST calls.
+    write_combined=True: write-only for the CPU (uncached reads), read by the copy engine without cache snooping."""
+
+    def __init__(self, ctx, shape, dtype=np.uint8, write_combined=False):
+        self.ctx = ctx
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        self._p = C.c_void_p()
+        ctx.check(lib().svo_cuda_host_alloc(ctx._h, n, int(bool(write_combined)), C.byref(self._p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+        self.nbytes = n
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().svo_cuda_host_free(self.ctx._h, self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Pyramid:
     """svo_cuda_pyr: a device-resident batch of image pyramids (svo::Frame::img_pyr_ for n_frames frames)."""
 
@@ -329,8 +360,9 @@ class Pyramid:
         ctx.check(lib().svo_cuda_pyr_create(ctx._h, n_frames, width, height, n_levels, halfsample_mode, C.byref(self._h)))
         self.n_frames, self.width, self.height, self.n_levels = n_frames, width, height, n_levels
 
-    def upload(self, images, first=0):
-        """images: [count, H, W] uint8 numpy (host) or torch cuda tensor."""
+    def upload(self, images, first=0, sync=None):
+        """images: [count, H, W] uint8 numpy (host) or torch tensor (pinned host or cuda). sync: wait for the copy (default: only for
+        numpy input, whose pageable buffer must not be freed under the copy; pass False for page-locked HostBuffer arrays)."""
         if not _is_torch(images):
             images = np.ascontiguousarray(images, dtype=np.uint8)
         if images.ndim == 2:
@@ -339,7 +371,7 @@ class Pyramid:
         assert (h, w) == (self.height, self.width)
         p, kind = _ptr(images)
         self.ctx.check(lib().svo_cuda_pyr_upload(self.ctx._h, self._h, first, count, p, w, w * h, kind))
-        if kind == MEM_HOST and not _is_torch(images):
+        if (kind == MEM_HOST and not _is_torch(images)) if sync is None else sync:
             self.ctx.synchronize()  # pageable numpy buffer: do not let it be freed under the copy
 
     def build(self, first=0, count=None):

@@ -104,6 +104,24 @@ int svo_cuda_ctx_synchronize(svo_cuda_ctx* ctx) {
   return SVO_OK;
 }
 
+int svo_cuda_host_alloc(svo_cuda_ctx* ctx, size_t bytes, int write_combined, void** out) {
+  if (!ctx || !out) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_host_alloc: bad arguments");
+  *out = nullptr;
+  SVO_BIND(ctx);
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  if (cudaHostAlloc(out, bytes ? bytes : 1, flags) != cudaSuccess) {
+    cudaGetLastError();
+    return SVO_FAIL(ctx, SVO_ERR_OUT_OF_MEMORY, "svo_cuda_host_alloc: cudaHostAlloc failed");
+  }
+  return SVO_OK;
+}
+
+int svo_cuda_host_free(svo_cuda_ctx* ctx, void* ptr) {
+  if (!ptr) return SVO_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  return cudaFreeHost(ptr) == cudaSuccess ? SVO_OK : SVO_ERR_CUDA;
+}
+
 const char* svo_cuda_last_error(const svo_cuda_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 long long svo_cuda_launch_count(const svo_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
