@@ -134,6 +134,24 @@ int svo_cuda_pyramid_fast_detect(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first
 int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int threshold, int arc_length,
                              int16_t* score_map, uint8_t* nonmax_map, svo_mem mem);
 
+/* The fast:: leaf functions with their list-shaped results (src/fast_neon/include/fast/fast.h:11-41): corners of ONE level of ONE
+ * frame in raster order, as fast_corner_detect_10[_sse2] (arc_length 10) / fast_corner_detect_9[_sse2] (9) push them. */
+typedef struct { short x, y; } svo_fast_xy; /* fast::fast_xy, fast.h:11-15 */
+/* fast_corner_detect_* + fast_corner_score_* + fast_nonmax_3x3 of a level in one call. n_out (HOST pointer in both memory modes) = number
+ * of corners found; the first min(n_out, max_corners) are written: xy_out[i], scores_out[i] = fast_corner_score_10 at `threshold`,
+ * nonmax_out[i] = 1 if fast_nonmax_3x3 keeps corner i (the reference returns the indices of these). Any output may be NULL. The call
+ * synchronises the context's stream. */
+int svo_cuda_fast_corner_list(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int threshold, int arc_length,
+                              int max_corners, svo_fast_xy* xy_out, int* scores_out, uint8_t* nonmax_out, int* n_out, svo_mem mem);
+/* fast_corner_score_10 (fast.h:38; src/fast_neon/src/fast_10_score.cpp:3150-3178) for a caller-supplied list: scores_out[i] = the largest
+ * barrier at which xy[i] is still a corner, `threshold` if it is none above it (pixels closer than 3 to the border: `threshold`). */
+int svo_cuda_fast_corner_score(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int n, const svo_fast_xy* xy,
+                               int threshold, int arc_length, int* scores_out, svo_mem mem);
+/* fast_nonmax_3x3 (fast.h:41; src/fast_neon/src/nonmax_3x3.cpp:17-112) on a raster-ordered list: nonmax_idx_out (capacity n) receives the
+ * indices, ascending, of the corners no 8-neighbour in the list matches or beats; n_out (HOST pointer) their number. Synchronises. */
+int svo_cuda_fast_nonmax_3x3(svo_cuda_ctx* ctx, int n, const svo_fast_xy* xy, const int* scores, int* nonmax_idx_out, int* n_out,
+                             svo_mem mem);
+
 /* ---- (f2) edgelet detector and the FastGrad combination (the reference's default detector, svo_factory.cpp:292-295) ------ */
 /* feature_detection_utils::edgeletDetector_V2 (src/svo_direct/include/svo/direct/feature_detection_utils.h:75-82;
  * src/svo_direct/src/feature_detection_utils.cpp:313-385) with getAngleAtPixelUsingHistogram (:831-839, 945-1009) for the
@@ -235,6 +253,7 @@ typedef struct { /* Matcher public members read back by callers (matcher.h:70-79
   int search_level;
   int reject;
   int _pad;
+  double epi_image[2]; /* Matcher::epi_image_ (matcher.h:73): px_A - px_B, set by findEpipolarMatchDirect */
 } svo_match_out;
 
 /* feature_alignment::align2D (src/svo_direct/include/svo/direct/feature_alignment.h:34-43; .cpp:212-391).
@@ -275,6 +294,15 @@ int svo_cuda_find_epipolar_match_direct(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
                                         const svo_camera* cam_cur, const double* T_cur_ref, const int* T_idx, int M,
                                         const svo_feature* ftrs, const double* d_inv, const svo_matcher_options* opt,
                                         svo_match_out* out, svo_mem mem);
+
+/* Matcher::scanEpipolarLine (matcher.h:111-122; matcher.cpp:324-488) on its own, for M independent scans: segment A~C~B [M][3] each
+ * (points in the cur camera frame), the 8x8 reference patch [M][64] the PatchScore is built from, patch_level [M], the Matcher member
+ * epi_length_pyramid_ [M] the scan length derives from, zmssd_best [M] in/out (the caller's starting value, PatchScore::threshold() in
+ * the reference's own call), image_best [M][2] out. opt: scan_on_unit_sphere and max_epi_search_steps are read. */
+int svo_cuda_scan_epipolar_line(svo_cuda_ctx* ctx, const svo_cuda_pyr* cur_pyr, const int* cur_frame_idx, const svo_camera* cam_cur, int M,
+                                const double* A, const double* B, const double* C, const uint8_t* patch, const int* patch_level,
+                                const double* epi_length_pyramid, const svo_matcher_options* opt, double* image_best, int* zmssd_best,
+                                svo_mem mem);
 
 /* ---- (f3) svo::StereoTriangulation ------------------------------------------------------------------------------- */
 typedef enum { SVO_STEREO_NOT_REACHED = 0, SVO_STEREO_FAILED = 1, SVO_STEREO_SUCCESS = 2 } svo_stereo_status;

@@ -104,6 +104,7 @@ class MatchOut(C.Structure):
         ("reject", C.c_int),
         ("depth", C.c_double),
         ("patch_with_border", C.c_uint8 * 100),
+        ("epi_image", C.c_double * 2),
     ]
 
 
@@ -404,7 +405,7 @@ def make_features(px, f, grad, ftype, level):
 
 MATCH_OUT_NP = np.dtype([("result", "<i4"), ("px_cur", "<f8", 2), ("f_cur", "<f8", 3), ("search_level", "<i4"),
                          ("A_cur_ref", "<f8", 4), ("h_inv", "<f8"), ("epi_length_pyramid", "<f8"), ("reject", "<i4"),
-                         ("depth", "<f8"), ("patch_with_border", "u1", 100)], align=True)
+                         ("depth", "<f8"), ("patch_with_border", "u1", 100), ("epi_image", "<f8", 2)], align=True)
 
 
 def find_match_direct_batch(ref, cur, T_cur_ref, ftrs, ref_depth, px_guess, opt, n_threads=1):
@@ -425,6 +426,24 @@ def find_epipolar_match_direct_batch(ref, cur, T_cur_ref, ftrs, d_inv3, opt, n_t
     d3 = np.ascontiguousarray(d_inv3, np.float64)
     lib().orc_find_epipolar_match_direct_batch(C.byref(ref), C.byref(cur), _f64(T), M, ftrs, _f64(d3), C.byref(opt), out, n_threads)
     return np.frombuffer(out, dtype=MATCH_OUT_NP).copy()
+
+
+def scan_epipolar_line(cur, A, B, Cpt, patch64, patch_level, epi_length_pyramid, opt, zmssd_best=2000 * 64, which="orc"):
+    """Matcher::scanEpipolarLine on its own: (image_best [2], zmssd_best). which = "orc" (restatement) or "ref" (the compiled
+    reference / the swap library, see use_frontend_lib)."""
+    if which == "orc":
+        fn = lib().orc_scan_epipolar_line
+    else:
+        fn = ref_frontend_lib().ref_scan_epipolar_line
+    fn.restype = None
+    fn.argtypes = [C.POINTER(Frame), f64p, f64p, f64p, u8p, C.c_int, C.c_double, C.POINTER(MatcherOptions), f64p, i32p]
+    a, b, c = (np.ascontiguousarray(v, np.float64) for v in (A, B, Cpt))
+    patch = np.ascontiguousarray(patch64, np.uint8).reshape(64)
+    best = np.zeros(2)
+    z = np.array([zmssd_best], np.int32)
+    fn(C.byref(cur), _f64(a), _f64(b), _f64(c), _u8(patch), int(patch_level), float(epi_length_pyramid), C.byref(opt), _f64(best),
+       z.ctypes.data_as(i32p))
+    return best, int(z[0])
 
 
 def update_seeds(ref, cur_frames, T_cur_ref, ftrs, types, states, mu_range, opt, sigma2_thresh=200.0, mappoint_thresh=500.0,

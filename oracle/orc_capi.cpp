@@ -84,6 +84,7 @@ void fillMatchOut(const Matcher& m, Matcher::MatchResult r, double depth, orc_ma
   out->reject = m.reject_;
   out->depth = depth;
   std::memcpy(out->patch_with_border, m.patch_with_border_, 100);
+  out->epi_image[0] = m.epi_image_.x; out->epi_image[1] = m.epi_image_.y;
 }
 
 template <class F>
@@ -356,6 +357,21 @@ int orc_find_epipolar_match_direct(const orc_frame* ref, const orc_frame* cur, c
                                                            d_min_inv, d_max_inv, depth);
   fillMatchOut(m, r, depth, out);
   return int(r);
+}
+
+void orc_scan_epipolar_line(const orc_frame* cur, const double A[3], const double B[3], const double C[3], const uint8_t* patch64,
+                            int patch_level, double epi_length_pyramid, const orc_matcher_options* opt, double image_best[2],
+                            int* zmssd_best) {
+  const MatchFrame cf = matchFrameOf(cur);
+  Matcher m;
+  setMatcherOptions(m, opt);
+  m.epi_length_pyramid_ = epi_length_pyramid;
+  const ZMSSD patch_score(patch64);
+  V2 best{0, 0};
+  const V3 a{A[0], A[1], A[2]}, b{B[0], B[1], B[2]}, c{C[0], C[1], C[2]};
+  if (m.options_.scan_on_unit_sphere) m.scanEpipolarUnitSphere(cf, a, b, c, patch_score, patch_level, &best, zmssd_best);  // matcher.cpp:335-338
+  else m.scanEpipolarUnitPlane(cf, a, b, c, patch_score, patch_level, &best, zmssd_best);
+  image_best[0] = best.x; image_best[1] = best.y;
 }
 
 // StereoTriangulation::compute from the matching loop on — ref: src/svo/src/stereo_triangulation.cpp:87-137.

@@ -91,6 +91,7 @@ typedef struct {
   int reject;
   double depth;
   uint8_t patch_with_border[100];
+  double epi_image[2]; /* Matcher::epi_image_ (matcher.h:73) */
 } orc_match_out;
 
 /* a1 */
@@ -153,6 +154,11 @@ int orc_find_match_direct(const orc_frame* ref, const orc_frame* cur, const doub
 int orc_find_epipolar_match_direct(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], const orc_feature* ftr,
                                    double d_estimate_inv, double d_min_inv, double d_max_inv, const orc_matcher_options* opt,
                                    orc_match_out* out);
+/* Matcher::scanEpipolarLine on its own (matcher.h:111-122; matcher.cpp:324-488): segment A~C~B in the cur camera frame, the 8x8
+ * reference patch, the member epi_length_pyramid_ the scan length derives from; zmssd_best in/out, image_best out. */
+void orc_scan_epipolar_line(const orc_frame* cur, const double A[3], const double B[3], const double C[3], const uint8_t* patch64,
+                            int patch_level, double epi_length_pyramid, const orc_matcher_options* opt, double image_best[2],
+                            int* zmssd_best);
 /* M features sharing (ref, cur, T_cur_ref); threaded. */
 int orc_find_match_direct_batch(const orc_frame* ref, const orc_frame* cur, const double T_cur_ref[7], int M,
                                 const orc_feature* ftrs, const double* ref_depth, const double* px_cur_in,

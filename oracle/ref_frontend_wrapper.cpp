@@ -184,6 +184,7 @@ void fillOut(const svo::Matcher& m, svo::Matcher::MatchResult r, double depth, o
   out->reject = m.reject_;
   out->depth = depth;
   std::memcpy(out->patch_with_border, m.patch_with_border_, 100);
+  out->epi_image[0] = m.epi_image_[0]; out->epi_image[1] = m.epi_image_[1];
 }
 // a one-feature frame around the reference feature (FeatureWrapper binds to the frame's SoA columns)
 void setFeature(svo::Frame& rf, const orc_feature* f) {
@@ -236,6 +237,22 @@ int ref_find_epipolar_match_direct(const orc_frame* ref, const orc_frame* cur, c
   const svo::Matcher::MatchResult r = m.findEpipolarMatchDirect(*rf, *cf, toT(T_cur_ref), fw, d_estimate_inv, d_min_inv, d_max_inv, depth);
   fillOut(m, r, depth, out);
   return int(r);
+}
+
+void ref_scan_epipolar_line(const orc_frame* cur, const double A[3], const double B[3], const double C[3], const uint8_t* patch64,
+                            int patch_level, double epi_length_pyramid, const orc_matcher_options* opt, double image_best[2],
+                            int* zmssd_best) {
+  svo::FramePtr cf = makeFrame(*cur);
+  svo::Matcher m;
+  initMatcher(m);
+  setOptions(m, opt);
+  m.epi_length_pyramid_ = epi_length_pyramid;
+  std::memcpy(m.patch_, patch64, 64);
+  svo::Matcher::PatchScore patch_score(m.patch_);
+  svo::Keypoint best(0.0, 0.0);
+  m.scanEpipolarLine(*cf, Eigen::Vector3d(A[0], A[1], A[2]), Eigen::Vector3d(B[0], B[1], B[2]), Eigen::Vector3d(C[0], C[1], C[2]),
+                     patch_score, patch_level, &best, zmssd_best);
+  image_best[0] = best[0]; image_best[1] = best[1];
 }
 
 void ref_get_warp_matrix_affine(const orc_frame* ref, const orc_frame* cur, const double px_ref[2], const double f_ref[3],

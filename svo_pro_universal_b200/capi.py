@@ -77,7 +77,8 @@ CORNER_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score",
 FEATURE_DTYPE = np.dtype([("px", "<f8", 2), ("f", "<f8", 3), ("grad", "<f8", 2), ("type", "<i4"), ("level", "<i4")])
 MATCH_OUT_DTYPE = np.dtype([("px_cur", "<f8", 2), ("f_cur", "<f8", 3), ("A_cur_ref", "<f8", 4), ("h_inv", "<f8"),
                             ("epi_length_pyramid", "<f8"), ("depth", "<f8"), ("result", "<i4"), ("search_level", "<i4"),
-                            ("reject", "<i4"), ("_pad", "<i4")])
+                            ("reject", "<i4"), ("_pad", "<i4"), ("epi_image", "<f8", 2)])
+FAST_XY_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2")])  # svo_fast_xy = fast::fast_xy
 
 
 class MatcherOptions(C.Structure):
@@ -220,6 +221,12 @@ def lib():
                                                vp, ci, vp, vp, C.POINTER(ReprojectorOptions), vp, vp, ci]
         L.svo_cuda_pose_optimize.argtypes = [vp, ci, C.POINTER(Camera), vp, ci, vp, vp, ci, vp, vp, vp, vp, vp,
                                              C.POINTER(PoseOptimizerOptions), vp, vp, ci]
+        if hasattr(L, "svo_cuda_fast_corner_list"):
+            L.svo_cuda_fast_corner_list.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, C.POINTER(ci), ci]
+            L.svo_cuda_fast_corner_score.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, vp, ci]
+            L.svo_cuda_fast_nonmax_3x3.argtypes = [vp, ci, vp, vp, vp, C.POINTER(ci), ci]
+            L.svo_cuda_scan_epipolar_line.argtypes = [vp, vp, vp, C.POINTER(Camera), ci, vp, vp, vp, vp, vp, vp, C.POINTER(MatcherOptions),
+                                                      vp, vp, ci]
         _lib = L
     return _lib
 
@@ -233,7 +240,8 @@ EXPORTED_SYMBOLS = [
     "svo_cuda_update_filter_vogiatzis", "svo_cuda_compute_tau", "svo_cuda_update_seeds", "svo_cuda_align_pyr2d",
     "svo_cuda_reproject_match", "svo_cuda_pose_optimize", "svo_cuda_edgelet_detect", "svo_cuda_fastgrad_detect",
     "svo_cuda_angle_histogram_bins", "svo_cuda_stereo_triangulate", "svo_cuda_optimize_points", "svo_cuda_update_filter_seq",
-    "svo_cuda_host_alloc", "svo_cuda_host_free",
+    "svo_cuda_host_alloc", "svo_cuda_host_free", "svo_cuda_fast_corner_list", "svo_cuda_fast_corner_score", "svo_cuda_fast_nonmax_3x3",
+    "svo_cuda_scan_epipolar_line",
 ]
 
 
@@ -459,6 +467,64 @@ def fast_level_maps(ctx, pyr, frame, level, threshold=10, arc_length=10):
     ctx.check(lib().svo_cuda_fast_level_maps(ctx._h, pyr._h, frame, level, threshold, arc_length,
                                              C.c_void_p(score.ctypes.data), C.c_void_p(nonmax.ctypes.data), MEM_HOST))
     return score, nonmax
+
+
+def fast_corner_list(ctx, pyr, frame, level, threshold=10, arc_length=10, max_corners=None):
+    """fast_corner_detect_10/9 + fast_corner_score_10 + fast_nonmax_3x3 of one level: (xy FAST_XY_DTYPE [n], scores int32 [n],
+    nonmax uint8 [n]) in raster order (host arrays)."""
+    info = pyr.level_info(level)
+    cap = int(max_corners) if max_corners is not None else max(1024, info["rows"] * info["cols"] // 16)
+    while True:
+        xy = np.zeros(cap, FAST_XY_DTYPE)
+        sc = np.zeros(cap, np.int32)
+        nm = np.zeros(cap, np.uint8)
+        n = C.c_int(0)
+        ctx.check(lib().svo_cuda_fast_corner_list(ctx._h, pyr._h, int(frame), int(level), int(threshold), int(arc_length), cap,
+                                                  C.c_void_p(xy.ctypes.data), C.c_void_p(sc.ctypes.data), C.c_void_p(nm.ctypes.data),
+                                                  C.byref(n), MEM_HOST))
+        if n.value <= cap or max_corners is not None:
+            m = min(n.value, cap)
+            return xy[:m], sc[:m], nm[:m]
+        cap = n.value
+
+
+def fast_corner_score(ctx, pyr, frame, level, xy, threshold=10, arc_length=10):
+    """fast_corner_score_10 of a caller-supplied corner list (FAST_XY_DTYPE): int32 [n]."""
+    xy = np.ascontiguousarray(xy, FAST_XY_DTYPE)
+    out = np.zeros(len(xy), np.int32)
+    ctx.check(lib().svo_cuda_fast_corner_score(ctx._h, pyr._h, int(frame), int(level), len(xy), C.c_void_p(xy.ctypes.data), int(threshold),
+                                               int(arc_length), C.c_void_p(out.ctypes.data), MEM_HOST))
+    return out
+
+
+def fast_nonmax_3x3(ctx, xy, scores):
+    """fast_nonmax_3x3 on a raster-ordered list: indices (int32, ascending) of the surviving corners."""
+    xy = np.ascontiguousarray(xy, FAST_XY_DTYPE)
+    scores = np.ascontiguousarray(scores, np.int32)
+    assert len(xy) == len(scores)
+    idx = np.zeros(max(len(xy), 1), np.int32)
+    n = C.c_int(0)
+    ctx.check(lib().svo_cuda_fast_nonmax_3x3(ctx._h, len(xy), C.c_void_p(xy.ctypes.data), C.c_void_p(scores.ctypes.data),
+                                             C.c_void_p(idx.ctypes.data), C.byref(n), MEM_HOST))
+    return idx[:n.value]
+
+
+def scan_epipolar_line(ctx, cur_pyr, cam_cur, A, B, Cpt, patch, patch_level, epi_length_pyramid, opt, zmssd_best=None, cur_frame_idx=None):
+    """Matcher::scanEpipolarLine for M scans (host arrays): returns (image_best [M, 2], zmssd_best [M])."""
+    A = np.ascontiguousarray(A, np.float64).reshape(-1, 3)
+    M = len(A)
+    B = np.ascontiguousarray(B, np.float64).reshape(M, 3)
+    Cpt = np.ascontiguousarray(Cpt, np.float64).reshape(M, 3)
+    patch = np.ascontiguousarray(patch, np.uint8).reshape(M, 64)
+    patch_level = np.ascontiguousarray(patch_level, np.int32).reshape(M)
+    epi = np.ascontiguousarray(epi_length_pyramid, np.float64).reshape(M)
+    z = np.full(M, 2000 * 64, np.int32) if zmssd_best is None else np.ascontiguousarray(zmssd_best, np.int32).copy()
+    best = np.zeros((M, 2))
+    cf = None if cur_frame_idx is None else np.ascontiguousarray(cur_frame_idx, np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    ctx.check(lib().svo_cuda_scan_epipolar_line(ctx._h, cur_pyr._h, vp(cf), C.byref(cam_cur), M, vp(A), vp(B), vp(Cpt), vp(patch),
+                                                vp(patch_level), vp(epi), C.byref(opt), vp(best), vp(z), MEM_HOST))
+    return best, z
 
 
 def sparse_align(ctx, ref_pyrs, cur_pyrs, cams, T_cam_imu, T_imu_world_ref, T_imu_world_cur, n_features, px, f, depth, eligible,

@@ -286,6 +286,151 @@ int launchLevels(svo_cuda_ctx* ctx, const PyrView& v, FastParams& P, int arc, in
   return SVO_OK;
 }
 
+
+// ---- corner lists in raster order (the shapes of fast.h:32-41: std::vector<fast_xy> + scores + indices of the maxima) -------------
+// Ordered compaction of the flagged elements of a flat index space in chunks of 1024: count per chunk, scan of the chunk counts
+// (one CTA), scatter with an in-chunk scan. 256 threads, 4 consecutive elements per thread, so the output keeps the input order.
+constexpr int kChunk = 1024;
+
+template <class T>
+__global__ void __launch_bounds__(256) flag_count_kernel(const T* flags, int n, int* chunk_count) {
+  const int base = blockIdx.x * kChunk + 4 * threadIdx.x;
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c += (base + j < n && flags[base + j] != 0) ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int s_w[8];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) chunk_count[blockIdx.x] = ((s_w[0] + s_w[1]) + (s_w[2] + s_w[3])) + ((s_w[4] + s_w[5]) + (s_w[6] + s_w[7]));
+}
+
+// exclusive scan of chunk_count in place; total -> *total
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(int* chunk_count, int n_chunks, int* total) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_chunks; base += 1024) {
+    const int i = base + tid;
+    const int v = i < n_chunks ? chunk_count[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      s_w[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int off = carry + (warp ? s_w[warp - 1] : 0) + inc - v;
+    if (i < n_chunks) chunk_count[i] = off;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + s_w[31];
+    __syncthreads();
+  }
+  if (tid == 0) *total = s_carry;
+}
+
+// in-chunk exclusive offset of this thread's first flagged element (block of 256, `c` flagged elements in this thread)
+SVO_D int chunkOffset(int c, int* s_w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  int off = inc - c;
+  for (int w = 0; w < warp; ++w) off += s_w[w];
+  return off;
+}
+
+// dense maps of one level -> (x, y), score, non-max flag of every corner in raster order
+__global__ void __launch_bounds__(256) corner_scatter_kernel(const short* score_map, const uint8_t* nonmax_map, int n, int cols,
+                                                             const int* chunk_off, int max_corners, svo_fast_xy* xy, int* scores,
+                                                             uint8_t* nonmax) {
+  __shared__ int s_w[8];
+  const int base = blockIdx.x * kChunk + 4 * threadIdx.x;
+  short sc[4];
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sc[j] = base + j < n ? score_map[base + j] : (short)0; c += sc[j] != 0; }
+  int at = chunk_off[blockIdx.x] + chunkOffset(c, s_w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (sc[j] == 0) continue;
+    if (at < max_corners) {
+      const int i = base + j, y = i / cols;
+      if (xy) xy[at] = svo_fast_xy{(short)(i - y * cols), (short)y};
+      if (scores) scores[at] = sc[j];
+      if (nonmax) nonmax[at] = nonmax_map[i];
+    }
+    ++at;
+  }
+}
+
+// indices of the flagged list entries, in order (fast_nonmax_3x3's output)
+__global__ void __launch_bounds__(256) index_scatter_kernel(const uint8_t* flags, int n, const int* chunk_off, int* idx_out) {
+  __shared__ int s_w[8];
+  const int base = blockIdx.x * kChunk + 4 * threadIdx.x;
+  bool f[4];
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[j] = base + j < n && flags[base + j] != 0; c += f[j]; }
+  int at = chunk_off[blockIdx.x] + chunkOffset(c, s_w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (f[j]) idx_out[at++] = base + j;
+}
+
+// fast_corner_score_10 of listed pixels (fast_10_score.cpp:3150-3178): the largest barrier at which the pixel is still a corner,
+// `threshold` itself for a pixel that is no corner above it (the reference's search starts at threshold + 1 and returns b - 1).
+template <int ARC>
+__global__ void corner_score_kernel(const uint8_t* img, int cols, int rows, int pitch, const svo_fast_xy* xy, int n, int threshold, int* scores) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = xy[i].x, y = xy[i].y;
+  int sc = threshold;
+  if (x >= 3 && y >= 3 && x < cols - 3 && y < rows - 3) sc = max(threshold, fastMargin<ARC>(img + (size_t)y * pitch + x, pitch));
+  scores[i] = sc;
+}
+
+// fast_nonmax_3x3 on a raster-ordered corner list (nonmax_3x3.cpp:17-112): an entry survives unless one of its 8 neighbours is in the
+// list with a score >= its own. The list is sorted by (y, x), so a neighbour is found by binary search.
+SVO_D int findCorner(const svo_fast_xy* xy, int n, int x, int y) {
+  const int key = (y << 16) | (x & 0xFFFF);
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int k = ((int)xy[mid].y << 16) | ((int)xy[mid].x & 0xFFFF);
+    if (k < key) lo = mid + 1; else hi = mid;
+  }
+  return (lo < n && xy[lo].x == x && xy[lo].y == y) ? lo : -1;
+}
+__global__ void list_nonmax_kernel(const svo_fast_xy* xy, const int* scores, int n, uint8_t* keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = xy[i].x, y = xy[i].y, sc = scores[i];
+  bool k = true;
+  // left / right neighbours are the adjacent list entries
+  if (i > 0 && xy[i - 1].x == x - 1 && xy[i - 1].y == y && scores[i - 1] >= sc) k = false;
+  if (i < n - 1 && xy[i + 1].x == x + 1 && xy[i + 1].y == y && scores[i + 1] >= sc) k = false;
+  for (int dy = -1; dy <= 1 && k; dy += 2) {
+    if (y + dy < 0) continue;
+    for (int dx = -1; dx <= 1 && k; ++dx) {
+      if (x + dx < 0) continue;
+      const int j = findCorner(xy, n, x + dx, y + dy);
+      if (j >= 0 && scores[j] >= sc) k = false;
+    }
+  }
+  keep[i] = k ? 1 : 0;
+}
+
 }  // namespace
 
 int svoPyrBuildLaunch(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count);
@@ -353,6 +498,103 @@ int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fra
   P.first = frame; P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
   const int rc = launchLevels(ctx, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
   if (rc != SVO_OK) return rc;
+  return st.finish();
+}
+
+int svo_cuda_fast_corner_list(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int threshold, int arc_length,
+                              int max_corners, svo_fast_xy* xy_out, int* scores_out, uint8_t* nonmax_out, int* n_out, svo_mem mem) {
+  if (!ctx || !pyr || !n_out || frame < 0 || frame >= pyr->n_frames || level < 0 || level >= pyr->n_levels || threshold < 1 ||
+      threshold > 254 || max_corners < 0 || pyr->cols[level] >= 32768 || pyr->rows[level] >= 32768)
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_fast_corner_list: bad arguments");
+  *n_out = 0;
+  SVO_BIND(ctx);
+  const int cols = pyr->cols[level], rows = pyr->rows[level];
+  const size_t n = (size_t)cols * rows;
+  const int n_chunks = (int)((n + kChunk - 1) / kChunk);
+  Stager st(ctx, SVO_MEM_DEVICE);  // outputs are copied back by hand: only the corners found, not max_corners entries
+  short* d_sc = (short*)st.scratch(n * sizeof(short));
+  uint8_t* d_nm = (uint8_t*)st.scratch(n);
+  int* d_chunk = (int*)st.scratch((size_t)(n_chunks + 1) * sizeof(int));
+  const bool host = mem == SVO_MEM_HOST;
+  const size_t cap = (size_t)(max_corners > 0 ? max_corners : 1);
+  svo_fast_xy* d_xy = xy_out ? (host ? (svo_fast_xy*)st.scratch(cap * sizeof(svo_fast_xy)) : xy_out) : nullptr;
+  int* d_scores = scores_out ? (host ? (int*)st.scratch(cap * sizeof(int)) : scores_out) : nullptr;
+  uint8_t* d_nonmax = nonmax_out ? (host ? (uint8_t*)st.scratch(cap) : nonmax_out) : nullptr;
+  if (st.failed() || !d_sc || !d_nm || !d_chunk) return SVO_FAIL(ctx, SVO_ERR_OUT_OF_MEMORY, "svo_cuda_fast_corner_list: scratch allocation failed");
+  FastParams P;
+  P.min_level = level; P.max_level = level; P.threshold = threshold; P.border = 0; P.cell_size = 1; P.n_cols = 1; P.n_cells = 1;
+  P.first = frame; P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
+  const int rc = launchLevels(ctx, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
+  if (rc != SVO_OK) return rc;
+  flag_count_kernel<short><<<n_chunks, 256, 0, ctx->stream>>>(d_sc, (int)n, d_chunk);
+  SVO_LAUNCH_CHECK(ctx);
+  chunk_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_chunk, n_chunks, d_chunk + n_chunks);
+  SVO_LAUNCH_CHECK(ctx);
+  if (max_corners > 0 && (d_xy || d_scores || d_nonmax)) {
+    corner_scatter_kernel<<<n_chunks, 256, 0, ctx->stream>>>(d_sc, d_nm, (int)n, cols, d_chunk, max_corners, d_xy, d_scores, d_nonmax);
+    SVO_LAUNCH_CHECK(ctx);
+  }
+  int total = 0;
+  SVO_CUDA_TRY(ctx, cudaMemcpyAsync(&total, d_chunk + n_chunks, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SVO_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_out = total;  // may exceed max_corners: the lists then hold the first max_corners corners
+  const size_t m = (size_t)min(total, max_corners);
+  if (host && m) {
+    if (xy_out) SVO_CUDA_TRY(ctx, cudaMemcpyAsync(xy_out, d_xy, m * sizeof(svo_fast_xy), cudaMemcpyDeviceToHost, ctx->stream));
+    if (scores_out) SVO_CUDA_TRY(ctx, cudaMemcpyAsync(scores_out, d_scores, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nonmax_out) SVO_CUDA_TRY(ctx, cudaMemcpyAsync(nonmax_out, d_nonmax, m, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return st.finish();
+}
+
+int svo_cuda_fast_corner_score(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int frame, int level, int n, const svo_fast_xy* xy,
+                               int threshold, int arc_length, int* scores_out, svo_mem mem) {
+  if (!ctx || !pyr || frame < 0 || frame >= pyr->n_frames || level < 0 || level >= pyr->n_levels || n < 0 || (n && (!xy || !scores_out)) ||
+      threshold < 0 || threshold > 254)
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_fast_corner_score: bad arguments");
+  if (n == 0) return SVO_OK;
+  SVO_BIND(ctx);
+  Stager st(ctx, mem);
+  const svo_fast_xy* d_xy = st.in(xy, (size_t)n);
+  int* d_sc = st.out(scores_out, (size_t)n);
+  if (st.failed()) return st.finish();
+  const uint8_t* img = pyr->data[level] + pyr->frame_stride[level] * (size_t)frame;
+  if (arc_length == 9) corner_score_kernel<9><<<(n + 127) / 128, 128, 0, ctx->stream>>>(img, pyr->cols[level], pyr->rows[level], (int)pyr->pitch[level], d_xy, n, threshold, d_sc);
+  else corner_score_kernel<10><<<(n + 127) / 128, 128, 0, ctx->stream>>>(img, pyr->cols[level], pyr->rows[level], (int)pyr->pitch[level], d_xy, n, threshold, d_sc);
+  SVO_LAUNCH_CHECK(ctx);
+  return st.finish();
+}
+
+int svo_cuda_fast_nonmax_3x3(svo_cuda_ctx* ctx, int n, const svo_fast_xy* xy, const int* scores, int* nonmax_idx_out, int* n_out,
+                             svo_mem mem) {
+  if (!ctx || !n_out || n < 0 || (n && (!xy || !scores || !nonmax_idx_out)))
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_fast_nonmax_3x3: bad arguments");
+  *n_out = 0;
+  if (n == 0) return SVO_OK;
+  SVO_BIND(ctx);
+  const int n_chunks = (n + kChunk - 1) / kChunk;
+  Stager st(ctx, mem);
+  const svo_fast_xy* d_xy = st.in(xy, (size_t)n);
+  const int* d_sc = st.in(scores, (size_t)n);
+  const bool host = mem == SVO_MEM_HOST;
+  int* d_idx = host ? (int*)st.scratch((size_t)n * sizeof(int)) : nonmax_idx_out;
+  uint8_t* d_keep = (uint8_t*)st.scratch((size_t)n);
+  int* d_chunk = (int*)st.scratch((size_t)(n_chunks + 1) * sizeof(int));
+  if (st.failed() || !d_idx || !d_keep || !d_chunk) return SVO_FAIL(ctx, SVO_ERR_OUT_OF_MEMORY, "svo_cuda_fast_nonmax_3x3: scratch allocation failed");
+  list_nonmax_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_xy, d_sc, n, d_keep);
+  SVO_LAUNCH_CHECK(ctx);
+  flag_count_kernel<uint8_t><<<n_chunks, 256, 0, ctx->stream>>>(d_keep, n, d_chunk);
+  SVO_LAUNCH_CHECK(ctx);
+  chunk_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_chunk, n_chunks, d_chunk + n_chunks);
+  SVO_LAUNCH_CHECK(ctx);
+  index_scatter_kernel<<<n_chunks, 256, 0, ctx->stream>>>(d_keep, n, d_chunk, d_idx);
+  SVO_LAUNCH_CHECK(ctx);
+  int total = 0;
+  SVO_CUDA_TRY(ctx, cudaMemcpyAsync(&total, d_chunk + n_chunks, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SVO_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_out = total;
+  if (host && total) SVO_CUDA_TRY(ctx, cudaMemcpyAsync(nonmax_idx_out, d_idx, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   return st.finish();
 }
 

@@ -50,6 +50,7 @@ SVO_D void writeOut(const Group& g, svo_match_out* out, int i, const MatchState&
   o.search_level = m.search_level;
   o.reject = m.reject;
   o._pad = 0;
+  o.epi_image[0] = m.epi_x; o.epi_image[1] = m.epi_y;
   out[i] = o;
 }
 
@@ -138,6 +139,53 @@ __global__ void __launch_bounds__(kThreads) align_only_kernel(const AlignOnlyPar
     P.px[2 * i] = x; P.px[2 * i + 1] = y;
     P.converged[i] = conv ? 1 : 0;
     if (P.h_inv) P.h_inv[i] = hinv;
+  }
+}
+
+// Matcher::scanEpipolarLine on its own (matcher.cpp:324-488): one group per scan, the caller supplies the segment, the 8x8 reference
+// patch and the members the scan reads (epi_length_pyramid_, options_).
+struct ScanParams {
+  PyrView cur_pyr;
+  svo_camera cam_cur;
+  const int* cur_frame_idx;
+  int M;
+  const double* A;
+  const double* B;
+  const double* C;
+  const uint8_t* patch;       // [M][64]
+  const int* patch_level;
+  const double* epi_length_pyramid;
+  svo_matcher_options opt;
+  double* image_best;         // [M][2]
+  int* zmssd_best;            // [M] in / out
+};
+
+__global__ void __launch_bounds__(kThreads) scan_epipolar_kernel(const ScanParams P) {
+  __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
+  const Group g = makeGroup();
+  const int gi = threadIdx.x / kGroup;
+  const int i = blockIdx.x * kGroupsPerCta + gi;
+  if (i >= P.M) return;
+  uint8_t* pwb = s_pwb + gi * kPwbPitch;
+  // row r of the 8x8 patch into the interior of the 10x10 bordered layout makeZmssdRef reads
+  for (int x = 0; x < 8; ++x) pwb[(g.r + 1) * 10 + 1 + x] = P.patch[64 * (size_t)i + 8 * g.r + x];
+  __syncwarp(g.mask);
+  const ZmssdRef zref = makeZmssdRef(g, pwb);
+  const int pl = P.patch_level[i];
+  EpiSetup e;
+  memset(&e, 0, sizeof(e));
+  e.epi_length_pyramid = P.epi_length_pyramid[i];
+  const V3d A{P.A[3 * i], P.A[3 * i + 1], P.A[3 * i + 2]}, B{P.B[3 * i], P.B[3 * i + 1], P.B[3 * i + 2]};
+  const V3d C{P.C[3 * i], P.C[3 * i + 1], P.C[3 * i + 2]};
+  epiScanSetup(A, B, C, P.opt, e);
+  const ImgView cur = levelView(P.cur_pyr, P.cur_frame_idx ? P.cur_frame_idx[i] : 0, pl);
+  double px_x = 0.0, px_y = 0.0;
+  const int z0 = P.zmssd_best[i];
+  const int z = P.opt.scan_on_unit_sphere ? scanEpipolarUnitSphere(g, e, P.cam_cur, cur, pl, zref, px_x, px_y, z0)
+                                          : scanEpipolarUnitPlane(g, e, P.cam_cur, cur, pl, zref, px_x, px_y, z0);
+  if (g.r == 0) {
+    P.image_best[2 * i] = px_x; P.image_best[2 * i + 1] = px_y;
+    P.zmssd_best[i] = z;
   }
 }
 
@@ -337,6 +385,35 @@ static int countT(const int* T_idx, int M, svo_mem mem, int* n_T) {
   for (int i = 0; i < M; ++i) mx = T_idx[i] > mx ? T_idx[i] : mx;
   *n_T = mx + 1;
   return SVO_OK;
+}
+
+int svo_cuda_scan_epipolar_line(svo_cuda_ctx* ctx, const svo_cuda_pyr* cur_pyr, const int* cur_frame_idx, const svo_camera* cam_cur, int M,
+                                const double* A, const double* B, const double* C, const uint8_t* patch, const int* patch_level,
+                                const double* epi_length_pyramid, const svo_matcher_options* opt, double* image_best, int* zmssd_best,
+                                svo_mem mem) {
+  if (!ctx || !cur_pyr || !cam_cur || M < 0 || !A || !B || !C || !patch || !patch_level || !epi_length_pyramid || !opt || !image_best ||
+      !zmssd_best)
+    return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, "svo_cuda_scan_epipolar_line: bad arguments");
+  if (M == 0) return SVO_OK;
+  SVO_BIND(ctx);
+  Stager st(ctx, mem);
+  ScanParams P;
+  memset(&P, 0, sizeof(P));
+  P.cur_pyr = makeView(cur_pyr);
+  P.cam_cur = *cam_cur;
+  P.cur_frame_idx = st.in(cur_frame_idx, (size_t)M);
+  P.M = M;
+  P.A = st.in(A, (size_t)M * 3); P.B = st.in(B, (size_t)M * 3); P.C = st.in(C, (size_t)M * 3);
+  P.patch = st.in(patch, (size_t)M * 64);
+  P.patch_level = st.in(patch_level, (size_t)M);
+  P.epi_length_pyramid = st.in(epi_length_pyramid, (size_t)M);
+  P.opt = *opt;
+  P.image_best = st.out(image_best, (size_t)M * 2);
+  P.zmssd_best = st.inout(zmssd_best, (size_t)M);
+  if (st.failed()) return st.finish();
+  scan_epipolar_kernel<<<(M + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
+  SVO_LAUNCH_CHECK(ctx);
+  return st.finish();
 }
 
 int svo_cuda_warp_affine(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const int* ref_frame_idx, const svo_camera* cam_ref,

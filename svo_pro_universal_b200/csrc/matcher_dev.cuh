@@ -502,6 +502,26 @@ struct EpiSetup {
   double step_x, step_y, uvC_x, uvC_y;     // unit plane: step and start on the plane z = 1
 };
 
+// The scan parameters Matcher::scanEpipolarUnitSphere / scanEpipolarUnitPlane derive from the segment A~C~B and the member
+// epi_length_pyramid_ (matcher.cpp:340-362, 415-441); e.epi_length_pyramid must be set.
+SVO_D void epiScanSetup(const V3d& A, const V3d& B, const V3d& C, const svo_matcher_options& opt, EpiSetup& e) {
+  size_t n_steps = (size_t)(e.epi_length_pyramid / 0.7);
+  if (opt.scan_on_unit_sphere) {  // matcher.cpp:415-441
+    n_steps = n_steps > (size_t)opt.max_epi_search_steps ? (size_t)opt.max_epi_search_steps : n_steps;
+    const V3d f_A = normalized3(A), f_B = normalized3(B);
+    e.step = acos(dot3(f_A, f_B)) / n_steps;
+    e.axis = normalized3(cross3(f_B, f_A));
+    e.f_C = normalized3(C);
+    e.n_steps = (int)n_steps;
+    e.half_steps = (int)(n_steps / 2);
+  } else {  // matcher.cpp:340-362
+    e.step_x = (A.x / A.z - B.x / B.z) / n_steps; e.step_y = (A.y / A.z - B.y / B.z) / n_steps;
+    if (n_steps > (size_t)opt.max_epi_search_steps) n_steps = (size_t)opt.max_epi_search_steps;
+    e.uvC_x = C.x / C.z; e.uvC_y = C.y / C.z;
+    e.n_steps = (int)n_steps;
+  }
+}
+
 SVO_D void epiSetup(const svo_camera& cam_ref, const svo_camera& cam_cur, const SE3d& T_cur_ref, const svo_feature& ft, double d_estimate_inv,
                     double d_min_inv, double d_max_inv, const svo_matcher_options& opt, int max_level, EpiSetup& e) {
   const V3d f_ref{ft.f[0], ft.f[1], ft.f[2]};
@@ -532,21 +552,7 @@ SVO_D void epiSetup(const svo_camera& cam_ref, const svo_camera& cam_cur, const 
     return;
   }
   const V3d C = Rf + T_cur_ref.t * d_estimate_inv;
-  size_t n_steps = (size_t)(e.epi_length_pyramid / 0.7);
-  if (opt.scan_on_unit_sphere) {  // matcher.cpp:415-441
-    n_steps = n_steps > (size_t)opt.max_epi_search_steps ? (size_t)opt.max_epi_search_steps : n_steps;
-    const V3d f_A = normalized3(A), f_B = normalized3(B);
-    e.step = acos(dot3(f_A, f_B)) / n_steps;
-    e.axis = normalized3(cross3(f_B, f_A));
-    e.f_C = normalized3(C);
-    e.n_steps = (int)n_steps;
-    e.half_steps = (int)(n_steps / 2);
-  } else {  // matcher.cpp:340-362
-    e.step_x = (A.x / A.z - B.x / B.z) / n_steps; e.step_y = (A.y / A.z - B.y / B.z) / n_steps;
-    if (n_steps > (size_t)opt.max_epi_search_steps) n_steps = (size_t)opt.max_epi_search_steps;
-    e.uvC_x = C.x / C.z; e.uvC_y = C.y / C.z;
-    e.n_steps = (int)n_steps;
-  }
+  epiScanSetup(A, B, C, opt, e);
 }
 
 // Group arg-min of the lanes' scores; ties go to the lowest lane = the earliest scan step (the reference keeps the first
@@ -577,11 +583,11 @@ SVO_D bool withinBox(const WithinBox& b, int px, int py) { return !(px < 8 || py
 // pixel); the first out-of-image pixel of a chunk ends the chunk (first half: jump to half_steps + 1, second half: stop) and
 // the lanes behind it are discarded. Returns the best ZMSSD score and the pixel of the best bearing.
 SVO_D int scanEpipolarUnitSphere(const Group& g, const EpiSetup& e, const svo_camera& cam_cur, const ImgView& cur, int pl,
-                                 const ZmssdRef& zref, double& px_x, double& px_y) {
+                                 const ZmssdRef& zref, double& px_x, double& px_y, const int zmssd_init = 2000 * 64) {
   const double inv_pl = 1.0 / (double)(1 << pl);  // exact: x / 2^pl == x * 2^-pl
   const WithinBox box = makeWithinBox(cam_cur, pl);
   const double neg_step = -e.step;
-  int zmssd_best = 2000 * 64;
+  int zmssd_best = zmssd_init;  // PatchScore::threshold() in findEpipolarMatchDirect (matcher.cpp:167)
   V3d f_best = e.f_C;
   int last_x = 0, last_y = 0;
   int i_base = 0;
@@ -622,11 +628,11 @@ SVO_D int scanEpipolarUnitSphere(const Group& g, const EpiSetup& e, const svo_ca
 // chunk forms the 8 prefix sums by the same sequence of additions (every lane forms all eight and keeps its own); besides
 // the rules above, the first scored iteration with i > n_steps / 2 of the forward pass reverses the scan after its score.
 SVO_D int scanEpipolarUnitPlane(const Group& g, const EpiSetup& e, const svo_camera& cam_cur, const ImgView& cur, int pl,
-                                const ZmssdRef& zref, double& px_x, double& px_y) {
+                                const ZmssdRef& zref, double& px_x, double& px_y, const int zmssd_init = 2000 * 64) {
   const double inv_pl = 1.0 / (double)(1 << pl);
   const WithinBox box = makeWithinBox(cam_cur, pl);
   const double half_n = e.n_steps * 0.5;
-  int zmssd_best = 2000 * 64;
+  int zmssd_best = zmssd_init;  // PatchScore::threshold() in findEpipolarMatchDirect (matcher.cpp:167)
   double step_x = e.step_x, step_y = e.step_y;
   double base_x = e.uvC_x, base_y = e.uvC_y, best_x = e.uvC_x, best_y = e.uvC_y;
   bool forward = true;

@@ -25,6 +25,7 @@
 #include <svo/direct/feature_alignment.h>
 #include <svo/direct/feature_detection_utils.h>
 #include <svo/direct/patch_utils.h>
+#include <svo/direct/patch_score.h>
 #include <svo/common/frame.h>
 #include <svo/common/camera.h>
 #include <svo/common/seed.h>
@@ -321,6 +322,7 @@ Matcher::MatchResult Matcher::findEpipolarMatchDirect(const Frame& ref_frame, co
                   "svo_cuda_find_epipolar_match_direct");
   const MatchResult r = static_cast<MatchResult>(out.result);
   reject_ = out.reject != 0;
+  epi_image_ = Eigen::Vector2d(out.epi_image[0], out.epi_image[1]);  // matcher.cpp:176: set before every return
   A_cur_ref_(0, 0) = out.A_cur_ref[0]; A_cur_ref_(0, 1) = out.A_cur_ref[1]; A_cur_ref_(1, 0) = out.A_cur_ref[2]; A_cur_ref_(1, 1) = out.A_cur_ref[3];
   if (r == MatchResult::kFailAngle) return r;  // matcher.cpp:181-192: returns before the search level is chosen
   search_level_ = out.search_level;
@@ -335,9 +337,15 @@ Matcher::MatchResult Matcher::findEpipolarMatchDirect(const Frame& ref_frame, co
   return r;
 }
 
-void Matcher::scanEpipolarLine(const Frame&, const Eigen::Vector3d&, const Eigen::Vector3d&, const Eigen::Vector3d&, const PatchScore&, const int,
-                               Keypoint*, int*) {
-  LOG(FATAL) << "Matcher::scanEpipolarLine: the scan runs inside svo_cuda_find_epipolar_match_direct; there is no stand-alone entry point";
+void Matcher::scanEpipolarLine(const Frame& frame, const Eigen::Vector3d& A, const Eigen::Vector3d& B, const Eigen::Vector3d& C,
+                               const PatchScore& patch_score, const int patch_level, Keypoint* image_best, int* zmssd_best) {
+  const svo_camera cc = b200swap::toCamera(*frame.cam());
+  const svo_matcher_options mo = b200swap::toOptions(options_);
+  double best[2] = {0.0, 0.0};
+  b200swap::check(svo_cuda_scan_epipolar_line(b200swap::context(), b200swap::pyramids().get(frame), nullptr, &cc, 1, A.data(), B.data(), C.data(),
+                                              patch_score.ref_patch_, &patch_level, &epi_length_pyramid_, &mo, best, zmssd_best, SVO_MEM_HOST),
+                  "svo_cuda_scan_epipolar_line");
+  *image_best = Keypoint(best[0], best[1]);
 }
 
 std::string Matcher::getResultString(const Matcher::MatchResult& result) {  // matcher.cpp:243-260

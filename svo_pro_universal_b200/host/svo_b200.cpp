@@ -263,6 +263,18 @@ static svo_feature cFeature(const FeatureWrapper& f) {
   c.level = f.level;
   return c;
 }
+// Matcher::patch_with_border_ / patch_ (matcher.h:70-71): the warped reference patch of one feature, as the matcher kernels form it
+// (patch_warp.cpp:97-156 + patch_utils::createPatchFromPatchWithBorder) — one more single-feature launch, only for the callers
+// that read the members.
+static void warpedPatch(Matcher& m, const Frame& ref_frame, const Frame& cur_frame, const double T_cur_ref[7], const svo_feature& ft, double depth) {
+  double A[4];
+  int sl = 0;
+  uint8_t ok = 0;
+  b200::check(svo_cuda_warp_affine(b200::context(), b200::ensureGpu(ref_frame).handle(), nullptr, &ref_frame.cam_->model, &cur_frame.cam_->model,
+                                   T_cur_ref, nullptr, 1, &ft, &depth, A, &sl, m.patch_with_border_, &ok, SVO_MEM_HOST),
+              "svo_cuda_warp_affine");
+  for (int y = 0; y < 8; ++y) std::memcpy(m.patch_ + 8 * y, m.patch_with_border_ + 10 * (y + 1) + 1, 8);
+}
 static void unpack(Matcher& m, const svo_match_out& o) {
   std::copy(o.A_cur_ref, o.A_cur_ref + 4, m.A_cur_ref_.begin());
   m.epi_length_pyramid_ = o.epi_length_pyramid;
@@ -285,8 +297,10 @@ Matcher::MatchResult Matcher::findMatchDirect(const Frame& ref_frame, const Fram
                                          &ref_frame.cam_->model, &cur_frame.cam_->model, T, &zero, 1, &ft, &d, px_cur.data(), &o, &out, SVO_MEM_HOST),
               "svo_cuda_find_match_direct");
   unpack(*this, out);
+  const MatchResult r = static_cast<MatchResult>(out.result);
+  if (r != MatchResult::kFailVisibility && r != MatchResult::kFailWarp) warpedPatch(*this, ref_frame, cur_frame, T, ft, d);
   if (out.result == 0) px_cur = px_cur_;
-  return static_cast<MatchResult>(out.result);
+  return r;
 }
 Matcher::MatchResult Matcher::findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const FeatureWrapper& ref_ftr,
                                                       const double d_estimate_inv, const double d_min_inv, const double d_max_inv, double& depth) {
@@ -307,8 +321,20 @@ Matcher::MatchResult Matcher::findEpipolarMatchDirect(const Frame& ref_frame, co
                                                   &zero, &ref_frame.cam_->model, &cur_frame.cam_->model, T, &zero, 1, &ft, d3, &o, &out, SVO_MEM_HOST),
               "svo_cuda_find_epipolar_match_direct");
   unpack(*this, out);
+  epi_image_ = {out.epi_image[0], out.epi_image[1]};  // matcher.cpp:176: set before every return
+  const MatchResult r = static_cast<MatchResult>(out.result);
+  if (r != MatchResult::kFailAngle && r != MatchResult::kFailWarp) warpedPatch(*this, ref_frame, cur_frame, T, ft, 1.0 / std::max(0.000001, d_estimate_inv));
   if (out.result == 0) depth = out.depth;
-  return static_cast<MatchResult>(out.result);
+  return r;
+}
+void Matcher::scanEpipolarLine(const Frame& frame, const BearingVector& A, const BearingVector& B, const BearingVector& C,
+                               const PatchScore& patch_score, const int patch_level, Keypoint* image_best, int* zmssd_best) {
+  const svo_matcher_options o = cOptions();
+  double best[2] = {0.0, 0.0};
+  b200::check(svo_cuda_scan_epipolar_line(b200::context(), b200::ensureGpu(frame).handle(), nullptr, &frame.cam_->model, 1, A.data(), B.data(),
+                                          C.data(), patch_score.ref_patch_, &patch_level, &epi_length_pyramid_, &o, best, zmssd_best, SVO_MEM_HOST),
+              "svo_cuda_scan_epipolar_line");
+  *image_best = {best[0], best[1]};
 }
 std::string Matcher::getResultString(const MatchResult& result) {  // matcher.cpp:243-260
   switch (result) {
@@ -375,6 +401,11 @@ bool updateSeed(const Frame& cur_frame, Frame& ref_frame, const size_t& seed_ind
 bool updateFilterVogiatzis(const FloatType z, const FloatType tau2, const FloatType z_range, SeedState& seed) {
   uint8_t ok = 0;
   b200::check(svo_cuda_update_filter_vogiatzis(b200::context(), 1, &z, &tau2, &z_range, seed.data(), &ok, SVO_MEM_HOST), "svo_cuda_update_filter_vogiatzis");
+  return ok != 0;
+}
+bool updateFilterGaussian(const FloatType z, const FloatType tau2, SeedState& seed) {
+  uint8_t ok = 0;
+  b200::check(svo_cuda_update_filter_seq(b200::context(), 1, 1, &z, &tau2, nullptr, seed.data(), &ok, 1, SVO_MEM_HOST), "svo_cuda_update_filter_seq");
   return ok != 0;
 }
 double computeTau(const Transformation& T_ref_cur, const BearingVector& f, const FloatType z, const FloatType px_error_angle) {
@@ -806,7 +837,11 @@ AbstractDetector::Ptr makeDetector(const DetectorOptions& options, const CameraP
 AbstractDetector::AbstractDetector(const DetectorOptions& options, const CameraPtr& cam)
     : options_(options),
       grid_(int(options.cell_size), int(std::ceil(double(cam->imageWidth()) / options.cell_size)),
-            int(std::ceil(double(cam->imageHeight()) / options.cell_size))) {}
+            int(std::ceil(double(cam->imageHeight()) / options.cell_size))),
+      // feature_detection.cpp:34-39: cell_size / sec_grid_fineness, ceil(width / (cell_size / fineness)) x ceil(height / ...)
+      closeness_check_grid_(int(options.cell_size / std::max<size_t>(options.sec_grid_fineness, 1)),
+                            int(std::ceil(double(cam->imageWidth()) / double(options.cell_size / std::max<size_t>(options.sec_grid_fineness, 1)))),
+                            int(std::ceil(double(cam->imageHeight()) / double(options.cell_size / std::max<size_t>(options.sec_grid_fineness, 1))))) {}
 
 void FastDetector::detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec, Levels& level_vec,
                           Gradients& grad_vec, FeatureTypes& types_vec) {
@@ -1260,3 +1295,63 @@ void StereoTriangulation::compute(const FramePtr& frame0, const FramePtr& frame1
 }
 
 }  // namespace svo
+
+// ---- fast:: leaves (fast.h:20-41) -----------------------------------------------------------------------------------------------------
+namespace fast {
+namespace {
+using svo::b200::check;
+using svo::b200::context;
+struct OneLevel {  // a one-level device pyramid holding the caller's image
+  svo_cuda_pyr* pyr = nullptr;
+  OneLevel(const fast_byte* img, int w, int h, int stride) {
+    check(svo_cuda_pyr_create(context(), 1, w, h, 1, -1, &pyr), "svo_cuda_pyr_create");
+    const int rc = svo_cuda_pyr_upload(context(), pyr, 0, 1, img, size_t(stride), size_t(stride) * h, SVO_MEM_HOST);
+    if (rc == SVO_OK) svo_cuda_ctx_synchronize(context());
+    if (rc != SVO_OK) { svo_cuda_pyr_destroy(context(), pyr); pyr = nullptr; check(rc, "svo_cuda_pyr_upload"); }
+  }
+  ~OneLevel() { if (pyr) svo_cuda_pyr_destroy(context(), pyr); }
+};
+void detect(const fast_byte* img, int w, int h, int stride, short barrier, int arc, std::vector<fast_xy>& corners) {
+  if (w < 7 || h < 7) return;  // the reference's loops over [3, w-3) x [3, h-3) are empty
+  OneLevel lvl(img, w, h, stride);
+  std::vector<svo_fast_xy> xy(std::max(1024, w * h / 16));
+  int n = 0;
+  for (;;) {
+    check(svo_cuda_fast_corner_list(context(), lvl.pyr, 0, 0, barrier, arc, int(xy.size()), xy.data(), nullptr, nullptr, &n, SVO_MEM_HOST),
+          "svo_cuda_fast_corner_list");
+    if (n <= int(xy.size())) break;
+    xy.resize(size_t(n));
+  }
+  corners.reserve(corners.size() + size_t(n));
+  for (int i = 0; i < n; ++i) corners.push_back(fast_xy(xy[i].x, xy[i].y));  // appended, as the reference's push_back
+}
+}  // namespace
+void fast_corner_detect_9(const fast_byte* img, int w, int h, int stride, short barrier, std::vector<fast_xy>& corners) { detect(img, w, h, stride, barrier, 9, corners); }
+void fast_corner_detect_9_sse2(const fast_byte* img, int w, int h, int stride, short barrier, std::vector<fast_xy>& corners) { detect(img, w, h, stride, barrier, 9, corners); }
+void fast_corner_detect_10(const fast_byte* img, int w, int h, int stride, short barrier, std::vector<fast_xy>& corners) { detect(img, w, h, stride, barrier, 10, corners); }
+void fast_corner_detect_10_sse2(const fast_byte* img, int w, int h, int stride, short barrier, std::vector<fast_xy>& corners) { detect(img, w, h, stride, barrier, 10, corners); }
+
+void fast_corner_score_10(const fast_byte* img, const int img_stride, const std::vector<fast_xy>& corners, const int threshold, std::vector<int>& scores) {
+  scores.resize(corners.size());
+  if (corners.empty()) return;
+  int max_x = 0, max_y = 0;
+  for (const fast_xy& c : corners) { max_x = std::max<int>(max_x, c.x); max_y = std::max<int>(max_y, c.y); }
+  const int w = std::min(max_x + 4, img_stride), h = max_y + 4;  // every pixel fast_10_score.cpp:3158-3177 reads
+  OneLevel lvl(img, w, h, img_stride);
+  static_assert(sizeof(fast_xy) == sizeof(svo_fast_xy), "fast_xy layout");
+  check(svo_cuda_fast_corner_score(context(), lvl.pyr, 0, 0, int(corners.size()), reinterpret_cast<const svo_fast_xy*>(corners.data()), threshold, 10,
+                                   scores.data(), SVO_MEM_HOST),
+        "svo_cuda_fast_corner_score");
+}
+
+void fast_nonmax_3x3(const std::vector<fast_xy>& corners, const std::vector<int>& scores, std::vector<int>& nonmax_corners) {
+  nonmax_corners.clear();
+  if (corners.empty()) return;
+  nonmax_corners.resize(corners.size());
+  int n = 0;
+  check(svo_cuda_fast_nonmax_3x3(context(), int(corners.size()), reinterpret_cast<const svo_fast_xy*>(corners.data()), scores.data(),
+                                 nonmax_corners.data(), &n, SVO_MEM_HOST),
+        "svo_cuda_fast_nonmax_3x3");
+  nonmax_corners.resize(size_t(n));
+}
+}  // namespace fast

@@ -12,6 +12,7 @@
 #include <array>
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -180,6 +181,15 @@ class SparseImgAlignBase {
   void setWeightedPrior(const Transformation& T_cur_ref_prior, double alpha_prior, double beta_prior, double lambda_rot,
                         double lambda_trans, double lambda_alpha, double lambda_beta);
   void reset();  // MiniLeastSquaresSolver::reset (mini_least_squares_solver.hpp:240-250)
+  // sparse_img_align_base.h:85-93. The device kernel is built for the reference's own 4x4 patches (sparse_img_align.cpp:31: the only
+  // size SparseImgAlign ever sets); any other size is rejected instead of silently aligning with a different patch.
+  template <class derived>
+  void setPatchSize(size_t patch_size) {
+    if (patch_size != 4) throw std::invalid_argument("SparseImgAlign (B200): only patch_size 4 is implemented (sparse_img_align.cpp:31)");
+    patch_size_ = int(patch_size); border_size_ = 1;
+    patch_size_with_border_ = patch_size_ + 2 * border_size_;
+    patch_area_ = patch_size_ * patch_size_;
+  }
   inline void setMaxNumFeaturesToAlign(int num) { max_num_features_ = num; }
   inline void setAlphaInitialValue(double alpha_init) { alpha_init_ = alpha_init; }
   inline void setBetaInitialValue(double beta_init) { beta_init_ = beta_init; }
@@ -199,6 +209,7 @@ class SparseImgAlignBase {
   double alpha_init_ = 0.0, beta_init_ = 0.0;
   double chi2_ = 0.0;
   std::array<double, 64> H_{};
+  int patch_size_ = 4, border_size_ = 1, patch_size_with_border_ = 6, patch_area_ = 16;  // sparse_img_align_base.h:132-135
 };
 
 class SparseImgAlign : public SparseImgAlignBase {  // src/svo_img_align/include/svo/img_align/sparse_img_align.h:30-77
@@ -226,10 +237,31 @@ struct FeatureWrapper {  // src/svo_common/include/svo/common/feature_wrapper.h:
   int level;
 };
 
+namespace patch_score {
+// src/svo_direct/include/svo/direct/patch_score.h:43-109: the reference patch and its sums; the scoring itself (computeScore) runs on
+// the device inside the epipolar scan.
+template <int HALF_PATCH_SIZE>
+class ZMSSD {
+ public:
+  static const int patch_size_ = 2 * HALF_PATCH_SIZE;
+  static const int patch_area_ = patch_size_ * patch_size_;
+  static const int threshold_ = 2000 * patch_area_;
+  uint8_t* ref_patch_;
+  int sumA_, sumAA_;
+  explicit ZMSSD(uint8_t* ref_patch) : ref_patch_(ref_patch) {
+    uint32_t a = 0, aa = 0;
+    for (int r = 0; r < patch_area_; ++r) { const uint32_t n = ref_patch_[r]; a += n; aa += n * n; }
+    sumA_ = int(a); sumAA_ = int(aa);
+  }
+  static int threshold() { return threshold_; }
+};
+}  // namespace patch_score
+
 class Matcher {  // src/svo_direct/include/svo/direct/matcher.h:28-140
  public:
   static const int kHalfPatchSize = 4;
   static const int kPatchSize = 8;
+  typedef patch_score::ZMSSD<kHalfPatchSize> PatchScore;  // matcher.h:36
   struct Options {
     bool align_1d = false;
     int align_max_iter = 10;
@@ -247,7 +279,10 @@ class Matcher {  // src/svo_direct/include/svo/direct/matcher.h:28-140
   } options_;
   enum class MatchResult { kSuccess, kFailScore, kFailTriangulation, kFailVisibility, kFailWarp, kFailAlignment, kFailRange,
                            kFailAngle, kFailCloseView, kFailLock, kFailTooFar };
+  alignas(16) uint8_t patch_[kPatchSize * kPatchSize] = {};                           // matcher.h:70: the warped reference patch
+  alignas(16) uint8_t patch_with_border_[(kPatchSize + 2) * (kPatchSize + 2)] = {};   // matcher.h:71
   std::array<double, 4> A_cur_ref_{};  // row-major 2x2
+  std::array<double, 2> epi_image_{};  // matcher.h:73: vector from epipolar start to end on the image plane
   double epi_length_pyramid_ = 0;
   double h_inv_ = 0;
   int search_level_ = 0;
@@ -262,6 +297,9 @@ class Matcher {  // src/svo_direct/include/svo/direct/matcher.h:28-140
   MatchResult findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const Transformation& T_cur_ref,
                                       const FeatureWrapper& ref_ftr, const double d_estimate_inv, const double d_min_inv,
                                       const double d_max_inv, double& depth);
+  // matcher.h:111-122: the ZMSSD scan of the segment A~C~B on its own (reads options_ and epi_length_pyramid_, as the reference does)
+  void scanEpipolarLine(const Frame& frame, const BearingVector& A, const BearingVector& B, const BearingVector& C,
+                        const PatchScore& patch_score, const int patch_level, Keypoint* image_best, int* zmssd_best);
   static std::string getResultString(const MatchResult& result);
   svo_matcher_options cOptions() const;
 };
@@ -289,13 +327,17 @@ bool updateSeed(const Frame& cur_frame, Frame& ref_frame, const size_t& seed_ind
                 const FloatType sigma2_convergence_threshold, const bool check_visibility = true, const bool check_convergence = false,
                 const bool use_vogiatzis_update = true);
 bool updateFilterVogiatzis(const FloatType z, const FloatType tau2, const FloatType z_range, SeedState& seed);
+bool updateFilterGaussian(const FloatType z, const FloatType tau2, SeedState& seed);  // depth_filter.h:207-211; depth_filter.cpp:554-579
 double computeTau(const Transformation& T_ref_cur, const BearingVector& f, const FloatType z, const FloatType px_error_angle);
 }  // namespace depth_filter_utils
 
 class DepthFilter {
  public:
   DepthFilterOptions options_;
-  std::shared_ptr<AbstractDetector> feature_detector_;  // depth_filter.h:95 (set by the detector-building constructor)
+  // depth_filter.h:162-165 ("need public access to set grid occupancy"): callers lock feature_detector_mut_ around grid updates
+  std::mutex feature_detector_mut_;
+  std::shared_ptr<AbstractDetector> feature_detector_;      // set by the detector-building constructor
+  std::shared_ptr<AbstractDetector> sec_feature_detector_;  // extra Shi-Tomasi points for loop closing (extra_map_points): never built here
   explicit DepthFilter(const DepthFilterOptions& options);
   // depth_filter.h:80-84: the constructor that builds its own detector through makeDetector
   DepthFilter(const DepthFilterOptions& options, const DetectorOptions& detector_options, const CameraPtr& cam);
@@ -331,6 +373,7 @@ struct DetectorOptions {  // feature_detection_types.h:49-84
   DetectorType detector_type = DetectorType::kFast;
   double threshold_primary = 10.0;
   double threshold_secondary = 100.0;
+  size_t sec_grid_fineness = 1;  // feature_detection_types.h:79-80
 };
 
 class OccupandyGrid2D {  // src/svo_common/include/svo/common/occupancy_grid_2d.h:10-110
@@ -342,6 +385,7 @@ class OccupandyGrid2D {  // src/svo_common/include/svo/common/occupancy_grid_2d.
   void reset() { std::fill(occupancy_.begin(), occupancy_.end(), 0); }
   size_t size() const { return occupancy_.size(); }
   size_t getCellIndex(int x, int y, int scale = 1) const { return size_t((scale * y) / cell_size) * n_cols + size_t((scale * x) / cell_size); }
+  void fillWithKeypoints(const Keypoint& px) { occupancy_.at(getCellIndex(int(px[0]), int(px[1]), 1)) = 1; }  // occupancy_grid_2d.h:40-48 (one column)
 };
 
 using Keypoints = std::vector<Keypoint>;
@@ -368,6 +412,9 @@ class AbstractDetector {  // src/svo_direct/include/svo/direct/feature_detection
   using Ptr = std::shared_ptr<AbstractDetector>;
   DetectorOptions options_;
   OccupandyGrid2D grid_;
+  // feature_detection.h:59-61: the finer grid a secondary detector checks new features against (filled by the caller through
+  // fillWithKeypoints; only the Shi-Tomasi detector, which is not on this path, reads it)
+  OccupandyGrid2D closeness_check_grid_;
   AbstractDetector(const DetectorOptions& options, const CameraPtr& cam);
   virtual ~AbstractDetector() = default;
   // AbstractDetector::detect(const FramePtr&) (feature_detection.cpp:40-50): appends the features to the frame's SoA arrays and
@@ -376,7 +423,7 @@ class AbstractDetector {  // src/svo_direct/include/svo/direct/feature_detection
   // The virtual detect of the reference (feature_detection.h:41-49) with the frame's device pyramid in place of (img_pyr, mask).
   virtual void detect(const b200::GpuPyramid& gpu, const size_t max_n_features, Keypoints& px_vec, Scores& score_vec, Levels& level_vec,
                       Gradients& grad_vec, FeatureTypes& types_vec) = 0;
-  void resetGrid() { grid_.reset(); }
+  void resetGrid() { grid_.reset(); closeness_check_grid_.reset(); }  // feature_detection.h:51-55
 };
 
 class FastDetector : public AbstractDetector {  // feature_detection.h:66-81; feature_detection.cpp:53-74
@@ -610,3 +657,22 @@ const GpuPyramid& ensureGpu(const Frame& frame);
 }  // namespace b200
 
 }  // namespace svo
+
+// ---- (a2-a4) the fast:: leaves with their list-shaped results (src/fast_neon/include/fast/fast.h:11-41) ---------------------------------
+// Same signatures as the reference; each call uploads the image it is given, runs the level kernel and compacts the corners in raster
+// order on the device (svo_cuda_fast_corner_list / _corner_score / _nonmax_3x3). The detectors above do not go through these: they keep
+// everything on the device and only read back one corner per grid cell.
+namespace fast {
+struct fast_xy {
+  short x, y;
+  fast_xy(short x_, short y_) : x(x_), y(y_) {}
+};
+typedef unsigned char fast_byte;
+void fast_corner_detect_9(const fast_byte* img, int imgWidth, int imgHeight, int widthStep, short barrier, std::vector<fast_xy>& corners);
+void fast_corner_detect_9_sse2(const fast_byte* img, int imgWidth, int imgHeight, int widthStep, short barrier, std::vector<fast_xy>& corners);
+void fast_corner_detect_10(const fast_byte* img, int imgWidth, int imgHeight, int widthStep, short barrier, std::vector<fast_xy>& corners);
+void fast_corner_detect_10_sse2(const fast_byte* img, int imgWidth, int imgHeight, int widthStep, short barrier, std::vector<fast_xy>& corners);
+// NOTE: the reference takes no image size here; the pixels it reads lie within 3 of the listed corners, and so does the upload.
+void fast_corner_score_10(const fast_byte* img, const int img_stride, const std::vector<fast_xy>& corners, const int threshold, std::vector<int>& scores);
+void fast_nonmax_3x3(const std::vector<fast_xy>& corners, const std::vector<int>& scores, std::vector<int>& nonmax_corners);
+}  // namespace fast

@@ -2,7 +2,10 @@
 // tests/test_gpu_host_facade.py, runs the reference-shaped calls (createImgPyramid, FastDetector::detect,
 // SparseImgAlign::run, Matcher::findMatchDirect / findEpipolarMatchDirect, DepthFilter::updateSeeds) and writes the results
 // back as raw doubles. The Python test compares them with the oracle.
+#include <algorithm>
 #include <cstdio>
+#include <mutex>
+#include <stdexcept>
 #include <cstdlib>
 #include <fstream>
 #include <cstring>
@@ -200,6 +203,82 @@ int main(int argc, char** argv) {
         for (int k = 0; k < 4; ++k) mismatches += rb[4 * i + k] != s7[3 + k];
       }
       out.push_back(double(mismatches));
+    }
+    // (f) the rest of the reference's public surface on this path
+    {
+      // fast:: leaves with list-shaped results (fast.h:20-41) on level 0 of the reference frame
+      const Image& l0 = ref->img_pyr_[0];
+      std::vector<fast::fast_xy> corners, corners9;
+      fast::fast_corner_detect_10_sse2(l0.data, l0.cols, l0.rows, int(l0.step), 10, corners);
+      fast::fast_corner_detect_9(l0.data, l0.cols, l0.rows, int(l0.step), 10, corners9);
+      std::vector<int> scores, nm;
+      fast::fast_corner_score_10(l0.data, int(l0.step), corners, 10, scores);
+      fast::fast_nonmax_3x3(corners, scores, nm);
+      out.push_back(double(corners.size()));
+      for (size_t i = 0; i < corners.size(); ++i) { out.push_back(corners[i].x); out.push_back(corners[i].y); out.push_back(scores[i]); }
+      out.push_back(double(nm.size()));
+      for (int i : nm) out.push_back(i);
+      out.push_back(double(corners9.size()));
+      const size_t before = corners.size();
+      fast::fast_corner_detect_10(l0.data, l0.cols, l0.rows, int(l0.step), 10, corners);  // appends, as the reference's push_back
+      out.push_back(double(corners.size() == 2 * before));
+      // Matcher::epi_image_ / patch_ / patch_with_border_ and scanEpipolarLine on its own
+      Matcher m;
+      const int n_chk = std::min(N, 40);
+      out.push_back(double(n_chk));
+      for (int i = 0; i < n_chk; ++i) {
+        FeatureWrapper fw{FeatureType(type[i]), ref->px_vec_[i], ref->f_vec_[i], ref->grad_vec_[i], level[i]};
+        double d = 0;
+        const auto r2 = m.findEpipolarMatchDirect(*ref, *cur, fw, 1.0 / depth[i], 1.3 / depth[i], 0.7 / depth[i], d);
+        out.push_back(double(int(r2)));
+        out.push_back(m.epi_image_[0]); out.push_back(m.epi_image_[1]);
+        out.push_back(double(m.search_level_)); out.push_back(m.epi_length_pyramid_);
+        for (int k = 0; k < 100; ++k) out.push_back(m.patch_with_border_[k]);
+        for (int k = 0; k < 64; ++k) out.push_back(m.patch_[k]);
+        // the scan alone, on the segment the driver's caller also forms (A, B, C follow the patch in the output)
+        const Transformation T_cr = cur->T_f_w_ * ref->T_f_w_.inverse();
+        BearingVector Rf;
+        {  // q * f * q^-1
+          const double w = T_cr.q[0], x = T_cr.q[1], y = T_cr.q[2], z = T_cr.q[3];
+          const double ux = 2 * (y * fw.f[2] - z * fw.f[1]), uy = 2 * (z * fw.f[0] - x * fw.f[2]), uz = 2 * (x * fw.f[1] - y * fw.f[0]);
+          Rf = {fw.f[0] + w * ux + (y * uz - z * uy), fw.f[1] + w * uy + (z * ux - x * uz), fw.f[2] + w * uz + (x * uy - y * ux)};
+        }
+        BearingVector A, B, C;
+        for (int k = 0; k < 3; ++k) {
+          A[k] = Rf[k] + T_cr.t[k] * (1.3 / depth[i]); B[k] = Rf[k] + T_cr.t[k] * (0.7 / depth[i]); C[k] = Rf[k] + T_cr.t[k] * (1.0 / depth[i]);
+        }
+        Matcher::PatchScore ps(m.patch_);
+        Keypoint best{0, 0};
+        int z = Matcher::PatchScore::threshold();
+        m.scanEpipolarLine(*cur, A, B, C, ps, m.search_level_, &best, &z);
+        for (int k = 0; k < 3; ++k) { out.push_back(A[k]); out.push_back(B[k]); out.push_back(C[k]); }
+        out.push_back(best[0]); out.push_back(best[1]); out.push_back(double(z));
+      }
+      // depth_filter_utils::updateFilterGaussian
+      SeedState st{0.31, 0.004, 10.0, 10.0};
+      const bool okg = depth_filter_utils::updateFilterGaussian(0.33, 0.0007, st);
+      out.push_back(double(okg));
+      for (double v : st) out.push_back(v);
+      // SparseImgAlignBase::setPatchSize: 4 is the reference's (and the kernel's) size, anything else is refused
+      SparseImgAlign align(SparseImgAlign::getDefaultSolverOptions(), SparseImgAlignOptions());
+      align.setPatchSize<SparseImgAlign>(4);
+      bool refused = false;
+      try { align.setPatchSize<SparseImgAlign>(8); } catch (const std::invalid_argument&) { refused = true; }
+      out.push_back(double(refused));
+      // AbstractDetector::closeness_check_grid_ and the DepthFilter's public detector members
+      DetectorOptions dopt;
+      dopt.sec_grid_fineness = 2;
+      FastDetector fd(dopt, cam);
+      out.push_back(double(fd.grid_.size())); out.push_back(double(fd.closeness_check_grid_.size()));
+      fd.closeness_check_grid_.fillWithKeypoints(Keypoint{100.0, 50.0});
+      out.push_back(double(std::count(fd.closeness_check_grid_.occupancy_.begin(), fd.closeness_check_grid_.occupancy_.end(), uint8_t(1))));
+      fd.resetGrid();
+      out.push_back(double(std::count(fd.closeness_check_grid_.occupancy_.begin(), fd.closeness_check_grid_.occupancy_.end(), uint8_t(1))));
+      DepthFilter df(DepthFilterOptions(), DetectorOptions(), cam);
+      {
+        std::lock_guard<std::mutex> lock(df.feature_detector_mut_);
+        out.push_back(double(df.feature_detector_ != nullptr)); out.push_back(double(df.sec_feature_detector_ == nullptr));
+      }
     }
     std::ofstream o(argv[2], std::ios::binary);
     o.write(reinterpret_cast<const char*>(out.data()), sizeof(double) * out.size());

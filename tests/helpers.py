@@ -141,6 +141,21 @@ def _align_arrays(r):
                                                     r.n_tracked]]), np.array(r.H), np.array([list(t) for t in r.T_f_w])
 
 
+def scan_cases(orc, ms, rf, cf, oft, d3):
+    """Inputs of stand-alone Matcher::scanEpipolarLine calls: the segment end points A, B and the estimate C of every feature of the
+    match set whose epipolar segment is long enough to be scanned (matcher.cpp:170-176, 222-224), with the search level, the warped
+    8x8 patch and epi_length_pyramid_ the restatement's findEpipolarMatchDirect leaves (always the restatement, so that the inputs do
+    not depend on the implementation under test)."""
+    r = orc.find_epipolar_match_direct_batch(rf, cf, ms["T_cur_ref"], oft, d3, orc.default_matcher_options(), n_threads=8)
+    R, t = synth.se3_to_Rt(np.asarray(ms["T_cur_ref"], np.float64))
+    Rf = ms["f"] @ R.T
+    A, B, Cc = Rf + t[None] * d3[:, 1:2], Rf + t[None] * d3[:, 2:3], Rf + t[None] * d3[:, 0:1]
+    sel = np.flatnonzero((r["epi_length_pyramid"] >= 2.0) & (r["result"] != 4) & (r["result"] != 7))
+    pwb = r["patch_with_border"][sel].reshape(-1, 10, 10)
+    return {"A": A[sel], "B": B[sel], "C": Cc[sel], "patch": np.ascontiguousarray(pwb[:, 1:9, 1:9]).reshape(-1, 64),
+            "level": r["search_level"][sel].astype(np.int32), "epi_length": r["epi_length_pyramid"][sel], "sel": sel}
+
+
 def frontend_outputs(orc, which):
     align = orc.sparse_align if which == "orc" else orc.ref_sparse_align
     fmd = (lambda *a: orc.find_match_direct_batch(*a, n_threads=8)) if which == "orc" else orc.ref_find_match_direct_batch
@@ -191,8 +206,17 @@ def frontend_outputs(orc, which):
     d3 = np.stack([d_inv * np.random.default_rng(1).uniform(0.9, 1.1, len(d_inv)), d_inv * 1.5, d_inv * 0.6], 1)
     for name, kw in (("sphere", dict()), ("plane", dict(scan_on_unit_sphere=0)), ("a1d", dict(align_1d=1)), ("nosub", dict(subpix_refinement=0))):
         r = epi(rf, cf, ms["T_cur_ref"], oft, d3, orc.default_matcher_options(**kw))
-        for k in fields:
+        for k in fields + ("epi_image", "reject"):
             out[f"epi_{name}_{k}"] = r[k]
+    # c7: Matcher::scanEpipolarLine on its own (both scan variants, a capped scan, a caller-supplied starting score)
+    sc = scan_cases(orc, ms, rf, cf, oft, d3)
+    for name, kw, z0 in (("sphere", dict(), 2000 * 64), ("plane", dict(scan_on_unit_sphere=0), 2000 * 64),
+                         ("capped", dict(max_epi_search_steps=4), 2000 * 64), ("low_start", dict(), 9000)):
+        o = orc.default_matcher_options(**kw)
+        res = [orc.scan_epipolar_line(cf, sc["A"][i], sc["B"][i], sc["C"][i], sc["patch"][i], sc["level"][i], sc["epi_length"][i], o, z0,
+                                      which=("orc" if which == "orc" else "ref")) for i in range(len(sc["A"]))]
+        out[f"scan_{name}_px"] = np.array([r[0] for r in res])
+        out[f"scan_{name}_zmssd"] = np.array([r[1] for r in res], np.int32)
     # d: updateSeed chain over ordered observations
     sq = synth.make_seed_sequence(17, n_seeds=160, n_obs=6)
     rf = orc.make_frame(orc.create_img_pyramid(sq["ref_img"], 5), sq["cam"], keep=keep)

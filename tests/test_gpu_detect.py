@@ -71,6 +71,65 @@ def test_fast_stages_match_reference_golden(ctx, orc):
             assert np.array_equal(np.argwhere(sm9 > 0)[:, ::-1].astype(np.int16), g[f"xy9_{seed}_{l}"])
 
 
+def test_fast_corner_lists_match_reference_golden(ctx, orc):
+    """The list-shaped leaves of fast.h:32-41 (svo_cuda_fast_corner_list / _corner_score / _nonmax_3x3) against the vectors generated
+    from the reference's own fast_corner_detect_10[_sse2] / fast_corner_detect_9 / fast_corner_score_10 / fast_nonmax_3x3."""
+    g = np.load(os.path.join(GOLD, "fast_ref_golden.npz"))
+    for seed, w, h, thr in g["cases"]:
+        seed, w, h, thr = int(seed), int(w), int(h), int(thr)
+        img0 = synth.make_image(seed, w, h, n_rect=max(8, w * h // 400))
+        n_levels = 3 if min(w, h) >= 28 else 1
+        p = _gpu_pyr(ctx, img0, n_levels)
+        for l in range(n_levels):
+            gxy, gsc, gnm = g[f"xy_{seed}_{l}"], g[f"score_{seed}_{l}"].astype(np.int32), g[f"nonmax_{seed}_{l}"]
+            xy, sc, nm = capi.fast_corner_list(ctx, p, 0, l, thr, 10)
+            assert np.array_equal(np.stack([xy["x"], xy["y"]], 1), gxy) and np.array_equal(sc, gsc)
+            assert np.array_equal(np.flatnonzero(nm), gnm)
+            xy9, _, _ = capi.fast_corner_list(ctx, p, 0, l, thr, 9)
+            assert np.array_equal(np.stack([xy9["x"], xy9["y"]], 1), g[f"xy9_{seed}_{l}"])
+            # the stand-alone leaves on the reference's own lists
+            lst = np.zeros(len(gxy), capi.FAST_XY_DTYPE)
+            lst["x"], lst["y"] = gxy[:, 0], gxy[:, 1]
+            assert np.array_equal(capi.fast_corner_score(ctx, p, 0, l, lst, thr, 10), gsc)
+            assert np.array_equal(capi.fast_nonmax_3x3(ctx, lst, gsc), gnm)
+            if len(gxy) > 4:  # a truncated list reports the full count
+                n_cap = len(gxy) // 2
+                xy_t, sc_t, _ = capi.fast_corner_list(ctx, p, 0, l, thr, 10, max_corners=n_cap)
+                assert len(xy_t) == n_cap and np.array_equal(sc_t, gsc[:n_cap])
+
+
+def test_fast_corner_list_leaves_random(ctx, orc):
+    """Random images and lists: scores of pixels that are NOT corners (fast_corner_score_10 returns the threshold), non-max on
+    arbitrary score lists (ties, neighbours on the row ends), empty lists."""
+    rng = np.random.default_rng(23)
+    for trial in range(4):
+        w, h = int(rng.integers(40, 400)), int(rng.integers(20, 260))
+        img = np.kron(rng.integers(0, 256, (h // 2 + 1, w // 2 + 1)), np.ones((2, 2)))[:h, :w].astype(np.uint8)
+        p = _gpu_pyr(ctx, img, 1)
+        for thr in (5, 40, 200):
+            xy, sc, nm = capi.fast_corner_list(ctx, p, 0, 0, thr, 10)
+            oxy = orc.fast_detect(img, thr, 10)
+            osc = orc.fast_score10(img, oxy, thr)
+            assert np.array_equal(np.stack([xy["x"], xy["y"]], 1), oxy) and np.array_equal(sc, osc)
+            assert np.array_equal(np.flatnonzero(nm), orc.fast_nonmax3x3(oxy, osc))
+            # arbitrary pixels, most of them no corners
+            m = 300
+            pts = np.unique(np.stack([rng.integers(3, w - 3, m), rng.integers(3, h - 3, m)], 1), axis=0)
+            pts = pts[np.lexsort((pts[:, 0], pts[:, 1]))].astype(np.int16)   # raster order
+            lst = np.zeros(len(pts), capi.FAST_XY_DTYPE); lst["x"], lst["y"] = pts[:, 0], pts[:, 1]
+            assert np.array_equal(capi.fast_corner_score(ctx, p, 0, 0, lst, thr, 10), orc.fast_score10(img, pts, thr))
+            # non-max with random scores (many ties) on a dense block of listed pixels
+            yy, xx = np.mgrid[3:3 + min(12, h - 6), 3:3 + min(40, w - 6)]
+            keep = rng.uniform(size=yy.size) < 0.7
+            blk = np.stack([xx.ravel()[keep], yy.ravel()[keep]], 1).astype(np.int16)
+            bsc = rng.integers(1, 6, len(blk)).astype(np.int32)
+            lst = np.zeros(len(blk), capi.FAST_XY_DTYPE); lst["x"], lst["y"] = blk[:, 0], blk[:, 1]
+            assert np.array_equal(capi.fast_nonmax_3x3(ctx, lst, bsc), orc.fast_nonmax3x3(blk, bsc))
+    assert len(capi.fast_nonmax_3x3(ctx, np.zeros(0, capi.FAST_XY_DTYPE), np.zeros(0, np.int32))) == 0
+    flat = _gpu_pyr(ctx, np.full((64, 64), 90, np.uint8), 1)
+    assert len(capi.fast_corner_list(ctx, flat, 0, 0, 10, 10)[0]) == 0
+
+
 def test_fast_stages_match_oracle_random(ctx, orc):
     rng = np.random.default_rng(11)
     for trial in range(6):

@@ -132,6 +132,49 @@ def test_cpp_facades_match_oracle(orc, tmp_path):
     # (e) two host threads (own contexts / streams) racing into the lazy device upload of shared frames: same results as (c)
     assert out[p] == 0.0, f"{int(out[p])} results differ between the two-thread and the sequential run"
     p += 1
+    # (f) fast:: leaves with list-shaped results == the oracle's (== the reference's own, tests/test_oracle_cpu.py)
+    nc = int(out[p]); p += 1
+    lst = out[p:p + 3 * nc].reshape(nc, 3); p += 3 * nc
+    n_nm = int(out[p]); p += 1
+    nm = out[p:p + n_nm].astype(int); p += n_nm
+    n9 = int(out[p]); p += 1
+    appended = out[p]; p += 1
+    oxy = orc.fast_detect(d["ref_img"], 10, 10)
+    osc = orc.fast_score10(d["ref_img"], oxy, 10)
+    assert nc == len(oxy) > 1000 and np.array_equal(lst[:, :2].astype(np.int16), oxy) and np.array_equal(lst[:, 2].astype(np.int32), osc)
+    assert np.array_equal(nm, orc.fast_nonmax3x3(oxy, osc))
+    assert n9 == len(orc.fast_detect(d["ref_img"], 10, 9)) > nc and appended == 1.0
+    # Matcher members (patch_, patch_with_border_, epi_image_) and scanEpipolarLine on its own
+    n_chk = int(out[p]); p += 1
+    rec = out[p:p + n_chk * 181].reshape(n_chk, 181); p += n_chk * 181
+    inv = 1.0 / d["depth"][:n_chk]
+    oft_c = orc.make_features(d["px"][:n_chk], d["f"][:n_chk], grad[:n_chk], ftype[:n_chk], level[:n_chk])
+    e = orc.find_epipolar_match_direct_batch(rf, cf, d["T_cur_ref_gt"], oft_c, np.stack([inv, 1.3 * inv, 0.7 * inv], 1), orc.default_matcher_options())
+    assert np.array_equal(rec[:, 0].astype(int), e["result"])
+    np.testing.assert_allclose(rec[:, 1:3], e["epi_image"], rtol=1e-9, atol=1e-9)
+    warped = (e["result"] != 4) & (e["result"] != 7)   # kFailWarp / kFailAngle return before the patch exists
+    assert warped.sum() > n_chk // 2
+    assert np.array_equal(rec[warped, 5:105].astype(np.uint8), e["patch_with_border"][warped])
+    assert np.array_equal(rec[warped, 105:169].astype(np.uint8).reshape(-1, 8, 8), e["patch_with_border"][warped].reshape(-1, 10, 10)[:, 1:9, 1:9])
+    n_scanned = 0
+    for i in np.flatnonzero(warped):
+        A, B, Cc = rec[i, 169:178:3], rec[i, 170:178:3], rec[i, 171:178:3]
+        if rec[i, 4] < 1e-9:
+            continue  # a zero-length segment has no scan steps
+        best, z = orc.scan_epipolar_line(cf, A, B, Cc, rec[i, 105:169].astype(np.uint8), int(rec[i, 3]), rec[i, 4], orc.default_matcher_options())
+        assert z == int(rec[i, 180]) and np.abs(best - rec[i, 178:180]).max() < 1e-9, i
+        n_scanned += 1
+    assert n_scanned > n_chk // 2
+    okg = out[p]; stg = out[p + 1:p + 5]; p += 5
+    sto = np.array([0.31, 0.004, 10.0, 10.0])
+    assert okg == orc.lib().orc_update_filter_gaussian(0.33, 0.0007, orc._f64(sto))
+    np.testing.assert_allclose(stg, sto, rtol=1e-12)
+    assert out[p] == 1.0, "setPatchSize(8) must be refused"
+    p += 1
+    assert list(out[p:p + 4]) == [26.0 * 16.0, 51.0 * 32.0, 1.0, 0.0]   # grid 30 px cells, closeness grid 15 px cells; fill; resetGrid
+    p += 4
+    assert list(out[p:p + 2]) == [1.0, 1.0]
+    p += 2
     assert p == len(out)
     types = np.where(ftype == synth.K_EDGELET, synth.K_EDGELET_SEED, synth.K_CORNER_SEED).astype(np.uint8)
     st = np.tile(np.array([0.25, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (N, 1))

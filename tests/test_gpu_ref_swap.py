@@ -69,6 +69,12 @@ def test_reference_headers_plus_swap_tu_reproduce_the_frontend_goldens(swap):
         if name.startswith("epi"):
             np.testing.assert_allclose(mine[f"{name}_depth"][ok], gold[f"{name}_depth"][ok], rtol=1e-4)
             assert np.array_equal(mine[f"{name}_epi_length_pyramid"][ok], gold[f"{name}_epi_length_pyramid"][ok])
+            assert np.array_equal(mine[f"{name}_reject"], gold[f"{name}_reject"])
+            np.testing.assert_allclose(mine[f"{name}_epi_image"], gold[f"{name}_epi_image"], rtol=1e-12, atol=1e-12)  # Matcher::epi_image_
+    # ---- svo::Matcher::scanEpipolarLine called on its own (svo_cuda_scan_epipolar_line behind the reference's signature)
+    for name in ("sphere", "plane", "capped", "low_start"):
+        assert np.array_equal(mine[f"scan_{name}_zmssd"], gold[f"scan_{name}_zmssd"]), name
+        assert np.abs(mine[f"scan_{name}_px"] - gold[f"scan_{name}_px"]).max() < 1e-9, name
     # ---- depth_filter_utils::updateSeed chains
     for name in ("vog", "gauss", "conv"):
         assert int(mine[f"seeds_{name}_n"]) == int(gold[f"seeds_{name}_n"]) > 300

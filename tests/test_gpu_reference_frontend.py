@@ -77,6 +77,29 @@ def test_matcher_equals_reference(ctx, gold):
         assert np.abs(got["px_cur"][ok] - gold[f"epi_{name}_px_cur"][ok]).max() < PX_TOL
         np.testing.assert_allclose(got["depth"][ok], gold[f"epi_{name}_depth"][ok], rtol=1e-4)
         np.testing.assert_allclose(got["epi_length_pyramid"][ok], gold[f"epi_{name}_epi_length_pyramid"][ok], rtol=1e-9)
+        assert np.array_equal(got["reject"], gold[f"epi_{name}_reject"])
+        np.testing.assert_allclose(got["epi_image"], gold[f"epi_{name}_epi_image"], rtol=1e-12, atol=1e-12)  # Matcher::epi_image_
+
+
+def test_scan_epipolar_line_equals_reference(ctx, orc, gold):
+    """Matcher::scanEpipolarLine on its own (svo_cuda_scan_epipolar_line, all scans in one launch) against the reference's own
+    compiled scan on the same segments / patches: best score bit-equal, best pixel to rounding."""
+    ms = _match_set()
+    cur = capi.Pyramid(ctx, 1, 752, 480, 5)
+    cur.upload(ms["cur_img"]); cur.build()
+    cam = capi.Camera.from_dict(ms["cam"])
+    keep = []
+    rf = orc.make_frame(orc.create_img_pyramid(ms["ref_img"], 5), ms["cam"], keep=keep)
+    cf = orc.make_frame(orc.create_img_pyramid(ms["cur_img"], 5), ms["cam"], keep=keep)
+    d_inv = 1.0 / ms["depth"]
+    d3 = np.stack([d_inv * np.random.default_rng(1).uniform(0.9, 1.1, len(d_inv)), d_inv * 1.5, d_inv * 0.6], 1)
+    sc = helpers.scan_cases(orc, ms, rf, cf, orc.make_features(ms["px"], ms["f"], ms["grad"], ms["type"], ms["level"]), d3)
+    for name, kw, z0 in (("sphere", dict(), None), ("plane", dict(scan_on_unit_sphere=0), None), ("capped", dict(max_epi_search_steps=4), None),
+                         ("low_start", dict(), np.full(len(sc["A"]), 9000, np.int32))):
+        px, z = capi.scan_epipolar_line(ctx, cur, cam, sc["A"], sc["B"], sc["C"], sc["patch"], sc["level"], sc["epi_length"],
+                                        capi.matcher_options(**kw), zmssd_best=z0)
+        assert np.array_equal(z, gold[f"scan_{name}_zmssd"]), name
+        assert np.abs(px - gold[f"scan_{name}_px"]).max() < 1e-9, name
 
 
 def test_update_seeds_equals_reference(ctx, gold):

@@ -60,6 +60,14 @@ def test_matcher_equals_reference(mine, gold):
         if name.startswith("epi"):
             np.testing.assert_allclose(mine[f"{name}_depth"][ok], gold[f"{name}_depth"][ok], rtol=1e-4)
             assert np.array_equal(mine[f"{name}_epi_length_pyramid"][ok], gold[f"{name}_epi_length_pyramid"][ok])
+            assert np.array_equal(mine[f"{name}_reject"], gold[f"{name}_reject"])
+            assert np.array_equal(mine[f"{name}_epi_image"], gold[f"{name}_epi_image"]), "Matcher::epi_image_ (set before every return)"
+    # Matcher::scanEpipolarLine on its own: best ZMSSD bit-equal, best pixel up to the rounding of the rotated bearing
+    for name in ("sphere", "plane", "capped", "low_start"):
+        assert np.array_equal(mine[f"scan_{name}_zmssd"], gold[f"scan_{name}_zmssd"]), name
+        assert np.abs(mine[f"scan_{name}_px"] - gold[f"scan_{name}_px"]).max() < 1e-9, name
+    assert (gold["scan_sphere_zmssd"] < 2000 * 64).sum() > 100 and (gold["scan_capped_zmssd"] != gold["scan_sphere_zmssd"]).any()
+    assert ((gold["scan_low_start_zmssd"] == 9000) & (gold["scan_sphere_zmssd"] > 9000)).any(), "a scan that never beats the caller's start"
     # wherever the sub-pixel position is bit-identical (everything except a few align2D refinements, whose 4x4 inverse is
     # Eigen arithmetic restated on both sides) the triangulated depth is bit-identical too
     for name in ("epi_sphere", "epi_plane", "epi_a1d", "epi_nosub"):
