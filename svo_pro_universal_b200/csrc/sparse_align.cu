@@ -32,8 +32,18 @@ using namespace svo_align;
 
 namespace {
 
-constexpr int kThreads = 192;
+// Threads per CTA (= per pair): a thread owns feature slots tid, tid + kThreads, ... Measured on the B200 (4096 pairs, FP32 patch cache):
+// 192 threads / 4 pairs per SM 0.821 ms, 128 threads / 6 pairs 0.928 ms, 96 threads / 7 pairs 0.854 ms: the register file holds about 24
+// warps of this kernel whatever the CTA size, so smaller CTAs only lengthen a pair's own path. A/B builds: -DSVO_ALIGN_THREADS=.
+#ifndef SVO_ALIGN_THREADS
+#define SVO_ALIGN_THREADS 192
+#endif
+constexpr int kThreads = SVO_ALIGN_THREADS;
 constexpr int kWarps = kThreads / 32;
+static_assert(kThreads % 32 == 0 && kWarps >= 1 && kWarps <= 8, "kThreads");
+// resident CTAs per SM the register allocation is held to: (common case, variants with more per-thread state)
+constexpr int kMinBlocks = kThreads <= 96 ? 7 : (kThreads <= 128 ? 6 : 4);
+constexpr int kMinBlocksHeavy = kThreads <= 96 ? 6 : (kThreads <= 128 ? 4 : 3);
 // The warp that runs the serial part of an iteration. (Warps are dealt to the four SM sub-partitions round robin, so sub-partitions
 // 2 and 3 hold one warp of every resident CTA instead of two; moving the serial work there was measured on the B200: 0.888 ms
 // instead of 0.869 ms per 4096 pairs, so it stays on warp 0.)
@@ -74,7 +84,7 @@ struct Ctl {
 // ILL: 0 = no illumination parameters and alpha = beta = 0 (the subtraction of the reference pixel rides in the
 // interpolation's FMA chain), 1 = no illumination parameters but non-zero initial alpha/beta, 2 = gain and/or offset estimated.
 template <int ILL, bool ROBUST, bool DJ, int SLOTS>
-__global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) ? 3 : 4) : 1) sparse_align_kernel(const AlignParams P) {
+__global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) ? kMinBlocksHeavy : kMinBlocks) : 1) sparse_align_kernel(const AlignParams P) {
   constexpr bool ILLUM = ILL == 2;
   constexpr bool unit_gain = ILL == 0;
   constexpr int D = ILLUM ? 8 : 6;
@@ -87,15 +97,15 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
   const int iCM = NH, iG6 = NH + 6 * n_cams, iChi = iG6 + (ILLUM ? 2 : 0), iN = iChi + 1, iCh = iChi + 2, NV = iChi + 3;
   double* s_xyz = smem;                          // [3][stride]
   double* s_aux = s_xyz + 3 * stride;            // [NAUX][stride]  1/z, or the 2x3 projection Jacobian
-  double* s_patch = s_aux + NAUX * stride;       // [32][stride]
-  double* s_red = s_patch + 32 * stride;         // [kWarps][NV]
+  double* s_red = s_aux + NAUX * stride;         // [kWarps][NV]
   double* s_tot = s_red + kWarps * NV;           // [NV]
   double* s_camblk = s_tot + NV;                 // [n_cams][kCamBlk]
   const int NG = 6 * n_cams + (ILLUM ? 2 : 0);   // gradient-related totals: per-camera (c, xyz x c), then g6 g7
   double* s_Hinv = s_camblk + kCamBlk * n_cams;  // [D][D]   H^-1 (rebuilt with H)
   double* s_P = s_Hinv + D * D;                  // [D][NG]  H^-1 M: dx = P * totals
   Ctl& ctl = *reinterpret_cast<Ctl*>(s_P + D * NG + (NG & 1));
-  int* s_src = reinterpret_cast<int*>(&ctl + 1);                // [stride] feature index inside its camera's array
+  PatchT* s_patch = reinterpret_cast<PatchT*>(&ctl + 1);       // [32][stride] reference patch cache of the current level
+  int* s_src = reinterpret_cast<int*>(s_patch + 32 * stride);   // [stride] feature index inside its camera's array
   uint8_t* s_cam = reinterpret_cast<uint8_t*>(s_src + stride);  // [stride]
 
   const int pair = blockIdx.x;
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
           for (int x = 0; x < 6; ++x) {
             const bool used = (y >= 1 && y <= 4) || (x >= 1 && x <= 4);
             if (!used) continue;
-            s_patch[patchIdx(x, y) * stride + s] = wtl * tp[x] + wtr * tp[x + 1] + wbl * tn[x] + wbr * tn[x + 1];
+            s_patch[patchIdx(x, y) * stride + s] = (PatchT)(wtl * tp[x] + wtr * tp[x + 1] + wbl * tn[x] + wbr * tn[x + 1]);
           }
 #pragma unroll
           for (int x = 0; x < 7; ++x) tp[x] = tn[x];
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
                 const double su = u_tl - ui, sv = v_tl - vi;
                 const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
                 const double gain = 1.0 + alpha_f;
-                const double* patch = s_patch + s;
+                const PatchT* patch = s_patch + s;
                 // 5x5 taps, each converted once; the 32 stored patch values are read exactly once (rolling rows)
                 double tp[5], tn[5];
                 {
@@ -301,9 +311,9 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
                 }
                 double up[4], mid[6], low[6];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) up[x] = patch[patchIdx(x + 1, 0) * stride];
+                for (int x = 0; x < 4; ++x) up[x] = patchLoad(patch + patchIdx(x + 1, 0) * stride);
 #pragma unroll
-                for (int x = 0; x < 6; ++x) mid[x] = patch[patchIdx(x, 1) * stride];
+                for (int x = 0; x < 6; ++x) mid[x] = patchLoad(patch + patchIdx(x, 1) * stride);
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
                   unsigned na, nb;
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
 #pragma unroll
                   for (int x = 0; x < 5; ++x) tn[x] = u8ToDouble(x < 4 ? byteAt(na, x) : byteAt(nb, 0));
 #pragma unroll
-                  for (int x = (y < 3 ? 0 : 1); x < (y < 3 ? 6 : 5); ++x) low[x] = patch[patchIdx(x, y + 2) * stride];
+                  for (int x = (y < 3 ? 0 : 1); x < (y < 3 ? 6 : 5); ++x) low[x] = patchLoad(patch + patchIdx(x, y + 2) * stride);
 #pragma unroll
                   for (int x = 0; x < 4; ++x) {
                     const double ref = mid[x + 1];
@@ -455,7 +465,10 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
           for (int k = lane; k < NV; k += 32) {
             if (k < NH && !h_fresh) continue;
             const double* r0 = s_red + k;
-            s_tot[k] = ((r0[0] + r0[NV]) + (r0[2 * NV] + r0[3 * NV])) + (r0[4 * NV] + r0[5 * NV]);
+            double t = r0[0];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) t += r0[w * NV];
+            s_tot[k] = t;
           }
           __syncwarp();
 #ifdef SVO_ALIGN_TIMING
@@ -679,9 +692,9 @@ inline size_t alignSmemBytes(int slots, int n_cams, bool illum, bool dj) {
   const int D = illum ? 8 : 6, NH = D * (D + 1) / 2;
   const int NV = NH + 6 * n_cams + (illum ? 2 : 0) + 3;
   const int NG = 6 * n_cams + (illum ? 2 : 0);
-  const size_t doubles = (size_t)slots * (3 + (dj ? 6 : 1) + 32) + (size_t)(kWarps + 1) * NV + (size_t)kCamBlk * n_cams + (size_t)D * D +
+  const size_t doubles = (size_t)slots * (3 + (dj ? 6 : 1)) + (size_t)(kWarps + 1) * NV + (size_t)kCamBlk * n_cams + (size_t)D * D +
                          (size_t)D * NG + (NG & 1);
-  return doubles * 8 + sizeof(Ctl) + (size_t)slots * 5 + 16;
+  return doubles * 8 + sizeof(Ctl) + (size_t)slots * 32 * sizeof(PatchT) + (size_t)slots * 5 + 16;
 }
 
 template <int ILL, bool ROBUST, bool DJ, int SLOTS>

@@ -42,6 +42,30 @@ def test_default_options_batch(ctx, orc):
         assert dq < 2e-3 and dt < 5e-3  # and it lands near the synthetic ground truth
 
 
+def test_subpixel_feature_positions(ctx, orc):
+    """Features at sub-pixel positions (what the Reprojector's refined matches are): the interpolated reference patch values are then
+    not representable in the kernel's FP32 patch cache, whose rounding (relative 2^-24 of a grey level) must stay far inside the
+    tolerance: pose within 1e-7 rad / 1e-9 m of the FP64 oracle, same iteration counts, for several option sets."""
+    pairs = []
+    for s in range(31, 39):
+        d = synth.make_align_pair(s)
+        rng = np.random.default_rng(s)
+        d["px"] = d["px"] + rng.uniform(-0.5, 0.5, d["px"].shape)
+        X = d["scene"].ref_points(d["px"])
+        d["depth"] = np.linalg.norm(X, axis=1)
+        d["f"] = X / d["depth"][:, None]
+        pairs.append(d)
+    for kw in (dict(), dict(estimate_illumination_gain=1, estimate_illumination_offset=1), dict(robustification=1, weight_scale=10.0),
+               dict(max_level=2, min_level=0)):
+        gopt = capi.sparse_align_options(**kw)
+        res, _, _ = gpu_align(ctx, pairs, gopt)
+        _compare(orc, pairs, res, gopt)
+        for d, r in zip(pairs, res):
+            o = oracle_align(orc, d, to_orc_options(orc, gopt))
+            dq, dt = pose_diff(r["T_icur_iref"], o.T_icur_iref)
+            assert dq < 1e-7 and dt < 1e-9, (kw, dq, dt)
+
+
 @pytest.mark.parametrize("kw", [
     dict(estimate_illumination_gain=1, estimate_illumination_offset=1),
     dict(robustification=1, weight_scale=10.0),

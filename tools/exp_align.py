@@ -37,3 +37,6 @@ if tm[:, 0].max() > 0:  # profiling build (make -C svo_pro_universal_b200/csrc t
     print("residual pass per warp / iteration: " + " ".join(f"w{w}={m[10+w]/it:.0f}" for w in range(6)))
     print("serial phase / iteration: " + ", ".join(f"{n}={m[16+k]/it:.0f}" for k, n in enumerate(["totals", "dx", "broadcast", "update", "store+refresh"])))
 print(f"lib={os.path.basename(os.environ.get('SVO_CUDA_LIB','libsvo_cuda.so'))} pad={os.environ.get('SVO_ALIGN_PAD_SMEM','0')} B={B} align_ms={e0.elapsed_time(e1)/10:.4f} iters_mean={res['iters'][:, :4].sum(1).mean():.2f} iters0={res['iters'][0][:4].tolist()}")
+tag = os.path.basename(os.environ.get('SVO_CUDA_LIB', 'libsvo_cuda.so')).replace('.so', '')
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+np.savez(os.path.join(ROOT, "gpurun_out", f"align_res_{tag}_B{B}.npz"), T=res["T_icur_iref"], iters=res["iters"], n=res["n_tracked"], chi2=res["chi2"])
