@@ -27,6 +27,11 @@ struct svo_cuda_ctx {
   long long launches = 0;
   int sm_count = 148;
   bool attr_pyr = false, attr_reproj = false;  // cudaFuncSetAttribute applied on THIS context's device (per device, not per process)
+  // Staging arena of SVO_MEM_HOST calls (Stager): one page-locked host buffer and one device buffer, halves for inputs / outputs. The small
+  // arrays of a call travel in ONE copy each way instead of one cudaMallocAsync + one pageable copy per array (single-frame latency).
+  uint8_t* stage_host = nullptr;
+  uint8_t* stage_dev = nullptr;
+  bool stage_busy = false;       // claimed by the Stager of the call in progress (nested Stagers fall back to per-array staging)
   int8_t* angle_bins = nullptr;  // 511 x 511 orientation-histogram bins of every u8 central-difference gradient (edgelet.cu), built on first use
   std::string last_error;
 };
@@ -81,15 +86,20 @@ int svoFail(svo_cuda_ctx* ctx, int code, const char* what, const char* file, int
     SVO_CUDA_TRY(ctx, cudaGetLastError());        \
   } while (0)
 
-// Staging of I/O arrays of a batched call. For SVO_MEM_DEVICE the caller's pointers are used in place;
-// for SVO_MEM_HOST inputs are copied to stream-ordered temporaries and outputs copied back in finish().
+// Staging of I/O arrays of a batched call. For SVO_MEM_DEVICE the caller's pointers are used in place; for SVO_MEM_HOST inputs are
+// copied to the device and outputs copied back in finish(). Arrays of at most kStageSmall bytes go through the context's staging arena
+// (packed into page-locked memory, one H2D copy issued by ready() right before the first launch, one D2H copy in finish()); larger ones
+// are copied one by one from / to the caller's memory (which the caller may have page-locked for bandwidth) through stream-ordered
+// temporaries.
 class Stager {
  public:
-  Stager(svo_cuda_ctx* c, svo_mem m) : ctx_(c), mem_(m) {}
+  static constexpr size_t kStageHalf = 128 * 1024, kStageSmall = 32 * 1024;
+  Stager(svo_cuda_ctx* c, svo_mem m);
   ~Stager() { release(); }
   template <class T>
   const T* in(const T* p, size_t n) {
     if (!p || mem_ == SVO_MEM_DEVICE || n == 0) return p;
+    if (void* a = arenaIn(p, n * sizeof(T))) return (const T*)a;
     void* d = alloc(n * sizeof(T));
     if (!d) return nullptr;
     if (cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, ctx_->stream) != cudaSuccess) failed_ = true;
@@ -98,6 +108,7 @@ class Stager {
   template <class T>
   T* out(T* p, size_t n) {
     if (!p || mem_ == SVO_MEM_DEVICE || n == 0) return p;
+    if (void* a = arenaOut(p, n * sizeof(T))) return (T*)a;
     void* d = alloc(n * sizeof(T));
     if (!d) return nullptr;
     outs_.push_back({p, d, n * sizeof(T)});
@@ -114,18 +125,24 @@ class Stager {
   }
   // device scratch that lives until finish()
   void* scratch(size_t bytes) { return alloc(bytes); }
-  bool failed() const { return failed_; }
+  // Called by every entry point after its last in() / out() and before its first launch: sends the packed inputs; true = staging failed.
+  bool failed();
   int finish();
 
  private:
   struct Out { void* host; void* dev; size_t bytes; };
   void* alloc(size_t bytes);
+  void* arenaIn(const void* p, size_t bytes);
+  void* arenaOut(void* p, size_t bytes);
   void release();
   svo_cuda_ctx* ctx_;
   svo_mem mem_;
   bool failed_ = false;
+  bool arena_ = false, sent_ = false;
+  size_t in_used_ = 0, out_used_ = 0;
   std::vector<void*> allocs_;
-  std::vector<Out> outs_;
+  std::vector<Out> outs_;        // per-array D2H copies
+  std::vector<Out> arena_outs_;  // host pointer | offset into the arena's output half (as a pointer into stage_host) | bytes
 };
 
 // ------------------------------------------------------------------------------------------------

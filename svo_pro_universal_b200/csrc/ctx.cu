@@ -10,6 +10,43 @@ int svoFail(svo_cuda_ctx* ctx, int code, const char* what, const char* file, int
   return code;
 }
 
+Stager::Stager(svo_cuda_ctx* c, svo_mem m) : ctx_(c), mem_(m) {
+  if (!c || m != SVO_MEM_HOST || c->stage_busy) return;
+  if (!c->stage_host) {  // first host-memory call of the context
+    cudaSetDevice(c->device);
+    void* h = nullptr;
+    void* d = nullptr;
+    if (cudaHostAlloc(&h, 2 * kStageHalf, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaMalloc(&d, 2 * kStageHalf) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
+    c->stage_host = (uint8_t*)h;
+    c->stage_dev = (uint8_t*)d;
+  }
+  c->stage_busy = true;
+  arena_ = true;
+}
+void* Stager::arenaIn(const void* p, size_t bytes) {
+  const size_t padded = (bytes + 15) & ~(size_t)15;
+  if (!arena_ || sent_ || bytes > kStageSmall || in_used_ + padded > kStageHalf) return nullptr;
+  memcpy(ctx_->stage_host + in_used_, p, bytes);
+  void* d = ctx_->stage_dev + in_used_;
+  in_used_ += padded;
+  return d;
+}
+void* Stager::arenaOut(void* p, size_t bytes) {
+  const size_t padded = (bytes + 15) & ~(size_t)15;
+  if (!arena_ || bytes > kStageSmall || out_used_ + padded > kStageHalf) return nullptr;
+  arena_outs_.push_back({p, ctx_->stage_host + kStageHalf + out_used_, bytes});
+  void* d = ctx_->stage_dev + kStageHalf + out_used_;
+  out_used_ += padded;
+  return d;
+}
+bool Stager::failed() {
+  if (arena_ && !sent_) {
+    sent_ = true;
+    if (in_used_ && cudaMemcpyAsync(ctx_->stage_dev, ctx_->stage_host, in_used_, cudaMemcpyHostToDevice, ctx_->stream) != cudaSuccess) failed_ = true;
+  }
+  return failed_;
+}
 void* Stager::alloc(size_t bytes) {
   void* d = nullptr;
   if (cudaMallocAsync(&d, bytes ? bytes : 1, ctx_->stream) != cudaSuccess) {
@@ -22,17 +59,22 @@ void* Stager::alloc(size_t bytes) {
 void Stager::release() {
   for (void* d : allocs_) cudaFreeAsync(d, ctx_->stream);
   allocs_.clear();
+  if (arena_) { ctx_->stage_busy = false; arena_ = false; }
 }
 int Stager::finish() {
-  if (failed_) return SVO_FAIL(ctx_, SVO_ERR_OUT_OF_MEMORY, "staging allocation or copy failed");
+  if (failed()) { release(); return SVO_FAIL(ctx_, SVO_ERR_OUT_OF_MEMORY, "staging allocation or copy failed"); }
   if (mem_ == SVO_MEM_HOST) {
+    if (out_used_)
+      SVO_CUDA_TRY(ctx_, cudaMemcpyAsync(ctx_->stage_host + kStageHalf, ctx_->stage_dev + kStageHalf, out_used_, cudaMemcpyDeviceToHost, ctx_->stream));
     for (const Out& o : outs_) SVO_CUDA_TRY(ctx_, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx_->stream));
     outs_.clear();
-    release();
+    for (void* d : allocs_) cudaFreeAsync(d, ctx_->stream);
+    allocs_.clear();
     SVO_CUDA_TRY(ctx_, cudaStreamSynchronize(ctx_->stream));
-  } else {
-    release();
+    for (const Out& o : arena_outs_) memcpy(o.host, o.dev, o.bytes);
+    arena_outs_.clear();
   }
+  release();
   return SVO_OK;
 }
 
@@ -86,6 +128,8 @@ int svo_cuda_ctx_destroy(svo_cuda_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->angle_bins) cudaFree(ctx->angle_bins);
+  if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+  if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return SVO_OK;
