@@ -296,7 +296,12 @@ SVO_D void blockMedian(const T* s_err, int m, T* s_out) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) pose_optimize_kernel(const PoseOptParams P) {
+// Resident CTAs per SM the register allocation is held to. Measured on the B200 (8192 two-camera bundles of the front-end chain):
+// 1 (202 registers, 2 CTAs / SM) 2.52 ms, 3 (168) 2.20 ms, 4 (128 registers, 4 CTAs / SM) 2.03 ms, 5 (96) 2.15 ms.
+#ifndef SVO_POSEOPT_MINB
+#define SVO_POSEOPT_MINB 4
+#endif
+__global__ void __launch_bounds__(kThreads, SVO_POSEOPT_MINB) pose_optimize_kernel(const PoseOptParams P) {
   __shared__ float s_err[kMaxFeat];     // start errors (float, as the reference's std::vector<float>)
   __shared__ double s_errd[kMaxFeat];   // final errors (double)
   __shared__ double s_mediand;

@@ -41,6 +41,10 @@ namespace {
 constexpr int kThreads = SVO_ALIGN_THREADS;
 constexpr int kWarps = kThreads / 32;
 static_assert(kThreads % 32 == 0 && kWarps >= 1 && kWarps <= 8, "kThreads");
+// Bundles with more than kFixedSlots features (stereo rigs: 2 x 150-180) get twice the threads, so that their slots are still walked in
+// one pass and an SM still holds 24 warps (2 CTAs x 12): 9.5 -> see profiles/ ms for the 8192 stereo pairs of the front-end chain.
+constexpr int kThreadsWide = 2 * kThreads;
+constexpr int kMaxWarps = kThreadsWide / 32;
 // resident CTAs per SM the register allocation is held to: (common case, variants with more per-thread state)
 constexpr int kMinBlocks = kThreads <= 96 ? 7 : (kThreads <= 128 ? 6 : 4);
 constexpr int kMinBlocksHeavy = kThreads <= 96 ? 6 : (kThreads <= 128 ? 4 : 3);
@@ -61,7 +65,7 @@ struct Ctl {
   double dx[8];                 // serial-solve path: lane 0 hands dx to the warp
   int stop, brk;
   int h_dirty;                  // a patch entered or left the image in this iteration: H must be re-reduced
-  int warp_cnt[kWarps];
+  int warp_cnt[kMaxWarps];
   int n_total;                  // features in the run (read from here inside the loops: a register copy would be spilled)
   int iters[SVO_MAX_LEVELS];
 #ifdef SVO_ALIGN_TIMING
@@ -84,7 +88,11 @@ struct Ctl {
 // ILL: 0 = no illumination parameters and alpha = beta = 0 (the subtraction of the reference pixel rides in the
 // interpolation's FMA chain), 1 = no illumination parameters but non-zero initial alpha/beta, 2 = gain and/or offset estimated.
 template <int ILL, bool ROBUST, bool DJ, int SLOTS>
-__global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) ? kMinBlocksHeavy : kMinBlocks) : 1) sparse_align_kernel(const AlignParams P) {
+__global__ void __launch_bounds__(SLOTS ? kThreads : kThreadsWide, SLOTS ? ((DJ || ILL == 2 || ROBUST) ? kMinBlocksHeavy : kMinBlocks)
+                                                                         : ((DJ || ILL == 2 || ROBUST) ? 1 : 2))
+sparse_align_kernel(const AlignParams P) {
+  constexpr int TH = SLOTS ? kThreads : kThreadsWide;  // threads of this variant
+  constexpr int NW = TH / 32;
   constexpr bool ILLUM = ILL == 2;
   constexpr bool unit_gain = ILL == 0;
   constexpr int D = ILLUM ? 8 : 6;
@@ -97,8 +105,8 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
   const int iCM = NH, iG6 = NH + 6 * n_cams, iChi = iG6 + (ILLUM ? 2 : 0), iN = iChi + 1, iCh = iChi + 2, NV = iChi + 3;
   double* s_xyz = smem;                          // [3][stride]
   double* s_aux = s_xyz + 3 * stride;            // [NAUX][stride]  1/z, or the 2x3 projection Jacobian
-  double* s_red = s_aux + NAUX * stride;         // [kWarps][NV]
-  double* s_tot = s_red + kWarps * NV;           // [NV]
+  double* s_red = s_aux + NAUX * stride;         // [NW][NV]
+  double* s_tot = s_red + NW * NV;           // [NV]
   double* s_camblk = s_tot + NV;                 // [n_cams][kCamBlk]
   const int NG = 6 * n_cams + (ILLUM ? 2 : 0);   // gradient-related totals: per-camera (c, xyz x c), then g6 g7
   double* s_Hinv = s_camblk + kCamBlk * n_cams;  // [D][D]   H^-1 (rebuilt with H)
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     for (int i = 0; i < 8; ++i) { ctl.I_prior[i] = 0.0; ctl.rd[i] = 0.0; }
     for (int i = 0; i < 28; ++i) ctl.L[i] = 0.0;
   }
-  for (int i = tid; i < NV; i += kThreads) s_tot[i] = 0.0;
+  for (int i = tid; i < NV; i += TH) s_tot[i] = 0.0;
   __syncthreads();
 
   // b2 + b3: ordered compaction of the eligible, in-bounds features of every ref camera, base caches
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     const int ml = opt.max_level;
     const double scale_max = 1.0f / (1 << ml);
     const int rows_m2 = rp.rows[ml] - 2, cols_m2 = rp.cols[ml] - 2;
-    for (int base = 0; base < n; base += kThreads) {
+    for (int base = 0; base < n; base += TH) {
       const int i = base + tid;
       bool ok = false;
       if (i < n && P.eligible[fbase + i]) {
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
       if (lane == 0) ctl.warp_cnt[warp] = __popc(bal);
       __syncthreads();
       int off = n_total, chunk = 0;
-      for (int w = 0; w < kWarps; ++w) {
+      for (int w = 0; w < NW; ++w) {
         if (w < warp) off += ctl.warp_cnt[w];
         chunk += ctl.warp_cnt[w];
       }
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
     for (int level = opt.max_level; level >= opt.min_level; --level) {
       const double scale = 1.0f / (1 << level);
       // ---- b4: reference patches of this level (sparse_img_align.cpp:319-403) ----
-      for (int s = tid; s < *n_total_s; s += kThreads) {
+      for (int s = tid; s < *n_total_s; s += TH) {
         const int c = s_cam[s] & 3;
         const PyrView& rp = P.ref_pyr[c];
         const int rf = P.ref_frame_idx ? P.ref_frame_idx[(size_t)pair * n_cams + c] : pair;
@@ -264,8 +272,8 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
         for (int k = lane; k < NV; k += 32) red[k] = 0.0;
         __syncwarp();
         const float alpha_f = ctl.alpha_f, beta_f = ctl.beta_f;
-        const int n_now = *n_total_s, n_round = ((n_now + kThreads - 1) / kThreads) * kThreads;
-        for (int s = tid; s < n_round; s += kThreads) {
+        const int n_now = *n_total_s, n_round = ((n_now + TH - 1) / TH) * TH;
+        for (int s = tid; s < n_round; s += TH) {
           bool vis = false;
           int c = 0;
           double gx = 0, gy = 0, chi = 0, g6 = 0, g7 = 0;
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
           // H depends only on the visible set: rebuild it when some patch entered or left the image (flag raised by the residual pass)
           h_fresh = ctl.h_dirty != 0;
           if (h_fresh) {
-            for (int s = tid; s < n_round; s += kThreads) {
+            for (int s = tid; s < n_round; s += TH) {
               const int sl = (s < n_now) ? s : 0;
               const unsigned cs = s_cam[sl];
               const bool vis = s < n_now && (cs & 0x80u) != 0u;
@@ -467,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
             const double* r0 = s_red + k;
             double t = r0[0];
 #pragma unroll
-            for (int w = 1; w < kWarps; ++w) t += r0[w * NV];
+            for (int w = 1; w < NW; ++w) t += r0[w * NV];
             s_tot[k] = t;
           }
           __syncwarp();
@@ -688,11 +696,11 @@ __global__ void __launch_bounds__(kThreads, SLOTS ? ((DJ || ILL == 2 || ROBUST) 
   }
 }
 
-inline size_t alignSmemBytes(int slots, int n_cams, bool illum, bool dj) {
+inline size_t alignSmemBytes(int slots, int n_cams, bool illum, bool dj, int n_warps) {
   const int D = illum ? 8 : 6, NH = D * (D + 1) / 2;
   const int NV = NH + 6 * n_cams + (illum ? 2 : 0) + 3;
   const int NG = 6 * n_cams + (illum ? 2 : 0);
-  const size_t doubles = (size_t)slots * (3 + (dj ? 6 : 1)) + (size_t)(kWarps + 1) * NV + (size_t)kCamBlk * n_cams + (size_t)D * D +
+  const size_t doubles = (size_t)slots * (3 + (dj ? 6 : 1)) + (size_t)(n_warps + 1) * NV + (size_t)kCamBlk * n_cams + (size_t)D * D +
                          (size_t)D * NG + (NG & 1);
   return doubles * 8 + sizeof(Ctl) + (size_t)slots * 32 * sizeof(PatchT) + (size_t)slots * 5 + 16;
 }
@@ -701,7 +709,7 @@ template <int ILL, bool ROBUST, bool DJ, int SLOTS>
 cudaError_t launchAlign(const AlignParams& P, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<ILL, ROBUST, DJ, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  sparse_align_kernel<ILL, ROBUST, DJ, SLOTS><<<P.B, kThreads, smem, stream>>>(P);
+  sparse_align_kernel<ILL, ROBUST, DJ, SLOTS><<<P.B, SLOTS ? kThreads : kThreadsWide, smem, stream>>>(P);
   return cudaGetLastError();
 }
 template <int ILL, bool ROBUST>
@@ -744,9 +752,9 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   const bool illum = opt->estimate_illumination_gain || opt->estimate_illumination_offset;
   const bool robust = opt->robustification != 0;
   const bool dj = opt->use_distortion_jacobian != 0;
-  size_t smem = alignSmemBytes(slots, n_cams, illum, dj);
+  size_t smem = alignSmemBytes(slots, n_cams, illum, dj, (fixed ? kThreads : kThreadsWide) / 32);
   if (const char* pad = getenv("SVO_ALIGN_PAD_SMEM")) smem += (size_t)atoi(pad);  // occupancy experiments only
-  if (smem > 227 * 1024) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: n_cams*max_features exceeds the shared-memory capacity (~590 features per bundle)");
+  if (smem > 227 * 1024) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: n_cams*max_features exceeds the shared-memory capacity (~1380 features per bundle)");
   for (int c = 0; c < n_cams; ++c) {
     P.ref_pyr[c] = makeView(ref_pyr[c]);
     P.cur_pyr[c] = makeView(cur_pyr[c]);

@@ -137,13 +137,21 @@ def test_many_features_and_max_capacity(ctx, orc):
     gopt = capi.sparse_align_options()
     res, _, _ = gpu_align(ctx, [d], gopt)
     _compare(orc, [d], res, gopt)
-    # more features than one CTA's shared memory can hold -> explicit error, not a silent truncation
-    big = np.zeros((1, 1, 800, 2))
+    # more features than one CTA's shared memory can hold (about 1380 with the FP32 patch cache) -> explicit error, not a silent truncation
+    n_big = 1600
     with pytest.raises(capi.SvoCudaError):
         p = capi.Pyramid(ctx, 1, 752, 480, 5)
         capi.sparse_align(ctx, [p], [p], [capi.Camera.from_dict(d["cam"])], np.array([synth.IDENTITY]), np.array([synth.IDENTITY]),
-                          np.array([synth.IDENTITY]), np.zeros((1, 1), np.int32), big, np.zeros((1, 1, 800, 3)), np.ones((1, 1, 800)),
-                          np.zeros((1, 1, 800), np.uint8), gopt)
+                          np.array([synth.IDENTITY]), np.zeros((1, 1), np.int32), np.zeros((1, 1, n_big, 2)), np.zeros((1, 1, n_big, 3)),
+                          np.ones((1, 1, n_big)), np.zeros((1, 1, n_big), np.uint8), gopt)
+    # a bundle that fills most of that capacity: the same 300-odd features four times over (two passes of the 384-thread variant)
+    rep = 4
+    d4 = dict(d)
+    for k in ("px", "f", "depth", "eligible"):
+        d4[k] = np.concatenate([d[k]] * rep)
+    res4, _, _ = gpu_align(ctx, [d4], gopt)
+    _compare(orc, [d4], res4, gopt)
+    assert res4[0]["n_tracked"] == rep * res[0]["n_tracked"] > 1000
 
 
 def test_frame_index_indirection_and_device_resident_io(ctx, orc):
