@@ -262,7 +262,7 @@ def cpu_step_fn(n_pairs_per_step, n_threads, seed0=1000, n_unique=16, kind="auto
     if kind == "reference":
         def fn():
             return orc.ref_pyramid_align_batch(L, R, Cc, opt, N_LEVELS, n_threads)
-        what = ("the reference's own SparseImgAlign + halfSample sources compiled -O2 against a scalar (non-vectorised) Eigen stand-in "
+        what = ("the reference's own SparseImgAlign + halfSample sources compiled -O3 against a scalar (non-vectorised) Eigen stand-in "
                 "(oracle/_ref/libfrontend_ref.so)")
     else:
         def fn():

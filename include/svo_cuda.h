@@ -125,7 +125,8 @@ int svo_cuda_grid_cells(int width, int height, int cell_size, int* n_cols, int* 
  * occupancy_in: [count][n_cells] bytes (non-zero = cell already holds a feature) or NULL. */
 int svo_cuda_fast_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
                          const uint8_t* occupancy_in, svo_corner* corners_out, svo_mem mem);
-/* Fused variant: builds the pyramid of the frames and detects in one pass over level 0 (a1 + a2-a5). */
+/* Convenience variant (a1 + a2-a5): svo_cuda_pyr_build of the frames followed by svo_cuda_fast_detect on the same stream — two launches,
+ * no host work in between; the detector re-reads levels 0-2 (it is bound by instruction issue, not by that traffic). */
 int svo_cuda_pyramid_fast_detect(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count, const svo_detector_options* opt,
                                  const uint8_t* occupancy_in, svo_corner* corners_out, svo_mem mem);
 /* Raw per-level stages, for parity tests against fast::* (a2, a3, a4): dense maps for one level of one frame.

@@ -62,6 +62,23 @@ dinv = np.stack([est, est + spread, np.maximum(est - spread, 1e-8)], 1)
 for _ in range(REPS):
     r = capi.find_epipolar_match_direct(ctx, ref, cur, cam, cam, T, ft, dinv, mopt, ref_frame_idx=fidx, cur_frame_idx=fidx, T_idx=fidx)
 print("epipolar success", float((r["result"] == 0).mean()))
+# Matcher::scanEpipolarLine on its own: the long segments of the call above with their warped patches (svo_cuda_warp_affine)
+long_ = np.flatnonzero(r["epi_length_pyramid"] >= 2.0)[: (64 if SMALL else 20000)]
+if len(long_):
+    Aw, slw, pwb, okw = capi.warp_affine(ctx, ref, cam, cam, T, ft[long_], 1.0 / np.maximum(dinv[long_, 0], 1e-6), ref_frame_idx=fidx[long_], T_idx=fidx[long_])
+    Rs = np.stack([synth.se3_to_Rt(T[i])[0] for i in range(NU)]); ts = np.stack([synth.se3_to_Rt(T[i])[1] for i in range(NU)])
+    fr = np.stack([ft["f"][i] for i in long_]); Rf = np.einsum("nij,nj->ni", Rs[fidx[long_]], fr); tt = ts[fidx[long_]]
+    for _ in range(REPS):
+        best, zb = capi.scan_epipolar_line(ctx, cur, cam, Rf + tt * dinv[long_, 1:2], Rf + tt * dinv[long_, 2:3], Rf + tt * dinv[long_, 0:1],
+                                           np.ascontiguousarray(pwb.reshape(-1, 10, 10)[:, 1:9, 1:9]), r["search_level"][long_],
+                                           r["epi_length_pyramid"][long_], mopt, cur_frame_idx=fidx[long_])
+    print("stand-alone scans", len(long_), "below threshold", float((zb < 2000 * 64).mean()))
+# fast:: leaves with list-shaped results on one level (device-side ordered compaction)
+for _ in range(REPS):
+    xy_l, sc_l, nm_l = capi.fast_corner_list(ctx, ref, 0, 0, 10, 10)
+    sc2 = capi.fast_corner_score(ctx, ref, 0, 0, xy_l, 10, 10)
+    nm2 = capi.fast_nonmax_3x3(ctx, xy_l, sc_l)
+print("corner list", len(xy_l), "scores equal", bool(np.array_equal(sc_l, sc2)), "non-max equal", bool(np.array_equal(np.flatnonzero(nm_l), nm2)))
 del ref, cur
 
 # (d): depth filter
