@@ -41,8 +41,17 @@ ALGO_BYTES_FAST_ONLY = 360960 + 92160 + 23040 + 416 * 20   # detection alone: re
 ALGO_BYTES_PER_FEATURE = 333       # (c) patch with border + cur footprint + feature in + result out
 ALGO_BYTES_PER_UPDATE = 80         # (d) pure filter update, state in + out
 METRIC = "aligned frame-pairs/sec (752x480, 4-level SparseImgAlign, ~180 features)"
-# ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, divided by the units of that launch
-NCU_DRAM_BYTES_PER_UNIT = {"sparse_align_kernel": (212.04e6 + 4.135e6) / 1184}
+
+
+def ncu_traffic(kernel, units):
+    """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` from this round's `ncu --set full`
+    capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), scaled from the captured launch's units to `units`; None if
+    the kernel was not captured."""
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"][kernel]
+    except (OSError, KeyError, ValueError):
+        return None
+    return k["dram_bytes_per_unit"] * units
 
 
 def load_peaks():
@@ -592,7 +601,7 @@ def leg_headline(rig, sample_n=64):
                 "note": "new frames' level-0 images + feature arrays H2D from page-locked memory, results D2H, every step"},
         "roofline": roofline("sparse_align_kernel<ILL=0, ROBUST=0, DJ=0, SLOTS=180>", ALGO_BYTES_PER_PAIR, B, align_ms, rig.peaks,
                              "algorithmic bytes 247,044 B/pair; the kernel is FP64-issue / latency bound, not HBM bound (DESIGN.md 4b)",
-                             traffic=NCU_DRAM_BYTES_PER_UNIT["sparse_align_kernel"] * B),
+                             traffic=ncu_traffic("sparse_align_kernel", B)),
         "parity_sampled": parity,
         "latency": {"p50_ms_pair_e2e": 1e3 * float(np.median(lat)), "p95_ms_pair_e2e": 1e3 * float(np.percentile(lat, 95)),
                     "p50_ms_align_call": 1e3 * float(np.median(lat_align)),
@@ -650,7 +659,8 @@ def leg_fast(rig):
            "scaling": "weak", "ms_per_step": ms_all, "kernel_ms": ms_det, "gpu_launches": int(launches),
            "roofline": roofline("fast_level_kernel<10> (+ key init / decode)", ALGO_BYTES_FAST_ONLY, B, ms_det, rig.peaks,
                                 "detection alone re-reads levels 0-2; the kernel is issue bound (DESIGN.md 4a); fused pyramid + detection "
-                                "moves %.0f GB/s of the 487,466 B/frame minimum" % (ALGO_BYTES_PER_FRAME * B / (ms_all * 1e-3) / 1e9)),
+                                "moves %.0f GB/s of the 487,466 B/frame minimum" % (ALGO_BYTES_PER_FRAME * B / (ms_all * 1e-3) / 1e9),
+                                traffic=ncu_traffic("fast_level_kernel", B)),
            "e2e": {"value": rig.world * B / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h_imgs.numel()),
                    "d2h_bytes_per_step": int(h_corners.numel())},
            "l2": "inputs larger than L2 (%.0f MB of level-0 images per step)" % (h_imgs.numel() / 1e6),
@@ -770,7 +780,8 @@ def leg_match(rig):
            "success_frac": {"find_match_direct": float((r0["result"] == 0).mean()), "find_epipolar_match_direct": float((r1["result"] == 0).mean())},
            "mean_epi_length_px": float(r1["epi_length_pyramid"].mean()),
            "roofline": roofline("match_kernel<0> + epipolar match kernels", 2 * ALGO_BYTES_PER_FEATURE, M, ms_step, rig.peaks,
-                                "333 B/feature compulsory per call; both calls are bound by issue slots (ordered float sums, per-feature control flow), not memory (DESIGN.md 4c)"),
+                                "333 B/feature compulsory per call; both calls are bound by issue slots (ordered float sums, per-feature control flow), not memory (DESIGN.md 4c)",
+                                traffic=(lambda a, b: None if a is None or b is None else a + b)(ncu_traffic("match_kernel<0>", M), ncu_traffic("match_kernel<1>", M))),
            "e2e": {"value": rig.world * M / (e2e_ms * 1e-3), "unit": "features/s",
                    "h2d_bytes_per_step": int(2 * (hft.numel() + sum(v.numel() * v.element_size() for v in h.values()))),
                    "d2h_bytes_per_step": int(h_out0.numel() + h_out1.numel()),

@@ -2,6 +2,7 @@
 // include/svo_cuda.h, calls ONE entry point with host buffers (SVO_MEM_HOST) and unpacks the results; nothing here
 // computes the hot path on the CPU.
 #include "svo_b200.h"
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -421,17 +422,78 @@ DepthFilter::DepthFilter(const DepthFilterOptions& options) : options_(options) 
   matcher_.options_.affine_est_offset_ = options.affine_est_offset;
   matcher_.options_.affine_est_gain_ = options.affine_est_gain;
 }
-size_t DepthFilter::updateSeeds(const std::vector<FramePtr>& ref_frames_with_seeds, const FramePtr& cur_frame) {
-  size_t n_success = 0;
+size_t DepthFilter::updateSeedsOfRefFrame(const FramePtr& ref_frame, const FramePtr& cur_frame) {
   const svo_depth_filter_options d = depth_filter_utils::cDepthOptions(options_.seed_convergence_sigma2_thresh,
                                                                        options_.mappoint_convergence_sigma2_thresh, true, false, true);
-  for (const FramePtr& ref_frame : ref_frames_with_seeds) {
-    std::vector<size_t> seeds;
-    for (size_t i = 0; i < ref_frame->num_features_; ++i)
-      if (isSeed(ref_frame->type_vec_[i])) seeds.push_back(i);
-    n_success += depth_filter_utils::updateSeedsOfFrame(*cur_frame, *ref_frame, seeds, matcher_, d);
+  std::vector<size_t> seeds;
+  for (size_t i = 0; i < ref_frame->num_features_; ++i)
+    if (isSeed(ref_frame->type_vec_[i])) seeds.push_back(i);
+  return depth_filter_utils::updateSeedsOfFrame(*cur_frame, *ref_frame, seeds, matcher_, d);
+}
+size_t DepthFilter::updateSeeds(const std::vector<FramePtr>& ref_frames_with_seeds, const FramePtr& cur_frame) {
+  size_t n_success = 0;
+  if (!thread_) {
+    for (const FramePtr& ref_frame : ref_frames_with_seeds) n_success += updateSeedsOfRefFrame(ref_frame, cur_frame);
+  } else {  // depth_filter.cpp:235-249
+    std::unique_lock<std::mutex> lock(jobs_mut_);
+    for (const FramePtr& ref_frame : ref_frames_with_seeds) {
+      Job j;
+      j.type = Job::UPDATE; j.cur_frame = cur_frame; j.ref_frame = ref_frame;
+      jobs_.push(j);
+    }
+    jobs_condvar_.notify_all();
   }
   return n_success;
+}
+DepthFilter::~DepthFilter() { stopThread(); }
+void DepthFilter::startThread() {
+  if (thread_) return;  // "Thread already started!"
+  quit_thread_ = false;
+  thread_.reset(new std::thread(&DepthFilter::updateSeedsLoop, this));
+}
+void DepthFilter::stopThread() {
+  if (!thread_) return;
+  {
+    std::unique_lock<std::mutex> lock(jobs_mut_);
+    quit_thread_ = true;
+  }
+  jobs_condvar_.notify_all();
+  thread_->join();
+  thread_.reset();
+}
+void DepthFilter::reset() {
+  std::unique_lock<std::mutex> lock(jobs_mut_);
+  while (!jobs_.empty()) jobs_.pop();
+}
+void DepthFilter::waitForJobs() {
+  std::unique_lock<std::mutex> lock(jobs_mut_);
+  idle_condvar_.wait(lock, [this] { return !thread_ || (jobs_.empty() && !busy_); });
+}
+void DepthFilter::updateSeedsLoop() {  // depth_filter.cpp:145-198
+  for (;;) {
+    Job job;
+    {
+      std::unique_lock<std::mutex> lock(jobs_mut_);
+      busy_ = false;
+      idle_condvar_.notify_all();
+      while (jobs_.empty() && !quit_thread_) jobs_condvar_.wait(lock);
+      if (quit_thread_) return;
+      job = jobs_.front();
+      jobs_.pop();
+      busy_ = true;
+    }
+    try {
+      if (job.type == Job::SEED_INIT) {
+        std::unique_lock<std::mutex> lock(feature_detector_mut_);
+        depth_filter_utils::initializeSeeds(job.cur_frame, feature_detector_, options_.max_n_seeds_per_frame, float(job.min_depth),
+                                            float(job.max_depth), float(job.mean_depth));
+      } else {
+        updateSeedsOfRefFrame(job.ref_frame, job.cur_frame);
+      }
+    } catch (const std::exception& e) {  // a worker thread must not take the process down through an uncaught exception
+      std::fprintf(stderr, "svo::DepthFilter worker: %s\n", e.what());
+    }
+  }
 }
 
 // ---- Reprojector -----------------------------------------------------------------------------------------------------------------
@@ -929,8 +991,18 @@ DepthFilter::DepthFilter(const DepthFilterOptions& options, const DetectorOption
 
 void DepthFilter::addKeyframe(const FramePtr& frame, const double depth_mean, const double depth_min, const double depth_max) {
   if (!feature_detector_) throw b200::Error("DepthFilter::addKeyframe: no feature detector (use the detector-building constructor)");
-  depth_filter_utils::initializeSeeds(frame, feature_detector_, options_.max_n_seeds_per_frame, float(depth_min), float(depth_max),
-                                      float(depth_mean));
+  if (!thread_) {
+    std::unique_lock<std::mutex> lock(feature_detector_mut_);
+    depth_filter_utils::initializeSeeds(frame, feature_detector_, options_.max_n_seeds_per_frame, float(depth_min), float(depth_max),
+                                        float(depth_mean));
+  } else {  // depth_filter.cpp:125-133: clear all other jobs, this one has priority
+    std::unique_lock<std::mutex> lock(jobs_mut_);
+    while (!jobs_.empty()) jobs_.pop();
+    Job j;
+    j.type = Job::SEED_INIT; j.cur_frame = frame; j.min_depth = depth_min; j.max_depth = depth_max; j.mean_depth = depth_mean;
+    jobs_.push(j);
+    jobs_condvar_.notify_all();
+  }
 }
 
 namespace depth_filter_utils {

@@ -12,9 +12,12 @@
 #include <array>
 #include <cstdint>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
+#include <queue>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/svo_cuda.h"
@@ -341,16 +344,40 @@ class DepthFilter {
   explicit DepthFilter(const DepthFilterOptions& options);
   // depth_filter.h:80-84: the constructor that builds its own detector through makeDetector
   DepthFilter(const DepthFilterOptions& options, const DetectorOptions& detector_options, const CameraPtr& cam);
-  // DepthFilter::addKeyframe (depth_filter.cpp:89-133, non-threaded branch): initializeSeeds on the new keyframe
+  ~DepthFilter();  // stops the thread if necessary (depth_filter.cpp:59-63)
+  DepthFilter(const DepthFilter&) = delete;
+  DepthFilter& operator=(const DepthFilter&) = delete;
+  // depth_filter.cpp:65-88: seed initialisation and seed updates in a parallel thread. The worker owns its own svo_cuda context
+  // (= its own stream, b200::context() is per host thread), so its launches overlap with the pipeline thread's — the GPU analogue of
+  // the reference's hand-off: addKeyframe / updateSeeds then only enqueue and return.
+  void startThread();
+  void stopThread();
+  // DepthFilter::addKeyframe (depth_filter.cpp:89-133): initializeSeeds on the new keyframe, at once or — threaded — as a job that
+  // first drops every queued job ("this one has priority", :129-131)
   void addKeyframe(const FramePtr& frame, const double depth_mean, const double depth_min, const double depth_max);
-  void reset() {}  // depth_filter.cpp:135-144 clears the worker thread's job queue; there is no worker thread here
-  // DepthFilter::updateSeeds (depth_filter.cpp:200-249, non-threaded branch): every seed of every ref frame against cur_frame,
-  // one batched launch; returns the number of successful updates.
+  void reset();  // depth_filter.cpp:135-144: drops the queued jobs
+  // DepthFilter::updateSeeds (depth_filter.cpp:200-249): every seed of every ref frame against cur_frame. Not threaded: one batched
+  // launch per ref frame, returns the number of successful updates. Threaded: one job per ref frame is queued (the reference queues one
+  // per seed and processes them one at a time; a batch of one per launch would idle the GPU) and 0 is returned, as in the reference.
   size_t updateSeeds(const std::vector<FramePtr>& ref_frames_with_seeds, const FramePtr& cur_frame);
   Matcher& getMatcher() { return matcher_; }
+  // (not in the reference) block until the worker has drained its queue: lets a caller read the seed states at a defined point
+  void waitForJobs();
 
  private:
+  struct Job {  // depth_filter.h:68-101
+    enum Type { UPDATE, SEED_INIT } type = UPDATE;
+    FramePtr cur_frame, ref_frame;
+    double min_depth = 0, max_depth = 0, mean_depth = 0;
+  };
+  void updateSeedsLoop();
+  size_t updateSeedsOfRefFrame(const FramePtr& ref_frame, const FramePtr& cur_frame);
   Matcher matcher_;
+  std::mutex jobs_mut_;
+  std::condition_variable jobs_condvar_, idle_condvar_;
+  std::queue<Job> jobs_;
+  bool quit_thread_ = false, busy_ = false;
+  std::unique_ptr<std::thread> thread_;
 };
 
 // ---- (a) FAST detector -----------------------------------------------------------------------------------------------------

@@ -280,6 +280,54 @@ int main(int argc, char** argv) {
         out.push_back(double(df.feature_detector_ != nullptr)); out.push_back(double(df.sec_feature_detector_ == nullptr));
       }
     }
+    // (g) the depth filter's parallel thread (depth_filter.cpp:65-88, 145-198): addKeyframe / updateSeeds only enqueue, the worker runs the
+    // same batched calls on its own context; results must equal the synchronous run of (d) bit for bit
+    {
+      auto clone = [&](const FramePtr& src) {
+        auto f = std::make_shared<Frame>();
+        f->id_ = src->id_ + 20;
+        f->cam_ = cam;
+        for (const Image& im : src->img_pyr_) {
+          Image c(im.rows, im.cols);
+          for (int y = 0; y < im.rows; ++y) std::memcpy(c.data + size_t(y) * c.step, im.data + size_t(y) * im.step, size_t(im.cols));
+          f->img_pyr_.push_back(std::move(c));
+        }
+        for (Image& im : f->img_pyr_) im.data = im.storage.data();
+        f->T_f_w_ = src->T_f_w_;
+        f->T_cam_imu_ = src->T_cam_imu_;
+        return f;
+      };
+      FramePtr ref3 = clone(ref), cur3 = clone(cur);
+      for (int i = 0; i < N; ++i) {
+        ref3->px_vec_.push_back(ref->px_vec_[i]); ref3->f_vec_.push_back(ref->f_vec_[i]); ref3->grad_vec_.push_back(ref->grad_vec_[i]);
+        ref3->score_vec_.push_back(0); ref3->level_vec_.push_back(level[i]); ref3->depth_vec_.push_back(depth[i]);
+        ref3->type_vec_.push_back((FeatureType(type[i]) == FeatureType::kEdgelet) ? FeatureType::kEdgeletSeed : FeatureType::kCornerSeed);
+        ref3->invmu_sigma2_a_b_vec_.push_back({0.25, (1 / 1.5) * (1 / 1.5) / 36.0, 10.0, 10.0});
+      }
+      ref3->num_features_ = N;
+      ref3->seed_mu_range_ = 1 / 1.5;
+      DepthFilterOptions o;
+      o.scan_epi_unit_sphere = true;
+      DepthFilter df(o, DetectorOptions(), cam);
+      df.startThread();
+      df.startThread();  // "Thread already started!": no second thread
+      const size_t queued = df.updateSeeds({ref3}, cur3);  // returns at once with 0, as the reference's threaded branch
+      FramePtr kf = clone(cur);
+      df.waitForJobs();
+      size_t mismatches = 0;
+      for (int i = 0; i < N; ++i) {
+        for (int k = 0; k < 4; ++k) mismatches += ref3->invmu_sigma2_a_b_vec_[i][k] != ref->invmu_sigma2_a_b_vec_[i][k];
+        mismatches += ref3->type_vec_[i] != ref->type_vec_[i];
+      }
+      out.push_back(double(queued)); out.push_back(double(mismatches));
+      // a queued update is dropped by the keyframe job that follows it ("clear all other jobs, this one has priority")
+      df.addKeyframe(kf, 3.0, 1.0, 10.0);
+      df.waitForJobs();
+      out.push_back(double(kf->num_features_));
+      df.reset();
+      df.stopThread();
+      df.stopThread();
+    }
     std::ofstream o(argv[2], std::ios::binary);
     o.write(reinterpret_cast<const char*>(out.data()), sizeof(double) * out.size());
     std::printf("facade_driver ok: %zu doubles\n", out.size());

@@ -175,6 +175,10 @@ def test_cpp_facades_match_oracle(orc, tmp_path):
     p += 4
     assert list(out[p:p + 2]) == [1.0, 1.0]
     p += 2
+    # (g) DepthFilter with its parallel thread: updateSeeds returned 0 at once, the worker's results equal the synchronous run's bit for
+    # bit, and the keyframe job initialised the reference's 200 seeds
+    assert list(out[p:p + 3]) == [0.0, 0.0, 200.0], list(out[p:p + 3])
+    p += 3
     assert p == len(out)
     types = np.where(ftype == synth.K_EDGELET, synth.K_EDGELET_SEED, synth.K_CORNER_SEED).astype(np.uint8)
     st = np.tile(np.array([0.25, (1 / 1.5) ** 2 / 36.0, 10.0, 10.0]), (N, 1))

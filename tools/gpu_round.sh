@@ -28,7 +28,7 @@ if has launches; then
       python tools/prof_paths.py > gpurun_out/${tag}_launches_paths.log 2>&1
 fi
 if has ncu; then
-  for k in ${NCU_KERNELS:-sparse_align_kernel pyr_down fast_level match_kernel.0 match_kernel.1 seed_step_kernel seed_match_kernel filter_seq_kernel scan_epipolar_kernel reproj_match reproj_sort pose_optimize_kernel edgelet_score edgelet_decode optimize_points_kernel stereo_commit corner_scatter_kernel}; do
+  for k in ${NCU_KERNELS:-sparse_align_kernel pyr_down fast_level match_kernel..int.0 match_kernel..int.1 seed_step_kernel seed_match_kernel filter_seq_kernel scan_epipolar_kernel reproj_match reproj_sort pose_optimize_kernel edgelet_score edgelet_decode optimize_points_kernel stereo_commit corner_scatter_kernel}; do
     kf=$(echo "$k" | tr -c 'A-Za-z0-9_\n' '_')
     timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$k" -s 1 -c 1 -f -o gpurun_out/${tag}_ncu_$kf \
         python tools/prof_paths.py > gpurun_out/${tag}_ncu_$kf.log 2>&1
