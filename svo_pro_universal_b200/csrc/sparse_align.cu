@@ -43,11 +43,21 @@ constexpr int kWarps = kThreads / 32;
 static_assert(kThreads % 32 == 0 && kWarps >= 1 && kWarps <= 8, "kThreads");
 // Bundles with more than kFixedSlots features (stereo rigs: 2 x 150-180) get twice the threads, so that their slots are still walked in
 // one pass and an SM still holds 24 warps (2 CTAs x 12): 9.5 -> see profiles/ ms for the 8192 stereo pairs of the front-end chain.
+#ifndef SVO_ALIGN_WIDE_ILLUM_MINB
+#define SVO_ALIGN_WIDE_ILLUM_MINB 2   // 8-DoF stereo bundles of the front-end chain: 1 CTA / SM (162 registers) 7.9 ms, 2 CTAs / SM (80) 5.7 ms per 8192 pairs
+#endif
+#ifndef SVO_ALIGN_ILLUM_MINB
+#define SVO_ALIGN_ILLUM_MINB kMinBlocks   // 8-DoF mono, 4096 pairs: 3 CTAs / SM 1.547 ms, 4 CTAs / SM (80 registers) 1.458 ms
+#endif
 constexpr int kThreadsWide = 2 * kThreads;
 constexpr int kMaxWarps = kThreadsWide / 32;
 // resident CTAs per SM the register allocation is held to: (common case, variants with more per-thread state)
 constexpr int kMinBlocks = kThreads <= 96 ? 7 : (kThreads <= 128 ? 6 : 4);
+#ifdef SVO_ALIGN_HEAVY_MINB
+constexpr int kMinBlocksHeavy = SVO_ALIGN_HEAVY_MINB;
+#else
 constexpr int kMinBlocksHeavy = kThreads <= 96 ? 6 : (kThreads <= 128 ? 4 : 3);
+#endif
 // The warp that runs the serial part of an iteration. (Warps are dealt to the four SM sub-partitions round robin, so sub-partitions
 // 2 and 3 hold one warp of every resident CTA instead of two; moving the serial work there was measured on the B200: 0.888 ms
 // instead of 0.869 ms per 4096 pairs, so it stays on warp 0.)
@@ -88,8 +98,9 @@ struct Ctl {
 // ILL: 0 = no illumination parameters and alpha = beta = 0 (the subtraction of the reference pixel rides in the
 // interpolation's FMA chain), 1 = no illumination parameters but non-zero initial alpha/beta, 2 = gain and/or offset estimated.
 template <int ILL, bool ROBUST, bool DJ, int SLOTS>
-__global__ void __launch_bounds__(SLOTS ? kThreads : kThreadsWide, SLOTS ? ((DJ || ILL == 2 || ROBUST) ? kMinBlocksHeavy : kMinBlocks)
-                                                                         : ((DJ || ILL == 2 || ROBUST) ? 1 : 2))
+// (measured per variant on the B200, 4096 pairs: robust weights alone 1.473 ms at 3 CTAs / SM, 1.410 at 4; robust + illumination 3.19 at 3, 3.70 at 4)
+__global__ void __launch_bounds__(SLOTS ? kThreads : kThreadsWide, SLOTS ? ((DJ || (ROBUST && ILL == 2)) ? kMinBlocksHeavy : (ILL == 2 ? SVO_ALIGN_ILLUM_MINB : kMinBlocks))
+                                                                         : ((DJ || ROBUST) ? 1 : (ILL == 2 ? SVO_ALIGN_WIDE_ILLUM_MINB : 2)))
 sparse_align_kernel(const AlignParams P) {
   constexpr int TH = SLOTS ? kThreads : kThreadsWide;  // threads of this variant
   constexpr int NW = TH / 32;

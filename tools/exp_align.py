@@ -16,7 +16,8 @@ ref.upload(torch.from_numpy(pk["ref_imgs"]).to(dev)); cur.upload(torch.from_nump
 cam = capi.Camera.from_dict(uniq[0]["cam"])
 d = {k: torch.from_numpy(np.ascontiguousarray(pk[k])).to(dev) for k in ("T_imu_world_ref", "T_imu_world_cur", "n_features", "px", "f", "depth", "eligible")}
 d_res = torch.zeros(B * capi.ALIGN_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-opt = capi.sparse_align_options()
+opt = capi.sparse_align_options(**({"estimate_illumination_gain": 1, "estimate_illumination_offset": 1} if os.environ.get("EXP_ILLUM") else {}),
+                                **({"robustification": 1, "weight_scale": 10.0} if os.environ.get("EXP_ROBUST") else {}))
 def run():
     capi.sparse_align(ctx, [ref], [cur], [cam], pk["T_cam_imu"], d["T_imu_world_ref"], d["T_imu_world_cur"], d["n_features"], d["px"], d["f"], d["depth"], d["eligible"], opt, results=d_res)
 for _ in range(3): run()
