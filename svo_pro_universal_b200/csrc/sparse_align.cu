@@ -326,7 +326,7 @@ sparse_align_kernel(const AlignParams P) {
                   unsigned ra, rb;
                   loadRow5(img + (size_t)vi * pitch, ui, ra, rb);
 #pragma unroll
-                  for (int x = 0; x < 5; ++x) tp[x] = u8ToDouble(x < 4 ? byteAt(ra, x) : byteAt(rb, 0));
+                  tp[0] = tapToDouble<0>(ra, 0); tp[1] = tapToDouble<1>(ra, 1); tp[2] = tapToDouble<2>(ra, 2); tp[3] = tapToDouble<3>(ra, 3); tp[4] = tapToDouble<4>(rb, 0);
                 }
                 double up[4], mid[6], low[6];
 #pragma unroll
@@ -338,7 +338,7 @@ sparse_align_kernel(const AlignParams P) {
                   unsigned na, nb;
                   loadRow5(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
 #pragma unroll
-                  for (int x = 0; x < 5; ++x) tn[x] = u8ToDouble(x < 4 ? byteAt(na, x) : byteAt(nb, 0));
+                  tn[0] = tapToDouble<0>(na, 0); tn[1] = tapToDouble<1>(na, 1); tn[2] = tapToDouble<2>(na, 2); tn[3] = tapToDouble<3>(na, 3); tn[4] = tapToDouble<4>(nb, 0);
 #pragma unroll
                   for (int x = (y < 3 ? 0 : 1); x < (y < 3 ? 6 : 5); ++x) low[x] = patchLoad(patch + patchIdx(x, y + 2) * stride);
 #pragma unroll

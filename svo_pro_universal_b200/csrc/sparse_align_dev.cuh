@@ -95,6 +95,16 @@ SVO_D void loadRow5(const uint8_t* row, int x0, unsigned& a, unsigned& b) {
 // exact u8 -> double on the FP64 pipe (2^52 + b has b in its low mantissa bits), instead of I2F on the quarter-rate XU pipe
 SVO_D double u8ToDouble(unsigned b) { return __hiloint2double(0x43300000, (int)b) - 4503599627370496.0; }
 SVO_D unsigned byteAt(unsigned w, int i) { return __byte_perm(w, 0u, 0x4440 | i); }
+// byte i of w as a double. SVO_ALIGN_I2F_MASK (A/B builds) selects, per tap column, the conversion instruction (I2F.F64.U8 with a byte
+// selector, conversion pipe) instead of the byte extraction + FP64 add above.
+#ifndef SVO_ALIGN_I2F_MASK
+#define SVO_ALIGN_I2F_MASK 31   // measured: 0.818 (none) -> 0.810 ms (all five columns) per 4096 pairs: the FP64 pipe is the shared one
+#endif
+template <int COL>
+SVO_D double tapToDouble(unsigned w, int i) {
+  if ((SVO_ALIGN_I2F_MASK >> COL) & 1) return (double)((w >> (8 * i)) & 0xffu);
+  return u8ToDouble(byteAt(w, i));
+}
 
 // cos(x) and sin(x)/x for y = x^2 <= 0.25 (Taylor to y^9: truncation < 1e-24), evaluated pairwise to keep the dependent chain short.
 SVO_D void cosSinc(double y, double& c, double& sc) {
