@@ -26,6 +26,8 @@ if has launches; then
       python bench.py --steps 2 --warmup 3 --batch 1184 > gpurun_out/${tag}_launches_bench.log 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches_paths.csv \
       python tools/prof_paths.py > gpurun_out/${tag}_launches_paths.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${tag}_launches_frontend.csv \
+      python tools/bench_frontend.py --pairs 8192 --steps 1 --warmup 1 > gpurun_out/${tag}_launches_frontend.log 2>&1
 fi
 if has ncu; then
   for k in ${NCU_KERNELS:-sparse_align_kernel pyr_down fast_level match_kernel..int.0 match_kernel..int.1 seed_step_kernel seed_match_kernel filter_seq_kernel scan_epipolar_kernel reproj_match reproj_sort pose_optimize_kernel edgelet_score edgelet_decode optimize_points_kernel stereo_commit corner_scatter_kernel}; do

@@ -49,13 +49,14 @@ try:
         print(f"| {k} | {v:.1f} |"); tot += v
     print(f"| **sum of device stages** | {tot:.1f} |")
     print(f"| host wall clock of the whole call, p50 (image H2D + pyramid + align + result D2H through the host-buffer C ABI) | {1e3 * lat['p50_ms_pair_e2e']:.1f} |")
-    print(f"| launch + staging (cudaMallocAsync temporaries, small H2D copies) + synchronisation overhead | {1e3 * lat['p50_ms_pair_e2e'] - tot:.1f} |")
+    print(f"| launch + staging (one packed H2D / D2H copy through the context's arena) + synchronisation overhead | {1e3 * lat['p50_ms_pair_e2e'] - tot:.1f} |")
     cb = b["cpu_baseline"]
     print(f"| reference CPU path ({cb['kind']}), single thread, p50 | {1e3 * cb['latency_ms_p50_single_thread']:.0f} |\n")
 except Exception as e:  # noqa: BLE001
     print(f"(no latency table: {e})\n")
 print("## tools/bench_kernels.py (per-path, CUDA events)\n```json\n" + rd("paths.jsonl") + "\n```\n")
-for name, what in (("launches_bench.csv", "bench.py --steps 2 --warmup 3 --batch 1184"), ("launches_paths.csv", "tools/prof_paths.py")):
+for name, what in (("launches_bench.csv", "bench.py --steps 2 --warmup 3 --batch 1184"), ("launches_paths.csv", "tools/prof_paths.py"),
+                   ("launches_frontend.csv", "tools/bench_frontend.py --pairs 8192 --steps 1 --warmup 1 (the configs[4] chain, 8192 stereo pairs)")):
     p = os.path.join(G, f"{tag}_{name}")
     if os.path.exists(p):
         print(f"## ncu launch list of `{what}` (gpu__time_duration.sum, cold-cache, serialised)\n" + cap(summarize_launches.main, p) + "\n")
