@@ -132,6 +132,52 @@ def test_reproject_match_batch_of_frames_and_ties(ctx, orc):
         assert s["n_matches"] > 5
 
 
+def test_progressive_matching_quotas_and_second_pass(ctx, orc):
+    """The matching is progressive (pass 1: quota + 25 % + 8 cells per frame in list order; a progress kernel lists the unvisited cells
+    that can still lie before the stop; pass 2). One call with eight frames whose quotas run from 1 to 120 over a large-motion scene
+    (many failed attempts, so pass 1 alone does not fill the larger quotas) and with occupied cells in front of the list: every entry's
+    status, order, slot, counters and the statistics equal the oracle's sequential walk."""
+    sc = synth.make_reproject_scene(6, n_cur=2, max_rot_deg=9.0, max_trans=0.5)
+    K = len(sc["kf_imgs"])
+    ref = capi.Pyramid(ctx, K, 752, 480, 5)
+    cur = capi.Pyramid(ctx, 2, 752, 480, 5)
+    ref.upload(np.stack(sc["kf_imgs"])); cur.upload(np.stack(sc["cur_imgs"]))
+    ref.build(); cur.build()
+    cam = capi.Camera.from_dict(sc["cam"])
+    ang = helpers.reproject_px_error_angle(sc["cam"])
+    max_n = 120
+    opt = capi.reprojector_options(max_n_features=max_n, px_error_angle=ang)
+    ef = np.ascontiguousarray(sc["entry_feat"], np.int32)
+    n_in = np.array([0, 0, 60, 60, 110, 119, 150, 30], np.int32)   # quotas 120, 120, 60, 60, 10, 1, 1 (already full), 90
+    F = len(n_in)
+    fidx = (np.arange(F) % 2).astype(np.int32)
+    rng = np.random.default_rng(4)
+    occ = (rng.uniform(size=(F, 416)) < np.array([0.0, 0.5, 0.0, 0.3, 0.0, 0.0, 0.2, 0.7])[:, None]).astype(np.uint8)
+    entry_begin = (np.arange(F + 1) * len(ef)).astype(np.int32)
+    occ_gpu = occ.copy()
+    res, st = capi.reproject_match(ctx, ref, cur, cam, cam, _gpu_tables(sc), np.ascontiguousarray(sc["cur_Ts"][fidx], np.float64), n_in,
+                                   entry_begin, np.tile(ef, F), occ_gpu, opt, cur_frame_idx=fidx)
+    keep = []
+    kfs = [orc.make_frame(orc.create_img_pyramid(im, 5), sc["cam"], helpers.IDENTITY7, T, keep=keep)
+           for im, T in zip(sc["kf_imgs"], sc["tables"]["kf_T_f_w"])]
+    oopt = orc.ReprojOptions(30, max_n, 1, 0, 0, 200.0, ang)
+    second_pass_needed = 0
+    for j in range(F):
+        cf = orc.make_frame(orc.create_img_pyramid(sc["cur_imgs"][fidx[j]], 5), sc["cam"], helpers.IDENTITY7, sc["cur_Ts"][fidx[j]], keep=keep)
+        o = occ[j].copy()
+        r, s = orc.reproject_match(kfs, sc["tables"], cf, ef, int(n_in[j]), o, oopt)
+        g = res[entry_begin[j]:entry_begin[j + 1]]
+        for k in helpers.REPROJ_INT_FIELDS:
+            assert np.array_equal(g[k], r[k]), (j, k, np.flatnonzero(g[k] != r[k])[:8])
+        assert np.abs(g["px"] - r["px"]).max() < PX_TOL
+        assert (st[j]["n_candidates"], st[j]["n_trials"], st[j]["n_matches"], st[j]["n_consumed"]) == \
+               (s["n_candidates"], s["n_trials"], s["n_matches"], s["n_consumed"]), j
+        assert np.array_equal(occ_gpu[j], o)
+        quota = max(1, max_n - int(n_in[j]))
+        second_pass_needed += int(s["n_trials"] + int((r["status"] == capi.REPROJ_SKIPPED).sum()) > quota + quota // 4 + 8)
+    assert second_pass_needed >= 2, "the case must exercise the second pass"
+
+
 def test_reproject_match_rejects_bad_arguments(ctx):
     sc = synth.make_reproject_scene(3, n_kfs=1, n_per_kf=20)
     ref = capi.Pyramid(ctx, 1, 752, 480, 5); cur = capi.Pyramid(ctx, 1, 752, 480, 5)
