@@ -280,7 +280,7 @@ __global__ void stereo_commit_kernel(const svo_match_out* match, const svo_featu
   }
 }
 
-int checkLevels(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const char* who) {
+[[maybe_unused]] int checkLevels(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const char* who) {
   if (!pyr) return SVO_FAIL(ctx, SVO_ERR_INVALID_ARG, who);
   return SVO_OK;
 }

@@ -62,7 +62,7 @@ constexpr int kMinBlocksHeavy = kThreads <= 96 ? 6 : (kThreads <= 128 ? 4 : 3);
 // 2 and 3 hold one warp of every resident CTA instead of two; moving the serial work there was measured on the B200: 0.888 ms
 // instead of 0.869 ms per 4096 pairs, so it stays on warp 0.)
 constexpr int kSerialWarp = 0;
-constexpr int kTimerTid = 32 * kSerialWarp;
+[[maybe_unused]] constexpr int kTimerTid = 32 * kSerialWarp;  // used by the profiling build (make timing)
 
 struct Ctl {
   SE3d T, T_old;
@@ -113,7 +113,7 @@ sparse_align_kernel(const AlignParams P) {
   const int stride = SLOTS ? SLOTS : P.slots;
   const int n_cams = P.n_cams;
   // per-warp accumulators: H | (c, xyz x c) per camera | g6 g7 | chi2 | n_meas | changed
-  const int iCM = NH, iG6 = NH + 6 * n_cams, iChi = iG6 + (ILLUM ? 2 : 0), iN = iChi + 1, iCh = iChi + 2, NV = iChi + 3;
+  const int iCM = NH, iG6 = NH + 6 * n_cams, iChi = iG6 + (ILLUM ? 2 : 0), iN = iChi + 1, NV = iChi + 3;
   double* s_xyz = smem;                          // [3][stride]
   double* s_aux = s_xyz + 3 * stride;            // [NAUX][stride]  1/z, or the 2x3 projection Jacobian
   double* s_red = s_aux + NAUX * stride;         // [NW][NV]
@@ -325,7 +325,6 @@ sparse_align_kernel(const AlignParams P) {
                 {
                   unsigned ra, rb;
                   loadRow5(img + (size_t)vi * pitch, ui, ra, rb);
-#pragma unroll
                   tp[0] = tapToDouble<0>(ra, 0); tp[1] = tapToDouble<1>(ra, 1); tp[2] = tapToDouble<2>(ra, 2); tp[3] = tapToDouble<3>(ra, 3); tp[4] = tapToDouble<4>(rb, 0);
                 }
                 double up[4], mid[6], low[6];
@@ -337,7 +336,6 @@ sparse_align_kernel(const AlignParams P) {
                 for (int y = 0; y < 4; ++y) {
                   unsigned na, nb;
                   loadRow5(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
-#pragma unroll
                   tn[0] = tapToDouble<0>(na, 0); tn[1] = tapToDouble<1>(na, 1); tn[2] = tapToDouble<2>(na, 2); tn[3] = tapToDouble<3>(na, 3); tn[4] = tapToDouble<4>(nb, 0);
 #pragma unroll
                   for (int x = (y < 3 ? 0 : 1); x < (y < 3 ? 6 : 5); ++x) low[x] = patchLoad(patch + patchIdx(x, y + 2) * stride);
