@@ -61,10 +61,20 @@ def load_peaks():
         return {}
 
 
-def roofline(kernel, bytes_per_unit, units, kernel_ms, peaks, note, traffic=None):
+def ncu_pipes(kernel):
+    """Pipe / issue utilisation of `kernel` in this round's `ncu --set full` capture (profiles/ncu_traffic.json): what the profiler says
+    bounds a kernel that is not memory bound. Shares measured under the profiler on the capture's workload, not live values."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return dict(j["kernels"][kernel]["pipes"], capture=j["capture"] + "/" + j["kernels"][kernel]["file"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def roofline(kernel, bytes_per_unit, units, kernel_ms, peaks, note, traffic=None, ncu=None):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_unit * units / (kernel_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "ncu": ncu,
             "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes_per_unit": bytes_per_unit, "units_per_launch": units,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "note": note}
 
@@ -601,7 +611,7 @@ def leg_headline(rig, sample_n=64):
                 "note": "new frames' level-0 images + feature arrays H2D from page-locked memory, results D2H, every step"},
         "roofline": roofline("sparse_align_kernel<ILL=0, ROBUST=0, DJ=0, SLOTS=180>", ALGO_BYTES_PER_PAIR, B, align_ms, rig.peaks,
                              "algorithmic bytes 247,044 B/pair; the kernel is FP64-issue / latency bound, not HBM bound (DESIGN.md 4b)",
-                             traffic=ncu_traffic("sparse_align_kernel", B)),
+                             traffic=ncu_traffic("sparse_align_kernel", B), ncu=ncu_pipes("sparse_align_kernel")),
         "parity_sampled": parity,
         "latency": {"p50_ms_pair_e2e": 1e3 * float(np.median(lat)), "p95_ms_pair_e2e": 1e3 * float(np.percentile(lat, 95)),
                     "p50_ms_align_call": 1e3 * float(np.median(lat_align)),
@@ -660,7 +670,7 @@ def leg_fast(rig):
            "roofline": roofline("fast_level_kernel<10> (+ key init / decode)", ALGO_BYTES_FAST_ONLY, B, ms_det, rig.peaks,
                                 "detection alone re-reads levels 0-2; the kernel is issue bound (DESIGN.md 4a); fused pyramid + detection "
                                 "moves %.0f GB/s of the 487,466 B/frame minimum" % (ALGO_BYTES_PER_FRAME * B / (ms_all * 1e-3) / 1e9),
-                                traffic=ncu_traffic("fast_level_kernel", B)),
+                                traffic=ncu_traffic("fast_level_kernel", B), ncu=ncu_pipes("fast_level_kernel")),
            "e2e": {"value": rig.world * B / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h_imgs.numel()),
                    "d2h_bytes_per_step": int(h_corners.numel())},
            "l2": "inputs larger than L2 (%.0f MB of level-0 images per step)" % (h_imgs.numel() / 1e6),
@@ -781,7 +791,8 @@ def leg_match(rig):
            "mean_epi_length_px": float(r1["epi_length_pyramid"].mean()),
            "roofline": roofline("match_kernel<0> + epipolar match kernels", 2 * ALGO_BYTES_PER_FEATURE, M, ms_step, rig.peaks,
                                 "333 B/feature compulsory per call; both calls are bound by issue slots (ordered float sums, per-feature control flow), not memory (DESIGN.md 4c)",
-                                traffic=(lambda a, b: None if a is None or b is None else a + b)(ncu_traffic("match_kernel<0>", M), ncu_traffic("match_kernel<1>", M))),
+                                traffic=(lambda a, b: None if a is None or b is None else a + b)(ncu_traffic("match_kernel<0>", M), ncu_traffic("match_kernel<1>", M)),
+                                ncu=ncu_pipes("match_kernel<0>")),
            "e2e": {"value": rig.world * M / (e2e_ms * 1e-3), "unit": "features/s",
                    "h2d_bytes_per_step": int(2 * (hft.numel() + sum(v.numel() * v.element_size() for v in h.values()))),
                    "d2h_bytes_per_step": int(h_out0.numel() + h_out1.numel()),

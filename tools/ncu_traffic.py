@@ -18,12 +18,45 @@ UNITS = {
     "match_kernel__int_0": ("match_kernel<0>", 64 * 2000, "features"),
     "match_kernel__int_1": ("match_kernel<1>", 64 * 2000, "features"),
     "filter_seq_kernel": ("filter_seq_kernel", 50000 * 16, "updates"),
+    "seed_match_kernel": ("seed_match_kernel", 12800, "work items (one observation wave)"),
+    "seed_step_kernel": ("seed_step_kernel", 12800, "seeds (one observation wave)"),
+    "reproj_match": ("reproj_match_kernel", 296, "frames"),
+    "pose_optimize_kernel": ("pose_optimize_kernel", 4736, "bundles"),
+    "edgelet_score": ("edgelet_score_kernel", 1184, "frames"),
 }
 
 
 def to_bytes(v, u):
     x = float(v.replace(",", ""))
     return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+
+
+PIPE_KEYS = {
+    "issue_slots_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "fp64_pipe_pct": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "alu_pipe_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "fma_pipe_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "lsu_pipe_pct": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "smem_wavefronts_pct": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "achieved_occupancy_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "active_threads_per_instruction": "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "warp_instructions": "smsp__inst_executed.sum",
+    "registers_per_thread": "launch__registers_per_thread",
+}
+
+
+def pipes(d):
+    """What the capture says bounds the kernel: pipe / issue utilisation of the captured launch (ncu --set full, under the profiler:
+    shares, not times)."""
+    out = {}
+    for k, m in PIPE_KEYS.items():
+        if m in d:
+            try:
+                out[k] = float(d[m][0].replace(",", ""))
+            except ValueError:
+                pass
+    return out
 
 
 def main(tag):
@@ -37,7 +70,7 @@ def main(tag):
         out["kernels"][key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "units_per_launch": units, "unit": unit,
                                "dram_bytes_per_unit": (rd + wr) / units, "kernel_name": d.get("Kernel Name", ("?", ""))[0][:120],
                                "duration_us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * {"us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(d["gpu__time_duration.sum"][1], 1),
-                               "file": f"{tag}_ncu_{stem}.ncu-rep"}
+                               "file": f"{tag}_ncu_{stem}.ncu-rep", "pipes": pipes(d)}
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     json.dump(out, open(path, "w"), indent=1)
     print(json.dumps(out, indent=1))
