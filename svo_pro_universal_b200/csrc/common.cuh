@@ -88,7 +88,7 @@ int svoFail(svo_cuda_ctx* ctx, int code, const char* what, const char* file, int
 
 // Staging of I/O arrays of a batched call. For SVO_MEM_DEVICE the caller's pointers are used in place; for SVO_MEM_HOST inputs are
 // copied to the device and outputs copied back in finish(). Arrays of at most kStageSmall bytes go through the context's staging arena
-// (packed into page-locked memory, one H2D copy issued by ready() right before the first launch, one D2H copy in finish()); larger ones
+// (packed into page-locked memory, one H2D copy issued by send() right before the first launch, one D2H copy in finish()); larger ones
 // are copied one by one from / to the caller's memory (which the caller may have page-locked for bandwidth) through stream-ordered
 // temporaries.
 class Stager {
@@ -125,8 +125,10 @@ class Stager {
   }
   // device scratch that lives until finish()
   void* scratch(size_t bytes) { return alloc(bytes); }
-  // Called by every entry point after its last in() / out() and before its first launch: sends the packed inputs; true = staging failed.
-  bool failed();
+  // Called by every entry point after its last in() / out() and before its first launch: sends the packed inputs (one H2D copy);
+  // false = an allocation or a copy of this call failed (the entry point then returns finish(), which reports it).
+  bool send();
+  bool failed() const { return failed_; }
   int finish();
 
  private:

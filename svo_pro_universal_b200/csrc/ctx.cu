@@ -40,12 +40,12 @@ void* Stager::arenaOut(void* p, size_t bytes) {
   out_used_ += padded;
   return d;
 }
-bool Stager::failed() {
+bool Stager::send() {
   if (arena_ && !sent_) {
     sent_ = true;
     if (in_used_ && cudaMemcpyAsync(ctx_->stage_dev, ctx_->stage_host, in_used_, cudaMemcpyHostToDevice, ctx_->stream) != cudaSuccess) failed_ = true;
   }
-  return failed_;
+  return !failed_;
 }
 void* Stager::alloc(size_t bytes) {
   void* d = nullptr;
@@ -62,7 +62,7 @@ void Stager::release() {
   if (arena_) { ctx_->stage_busy = false; arena_ = false; }
 }
 int Stager::finish() {
-  if (failed()) { release(); return SVO_FAIL(ctx_, SVO_ERR_OUT_OF_MEMORY, "staging allocation or copy failed"); }
+  if (!send()) { release(); return SVO_FAIL(ctx_, SVO_ERR_OUT_OF_MEMORY, "staging allocation or copy failed"); }
   if (mem_ == SVO_MEM_HOST) {
     if (out_used_)
       SVO_CUDA_TRY(ctx_, cudaMemcpyAsync(ctx_->stage_host + kStageHalf, ctx_->stage_dev + kStageHalf, out_used_, cudaMemcpyDeviceToHost, ctx_->stream));

@@ -290,7 +290,7 @@ int svo_cuda_update_filter_vogiatzis(svo_cuda_ctx* ctx, int n, const double* z, 
   const double* dm = st.in(mu_range, (size_t)n);
   double* ds = st.inout(state, (size_t)n * 4);
   uint8_t* dok = st.out(ok, (size_t)n);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   vogiatzis_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, dz, dt, dm, ds, dok);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -309,7 +309,7 @@ int svo_cuda_update_filter_seq(svo_cuda_ctx* ctx, int n, int n_obs, const double
   const double* dm = st.in(mu_range, (size_t)n);
   double* ds = st.inout(state, (size_t)n * 4);
   uint8_t* dok = st.out(ok, no);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   if (gaussian) filter_seq_kernel<true><<<(n + 63) / 64, 64, 0, ctx->stream>>>(n, n_obs, dz, dt, dm, ds, dok);
   else filter_seq_kernel<false><<<(n + 63) / 64, 64, 0, ctx->stream>>>(n, n_obs, dz, dt, dm, ds, dok);
   SVO_LAUNCH_CHECK(ctx);
@@ -326,7 +326,7 @@ int svo_cuda_compute_tau(svo_cuda_ctx* ctx, int n, const double* T_ref_cur, cons
   const double* df = st.in(f, (size_t)n * 3);
   const double* dz = st.in(z, (size_t)n);
   double* dtau = st.out(tau, (size_t)n);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   compute_tau_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, dT, df, dz, px_error_angle, dtau);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -373,7 +373,7 @@ int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const 
   uint8_t* d_pending = (uint8_t*)st.scratch((size_t)(S > 0 ? S : 1));
   int* d_list = (int*)st.scratch(sizeof(int) * (size_t)(S > 0 ? S : 1));
   int* d_counts = (int*)st.scratch(sizeof(int) * (size_t)(n_obs + 1));
-  if (st.failed() || !d_work || !d_pending || !d_list || !d_counts) return st.finish();
+  if (!st.send() || !d_work || !d_pending || !d_list || !d_counts) return st.finish();
   SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_ns, 0, sizeof(int), ctx->stream));
   if (S > 0 && n_obs > 0) {
     SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)(n_obs + 1), ctx->stream));

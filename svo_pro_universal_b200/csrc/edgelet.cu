@@ -451,7 +451,7 @@ int svo_cuda_edgelet_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int firs
   const uint8_t* d_occ = st.in(occupancy_in, n);
   svo_corner* d_out = st.out(corners_out, n);
   unsigned long long* keys = (unsigned long long*)st.scratch(n * sizeof(unsigned long long));
-  if (st.failed() || !keys) return st.finish();
+  if (!st.send() || !keys) return st.finish();
   const int rc2 = edgeletDeviceImpl(ctx, pyr, first, count, threshold, border, cell_size, d_occ, d_out, keys);
   if (rc2 != SVO_OK) return rc2;
   return st.finish();
@@ -462,7 +462,7 @@ int svo_cuda_angle_histogram_bins(svo_cuda_ctx* ctx, int8_t* bins_out, svo_mem m
   SVO_BIND(ctx);
   Stager st(ctx, mem);
   int8_t* d = st.out(bins_out, (size_t)511 * 511);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   angle_bin_table_kernel<<<(511 * 511 + 255) / 256, 256, 0, ctx->stream>>>(d);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -487,7 +487,7 @@ int svo_cuda_fastgrad_detect(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fir
   svo_corner* d_edge = st.out(edgelets_out, n);
   unsigned long long* keys = (unsigned long long*)st.scratch(n * sizeof(unsigned long long));
   uint8_t* d_occ2 = (uint8_t*)st.scratch(n);
-  if (st.failed() || !keys || !d_occ2) return st.finish();
+  if (!st.send() || !keys || !d_occ2) return st.finish();
   int rc2 = svoFastDetectImpl(ctx, pyr, first, count, opt, d_occ, d_fast, SVO_MEM_DEVICE);
   if (rc2 != SVO_OK) return rc2;
   fastgrad_merge_kernel<<<count, 128, 0, ctx->stream>>>(d_fast, d_occ, n_cells, opt->threshold, max_n_features, d_occ2);

@@ -452,7 +452,7 @@ int svoFastDetectImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int
   const uint8_t* d_occ = st.in(occupancy_in, n);
   svo_corner* d_out = st.out(corners_out, n);
   unsigned long long* keys = (unsigned long long*)st.scratch(n * sizeof(unsigned long long));
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   fast_keys_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys, n, opt->threshold);
   SVO_LAUNCH_CHECK(ctx);
   const PyrView v = makeView(pyr);
@@ -492,7 +492,7 @@ int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fra
   Stager st(ctx, mem);
   int16_t* d_sc = st.out(score_map, n);
   uint8_t* d_nm = st.out(nonmax_map, n);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   FastParams P;
   P.min_level = level; P.max_level = level; P.threshold = threshold; P.border = 0; P.cell_size = 1; P.n_cols = 1; P.n_cells = 1;
   P.first = frame; P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
@@ -520,7 +520,7 @@ int svo_cuda_fast_corner_list(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fr
   svo_fast_xy* d_xy = xy_out ? (host ? (svo_fast_xy*)st.scratch(cap * sizeof(svo_fast_xy)) : xy_out) : nullptr;
   int* d_scores = scores_out ? (host ? (int*)st.scratch(cap * sizeof(int)) : scores_out) : nullptr;
   uint8_t* d_nonmax = nonmax_out ? (host ? (uint8_t*)st.scratch(cap) : nonmax_out) : nullptr;
-  if (st.failed() || !d_sc || !d_nm || !d_chunk) return SVO_FAIL(ctx, SVO_ERR_OUT_OF_MEMORY, "svo_cuda_fast_corner_list: scratch allocation failed");
+  if (!st.send() || !d_sc || !d_nm || !d_chunk) return SVO_FAIL(ctx, SVO_ERR_OUT_OF_MEMORY, "svo_cuda_fast_corner_list: scratch allocation failed");
   FastParams P;
   P.min_level = level; P.max_level = level; P.threshold = threshold; P.border = 0; P.cell_size = 1; P.n_cols = 1; P.n_cells = 1;
   P.first = frame; P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
@@ -558,7 +558,7 @@ int svo_cuda_fast_corner_score(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int f
   Stager st(ctx, mem);
   const svo_fast_xy* d_xy = st.in(xy, (size_t)n);
   int* d_sc = st.out(scores_out, (size_t)n);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   const uint8_t* img = pyr->data[level] + pyr->frame_stride[level] * (size_t)frame;
   if (arc_length == 9) corner_score_kernel<9><<<(n + 127) / 128, 128, 0, ctx->stream>>>(img, pyr->cols[level], pyr->rows[level], (int)pyr->pitch[level], d_xy, n, threshold, d_sc);
   else corner_score_kernel<10><<<(n + 127) / 128, 128, 0, ctx->stream>>>(img, pyr->cols[level], pyr->rows[level], (int)pyr->pitch[level], d_xy, n, threshold, d_sc);
@@ -581,7 +581,7 @@ int svo_cuda_fast_nonmax_3x3(svo_cuda_ctx* ctx, int n, const svo_fast_xy* xy, co
   int* d_idx = host ? (int*)st.scratch((size_t)n * sizeof(int)) : nonmax_idx_out;
   uint8_t* d_keep = (uint8_t*)st.scratch((size_t)n);
   int* d_chunk = (int*)st.scratch((size_t)(n_chunks + 1) * sizeof(int));
-  if (st.failed() || !d_idx || !d_keep || !d_chunk) return SVO_FAIL(ctx, SVO_ERR_OUT_OF_MEMORY, "svo_cuda_fast_nonmax_3x3: scratch allocation failed");
+  if (!st.send() || !d_idx || !d_keep || !d_chunk) return SVO_FAIL(ctx, SVO_ERR_OUT_OF_MEMORY, "svo_cuda_fast_nonmax_3x3: scratch allocation failed");
   list_nonmax_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_xy, d_sc, n, d_keep);
   SVO_LAUNCH_CHECK(ctx);
   flag_count_kernel<uint8_t><<<n_chunks, 256, 0, ctx->stream>>>(d_keep, n, d_chunk);

@@ -163,7 +163,7 @@ extern "C" int svo_cuda_align_pyr2d(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_p
   P.px_ref = st.in(px_ref_level_0, (size_t)M * 2);
   P.px_cur = st.inout(px_cur, (size_t)M * 2);
   P.status = st.out(status, (size_t)M);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   klt_pyr2d_kernel<<<(M + kKltWarps - 1) / kKltWarps, kKltThreads, 0, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();

@@ -308,7 +308,7 @@ int svo_cuda_align2d(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const int* fram
   P.px = st.inout(px, (size_t)M * 2);
   P.h_inv = nullptr;
   P.converged = st.out(converged, (size_t)M);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   align_only_kernel<<<(M + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -333,7 +333,7 @@ int svo_cuda_align1d(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const int* fram
   P.px = st.inout(px, (size_t)M * 2);
   P.h_inv = st.out(h_inv, (size_t)M);
   P.converged = st.out(converged, (size_t)M);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   align_only_kernel<<<(M + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -367,7 +367,7 @@ static int matchCommon(int mode, svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr,
   P.search_level_out = st.out(sl_out, (size_t)M);
   P.pwb_out = st.out(pwb_out, (size_t)M * 100);
   P.ok_out = st.out(ok_out, (size_t)M);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   const int grid = (M + kGroupsPerCta - 1) / kGroupsPerCta;
   if (mode == 0) match_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(P);
   else if (mode == 1 && P.opt.scan_on_unit_sphere) match_kernel<1, 1><<<grid, kThreads, 0, ctx->stream>>>(P);
@@ -410,7 +410,7 @@ int svo_cuda_scan_epipolar_line(svo_cuda_ctx* ctx, const svo_cuda_pyr* cur_pyr, 
   P.opt = *opt;
   P.image_best = st.out(image_best, (size_t)M * 2);
   P.zmssd_best = st.inout(zmssd_best, (size_t)M);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   scan_epipolar_kernel<<<(M + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();
@@ -485,7 +485,7 @@ int svo_cuda_stereo_triangulate(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr0, con
   int* d_ep = (int*)st.scratch(sizeof(int) * (size_t)(n_features > 0 ? n_features : 1));
   int* d_succ = (int*)st.scratch(sizeof(int) * (size_t)B);
   uint8_t* d_done = (uint8_t*)st.scratch((size_t)B);
-  if (st.failed() || !d_shared || !d_e0 || !d_e1 || !d_match || !d_ep || !d_succ || !d_done) return st.finish();
+  if (!st.send() || !d_shared || !d_e0 || !d_e1 || !d_match || !d_ep || !d_succ || !d_done) return st.finish();
   SVO_CUDA_TRY(ctx, cudaMemcpyAsync(d_shared, h_shared, sizeof(h_shared), cudaMemcpyHostToDevice, ctx->stream));
   if (n_features > 0) {
     stereo_entry_frames_kernel<<<B, 128, 0, ctx->stream>>>(d_begin, d_f0, d_f1, d_e0, d_e1, d_ep);

@@ -134,7 +134,7 @@ extern "C" int svo_cuda_optimize_points(svo_cuda_ctx* ctx, int P, double* pos, c
   const double* d_f = st.in(obs_f, (size_t)n_obs * 3);
   const double* d_T = st.in(T_f_w, (size_t)n_frames * 7);
   int* d_it = st.out(iters_out, (size_t)P);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   optimize_points_kernel<<<(P + 127) / 128, 128, 0, ctx->stream>>>(P, d_pos, d_begin, d_frame, d_f, d_T, n_iter, using_bearing_vector, d_it);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();

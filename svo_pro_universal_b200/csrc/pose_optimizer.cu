@@ -502,7 +502,7 @@ extern "C" int svo_cuda_pose_optimize(svo_cuda_ctx* ctx, int n_cams, const svo_c
   P.prior_q = st.in(prior_q, (size_t)B * 4);
   P.results = st.out(results, (size_t)B);
   P.outlier = st.out(outlier, (size_t)n_features);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
   pose_optimize_kernel<<<B, kThreads, 0, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   return st.finish();

@@ -658,7 +658,7 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   P.work_item = (int*)st.scratch((size_t)F * P.n_cells * sizeof(int));
   P.work_count = (int*)st.scratch(sizeof(int));
   P.n_cand = (int*)st.scratch((size_t)F * sizeof(int));
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
 
   const int per_frame_cap = mem == SVO_MEM_HOST ? [&] { int m = 1; for (int j = 0; j < F; ++j) m = std::max(m, entry_begin[j + 1] - entry_begin[j]); return m; }()
                                                 : kMaxPerFrame;

@@ -784,7 +784,7 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   P.eligible = st.in(eligible, nf);
   P.priors = st.in(priors, (size_t)B);
   P.results = st.out(results, (size_t)B);
-  if (st.failed()) return st.finish();
+  if (!st.send()) return st.finish();
 
   cudaError_t e;
   const bool unit = (float)opt->alpha_init == 0.0f && (float)opt->beta_init == 0.0f;  // residual uses float alpha/beta
