@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) seed_step_kernel(const SeedParams P,
                                                              int* __restrict__ list, int* __restrict__ counts) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  bool active = false;
+  bool active = false, edge_item = false;
   int n_ok = 0;
   if (s < P.S) {
     int type = P.types[s];
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kThreads) seed_step_kernel(const SeedParams P,
             w.result = -1; w.px_x = 0.0; w.px_y = 0.0;
             work[s] = w;
             active = true;
+            edge_item = w.align_1d != 0;
           }
         }
       }
@@ -175,14 +176,24 @@ __global__ void __launch_bounds__(kThreads) seed_step_kernel(const SeedParams P,
       sp[1] = make_double2(st[2], st[3]);
     }
   }
-  // compact work list of this wave (one atomic per warp; the order inside a warp is the seed order)
-  const unsigned bal = __ballot_sync(0xffffffffu, active);
-  if (bal) {
+  // Compact work list of this wave, two-ended: edgelet seeds (1-D alignment) fill it from the front, corner seeds (2-D alignment) from
+  // the back, so that the four items of a warp of the match kernel run the same alignment code (a warp with both kinds executes
+  // both, one after the other). One atomic per warp and kind; the order inside a warp is the seed order.
+  const bool edge = active && edge_item;
+  const unsigned balA = __ballot_sync(0xffffffffu, active && edge), balB = __ballot_sync(0xffffffffu, active && !edge);
+  if (balA) {
     int base = 0;
-    const int leader = __ffs((int)bal) - 1;
-    if (lane == leader) base = atomicAdd(&counts[o], __popc(bal));
+    const int leader = __ffs((int)balA) - 1;
+    if (lane == leader) base = atomicAdd(&counts[2 * o], __popc(balA));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (active) list[base + __popc(bal & ((1u << lane) - 1u))] = s;
+    if (active && edge) list[base + __popc(balA & ((1u << lane) - 1u))] = s;
+  }
+  if (balB) {
+    int base = 0;
+    const int leader = __ffs((int)balB) - 1;
+    if (lane == leader) base = atomicAdd(&counts[2 * o + 1], __popc(balB));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (active && !edge) list[P.S - 1 - (base + __popc(balB & ((1u << lane) - 1u)))] = s;
   }
   const unsigned okb = __ballot_sync(0xffffffffu, n_ok != 0);
   if (okb && lane == 0) atomicAdd(P.n_success, __popc(okb));
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 4) seed_match_kernel(const SeedParam
   const Group g = makeGroup();
   const int gi = threadIdx.x / kGroup;
   const int k = blockIdx.x * kGroupsPerCta + gi;
-  if (k >= counts[o]) return;
+  if (k >= P.S || (k >= counts[2 * o] && k < P.S - counts[2 * o + 1])) return;  // front: edgelet seeds, back: corner seeds
   const int s = list[k];
   uint8_t* pwb = s_pwb + gi * kPwbPitch;
   SeedWork& w = work[s];
@@ -372,11 +383,11 @@ int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const 
   SeedWork* d_work = (SeedWork*)st.scratch(sizeof(SeedWork) * (size_t)(S > 0 ? S : 1));
   uint8_t* d_pending = (uint8_t*)st.scratch((size_t)(S > 0 ? S : 1));
   int* d_list = (int*)st.scratch(sizeof(int) * (size_t)(S > 0 ? S : 1));
-  int* d_counts = (int*)st.scratch(sizeof(int) * (size_t)(n_obs + 1));
+  int* d_counts = (int*)st.scratch(sizeof(int) * 2 * (size_t)(n_obs + 1));  // per wave: edgelet items (front of the list), corner items (back)
   if (!st.send() || !d_work || !d_pending || !d_list || !d_counts) return st.finish();
   SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_ns, 0, sizeof(int), ctx->stream));
   if (S > 0 && n_obs > 0) {
-    SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)(n_obs + 1), ctx->stream));
+    SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * 2 * (size_t)(n_obs + 1), ctx->stream));
     const int step_grid = (S + kThreads - 1) / kThreads, match_grid = (S + kGroupsPerCta - 1) / kGroupsPerCta;
     for (int o = 0; o <= n_obs; ++o) {
       seed_step_kernel<<<step_grid, kThreads, 0, ctx->stream>>>(P, o, d_work, d_pending, d_list, d_counts);

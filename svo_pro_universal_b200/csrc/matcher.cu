@@ -31,6 +31,7 @@ struct MatchParams {
   int depth_shared;        // one (estimate, min, max) inverse-depth triple for all features
   // progressive matching (svo_cuda_stereo_triangulate): entry i belongs to list entry_pair[i]; only the entries at list positions
   // [chunk_lo, chunk_hi) of lists that are not done yet are matched by this launch
+  const int* perm;         // group k works on feature perm[k] (features grouped by type and level), or null: k itself
   const int* entry_pair;
   const int* pair_begin;
   const uint8_t* pair_done;
@@ -61,8 +62,9 @@ __global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P)
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
   const Group g = makeGroup();
   const int gi = threadIdx.x / kGroup;
-  const int i = blockIdx.x * kGroupsPerCta + gi;
-  if (i >= P.M) return;
+  const int k_item = blockIdx.x * kGroupsPerCta + gi;
+  if (k_item >= P.M) return;
+  const int i = P.perm ? P.perm[k_item] : k_item;
   if (MODE == 1 && P.entry_pair) {
     const int b = P.entry_pair[i], pos = i - P.pair_begin[b];
     if (pos < P.chunk_lo || pos >= P.chunk_hi || P.pair_done[b]) return;
@@ -102,6 +104,92 @@ __global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P)
       P.ok_out[i] = ok ? 1 : 0;
     }
     for (int k = g.r; k < 100; k += kGroup) P.pwb_out[100 * (size_t)i + k] = pwb[k];
+  }
+}
+
+// ---- work order of a large matcher call --------------------------------------------------------------------------------------
+// The four features of a warp run in lock-step only while they are in the same code: an edgelet (1-D alignment, edgelet filter) next to
+// a corner (2-D alignment) makes the warp execute both, and features of different pyramid levels diverge in the warp / scan loops.
+// Measured on the B200 (512 k features, 25 % edgelets, levels 0-2): findMatchDirect 1.195 ms in the caller's order, 0.954 ms grouped by
+// (type, level); the epipolar search 1.314 -> 1.184 ms. The grouping is a stable counting sort of the feature INDICES over 16 buckets
+// (order inside a bucket = the caller's order, which keeps the features of a frame together: a random order costs the epipolar search
+// 16 %); results are written by feature index, so callers see no difference.
+constexpr int kOrderChunk = 1024, kOrderBuckets = 16, kOrderMinFeatures = 16384;
+SVO_D int orderBucket(const svo_feature& f) { return (isEdgeletType(f.type) ? 0 : 8) + min(max(f.level, 0), 7); }
+
+__global__ void __launch_bounds__(256) order_count_kernel(const svo_feature* __restrict__ ftrs, int M, int n_chunks, int* __restrict__ counts) {
+  __shared__ int s_c[kOrderBuckets];
+  if (threadIdx.x < kOrderBuckets) s_c[threadIdx.x] = 0;
+  __syncthreads();
+  for (int j = 0; j < kOrderChunk / 256; ++j) {
+    const int i = blockIdx.x * kOrderChunk + j * 256 + threadIdx.x;
+    if (i < M) atomicAdd(&s_c[orderBucket(ftrs[i])], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kOrderBuckets) counts[threadIdx.x * n_chunks + blockIdx.x] = s_c[threadIdx.x];  // bucket-major: scanned in (bucket, chunk) order
+}
+
+// exclusive scan of a[0..n) in place (one CTA)
+__global__ void __launch_bounds__(1024) order_scan_kernel(int* a, int n) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int v = i < n ? a[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      s_w[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    if (i < n) a[i] = carry + (warp ? s_w[warp - 1] : 0) + inc - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + s_w[31];
+    __syncthreads();
+  }
+}
+
+// stable scatter: thread t of a chunk owns 4 consecutive features; per bucket an exclusive prefix over the threads (four buckets at a
+// time in the 16-bit lanes of one 64-bit word: a chunk holds at most 1024 features of a bucket)
+__global__ void __launch_bounds__(256) order_scatter_kernel(const svo_feature* __restrict__ ftrs, int M, int n_chunks, const int* __restrict__ offsets,
+                                                            int* __restrict__ perm) {
+  __shared__ unsigned long long s_w[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * kOrderChunk + 4 * tid;
+  int key[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) key[j] = i0 + j < M ? orderBucket(ftrs[i0 + j]) : -1;
+  for (int q = 0; q < kOrderBuckets / 4; ++q) {
+    unsigned long long c = 0ull;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (key[j] >= 0 && (key[j] >> 2) == q) c += 1ull << (16 * (key[j] & 3));
+    unsigned long long inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();  // s_w of the previous round has been read
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned long long base = inc - c;
+    for (int w = 0; w < warp; ++w) base += s_w[w];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (key[j] >= 0 && (key[j] >> 2) == q) {
+        const int b = key[j], sh = 16 * (b & 3);
+        const int rank = (int)((base >> sh) & 0xFFFFull);
+        perm[offsets[b * n_chunks + blockIdx.x] + rank] = i0 + j;
+        base += 1ull << sh;
+      }
   }
 }
 
@@ -367,7 +455,24 @@ static int matchCommon(int mode, svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr,
   P.search_level_out = st.out(sl_out, (size_t)M);
   P.pwb_out = st.out(pwb_out, (size_t)M * 100);
   P.ok_out = st.out(ok_out, (size_t)M);
-  if (!st.send()) return st.finish();
+  int* d_perm = nullptr;
+  int* d_counts = nullptr;
+  const int n_chunks = (M + kOrderChunk - 1) / kOrderChunk;
+  const bool ordered = (mode == 0 || mode == 1) && M >= kOrderMinFeatures;
+  if (ordered) {
+    d_perm = (int*)st.scratch(sizeof(int) * (size_t)M);
+    d_counts = (int*)st.scratch(sizeof(int) * (size_t)kOrderBuckets * n_chunks);
+  }
+  if (!st.send() || (ordered && (!d_perm || !d_counts))) return st.finish();
+  if (ordered) {
+    order_count_kernel<<<n_chunks, 256, 0, ctx->stream>>>(P.ftrs, M, n_chunks, d_counts);
+    SVO_LAUNCH_CHECK(ctx);
+    order_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, kOrderBuckets * n_chunks);
+    SVO_LAUNCH_CHECK(ctx);
+    order_scatter_kernel<<<n_chunks, 256, 0, ctx->stream>>>(P.ftrs, M, n_chunks, d_counts, d_perm);
+    SVO_LAUNCH_CHECK(ctx);
+    P.perm = d_perm;
+  }
   const int grid = (M + kGroupsPerCta - 1) / kGroupsPerCta;
   if (mode == 0) match_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(P);
   else if (mode == 1 && P.opt.scan_on_unit_sphere) match_kernel<1, 1><<<grid, kThreads, 0, ctx->stream>>>(P);

@@ -46,6 +46,7 @@ struct ReprojParams {
   svo_matcher_options mopt;
   double px_error_angle;
   int F, n_cells, n_cols;
+  int frame0;          // first frame of this launch (grids with the frame in blockIdx.y cover at most 65535 frames per launch)
   const int* cur_frame_idx;
   const double* cur_T_f_w;
   const int* n_features_in;
@@ -83,7 +84,7 @@ SVO_D unsigned long long orderedDouble(double v) {
 
 // ---- stage 1: getCandidate ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) reproj_candidates_kernel(const ReprojParams P) {
-  const int j = blockIdx.y;
+  const int j = P.frame0 + (int)blockIdx.y;
   int base;
   const int n = frameEntries(P, j, &base);
   const int n_all = P.entry_begin[j + 1] - base;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, FULL ? SVO_REPROJ_MINB : 4) reproj_m
   const int total = mode == 1 ? *P.resume_count : (mode == 2 ? *P.work_count : 0);
   for (int k0 = blockIdx.x * kGroupsPerCta; mode == 0 || k0 < total; k0 += gridDim.x * kGroupsPerCta) {
   int item = k0 + gi;
-  int j = mode == 0 ? (int)blockIdx.y : 0;
+  int j = mode == 0 ? P.frame0 + (int)blockIdx.y : 0;
   int q = 0, q_end = 0;
   unsigned cell = 0;
   bool occupied = false;
@@ -663,8 +664,12 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   const int per_frame_cap = mem == SVO_MEM_HOST ? [&] { int m = 1; for (int j = 0; j < F; ++j) m = std::max(m, entry_begin[j + 1] - entry_begin[j]); return m; }()
                                                 : kMaxPerFrame;
   if (n_entries > 0) {
-    reproj_candidates_kernel<<<dim3((per_frame_cap + 255) / 256, F), 256, 0, ctx->stream>>>(P);
-    SVO_LAUNCH_CHECK(ctx);
+    for (int f0 = 0; f0 < F; f0 += 65535) {  // grid.y limit
+      P.frame0 = f0;
+      reproj_candidates_kernel<<<dim3((per_frame_cap + 255) / 256, std::min(65535, F - f0)), 256, 0, ctx->stream>>>(P);
+      SVO_LAUNCH_CHECK(ctx);
+    }
+    P.frame0 = 0;
   }
   int npad = 32;
   while (npad < per_frame_cap) npad <<= 1;
@@ -676,10 +681,14 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
   reproj_sort_kernel<<<F, kSortThreads, sort_smem, ctx->stream>>>(P);
   SVO_LAUNCH_CHECK(ctx);
   const int items = opt->max_n_features <= 0 ? per_frame_cap : P.n_cells;
-  const dim3 mgrid((items + kGroupsPerCta - 1) / kGroupsPerCta, F);
+  const dim3 mgrid((items + kGroupsPerCta - 1) / kGroupsPerCta, 1);
   if (opt->max_n_features <= 0) {  // unlimited: one candidate per item, every kind of candidate
-    reproj_match_kernel<true><<<mgrid, kThreads, 0, ctx->stream>>>(P, items, 0);
-    SVO_LAUNCH_CHECK(ctx);
+    for (int f0 = 0; f0 < F; f0 += 65535) {
+      P.frame0 = f0;
+      reproj_match_kernel<true><<<dim3(mgrid.x, std::min(65535, F - f0)), kThreads, 0, ctx->stream>>>(P, items, 0);
+      SVO_LAUNCH_CHECK(ctx);
+    }
+    P.frame0 = 0;
   } else {
     // Progressive matching. Pass 1 visits, per frame, the cells whose first candidates come first in list order — as many as the
     // frame's quota of new features plus a margin — with the direct-match kernel, then the full kernel on the queues that reached an
@@ -687,12 +696,16 @@ extern "C" int svo_cuda_reproject_match(svo_cuda_ctx* ctx, const svo_cuda_pyr* r
     // kernels on that list. The reference makes ~125 attempts per frame on the bench scenes (120 successes); matching every non-empty
     // cell at once made ~330.
     const int first_items = std::min(P.n_cells, opt->max_n_features + opt->max_n_features / 4 + 8);
-    const dim3 grid1((first_items + kGroupsPerCta - 1) / kGroupsPerCta, F);
+    const dim3 grid1((first_items + kGroupsPerCta - 1) / kGroupsPerCta, 1);
     const int list_grid = ctx->sm_count * 8;  // grid-stride over lists whose length is known only on the device
     SVO_CUDA_TRY(ctx, cudaMemsetAsync(P.resume_count, 0, sizeof(int), ctx->stream));
     SVO_CUDA_TRY(ctx, cudaMemsetAsync(P.work_count, 0, sizeof(int), ctx->stream));
-    reproj_match_kernel<false><<<grid1, kThreads, 0, ctx->stream>>>(P, first_items, 0);
-    SVO_LAUNCH_CHECK(ctx);
+    for (int f0 = 0; f0 < F; f0 += 65535) {
+      P.frame0 = f0;
+      reproj_match_kernel<false><<<dim3(grid1.x, std::min(65535, F - f0)), kThreads, 0, ctx->stream>>>(P, first_items, 0);
+      SVO_LAUNCH_CHECK(ctx);
+    }
+    P.frame0 = 0;
     reproj_match_kernel<true><<<list_grid, kThreads, 0, ctx->stream>>>(P, 0, 1);
     SVO_LAUNCH_CHECK(ctx);
     reproj_progress_kernel<<<F, 256, 0, ctx->stream>>>(P);

@@ -169,6 +169,34 @@ def test_find_epipolar_match_direct(ctx, orc, kw):
     assert np.median(rel) < 0.1  # the search finds the true surface
 
 
+def test_large_call_work_order(ctx, orc):
+    """Calls with >= 16384 features are worked on grouped by (type, level) — a stable counting sort of the feature indices on the device —
+    and written back by feature index: 17 shuffled copies of a 1200-feature set (20400 features, types and levels interleaved) give, copy
+    by copy, exactly the records of the small (unordered) call, for both Matcher entry points."""
+    ms = synth.make_match_set(13, n_features=1200, max_rot_deg=1.0, max_trans=0.25)
+    ref, cur, rf, cf, keep = _setup(ctx, orc, ms)
+    cam = capi.Camera.from_dict(ms["cam"])
+    gopt = capi.matcher_options()
+    n = len(ms["px"])
+    rng = np.random.default_rng(8)
+    inv = 1.0 / ms["depth"]
+    est = inv * rng.uniform(0.7, 1.4, n)
+    spread = rng.uniform(0.1, 0.8, n) * inv
+    d_inv = np.ascontiguousarray(np.stack([est, est + spread, np.maximum(est - spread, 1e-8)], 1))
+    ft = capi.make_features(ms["px"], ms["f"], ms["grad"], ms["type"], ms["level"])
+    guess = np.ascontiguousarray(ms["px_guess"])
+    small0 = capi.find_match_direct(ctx, ref, cur, cam, cam, ms["T_cur_ref"], ft, ms["depth"], guess, gopt)
+    small1 = capi.find_epipolar_match_direct(ctx, ref, cur, cam, cam, ms["T_cur_ref"], ft, d_inv, gopt)
+    idx = np.concatenate([rng.permutation(n) for _ in range(17)])
+    assert len(idx) >= 16384 and len(np.unique(ms["type"])) >= 2 and len(np.unique(ms["level"])) >= 2
+    big0 = capi.find_match_direct(ctx, ref, cur, cam, cam, ms["T_cur_ref"], np.ascontiguousarray(ft[idx]), np.ascontiguousarray(ms["depth"][idx]),
+                                  np.ascontiguousarray(guess[idx]), gopt)
+    big1 = capi.find_epipolar_match_direct(ctx, ref, cur, cam, cam, ms["T_cur_ref"], np.ascontiguousarray(ft[idx]), np.ascontiguousarray(d_inv[idx]), gopt)
+    assert big0.tobytes() == small0[idx].tobytes()
+    assert big1.tobytes() == small1[idx].tobytes()
+    assert (small0["result"] == 0).sum() > 0.5 * n and (small1["result"] == 0).sum() > 0.3 * n
+
+
 def test_per_feature_frame_and_transform_indices(ctx, orc):
     """Features of several frame pairs in one launch (ref/cur frame index + T index per feature)."""
     sets = [synth.make_match_set(s, n_features=200) for s in (21, 22, 23)]
