@@ -80,7 +80,10 @@ struct SeedWork {
 // Wave o (0 <= o <= n_obs), one thread per seed: finish observation o - 1 of the seeds that had a match pending, then prepare
 // observation o. Between the two halves the seed's type and state are exactly what the sequential loop of the reference holds
 // between two updateSeed calls.
-__global__ void __launch_bounds__(kThreads) seed_step_kernel(const SeedParams P, int o, SeedWork* __restrict__ work, uint8_t* __restrict__ pending,
+#ifndef SVO_SEED_STEP_MINB
+#define SVO_SEED_STEP_MINB 1   // 6 / 8 CTAs per SM (80 / 64 registers) measured: no gain (6.93 -> 7.09 / 7.12 ms per 3.2 M seed-observations)
+#endif
+__global__ void __launch_bounds__(kThreads, SVO_SEED_STEP_MINB) seed_step_kernel(const SeedParams P, int o, SeedWork* __restrict__ work, uint8_t* __restrict__ pending,
                                                              int* __restrict__ list, int* __restrict__ counts) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;

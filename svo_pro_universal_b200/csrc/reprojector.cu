@@ -299,7 +299,10 @@ SVO_D int firstPassCells(const ReprojParams& P, int j) {
 // of the direct-match pass (resume_cell / resume_q); mode 2: the work list of the second pass (work_item). The list modes run as a
 // grid-stride loop over lists whose length is known only on the device.
 template <bool FULL>
-__global__ void __launch_bounds__(kThreads, FULL ? SVO_REPROJ_MINB : 4) reproj_match_kernel(const ReprojParams P, int items_per_frame, int mode) {
+#ifndef SVO_REPROJ_DIRECT_MINB
+#define SVO_REPROJ_DIRECT_MINB 5   // chain stage per 16384 frames: 3 CTAs / SM 9.62 ms, 4 (128 registers) 8.32 ms, 5 (96) 8.04 ms
+#endif
+__global__ void __launch_bounds__(kThreads, FULL ? SVO_REPROJ_MINB : SVO_REPROJ_DIRECT_MINB) reproj_match_kernel(const ReprojParams P, int items_per_frame, int mode) {
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
   const Group g = makeGroup();
   const int gi = threadIdx.x / kGroup;
