@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(kThreads, SVO_SEED_STEP_MINB) seed_step_kernel
 
 // One 8-lane group per work item of wave o: affine warp of the reference patch, ZMSSD scan, sub-pixel alignment.
 template <int SCAN>
-__global__ void __launch_bounds__(kThreads, 4) seed_match_kernel(const SeedParams P, int o, SeedWork* __restrict__ work, const int* __restrict__ list,
+#ifndef SVO_SEED_MATCH_MINB
+#define SVO_SEED_MATCH_MINB 5   // 3.2 M seed-observations: 6.94 ms at 4 CTAs / SM, 6.40 at 5, 6.45 at 6
+#endif
+__global__ void __launch_bounds__(kThreads, SVO_SEED_MATCH_MINB) seed_match_kernel(const SeedParams P, int o, SeedWork* __restrict__ work, const int* __restrict__ list,
                                                                  const int* __restrict__ counts) {
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
   const Group g = makeGroup();

@@ -57,8 +57,12 @@ SVO_D void writeOut(const Group& g, svo_match_out* out, int i, const MatchState&
 
 // mode 0: findMatchDirect, 1: findEpipolarMatchDirect, 2: warp only; SCAN: the epipolar scan compiled in (1 sphere, 0 plane)
 template <int MODE, int SCAN = 2>
-// 126 registers, 4 CTAs/SM: fastest of 4/5/6 on the B200 (1.58 / 2.94 ms for 512 k features)
-__global__ void __launch_bounds__(kThreads, 4) match_kernel(const MatchParams P) {
+// Resident CTAs per SM the register allocation is held to, per mode (512 k features on the B200, work grouped by type and level):
+// findMatchDirect 1.084 / 0.973 / 0.948 ms at 4 / 5 / 6, epipolar search 1.342 / 1.289 / 1.335 ms (round 1, ungrouped work: 4 was best).
+#ifndef SVO_MATCH_MINB
+#define SVO_MATCH_MINB (MODE == 0 ? 6 : 5)
+#endif
+__global__ void __launch_bounds__(kThreads, SVO_MATCH_MINB) match_kernel(const MatchParams P) {
   __shared__ __align__(16) uint8_t s_pwb[kGroupsPerCta * kPwbPitch];
   const Group g = makeGroup();
   const int gi = threadIdx.x / kGroup;

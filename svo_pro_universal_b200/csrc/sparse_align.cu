@@ -52,7 +52,11 @@ static_assert(kThreads % 32 == 0 && kWarps >= 1 && kWarps <= 8, "kThreads");
 constexpr int kThreadsWide = 2 * kThreads;
 constexpr int kMaxWarps = kThreadsWide / 32;
 // resident CTAs per SM the register allocation is held to: (common case, variants with more per-thread state)
+#ifdef SVO_ALIGN_MINB
+constexpr int kMinBlocks = SVO_ALIGN_MINB;
+#else
 constexpr int kMinBlocks = kThreads <= 96 ? 7 : (kThreads <= 128 ? 6 : 4);
+#endif
 #ifdef SVO_ALIGN_HEAVY_MINB
 constexpr int kMinBlocksHeavy = SVO_ALIGN_HEAVY_MINB;
 #else
