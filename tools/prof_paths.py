@@ -62,6 +62,15 @@ dinv = np.stack([est, est + spread, np.maximum(est - spread, 1e-8)], 1)
 for _ in range(REPS):
     r = capi.find_epipolar_match_direct(ctx, ref, cur, cam, cam, T, ft, dinv, mopt, ref_frame_idx=fidx, cur_frame_idx=fidx, T_idx=fidx)
 print("epipolar success", float((r["result"] == 0).mean()))
+if SMALL:  # the grouped work order of large calls (>= 16384 features: counting sort of the feature indices) under the sanitizer as well
+    rep_o = -(-16400 // len(ft))
+    big = lambda a: np.ascontiguousarray(np.concatenate([a] * rep_o)[:16400])
+    rb = capi.find_match_direct(ctx, ref, cur, cam, cam, T, big(ft), big(cat("depth")), big(cat("px_guess")), mopt, ref_frame_idx=big(fidx),
+                                cur_frame_idx=big(fidx), T_idx=big(fidx))
+    re_ = capi.find_epipolar_match_direct(ctx, ref, cur, cam, cam, T, big(ft), big(dinv), mopt, ref_frame_idx=big(fidx), cur_frame_idx=big(fidx), T_idx=big(fidx))
+    print("ordered large call: results equal the small call's", bool(np.array_equal(rb["result"][:len(ft)], capi.find_match_direct(
+        ctx, ref, cur, cam, cam, T, ft, cat("depth"), cat("px_guess"), mopt, ref_frame_idx=fidx, cur_frame_idx=fidx, T_idx=fidx)["result"])),
+        bool(np.array_equal(re_["result"][:len(ft)], r["result"])))
 # Matcher::scanEpipolarLine on its own: the long segments of the call above with their warped patches (svo_cuda_warp_affine)
 long_ = np.flatnonzero(r["epi_length_pyramid"] >= 2.0)[: (64 if SMALL else 20000)]
 if len(long_):
