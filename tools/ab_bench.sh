@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B: bash tools/gpu_r03b.sh <tag> <paths> lib...
+# A/B of alternative builds of libsvo_cuda (make -C svo_pro_universal_b200/csrc variant ...) through bench.py legs on the GPU box:
+#   bash tools/ab_bench.sh <tag> <comma-separated bench paths> libsvo_cuda.so libsvo_cuda_<variant>.so ...
 tag=$1; paths=$2; shift; shift
 mkdir -p gpurun_out
 L=$PWD/svo_pro_universal_b200
