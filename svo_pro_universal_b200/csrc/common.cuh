@@ -30,6 +30,7 @@ struct svo_cuda_ctx {
   // Staging arena of SVO_MEM_HOST calls (Stager): one page-locked host buffer and one device buffer, halves for inputs / outputs. The small
   // arrays of a call travel in ONE copy each way instead of one cudaMallocAsync + one pageable copy per array (single-frame latency).
   uint8_t* stage_host = nullptr;
+  uint8_t* stage_host_dev = nullptr;  // device-side address of stage_host (mapped page-locked memory): small results are written there directly
   uint8_t* stage_dev = nullptr;
   bool stage_busy = false;       // claimed by the Stager of the call in progress (nested Stagers fall back to per-array staging)
   int8_t* angle_bins = nullptr;  // 511 x 511 orientation-histogram bins of every u8 central-difference gradient (edgelet.cu), built on first use
@@ -88,12 +89,16 @@ int svoFail(svo_cuda_ctx* ctx, int code, const char* what, const char* file, int
 
 // Staging of I/O arrays of a batched call. For SVO_MEM_DEVICE the caller's pointers are used in place; for SVO_MEM_HOST inputs are
 // copied to the device and outputs copied back in finish(). Arrays of at most kStageSmall bytes go through the context's staging arena
-// (packed into page-locked memory, one H2D copy issued by send() right before the first launch, one D2H copy in finish()); larger ones
+// (packed into page-locked memory, one H2D copy issued by send() right before the first launch, one D2H copy in finish() — none for
+// results of at most kZeroCopyOut bytes, which the kernels write into mapped host memory directly); larger ones
 // are copied one by one from / to the caller's memory (which the caller may have page-locked for bandwidth) through stream-ordered
 // temporaries.
 class Stager {
  public:
   static constexpr size_t kStageHalf = 128 * 1024, kStageSmall = 32 * 1024;
+  // write-only results of at most kZeroCopyOut bytes (outWriteOnly(); 16 KB of them per call) are written by the kernels straight into
+  // mapped page-locked host memory: a single-frame call then ends with a stream synchronisation, not with a copy + synchronisation
+  static constexpr size_t kZeroCopyOut = 4096, kZeroCopyRegion = 16 * 1024;
   Stager(svo_cuda_ctx* c, svo_mem m);
   ~Stager() { release(); }
   template <class T>
@@ -113,6 +118,14 @@ class Stager {
     if (!d) return nullptr;
     outs_.push_back({p, d, n * sizeof(T)});
     return (T*)d;
+  }
+  // out() for a result array that the kernels only WRITE, once per element (no read-back, no atomics): small ones are written straight
+  // into mapped page-locked host memory, so that the call ends with a stream synchronisation instead of a copy + synchronisation
+  template <class T>
+  T* outWriteOnly(T* p, size_t n) {
+    if (!p || mem_ == SVO_MEM_DEVICE || n == 0) return p;
+    if (void* z = zeroCopyOut(p, n * sizeof(T))) return (T*)z;
+    return out(p, n);
   }
   template <class T>
   T* inout(T* p, size_t n) {
@@ -136,12 +149,13 @@ class Stager {
   void* alloc(size_t bytes);
   void* arenaIn(const void* p, size_t bytes);
   void* arenaOut(void* p, size_t bytes);
+  void* zeroCopyOut(void* p, size_t bytes);
   void release();
   svo_cuda_ctx* ctx_;
   svo_mem mem_;
   bool failed_ = false;
   bool arena_ = false, sent_ = false;
-  size_t in_used_ = 0, out_used_ = 0;
+  size_t in_used_ = 0, out_used_ = 0, zc_used_ = 0;
   std::vector<void*> allocs_;
   std::vector<Out> outs_;        // per-array D2H copies
   std::vector<Out> arena_outs_;  // host pointer | offset into the arena's output half (as a pointer into stage_host) | bytes

@@ -16,9 +16,12 @@ Stager::Stager(svo_cuda_ctx* c, svo_mem m) : ctx_(c), mem_(m) {
     cudaSetDevice(c->device);
     void* h = nullptr;
     void* d = nullptr;
-    if (cudaHostAlloc(&h, 2 * kStageHalf, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaHostAlloc(&h, 2 * kStageHalf + kZeroCopyRegion, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
     if (cudaMalloc(&d, 2 * kStageHalf) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
+    void* hd = nullptr;
+    if (cudaHostGetDevicePointer(&hd, h, 0) != cudaSuccess) { cudaGetLastError(); hd = nullptr; }  // no mapping: results go through the device arena
     c->stage_host = (uint8_t*)h;
+    c->stage_host_dev = (uint8_t*)hd;
     c->stage_dev = (uint8_t*)d;
   }
   c->stage_busy = true;
@@ -30,6 +33,14 @@ void* Stager::arenaIn(const void* p, size_t bytes) {
   memcpy(ctx_->stage_host + in_used_, p, bytes);
   void* d = ctx_->stage_dev + in_used_;
   in_used_ += padded;
+  return d;
+}
+void* Stager::zeroCopyOut(void* p, size_t bytes) {
+  const size_t padded = (bytes + 15) & ~(size_t)15;
+  if (!arena_ || !ctx_->stage_host_dev || bytes > kZeroCopyOut || zc_used_ + padded > kZeroCopyRegion) return nullptr;
+  arena_outs_.push_back({p, ctx_->stage_host + 2 * kStageHalf + zc_used_, bytes});
+  void* d = ctx_->stage_host_dev + 2 * kStageHalf + zc_used_;
+  zc_used_ += padded;
   return d;
 }
 void* Stager::arenaOut(void* p, size_t bytes) {

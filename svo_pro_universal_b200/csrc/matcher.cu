@@ -454,7 +454,7 @@ static int matchCommon(int mode, svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr,
   P.depth = st.in(depth, (size_t)M * depth_per);
   P.px_guess = st.in(px_guess, (size_t)M * 2);
   if (opt) P.opt = *opt;
-  P.out = st.out(out, (size_t)M);
+  P.out = st.outWriteOnly(out, (size_t)M);
   P.A_out = st.out(A_out, (size_t)M * 4);
   P.search_level_out = st.out(sl_out, (size_t)M);
   P.pwb_out = st.out(pwb_out, (size_t)M * 100);
@@ -517,7 +517,7 @@ int svo_cuda_scan_epipolar_line(svo_cuda_ctx* ctx, const svo_cuda_pyr* cur_pyr, 
   P.patch_level = st.in(patch_level, (size_t)M);
   P.epi_length_pyramid = st.in(epi_length_pyramid, (size_t)M);
   P.opt = *opt;
-  P.image_best = st.out(image_best, (size_t)M * 2);
+  P.image_best = st.outWriteOnly(image_best, (size_t)M * 2);
   P.zmssd_best = st.inout(zmssd_best, (size_t)M);
   if (!st.send()) return st.finish();
   scan_epipolar_kernel<<<(M + kGroupsPerCta - 1) / kGroupsPerCta, kThreads, 0, ctx->stream>>>(P);

@@ -693,8 +693,11 @@ sparse_align_kernel(const AlignParams P) {
     if (ctl.n_total > 0) {
       int idx = 0;
       for (int a = 0; a < D; ++a)
-        for (int b = a; b < D; ++b) { r.H[a * 8 + b] = s_tot[idx]; r.H[b * 8 + a] = s_tot[idx]; ++idx; }
-      if (P.priors) for (int j = 0; j < 8; ++j) r.H[j * 8 + j] += ctl.I_prior[j];
+        for (int b = a; b < D; ++b) {  // (the result may live in mapped host memory: every element is written, none is read back)
+          const double h = s_tot[idx] + ((a == b && P.priors) ? ctl.I_prior[a] : 0.0);
+          r.H[a * 8 + b] = h; r.H[b * 8 + a] = h; ++idx;
+        }
+      if (P.priors) for (int j = D; j < 8; ++j) r.H[j * 8 + j] = ctl.I_prior[j];
     }
     r.n_tracked = ctl.n_total;
 #ifdef SVO_ALIGN_TIMING
@@ -787,7 +790,7 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   P.depth = st.in(depth, nf);
   P.eligible = st.in(eligible, nf);
   P.priors = st.in(priors, (size_t)B);
-  P.results = st.out(results, (size_t)B);
+  P.results = st.outWriteOnly(results, (size_t)B);
   if (!st.send()) return st.finish();
 
   cudaError_t e;
