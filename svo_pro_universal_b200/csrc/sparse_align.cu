@@ -101,12 +101,19 @@ struct Ctl {
 
 // ILL: 0 = no illumination parameters and alpha = beta = 0 (the subtraction of the reference pixel rides in the
 // interpolation's FMA chain), 1 = no illumination parameters but non-zero initial alpha/beta, 2 = gain and/or offset estimated.
-template <int ILL, bool ROBUST, bool DJ, int SLOTS>
-// (measured per variant on the B200, 4096 pairs: robust weights alone 1.473 ms at 3 CTAs / SM, 1.410 at 4; robust + illumination 3.19 at 3, 3.70 at 4)
-__global__ void __launch_bounds__(SLOTS ? kThreads : kThreadsWide, SLOTS ? ((DJ || (ROBUST && ILL == 2)) ? kMinBlocksHeavy : (ILL == 2 ? SVO_ALIGN_ILLUM_MINB : kMinBlocks))
-                                                                         : ((DJ || ROBUST) ? 1 : (ILL == 2 ? SVO_ALIGN_WIDE_ILLUM_MINB : 2)))
+// SPLIT2: two threads per patch (two of its four pixel rows each) on kThreadsWide threads — the latency variant for batches that leave
+// SMs idle anyway (B <= number of SMs): the residual pass of an iteration is a dependent chain per thread, half as long with half the
+// pixels. The gradient contributions are linear in the per-thread sums, so the two halves need no exchange: the warp reduction adds
+// them. Only the plain 6-DoF variant is instantiated with it.
+// (register caps measured per variant on the B200, 4096 pairs: robust weights alone 1.473 ms at 3 CTAs / SM, 1.410 at 4; robust + illumination 3.19 at 3, 3.70 at 4)
+template <int ILL, bool ROBUST, bool DJ, int SLOTS, bool SPLIT2 = false>
+__global__ void __launch_bounds__((SLOTS && !SPLIT2) ? kThreads : kThreadsWide,
+                                  SPLIT2 ? 1 : (SLOTS ? ((DJ || (ROBUST && ILL == 2)) ? kMinBlocksHeavy : (ILL == 2 ? SVO_ALIGN_ILLUM_MINB : kMinBlocks))
+                                                      : ((DJ || ROBUST) ? 1 : (ILL == 2 ? SVO_ALIGN_WIDE_ILLUM_MINB : 2))))
 sparse_align_kernel(const AlignParams P) {
-  constexpr int TH = SLOTS ? kThreads : kThreadsWide;  // threads of this variant
+  static_assert(!SPLIT2 || (!ROBUST && ILL != 2), "SPLIT2: per-patch weighted sums / illumination sums are not split");
+  constexpr int TH = (SLOTS && !SPLIT2) ? kThreads : kThreadsWide;  // threads of this variant
+  constexpr int NY = SPLIT2 ? 2 : 4;                                   // pixel rows of a patch per thread
   constexpr int NW = TH / 32;
   constexpr bool ILLUM = ILL == 2;
   constexpr bool unit_gain = ILL == 0;
@@ -287,8 +294,10 @@ sparse_align_kernel(const AlignParams P) {
         for (int k = lane; k < NV; k += 32) red[k] = 0.0;
         __syncwarp();
         const float alpha_f = ctl.alpha_f, beta_f = ctl.beta_f;
-        const int n_now = *n_total_s, n_round = ((n_now + TH - 1) / TH) * TH;
-        for (int s = tid; s < n_round; s += TH) {
+        const int n_now = *n_total_s, n_round = (((SPLIT2 ? 2 : 1) * n_now + TH - 1) / TH) * TH;
+        for (int st = tid; st < n_round; st += TH) {
+          const int s = SPLIT2 ? (st >> 1) : st;   // patch slot
+          const int y0 = SPLIT2 ? 2 * (st & 1) : 0;  // first of this thread's pixel rows
           bool vis = false;
           int c = 0;
           double gx = 0, gy = 0, chi = 0, g6 = 0, g7 = 0;
@@ -328,21 +337,22 @@ sparse_align_kernel(const AlignParams P) {
                 double tp[5], tn[5];
                 {
                   unsigned ra, rb;
-                  loadRow5(img + (size_t)vi * pitch, ui, ra, rb);
+                  loadRow5(img + (size_t)(vi + y0) * pitch, ui, ra, rb);
                   tp[0] = tapToDouble<0>(ra, 0); tp[1] = tapToDouble<1>(ra, 1); tp[2] = tapToDouble<2>(ra, 2); tp[3] = tapToDouble<3>(ra, 3); tp[4] = tapToDouble<4>(rb, 0);
                 }
                 double up[4], mid[6], low[6];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) up[x] = patchLoad(patch + patchIdx(x + 1, 0) * stride);
+                for (int x = 0; x < 4; ++x) up[x] = patchLoad(patch + (SPLIT2 ? patchIdxRt(x + 1, y0) : patchIdx(x + 1, 0)) * stride);
 #pragma unroll
-                for (int x = 0; x < 6; ++x) mid[x] = patchLoad(patch + patchIdx(x, 1) * stride);
+                for (int x = 0; x < 6; ++x) mid[x] = patchLoad(patch + (SPLIT2 ? patchIdxRt(x, y0 + 1) : patchIdx(x, 1)) * stride);
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
+                for (int y = 0; y < NY; ++y) {
                   unsigned na, nb;
-                  loadRow5(img + (size_t)(vi + y + 1) * pitch, ui, na, nb);
+                  loadRow5(img + (size_t)(vi + y0 + y + 1) * pitch, ui, na, nb);
                   tn[0] = tapToDouble<0>(na, 0); tn[1] = tapToDouble<1>(na, 1); tn[2] = tapToDouble<2>(na, 2); tn[3] = tapToDouble<3>(na, 3); tn[4] = tapToDouble<4>(nb, 0);
 #pragma unroll
-                  for (int x = (y < 3 ? 0 : 1); x < (y < 3 ? 6 : 5); ++x) low[x] = patchLoad(patch + patchIdx(x, y + 2) * stride);
+                  for (int x = (y < NY - 1 ? 0 : 1); x < (y < NY - 1 ? 6 : 5); ++x)  // the thread's last row is only a "below" row: x = 1..4
+                    low[x] = patchLoad(patch + (SPLIT2 ? patchIdxRt(x, y0 + y + 2) : patchIdx(x, y + 2)) * stride);
 #pragma unroll
                   for (int x = 0; x < 4; ++x) {
                     const double ref = mid[x + 1];
@@ -392,7 +402,8 @@ sparse_align_kernel(const AlignParams P) {
               }
             }
           }
-          if (s < n_now) s_cam[s] = (uint8_t)(c | (vis ? 0x80 : 0));  // only the slot's own thread writes it
+          if (SPLIT2) __syncwarp();  // both threads of a patch have read the slot's flags
+          if (s < n_now && y0 == 0) s_cam[s] = (uint8_t)(c | (vis ? 0x80 : 0));  // only the slot's own (first) thread writes it
           const bool changed = (iter == 0) || (vis != vis_before);
           const unsigned visb = __ballot_sync(0xffffffffu, vis);
           const unsigned chb = __ballot_sync(0xffffffffu, changed);
@@ -444,7 +455,7 @@ sparse_align_kernel(const AlignParams P) {
             }
           }
           if (lane == 0) {
-            red[iN] += 16.0 * __popc(visb);
+            red[iN] += (SPLIT2 ? 8.0 : 16.0) * __popc(visb);
             if (!ROBUST && chb) ctl.h_dirty = 1;  // benign race: every writer stores 1; read after the barrier, cleared by thread 0
           }
         }
@@ -721,11 +732,11 @@ inline size_t alignSmemBytes(int slots, int n_cams, bool illum, bool dj, int n_w
   return doubles * 8 + sizeof(Ctl) + (size_t)slots * 32 * sizeof(PatchT) + (size_t)slots * 5 + 16;
 }
 
-template <int ILL, bool ROBUST, bool DJ, int SLOTS>
+template <int ILL, bool ROBUST, bool DJ, int SLOTS, bool SPLIT2 = false>
 cudaError_t launchAlign(const AlignParams& P, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<ILL, ROBUST, DJ, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<ILL, ROBUST, DJ, SLOTS, SPLIT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  sparse_align_kernel<ILL, ROBUST, DJ, SLOTS><<<P.B, SLOTS ? kThreads : kThreadsWide, smem, stream>>>(P);
+  sparse_align_kernel<ILL, ROBUST, DJ, SLOTS, SPLIT2><<<P.B, (SLOTS && !SPLIT2) ? kThreads : kThreadsWide, smem, stream>>>(P);
   return cudaGetLastError();
 }
 template <int ILL, bool ROBUST>
@@ -768,7 +779,11 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   const bool illum = opt->estimate_illumination_gain || opt->estimate_illumination_offset;
   const bool robust = opt->robustification != 0;
   const bool dj = opt->use_distortion_jacobian != 0;
-  size_t smem = alignSmemBytes(slots, n_cams, illum, dj, (fixed ? kThreads : kThreadsWide) / 32);
+  const bool unit = (float)opt->alpha_init == 0.0f && (float)opt->beta_init == 0.0f;  // residual uses float alpha/beta
+  // few pairs (SMs idle anyway): the plain 6-DoF variant runs with two threads per patch (SVO_ALIGN_SPLIT=0 / 1 overrides: tests, A/B)
+  bool split = fixed && !illum && !robust && !dj && unit && B <= ctx->sm_count;
+  if (const char* e = getenv("SVO_ALIGN_SPLIT")) split = fixed && !illum && !robust && !dj && unit && atoi(e) != 0;
+  size_t smem = alignSmemBytes(slots, n_cams, illum, dj, ((fixed && !split) ? kThreads : kThreadsWide) / 32);
   if (const char* pad = getenv("SVO_ALIGN_PAD_SMEM")) smem += (size_t)atoi(pad);  // occupancy experiments only
   if (smem > 227 * 1024) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: n_cams*max_features exceeds the shared-memory capacity (~1380 features per bundle)");
   for (int c = 0; c < n_cams; ++c) {
@@ -794,8 +809,8 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   if (!st.send()) return st.finish();
 
   cudaError_t e;
-  const bool unit = (float)opt->alpha_init == 0.0f && (float)opt->beta_init == 0.0f;  // residual uses float alpha/beta
-  if (illum) e = robust ? launchAlignSel<2, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<2, false>(P, smem, ctx->stream, dj, fixed);
+  if (split) e = launchAlign<0, false, false, kFixedSlots, true>(P, smem, ctx->stream);
+  else if (illum) e = robust ? launchAlignSel<2, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<2, false>(P, smem, ctx->stream, dj, fixed);
   else if (unit) e = robust ? launchAlignSel<0, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<0, false>(P, smem, ctx->stream, dj, fixed);
   else e = robust ? launchAlignSel<1, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<1, false>(P, smem, ctx->stream, dj, fixed);
   ctx->launches++;

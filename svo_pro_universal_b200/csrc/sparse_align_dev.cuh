@@ -239,6 +239,8 @@ SVO_D void refreshCameraTransforms(const SE3d& T, double* camblk, int n_cams, in
 // (rows 0 and 5 keep only X = 1..4: the corners are never read)
 SVO_HD constexpr int patchIdx(int X, int Y) { return Y == 0 ? X - 1 : (Y == 5 ? 28 + X - 1 : 4 + (Y - 1) * 6 + X); }
 
+SVO_D int patchIdxRt(int X, int Y) { return Y == 0 ? X - 1 : (Y == 5 ? 27 + X : 4 + (Y - 1) * 6 + X); }  // patchIdx for run-time rows
+
 struct PatchSums {  // weighted sums over the 16 pixels of one patch
   double sxx, sxy, syy;                         // H pose block
   double sx6, sy6, sx7, sy7, s66, s67, s77;     // H illumination blocks

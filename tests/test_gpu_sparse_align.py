@@ -42,6 +42,24 @@ def test_default_options_batch(ctx, orc):
         assert dq < 2e-3 and dt < 5e-3  # and it lands near the synthetic ground truth
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_both_thread_mappings(ctx, orc, monkeypatch, split):
+    """The plain 6-DoF kernel exists with one thread per patch (throughput: large batches) and with two threads per patch (latency:
+    batches of at most one pair per SM, which is what the small parity cases are). SVO_ALIGN_SPLIT forces either: both must pass the
+    same parity checks on the same batch, and agree with each other to rounding."""
+    pairs = [synth.make_align_pair(s) for s in range(1, 9)]
+    gopt = capi.sparse_align_options()
+    monkeypatch.setenv("SVO_ALIGN_SPLIT", split)
+    res, _, _ = gpu_align(ctx, pairs, gopt)
+    _compare(orc, pairs, res, gopt)
+    monkeypatch.setenv("SVO_ALIGN_SPLIT", "1" if split == "0" else "0")
+    other, _, _ = gpu_align(ctx, pairs, gopt)
+    for a, b in zip(res, other):
+        assert list(a["iters"]) == list(b["iters"]) and a["n_tracked"] == b["n_tracked"]
+        dq, dt = pose_diff(a["T_icur_iref"], b["T_icur_iref"])
+        assert dq < 1e-7 and dt < 1e-11
+
+
 def test_subpixel_feature_positions(ctx, orc):
     """Features at sub-pixel positions (what the Reprojector's refined matches are): the interpolated reference patch values are then
     not representable in the kernel's FP32 patch cache, whose rounding (relative 2^-24 of a grey level) must stay far inside the
