@@ -104,14 +104,14 @@ struct Ctl {
 // SPLIT2: two threads per patch (two of its four pixel rows each) on kThreadsWide threads — the latency variant for batches that leave
 // SMs idle anyway (B <= number of SMs): the residual pass of an iteration is a dependent chain per thread, half as long with half the
 // pixels. The gradient contributions are linear in the per-thread sums, so the two halves need no exchange: the warp reduction adds
-// them. Only the plain 6-DoF variant is instantiated with it.
+// them. Instantiated for the fixed-slot variants without robust weights and without the distortion Jacobian.
 // (register caps measured per variant on the B200, 4096 pairs: robust weights alone 1.473 ms at 3 CTAs / SM, 1.410 at 4; robust + illumination 3.19 at 3, 3.70 at 4)
 template <int ILL, bool ROBUST, bool DJ, int SLOTS, bool SPLIT2 = false>
 __global__ void __launch_bounds__((SLOTS && !SPLIT2) ? kThreads : kThreadsWide,
                                   SPLIT2 ? 1 : (SLOTS ? ((DJ || (ROBUST && ILL == 2)) ? kMinBlocksHeavy : (ILL == 2 ? SVO_ALIGN_ILLUM_MINB : kMinBlocks))
                                                       : ((DJ || ROBUST) ? 1 : (ILL == 2 ? SVO_ALIGN_WIDE_ILLUM_MINB : 2))))
 sparse_align_kernel(const AlignParams P) {
-  static_assert(!SPLIT2 || (!ROBUST && ILL != 2), "SPLIT2: per-patch weighted sums / illumination sums are not split");
+  static_assert(!SPLIT2 || !ROBUST, "SPLIT2 is instantiated for the variants without robust weights (every per-pixel sum is linear, the split would be valid there too)");
   constexpr int TH = (SLOTS && !SPLIT2) ? kThreads : kThreadsWide;  // threads of this variant
   constexpr int NY = SPLIT2 ? 2 : 4;                                   // pixel rows of a patch per thread
   constexpr int NW = TH / 32;
@@ -780,9 +780,9 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   const bool robust = opt->robustification != 0;
   const bool dj = opt->use_distortion_jacobian != 0;
   const bool unit = (float)opt->alpha_init == 0.0f && (float)opt->beta_init == 0.0f;  // residual uses float alpha/beta
-  // few pairs (SMs idle anyway): the plain 6-DoF variant runs with two threads per patch (SVO_ALIGN_SPLIT=0 / 1 overrides: tests, A/B)
-  bool split = fixed && !illum && !robust && !dj && unit && B <= ctx->sm_count;
-  if (const char* e = getenv("SVO_ALIGN_SPLIT")) split = fixed && !illum && !robust && !dj && unit && atoi(e) != 0;
+  // few pairs (SMs idle anyway): the variants without robust weights / distortion Jacobian run with two threads per patch (SVO_ALIGN_SPLIT=0 / 1 overrides: tests, A/B)
+  bool split = fixed && !robust && !dj && B <= ctx->sm_count;
+  if (const char* e = getenv("SVO_ALIGN_SPLIT")) split = fixed && !robust && !dj && atoi(e) != 0;
   size_t smem = alignSmemBytes(slots, n_cams, illum, dj, ((fixed && !split) ? kThreads : kThreadsWide) / 32);
   if (const char* pad = getenv("SVO_ALIGN_PAD_SMEM")) smem += (size_t)atoi(pad);  // occupancy experiments only
   if (smem > 227 * 1024) return SVO_FAIL(ctx, SVO_ERR_TOO_MANY_FEATURES, "svo_cuda_sparse_align: n_cams*max_features exceeds the shared-memory capacity (~1380 features per bundle)");
@@ -809,7 +809,9 @@ extern "C" int svo_cuda_sparse_align(svo_cuda_ctx* ctx, int n_cams, const svo_cu
   if (!st.send()) return st.finish();
 
   cudaError_t e;
-  if (split) e = launchAlign<0, false, false, kFixedSlots, true>(P, smem, ctx->stream);
+  if (split) e = illum ? launchAlign<2, false, false, kFixedSlots, true>(P, smem, ctx->stream)
+                       : (unit ? launchAlign<0, false, false, kFixedSlots, true>(P, smem, ctx->stream)
+                               : launchAlign<1, false, false, kFixedSlots, true>(P, smem, ctx->stream));
   else if (illum) e = robust ? launchAlignSel<2, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<2, false>(P, smem, ctx->stream, dj, fixed);
   else if (unit) e = robust ? launchAlignSel<0, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<0, false>(P, smem, ctx->stream, dj, fixed);
   else e = robust ? launchAlignSel<1, true>(P, smem, ctx->stream, dj, fixed) : launchAlignSel<1, false>(P, smem, ctx->stream, dj, fixed);
