@@ -48,7 +48,13 @@ struct svo_cuda_pyr {
   // TMA descriptors (CUtensorMap, 128 opaque bytes) of the levels the pyramid kernel has read so far; built on first use
   alignas(64) unsigned char tmap[SVO_MAX_LEVELS][128] = {};
   bool tmap_ready[SVO_MAX_LEVELS] = {false};
+  // the same tensors with the FAST kernel's box (tile + halo), built on first use
+  alignas(64) mutable unsigned char tmap_fast[SVO_MAX_LEVELS][128] = {};
+  mutable bool tmap_fast_ready[SVO_MAX_LEVELS] = {false};
 };
+// pyramid.cu: TMA descriptor of level l as a {pitch, rows, frames} u8 tensor with a box of box_w x box_h x 1 bytes, encoded once
+// (under a lock: a pyramid may be shared by contexts on several host threads) into map128 / *ready.
+int svoEnsureLevelMap(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int l, int box_w, int box_h, unsigned char* map128, bool* ready);
 
 // POD view of a pyramid batch passed to kernels by value.
 struct PyrView {
@@ -341,6 +347,30 @@ SVO_HD void camProject3Jac(const svo_camera& c, const V3d& p, double J[2][3]) {
 }
 SVO_HD double camAngleError(const svo_camera& c, double img_err) {
   return atan(img_err / (2.0 * c.fx)) + atan(img_err / (2.0 * c.fy));
+}
+
+// ---- mbarrier / TMA tile loads (pyramid.cu, fast.cu) ----------------------------------------------------------------------------
+SVO_D unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SVO_D void mbarInit(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+SVO_D void mbarExpectTx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+SVO_D void mbarWait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared TMA tile load of the map's {w, h, 1} box at (x, y, frame); out-of-tensor bytes are zero-filled and the full box
+// size is always completed on the barrier
+SVO_D void tmaLoadTile(unsigned dst, const void* tmap, int x, int y, int z, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
 // Bilinear tap loader: the 2 aligned 32-bit words covering bytes [x0, x0+8) of a row whose start is

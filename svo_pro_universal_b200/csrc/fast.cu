@@ -11,7 +11,7 @@
 // the pixel is a corner at barrier b iff margin >= b, and fast_corner_score_10 = max(b, margin).
 //
 // Kernel layout (one launch for all levels of all frames): a CTA owns a 128x32 interior tile of one level; the u8 tile
-// with a 4-pixel halo is staged in shared memory with 128-bit loads. Three compacting stages keep every
+// with a 4-pixel halo is staged in shared memory by one TMA box load. Three compacting stages keep every
 // lane busy on the rare pixels that need work:
 //   1. compass quick-reject on ALL pixels, 4 pixels per thread with byte SIMD (VABSDIFF4.U8 + carry compares): an arc
 //      of >= 9 circle pixels always contains two adjacent compass points, i.e. one of {N,S} and one of {E,W};
@@ -100,6 +100,9 @@ SVO_D unsigned quick4Wide(unsigned C, unsigned N, unsigned S, unsigned E, unsign
 inline unsigned divMagic(int d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned)d + 1ull); }
 SVO_D int divFast(int x, unsigned magic) { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
 
+// TMA descriptors of the levels one launch walks (box = kSPitch x kSRows bytes: tile + halo)
+struct FastMaps { alignas(64) unsigned char m[SVO_MAX_LEVELS][128]; };
+
 struct FastParams {
   int min_level, max_level, threshold, border, cell_size, n_cols, n_cells, first;
   int tile_base[SVO_MAX_LEVELS + 1];  // first tile index of every level inside blockIdx.x
@@ -113,9 +116,16 @@ struct FastParams {
 
 template <int ARC>
 // (A/B on the B200: minBlocks 6 = this, 7 / 8 force 32 registers and spill: 1.148 / 1.155 ms per 1024 frames)
-__global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, FastParams P) {
-  __shared__ __align__(16) uint8_t s_img[kSRows * kSPitch];
-  __shared__ __align__(16) short s_score[kTH * kTW];
+__global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, FastParams P, const __grid_constant__ FastMaps maps) {
+  __shared__ __align__(128) uint8_t s_img[kSRows * kSPitch];
+#ifndef SVO_FAST_STAGE_CPASYNC
+  __shared__ __align__(8) unsigned long long s_full;
+#endif
+  // score tile with a one-pixel zero frame: the 3x3 non-max reads its 8 neighbours without edge tests
+  // (B200, 1024 frames: 1.245 -> 1.162 ms; together with the flat candidate push 1.147 ms)
+  constexpr int kSW = kTW + 2, kScoreN = ((kTH + 2) * kSW + 7) / 8 * 8;
+#define SVO_SCORE_IDX(r, c) (((r) + 1) * kSW + (c) + 1)
+  __shared__ __align__(16) short s_score[kScoreN];
   __shared__ unsigned short s_cand[kTH * kTW];
   __shared__ unsigned short s_corner[kTH * kTW];
   __shared__ int s_ncand, s_ncorner;
@@ -124,12 +134,28 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
   while (L < P.max_level && (int)blockIdx.x >= P.tile_base[L + 1]) ++L;
   const int tile = blockIdx.x - P.tile_base[L];
   const int ty = divFast(tile, P.tiles_x_magic[L]), tx = tile - ty * P.tiles_x[L];
-  const int cols = v.cols[L], rows = v.rows[L], pitch = v.pitch[L];
+  const int cols = v.cols[L], rows = v.rows[L];
   const int frame_local = blockIdx.y;
-  const uint8_t* img = v.level(P.first + frame_local, L);
   const int x0 = tx * kTW, y0 = ty * kTH;
   const int thr = P.threshold;
 
+#ifndef SVO_FAST_STAGE_CPASYNC
+  // stage tile + halo with ONE TMA box load issued by thread 0 (bytes outside the {pitch, rows} plane arrive as zeros); the score tile
+  // is cleared while the copy is in flight. B200, pyramid + detect of 1024 frames: 1.147 ms with the 16-byte cp.async loop below, 1.083 ms so
+  if (tid == 0) {
+    const unsigned bar = smemAddr(&s_full);
+    mbarInit(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbarExpectTx(bar, kSRows * kSPitch);
+    tmaLoadTile(smemAddr(s_img), maps.m[L], x0 - kPadL, y0 - kHalo, P.first + frame_local, bar);
+  }
+  for (int i = tid; i < kScoreN * 2 / 16; i += kThreadsFast) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { s_ncand = 0; s_ncorner = 0; }
+  __syncthreads();  // barrier initialised, counters and score tile cleared
+  mbarWait(smemAddr(&s_full), 0u);
+#else
+  const int pitch = v.pitch[L];
+  const uint8_t* img = v.level(P.first + frame_local, L);
   // stage tile + halo with 16-byte cp.async (x0 - 16 and the row pitch are multiples of 16; chunks outside the image are zero-filled
   // through src-size 0); the score tile is cleared while the copies are in flight
   for (int i = tid; i < kSRows * (kSPitch / 16); i += kThreadsFast) {
@@ -140,10 +166,11 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
     const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_img[r * kSPitch + q * 16]);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
   }
-  for (int i = tid; i < kTH * kTW * 2 / 16; i += kThreadsFast) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kScoreN * 2 / 16; i += kThreadsFast) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) { s_ncand = 0; s_ncorner = 0; }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+#endif
 
   // stage 1: quick reject, one warp per tile row, 4 pixels per lane
   {
@@ -165,7 +192,17 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
       const unsigned ww = __funnelshift_r(wm, wc, 8);   // pixels x-3 .. x
       unsigned f = thr < 128 ? quick4(wc, wn, ws, we, ww, K) : quick4Wide(wc, wn, ws, we, ww, K2);
       f &= (gy >= 3 && gy < rows - 3) ? colmask : 0u;
-#ifndef SVO_FAST_WARP_PUSH1  // every lane with a candidate does its own shared-memory atomic and walks its bits
+#if !defined(SVO_FAST_PUSH_WALK) && !defined(SVO_FAST_WARP_PUSH1)  // own atomic per lane, the (up to four) candidates stored by predicated stores
+      if (f) {
+        const unsigned nib = (((f >> 7) * 0x00204081u) >> 21) & 15u;  // bit j = pixel j of the word
+        const int at = atomicAdd(&s_ncand, __popc(nib));
+        const unsigned short id0 = (unsigned short)((r << 7) | (4 * g));
+        if (nib & 1u) s_cand[at] = id0;
+        if (nib & 2u) s_cand[at + (nib & 1u)] = id0 + 1;
+        if (nib & 4u) s_cand[at + __popc(nib & 3u)] = id0 + 2;
+        if (nib & 8u) s_cand[at + __popc(nib & 7u)] = id0 + 3;
+      }
+#elif !defined(SVO_FAST_WARP_PUSH1)  // the same with a walk over the set bits (1.162 vs 1.147 ms per 1024 frames)
       if (f) {
         int at = atomicAdd(&s_ncand, __popc(f));
         const int id0 = (r << 7) | (4 * g);
@@ -207,7 +244,7 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
     const int r = idx >> 7, c = idx & 127;
     const int m = fastMargin<ARC>(&s_img[(r + kHalo) * kSPitch + kPadL + c], kSPitch);
     if (m >= thr) {  // score = max(threshold, margin) = margin; threshold >= 1 so 0 means "no corner"
-      s_score[idx] = (short)m;
+      s_score[SVO_SCORE_IDX(r, c)] = (short)m;
       s_corner[atomicAdd(&s_ncorner, 1)] = (unsigned short)idx;
     }
   }
@@ -229,7 +266,7 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
       if ((tid & 31) == 0) base = atomicAdd(&s_ncorner, __popc(bal));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (corner) {
-        s_score[idx] = (short)m;
+        s_score[SVO_SCORE_IDX(idx >> 7, idx & 127)] = (short)m;
         s_corner[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned short)idx;
       }
     }
@@ -241,7 +278,7 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
     for (int i = tid; i < kTH * kTW; i += kThreadsFast) {
       const int gy = y0 + (i >> 7), gx = x0 + (i & 127);
       if (gx >= cols || gy >= rows) continue;
-      if (P.score_map) P.score_map[(size_t)gy * cols + gx] = s_score[i];
+      if (P.score_map) P.score_map[(size_t)gy * cols + gx] = s_score[SVO_SCORE_IDX(i >> 7, i & 127)];
       if (P.nonmax_map) P.nonmax_map[(size_t)gy * cols + gx] = 0;
     }
     __syncthreads();
@@ -253,15 +290,15 @@ __global__ void __launch_bounds__(kThreadsFast) fast_level_kernel(PyrView v, Fas
     const int idx = s_corner[i];
     const int r = idx >> 7, c = idx & 127;
     const int gy = y0 + r, gx = x0 + c;
-    const int sc = s_score[idx];
+    const int si = SVO_SCORE_IDX(r, c);
+    const int sc = s_score[si];
     const bool edge = !(r > 0 && r < kTH - 1 && c > 0 && c < kTW - 1);
     bool keep = true;
 #pragma unroll
     for (int n = 0; n < 9; ++n) {  // neighbours inside the tile
       if (n == 4) continue;
       const int dr = n / 3 - 1, dc = n % 3 - 1;
-      const bool inside = !edge || ((unsigned)(r + dr) < (unsigned)kTH && (unsigned)(c + dc) < (unsigned)kTW);
-      if (inside && s_score[idx + dr * kTW + dc] >= sc) keep = false;
+      if (s_score[si + dr * kSW + dc] >= sc) keep = false;  // the frame holds 0 < threshold <= sc
     }
     if (keep && edge) {  // rare: neighbours that belong to other tiles are scored from the halo
 #pragma unroll 1
@@ -307,7 +344,14 @@ __global__ void fast_keys_decode_kernel(const unsigned long long* keys, size_t n
   out[i] = c;
 }
 
-int launchLevels(svo_cuda_ctx* ctx, const PyrView& v, FastParams& P, int arc, int count) {
+int launchLevels(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, const PyrView& v, FastParams& P, int arc, int count) {
+  FastMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int L = P.min_level; L <= P.max_level; ++L) {
+    const int rc = svoEnsureLevelMap(ctx, pyr, L, kSPitch, kSRows, pyr->tmap_fast[L], &pyr->tmap_fast_ready[L]);
+    if (rc != SVO_OK) return rc;
+    memcpy(maps.m[L], pyr->tmap_fast[L], 128);
+  }
   int n_tiles = 0;
   for (int L = 0; L <= SVO_MAX_LEVELS; ++L) P.tile_base[L] = 0;
   P.cell_magic = divMagic(P.cell_size);
@@ -325,8 +369,8 @@ int launchLevels(svo_cuda_ctx* ctx, const PyrView& v, FastParams& P, int arc, in
     if (Q.keys) Q.keys += (size_t)f0 * P.n_cells;
     if (Q.occupancy) Q.occupancy += (size_t)f0 * P.n_cells;
     dim3 grid(n_tiles, n, 1);
-    if (arc == 9) fast_level_kernel<9><<<grid, kThreadsFast, 0, ctx->stream>>>(v, Q);
-    else fast_level_kernel<10><<<grid, kThreadsFast, 0, ctx->stream>>>(v, Q);
+    if (arc == 9) fast_level_kernel<9><<<grid, kThreadsFast, 0, ctx->stream>>>(v, Q, maps);
+    else fast_level_kernel<10><<<grid, kThreadsFast, 0, ctx->stream>>>(v, Q, maps);
     SVO_LAUNCH_CHECK(ctx);
   }
   return SVO_OK;
@@ -506,7 +550,7 @@ int svoFastDetectImpl(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int first, int
   P.min_level = opt->min_level; P.max_level = opt->max_level; P.threshold = opt->threshold; P.border = opt->border;
   P.cell_size = opt->cell_size; P.n_cols = n_cols; P.n_cells = n_cells; P.first = first;
   P.keys = keys; P.occupancy = d_occ; P.score_map = nullptr; P.nonmax_map = nullptr;
-  const int rc = launchLevels(ctx, v, P, arc, count);
+  const int rc = launchLevels(ctx, pyr, v, P, arc, count);
   if (rc != SVO_OK) return rc;
   fast_keys_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys, n, opt->threshold, d_out);
   SVO_LAUNCH_CHECK(ctx);
@@ -542,7 +586,7 @@ int svo_cuda_fast_level_maps(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fra
   FastParams P;
   P.min_level = level; P.max_level = level; P.threshold = threshold; P.border = 0; P.cell_size = 1; P.n_cols = 1; P.n_cells = 1;
   P.first = frame; P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
-  const int rc = launchLevels(ctx, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
+  const int rc = launchLevels(ctx, pyr, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
   if (rc != SVO_OK) return rc;
   return st.finish();
 }
@@ -570,7 +614,7 @@ int svo_cuda_fast_corner_list(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int fr
   FastParams P;
   P.min_level = level; P.max_level = level; P.threshold = threshold; P.border = 0; P.cell_size = 1; P.n_cols = 1; P.n_cells = 1;
   P.first = frame; P.keys = nullptr; P.occupancy = nullptr; P.score_map = d_sc; P.nonmax_map = d_nm;
-  const int rc = launchLevels(ctx, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
+  const int rc = launchLevels(ctx, pyr, makeView(pyr), P, arc_length == 9 ? 9 : 10, 1);
   if (rc != SVO_OK) return rc;
   flag_count_kernel<short><<<n_chunks, 256, 0, ctx->stream>>>(d_sc, (int)n, d_chunk);
   SVO_LAUNCH_CHECK(ctx);

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <algorithm>
+#include <mutex>
 
 namespace {
 
@@ -43,28 +44,6 @@ constexpr int kTileW = 256, kTileH = 32;
 constexpr int kStages = 4;                        // shared-memory ring depth (tiles of loads in flight per CTA)
 constexpr int kTileBytes = kTileW * kTileH;       // 8 KB
 constexpr int kPyrThreads = 256;
-
-SVO_D unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-SVO_D void mbarInit(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-SVO_D void mbarExpectTx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-SVO_D void mbarWait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// global -> shared TMA tile load of one {kTileW, kTileH, 1} box at (x, y, frame); always completes kTileBytes on the barrier
-SVO_D void tmaLoadTile(unsigned dst, const CUtensorMap* tmap, int x, int y, int z, unsigned bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-               "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
 
 struct TileCoord { int frame, x0, y0; };
 // floor(x / d) for x * d < 2^32 as one multiply-high; magic = 0 stands for d == 1.
@@ -191,10 +170,12 @@ unsigned svoHalfsampleRoundMask(const svo_cuda_pyr* pyr) {
   return m;
 }
 
-// {pitch, rows, frames} u8 tensor of level l, box = one 256x32 tile; the driver entry point is fetched through the runtime
-// so that the library does not link against libcuda.
-static int ensureTensorMap(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int l) {
-  if (pyr->tmap_ready[l]) return SVO_OK;
+// {pitch, rows, frames} u8 tensor of level l with the caller's box (the pyramid kernel: one 256x32 tile; FAST: tile + halo); the driver
+// entry point is fetched through the runtime so that the library does not link against libcuda.
+int svoEnsureLevelMap(svo_cuda_ctx* ctx, const svo_cuda_pyr* pyr, int l, int box_w, int box_h, unsigned char* map128, bool* ready) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (*ready) return SVO_OK;
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn encode = nullptr;
@@ -207,13 +188,13 @@ static int ensureTensorMap(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int l) {
   }
   const cuuint64_t dims[3] = {(cuuint64_t)pyr->pitch[l], (cuuint64_t)pyr->rows[l], (cuuint64_t)pyr->n_frames};
   const cuuint64_t strides[2] = {(cuuint64_t)pyr->pitch[l], (cuuint64_t)pyr->frame_stride[l]};
-  const cuuint32_t box[3] = {kTileW, kTileH, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(pyr->tmap[l]), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr->data[l], dims, strides, box,
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr->data[l], dims, strides, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return SVO_FAIL(ctx, SVO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  pyr->tmap_ready[l] = true;
+  *ready = true;
   return SVO_OK;
 }
 
@@ -239,7 +220,7 @@ int svoPyrBuildLaunch(svo_cuda_ctx* ctx, svo_cuda_pyr* pyr, int first, int count
       SVO_CUDA_TRY(ctx, cudaFuncSetAttribute(pyr_down_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kTileBytes));
       ctx->attr_pyr = true;
     }
-    const int rc = ensureTensorMap(ctx, pyr, l0);
+    const int rc = svoEnsureLevelMap(ctx, pyr, l0, kTileW, kTileH, pyr->tmap[l0], &pyr->tmap_ready[l0]);
     if (rc != SVO_OK) return rc;
     TileGrid tg;
     tg.tiles_x = tiles_x; tg.tiles_per_frame = tiles_x * tiles_y; tg.n_items = (int)n_items;
