@@ -40,6 +40,8 @@ for _ in range(REPS):  # (f2): edgelet detector alone, then FastGrad (FAST + mer
 for _ in range(REPS):
     capi.fastgrad_detect(ctx, cur, capi.detector_options(), 100)
 del cur
+if os.environ.get("PROF_UNTIL") == "detect":  # pyramid + alignment + detectors only (a quick sanitizer pass after a detector change)
+    sys.exit(0)
 
 # (c): matcher paths
 NP, NF, NU = (2, 300, 2) if SMALL else (64, 2000, 4)
