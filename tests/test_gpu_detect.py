@@ -165,6 +165,22 @@ def test_fast_detector_cells_bit_exact(ctx, orc, kw):
         assert (got[i]["score"] > opt.threshold).sum() > 50
 
 
+def test_fast_detector_subrange_of_odd_sized_frames(ctx, orc):
+    """Frames [2, 4) of a batch whose size is no multiple of the tile (377 x 241, levels 0-2): the tile loads take the frame index and
+    the out-of-image halo from the level's tensor map, so a wrong frame offset or fill would show here."""
+    w, h = 377, 241
+    imgs = np.stack([synth.make_image(40 + s, w, h, n_rect=300) for s in range(5)])
+    opt = capi.detector_options(threshold=12, border=5, min_level=0, max_level=2, cell_size=24)
+    p = _gpu_pyr(ctx, imgs, 4)
+    got = capi.fast_detect(ctx, p, opt, first=2, count=2)
+    assert got.shape[0] == 2
+    for j, i in enumerate((2, 3)):
+        exp = orc.fast_detector(imgs[i], 4, -1, opt.threshold, opt.border, opt.min_level, opt.max_level, opt.cell_size)
+        for k in ("x", "y", "level", "score"):
+            assert np.array_equal(got[j][k], exp[k]), f"frame {i} field {k}"
+        assert (got[j]["score"] > opt.threshold).sum() > 20
+
+
 def test_fast_detector_occupancy_and_flat_image(ctx, orc):
     opt = capi.detector_options()
     img = synth.make_image(2)
