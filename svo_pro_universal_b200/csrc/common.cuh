@@ -33,6 +33,10 @@ struct svo_cuda_ctx {
   uint8_t* stage_host_dev = nullptr;  // device-side address of stage_host (mapped page-locked memory): small results are written there directly
   uint8_t* stage_dev = nullptr;
   bool stage_busy = false;       // claimed by the Stager of the call in progress (nested Stagers fall back to per-array staging)
+  // side streams + fork / join events of entry points that run independent parts of one call concurrently (depth_filter.cu: seed groups)
+  static constexpr int kSideStreams = 3;
+  cudaStream_t side_stream[kSideStreams] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {};
   int8_t* angle_bins = nullptr;  // 511 x 511 orientation-histogram bins of every u8 central-difference gradient (edgelet.cu), built on first use
   std::string last_error;
 };
@@ -79,6 +83,8 @@ inline PyrView makeView(const svo_cuda_pyr* p) {
 }
 
 int svoFail(svo_cuda_ctx* ctx, int code, const char* what, const char* file, int line);
+// ctx.cu: creates the context's side streams and events on first use (SVO_OK or an error code)
+int svoEnsureSideStreams(svo_cuda_ctx* ctx);
 #define SVO_FAIL(ctx, code, what) svoFail(ctx, code, what, __FILE__, __LINE__)
 #define SVO_CUDA_TRY(ctx, expr)                                                            \
   do {                                                                                     \

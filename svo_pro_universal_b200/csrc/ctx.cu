@@ -89,6 +89,16 @@ int Stager::finish() {
   return SVO_OK;
 }
 
+int svoEnsureSideStreams(svo_cuda_ctx* ctx) {
+  if (ctx->ev_fork) return SVO_OK;
+  for (int i = 0; i < svo_cuda_ctx::kSideStreams; ++i) {
+    SVO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side_stream[i], cudaStreamNonBlocking));
+    SVO_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+  }
+  SVO_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  return SVO_OK;
+}
+
 extern "C" {
 
 int svo_cuda_device_count(void) {
@@ -141,6 +151,11 @@ int svo_cuda_ctx_destroy(svo_cuda_ctx* ctx) {
   if (ctx->angle_bins) cudaFree(ctx->angle_bins);
   if (ctx->stage_dev) cudaFree(ctx->stage_dev);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  for (int i = 0; i < svo_cuda_ctx::kSideStreams; ++i) {
+    if (ctx->side_stream[i]) { cudaStreamSynchronize(ctx->side_stream[i]); cudaStreamDestroy(ctx->side_stream[i]); }
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return SVO_OK;

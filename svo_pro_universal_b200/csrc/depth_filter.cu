@@ -18,6 +18,7 @@
 //                         spent 71 % of its warp samples waiting for instructions) and the FP64 geometry is no longer computed
 //                         eight times per seed.
 #include "depth_filter_dev.cuh"
+#include <cstdlib>
 
 using namespace svo_dev;
 
@@ -48,11 +49,16 @@ __global__ void __launch_bounds__(256) compute_tau_kernel(int n, const double* _
 
 constexpr int kThreads = 128;
 constexpr int kGroupsPerCta = kThreads / kGroup;
+// Concurrent seed groups of one large svo_cuda_update_seeds call (env SVO_SEED_GROUPS overrides per call). B200, 50 k seeds x 64
+// observations: 1 group 5.89 ms, 2: 5.68, 3: 5.29, 4: 4.51, 6: 4.53, 8: 5.1-5.4 (the host cannot issue 1024 launches fast enough).
+constexpr int kSeedGroups = 4;
+constexpr int kSeedGroupMin = 16384;          // calls with fewer seeds stay on one stream
 
 struct SeedParams {
   PyrView ref_pyr, cur_pyr;
   svo_camera cam_ref, cam_cur;
-  int S, n_obs;
+  int S, n_obs;     // seeds of this group, observation waves
+  int s0, S_all;    // first seed of the group, seeds of the call (stride of the observation-major arrays)
   const int* ref_frame_idx;
   const svo_feature* ftrs;
   uint8_t* types;
@@ -85,11 +91,12 @@ struct SeedWork {
 #endif
 __global__ void __launch_bounds__(kThreads, SVO_SEED_STEP_MINB) seed_step_kernel(const SeedParams P, int o, SeedWork* __restrict__ work, uint8_t* __restrict__ pending,
                                                              int* __restrict__ list, int* __restrict__ counts) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = P.s0 + sl;
   const int lane = threadIdx.x & 31;
   bool active = false, edge_item = false;
   int n_ok = 0;
-  if (s < P.S) {
+  if (sl < P.S) {
     int type = P.types[s];
     double2* sp = reinterpret_cast<double2*>(P.state) + 2 * (size_t)s;
     const double2 s01 = sp[0], s23 = sp[1];
@@ -130,11 +137,11 @@ __global__ void __launch_bounds__(kThreads, SVO_SEED_STEP_MINB) seed_step_kernel
           n_ok = 1;
         }
       }
-      if (P.match_results) P.match_results[(size_t)(o - 1) * P.S + s] = mr;
+      if (P.match_results) P.match_results[(size_t)(o - 1) * P.S_all + s] = mr;
       dirty = true;
     }
     if (o < P.n_obs) {  // depth_filter.cpp:377-439 for observation o
-      const size_t oi = (size_t)o * P.S + s;
+      const size_t oi = (size_t)o * P.S_all + s;
       int mr = -1;
       const int cf = P.obs_frame_idx[oi];
       bool go = cf >= 0;  // :377-381 (cur frame == ref frame): the caller marks such observations with a negative index
@@ -365,7 +372,7 @@ int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const 
   P.cur_pyr = makeView(cur_pyr);
   P.cam_ref = *cam_ref;
   P.cam_cur = *cam_cur;
-  P.S = S; P.n_obs = n_obs;
+  P.S = S; P.n_obs = n_obs; P.s0 = 0; P.S_all = S;
   const size_t so = (size_t)S * n_obs;
   int n_T = 0;
   if (mem == SVO_MEM_HOST) {
@@ -389,20 +396,49 @@ int svo_cuda_update_seeds(svo_cuda_ctx* ctx, const svo_cuda_pyr* ref_pyr, const 
   SeedWork* d_work = (SeedWork*)st.scratch(sizeof(SeedWork) * (size_t)(S > 0 ? S : 1));
   uint8_t* d_pending = (uint8_t*)st.scratch((size_t)(S > 0 ? S : 1));
   int* d_list = (int*)st.scratch(sizeof(int) * (size_t)(S > 0 ? S : 1));
-  int* d_counts = (int*)st.scratch(sizeof(int) * 2 * (size_t)(n_obs + 1));  // per wave: edgelet items (front of the list), corner items (back)
+  // Seeds are independent, only the observations of ONE seed are ordered: large calls are cut into groups of seeds whose wave chains run
+  // on the context's side streams, so that the step kernel of one group (one thread per seed, long dependent FP64 chains, few warps) and
+  // the tail of its match kernel overlap the match kernels of the other groups.
+  int G = 1;
+  if (S >= kSeedGroupMin) G = kSeedGroups;
+  if (const char* e = getenv("SVO_SEED_GROUPS")) G = atoi(e);
+  G = G < 1 ? 1 : (G > 1 + svo_cuda_ctx::kSideStreams ? 1 + svo_cuda_ctx::kSideStreams : G);
+  if (S < G * kThreads) G = 1;
+  const size_t counts_per_group = 2 * (size_t)(n_obs + 1);
+  int* d_counts = (int*)st.scratch(sizeof(int) * counts_per_group * G);  // per group and wave: edgelet items (front of the list), corner items (back)
   if (!st.send() || !d_work || !d_pending || !d_list || !d_counts) return st.finish();
   SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_ns, 0, sizeof(int), ctx->stream));
   if (S > 0 && n_obs > 0) {
-    SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * 2 * (size_t)(n_obs + 1), ctx->stream));
-    const int step_grid = (S + kThreads - 1) / kThreads, match_grid = (S + kGroupsPerCta - 1) / kGroupsPerCta;
+    SVO_CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * counts_per_group * G, ctx->stream));
+    if (G > 1) {
+      const int rc = svoEnsureSideStreams(ctx);
+      if (rc != SVO_OK) { st.finish(); return rc; }
+      SVO_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+      for (int g = 1; g < G; ++g) SVO_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream[g - 1], ctx->ev_fork, 0));
+    }
+    const int chunk = ((S + G - 1) / G + kThreads - 1) / kThreads * kThreads;  // whole step CTAs per group
     for (int o = 0; o <= n_obs; ++o) {
-      seed_step_kernel<<<step_grid, kThreads, 0, ctx->stream>>>(P, o, d_work, d_pending, d_list, d_counts);
-      SVO_LAUNCH_CHECK(ctx);
-      if (o < n_obs) {
-        if (mopt->scan_on_unit_sphere) seed_match_kernel<1><<<match_grid, kThreads, 0, ctx->stream>>>(P, o, d_work, d_list, d_counts);
-        else seed_match_kernel<0><<<match_grid, kThreads, 0, ctx->stream>>>(P, o, d_work, d_list, d_counts);
+      for (int g = 0; g < G; ++g) {
+        SeedParams Q = P;
+        Q.s0 = g * chunk;
+        Q.S = S - Q.s0 < chunk ? S - Q.s0 : chunk;
+        if (Q.S <= 0) continue;
+        cudaStream_t stream = g == 0 ? ctx->stream : ctx->side_stream[g - 1];
+        int* list = d_list + Q.s0;
+        int* counts = d_counts + counts_per_group * g;
+        const int step_grid = (Q.S + kThreads - 1) / kThreads, match_grid = (Q.S + kGroupsPerCta - 1) / kGroupsPerCta;
+        seed_step_kernel<<<step_grid, kThreads, 0, stream>>>(Q, o, d_work, d_pending, list, counts);
         SVO_LAUNCH_CHECK(ctx);
+        if (o < n_obs) {
+          if (mopt->scan_on_unit_sphere) seed_match_kernel<1><<<match_grid, kThreads, 0, stream>>>(Q, o, d_work, list, counts);
+          else seed_match_kernel<0><<<match_grid, kThreads, 0, stream>>>(Q, o, d_work, list, counts);
+          SVO_LAUNCH_CHECK(ctx);
+        }
       }
+    }
+    for (int g = 1; g < G; ++g) {
+      SVO_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[g - 1], ctx->side_stream[g - 1]));
+      SVO_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g - 1], 0));
     }
   }
   return st.finish();

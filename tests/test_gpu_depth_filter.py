@@ -141,8 +141,15 @@ def test_compute_tau(ctx, orc):
 
 @pytest.mark.parametrize("dkw,mkw", [(dict(), dict()), (dict(check_convergence=1, seed_convergence_sigma2_thresh=50.0), dict()),
                                       (dict(use_vogiatzis_update=0), dict(scan_on_unit_sphere=0)), (dict(check_visibility=0), dict())])
-def test_update_seeds_full_chain(ctx, orc, dkw, mkw):
-    """depth_filter_utils::updateSeed over ordered observations: matcher + tau + filter + convergence flags."""
+@pytest.mark.parametrize("groups", [None, "1", "3", "4"])
+def test_update_seeds_full_chain(ctx, orc, dkw, mkw, groups, monkeypatch):
+    """depth_filter_utils::updateSeed over ordered observations: matcher + tau + filter + convergence flags. `groups`: the number of
+    concurrent seed groups a call is cut into (SVO_SEED_GROUPS, read per call; None = the library's choice for this size) — 3 leaves a
+    ragged last group; every grouping must give the oracle's result."""
+    if groups is None:
+        monkeypatch.delenv("SVO_SEED_GROUPS", raising=False)
+    else:
+        monkeypatch.setenv("SVO_SEED_GROUPS", groups)
     sq = synth.make_seed_sequence(17, n_seeds=600, n_obs=10)
     S, O = len(sq["px"]), len(sq["cur_imgs"])
     ref = capi.Pyramid(ctx, 1, 752, 480, 5)
