@@ -917,7 +917,7 @@ def leg_seeds(rig):
     assert np.allclose(g_fs[pick], fexp, rtol=1e-4, atol=0), "fused filter updates differ from 64 oracle updates"
     conv = np.isin(g_types, (synth.K_CORNER_SEED_CONV, synth.K_EDGELET_SEED_CONV))
     out = {"config": f"{Sq} seeds x {O} ordered observations per GPU ({NSEQ} keyframes x {per} seeds, {NOBS_U} observation frames per keyframe revisited in order, "
-                     f"{NSEQ + NSEQ * NOBS_U} frames in HBM; {NSEQ_U} unique sequences tiled); ONE svo_cuda_update_seeds call = {2 * O + 1} launches (a step + a match kernel per observation wave)",
+                     f"{NSEQ + NSEQ * NOBS_U} frames in HBM; {NSEQ_U} unique sequences tiled); ONE svo_cuda_update_seeds call: a step + a match kernel per observation wave and seed group (4 concurrent groups on the context's side streams; launches counted in gpu_launches)",
            "metric": "seed-observations/s through depth_filter_utils::updateSeed (visibility gate + epipolar match + tau + Vogiatzis update + convergence)",
            "value": rig.world * Sq * O / (ms * 1e-3), "unit": "seed-observations/s", "scaling": "weak", "ms_per_step": ms, "kernel_ms": ms,
            "gpu_launches": int(launches), "success_frac": n_succ / (Sq * O), "converged_frac": float(conv.mean()),
